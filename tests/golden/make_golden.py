@@ -1,0 +1,242 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU
+box):   python tests/golden/make_golden.py
+
+The reference's own modules are imported from /root/reference via sys.path; nothing is
+copied.  Shims, all explicit below:
+  1. ``AutoModel.from_pretrained`` -> random-init ``WavLMModel(WavLMConfig(...))`` (no weights
+     offline); the conv feature-encoder parameters are then overwritten with
+     ``nrse_b200.utils.synthetic.frontend_weights`` so the GPU box can rebuild them from a seed.
+  2. ``AutoFeatureExtractor`` -> ``Wav2Vec2FeatureExtractor(do_normalize=True)`` (wavlm-large's
+     preprocessor settings; only ``do_normalize`` affects the path).
+  3. ``load_and_process_audio`` -> in-memory tensors (torchaudio cannot decode in this image).
+Outputs (float arrays kept small; inputs are stored too so fixtures are self-contained):
+  mix_byol.npz, mix_emotion.npz, mix_edge.npz, byol_loss.npz, ema.npz, frontend_layer.npz,
+  frontend_group.npz
+"""
+import os
+import random
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from nrse_b200.utils import synthetic  # noqa: E402
+
+import transformers  # noqa: E402
+from transformers import Wav2Vec2FeatureExtractor, WavLMConfig, WavLMModel  # noqa: E402
+
+# --- reference modules, unmodified -------------------------------------------------------------
+import src.models.encoder as ref_encoder_mod  # noqa: E402
+import src.data.noisy_speech_dataset as ref_ds_mod  # noqa: E402
+from src.data.augment import add_noise_to_speech as ref_add_noise  # noqa: E402
+from src.models.byol import BYOLSpeechModel as RefBYOL, byol_loss as ref_byol_loss  # noqa: E402
+
+torch.set_num_threads(1)  # single-thread reductions: the most reproducible summation order
+
+
+def small_wavlm_config(norm_mode):
+    """Full-size conv feature encoder (that is the path); tiny transformer (out of scope)."""
+    return WavLMConfig(
+        hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+        feat_extract_norm=norm_mode, do_stable_layer_norm=(norm_mode == "layer"), conv_bias=False,
+        num_conv_pos_embeddings=16, num_conv_pos_embedding_groups=4,
+    )
+
+
+def feature_extractor():
+    return Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0,
+                                    do_normalize=True, return_attention_mask=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_mix_byol(B=6, L=8000, Ln=8000, seed=11, snr_range=(2, 5, 10, 15, 20)):
+    """The real ``NoiseRobustSpeechDataset.__getitem__`` with an in-memory loader."""
+    clean, noise, _, _ = synthetic.waveforms(B, L, seed=seed, n_noise=Ln, snr_range=snr_range)
+    tmp = tempfile.mkdtemp()
+    cdir, ndir = os.path.join(tmp, "clean"), os.path.join(tmp, "noise")
+    os.makedirs(cdir), os.makedirs(ndir)
+    for b in range(B):
+        open(os.path.join(cdir, f"c{b:03d}.wav"), "w").close()
+        open(os.path.join(ndir, f"n{b:03d}.wav"), "w").close()
+    ds = ref_ds_mod.NoiseRobustSpeechDataset(cdir, ndir, sample_rate=16000, max_audio_length=L / 16000,
+                                             snr_range=list(snr_range), feature_extractor=feature_extractor())
+    ds.clean_files.sort(), ds.noise_files.sort()
+    picked = {}
+
+    def loader(path):
+        name = os.path.basename(path)
+        idx = int(name[1:4])
+        if name[0] == "n":
+            picked["noise"] = idx
+            return torch.from_numpy(noise[idx:idx + 1].copy())
+        return torch.from_numpy(clean[idx:idx + 1].copy())
+
+    ds._load_and_process_audio = loader
+    outs_c, outs_n, snrs, nidx = [], [], [], []
+    random.seed(seed)
+    for b in range(B):
+        item = ds[b]
+        outs_c.append(item["clean_input_values"].numpy()[0])
+        outs_n.append(item["noisy_input_values"].numpy()[0])
+        snrs.append(item["snr"])
+        nidx.append(picked["noise"])
+    snr_idx = np.array([snr_range.index(s) for s in snrs], dtype=np.int32)
+    np.savez_compressed(os.path.join(HERE, "mix_byol.npz"),
+                        clean=clean, noise=noise[np.array(nidx)], snr_idx=snr_idx,
+                        snr_table=np.array(snr_range, dtype=np.float64),
+                        clean_out=np.stack(outs_c), noisy_out=np.stack(outs_n))
+    print("mix_byol", np.stack(outs_c).shape, snrs, nidx)
+
+
+def gen_mix_emotion(B=4, L=6000, seed=12, snr_range=(4, 8)):
+    """Emotion fine-tune variant (ref:src/data/emotion_dataset.py:177-203): the reference's
+    ``add_noise_to_speech`` then the HF extractor, no peak-norm; noise shorter than speech (tiled)
+    on rows 0-1 and longer (truncated) on rows 2-3."""
+    fe = feature_extractor()
+    clean, _, snr_idx, _ = synthetic.waveforms(B, L, seed=seed, snr_range=snr_range)
+    noise_short = synthetic.waveforms(B, 2500, seed=seed + 1)[1]
+    noise_long = synthetic.waveforms(B, 7000, seed=seed + 2)[1]
+    outs, noises = [], []
+    for b in range(B):
+        nz = noise_short[b:b + 1] if b < 2 else noise_long[b:b + 1]
+        wav = torch.from_numpy(clean[b:b + 1].copy())
+        noisy = ref_add_noise(wav, torch.from_numpy(nz.copy()), snr_range[int(snr_idx[b])])
+        assert noisy is not None
+        inputs = fe(noisy.squeeze().numpy(), sampling_rate=16000, return_tensors="pt")
+        outs.append(inputs.input_values.squeeze(0).numpy())
+        noises.append(nz[0])
+    np.savez_compressed(os.path.join(HERE, "mix_emotion.npz"), clean=clean,
+                        noise_short=np.stack(noises[:2]), noise_long=np.stack(noises[2:]),
+                        snr_idx=snr_idx, snr_table=np.array(snr_range, dtype=np.float64),
+                        noisy_out=np.stack(outs))
+    print("mix_emotion", np.stack(outs).shape)
+
+
+def gen_mix_edge(L=4000, seed=13):
+    """``None`` exits of the reference's ``add_noise_to_speech`` (ref:src/data/augment.py:7-64)."""
+    clean, noise, _, _ = synthetic.waveforms(8, L, seed=seed)
+    clean[0, 17] = np.nan                      # speech NaN         -> None
+    noise[1, 5] = np.nan                       # noise NaN          -> None
+    clean[2] *= 1e-6                           # speech power<1e-10 -> None
+    noise[3] *= 1e-6                           # noise power<1e-10  -> None
+    noise[4, 9] = np.inf                       # Pn=inf -> scale=0 -> inf*0=NaN -> None
+    clean[5, 3] = np.inf                       # Ps=inf -> scale inf -> None
+    # rows 6,7 are valid
+    is_none = []
+    for b in range(8):
+        r = ref_add_noise(torch.from_numpy(clean[b:b + 1].copy()), torch.from_numpy(noise[b:b + 1].copy()), 10)
+        is_none.append(r is None)
+    np.savez_compressed(os.path.join(HERE, "mix_edge.npz"), clean=clean, noise=noise,
+                        is_none=np.array(is_none))
+    print("mix_edge none:", is_none)
+
+
+def gen_byol_loss(seed=21):
+    cases = {}
+    for name, (B, D) in {"b64": (64, 1024), "b2": (2, 1024), "b5_d96": (5, 96)}.items():
+        p, z = synthetic.embeddings(B, D, seed=seed + B)
+        if name == "b64":
+            z[0] = p[0]            # identical -> sim 1
+            z[1] = -p[1]           # opposite  -> sim -1
+            p[2] = 0.0             # all-zero online row (the +1e-10 path)
+            z[3] = 0.0             # all-zero target row
+        pt = torch.from_numpy(p.copy()).requires_grad_(True)
+        loss = ref_byol_loss(pt, torch.from_numpy(z.copy()))
+        loss.backward()
+        cases[f"{name}_p"], cases[f"{name}_z"] = p, z
+        cases[f"{name}_loss"] = loss.detach().numpy()
+        cases[f"{name}_grad"] = pt.grad.numpy()
+        print("byol_loss", name, float(loss))
+    np.savez_compressed(os.path.join(HERE, "byol_loss.npz"), **cases)
+
+
+def gen_ema(seed=31):
+    """``BYOLSpeechModel._update_target_network`` of the reference on a shimmed (tiny) WavLM."""
+    cfg_small = WavLMConfig(hidden_size=32, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64,
+                            conv_dim=(16,) * 7, num_conv_pos_embeddings=8, num_conv_pos_embedding_groups=2,
+                            feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=False)
+    orig = ref_encoder_mod.AutoModel.from_pretrained
+    ref_encoder_mod.AutoModel.from_pretrained = staticmethod(lambda name: WavLMModel(cfg_small))
+    try:
+        torch.manual_seed(seed)
+        model = RefBYOL({"model": {"name": "shim", "projection_dim": 24, "prediction_dim": 48, "ema_decay": 0.996}})
+    finally:
+        ref_encoder_mod.AutoModel.from_pretrained = orig
+    rs = np.random.RandomState(seed)
+    out = {}
+    with torch.no_grad():
+        for mod in (model.online_encoder, model.online_projector):
+            for p in mod.parameters():
+                p.add_(torch.from_numpy((0.05 * rs.standard_normal(tuple(p.shape))).astype(np.float32)))
+    pairs = list(zip(model.online_encoder.parameters(), model.target_encoder.parameters())) + \
+        list(zip(model.online_projector.parameters(), model.target_projector.parameters()))
+    for i, (o, t) in enumerate(pairs):
+        out[f"o{i}"] = o.detach().numpy().copy()
+        out[f"t{i}"] = t.detach().numpy().copy()
+    for decay in (0.996, 0.997):
+        model.ema_decay = decay
+        for i, (o, t) in enumerate(pairs):       # reset targets
+            t.data = torch.from_numpy(out[f"t{i}"].copy())
+        model._update_target_network()
+        model._update_target_network()            # two consecutive steps
+        for i, (o, t) in enumerate(pairs):
+            out[f"r{int(decay * 1000)}_{i}"] = t.detach().numpy().copy()
+    out["n"] = np.array(len(pairs))
+    np.savez_compressed(os.path.join(HERE, "ema.npz"), **out)
+    print("ema tensors", len(pairs), "elems", sum(o.numel() for o, _ in pairs))
+
+
+def gen_frontend(norm_mode, B=2, L=4000, seed=41):
+    """conv feature encoder through the reference's ``WavLMEncoder`` wrapper object
+    (ref:src/models/encoder.py:6-15): ``encoder.model.feature_extractor``."""
+    cfg = small_wavlm_config(norm_mode)
+    orig = ref_encoder_mod.AutoModel.from_pretrained
+    ref_encoder_mod.AutoModel.from_pretrained = staticmethod(lambda name: WavLMModel(cfg))
+    try:
+        torch.manual_seed(seed)
+        enc = ref_encoder_mod.WavLMEncoder("shim")
+    finally:
+        ref_encoder_mod.AutoModel.from_pretrained = orig
+    enc.eval()
+    layers = synthetic.frontend_weights(norm_mode, seed=seed)
+    with torch.no_grad():
+        for i, layer in enumerate(enc.model.feature_extractor.conv_layers):
+            layer.conv.weight.copy_(torch.from_numpy(layers[i]["conv"]))
+            if layers[i]["gamma"] is not None:
+                layer.layer_norm.weight.copy_(torch.from_numpy(layers[i]["gamma"]))
+                layer.layer_norm.bias.copy_(torch.from_numpy(layers[i]["beta"]))
+    # z-normalised waveform input, as the path feeds it
+    clean, noise, _, _ = synthetic.waveforms(B, L, seed=seed + 1)
+    x = np.stack([(c - c.mean()) / np.sqrt(c.var() + 1e-7) for c in clean]).astype(np.float32)
+    with torch.no_grad():
+        h = torch.from_numpy(x)[:, None]
+        per_layer = []
+        for conv_layer in enc.model.feature_extractor.conv_layers:
+            h = conv_layer(h)
+            per_layer.append(h.numpy().copy())
+        y = enc.model.feature_extractor(torch.from_numpy(x)).numpy()
+    assert np.array_equal(y, per_layer[-1])
+    np.savez_compressed(os.path.join(HERE, f"frontend_{norm_mode}.npz"), x=x, seed=np.array(seed),
+                        y=y, y0=per_layer[0][:, :, :64], y1=per_layer[1][:, :, :64])
+    print("frontend", norm_mode, y.shape, float(np.abs(y).mean()))
+
+
+if __name__ == "__main__":
+    print("transformers", transformers.__version__, "torch", torch.__version__, "numpy", np.__version__)
+    gen_mix_byol()
+    gen_mix_emotion()
+    gen_mix_edge()
+    gen_byol_loss()
+    gen_ema()
+    gen_frontend("layer")
+    gen_frontend("group")
+    print("sizes:", {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")})

@@ -1,0 +1,101 @@
+"""Pin the oracle against fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py)."""
+import numpy as np
+import torch
+
+import oracle
+from nrse_b200.utils import synthetic
+from conftest import rel_err
+
+torch.set_num_threads(1)
+
+
+def test_mix_byol_matches_reference_dataset(golden):
+    g = golden("mix_byol")
+    c, n, st = oracle.mix_normalize_batch(g["clean"], g["noise"], g["snr_idx"], g["snr_table"], peak_norm=True)
+    assert st.tolist() == [0] * len(st)
+    # same ops in the same order on the same thread count -> bit-identical
+    assert np.array_equal(c.numpy(), g["clean_out"])
+    assert np.array_equal(n.numpy(), g["noisy_out"])
+
+
+def test_mix_emotion_matches_reference(golden):
+    g = golden("mix_emotion")
+    for rows, noise in ((slice(0, 2), g["noise_short"]), (slice(2, 4), g["noise_long"])):
+        _, n, st = oracle.mix_normalize_batch(g["clean"][rows], noise, g["snr_idx"][rows], g["snr_table"],
+                                              peak_norm=False)
+        assert st.tolist() == [0, 0]
+        assert np.array_equal(n.numpy(), g["noisy_out"][rows])
+
+
+def test_mix_edge_none_conditions(golden):
+    g = golden("mix_edge")
+    expect = [oracle.mix.STATUS_SPEECH_NAN, oracle.mix.STATUS_NOISE_NAN, oracle.mix.STATUS_SPEECH_POWER,
+              oracle.mix.STATUS_NOISE_POWER, oracle.mix.STATUS_SCALED_NOISE_NAN, oracle.mix.STATUS_SCALE_INVALID, 0, 0]
+    for b in range(8):
+        r = oracle.add_noise_to_speech(torch.from_numpy(g["clean"][b:b + 1]), torch.from_numpy(g["noise"][b:b + 1]), 10)
+        assert (r is None) == bool(g["is_none"][b])
+        _, _, st = oracle.mix_normalize_item(torch.from_numpy(g["clean"][b:b + 1]),
+                                             torch.from_numpy(g["noise"][b:b + 1]), 10)
+        assert st == expect[b]
+
+
+def test_byol_loss_matches_reference(golden):
+    g = golden("byol_loss")
+    for name in ("b64", "b2", "b5_d96"):
+        p = torch.from_numpy(g[f"{name}_p"]).requires_grad_(True)
+        loss = oracle.byol_loss(p, torch.from_numpy(g[f"{name}_z"]))
+        loss.backward()
+        assert np.array_equal(loss.detach().numpy(), g[f"{name}_loss"])
+        assert np.array_equal(p.grad.numpy(), g[f"{name}_grad"])
+
+
+def test_ema_matches_reference(golden):
+    g = golden("ema")
+    n = int(g["n"])
+    online = [torch.from_numpy(g[f"o{i}"]) for i in range(n)]
+    for decay in (0.996, 0.997):
+        target = [torch.from_numpy(g[f"t{i}"]) for i in range(n)]
+        target = oracle.ema_update(online, target, decay)
+        target = oracle.ema_update(online, target, decay)
+        for i in range(n):
+            assert np.array_equal(target[i].numpy(), g[f"r{int(decay * 1000)}_{i}"])
+
+
+def test_frontend_matches_reference(golden):
+    for mode in ("layer", "group"):
+        g = golden(f"frontend_{mode}")
+        layers = synthetic.frontend_weights(mode, seed=int(g["seed"]))
+        outs = oracle.conv_frontend(torch.from_numpy(g["x"]), layers, mode, return_all=True)
+        assert list(outs[-1].shape) == list(g["y"].shape)
+        assert rel_err(outs[-1].numpy(), g["y"]) < 1e-6
+        assert rel_err(outs[0].numpy()[:, :, :64], g["y0"]) < 1e-6
+        assert rel_err(outs[1].numpy()[:, :, :64], g["y1"]) < 1e-6
+
+
+def test_frontend_matches_installed_transformers():
+    """The restatement vs the third-party classes themselves (present on the GPU box as well)."""
+    from transformers import WavLMConfig
+    from transformers.models.wavlm.modeling_wavlm import WavLMFeatureEncoder
+
+    for mode in ("layer", "group"):
+        layers = synthetic.frontend_weights(mode, seed=3)
+        fe = WavLMFeatureEncoder(WavLMConfig(feat_extract_norm=mode, conv_bias=False)).eval()
+        with torch.no_grad():
+            for i, cl in enumerate(fe.conv_layers):
+                cl.conv.weight.copy_(torch.from_numpy(layers[i]["conv"]))
+                if layers[i]["gamma"] is not None:
+                    cl.layer_norm.weight.copy_(torch.from_numpy(layers[i]["gamma"]))
+                    cl.layer_norm.bias.copy_(torch.from_numpy(layers[i]["beta"]))
+            x = torch.from_numpy(synthetic.waveforms(2, 2000, seed=5)[0]) * 10
+            ref = fe(x)
+        got = oracle.conv_frontend(x, layers, mode)
+        assert rel_err(got.numpy(), ref.numpy()) < 1e-6
+        assert got.shape[-1] == synthetic.conv_out_lengths(2000)[-1] == oracle.conv_out_lengths(2000)[-1]
+
+
+def test_synthetic_is_deterministic():
+    a = synthetic.waveforms(3, 1000, seed=9)
+    b = synthetic.waveforms(3, 1000, seed=9)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert synthetic.conv_out_lengths(64000) == [12799, 6399, 3199, 1599, 799, 399, 199]
