@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 BYOL noisy-view hot path (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One step = one pass of the hot path over one synthetic batch per GPU (64 utterances x 4 s @ 16 kHz):
+fused SNR mix + peak-norm + z-norm of the clean/noisy views, then the WavLM-large conv feature encoder
+forward on BOTH views (online = clean, target = noisy).  Metric: utterance-seconds per second, whole job.
+`value` is timed with the inputs resident in HBM; `e2e` goes through the public module API with pinned HOST
+buffers (H2D of the raw waveforms and D2H of the result inside the timed region).  `roofline` is measured live
+with CUDA events around the dominant kernel (the tcgen05 implicit-GEMM conv layers); `cpu_baseline` times the
+oracle (a CPU port of the reference path) on a bounded sample on rank 0.  `--impl reference` runs only that CPU
+path and prints the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BATCH = 64
+N_SAMPLES = 64000
+SAMPLE_RATE = 16000
+UTT_SEC_PER_STEP = BATCH * N_SAMPLES / SAMPLE_RATE  # 256 utterance-seconds per GPU per step
+METRIC = "utterance-sec/sec, BYOL noisy-view step (SNR mix + WavLM-large conv frontend fwd, both views)"
+UNIT = "utterance-seconds/s"
+CONV_KERNEL = (10, 3, 3, 3, 3, 2, 2)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = f"/tmp/nrse_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.out, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.out.close()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (CPU port of the reference path) on a bounded sample
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(sample_utts: int, clean, noise, snr_idx, snr_table, layers):
+    """One bounded-sample step of the SAME workload on the host cores: mix+normalise `sample_utts` utterances the
+    way the reference's DataLoader worker does, then the fp32 conv feature encoder on both views."""
+    import oracle
+    t0 = time.perf_counter()
+    c, n, st = oracle.mix_normalize_batch(clean[:sample_utts], noise[:sample_utts], snr_idx[:sample_utts], snr_table,
+                                          peak_norm=True)
+    with torch.no_grad():
+        y_c = oracle.conv_frontend(c, layers, "layer")
+        y_n = oracle.conv_frontend(n, layers, "layer")
+    dt = time.perf_counter() - t0
+    return dt, float(y_c.abs().mean() + y_n.abs().mean())
+
+
+def run_cpu(sample_utts: int, steps: int, warmup: int):
+    from nrse_b200.utils import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    clean, noise, snr_idx, snr_table = synthetic.waveforms(sample_utts, N_SAMPLES, seed=1234)
+    layers = synthetic.frontend_weights("layer", seed=0)
+    for _ in range(warmup):
+        cpu_reference_step(sample_utts, clean, noise, snr_idx, snr_table, layers)
+    times = [cpu_reference_step(sample_utts, clean, noise, snr_idx, snr_table, layers)[0] for _ in range(steps)]
+    dt = sum(times) / len(times)
+    value = sample_utts * N_SAMPLES / SAMPLE_RATE / dt
+    return value, dt, cores, torch.get_num_threads()
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample = 4
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 1))
+    value, dt, cores, threads = run_cpu(sample, steps, warmup)
+    sample_txt = (f"{sample} of {BATCH} utterances x 4 s per step (mix+normalise per utterance, fp32 conv frontend on both "
+                  f"views), oracle port of the reference path, torch {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: SNR mix + WavLM-large conv frontend fwd, batch 64 x 4 s 16 kHz (bounded CPU sample)",
+                   "batch_per_gpu": BATCH, "n_samples": N_SAMPLES, "views": 2},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+def main_gpu(args):
+    import torch.distributed as dist
+
+    from nrse_b200 import ops
+    from nrse_b200.utils import synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = measured_peaks()
+
+    # ---- synthetic inputs and WavLM-large-shaped frontend weights (random init: no checkpoints offline) ----------
+    clean_np, noise_np, snr_idx_np, snr_table = synthetic.waveforms(BATCH, N_SAMPLES, seed=1234 + rank)
+    layers = synthetic.frontend_weights("layer", seed=0)
+    clean_h = torch.from_numpy(clean_np).pin_memory()
+    noise_h = torch.from_numpy(noise_np).pin_memory()
+    snr_h = torch.from_numpy(snr_idx_np).pin_memory()
+    clean_d, noise_d, snr_d = clean_h.to(dev), noise_h.to(dev), snr_h.to(dev)
+    snr_list = [float(v) for v in snr_table]
+    conv_w = [torch.from_numpy(l["conv"]).to(dev) for l in layers]
+    gammas = [torch.from_numpy(l["gamma"]).to(dev) for l in layers]
+    betas = [torch.from_numpy(l["beta"]).to(dev) for l in layers]
+    packed = [ops.pack_conv_weight(w) for w in conv_w[1:]]
+    T, P = ops.frontend_geometry(N_SAMPLES)
+
+    def hot_path(clean, noise, snr):
+        c, n, st = ops.mix_normalize(clean, noise, snr, snr_list, peak_norm=True)
+        y_online = ops.conv_frontend(c, conv_w, gammas, betas, "layer", out_dtype=torch.bfloat16, packed=packed)
+        y_target = ops.conv_frontend(n, conv_w, gammas, betas, "layer", out_dtype=torch.bfloat16, packed=packed)
+        return y_online, y_target, st
+
+    launches_per_step = 1 + 2 * 7  # mix + 2 views x (layer0 + 6 tcgen05 GEMM layers)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    # ---- value: inputs resident in HBM ----------------------------------------------------------------------------
+    step_dev = lambda: hot_path(clean_d, noise_d, snr_d)
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total, out = timed(step_dev, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    assert int(out[2].abs().sum().item()) == 0, "synthetic batch produced rejected rows"
+    ms_per_step = ms_total / args.steps
+    value = world * UTT_SEC_PER_STEP / (ms_per_step * 1e-3)
+
+    # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region ---------------------------------
+    pooled_h = torch.empty(2, BATCH, 512, dtype=torch.float32).pin_memory()
+    status_h = torch.empty(BATCH, dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        c = clean_h.to(dev, non_blocking=True)
+        n = noise_h.to(dev, non_blocking=True)
+        s = snr_h.to(dev, non_blocking=True)
+        y_o, y_t, st = hot_path(c, n, s)
+        pooled_h[0].copy_(y_o.float().mean(dim=1), non_blocking=True)  # the [B,H]-pooled result the BYOL heads consume
+        pooled_h[1].copy_(y_t.float().mean(dim=1), non_blocking=True)
+        status_h.copy_(st, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result every step
+        return y_o, y_t, st
+
+    for _ in range(3):
+        step_e2e()
+    ms_e2e_total, _ = timed(step_e2e, args.steps)
+    e2e_value = world * UTT_SEC_PER_STEP / (ms_e2e_total / args.steps * 1e-3)
+    h2d = clean_h.numel() * 4 + noise_h.numel() * 4 + snr_h.numel() * 4
+    d2h = pooled_h.numel() * 4 + status_h.numel() * 4
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 (conv operands/activations, fp32 accumulate + fp32 LayerNorm/GELU); f32 (mix)",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: SNR mix + WavLM-large conv frontend fwd, batch 64 x 4 s 16 kHz per GPU, "
+                               "both BYOL views (clean->online, noisy->target)",
+                   "batch_per_gpu": BATCH, "n_samples": N_SAMPLES, "views": 2, "norm": "layer",
+                   "weights": "random init, WavLM-large conv shapes", "parallelism": f"dp{world} (no data-path collective)",
+                   "l2": "per-step working set 3.4 GB >> 126 MB L2: inputs are evicted between timed iterations"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e_total / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+
+    # ---- per-kernel rooflines (rank 0 only, outside the headline timing) -------------------------------------------
+    if rank == 0:
+        line.update(kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w, gammas, betas, packed,
+                                     T, P, max(3, min(args.steps, 10))))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cv, cdt, cores, threads = run_cpu(4, 3, 1)
+        line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"4 of {BATCH} utterances x 4 s per step, 3 steps after 1 warm-up: oracle "
+                                          f"(CPU port of the reference path: per-utterance mix+normalise, fp32 conv "
+                                          f"frontend on both views), torch {threads} threads on {cores} host cores"}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w, gammas, betas, packed, T, P, reps):
+    """CUDA-event timing of each hot-path kernel on its own launch stream; algorithmic work from SURVEY.md 8(d)."""
+    def ev_time(fn, n=reps, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n  # ms per call
+
+    B, L = clean_d.shape
+    # the conv GEMM layers: run layer by layer on real activations so every launch can be bracketed by events
+    c, n, _ = ops.mix_normalize(clean_d, noise_d, snr_d, snr_list, True)
+    act = ops.conv_layer0(c, conv_w[0], gammas[0], betas[0], "layer").view(B * P[0], 512)
+    t_l0 = ev_time(lambda: ops.conv_layer0(c, conv_w[0], gammas[0], betas[0], "layer"))
+    gemm_ms, gemm_flops, per_layer = 0.0, 0.0, []
+    for i in range(1, 7):
+        k = CONV_KERNEL[i]
+        inp = act
+        t = ev_time(lambda: ops.conv_layer(inp, packed[i - 1], k, gammas[i], betas[i]))
+        act = ops.conv_layer(inp, packed[i - 1], k, gammas[i], betas[i])
+        flops = 2.0 * B * T[i] * 512 * (512 * k)  # algorithmic: valid frames only
+        gemm_ms += t
+        gemm_flops += flops
+        per_layer.append({"layer": i, "ms": t, "tflops": flops / (t * 1e-3) / 1e12})
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (layers 1-6, tcgen05 implicit GEMM + LayerNorm + GELU)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed back to back)",
+                "launches": 6, "ms_per_view": gemm_ms, "algorithmic_flops_per_view": gemm_flops, "per_layer": per_layer}
+
+    hbm = peaks["hbm_gbs"]
+    kernels = []
+    t_mix = ev_time(lambda: ops.mix_normalize(clean_d, noise_d, snr_d, snr_list, True))
+    kernels.append({"kernel": "mix_normalize (B=64, L2-resident working set)", "bound": "hbm", "ms": t_mix,
+                    "achieved": 16.0 * B * L / (t_mix * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s"})
+    big = 512
+    cb = clean_d.repeat(big // B, 1).contiguous(); nb = noise_d.repeat(big // B, 1).contiguous(); sb = snr_d.repeat(big // B)
+    t_mix_big = ev_time(lambda: ops.mix_normalize(cb, nb, sb, snr_list, True))
+    kernels.append({"kernel": "mix_normalize (B=512, 524 MB > L2)", "bound": "hbm", "ms": t_mix_big,
+                    "achieved": 16.0 * big * L / (t_mix_big * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s"})
+    del cb, nb
+    kernels.append({"kernel": "layer0_kernel (conv k=10 + LayerNorm + GELU, bf16 out)", "bound": "hbm", "ms": t_l0,
+                    "achieved": (4.0 * B * L + 2.0 * 512 * B * T[0]) / (t_l0 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s"})
+    # EMA over the WavLM-large encoder + projector parameter sizes (317,556,416 fp32 values, 12 B each)
+    sizes = [8] * 24 + [16] * 24 + [128] + [512] * 40 + [1024] * 227 + [4096] * 24 + [5120] * 2 + [524288] * 3 + \
+            [786432] * 4 + [1048576] * 98 + [4194304] * 48 + [8388608]
+    online = [torch.randn(s, device=dev) for s in sizes]
+    target = [torch.randn(s, device=dev) for s in sizes]
+    plan = ops.EmaPlan(online, target)
+    t_ema = ev_time(lambda: plan.step(0.996))
+    kernels.append({"kernel": "ema_chunks_kernel (317.6 M params, 496 tensors, 1 launch)", "bound": "hbm", "ms": t_ema,
+                    "achieved": 12.0 * plan.numel / (t_ema * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s"})
+    del online, target, plan
+    p = torch.randn(B, 1024, device=dev, requires_grad=True)
+    z = torch.randn(B, 1024, device=dev)
+    t_loss = ev_time(lambda: ops.byol_loss(p, z))
+    kernels.append({"kernel": "byol_loss_fwd (64x1024 fp32, 1 launch, 0 syncs)", "bound": "hbm", "ms": t_loss,
+                    "achieved": 8.0 * B * 1024 / (t_loss * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s"})
+    for kk in kernels:
+        kk["frac"] = kk["achieved"] / kk["peak"]
+    return {"roofline": roofline, "kernels": kernels}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,167 @@
+/*
+ * nrse_b200.h -- C ABI of the B200-native BYOL noisy-view hot path.
+ *
+ * The reference (sunYtokki/Noise-Robust-Speech-Embedding) is pure Python and has no FFI;
+ * its boundary for this path is the Python module surface.  Each entry point
+ * below replaces the body of one reference function; the host-side Python mirror in
+ * noise-robust-speech-embedding_b200/ binds these with ctypes (INTEGRATION.md shows the stub
+ * a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every function returns 0 (NRSE_OK) or a negative nrse_status; nothing throws;
+ *   - pointers are DEVICE pointers owned by the caller unless the name ends in _host;
+ *   - no entry point allocates device memory or synchronises the stream;
+ *   - `stream` is a cudaStream_t (CUstream), e.g. torch.cuda.current_stream().cuda_stream;
+ *   - re-entrant per stream; the only global state is the lazily resolved driver entry point for TMA
+ *     descriptor encoding, one-time kernel attributes and the tuning knob nrse_conv_frontend_set_variant.
+ *   - sm_100a only.  There is no CPU or other-arch fallback.
+ */
+#ifndef NRSE_B200_H_
+#define NRSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* nrse_stream_t;
+
+typedef enum {
+  NRSE_OK = 0,
+  NRSE_ERR_INVALID_ARG = -1,
+  NRSE_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels implement */
+  NRSE_ERR_CUDA = -3,         /* a CUDA runtime/driver call failed: see nrse_last_cuda_error() */
+  NRSE_ERR_WORKSPACE = -4,    /* caller-provided workspace too small */
+  NRSE_ERR_NO_DEVICE = -5     /* not an sm_100 device */
+} nrse_status;
+
+#define NRSE_DTYPE_F32 0
+#define NRSE_DTYPE_BF16 1
+
+#define NRSE_NORM_LAYER 0 /* wavlm-large: LayerNorm over channels on every conv layer */
+#define NRSE_NORM_GROUP 1 /* wavlm-base(-plus): GroupNorm(512,512) on layer 0 only     */
+
+#define NRSE_FRONTEND_LAYERS 7
+#define NRSE_FRONTEND_CHANNELS 512
+
+int nrse_version(void);
+const char* nrse_strerror(int status);
+/* cudaError_t (as int) of the last failing CUDA call made by this library on the calling thread. */
+int nrse_last_cuda_error(void);
+/* 0 if the current device is compute capability 10.x, else NRSE_ERR_NO_DEVICE / NRSE_ERR_CUDA. */
+int nrse_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused SNR mix + peak normalisation + z-normalisation.
+ * Replaces, per utterance row b:
+ *   add_noise_to_speech          ref:src/data/augment.py:4-66
+ *   peak normalisation           ref:src/data/noisy_speech_dataset.py:88-116      (peak_norm=1)
+ *   HF zero_mean_unit_var_norm   hf:models/wav2vec2/feature_extraction_wav2vec2.py:95,
+ *                                called at ref:src/data/noisy_speech_dataset.py:120-129 and
+ *                                ref:src/data/emotion_dataset.py:198-203
+ * peak_norm=1 (BYOL pre-training): clean_out and noisy_out are both written.
+ * peak_norm=0 (emotion fine-tune, ref:src/data/emotion_dataset.py:177-203): only noisy_out is
+ *   written (clean_out may be NULL); a failed mix keeps the clean waveform (:193-194).
+ * clean [B,L], noise [B,L_noise] (truncated if longer, tiled if shorter, augment.py:16-21),
+ * snr_idx [B] indexes snr_db_table_host[n_snr] (dB; HOST pointer, n_snr <= 32).
+ * status[b] = 0 or the number of the reference's `return None`/`continue` exit that row b would
+ *   have taken (1..14, see nrse_mix_status_name); in BYOL mode such rows are zero-filled.
+ * ------------------------------------------------------------------------------------------- */
+int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t* snr_idx,
+                           const double* snr_db_table_host, int n_snr,
+                           float* clean_out, float* noisy_out, int32_t* status,
+                           int B, int L, int L_noise, int peak_norm, nrse_stream_t stream);
+const char* nrse_mix_status_name(int status_code);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-tensor EMA:  target = decay*target + one_minus_decay*online   (fp32, in place,
+ * rounding identical to the reference expression: two products, one sum, no FMA).
+ * Replaces BYOLSpeechModel._update_target_network, ref:src/models/byol.py:62-73.
+ *
+ * The launch works on a chunk table built once per model:
+ *   nrse_ema_plan_chunks_host splits n_tensors tensors (host arrays of device pointers and element
+ *   counts) into chunks of at most chunk_elems elements; it returns the number of chunks and, when
+ *   the output arrays are non-NULL (capacity max_chunks), fills them.  Copy the three arrays to the
+ *   device and pass them to nrse_ema_chunks_f32.
+ * ------------------------------------------------------------------------------------------- */
+int64_t nrse_ema_plan_chunks_host(const uint64_t* target_ptrs_host, const uint64_t* online_ptrs_host,
+                                  const int64_t* numel_host, int n_tensors, int64_t chunk_elems,
+                                  uint64_t* chunk_target_host, uint64_t* chunk_online_host,
+                                  int32_t* chunk_numel_host, int64_t max_chunks);
+int nrse_ema_chunks_f32(const uint64_t* chunk_target, const uint64_t* chunk_online,
+                        const int32_t* chunk_numel, int64_t n_chunks,
+                        float decay, float one_minus_decay, nrse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BYOL loss with fused +1e-10, L2 normalisation (eps 1e-10), row dot product, clamp and mean.
+ * Replaces byol_loss, ref:src/models/byol.py:104-129.  One launch, no host sync.
+ *   p, z   [B,D] row-major, dtype NRSE_DTYPE_F32 or NRSE_DTYPE_BF16 (D % 4 == 0 for f32, % 8 for bf16)
+ *   loss   [1] fp32 = 2 - 2*mean_b clamp(<p^,z^>, -1, 1)
+ *   saved  [B,4] fp32 = (||p+1e-10||, ||z+1e-10||, unclamped similarity, 0) for the backward
+ *   row_sim (nullable) [B] fp32 clamped similarities (evaluate_byol.py:55 uses these per row)
+ * Backward w.r.t. p only (the target branch is under no_grad, ref:src/models/byol.py:94-96).
+ * ------------------------------------------------------------------------------------------- */
+int nrse_byol_loss_fwd(const void* p, const void* z, float* loss, float* saved, float* row_sim,
+                       int B, int D, int dtype, nrse_stream_t stream);
+int nrse_byol_loss_bwd(const void* p, const void* z, const float* saved, const float* grad_loss,
+                       void* grad_p, int B, int D, int dtype, nrse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * WavLM convolutional feature encoder, forward.
+ * Replaces WavLMFeatureEncoder.forward, hf:models/wavlm/modeling_wavlm.py:779-789 (reached from
+ * ref:src/models/encoder.py:25): 7 x { Conv1d(bias=False) ; LayerNorm over C | GroupNorm | none ;
+ * exact GELU }, k=(10,3,3,3,3,2,2), s=(5,2,2,2,2,2,2), C=512.
+ *
+ * Activations are channels-last [B, P_i, 512] bf16 with a per-utterance frame pitch P_i >= T_i chosen
+ * so that P_{i-1} = s_i * P_i (nrse_conv_frontend_geometry); then output frame m = b*P_i + t of layer i
+ * reads the contiguous window x[(s_i*m) .. (s_i*m + k_i)) * 512 of layer i-1, and the conv is one
+ * implicit GEMM [B*P_i, k_i*512] x [k_i*512, 512] with no im2col.
+ *
+ *   x          [B,L] fp32 waveform (already z-normalised)
+ *   w0         [512,10] fp32   (= conv_layers.0.conv.weight [512,1,10])
+ *   w_packed   6 device pointers, layer i=1..6: bf16 [512, k_i*512] with K index = tap*512 + c_in
+ *              (nrse_conv_frontend_pack_weights converts from the checkpoint layout [512,512,k] fp32)
+ *   gamma/beta 7 device pointers [512] fp32; NULL where the layer has no norm (group mode, i >= 1)
+ *   y          [B, P_6, 512] y_dtype (bf16 or f32); frames t >= T_6 of each utterance are padding
+ *   workspace  nrse_conv_frontend_workspace_bytes(B, L) bytes, 1024-byte aligned
+ *   acts_out   nullable array of 6 HOST-visible slots receiving the device addresses (inside the
+ *              workspace) of the layer 0..5 outputs, for the backward / debugging
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* w0;
+  const void* w_packed[NRSE_FRONTEND_LAYERS - 1];
+  const float* gamma[NRSE_FRONTEND_LAYERS];
+  const float* beta[NRSE_FRONTEND_LAYERS];
+} nrse_frontend_params;
+
+/* T[i], P[i] for i = 0..6.  Returns NRSE_ERR_INVALID_ARG if L < 400 (empty output). */
+int nrse_conv_frontend_geometry(int L, int32_t* T_out_host, int32_t* P_out_host);
+size_t nrse_conv_frontend_workspace_bytes(int B, int L);
+/* w [512,512,k] fp32 (checkpoint layout) -> packed bf16 [512, k*512] */
+int nrse_conv_frontend_pack_weights(const float* w, void* w_packed, int k, nrse_stream_t stream);
+int nrse_conv_frontend_fwd(const float* x, const nrse_frontend_params* params_host, int norm_mode,
+                           void* y, int y_dtype, void* workspace, size_t workspace_bytes,
+                           uint64_t* acts_out_host, int B, int L, nrse_stream_t stream);
+
+/* The two building blocks of nrse_conv_frontend_fwd, exported for per-layer parity tests and for callers
+ * that keep their own activation buffers.
+ *   layer 0 (WavLMLayerNormConvLayer / WavLMGroupNormConvLayer with C_in = 1, hf:...modeling_wavlm.py:703-751):
+ *     x [B,L] fp32 -> out [B*P0, 512] bf16 (frames t >= T0 zero-filled).  norm_mode LAYER: gamma/beta [512];
+ *     GROUP: gamma/beta [512] and gn_scratch = the tail of the frontend workspace (statistics over time).
+ *   layers 1..6 (stride 2, k = 3 or 2): act_prev [rows_prev = 2*rows_out, 512] bf16 -> out [rows_out, 512]
+ *     (bf16 or f32); gamma/beta NULL = no normalisation (WavLMNoLayerNormConvLayer, :682-700). */
+int nrse_conv_layer0_fwd(const float* x, const float* w0, const float* gamma, const float* beta, int norm_mode,
+                         void* out, void* gn_scratch, int B, int L, int T0, int P0, nrse_stream_t stream);
+int nrse_conv_layer_fwd(const void* act_prev, int64_t rows_prev, const void* w_packed, int k, int stride,
+                        const float* gamma, const float* beta, void* out, int out_dtype, int64_t rows_out,
+                        nrse_stream_t stream);
+/* Tile decomposition of the tcgen05 kernel: 1 = one CTA owns all 512 channels of a 128-frame tile,
+ * 2 = a 2-CTA cluster splits the channels and exchanges LayerNorm partials through DSMEM (default). */
+int nrse_conv_frontend_set_variant(int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRSE_B200_H_ */

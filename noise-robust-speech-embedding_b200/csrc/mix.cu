@@ -1,0 +1,368 @@
+// Fused SNR mix + peak normalisation + z-normalisation (fp32, HBM-bound).
+//
+// One thread-block CLUSTER per utterance row.  The reference does this per utterance on a DataLoader
+// worker with ~20 tensor ops and three dependent full-row reductions:
+//   add_noise_to_speech          ref:src/data/augment.py:4-66
+//   peak normalisation           ref:src/data/noisy_speech_dataset.py:88-116
+//   zero_mean_unit_var_norm      hf:models/wav2vec2/feature_extraction_wav2vec2.py:95
+// Here the row is streamed from HBM once (pass 1: powers, sums, cross term, peaks), re-read from L2 for
+// the peak of the mixed signal (pass 2, BYOL mode only) and for the output pass.  Every later statistic
+// (mean / variance of both normalised views) is derived algebraically from the pass-1 sums, so the three
+// dependent reductions of the reference cost one HBM read.  Partial sums are combined across the CTAs of
+// the cluster through distributed shared memory; there is no workspace and no atomics, and the result is
+// deterministic.  Algorithmic traffic: 16 B per sample (BYOL mode), 12 B (emotion mode).
+#include <cooperative_groups.h>
+
+#include <cmath>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace nrse {
+namespace {
+
+constexpr int kMixThreads = 512;
+constexpr int kMixWarps = kMixThreads / 32;
+constexpr int kMixCluster = 4;  // CTAs per utterance row
+constexpr int kMaxSnr = 32;
+
+struct MixParams {
+  const float* clean;
+  const float* noise;
+  const int32_t* snr_idx;
+  float* clean_out;
+  float* noisy_out;
+  int32_t* status;
+  int B, L, Ln, peak_norm, n_snr;
+  float snr_lin[kMaxSnr];  // float(10 ** (snr_db / 10)), ref:src/data/augment.py:39
+};
+
+// 4 consecutive samples of the clean row and of the length-matched noise row (augment.py:16-21:
+// truncate if longer, tile if shorter).  Samples at index >= L read as 0 and contribute nothing.
+template <bool kVec>
+__device__ __forceinline__ void load4(const float* __restrict__ c_row, const float* __restrict__ n_row,
+                                      int L, int Ln, int v, float (&c)[4], float (&n)[4]) {
+  if constexpr (kVec) {
+    const float4 cv = ld_stream_f4(reinterpret_cast<const float4*>(c_row) + v);
+    const float4 nv = ld_stream_f4(reinterpret_cast<const float4*>(n_row) + v);
+    c[0] = cv.x; c[1] = cv.y; c[2] = cv.z; c[3] = cv.w;
+    n[0] = nv.x; n[1] = nv.y; n[2] = nv.z; n[3] = nv.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = 4 * v + j;
+      const bool in = i < L;
+      c[j] = in ? __ldg(c_row + i) : 0.f;
+      n[j] = in ? __ldg(n_row + (Ln >= L ? i : i % Ln)) : 0.f;
+    }
+  }
+}
+
+template <bool kVec>
+__device__ __forceinline__ void store4(float* __restrict__ row, int L, int v, const float (&o)[4]) {
+  if constexpr (kVec) {
+    reinterpret_cast<float4*>(row)[v] = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * v + j < L) row[4 * v + j] = o[j];
+  }
+}
+
+// Block-wide sum of kN doubles; result valid in every thread.  `scratch` holds kMixWarps*kN doubles.
+template <int kN>
+__device__ __forceinline__ void block_sum(double (&v)[kN], double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kN; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();  // scratch may still be read from a previous call
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kN; ++k) scratch[warp * kN + k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kN; ++k) {
+    double s = 0.0;
+    for (int w = 0; w < kMixWarps; ++w) s += scratch[w * kN + k];  // fixed order: deterministic
+    v[k] = s;
+  }
+}
+
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float m = scratch[0];
+  for (int w = 1; w < kMixWarps; ++w) m = fmaxf(m, scratch[w]);
+  return m;
+}
+
+// fmaxf drops NaNs, which is what we want for peaks: rows containing NaN are rejected through the sums.
+__device__ __forceinline__ float absmax4(float m, const float (&x)[4]) {
+  return fmaxf(fmaxf(m, fmaxf(fabsf(x[0]), fabsf(x[1]))), fmaxf(fabsf(x[2]), fabsf(x[3])));
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kMixThreads) mix_normalize_kernel(const MixParams p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int row = blockIdx.x / kMixCluster;
+  const int tid = threadIdx.x;
+
+  __shared__ double red_d[kMixWarps * 5];
+  __shared__ float red_f[kMixWarps];
+  __shared__ double xch1_d[kMixCluster][5];
+  __shared__ float xch1_f[kMixCluster][2];
+  __shared__ float xch2_f[kMixCluster];
+  __shared__ unsigned xch2_u[kMixCluster];
+
+  const int L = p.L, Ln = p.Ln;
+  const float* c_row = p.clean + static_cast<size_t>(row) * L;
+  const float* n_row = p.noise + static_cast<size_t>(row) * Ln;
+  const int nvec = (L + 3) / 4;
+  const int seg = (nvec + kMixCluster - 1) / kMixCluster;
+  const int v_begin = rank * seg;
+  const int v_end = min(nvec, v_begin + seg);
+
+  // ---- pass 1 (HBM): sum c^2, n^2, c, n, c*n; max|c|, max|n| -------------------------------------
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  float cmax = 0.f, nmax_in = 0.f;
+  for (int v0 = v_begin + tid; v0 < v_end; v0 += 2 * kMixThreads) {
+    float c[2][4], n[2][4];
+    const int v1 = v0 + kMixThreads;
+    load4<kVec>(c_row, n_row, L, Ln, v0, c[0], n[0]);
+    if (v1 < v_end) {
+      load4<kVec>(c_row, n_row, L, Ln, v1, c[1], n[1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[1][j] = n[1][j] = 0.f;
+    }
+    // 8 samples are summed in fp32, then folded into the fp64 running sums (keeps F2F/DADD traffic low
+    // while the long accumulation stays in double: no cancellation trouble in var = E[x^2] - mean^2).
+    float f[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f[0] = fmaf(c[u][j], c[u][j], f[0]);
+        f[1] = fmaf(n[u][j], n[u][j], f[1]);
+        f[2] += c[u][j];
+        f[3] += n[u][j];
+        f[4] = fmaf(c[u][j], n[u][j], f[4]);
+      }
+      cmax = absmax4(cmax, c[u]);
+      nmax_in = absmax4(nmax_in, n[u]);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[k] += static_cast<double>(f[k]);
+  }
+  block_sum<5>(acc, red_d);
+  cmax = block_max(cmax, red_f);
+  nmax_in = block_max(nmax_in, red_f);
+
+  // all-to-all inside the cluster through distributed shared memory
+  if (tid < kMixCluster) {
+    double* dst_d = cluster.map_shared_rank(&xch1_d[rank][0], tid);
+    float* dst_f = cluster.map_shared_rank(&xch1_f[rank][0], tid);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) dst_d[k] = acc[k];
+    dst_f[0] = cmax;
+    dst_f[1] = nmax_in;
+  }
+  cluster.sync();
+  double s_cc = 0.0, s_nn = 0.0, s_c = 0.0, s_n = 0.0, s_cn = 0.0;
+  cmax = 0.f;
+  nmax_in = 0.f;
+#pragma unroll
+  for (int r = 0; r < kMixCluster; ++r) {
+    s_cc += xch1_d[r][0];
+    s_nn += xch1_d[r][1];
+    s_c += xch1_d[r][2];
+    s_n += xch1_d[r][3];
+    s_cn += xch1_d[r][4];
+    cmax = fmaxf(cmax, xch1_f[r][0]);
+    nmax_in = fmaxf(nmax_in, xch1_f[r][1]);
+  }
+
+  // ---- add_noise_to_speech decisions (augment.py:7-51), evaluated identically by every thread ----
+  const double Ld = static_cast<double>(L);
+  const float Ps = static_cast<float>(s_cc / Ld);  // torch.mean(speech ** 2)
+  const float Pn = static_cast<float>(s_nn / Ld);
+  int idx = p.snr_idx[row];
+  idx = idx < 0 ? 0 : (idx >= p.n_snr ? p.n_snr - 1 : idx);
+  const float scale = __fsqrt_rn(__fdiv_rn(Ps, __fmul_rn(Pn, p.snr_lin[idx])));  // augment.py:40, fp32
+  int st = 0;
+  if (isnan(Ps)) st = 1;                         // isnan(speech).any()
+  else if (isnan(Pn)) st = 2;                    // isnan(noise).any()
+  else if (Ps < 1e-10f) st = 3;
+  else if (Pn < 1e-10f) st = 4;
+  else if (isinf(scale) || isnan(scale)) st = 5;
+  else if (scale > 1e6f) st = 6;
+  else if (isinf(nmax_in)) st = 7;               // inf * 0 -> NaN in noise * scale (augment.py:56)
+
+  float nmax = 0.f;
+  if (p.peak_norm && st == 0) {
+    // ---- pass 2 (L2): peak of the mixed signal, NaN flags of augment.py:56-64 ---------------------
+    unsigned flags = 0;
+    for (int v0 = v_begin + tid; v0 < v_end; v0 += kMixThreads) {
+      float c[4], n[4], y[4];
+      load4<kVec>(c_row, n_row, L, Ln, v0, c, n);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float sn = __fmul_rn(n[j], scale);
+        y[j] = __fadd_rn(c[j], sn);
+        flags |= (isnan(sn) ? 1u : 0u) | (isnan(y[j]) ? 2u : 0u);
+      }
+      nmax = absmax4(nmax, y);
+    }
+    nmax = block_max(nmax, red_f);
+    flags = __syncthreads_or(static_cast<int>(flags));
+    if (tid < kMixCluster) {
+      *cluster.map_shared_rank(&xch2_f[rank], tid) = nmax;
+      *cluster.map_shared_rank(&xch2_u[rank], tid) = flags;
+    }
+    cluster.sync();
+    nmax = 0.f;
+    flags = 0;
+#pragma unroll
+    for (int r = 0; r < kMixCluster; ++r) {
+      nmax = fmaxf(nmax, xch2_f[r]);
+      flags |= xch2_u[r];
+    }
+    if (flags & 1u) st = 7;
+    else if (flags & 2u) st = 8;
+    else if (cmax < 1e-8f) st = 9;               // noisy_speech_dataset.py:95
+    else if (nmax < 1e-8f) st = 10;              // :99
+    else if (isinf(cmax)) st = 11;               // inf / inf -> NaN after the peak division (:107)
+    else if (isinf(nmax)) st = 12;               // (:111)
+  }
+
+  // ---- statistics of the normalised views, from the pass-1 sums -----------------------------------
+  // clean view : x = c / dc             noisy view : x = (c + s n) / dn
+  const double s = static_cast<double>(scale);
+  float a_c = 0.f, b_c = 0.f, a_n = 0.f, b_n = 0.f, inv_dc = 1.f, inv_dn = 1.f;
+  bool mixed = (st == 0);
+  if (p.peak_norm) {
+    if (st == 0) {
+      const double dc = static_cast<double>(__fadd_rn(cmax, 1e-8f));
+      const double dn = static_cast<double>(__fadd_rn(nmax, 1e-8f));
+      const double mc = s_c / Ld / dc;
+      const double vc = s_cc / Ld / (dc * dc) - mc * mc;
+      const double mn = (s_c + s * s_n) / Ld / dn;
+      const double vn = (s_cc + 2.0 * s * s_cn + s * s * s_nn) / Ld / (dn * dn) - mn * mn;
+      const float vcf = static_cast<float>(vc), vnf = static_cast<float>(vn);
+      const float mcf = static_cast<float>(mc), mnf = static_cast<float>(mn);
+      if (!isfinite(mcf) || !isfinite(vcf)) st = 13;
+      else if (!isfinite(mnf) || !isfinite(vnf)) st = 14;
+      inv_dc = static_cast<float>(1.0 / dc);
+      inv_dn = static_cast<float>(1.0 / dn);
+      a_c = mcf;
+      b_c = 1.0f / __fsqrt_rn(__fadd_rn(vcf, 1e-7f));  // np.sqrt(x.var() + 1e-7) in float32
+      a_n = mnf;
+      b_n = 1.0f / __fsqrt_rn(__fadd_rn(vnf, 1e-7f));
+    }
+  } else {
+    // emotion mode (emotion_dataset.py:177-203): no peak normalisation; a failed mix keeps the clean wave
+    const double sw = mixed ? (s_c + s * s_n) : s_c;
+    const double sww = mixed ? (s_cc + 2.0 * s * s_cn + s * s * s_nn) : s_cc;
+    const double mn = sw / Ld;
+    const double vn = sww / Ld - mn * mn;
+    a_n = static_cast<float>(mn);
+    b_n = 1.0f / __fsqrt_rn(__fadd_rn(static_cast<float>(vn), 1e-7f));
+  }
+  if (rank == 0 && tid == 0) p.status[row] = st;
+
+  // ---- output pass (inputs from L2) ----------------------------------------------------------------
+  float* co_row = p.clean_out ? p.clean_out + static_cast<size_t>(row) * L : nullptr;
+  float* no_row = p.noisy_out + static_cast<size_t>(row) * L;
+  if (p.peak_norm && st != 0) {  // the reference would re-draw this item: hand back zeros + status
+    const float z[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int v0 = v_begin + tid; v0 < v_end; v0 += kMixThreads) {
+      store4<kVec>(co_row, L, v0, z);
+      store4<kVec>(no_row, L, v0, z);
+    }
+    return;
+  }
+  for (int v0 = v_begin + tid; v0 < v_end; v0 += 2 * kMixThreads) {
+    float c[2][4], n[2][4];
+    const int v1 = v0 + kMixThreads;
+    const bool has1 = v1 < v_end;
+    load4<kVec>(c_row, n_row, L, Ln, v0, c[0], n[0]);
+    if (has1) load4<kVec>(c_row, n_row, L, Ln, v1, c[1], n[1]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !has1) break;
+      float oc[4], on[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float y = mixed ? __fadd_rn(c[u][j], __fmul_rn(n[u][j], scale)) : c[u][j];  // augment.py:54,60
+        if (p.peak_norm) {
+          oc[j] = (__fmul_rn(c[u][j], inv_dc) - a_c) * b_c;
+          on[j] = (__fmul_rn(y, inv_dn) - a_n) * b_n;
+        } else {
+          on[j] = (y - a_n) * b_n;
+        }
+      }
+      if (p.peak_norm) store4<kVec>(co_row, L, u ? v1 : v0, oc);
+      store4<kVec>(no_row, L, u ? v1 : v0, on);
+    }
+  }
+}
+
+const char* const kMixStatusNames[] = {
+    "ok", "speech_nan", "noise_nan", "speech_power_too_small", "noise_power_too_small", "scale_invalid",
+    "scale_too_large", "scaled_noise_nan", "noisy_nan", "clean_peak_too_small", "noisy_peak_too_small",
+    "clean_norm_nan", "noisy_norm_nan", "clean_znorm_nan", "noisy_znorm_nan"};
+
+}  // namespace
+}  // namespace nrse
+
+extern "C" {
+
+const char* nrse_mix_status_name(int code) {
+  return (code >= 0 && code <= 14) ? nrse::kMixStatusNames[code] : "unknown";
+}
+
+int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t* snr_idx,
+                           const double* snr_db_table_host, int n_snr, float* clean_out, float* noisy_out,
+                           int32_t* status, int B, int L, int L_noise, int peak_norm, nrse_stream_t stream) {
+  using namespace nrse;
+  if (!clean || !noise || !snr_idx || !snr_db_table_host || !noisy_out || !status) return NRSE_ERR_INVALID_ARG;
+  if (B < 0 || L <= 0 || L_noise <= 0 || n_snr <= 0 || n_snr > kMaxSnr) return NRSE_ERR_INVALID_ARG;
+  if (peak_norm && !clean_out) return NRSE_ERR_INVALID_ARG;
+  if (B == 0) return NRSE_OK;
+
+  MixParams p;
+  p.clean = clean; p.noise = noise; p.snr_idx = snr_idx;
+  p.clean_out = peak_norm ? clean_out : nullptr;
+  p.noisy_out = noisy_out; p.status = status;
+  p.B = B; p.L = L; p.Ln = L_noise; p.peak_norm = peak_norm ? 1 : 0; p.n_snr = n_snr;
+  for (int i = 0; i < kMaxSnr; ++i)
+    p.snr_lin[i] = i < n_snr ? static_cast<float>(std::pow(10.0, snr_db_table_host[i] / 10.0)) : 1.0f;
+
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const bool vec = (L % 4 == 0) && (L_noise % 4 == 0) && (L_noise >= L) && aligned16(clean) && aligned16(noise) &&
+                   aligned16(noisy_out) && (!peak_norm || aligned16(clean_out));
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(B) * kMixCluster);
+  cfg.blockDim = dim3(kMixThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kMixCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (vec) NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_kernel<true>, p));
+  else NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_kernel<false>, p));
+  return NRSE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,368 @@
+"""Torch-facing operators of the B200 hot path: thin wrappers that hand raw device pointers and the current
+CUDA stream to the C-ABI library (include/nrse_b200.h) and register the calls as ``torch.library`` custom ops
+(namespace ``nrse``).  PyTorch is plumbing here -- memory, streams, autograd bookkeeping -- not arithmetic.
+
+Every function requires CUDA tensors on an sm_100 device and raises otherwise: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import DTYPE_BF16, DTYPE_F32, NORM_GROUP, NORM_LAYER, FrontendParams, NrseError, check
+
+CONV_KERNEL = (10, 3, 3, 3, 3, 2, 2)
+CONV_STRIDE = (5, 2, 2, 2, 2, 2, 2)
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[C.c_void_p]:
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*tensors: Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NrseError("nrse_b200 operators need CUDA tensors on a B200 (there is no CPU fallback)")
+
+
+def _dtype_code(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return DTYPE_BF16
+    raise NrseError(f"unsupported dtype {t.dtype}: float32 or bfloat16 expected")
+
+
+# --------------------------------------------------------------------------------------------------------------
+# SNR mix + peak-norm + z-norm
+# --------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("nrse::mix_normalize", mutates_args=())
+def _mix_normalize_op(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db: Sequence[float],
+                      peak_norm: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda(clean, noise, snr_idx)
+    lib = _lib.load()
+    B, L = clean.shape
+    noisy_out = torch.empty_like(clean)
+    clean_out = torch.empty_like(clean) if peak_norm else clean.new_empty(0)
+    status = torch.empty(B, dtype=torch.int32, device=clean.device)
+    table = (C.c_double * len(snr_db))(*[float(v) for v in snr_db])
+    check(lib.nrse_mix_normalize_f32(_ptr(clean), _ptr(noise), _ptr(snr_idx), table, len(snr_db),
+                                     _ptr(clean_out) if peak_norm else None, _ptr(noisy_out), _ptr(status),
+                                     B, L, noise.shape[1], 1 if peak_norm else 0, _stream()),
+          "nrse_mix_normalize_f32")
+    return clean_out, noisy_out, status
+
+
+@_mix_normalize_op.register_fake
+def _(clean, noise, snr_idx, snr_db, peak_norm):
+    return (torch.empty_like(clean) if peak_norm else clean.new_empty(0), torch.empty_like(clean),
+            clean.new_empty(clean.shape[0], dtype=torch.int32))
+
+
+def mix_normalize(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db_table: Sequence[float],
+                  peak_norm: bool = True) -> Tuple[Optional[Tensor], Tensor, Tensor]:
+    """Batched ``add_noise_to_speech`` + peak normalisation + HF z-normalisation on the GPU.
+
+    clean [B,L] f32, noise [B,Ln] f32, snr_idx [B] int32 indexing ``snr_db_table`` (dB, e.g. the YAML
+    ``data.snr_range``).  Returns (clean_input_values | None, noisy_input_values, status [B] int32);
+    ``status[b] != 0`` names the reference's ``return None`` / retry exit that row b would have taken
+    (ref:src/data/augment.py:7-64, ref:src/data/noisy_speech_dataset.py:95-138); such rows are zero-filled
+    in BYOL mode.  peak_norm=False is the emotion fine-tune variant (ref:src/data/emotion_dataset.py:177-203).
+    """
+    if clean.dim() != 2 or noise.dim() != 2 or clean.shape[0] != noise.shape[0]:
+        raise NrseError("mix_normalize expects clean [B,L] and noise [B,Ln]")
+    clean = clean.contiguous().float()
+    noise = noise.contiguous().float()
+    snr_idx = snr_idx.to(device=clean.device, dtype=torch.int32).contiguous()
+    c, n, st = _mix_normalize_op(clean, noise, snr_idx, [float(v) for v in snr_db_table], bool(peak_norm))
+    return (c if peak_norm else None), n, st
+
+
+# --------------------------------------------------------------------------------------------------------------
+# multi-tensor EMA
+# --------------------------------------------------------------------------------------------------------------
+class EmaPlan:
+    """Chunk table for ``target = decay*target + (1-decay)*online`` over many tensor pairs, built once.
+
+    Replaces the per-tensor loop of ``BYOLSpeechModel._update_target_network`` (ref:src/models/byol.py:62-73).
+    The update is in place (the reference re-binds ``.data`` to a fresh tensor every step; values are identical).
+    """
+
+    CHUNK_ELEMS = 16384
+
+    def __init__(self, online: Sequence[Tensor], target: Sequence[Tensor]):
+        if len(online) != len(target):
+            raise NrseError("EmaPlan: online/target lists differ in length")
+        self.online = list(online)
+        self.target = list(target)
+        self._key = None
+        self._build()
+
+    def _signature(self):
+        return tuple((o.data_ptr(), t.data_ptr(), t.numel()) for o, t in zip(self.online, self.target))
+
+    def _build(self):
+        lib = _lib.load()
+        n = len(self.online)
+        for o, t in zip(self.online, self.target):
+            _need_cuda(o, t)
+            if o.dtype != torch.float32 or t.dtype != torch.float32:
+                raise NrseError("EmaPlan: fp32 parameters expected")
+            if o.shape != t.shape or not o.is_contiguous() or not t.is_contiguous():
+                raise NrseError("EmaPlan: online/target tensors must be contiguous and of equal shape")
+        self._key = self._signature()
+        self.n_chunks = 0
+        self.numel = sum(t.numel() for t in self.target)
+        if n == 0:
+            return
+        tp = (C.c_uint64 * n)(*[t.data_ptr() for t in self.target])
+        op = (C.c_uint64 * n)(*[o.data_ptr() for o in self.online])
+        ne = (C.c_int64 * n)(*[t.numel() for t in self.target])
+        cnt = lib.nrse_ema_plan_chunks_host(tp, op, ne, n, self.CHUNK_ELEMS, None, None, None, 0)
+        if cnt < 0:
+            check(int(cnt), "nrse_ema_plan_chunks_host")
+        ct = (C.c_uint64 * cnt)()
+        co = (C.c_uint64 * cnt)()
+        cn = (C.c_int32 * cnt)()
+        got = lib.nrse_ema_plan_chunks_host(tp, op, ne, n, self.CHUNK_ELEMS, ct, co, cn, cnt)
+        if got != cnt:
+            raise NrseError("nrse_ema_plan_chunks_host: inconsistent chunk count")
+        dev = self.target[0].device
+        # uint64 addresses travel as int64 bit patterns
+        self._ct = torch.frombuffer(bytearray(bytes(ct)), dtype=torch.int64).to(dev)
+        self._co = torch.frombuffer(bytearray(bytes(co)), dtype=torch.int64).to(dev)
+        self._cn = torch.frombuffer(bytearray(bytes(cn)), dtype=torch.int32).to(dev)
+        self.n_chunks = int(cnt)
+
+    @torch.no_grad()
+    def step(self, decay: float) -> None:
+        if self._signature() != self._key:  # parameters were moved / re-allocated
+            self._build()
+        if self.n_chunks == 0:
+            return
+        lib = _lib.load()
+        # (1 - decay) is evaluated in Python double and then applied as an fp32 scalar, as torch does for
+        # `(1 - self.ema_decay) * online_param.data` (ref:src/models/byol.py:67-68)
+        check(lib.nrse_ema_chunks_f32(_ptr(self._ct), _ptr(self._co), _ptr(self._cn), self.n_chunks,
+                                      float(decay), float(1 - decay), _stream()), "nrse_ema_chunks_f32")
+
+
+def ema_update_(online: Sequence[Tensor], target: Sequence[Tensor], decay: float) -> None:
+    """One-shot convenience wrapper (builds a plan, runs one step)."""
+    EmaPlan(online, target).step(decay)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# BYOL loss
+# --------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("nrse::byol_loss_fwd", mutates_args=())
+def _byol_loss_fwd(p: Tensor, z: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda(p, z)
+    lib = _lib.load()
+    B, D = p.shape
+    loss = torch.empty((), dtype=torch.float32, device=p.device)
+    saved = torch.empty(B, 4, dtype=torch.float32, device=p.device)
+    row_sim = torch.empty(B, dtype=torch.float32, device=p.device)
+    check(lib.nrse_byol_loss_fwd(_ptr(p), _ptr(z), _ptr(loss), _ptr(saved), _ptr(row_sim), B, D, _dtype_code(p),
+                                 _stream()), "nrse_byol_loss_fwd")
+    return loss, saved, row_sim
+
+
+@_byol_loss_fwd.register_fake
+def _(p, z):
+    B = p.shape[0]
+    return (p.new_empty((), dtype=torch.float32), p.new_empty(B, 4, dtype=torch.float32),
+            p.new_empty(B, dtype=torch.float32))
+
+
+@torch.library.custom_op("nrse::byol_loss_bwd", mutates_args=())
+def _byol_loss_bwd(p: Tensor, z: Tensor, saved: Tensor, grad_loss: Tensor) -> Tensor:
+    lib = _lib.load()
+    B, D = p.shape
+    grad_p = torch.empty_like(p)
+    g = grad_loss.to(torch.float32).contiguous()
+    check(lib.nrse_byol_loss_bwd(_ptr(p), _ptr(z), _ptr(saved), _ptr(g), _ptr(grad_p), B, D, _dtype_code(p),
+                                 _stream()), "nrse_byol_loss_bwd")
+    return grad_p
+
+
+@_byol_loss_bwd.register_fake
+def _(p, z, saved, grad_loss):
+    return torch.empty_like(p)
+
+
+def _loss_setup(ctx, inputs, output):
+    p, z = inputs
+    ctx.save_for_backward(p, z, output[1])
+
+
+def _loss_backward(ctx, g_loss, g_saved, g_rowsim):
+    p, z, saved = ctx.saved_tensors
+    return _byol_loss_bwd(p, z, saved, g_loss), None  # no gradient to the target branch (byol.py:94-96)
+
+
+_byol_loss_fwd.register_autograd(_loss_backward, setup_context=_loss_setup)
+
+
+def _loss_inputs(online_pred: Tensor, target_proj: Tensor):
+    if online_pred.dim() != 2 or online_pred.shape != target_proj.shape:
+        raise NrseError("byol_loss expects two [B,D] tensors of equal shape")
+    if target_proj.dtype != online_pred.dtype:
+        target_proj = target_proj.to(online_pred.dtype)
+    return online_pred.contiguous(), target_proj.detach().contiguous()
+
+
+def byol_loss(online_pred: Tensor, target_proj: Tensor) -> Tensor:
+    """Drop-in for ``byol_loss`` (ref:src/models/byol.py:104-129): 0-d fp32 tensor, differentiable w.r.t.
+    ``online_pred``; one kernel launch forward, one backward, no host synchronisation."""
+    p, z = _loss_inputs(online_pred, target_proj)
+    return _byol_loss_fwd(p, z)[0]
+
+
+def cosine_rows(a: Tensor, b: Tensor) -> Tensor:
+    """Per-row clamped cosine similarity [B] (what ref:evaluate_byol.py:51-55 computes with F.normalize + sum)."""
+    p, z = _loss_inputs(a.detach(), b)
+    return _byol_loss_fwd(p, z)[2]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# conv feature encoder
+# --------------------------------------------------------------------------------------------------------------
+def frontend_geometry(n_samples: int) -> Tuple[List[int], List[int]]:
+    """(T_i, P_i): valid frames and per-utterance frame pitch of each conv layer's channels-last output."""
+    lib = _lib.load()
+    T = (C.c_int32 * 7)()
+    P = (C.c_int32 * 7)()
+    check(lib.nrse_conv_frontend_geometry(int(n_samples), T, P), "nrse_conv_frontend_geometry")
+    return list(T), list(P)
+
+
+def pack_conv_weight(w: Tensor) -> Tensor:
+    """[512, 512, k] fp32 checkpoint layout -> bf16 [512, k*512] (K index = tap*512 + c_in) for the tcgen05 kernel."""
+    _need_cuda(w)
+    lib = _lib.load()
+    n, cin, k = w.shape
+    if n != 512 or cin != 512:
+        raise NrseError("pack_conv_weight expects [512, 512, k]")
+    w = w.detach().contiguous().float()
+    out = torch.empty(512, k * 512, dtype=torch.bfloat16, device=w.device)
+    check(lib.nrse_conv_frontend_pack_weights(_ptr(w), _ptr(out), k, _stream()), "nrse_conv_frontend_pack_weights")
+    return out
+
+
+_workspaces = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> Tensor:
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _aligned(ws: Tensor, align: int = 1024) -> Tuple[int, int]:
+    base = ws.data_ptr()
+    off = (-base) % align
+    return base + off, ws.numel() - off
+
+
+@torch.library.custom_op("nrse::conv_frontend_fwd", mutates_args=())
+def _conv_frontend_fwd(x: Tensor, w0: Tensor, w_packed: Sequence[Tensor], gammas: Sequence[Tensor],
+                       betas: Sequence[Tensor], norm_mode: int, out_bf16: bool) -> Tensor:
+    _need_cuda(x, w0)
+    lib = _lib.load()
+    B, L = x.shape
+    T, P = frontend_geometry(L)
+    y = torch.empty(B, P[6], 512, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    nbytes = lib.nrse_conv_frontend_workspace_bytes(B, L)
+    ws = _workspace(nbytes, x.device)
+    ws_ptr, ws_len = _aligned(ws)
+    prm = FrontendParams()
+    prm.w0 = w0.data_ptr()
+    for i in range(6):
+        prm.w_packed[i] = w_packed[i].data_ptr()
+    n_norm = 7 if norm_mode == NORM_LAYER else 1
+    for i in range(7):
+        prm.gamma[i] = gammas[i].data_ptr() if i < n_norm else None
+        prm.beta[i] = betas[i].data_ptr() if i < n_norm else None
+    check(lib.nrse_conv_frontend_fwd(_ptr(x), C.byref(prm), norm_mode, _ptr(y), DTYPE_BF16 if out_bf16 else DTYPE_F32,
+                                     C.c_void_p(ws_ptr), ws_len, None, B, L, _stream()), "nrse_conv_frontend_fwd")
+    return y
+
+
+@_conv_frontend_fwd.register_fake
+def _(x, w0, w_packed, gammas, betas, norm_mode, out_bf16):
+    t = x.shape[1]
+    for k, s in zip(CONV_KERNEL, CONV_STRIDE):
+        t = (t - k) // s + 1
+    return x.new_empty(x.shape[0], t + 1, 512, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+
+
+def conv_frontend(x: Tensor, conv_weights: Sequence[Tensor], gammas: Sequence[Optional[Tensor]],
+                  betas: Sequence[Optional[Tensor]], norm_mode: str = "layer", out_dtype=torch.float32,
+                  packed: Optional[Sequence[Tensor]] = None) -> Tensor:
+    """WavLM conv feature encoder forward on the B200 kernels.
+
+    x [B,L] fp32 (z-normalised waveform) -> channels-last features [B, T, 512] (a view of the pitched
+    [B, P, 512] kernel output); ``.transpose(1, 2)`` gives the HF layout [B, 512, T] without a copy.
+    conv_weights: 7 tensors in checkpoint layout ([512,1,10], then [512,512,k]); gammas/betas: LayerNorm /
+    GroupNorm affine parameters per layer (None where the layer has no norm).
+    """
+    if x.dim() == 3:
+        x = x.squeeze(1)
+    mode = {"layer": NORM_LAYER, "group": NORM_GROUP}[norm_mode]
+    x = x.contiguous().float()
+    T, _ = frontend_geometry(x.shape[1])
+    w0 = conv_weights[0].detach().reshape(512, 10).contiguous().float()
+    if packed is None:
+        packed = [pack_conv_weight(w) for w in conv_weights[1:]]
+    n_norm = 7 if mode == NORM_LAYER else 1
+    g = [gammas[i].detach().contiguous().float() for i in range(n_norm)]
+    b = [betas[i].detach().contiguous().float() for i in range(n_norm)]
+    y = _conv_frontend_fwd(x, w0, list(packed), g, b, mode, out_dtype == torch.bfloat16)
+    return y[:, :T[6], :]
+
+
+def set_frontend_variant(variant: int) -> None:
+    check(_lib.load().nrse_conv_frontend_set_variant(int(variant)), "nrse_conv_frontend_set_variant")
+
+
+# ---- per-layer entry points (parity tests, callers that own their activation buffers) ---------------------------
+def conv_layer0(x: Tensor, w0: Tensor, gamma: Tensor, beta: Tensor, norm_mode: str = "layer") -> Tensor:
+    """x [B,L] fp32 -> channels-last bf16 [B, P0, 512] (frames t >= T0 are zero padding)."""
+    _need_cuda(x, w0, gamma, beta)
+    lib = _lib.load()
+    B, L = x.shape
+    T, P = frontend_geometry(L)
+    out = torch.empty(B, P[0], 512, dtype=torch.bfloat16, device=x.device)
+    mode = {"layer": NORM_LAYER, "group": NORM_GROUP}[norm_mode]
+    scratch = torch.empty(B * 32 * 1024 * 4 + 2 * (B * 512 * 4 + 1024) + 4096, dtype=torch.uint8, device=x.device)
+    sp, _ = _aligned(scratch)
+    check(lib.nrse_conv_layer0_fwd(_ptr(x.contiguous()), _ptr(w0.reshape(512, 10).contiguous()), _ptr(gamma), _ptr(beta),
+                                   mode, _ptr(out), C.c_void_p(sp), B, L, T[0], P[0], _stream()), "nrse_conv_layer0_fwd")
+    return out
+
+
+def conv_layer(act_prev: Tensor, w_packed: Tensor, k: int, gamma: Optional[Tensor], beta: Optional[Tensor],
+               out_dtype=torch.bfloat16) -> Tensor:
+    """One stride-2 conv layer as an implicit GEMM: act_prev [rows_prev, 512] bf16 -> [rows_prev/2, 512]."""
+    _need_cuda(act_prev, w_packed)
+    lib = _lib.load()
+    rows_prev = act_prev.shape[0]
+    if rows_prev % 2 or act_prev.dtype != torch.bfloat16 or not act_prev.is_contiguous():
+        raise NrseError("conv_layer expects a contiguous bf16 [2*rows_out, 512] activation")
+    rows_out = rows_prev // 2
+    out = torch.empty(rows_out, 512, dtype=out_dtype, device=act_prev.device)
+    check(lib.nrse_conv_layer_fwd(_ptr(act_prev), rows_prev, _ptr(w_packed), k, 2, _ptr(gamma), _ptr(beta), _ptr(out),
+                                  _dtype_code(out), rows_out, _stream()), "nrse_conv_layer_fwd")
+    return out

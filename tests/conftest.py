@@ -27,3 +27,15 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+@pytest.fixture(scope="session")
+def dev():
+    """cuda:0 on the B200 box.  The GPU tests fail (not skip) if the CUDA library is missing."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device in this container (run with -m gpu on the B200 box)")
+    from nrse_b200 import _lib
+    _lib.load()
+    _lib.check(_lib.load().nrse_check_device(), "nrse_check_device")
+    return torch.device("cuda:0")

@@ -1,0 +1,116 @@
+"""Parity of the conv feature encoder kernels (layer-0 SIMT kernel, tcgen05 implicit-GEMM layers 1-6) with the
+fp32 oracle.  Tolerance: 1e-2 norm-relative for bf16 features (north star); per-layer checks are tighter."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from conftest import rel_err
+from nrse_b200 import ops
+from nrse_b200.utils import synthetic
+
+pytestmark = pytest.mark.gpu
+VARIANTS = (1, 2)
+
+
+def _layer_params(layers, dev):
+    w = [torch.from_numpy(l["conv"]).to(dev) for l in layers]
+    g = [None if l["gamma"] is None else torch.from_numpy(l["gamma"]).to(dev) for l in layers]
+    b = [None if l["beta"] is None else torch.from_numpy(l["beta"]).to(dev) for l in layers]
+    return w, g, b
+
+
+@pytest.mark.parametrize("mode", ["layer", "group"])
+def test_layer0_vs_oracle(dev, mode):
+    layers = synthetic.frontend_weights(mode, seed=2)
+    x = synthetic.waveforms(3, 4000, seed=8)[0] * 10  # roughly unit variance like a z-normed waveform
+    ref = oracle.conv_frontend(torch.from_numpy(x), layers, mode, return_all=True)[0]  # [B,512,T0]
+    w, g, b = _layer_params(layers, dev)
+    out = ops.conv_layer0(torch.from_numpy(x).to(dev), w[0], g[0], b[0], mode)
+    T, P = ops.frontend_geometry(4000)
+    assert out.shape == (3, P[0], 512)
+    got = out[:, :T[0]].float().transpose(1, 2).cpu().numpy()
+    assert rel_err(got, ref.numpy()) < 6e-3   # bf16 output rounding (2^-9) dominates
+    assert not out[:, T[0]:].any()            # pitch padding is zero-filled
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("k,rows_out,norm", [(3, 128, True), (2, 128, True), (3, 1000, True), (2, 777, False),
+                                             (3, 128 * 149 + 5, True)])
+def test_gemm_layer_vs_torch(dev, variant, k, rows_out, norm):
+    """One implicit-GEMM layer against conv1d+LayerNorm+GELU in fp32 on the same bf16-rounded operands."""
+    ops.set_frontend_variant(variant)
+    rs = np.random.RandomState(k * 1000 + rows_out)
+    act = torch.from_numpy(rs.standard_normal((2 * rows_out, 512)).astype(np.float32)).bfloat16()
+    w = torch.from_numpy((rs.standard_normal((512, 512, k)) * np.sqrt(2.0 / (512 * k))).astype(np.float32))
+    gamma = torch.from_numpy((1 + 0.1 * rs.standard_normal(512)).astype(np.float32))
+    beta = torch.from_numpy((0.1 * rs.standard_normal(512)).astype(np.float32))
+    wp = ops.pack_conv_weight(w.to(dev))
+    assert wp.shape == (512, k * 512)
+    assert torch.equal(wp.cpu().view(512, k, 512), w.bfloat16().permute(0, 2, 1).contiguous())
+    out = ops.conv_layer(act.to(dev), wp, k, gamma.to(dev) if norm else None, beta.to(dev) if norm else None,
+                         out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    # reference: frames 2m .. 2m+k-1 of the (zero-extended) input, fp32 math on bf16-rounded operands
+    a = torch.cat([act.float(), torch.zeros(2, 512)], 0)              # rows past the end read as zero (TMA OOB fill)
+    h = F.conv1d(a.t()[None], w.bfloat16().float(), stride=2)[0].t()  # [rows_out(+), 512]
+    h = h[:rows_out]
+    if norm:
+        h = F.layer_norm(h, (512,), gamma, beta, eps=1e-5)
+    ref = F.gelu(h)
+    err = rel_err(out.cpu().numpy(), ref.numpy())
+    assert err < 2e-4, err
+    # bf16 output path
+    out16 = ops.conv_layer(act.to(dev), wp, k, gamma.to(dev) if norm else None, beta.to(dev) if norm else None)
+    assert rel_err(out16.float().cpu().numpy(), ref.numpy()) < 5e-3
+    ops.set_frontend_variant(2)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("mode", ["layer", "group"])
+def test_frontend_golden(dev, golden, variant, mode):
+    ops.set_frontend_variant(variant)
+    g = golden(f"frontend_{mode}")
+    layers = synthetic.frontend_weights(mode, seed=int(g["seed"]))
+    w, gm, bt = _layer_params(layers, dev)
+    y = ops.conv_frontend(torch.from_numpy(g["x"]).to(dev), w, gm, bt, mode)
+    assert y.shape == (2, 12, 512)
+    got = y.transpose(1, 2).cpu().numpy()
+    assert got.shape == g["y"].shape
+    assert rel_err(got, g["y"]) < 1e-2
+    ops.set_frontend_variant(2)
+
+
+@pytest.mark.parametrize("mode,B,L", [("layer", 3, 16000), ("group", 2, 16000), ("layer", 1, 400), ("layer", 2, 12345)])
+def test_frontend_vs_oracle(dev, mode, B, L):
+    layers = synthetic.frontend_weights(mode, seed=4)
+    x = synthetic.waveforms(B, L, seed=21)[0]
+    x = (x - x.mean(1, keepdims=True)) / x.std(1, keepdims=True)
+    ref = oracle.conv_frontend(torch.from_numpy(x), layers, mode)
+    w, gm, bt = _layer_params(layers, dev)
+    y = ops.conv_frontend(torch.from_numpy(x).to(dev), w, gm, bt, mode)
+    assert tuple(y.shape) == (B, ref.shape[2], 512)
+    err = rel_err(y.transpose(1, 2).cpu().numpy(), ref.numpy())
+    assert err < 1e-2, err
+    y16 = ops.conv_frontend(torch.from_numpy(x).to(dev), w, gm, bt, mode, out_dtype=torch.bfloat16)
+    assert rel_err(y16.float().transpose(1, 2).cpu().numpy(), ref.numpy()) < 1.5e-2
+
+
+def test_frontend_full_size_batch_independence(dev):
+    """BASELINE shape 64 x 64000: every utterance's features are bit-identical to running that utterance alone
+    (rows of the implicit GEMM are independent), and two sampled utterances match the fp32 oracle."""
+    B, L = 64, 64000
+    layers = synthetic.frontend_weights("layer", seed=0)
+    x = synthetic.waveforms(B, L, seed=1234)[0]
+    x = ((x - x.mean(1, keepdims=True)) / x.std(1, keepdims=True)).astype(np.float32)
+    w, gm, bt = _layer_params(layers, dev)
+    xd = torch.from_numpy(x).to(dev)
+    y = ops.conv_frontend(xd, w, gm, bt, "layer").clone()
+    assert y.shape == (B, 199, 512) and torch.isfinite(y).all()
+    for b in (0, 37, 63):
+        yb = ops.conv_frontend(xd[b:b + 1], w, gm, bt, "layer")
+        assert torch.equal(yb[0], y[b])
+    for b in (5, 63):
+        ref = oracle.conv_frontend(torch.from_numpy(x[b:b + 1]), layers, "layer")
+        assert rel_err(y[b].t().cpu().numpy(), ref[0].numpy()) < 1e-2

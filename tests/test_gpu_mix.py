@@ -1,0 +1,110 @@
+"""Parity of the fused SNR-mix + peak-norm + z-norm kernel with the oracle / reference fixtures (fp32, 1e-6)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import rel_err
+from nrse_b200 import ops
+from nrse_b200.utils import synthetic
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6  # north star: mixing within 1e-6 relative (norm-relative)
+
+
+def _run(dev, clean, noise, snr_idx, table, peak_norm=True):
+    c, n, st = ops.mix_normalize(torch.from_numpy(np.ascontiguousarray(clean)).to(dev),
+                                 torch.from_numpy(np.ascontiguousarray(noise)).to(dev),
+                                 torch.from_numpy(np.asarray(snr_idx, dtype=np.int32)).to(dev),
+                                 [float(v) for v in table], peak_norm)
+    return (None if c is None else c.cpu().numpy()), n.cpu().numpy(), st.cpu().numpy()
+
+
+def test_golden_byol(dev, golden):
+    g = golden("mix_byol")
+    c, n, st = _run(dev, g["clean"], g["noise"], g["snr_idx"], g["snr_table"])
+    assert st.tolist() == [0] * len(st)
+    assert rel_err(c, g["clean_out"]) < TOL
+    assert rel_err(n, g["noisy_out"]) < TOL
+    for row in range(len(st)):  # per-row as well: a batch-wide max would hide a bad quiet row
+        assert rel_err(n[row], g["noisy_out"][row]) < TOL
+        assert rel_err(c[row], g["clean_out"][row]) < TOL
+
+
+def test_golden_emotion_short_and_long_noise(dev, golden):
+    g = golden("mix_emotion")
+    for rows, noise in ((slice(0, 2), g["noise_short"]), (slice(2, 4), g["noise_long"])):
+        c, n, st = _run(dev, g["clean"][rows], noise, g["snr_idx"][rows], g["snr_table"], peak_norm=False)
+        assert c is None and st.tolist() == [0, 0]
+        assert rel_err(n, g["noisy_out"][rows]) < TOL
+
+
+def test_golden_edge_statuses(dev, golden):
+    g = golden("mix_edge")
+    c_ref, n_ref, st_ref = oracle.mix_normalize_batch(g["clean"], g["noise"], np.zeros(8, np.int32), [10.0])
+    c, n, st = _run(dev, g["clean"], g["noise"], np.zeros(8, np.int32), [10.0])
+    assert st.tolist() == st_ref.tolist()
+    assert [bool(s) for s in st[:6]] == [True] * 6 and st[6] == 0 and st[7] == 0
+    for b in range(8):
+        if st[b] != 0:
+            assert not c[b].any() and not n[b].any()  # rejected rows are zero-filled
+        else:
+            assert rel_err(n[b], n_ref[b].numpy()) < TOL and rel_err(c[b], c_ref[b].numpy()) < TOL
+    # emotion mode: a failed mix keeps the clean waveform (emotion_dataset.py:193-194)
+    _, n_ref, st_ref = oracle.mix_normalize_batch(g["clean"], g["noise"], np.zeros(8, np.int32), [10.0], peak_norm=False)
+    _, n, st = _run(dev, g["clean"], g["noise"], np.zeros(8, np.int32), [10.0], peak_norm=False)
+    assert st.tolist() == st_ref.tolist()
+    for b in range(8):
+        r = n_ref[b].numpy()
+        if np.isnan(r).any():
+            assert np.isnan(n[b]).any()
+        else:
+            assert rel_err(n[b], r) < TOL
+
+
+@pytest.mark.parametrize("B,L,Ln,peak", [(5, 4000, 4000, True), (3, 4001, 4001, True), (4, 3998, 1500, True),
+                                         (3, 6000, 7003, False), (2, 401, 401, True), (7, 16000, 16000, False),
+                                         (2, 64000, 64000, True)])
+def test_random_vs_oracle(dev, B, L, Ln, peak):
+    clean, noise, snr_idx, table = synthetic.waveforms(B, L, seed=100 + L % 97, n_noise=Ln)
+    c_ref, n_ref, st_ref = oracle.mix_normalize_batch(clean, noise, snr_idx, table, peak_norm=peak)
+    c, n, st = _run(dev, clean, noise, snr_idx, table, peak)
+    assert st.tolist() == st_ref.tolist()
+    for b in range(B):
+        assert rel_err(n[b], n_ref[b].numpy()) < TOL
+        if peak:
+            assert rel_err(c[b], c_ref[b].numpy()) < TOL
+
+
+def test_dc_offset_and_quiet_rows(dev):
+    """Large DC offset (var << mean^2) and very quiet rows stress the algebraic variance."""
+    clean, noise, snr_idx, table = synthetic.waveforms(4, 8000, seed=3)
+    clean[0] += 0.5
+    noise[1] += 2.0
+    clean[2] *= 1e-3
+    noise[3] *= 1e-3
+    c_ref, n_ref, st_ref = oracle.mix_normalize_batch(clean, noise, snr_idx, table)
+    c, n, st = _run(dev, clean, noise, snr_idx, table)
+    assert st.tolist() == st_ref.tolist() == [0, 0, 0, 0]
+    for b in range(4):
+        assert rel_err(n[b], n_ref[b].numpy()) < 2 * TOL
+        assert rel_err(c[b], c_ref[b].numpy()) < 2 * TOL
+
+
+def test_full_size_properties(dev):
+    """BASELINE shape 64 x 64000: z-normed outputs have mean 0 / var 1, and the realised SNR of the mix
+    (recovered from the normalised views) equals the requested one."""
+    B, L = 64, 64000
+    clean, noise, snr_idx, table = synthetic.waveforms(B, L, seed=1234)
+    c, n, st = _run(dev, clean, noise, snr_idx, table)
+    assert not st.any()
+    assert np.abs(c.mean(1)).max() < 1e-5 and np.abs(n.mean(1)).max() < 1e-5
+    assert np.abs(c.astype(np.float64).var(1) - 1).max() < 1e-4
+    assert np.abs(n.astype(np.float64).var(1) - 1).max() < 1e-4
+    # noisy_z = a*(clean + s*noise) + b  =>  regress out clean, the residual is the scaled noise
+    for b in range(0, B, 9):
+        cz, nz = clean[b].astype(np.float64), n[b].astype(np.float64)
+        A = np.stack([cz, noise[b].astype(np.float64), np.ones(L)], 1)
+        coef, *_ = np.linalg.lstsq(A, nz, rcond=None)
+        snr = 10 * np.log10((coef[0] ** 2 * (cz ** 2).mean()) / (coef[1] ** 2 * (noise[b].astype(np.float64) ** 2).mean()))
+        assert abs(snr - table[snr_idx[b]]) < 1e-3
