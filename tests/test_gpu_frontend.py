@@ -35,7 +35,7 @@ def test_layer0_vs_oracle(dev, mode):
     assert not out[:, T[0]:].any()            # pitch padding is zero-filled
 
 
-@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("variant", VARIANTS, ids=["v1", "v2"])
 @pytest.mark.parametrize("k,rows_out,norm", [(3, 128, True), (2, 128, True), (3, 1000, True), (2, 777, False),
                                              (3, 128 * 149 + 5, True)])
 def test_gemm_layer_vs_torch(dev, variant, k, rows_out, norm):
@@ -67,7 +67,7 @@ def test_gemm_layer_vs_torch(dev, variant, k, rows_out, norm):
     ops.set_frontend_variant(2)
 
 
-@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("variant", VARIANTS, ids=["v1", "v2"])
 @pytest.mark.parametrize("mode", ["layer", "group"])
 def test_frontend_golden(dev, golden, variant, mode):
     ops.set_frontend_variant(variant)
