@@ -64,6 +64,8 @@ int nrse_check_device(void);
  * peak_norm=1 (BYOL pre-training): clean_out and noisy_out are both written.
  * peak_norm=0 (emotion fine-tune, ref:src/data/emotion_dataset.py:177-203): only noisy_out is
  *   written (clean_out may be NULL); a failed mix keeps the clean waveform (:193-194).
+ * peak_norm=2: add_noise_to_speech alone -- noisy_out receives the un-normalised mix speech + scale*noise
+ *   (rows with status != 0 carry the clean waveform; the Python wrapper returns None for them).
  * clean [B,L], noise [B,L_noise] (truncated if longer, tiled if shorter, augment.py:16-21),
  * snr_idx [B] indexes snr_db_table_host[n_snr] (dB; HOST pointer, n_snr <= 32).
  * status[b] = 0 or the number of the reference's `return None`/`continue` exit that row b would
@@ -74,6 +76,9 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
                            float* clean_out, float* noisy_out, int32_t* status,
                            int B, int L, int L_noise, int peak_norm, nrse_stream_t stream);
 const char* nrse_mix_status_name(int status_code);
+/* 1 (default): rows staged once in shared memory by bulk async copies (used when 16-byte aligned, L % 4 == 0,
+ * L_noise >= L and the row fits the cluster's shared memory); 0: always use the re-read-from-L2 kernel. */
+int nrse_mix_set_variant(int variant);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-tensor EMA:  target = decay*target + one_minus_decay*online   (fp32, in place,
@@ -160,6 +165,8 @@ int nrse_conv_layer_fwd(const void* act_prev, int64_t rows_prev, const void* w_p
 /* Tile decomposition of the tcgen05 kernel: 1 = one CTA owns all 512 channels of a 128-frame tile,
  * 2 = a 2-CTA cluster splits the channels and exchanges LayerNorm partials through DSMEM (default). */
 int nrse_conv_frontend_set_variant(int variant);
+/* Layer-0 kernel in LayerNorm mode: 0 = SIMT (warp per frame), 1 = tensor cores (hi/lo-split K=32 UMMA, default). */
+int nrse_conv_frontend_set_layer0_variant(int variant);
 
 #ifdef __cplusplus
 }

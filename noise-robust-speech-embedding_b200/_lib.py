@@ -44,6 +44,7 @@ SIGNATURES = {
     "nrse_check_device": (_i, []),
     "nrse_mix_normalize_f32": (_i, [_p, _p, _p, C.POINTER(C.c_double), _i, _p, _p, _p, _i, _i, _i, _i, _p]),
     "nrse_mix_status_name": (C.c_char_p, [_i]),
+    "nrse_mix_set_variant": (_i, [_i]),
     "nrse_ema_plan_chunks_host": (_i64, [_p, _p, _p, _i, _i64, _p, _p, _p, _i64]),
     "nrse_ema_chunks_f32": (_i, [_p, _p, _p, _i64, _f, _f, _p]),
     "nrse_byol_loss_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
@@ -55,6 +56,7 @@ SIGNATURES = {
     "nrse_conv_layer0_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "nrse_conv_layer_fwd": (_i, [_p, _i64, _p, _i, _i, _p, _p, _p, _i, _i64, _p]),
     "nrse_conv_frontend_set_variant": (_i, [_i]),
+    "nrse_conv_frontend_set_layer0_variant": (_i, [_i]),
 }
 
 _lib = None

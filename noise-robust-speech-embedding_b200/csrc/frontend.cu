@@ -242,23 +242,24 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = one 128-byte swizzled row
 constexpr int kUmmaK = 16;
 constexpr int kUmmaN = 256;
-constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
-constexpr int kEpiThreads = 128;
+constexpr int kEpiThreads = 128;  // one epilogue team = 4 warps = the 4 TMEM lane quadrants
 
 template <int kClusterN>
 struct GemmCfg {
   static constexpr int kNPC = kC / kClusterN;            // channels per CTA
   static constexpr int kNumMma = kNPC / kUmmaN;          // UMMA instructions per K step
   static constexpr int kAccBufs = 512 / kNPC;            // TMEM accumulator buffers (512 columns total)
+  static constexpr int kTeams = kAccBufs;                // one epilogue team (4 warps) per accumulator buffer
+  static constexpr int kThreads = 64 + kTeams * kEpiThreads;  // warp 0 TMA, warp 1 MMA, then the teams
   static constexpr int kStages = kClusterN == 2 ? 4 : 2;
   static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
   static constexpr int kBBytes = kNPC * kBlockK * 2;     // 32 / 64 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // after the stage ring: gamma/beta (float2 per channel), LN partials (2 buffers x 128 rows x float2),
+  // after the stage ring: gamma/beta (float2 per channel), LN partials (2 teams x 2 slots x 128 rows x float2),
   // mbarriers, TMEM base address
   static constexpr int kGbOff = kStages * kStageBytes;
   static constexpr int kStatsOff = kGbOff + kNPC * 8;
-  static constexpr int kBarOff = kStatsOff + 2 * kBlockM * 8;
+  static constexpr int kBarOff = kStatsOff + 4 * kBlockM * 8;
   static constexpr int kNumBars = 2 * kStages + 2 * kAccBufs + 2;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kSmemBytes = kTmemPtrOff + 16 + 1024;  // + slack for the 1024-byte alignment
@@ -275,8 +276,185 @@ struct GemmArgs {
   int stride;          // s_i (frame parity dimension of the A tensor map)
 };
 
+// ---- epilogue of one accumulator row (shared by the GEMM layers and the tensor-core layer 0) ----------------
+// One thread owns one output frame: it reads its TMEM lane twice (statistics, then normalise + GELU + store).
+struct EpiCtx {
+  uint32_t taddr;           // TMEM address: lane quadrant of this warp + first column of the accumulator buffer
+  uint32_t bar_tmem_empty;  // arrived on once this thread has read the whole accumulator row
+  uint32_t stats_slot;      // shared-window address of this row's (mean, M2) slot (same offset in the peer CTA)
+  const float2* stats_local;
+  uint32_t bar_stats;
+  uint32_t stats_parity;
+  uint32_t peer;
+  const float2* s_gb;       // gamma[kNPC] followed by beta[kNPC] of this CTA's channels
+  bool has_norm, store, zero, out_f32;
+  bool arm;                 // this thread arms the statistics barrier (expect_tx) for the tile
+  void* out_row;            // first element of this row's channels [n0, n0 + kNPC)
+};
+
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction) --------------
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 f2_make(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f2 f2_bits(uint32_t lo, uint32_t hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_split(f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// Exact (erf) GELU of two values with ONE MUFU each:
+//   gelu(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2),   erfc(u / sqrt 2) = 2^-q(u),  q(u) = u (c0 + c1 u + .. + c4 u^4)
+// q is a degree-5 fit of -log2 erfc(u/sqrt2) on [0, 5.6] (max abs error of erfc 6.5e-7, tests/test_oracle_golden.py
+// pins it against math.erfc); beyond 5.6 erfc < 2e-8 and |x| is clamped.  NaN inputs propagate (max.NaN).
+__device__ __forceinline__ f2 gelu2(f2 x) {
+  float x0, x1;
+  f2_split(x, x0, x1);
+  const f2 u = f2_make(fminf(fabsf(x0), 5.6f), fminf(fabsf(x1), 5.6f));
+  f2 p = f2_fma(u, f2_make(-0.0005235913558863103f, -0.0005235913558863103f),
+                f2_make(0.007414255291223526f, 0.007414255291223526f));
+  p = f2_fma(p, u, f2_make(-0.05259089171886444f, -0.05259089171886444f));
+  p = f2_fma(p, u, f2_make(-0.4592348039150238f, -0.4592348039150238f));
+  p = f2_fma(p, u, f2_make(-1.1510953903198242f, -1.1510953903198242f));
+  float q0, q1;
+  f2_split(f2_mul(p, u), q0, q1);  // = -q(u)
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+  float r0, r1;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r0) : "f"(x0));
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r1) : "f"(x1));
+  return f2_fma(f2_mul(u, f2_make(e0, e1)), f2_make(-0.5f, -0.5f), f2_make(r0, r1));
+}
+
 template <int kClusterN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
+  constexpr int kNPC = kC / kClusterN;
+  constexpr int kChunks = kNPC / 32;
+  const uint32_t taddr = e.taddr;
+  const f2* s_gamma2 = reinterpret_cast<const f2*>(e.s_gb);           // [kNPC/2] pairs of gamma
+  const f2* s_beta2 = reinterpret_cast<const f2*>(e.s_gb) + kNPC / 2;  // [kNPC/2] pairs of beta
+  uint32_t ra[32], rb[32];  // two TMEM chunks in flight: the next load overlaps the math on the current one
+  float mean = 0.f, rstd = 1.f;
+
+  ptx::tmem_ld32(taddr, ra);
+  if (e.has_norm) {
+    if constexpr (kClusterN == 2) {
+      if (e.arm) ptx::mbar_arrive_expect_tx(e.bar_stats, kBlockM * 8);  // 128 peer rows x (mean, M2)
+    }
+    // pass 1: shifted sums over this CTA's channels (shift = first element: no cancellation), even/odd lanes packed
+    f2 s1 = f2_make(0.f, 0.f), s2 = f2_make(0.f, 0.f), nshift = s1;
+    float shift = 0.f;
+    auto stats32 = [&](const uint32_t (&r)[32]) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const f2 d = f2_add(f2_bits(r[2 * j], r[2 * j + 1]), nshift);
+        s1 = f2_add(s1, d);
+        s2 = f2_fma(d, d, s2);
+      }
+    };
+#pragma unroll 1
+    for (int c = 0; c < kChunks; c += 2) {
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld32(taddr + (c + 1) * 32, rb);
+      if (c == 0) {
+        shift = __uint_as_float(ra[0]);
+        nshift = f2_make(-shift, -shift);
+      }
+      stats32(ra);
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld32(taddr + ((c + 2 < kChunks) ? (c + 2) * 32 : 0), ra);  // wraps to chunk 0 for pass 2
+      stats32(rb);
+    }
+    float s1a, s1b, s2a, s2b;
+    f2_split(s1, s1a, s1b);
+    f2_split(s2, s2a, s2b);
+    const float sum1 = s1a + s1b, sum2 = s2a + s2b;
+    constexpr float kInvN = 1.0f / kNPC;
+    float mean_c = shift + sum1 * kInvN;
+    float m2 = fmaxf(sum2 - sum1 * sum1 * kInvN, 0.f);
+    if constexpr (kClusterN == 2) {
+      // exchange (mean, M2) of my 256 channels with the peer CTA that holds the other 256 (Chan et al.)
+      ptx::st_async_f2(ptx::mapa(e.stats_slot, e.peer), mean_c, m2, ptx::mapa(e.bar_stats, e.peer));
+      ptx::mbar_wait(e.bar_stats, e.stats_parity);
+      const float2 o = *e.stats_local;
+      const float delta = mean_c - o.x;
+      m2 = m2 + o.y + delta * delta * (0.5f * kNPC);
+      mean_c = 0.5f * (mean_c + o.x);
+    }
+    mean = mean_c;
+    rstd = rsqrtf(m2 * (1.0f / kC) + kNormEps);
+  }
+
+  // pass 2: normalise, GELU, store this row's channels.  v = (x*rstd - mean*rstd) * gamma + beta
+  const f2 rstd2 = f2_make(rstd, rstd);
+  const f2 nmr2 = f2_make(-mean * rstd, -mean * rstd);
+  auto emit32 = [&](const uint32_t (&r)[32], int c) {
+    uint32_t o16[16];
+    float o32[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      f2 x = f2_bits(r[2 * j], r[2 * j + 1]);
+      if (e.has_norm) x = f2_fma(f2_fma(x, rstd2, nmr2), s_gamma2[c * 16 + j], s_beta2[c * 16 + j]);
+      float y0, y1;
+      f2_split(gelu2(x), y0, y1);
+      o16[j] = pack_bf16x2(y0, y1);
+      o32[2 * j] = y0;
+      o32[2 * j + 1] = y1;
+    }
+    if (e.store) {
+      if (e.out_f32) {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out_row) + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = e.zero ? make_float4(0.f, 0.f, 0.f, 0.f)
+                          : make_float4(o32[4 * j], o32[4 * j + 1], o32[4 * j + 2], o32[4 * j + 3]);
+      } else {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out_row) + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = e.zero ? make_uint4(0, 0, 0, 0) : make_uint4(o16[4 * j], o16[4 * j + 1], o16[4 * j + 2], o16[4 * j + 3]);
+      }
+    }
+  };
+#pragma unroll 1
+  for (int c = 0; c < kChunks; c += 2) {
+    ptx::tmem_ld_wait();
+    ptx::tmem_ld32(taddr + (c + 1) * 32, rb);
+    emit32(ra, c);
+    ptx::tmem_ld_wait();
+    if (c + 2 < kChunks) {
+      ptx::tmem_ld32(taddr + (c + 2) * 32, ra);
+    } else {  // accumulator fully read: hand it back to the MMA warp
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(e.bar_tmem_empty);
+    }
+    emit32(rb, c + 1);
+  }
+}
+
+template <int kClusterN>
+__global__ void __launch_bounds__(GemmCfg<kClusterN>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const GemmArgs g) {
   using Cfg = GemmCfg<kClusterN>;
@@ -308,8 +486,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::mbar_init(bar(kTmemFull + b), 1);
       ptx::mbar_init(bar(kTmemEmpty + b), kEpiThreads);
     }
-    ptx::mbar_init(bar(kStats + 0), kEpiThreads);
-    ptx::mbar_init(bar(kStats + 1), kEpiThreads);
+    ptx::mbar_init(bar(kStats + 0), 1);  // armed per tile with expect_tx; the peer's st.async complete the bytes
+    ptx::mbar_init(bar(kStats + 1), 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -317,8 +495,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     ptx::tmem_relinquish();
   }
   const bool has_norm = g.gamma != nullptr;
-  for (int i = threadIdx.x; i < Cfg::kNPC; i += kGemmThreads)
-    s_gb[i] = has_norm ? make_float2(g.gamma[n0 + i], g.beta[n0 + i]) : make_float2(1.f, 0.f);
+  for (int i = threadIdx.x; i < Cfg::kNPC; i += Cfg::kThreads) {  // gamma[kNPC] then beta[kNPC]
+    reinterpret_cast<float*>(s_gb)[i] = has_norm ? g.gamma[n0 + i] : 1.f;
+    reinterpret_cast<float*>(s_gb)[Cfg::kNPC + i] = has_norm ? g.beta[n0 + i] : 0.f;
+  }
   ptx::tc_fence_before();
   if constexpr (kClusterN == 2) ptx::cluster_sync_all();  // peer barriers must be initialised before remote arrives
   else __syncthreads();
@@ -388,86 +568,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncwarp();
   } else {
     // ===== epilogue: TMEM -> LayerNorm -> GELU -> global ================================================
+    // Team t (4 warps) owns accumulator buffer t and every kTeams-th tile, so two tiles are in the epilogue at
+    // once (2 warps per scheduler: one hides the other's TMEM / MUFU / shared-memory latencies).
+    const int team = (warp - 2) >> 2;
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;        // accumulator row == TMEM lane
     const uint32_t peer = cta_rank ^ 1u;
-    int it = 0;
-    for (int tile = first_tile; tile < g.num_tiles; tile += tile_step, ++it) {
-      const int buf = it % Cfg::kAccBufs;
+    for (int it = team, tile = first_tile + team * tile_step; tile < g.num_tiles;
+         it += Cfg::kTeams, tile += Cfg::kTeams * tile_step) {
+      const int buf = team;
       const uint32_t acc_phase = static_cast<uint32_t>(it / Cfg::kAccBufs) & 1u;
       const long long m = static_cast<long long>(tile) * kBlockM + row;
       ptx::mbar_wait(bar(kTmemFull + buf), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * Cfg::kNPC);
 
-      float mean = 0.f, rstd = 1.f;
-      if (has_norm) {
-        // pass 1: shifted sums over this CTA's channels (shift = first element: no cancellation)
-        float shift = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < Cfg::kNPC; c += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld32(taddr + c, r);
-          ptx::tmem_ld_wait();
-          if (c == 0) shift = __uint_as_float(r[0]);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = __uint_as_float(r[j]) - shift;
-            s1 += d;
-            s2 = fmaf(d, d, s2);
-          }
-        }
-        constexpr float kInvN = 1.0f / Cfg::kNPC;
-        float mean_c = shift + s1 * kInvN;
-        float m2 = fmaxf(s2 - s1 * s1 * kInvN, 0.f);
-        if constexpr (kClusterN == 2) {
-          // exchange (mean, M2) of my 256 channels with the peer CTA that holds the other 256 (Chan et al.)
-          const int sb = it & 1;
-          const uint32_t slot = smem_base + Cfg::kStatsOff + static_cast<uint32_t>((sb * kBlockM + row) * 8);
-          ptx::st_cluster_f2(ptx::mapa(slot, peer), mean_c, m2);
-          ptx::mbar_arrive_remote_release(ptx::mapa(bar(kStats + sb), peer));
-          ptx::mbar_wait_cluster(bar(kStats + sb), static_cast<uint32_t>(it >> 1) & 1u);
-          const float2 o = s_stats[sb * kBlockM + row];
-          const float delta = mean_c - o.x;
-          m2 = m2 + o.y + delta * delta * (0.5f * Cfg::kNPC);
-          mean_c = 0.5f * (mean_c + o.x);
-        }
-        mean = mean_c;
-        rstd = rsqrtf(m2 * (1.0f / kC) + kNormEps);
-      }
-
-      // pass 2: normalise, GELU, store this row's channels [n0, n0 + kNPC)
-      const bool in_range = m < g.M_total;
-#pragma unroll 1
-      for (int c = 0; c < Cfg::kNPC; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld32(taddr + c, r);
-        ptx::tmem_ld_wait();
-        if (c + 32 >= Cfg::kNPC) {  // accumulator fully read: hand it back to the MMA warp
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(bar(kTmemEmpty + buf));
-        }
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float2 gb = s_gb[c + j];  // warp-uniform address: broadcast
-          const float x = has_norm ? fmaf((__uint_as_float(r[j]) - mean) * rstd, gb.x, gb.y) : __uint_as_float(r[j]);
-          v[j] = gelu_erf(x);
-        }
-        if (in_range) {
-          if (g.out_f32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + m * kC + n0 + c);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + m * kC + n0 + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-          }
-        }
-      }
+      const int slot = team * 2 + static_cast<int>(acc_phase);  // double-buffered per team
+      EpiCtx ec;
+      ec.taddr = taddr;
+      ec.bar_tmem_empty = bar(kTmemEmpty + buf);
+      ec.stats_slot = smem_base + Cfg::kStatsOff + static_cast<uint32_t>((slot * kBlockM + row) * 8);
+      ec.stats_local = s_stats + slot * kBlockM + row;
+      ec.bar_stats = bar(kStats + team);
+      ec.stats_parity = acc_phase;
+      ec.arm = row == 0;
+      ec.peer = peer;
+      ec.s_gb = s_gb;
+      ec.has_norm = has_norm;
+      ec.store = m < g.M_total;
+      ec.zero = false;
+      ec.out_f32 = g.out_f32 != 0;
+      ec.out_row = g.out_f32 ? static_cast<void*>(reinterpret_cast<float*>(g.out) + m * kC + n0)
+                             : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(g.out) + m * kC + n0);
+      epilogue_row<kClusterN>(ec);
     }
   }
 
@@ -476,6 +609,226 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if constexpr (kClusterN == 2) ptx::cluster_sync_all();  // no CTA may exit while its peer can still write to it
   else __syncthreads();
   if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =========================================================================================================
+// Layer 0 on the tensor cores (LayerNorm mode).  The SIMT kernel above is bound by shuffle-reduction latency
+// and by its 160 FMAs per lane per frame; here the 10-tap convolution becomes a K = 32 UMMA
+//     y = w_hi.x_hi + w_hi.x_lo + w_lo.x_hi          (bf16 hi/lo split of both operands, fp32 accumulate:
+//                                                     error ~2^-16 relative, i.e. fp32-class, not bf16-class)
+// whose A rows (the 10-sample windows, stride 5 -- not expressible as a TMA box because 20-byte strides are not
+// 16-byte multiples) are written to shared memory by four builder warps in the 128-byte-swizzled K-major layout
+// the UMMA descriptor expects, and the LayerNorm + GELU epilogue is the same TMEM epilogue as layers 1-6
+// (statistics are thread-local: one thread = one frame).
+// =========================================================================================================
+constexpr int kL0AStages = 2;  // warps 0-3: A-row builders, warp 4: MMA issuer, warps 5..: epilogue teams
+
+template <int kClusterN>
+struct L0tcCfg {
+  static constexpr int kNPC = kC / kClusterN;
+  static constexpr int kNumMma = kNPC / kUmmaN;
+  static constexpr int kAccBufs = 512 / kNPC;
+  static constexpr int kTeams = kAccBufs;
+  static constexpr int kThreads = 160 + kTeams * kEpiThreads;
+  static constexpr int kABytes = kBlockM * 128;  // 128-byte row pitch, K = 32 bf16 uses the first 64 bytes
+  static constexpr int kWOff = kL0AStages * kABytes;
+  static constexpr int kWBytes = kNPC * 128;
+  static constexpr int kGbOff = kWOff + kWBytes;
+  static constexpr int kStatsOff = kGbOff + kNPC * 8;
+  static constexpr int kBarOff = kStatsOff + 4 * kBlockM * 8;
+  static constexpr int kNumBars = 2 * kL0AStages + 2 * kAccBufs + 2;
+  static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr int kSmemBytes = kTmemPtrOff + 16 + 1024;
+};
+
+// K layout of one operand row (32 bf16 = 16 words): [a_0..a_9 | b_0..b_9 | c_0..c_9 | 0 0]
+__device__ __forceinline__ void l0_store_row(uint32_t tile_base, int row, const uint32_t (&w)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t addr = tile_base + static_cast<uint32_t>(row * 128 + ((c ^ (row & 7)) << 4));  // SWIZZLE_128B
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * c]), "r"(w[4 * c + 1]),
+                 "r"(w[4 * c + 2]), "r"(w[4 * c + 3])
+                 : "memory");
+  }
+}
+
+// v[10] fp32 -> hi[5], lo[5] packed bf16 pairs with v = hi + lo (+ O(2^-17))
+__device__ __forceinline__ void l0_split(const float (&v)[10], uint32_t (&hi)[5], uint32_t (&lo)[5]) {
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+    const float r0 = v[2 * j] - __bfloat162float(h0), r1 = v[2 * j + 1] - __bfloat162float(h1);
+    hi[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+    lo[j] = pack_bf16x2(r0, r1);
+  }
+}
+
+template <int kClusterN>
+__global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_kernel(const L0Args a) {
+  using Cfg = L0tcCfg<kClusterN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kClusterN == 2 ? ptx::cluster_ctarank() : 0u;
+  const int n0 = static_cast<int>(cta_rank) * Cfg::kNPC;
+
+  auto bar = [&](int i) { return smem_base + Cfg::kBarOff + 8u * static_cast<uint32_t>(i); };
+  const int kFull = 0, kEmpty = kL0AStages, kTmemFull = 2 * kL0AStages, kTmemEmpty = kTmemFull + Cfg::kAccBufs,
+            kStats = kTmemEmpty + Cfg::kAccBufs;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + Cfg::kTmemPtrOff);
+  float2* s_gb = reinterpret_cast<float2*>(smem + Cfg::kGbOff);
+  float2* s_stats = reinterpret_cast<float2*>(smem + Cfg::kStatsOff);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kL0AStages; ++s) {
+      ptx::mbar_init(bar(kFull + s), kBlockM);  // 128 builder threads arrive
+      ptx::mbar_init(bar(kEmpty + s), 1);
+    }
+    for (int b = 0; b < Cfg::kAccBufs; ++b) {
+      ptx::mbar_init(bar(kTmemFull + b), 1);
+      ptx::mbar_init(bar(kTmemEmpty + b), kEpiThreads);
+    }
+    ptx::mbar_init(bar(kStats + 0), 1);
+    ptx::mbar_init(bar(kStats + 1), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 512);
+    ptx::tmem_relinquish();
+  }
+  // this CTA's filters, split hi/lo, as the B operand: [w_hi | w_hi | w_lo | 0 0] against A = [x_hi | x_lo | x_hi | 0 0]
+  for (int n = threadIdx.x; n < Cfg::kNPC; n += Cfg::kThreads) {
+    float w[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) w[k] = __ldg(a.w + (n0 + n) * 10 + k);
+    uint32_t hi[5], lo[5], words[16];
+    l0_split(w, hi, lo);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      words[j] = hi[j];
+      words[5 + j] = hi[j];
+      words[10 + j] = lo[j];
+    }
+    words[15] = 0;
+    l0_store_row(smem_base + Cfg::kWOff, n, words);
+    reinterpret_cast<float*>(s_gb)[n] = a.gamma[n0 + n];
+    reinterpret_cast<float*>(s_gb)[Cfg::kNPC + n] = a.beta[n0 + n];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
+  ptx::tc_fence_before();
+  if constexpr (kClusterN == 2) ptx::cluster_sync_all();
+  else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const long long m_total = static_cast<long long>(a.B) * a.P0;
+  const int num_tiles = static_cast<int>((m_total + kBlockM - 1) / kBlockM);
+  const int first_tile = static_cast<int>(blockIdx.x) / kClusterN;
+  const int tile_step = static_cast<int>(gridDim.x) / kClusterN;
+
+  if (warp < 4) {
+    // ===== A-row builders: one thread = one output frame ==================================================
+    const int row = threadIdx.x;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const long long m = static_cast<long long>(tile) * kBlockM + row;
+      const int b = static_cast<int>(m / a.P0), t = static_cast<int>(m % a.P0);
+      float x[10];
+      if (m < m_total && t < a.T0) {
+        const float* xw = a.x + static_cast<size_t>(b) * a.L + 5 * t;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) x[k] = __ldg(xw + k);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) x[k] = 0.f;
+      }
+      uint32_t hi[5], lo[5], words[16];
+      l0_split(x, hi, lo);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        words[j] = hi[j];
+        words[5 + j] = lo[j];
+        words[10 + j] = hi[j];
+      }
+      words[15] = 0;
+      ptx::mbar_wait(bar(kEmpty + stage), phase ^ 1u);
+      l0_store_row(smem_base + stage * Cfg::kABytes, row, words);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      ptx::mbar_arrive(bar(kFull + stage));
+      if (++stage == kL0AStages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 4) {
+    // ===== MMA issuer =========================================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, kUmmaN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+        const int buf = it % Cfg::kAccBufs;
+        const uint32_t acc_phase = static_cast<uint32_t>(it / Cfg::kAccBufs) & 1u;
+        ptx::mbar_wait(bar(kTmemEmpty + buf), acc_phase ^ 1u);
+        ptx::mbar_wait(bar(kFull + stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t a_src = smem_base + stage * Cfg::kABytes;
+        const uint32_t w_src = smem_base + Cfg::kWOff;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {  // K = 32 = 2 x UMMA_K
+          const uint64_t da = ptx::umma_desc_sw128(a_src + k * (kUmmaK * 2));
+#pragma unroll
+          for (int h = 0; h < Cfg::kNumMma; ++h) {
+            const uint64_t db = ptx::umma_desc_sw128(w_src + h * (kUmmaN * 128) + k * (kUmmaK * 2));
+            ptx::umma_bf16(tmem_base + static_cast<uint32_t>(buf * Cfg::kNPC + h * kUmmaN), da, db, idesc, k != 0 ? 1u : 0u);
+          }
+        }
+        ptx::umma_commit(bar(kEmpty + stage));
+        ptx::umma_commit(bar(kTmemFull + buf));
+        if (++stage == kL0AStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue teams (see conv_gemm_kernel) ==========================================================
+    const int team = (warp - 5) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t peer = cta_rank ^ 1u;
+    for (int it = team, tile = first_tile + team * tile_step; tile < num_tiles;
+         it += Cfg::kTeams, tile += Cfg::kTeams * tile_step) {
+      const int buf = team;
+      const uint32_t acc_phase = static_cast<uint32_t>(it / Cfg::kAccBufs) & 1u;
+      const long long m = static_cast<long long>(tile) * kBlockM + row;
+      ptx::mbar_wait(bar(kTmemFull + buf), acc_phase);
+      ptx::tc_fence_after();
+      const int slot = team * 2 + static_cast<int>(acc_phase);
+      EpiCtx ec;
+      ec.taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * Cfg::kNPC);
+      ec.bar_tmem_empty = bar(kTmemEmpty + buf);
+      ec.stats_slot = smem_base + Cfg::kStatsOff + static_cast<uint32_t>((slot * kBlockM + row) * 8);
+      ec.stats_local = s_stats + slot * kBlockM + row;
+      ec.bar_stats = bar(kStats + team);
+      ec.stats_parity = acc_phase;
+      ec.arm = row == 0;
+      ec.peer = peer;
+      ec.s_gb = s_gb;
+      ec.has_norm = true;
+      ec.store = m < m_total;
+      ec.zero = static_cast<int>(m % a.P0) >= a.T0;  // pitch padding is written as zeros
+      ec.out_f32 = false;
+      ec.out_row = a.out + m * kC + n0;
+      epilogue_row<kClusterN>(ec);
+    }
+  }
+
+  ptx::tc_fence_before();
+  if constexpr (kClusterN == 2) ptx::cluster_sync_all();
+  else __syncthreads();
+  if (warp == 4) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
@@ -542,7 +895,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmArgs& g,
   const int groups = g.num_tiles < max_groups ? g.num_tiles : max_groups;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * kClusterN));
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -555,6 +908,37 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmArgs& g,
   NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<kClusterN>, ta, tw, g));
   return NRSE_OK;
 }
+
+template <int kClusterN>
+int launch_layer0_tc(const L0Args& a, cudaStream_t stream) {
+  using Cfg = L0tcCfg<kClusterN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(layer0_tc_kernel<kClusterN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const long long m_total = static_cast<long long>(a.B) * a.P0;
+  const int num_tiles = static_cast<int>((m_total + kBlockM - 1) / kBlockM);
+  const int max_groups = kNumSMs / kClusterN;
+  const int groups = num_tiles < max_groups ? num_tiles : max_groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(groups * kClusterN));
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kClusterN;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, layer0_tc_kernel<kClusterN>, a));
+  return NRSE_OK;
+}
+
+int g_layer0_variant = 1;  // 0: SIMT kernel, 1: tensor-core kernel (LayerNorm mode only)
 
 int geometry(int L, int32_t* T, int32_t* P) {
   long long t = L;
@@ -603,6 +987,12 @@ int nrse_conv_frontend_set_variant(int variant) {
   return NRSE_OK;
 }
 
+int nrse_conv_frontend_set_layer0_variant(int variant) {
+  if (variant != 0 && variant != 1) return NRSE_ERR_INVALID_ARG;
+  nrse::g_layer0_variant = variant;
+  return NRSE_OK;
+}
+
 int nrse_conv_frontend_pack_weights(const float* w, void* w_packed, int k, nrse_stream_t stream) {
   using namespace nrse;
   if (!w || !w_packed || (k != 2 && k != 3)) return NRSE_ERR_INVALID_ARG;
@@ -626,6 +1016,7 @@ int nrse_conv_layer0_fwd(const float* x, const float* w0, const float* gamma, co
   const long long want = ceil_div(rows, static_cast<long long>(kL0Warps));
   const unsigned grid = static_cast<unsigned>(want < kNumSMs ? want : kNumSMs);
   if (norm_mode == NRSE_NORM_LAYER) {
+    if (g_layer0_variant == 1) return g_variant == 2 ? launch_layer0_tc<2>(a, s) : launch_layer0_tc<1>(a, s);
     layer0_kernel<false><<<grid, kL0Threads, 0, s>>>(a);
     NRSE_CHECK_LAUNCH();
     return NRSE_OK;

@@ -35,6 +35,7 @@ struct MixParams {
   float* noisy_out;
   int32_t* status;
   int B, L, Ln, peak_norm, n_snr;
+  int raw;  // 1: write the un-normalised mix c + s*n (add_noise_to_speech alone); peak_norm must be 0
   float snr_lin[kMaxSnr];  // float(10 ** (snr_db / 10)), ref:src/data/augment.py:39
 };
 
@@ -273,6 +274,10 @@ __global__ void __launch_bounds__(kMixThreads) mix_normalize_kernel(const MixPar
     const double vn = sww / Ld - mn * mn;
     a_n = static_cast<float>(mn);
     b_n = 1.0f / __fsqrt_rn(__fadd_rn(static_cast<float>(vn), 1e-7f));
+    if (p.raw) {  // (y - 0) * 1 is exact: the output is the mixed signal itself
+      a_n = 0.f;
+      b_n = 1.f;
+    }
   }
   if (rank == 0 && tid == 0) p.status[row] = st;
 
@@ -313,6 +318,284 @@ __global__ void __launch_bounds__(kMixThreads) mix_normalize_kernel(const MixPar
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory-resident variant (the default when the row fits): each CTA of the cluster pulls its segment of
+// the clean and noise rows into shared memory ONCE with bulk async copies (cp.async.bulk + mbarrier
+// complete_tx, issued by one thread, several chunks in flight so the statistics pass starts as soon as the
+// first chunk lands); the second and third passes then run out of shared memory, so HBM/L2 see exactly the
+// algorithmic traffic (read 8 B, write 8 B per sample) whatever the batch size.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSmemThreads = 256;
+constexpr int kSmemWarps = kSmemThreads / 32;
+constexpr int kSmemMaxCluster = 8;
+constexpr int kSmemChunks = 4;
+
+template <int kN>
+__device__ __forceinline__ void block_sum_n(double (&v)[kN], double* scratch, int n_warps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kN; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kN; ++k) scratch[warp * kN + k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kN; ++k) {
+    double s = 0.0;
+    for (int w = 0; w < n_warps; ++w) s += scratch[w * kN + k];
+    v[k] = s;
+  }
+}
+
+__device__ __forceinline__ float block_max_n(float v, float* scratch, int n_warps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float m = scratch[0];
+  for (int w = 1; w < n_warps; ++w) m = fmaxf(m, scratch[w]);
+  return m;
+}
+
+__global__ void __launch_bounds__(kSmemThreads) mix_normalize_smem_kernel(const MixParams p, int seg_vec) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int cs = static_cast<int>(cluster.num_blocks());
+  const int row = blockIdx.x / cs;
+  const int tid = threadIdx.x;
+
+  extern __shared__ __align__(128) unsigned char mix_smem[];
+  __shared__ __align__(8) unsigned long long bars[kSmemChunks];
+  __shared__ double red_d[kSmemWarps * 5];
+  __shared__ float red_f[kSmemWarps];
+  __shared__ double xch1_d[kSmemMaxCluster][5];
+  __shared__ float xch1_f[kSmemMaxCluster][2];
+  __shared__ float xch2_f[kSmemMaxCluster];
+  __shared__ unsigned xch2_u[kSmemMaxCluster];
+
+  const int L = p.L;
+  const int nvec = L >> 2;  // L % 4 == 0 on this path
+  const int v_begin = min(nvec, rank * seg_vec);
+  const int v_end = min(nvec, v_begin + seg_vec);
+  const int n_my = v_end - v_begin;
+  float4* s_c = reinterpret_cast<float4*>(mix_smem);
+  float4* s_n = s_c + seg_vec;
+  const int chunk_vec = (seg_vec + kSmemChunks - 1) / kSmemChunks;
+
+  // ---- bulk async loads: global -> shared, one mbarrier per chunk -------------------------------------------
+  if (tid == 0) {
+    for (int c = 0; c < kSmemChunks; ++c) {
+      const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[c]));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const float4* g_c = reinterpret_cast<const float4*>(p.clean + static_cast<size_t>(row) * L) + v_begin;
+    const float4* g_n = reinterpret_cast<const float4*>(p.noise + static_cast<size_t>(row) * p.Ln) + v_begin;
+    for (int c = 0; c < kSmemChunks; ++c) {
+      const int c0 = c * chunk_vec;
+      const int len = min(chunk_vec, n_my - c0);
+      const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[c]));
+      if (len <= 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        continue;
+      }
+      const unsigned bytes = static_cast<unsigned>(len) * 16u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       static_cast<unsigned>(__cvta_generic_to_shared(s_c + c0))),
+                   "l"(g_c + c0), "r"(bytes), "r"(bar)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       static_cast<unsigned>(__cvta_generic_to_shared(s_n + c0))),
+                   "l"(g_n + c0), "r"(bytes), "r"(bar)
+                   : "memory");
+    }
+  }
+  __syncthreads();  // barrier inits visible to the waiting threads
+
+  // ---- pass 1 (shared memory, chunk by chunk as the copies land) ---------------------------------------------
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  float cmax = 0.f, nmax_in = 0.f;
+  for (int c = 0; c < kSmemChunks; ++c) {
+    const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[c]));
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}\n" ::"r"(bar)
+        : "memory");
+    const int c_end = min(n_my, (c + 1) * chunk_vec);
+    for (int v0 = c * chunk_vec + tid; v0 < c_end; v0 += 2 * kSmemThreads) {
+      float f[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int v = v0 + u * kSmemThreads;
+        if (v < c_end) {
+          const float4 cv = s_c[v], nv = s_n[v];
+          const float cc[4] = {cv.x, cv.y, cv.z, cv.w}, nn[4] = {nv.x, nv.y, nv.z, nv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            f[0] = fmaf(cc[j], cc[j], f[0]);
+            f[1] = fmaf(nn[j], nn[j], f[1]);
+            f[2] += cc[j];
+            f[3] += nn[j];
+            f[4] = fmaf(cc[j], nn[j], f[4]);
+          }
+          cmax = absmax4(cmax, cc);
+          nmax_in = absmax4(nmax_in, nn);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc[k] += static_cast<double>(f[k]);
+    }
+  }
+  block_sum_n<5>(acc, red_d, kSmemWarps);
+  cmax = block_max_n(cmax, red_f, kSmemWarps);
+  nmax_in = block_max_n(nmax_in, red_f, kSmemWarps);
+  if (tid < cs) {
+    double* dst_d = cluster.map_shared_rank(&xch1_d[rank][0], tid);
+    float* dst_f = cluster.map_shared_rank(&xch1_f[rank][0], tid);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) dst_d[k] = acc[k];
+    dst_f[0] = cmax;
+    dst_f[1] = nmax_in;
+  }
+  cluster.sync();
+  double s_cc = 0.0, s_nn = 0.0, s_c1 = 0.0, s_n1 = 0.0, s_cn = 0.0;
+  cmax = 0.f;
+  nmax_in = 0.f;
+  for (int r = 0; r < cs; ++r) {
+    s_cc += xch1_d[r][0];
+    s_nn += xch1_d[r][1];
+    s_c1 += xch1_d[r][2];
+    s_n1 += xch1_d[r][3];
+    s_cn += xch1_d[r][4];
+    cmax = fmaxf(cmax, xch1_f[r][0]);
+    nmax_in = fmaxf(nmax_in, xch1_f[r][1]);
+  }
+
+  const double Ld = static_cast<double>(L);
+  const float Ps = static_cast<float>(s_cc / Ld);
+  const float Pn = static_cast<float>(s_nn / Ld);
+  int idx = p.snr_idx[row];
+  idx = idx < 0 ? 0 : (idx >= p.n_snr ? p.n_snr - 1 : idx);
+  const float scale = __fsqrt_rn(__fdiv_rn(Ps, __fmul_rn(Pn, p.snr_lin[idx])));
+  int st = 0;
+  if (isnan(Ps)) st = 1;
+  else if (isnan(Pn)) st = 2;
+  else if (Ps < 1e-10f) st = 3;
+  else if (Pn < 1e-10f) st = 4;
+  else if (isinf(scale) || isnan(scale)) st = 5;
+  else if (scale > 1e6f) st = 6;
+  else if (isinf(nmax_in)) st = 7;
+
+  float nmax = 0.f;
+  if (p.peak_norm && st == 0) {
+    // ---- pass 2 (shared memory): mix in place (noise slot <- noisy), peak of the mix, NaN flags ---------------
+    unsigned flags = 0;
+    for (int v = tid; v < n_my; v += kSmemThreads) {
+      const float4 cv = s_c[v], nv = s_n[v];
+      const float cc[4] = {cv.x, cv.y, cv.z, cv.w}, nn[4] = {nv.x, nv.y, nv.z, nv.w};
+      float y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float sn = __fmul_rn(nn[j], scale);
+        y[j] = __fadd_rn(cc[j], sn);
+        flags |= (isnan(sn) ? 1u : 0u) | (isnan(y[j]) ? 2u : 0u);
+      }
+      nmax = absmax4(nmax, y);
+      s_n[v] = make_float4(y[0], y[1], y[2], y[3]);
+    }
+    nmax = block_max_n(nmax, red_f, kSmemWarps);
+    flags = __syncthreads_or(static_cast<int>(flags));
+    if (tid < cs) {
+      *cluster.map_shared_rank(&xch2_f[rank], tid) = nmax;
+      *cluster.map_shared_rank(&xch2_u[rank], tid) = flags;
+    }
+    cluster.sync();
+    nmax = 0.f;
+    flags = 0;
+    for (int r = 0; r < cs; ++r) {
+      nmax = fmaxf(nmax, xch2_f[r]);
+      flags |= xch2_u[r];
+    }
+    if (flags & 1u) st = 7;
+    else if (flags & 2u) st = 8;
+    else if (cmax < 1e-8f) st = 9;
+    else if (nmax < 1e-8f) st = 10;
+    else if (isinf(cmax)) st = 11;
+    else if (isinf(nmax)) st = 12;
+  }
+
+  const double s = static_cast<double>(scale);
+  float a_c = 0.f, b_c = 0.f, a_n = 0.f, b_n = 0.f, inv_dc = 1.f, inv_dn = 1.f;
+  const bool mixed = (st == 0);
+  if (p.peak_norm) {
+    if (st == 0) {
+      const double dc = static_cast<double>(__fadd_rn(cmax, 1e-8f));
+      const double dn = static_cast<double>(__fadd_rn(nmax, 1e-8f));
+      const double mc = s_c1 / Ld / dc;
+      const double vc = s_cc / Ld / (dc * dc) - mc * mc;
+      const double mn = (s_c1 + s * s_n1) / Ld / dn;
+      const double vn = (s_cc + 2.0 * s * s_cn + s * s * s_nn) / Ld / (dn * dn) - mn * mn;
+      const float vcf = static_cast<float>(vc), vnf = static_cast<float>(vn);
+      const float mcf = static_cast<float>(mc), mnf = static_cast<float>(mn);
+      if (!isfinite(mcf) || !isfinite(vcf)) st = 13;
+      else if (!isfinite(mnf) || !isfinite(vnf)) st = 14;
+      inv_dc = static_cast<float>(1.0 / dc);
+      inv_dn = static_cast<float>(1.0 / dn);
+      a_c = mcf;
+      b_c = 1.0f / __fsqrt_rn(__fadd_rn(vcf, 1e-7f));
+      a_n = mnf;
+      b_n = 1.0f / __fsqrt_rn(__fadd_rn(vnf, 1e-7f));
+    }
+  } else {
+    const double sw = mixed ? (s_c1 + s * s_n1) : s_c1;
+    const double sww = mixed ? (s_cc + 2.0 * s * s_cn + s * s * s_nn) : s_cc;
+    const double mn = sw / Ld;
+    const double vn = sww / Ld - mn * mn;
+    a_n = static_cast<float>(mn);
+    b_n = 1.0f / __fsqrt_rn(__fadd_rn(static_cast<float>(vn), 1e-7f));
+    if (p.raw) {  // (y - 0) * 1 is exact: the output is the mixed signal itself
+      a_n = 0.f;
+      b_n = 1.f;
+    }
+  }
+  if (rank == 0 && tid == 0) p.status[row] = st;
+
+  // ---- output pass: shared memory -> global, 128-bit coalesced stores ------------------------------------------
+  float4* co = p.clean_out ? reinterpret_cast<float4*>(p.clean_out + static_cast<size_t>(row) * L) + v_begin : nullptr;
+  float4* no = reinterpret_cast<float4*>(p.noisy_out + static_cast<size_t>(row) * L) + v_begin;
+  if (p.peak_norm && st != 0) {
+    for (int v = tid; v < n_my; v += kSmemThreads) {
+      co[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      no[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+  for (int v = tid; v < n_my; v += kSmemThreads) {
+    const float4 cv = s_c[v], yv = s_n[v];  // BYOL mode: the noise slot already holds the mixed signal
+    const float cc[4] = {cv.x, cv.y, cv.z, cv.w}, yy[4] = {yv.x, yv.y, yv.z, yv.w};
+    float oc[4], on[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (p.peak_norm) {
+        oc[j] = (__fmul_rn(cc[j], inv_dc) - a_c) * b_c;
+        on[j] = (__fmul_rn(yy[j], inv_dn) - a_n) * b_n;
+      } else {
+        const float y = mixed ? __fadd_rn(cc[j], __fmul_rn(yy[j], scale)) : cc[j];
+        on[j] = (y - a_n) * b_n;
+      }
+    }
+    if (p.peak_norm) co[v] = make_float4(oc[0], oc[1], oc[2], oc[3]);
+    no[v] = make_float4(on[0], on[1], on[2], on[3]);
+  }
+}
+
+int g_mix_variant = 1;  // 1: shared-memory-resident rows (default), 0: re-read from L2
+
 const char* const kMixStatusNames[] = {
     "ok", "speech_nan", "noise_nan", "speech_power_too_small", "noise_power_too_small", "scale_invalid",
     "scale_too_large", "scaled_noise_nan", "noisy_nan", "clean_peak_too_small", "noisy_peak_too_small",
@@ -322,6 +605,12 @@ const char* const kMixStatusNames[] = {
 }  // namespace nrse
 
 extern "C" {
+
+int nrse_mix_set_variant(int variant) {
+  if (variant != 0 && variant != 1) return NRSE_ERR_INVALID_ARG;
+  nrse::g_mix_variant = variant;
+  return NRSE_OK;
+}
 
 const char* nrse_mix_status_name(int code) {
   return (code >= 0 && code <= 14) ? nrse::kMixStatusNames[code] : "unknown";
@@ -333,33 +622,59 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
   using namespace nrse;
   if (!clean || !noise || !snr_idx || !snr_db_table_host || !noisy_out || !status) return NRSE_ERR_INVALID_ARG;
   if (B < 0 || L <= 0 || L_noise <= 0 || n_snr <= 0 || n_snr > kMaxSnr) return NRSE_ERR_INVALID_ARG;
-  if (peak_norm && !clean_out) return NRSE_ERR_INVALID_ARG;
+  if (peak_norm < 0 || peak_norm > 2) return NRSE_ERR_INVALID_ARG;
+  if (peak_norm == 1 && !clean_out) return NRSE_ERR_INVALID_ARG;
   if (B == 0) return NRSE_OK;
 
   MixParams p;
   p.clean = clean; p.noise = noise; p.snr_idx = snr_idx;
-  p.clean_out = peak_norm ? clean_out : nullptr;
+  p.clean_out = peak_norm == 1 ? clean_out : nullptr;
   p.noisy_out = noisy_out; p.status = status;
-  p.B = B; p.L = L; p.Ln = L_noise; p.peak_norm = peak_norm ? 1 : 0; p.n_snr = n_snr;
+  p.B = B; p.L = L; p.Ln = L_noise; p.peak_norm = peak_norm == 1 ? 1 : 0; p.n_snr = n_snr;
+  p.raw = peak_norm == 2 ? 1 : 0;
   for (int i = 0; i < kMaxSnr; ++i)
     p.snr_lin[i] = i < n_snr ? static_cast<float>(std::pow(10.0, snr_db_table_host[i] / 10.0)) : 1.0f;
 
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   const bool vec = (L % 4 == 0) && (L_noise % 4 == 0) && (L_noise >= L) && aligned16(clean) && aligned16(noise) &&
-                   aligned16(noisy_out) && (!peak_norm || aligned16(clean_out));
+                   aligned16(noisy_out) && (peak_norm != 1 || aligned16(clean_out));
 
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
   cudaLaunchConfig_t cfg = {};
+  cfg.stream = as_stream(stream);
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+
+  if (vec && g_mix_variant == 1) {
+    // smallest power-of-two cluster that keeps a CTA's two row segments within 64 KB (3 CTAs per SM), up to 8
+    const size_t row_bytes = static_cast<size_t>(L) * 8;
+    int cs = 1;
+    while (cs < kSmemMaxCluster && row_bytes > static_cast<size_t>(cs) * 65536) cs *= 2;
+    const int nvec = L / 4;
+    const int seg_vec = ceil_div(nvec, cs);
+    const size_t smem = static_cast<size_t>(seg_vec) * 32;
+    if (smem <= 200 * 1024) {
+      static size_t attr_smem = 0;  // grows monotonically; benign race (idempotent attribute)
+      if (smem > attr_smem) {
+        NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024));
+        attr_smem = 200 * 1024;
+      }
+      cfg.gridDim = dim3(static_cast<unsigned>(B) * cs);
+      cfg.blockDim = dim3(kSmemThreads);
+      cfg.dynamicSmemBytes = smem;
+      attr[0].val.clusterDim.x = cs;
+      NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_smem_kernel, p, seg_vec));
+      return NRSE_OK;
+    }
+  }
   cfg.gridDim = dim3(static_cast<unsigned>(B) * kMixCluster);
   cfg.blockDim = dim3(kMixThreads);
   cfg.dynamicSmemBytes = 0;
-  cfg.stream = as_stream(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kMixCluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   if (vec) NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_kernel<true>, p));
   else NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_kernel<false>, p));
   return NRSE_OK;

@@ -70,6 +70,15 @@ __device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, fl
 __device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
+// 8-byte store into a peer CTA's shared memory that also performs complete_tx(8) on a peer mbarrier: the
+// receiver arms the barrier with expect_tx and simply waits on it -- no fence / L1 invalidate on either side.
+__device__ __forceinline__ void st_async_f2(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar_addr) {
+  const unsigned long long v =
+      static_cast<unsigned long long>(__float_as_uint(a)) | (static_cast<unsigned long long>(__float_as_uint(b)) << 32);
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(cluster_addr),
+               "l"(v), "r"(cluster_bar_addr)
+               : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }

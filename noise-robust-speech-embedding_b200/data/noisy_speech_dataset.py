@@ -1,0 +1,220 @@
+"""Data side of the BYOL hot path with the reference's surface (ref:src/data/noisy_speech_dataset.py).
+
+What changed relative to the reference, and why: the reference mixes and normalises every utterance on a DataLoader
+worker (``__getitem__``: ~20 tensor ops + numpy z-norm per item).  Here the workers only do I/O -- load, mono,
+crop/pad (ref:src/utils/audio_utils.py:9-62) and draw the noise file / SNR index -- and hand back RAW crops; the
+main process copies the batch to the GPU (pinned, non-blocking) and ``GpuBatchMixer`` runs the fused
+mix + peak-norm + z-norm kernel once per batch.  The batches the training loop sees are the reference's:
+``{"clean_input_values": [B,1,L] f32, "noisy_input_values": [B,1,L] f32, "snr": [B] int64}``
+(ref:src/data/noisy_speech_dataset.py:140-144), already on the device.
+
+The reference's retry policy (up to 5 re-draws when ``add_noise_to_speech`` / normalisation rejects an item,
+:56-148) is kept: the kernel reports one status word per row, the mixer re-draws the noise of rejected rows from the
+other rows of the batch, and rows that still fail after ``max_attempts`` are dropped from the batch.
+"""
+from __future__ import annotations
+
+import os
+import random
+import wave
+from typing import Dict, Iterator, List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Dataset, random_split
+
+from .. import ops
+from ..utils.logging_utils import logger
+
+AUDIO_EXTENSIONS = {".wav", ".flac", ".mp3"}
+
+
+def get_audio_files(directory: str) -> List[str]:
+    """ref:src/utils/audio_utils.py:65-72 (sorted, so that the seeded split is reproducible across file systems)."""
+    found = []
+    for root, _, files in os.walk(directory):
+        for f in files:
+            if os.path.splitext(f)[1].lower() in AUDIO_EXTENSIONS:
+                found.append(os.path.join(root, f))
+    return sorted(found)
+
+
+def _read_audio(path: str):
+    """-> (waveform [C, N] float32, sample_rate).  torchaudio when it works, stdlib ``wave`` for PCM WAV otherwise
+    (torchaudio.load needs TorchCodec, which is absent from this image: SURVEY.md fact 6)."""
+    try:
+        import torchaudio
+        wav, sr = torchaudio.load(path)
+        return wav.float(), int(sr)
+    except Exception:
+        pass
+    with wave.open(path, "rb") as w:
+        sr, ch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+        raw = w.readframes(n)
+    if width == 2:
+        data = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+    elif width == 4:
+        data = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+    elif width == 1:
+        data = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+    else:
+        raise ValueError(f"unsupported WAV sample width {width} in {path}")
+    return torch.from_numpy(data.reshape(-1, ch).T.copy()), int(sr)
+
+
+def load_and_process_audio(file_path: str, sample_rate: int = 16000, max_audio_length: float = 5.0,
+                           random_crop: bool = True) -> Optional[torch.Tensor]:
+    """Mono, resampled, cropped / zero-padded waveform [1, max_samples], or ``None`` for unusable audio
+    (same validity rules as ref:src/utils/audio_utils.py:9-62)."""
+    try:
+        max_samples = int(max_audio_length * sample_rate)
+        wav, sr = _read_audio(file_path)
+        if wav.shape[0] > 1:
+            wav = wav.mean(dim=0, keepdim=True)
+        if sr != sample_rate:
+            import torchaudio
+            wav = torchaudio.functional.resample(wav, sr, sample_rate)
+        n = wav.shape[1]
+        if n > max_samples:
+            start = random.randint(0, n - max_samples) if random_crop else 0
+            wav = wav[:, start:start + max_samples]
+        elif n < max_samples:
+            wav = torch.nn.functional.pad(wav, (0, max_samples - n))
+        if torch.isnan(wav).any() or float(wav.abs().max()) < 1e-8:
+            logger.warning("unusable audio (NaN or silent): %s", file_path)
+            return None
+        return wav.contiguous()
+    except Exception as e:  # noqa: BLE001 -- the reference logs and skips any loader failure
+        logger.error("error loading audio file %s: %s", file_path, e)
+        return None
+
+
+class NoiseRobustSpeechDataset(Dataset):
+    """Same constructor as the reference (ref:src/data/noisy_speech_dataset.py:12-41).  Items are RAW crops:
+    ``{"clean_wave": [1,L], "noise_wave": [1,L], "snr_idx": int, "snr": int}``; mixing happens on the GPU."""
+
+    def __init__(self, clean_data_path: str, noise_data_path: str, sample_rate: int = 16000,
+                 max_audio_length: float = 5.0, snr_range: Sequence[int] = (0, 5, 10, 15, 20),
+                 feature_extractor=None):
+        self.sample_rate = sample_rate
+        self.max_samples = int(max_audio_length * sample_rate)
+        self.snr_range = list(snr_range)
+        self.feature_extractor = feature_extractor  # kept for interface parity; z-norm is fused into the mix kernel
+        if feature_extractor is not None and not getattr(feature_extractor, "do_normalize", True):
+            raise ValueError("the fused mix kernel implements do_normalize=True (wavlm preprocessor setting)")
+        self.clean_files = get_audio_files(clean_data_path)
+        self.noise_files = get_audio_files(noise_data_path)
+        logger.info("Found %d clean files and %d noise files.", len(self.clean_files), len(self.noise_files))
+
+    def __len__(self) -> int:
+        return len(self.clean_files)
+
+    def _load(self, path: str) -> Optional[torch.Tensor]:
+        return load_and_process_audio(path, self.sample_rate, self.max_samples / self.sample_rate, random_crop=True)
+
+    def __getitem__(self, idx: int) -> Dict[str, object]:
+        max_attempts = 5  # ref:src/data/noisy_speech_dataset.py:56
+        for attempt in range(max_attempts):
+            clean = self._load(self.clean_files[idx])
+            if clean is None:
+                idx = (idx + 1) % len(self.clean_files)
+                continue
+            noise = self._load(self.noise_files[random.randint(0, len(self.noise_files) - 1)])
+            if noise is None:
+                continue
+            snr_idx = random.randrange(len(self.snr_range))
+            return {"clean_wave": clean, "noise_wave": noise, "snr_idx": snr_idx, "snr": int(self.snr_range[snr_idx])}
+        raise RuntimeError(f"no usable audio after {max_attempts} attempts starting at index {idx}")
+
+
+class TensorPairDataset(Dataset):
+    """In-memory clean/noise waveforms with SNR cycled by index -- the recipe of ref:test/create_mock_dataset.py
+    (clean randn, noise randn, snr = snr_range[i % n]) at real utterance lengths."""
+
+    def __init__(self, clean: torch.Tensor, noise: torch.Tensor, snr_range: Sequence[int]):
+        assert clean.dim() == 2 and noise.dim() == 2 and clean.shape[0] == noise.shape[0]
+        self.clean, self.noise, self.snr_range = clean.float(), noise.float(), list(snr_range)
+
+    def __len__(self) -> int:
+        return self.clean.shape[0]
+
+    def __getitem__(self, i: int):
+        k = i % len(self.snr_range)
+        return {"clean_wave": self.clean[i:i + 1], "noise_wave": self.noise[i:i + 1], "snr_idx": k,
+                "snr": int(self.snr_range[k])}
+
+
+class GpuBatchMixer:
+    """Raw batch -> reference-format batch on the device: one fused mix + peak-norm + z-norm launch per batch."""
+
+    def __init__(self, snr_range: Sequence[int], device, peak_norm: bool = True, max_attempts: int = 5):
+        self.snr_table = [float(v) for v in snr_range]
+        self.device = torch.device(device)
+        self.peak_norm = peak_norm
+        self.max_attempts = max_attempts
+
+    @torch.no_grad()
+    def __call__(self, raw: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        dev = self.device
+        clean = raw["clean_wave"].to(dev, non_blocking=True).flatten(1)
+        noise = raw["noise_wave"].to(dev, non_blocking=True).flatten(1)
+        snr_idx = torch.as_tensor(raw["snr_idx"]).to(dev, non_blocking=True).to(torch.int32)
+        snr = torch.as_tensor(raw["snr"]).to(dev, non_blocking=True).to(torch.int64)
+        c, n, status = ops.mix_normalize(clean, noise, snr_idx, self.snr_table, self.peak_norm)
+        bad = status != 0
+        attempt = 1
+        # one host read of the status vector per batch (the reference syncs ~20 times per ITEM)
+        while self.peak_norm and bool(bad.any()) and attempt < self.max_attempts:
+            rows = bad.nonzero().flatten()
+            logger.warning("mix rejected %d row(s) (status %s); re-drawing noise (attempt %d)", rows.numel(),
+                           sorted(set(status[rows].tolist())), attempt + 1)
+            donor = (rows + attempt) % clean.shape[0]  # another row's noise crop
+            c2, n2, st2 = ops.mix_normalize(clean[rows], noise[donor], snr_idx[rows], self.snr_table, True)
+            c[rows], n[rows], status[rows] = c2, n2, st2
+            bad = status != 0
+            attempt += 1
+        if self.peak_norm and bool(bad.any()):
+            keep = (~bad).nonzero().flatten()
+            logger.error("dropping %d row(s) that failed %d mix attempts", int(bad.sum()), self.max_attempts)
+            c, n, snr = c[keep], n[keep], snr[keep]
+        out = {"noisy_input_values": n.unsqueeze(1), "snr": snr}
+        if self.peak_norm:
+            out["clean_input_values"] = c.unsqueeze(1)
+        return out
+
+
+class MixedBatchLoader:
+    """Iterates a raw DataLoader and yields device batches in the reference's format (len / dataset forwarded)."""
+
+    def __init__(self, loader: DataLoader, mixer: GpuBatchMixer):
+        self.loader, self.mixer = loader, mixer
+        self.dataset = loader.dataset
+        self.batch_size = loader.batch_size
+
+    def __len__(self) -> int:
+        return len(self.loader)
+
+    def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
+        for raw in self.loader:
+            yield self.mixer(raw)
+
+
+def create_dataloaders(config, feature_extractor=None, device=None, dataset: Optional[Dataset] = None):
+    """(train_loader, val_loader) as in ref:src/data/noisy_speech_dataset.py:151-194: seeded ``random_split``,
+    ``pin_memory``, shuffle on train only.  ``device`` defaults to ``config['device']`` / cuda:0; ``dataset`` lets
+    callers substitute an in-memory dataset (tests, benchmarks)."""
+    data, training = config["data"], config["training"]
+    if dataset is None:
+        dataset = NoiseRobustSpeechDataset(data["clean_data_path"], data["noise_data_path"], data["sample_rate"],
+                                           data["max_audio_length"], data["snr_range"], feature_extractor)
+    val_size = int(len(dataset) * data.get("validation_ratio", 0.1))
+    train_size = len(dataset) - val_size
+    logger.info("Splitting dataset: %d training samples, %d validation samples", train_size, val_size)
+    train_ds, val_ds = random_split(dataset, [train_size, val_size],
+                                    generator=torch.Generator().manual_seed(training.get("seed", 42)))
+    device = device or config.get("device", "cuda:0")
+    mixer = GpuBatchMixer(data["snr_range"], device)
+    kw = dict(batch_size=training["batch_size"], num_workers=training.get("num_workers", 4), pin_memory=True)
+    train = DataLoader(train_ds, shuffle=True, **kw)
+    val = DataLoader(val_ds, shuffle=False, **kw)
+    return MixedBatchLoader(train, mixer), MixedBatchLoader(val, mixer)

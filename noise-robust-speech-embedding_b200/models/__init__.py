@@ -1,0 +1,4 @@
+from .byol import BYOLSpeechModel, byol_loss  # noqa: F401
+from .encoder import WavLMEncoder, install_b200_frontend, wavlm_large_config  # noqa: F401
+from .frontend import B200FeatureEncoder  # noqa: F401
+from .multi_layer_heads import PredictionHead, ProjectionHead  # noqa: F401

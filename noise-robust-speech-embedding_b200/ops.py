@@ -46,7 +46,9 @@ def _dtype_code(t: Tensor) -> int:
 # --------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("nrse::mix_normalize", mutates_args=())
 def _mix_normalize_op(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db: Sequence[float],
-                      peak_norm: bool) -> Tuple[Tensor, Tensor, Tensor]:
+                      mode: int) -> Tuple[Tensor, Tensor, Tensor]:
+    # mode: 1 = BYOL (peak-norm + z-norm, two outputs), 0 = emotion (z-norm only), 2 = raw mix (no normalisation)
+    peak_norm = mode == 1
     _need_cuda(clean, noise, snr_idx)
     lib = _lib.load()
     B, L = clean.shape
@@ -56,14 +58,14 @@ def _mix_normalize_op(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db: Seq
     table = (C.c_double * len(snr_db))(*[float(v) for v in snr_db])
     check(lib.nrse_mix_normalize_f32(_ptr(clean), _ptr(noise), _ptr(snr_idx), table, len(snr_db),
                                      _ptr(clean_out) if peak_norm else None, _ptr(noisy_out), _ptr(status),
-                                     B, L, noise.shape[1], 1 if peak_norm else 0, _stream()),
+                                     B, L, noise.shape[1], int(mode), _stream()),
           "nrse_mix_normalize_f32")
     return clean_out, noisy_out, status
 
 
 @_mix_normalize_op.register_fake
-def _(clean, noise, snr_idx, snr_db, peak_norm):
-    return (torch.empty_like(clean) if peak_norm else clean.new_empty(0), torch.empty_like(clean),
+def _(clean, noise, snr_idx, snr_db, mode):
+    return (torch.empty_like(clean) if mode == 1 else clean.new_empty(0), torch.empty_like(clean),
             clean.new_empty(clean.shape[0], dtype=torch.int32))
 
 
@@ -82,8 +84,22 @@ def mix_normalize(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db_table: S
     clean = clean.contiguous().float()
     noise = noise.contiguous().float()
     snr_idx = snr_idx.to(device=clean.device, dtype=torch.int32).contiguous()
-    c, n, st = _mix_normalize_op(clean, noise, snr_idx, [float(v) for v in snr_db_table], bool(peak_norm))
+    c, n, st = _mix_normalize_op(clean, noise, snr_idx, [float(v) for v in snr_db_table], 1 if peak_norm else 0)
     return (c if peak_norm else None), n, st
+
+
+def mix_status_name(code: int) -> str:
+    return _lib.load().nrse_mix_status_name(int(code)).decode()
+
+
+def mix_raw(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db_table: Sequence[float]) -> Tuple[Tensor, Tensor]:
+    """``add_noise_to_speech`` alone (ref:src/data/augment.py:4-66), batched: returns (speech + scale*noise [B,L],
+    status [B]); rows with status != 0 are the ones for which the reference returns ``None``."""
+    clean = clean.contiguous().float()
+    noise = noise.contiguous().float()
+    snr_idx = snr_idx.to(device=clean.device, dtype=torch.int32).contiguous()
+    _, n, st = _mix_normalize_op(clean, noise, snr_idx, [float(v) for v in snr_db_table], 2)
+    return n, st
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -335,6 +351,14 @@ def conv_frontend(x: Tensor, conv_weights: Sequence[Tensor], gammas: Sequence[Op
 
 def set_frontend_variant(variant: int) -> None:
     check(_lib.load().nrse_conv_frontend_set_variant(int(variant)), "nrse_conv_frontend_set_variant")
+
+
+def set_mix_variant(variant: int) -> None:
+    check(_lib.load().nrse_mix_set_variant(int(variant)), "nrse_mix_set_variant")
+
+
+def set_layer0_variant(variant: int) -> None:
+    check(_lib.load().nrse_conv_frontend_set_layer0_variant(int(variant)), "nrse_conv_frontend_set_layer0_variant")
 
 
 # ---- per-layer entry points (parity tests, callers that own their activation buffers) ---------------------------

@@ -21,8 +21,11 @@ def _layer_params(layers, dev):
     return w, g, b
 
 
-@pytest.mark.parametrize("mode", ["layer", "group"])
-def test_layer0_vs_oracle(dev, mode):
+@pytest.mark.parametrize("mode,l0,variant", [("layer", 0, 2), ("layer", 1, 1), ("layer", 1, 2), ("group", 0, 2)],
+                         ids=["layer-simt", "layer-tc-v1", "layer-tc-v2", "group-simt"])
+def test_layer0_vs_oracle(dev, mode, l0, variant):
+    ops.set_layer0_variant(l0)
+    ops.set_frontend_variant(variant)
     layers = synthetic.frontend_weights(mode, seed=2)
     x = synthetic.waveforms(3, 4000, seed=8)[0] * 10  # roughly unit variance like a z-normed waveform
     ref = oracle.conv_frontend(torch.from_numpy(x), layers, mode, return_all=True)[0]  # [B,512,T0]
@@ -33,6 +36,23 @@ def test_layer0_vs_oracle(dev, mode):
     got = out[:, :T[0]].float().transpose(1, 2).cpu().numpy()
     assert rel_err(got, ref.numpy()) < 6e-3   # bf16 output rounding (2^-9) dominates
     assert not out[:, T[0]:].any()            # pitch padding is zero-filled
+    ops.set_layer0_variant(1)
+    ops.set_frontend_variant(2)
+
+
+def test_layer0_tc_is_fp32_class(dev):
+    """The hi/lo-split tensor-core layer 0 must agree with the SIMT fp32 kernel to bf16 output rounding (1 ulp)."""
+    layers = synthetic.frontend_weights("layer", seed=6)
+    x = synthetic.waveforms(4, 16000, seed=2)[0] * 10
+    w, g, b = _layer_params(layers, dev)
+    xd = torch.from_numpy(x).to(dev)
+    ops.set_layer0_variant(0)
+    ref = ops.conv_layer0(xd, w[0], g[0], b[0], "layer").float()
+    ops.set_layer0_variant(1)
+    got = ops.conv_layer0(xd, w[0], g[0], b[0], "layer").float()
+    diff = (got - ref).abs()
+    assert float(diff.max()) <= 2 ** -7 * float(ref.abs().max())      # never more than ~1 bf16 ulp of the range
+    assert float((diff > 0).float().mean()) < 0.05                     # and almost always bit-identical
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=["v1", "v2"])

@@ -12,6 +12,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-6  # north star: mixing within 1e-6 relative (norm-relative)
 
 
+@pytest.fixture(params=[1, 0], ids=["smem", "l2"], autouse=True)
+def mix_variant(request):
+    """Every test runs on both kernels: shared-memory-resident rows (default) and the re-read-from-L2 kernel."""
+    ops.set_mix_variant(request.param)
+    yield request.param
+    ops.set_mix_variant(1)
+
+
 def _run(dev, clean, noise, snr_idx, table, peak_norm=True):
     c, n, st = ops.mix_normalize(torch.from_numpy(np.ascontiguousarray(clean)).to(dev),
                                  torch.from_numpy(np.ascontiguousarray(noise)).to(dev),
@@ -64,7 +72,8 @@ def test_golden_edge_statuses(dev, golden):
 
 @pytest.mark.parametrize("B,L,Ln,peak", [(5, 4000, 4000, True), (3, 4001, 4001, True), (4, 3998, 1500, True),
                                          (3, 6000, 7003, False), (2, 401, 401, True), (7, 16000, 16000, False),
-                                         (2, 64000, 64000, True)])
+                                         (2, 64000, 64000, True), (2, 192000, 192000, True), (3, 32000, 32004, False),
+                                         (1, 240000, 240000, True), (9, 8, 8, True)])
 def test_random_vs_oracle(dev, B, L, Ln, peak):
     clean, noise, snr_idx, table = synthetic.waveforms(B, L, seed=100 + L % 97, n_noise=Ln)
     c_ref, n_ref, st_ref = oracle.mix_normalize_batch(clean, noise, snr_idx, table, peak_norm=peak)
