@@ -1,0 +1,9 @@
+from .byol import (  # noqa: F401
+    EarlyStopping,
+    byol_step,
+    check_audio_tensor,
+    evaluate_embedding_similarity,
+    train_one_epoch,
+    validate_model,
+)
+from .distributed import init_distributed, wrap_data_parallel  # noqa: F401

@@ -14,7 +14,7 @@ copied.  Shims, all explicit below:
   3. ``load_and_process_audio`` -> in-memory tensors (torchaudio cannot decode in this image).
 Outputs (float arrays kept small; inputs are stored too so fixtures are self-contained):
   mix_byol.npz, mix_emotion.npz, mix_edge.npz, byol_loss.npz, ema.npz, frontend_layer.npz,
-  frontend_group.npz
+  frontend_group.npz, byol_step.npz, byol_state_dict_keys.json
 """
 import os
 import random
@@ -230,6 +230,66 @@ def gen_frontend(norm_mode, B=2, L=4000, seed=41):
     print("frontend", norm_mode, y.shape, float(np.abs(y).mean()))
 
 
+def gen_byol_step(seed=51, B=4, L=4000):
+    """The reference's BYOLSpeechModel (+ the mean-pool shim of SURVEY.md fact 3, applied to the reference's own
+    ``WavLMEncoder.forward``) on a tiny transformer with the FULL-SIZE conv feature encoder: state-dict keys/shapes,
+    an eval-mode forward + byol_loss, and one deterministic training step (train mode with dropout / layerdrop /
+    SpecAugment disabled in the config): loss, clipped-gradient AdamW update, EMA (ref:train_byol.py:56-74)."""
+    import json
+    cfg = small_wavlm_config("layer")
+    for k in ("hidden_dropout", "activation_dropout", "attention_dropout", "feat_proj_dropout", "final_dropout",
+              "layerdrop", "mask_time_prob", "mask_feature_prob"):
+        setattr(cfg, k, 0.0)
+    cfg.apply_spec_augment = False
+    orig_from = ref_encoder_mod.AutoModel.from_pretrained
+    orig_fwd = ref_encoder_mod.WavLMEncoder.forward
+    ref_encoder_mod.AutoModel.from_pretrained = staticmethod(lambda name: WavLMModel(cfg))
+    ref_encoder_mod.WavLMEncoder.forward = lambda self, x, attention_mask=None: orig_fwd(self, x, attention_mask).mean(dim=1)
+    try:
+        torch.manual_seed(seed)
+        model = RefBYOL({"model": {"name": "shim", "projection_dim": 96, "prediction_dim": 128, "ema_decay": 0.99}})
+        keys = {k: list(v.shape) for k, v in model.state_dict().items()}
+        with open(os.path.join(HERE, "byol_state_dict_keys.json"), "w") as f:
+            json.dump(keys, f, indent=0, sort_keys=True)
+        clean, noise, snr_idx, table = synthetic.waveforms(B, L, seed=seed)
+        import oracle
+        c, n, st = oracle.mix_normalize_batch(clean, noise, snr_idx, table, peak_norm=True)
+        assert not st.any()
+        c, n = c[:, None], n[:, None]
+        out = {"clean_in": c.numpy(), "noisy_in": n.numpy(), "seed": np.array(seed)}
+        model.eval()
+        with torch.no_grad():
+            op, tp = model(c, n)
+            out["eval_online_pred"], out["eval_target_proj"] = op.numpy(), tp.numpy()
+            out["eval_loss"] = ref_byol_loss(op, tp).numpy()
+            out["eval_online_emb"] = model.online_encoder(c).numpy()
+        model.train()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
+        op, tp = model(c, n)
+        loss = ref_byol_loss(op, tp)
+        opt.zero_grad()
+        loss.backward()
+        gnorm = torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        opt.step()
+        model._update_target_network()
+        out["train_loss"] = loss.detach().numpy()
+        out["train_grad_norm"] = gnorm.numpy()
+        sd = model.state_dict()
+        for k in ("online_encoder.model.feature_extractor.conv_layers.0.conv.weight",
+                  "online_encoder.model.feature_extractor.conv_layers.3.conv.weight",
+                  "online_encoder.model.feature_extractor.conv_layers.6.layer_norm.weight",
+                  "target_encoder.model.feature_extractor.conv_layers.3.conv.weight",
+                  "target_encoder.model.encoder.layers.1.feed_forward.output_dense.weight",
+                  "target_projector.layers.3.weight", "online_predictor.layers.6.bias"):
+            out["after::" + k] = sd[k].numpy().reshape(-1)[:2048].copy()
+        np.savez_compressed(os.path.join(HERE, "byol_step.npz"), **out)
+        print("byol_step: keys", len(keys), "eval loss", float(out["eval_loss"]), "train loss", float(loss),
+              "grad norm", float(gnorm))
+    finally:
+        ref_encoder_mod.AutoModel.from_pretrained = orig_from
+        ref_encoder_mod.WavLMEncoder.forward = orig_fwd
+
+
 if __name__ == "__main__":
     print("transformers", transformers.__version__, "torch", torch.__version__, "numpy", np.__version__)
     gen_mix_byol()
@@ -239,4 +299,5 @@ if __name__ == "__main__":
     gen_ema()
     gen_frontend("layer")
     gen_frontend("group")
+    gen_byol_step()
     print("sizes:", {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")})

@@ -1,0 +1,162 @@
+"""GPU tests of the drop-in modules: the B200 feature encoder inside HF WavLM, BYOLSpeechModel forward / train step
+against fixtures produced by the reference (tests/golden/make_golden.py::gen_byol_step), the EMA update, the batch
+mixer with its retry policy, ``add_noise_to_speech``, and the train/validate loops."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import rel_err
+from nrse_b200 import ops
+from nrse_b200.data import GpuBatchMixer, MixedBatchLoader, TensorPairDataset, add_noise_to_speech
+from nrse_b200.models import B200FeatureEncoder, BYOLSpeechModel, WavLMEncoder, byol_loss
+from nrse_b200.train import byol_step, check_audio_tensor, evaluate_embedding_similarity, train_one_epoch, validate_model
+from nrse_b200.utils import synthetic
+from test_host_modules import byol_config, golden_config, small_config
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("norm", ["layer", "group"])
+def test_feature_encoder_matches_hf_module(dev, norm):
+    from transformers.models.wavlm.modeling_wavlm import WavLMFeatureEncoder
+    torch.manual_seed(1)
+    hf = WavLMFeatureEncoder(small_config(norm)).to(dev).eval()
+    x = torch.randn(3, 8000, device=dev)
+    with torch.no_grad():
+        want = hf(x)
+        mine = B200FeatureEncoder.convert(hf)
+        got = mine(x)
+        got3 = mine(x[:, None])
+    assert got.shape == want.shape == (3, 512, 24) and got.dtype == torch.float32
+    assert got.stride(1) == 1                     # a transposed view of the channels-last kernel output
+    assert torch.equal(got, got3)
+    assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < 1e-2
+
+
+def _golden_model(dev, g):
+    torch.manual_seed(int(g["seed"]))             # same construction order => same init as the reference run
+    return BYOLSpeechModel(byol_config(golden_config())).to(dev)
+
+
+def test_byol_eval_forward_matches_reference(dev, golden):
+    g = golden("byol_step")
+    model = _golden_model(dev, g).eval()
+    c, n = torch.from_numpy(g["clean_in"]).to(dev), torch.from_numpy(g["noisy_in"]).to(dev)
+    with torch.no_grad():
+        emb = model._pool(model.online_encoder(c))
+        op, tp = model(c, n)
+        loss = byol_loss(op, tp)
+    assert rel_err(emb.cpu().numpy(), g["eval_online_emb"]) < 1e-2
+    assert rel_err(op.cpu().numpy(), g["eval_online_pred"]) < 1e-2
+    assert rel_err(tp.cpu().numpy(), g["eval_target_proj"]) < 1e-2
+    assert abs(loss.item() - float(g["eval_loss"])) < 1e-2 * float(g["eval_loss"])
+
+
+def test_byol_train_step_matches_reference(dev, golden):
+    g = golden("byol_step")
+    model = _golden_model(dev, g).train()
+    c, n = torch.from_numpy(g["clean_in"]).to(dev), torch.from_numpy(g["noisy_in"]).to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    online_before = [p.detach().clone() for p in model.online_encoder.parameters()]
+    target_before = [p.detach().clone() for p in model.target_encoder.parameters()]
+    loss = byol_step(model, c, n, opt)
+    assert abs(loss.item() - float(g["train_loss"])) < 1e-2 * float(g["train_loss"])
+    sd = model.state_dict()
+    for key in [k for k in g.files if k.startswith("after::")]:
+        got = sd[key[len("after::"):]].detach().reshape(-1)[:2048].cpu().numpy()
+        # first Adam step moves every weight by ~lr*sign(grad): allow sign flips of near-zero gradients (2*lr), and
+        # require the bulk to agree
+        assert np.abs(got - g[key]).max() <= 2.5e-3
+        assert np.mean(np.abs(got - g[key]) < 1e-4) > 0.8, key
+    # EMA relation holds bit-exactly on the model's own tensors
+    online_after = list(model.online_encoder.parameters())
+    want = oracle.ema_update([p.detach().cpu() for p in online_after], [t.cpu() for t in target_before], 0.99)
+    for w, t in zip(want, model.target_encoder.parameters()):
+        assert np.array_equal(w.numpy(), t.detach().cpu().numpy())
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(online_before, online_after))
+    # frontend gradients reached the conv weights (recompute-based backward)
+    model.zero_grad()
+    op, tp = model(c, n)
+    byol_loss(op, tp).backward()
+    w3 = model.online_encoder.model.feature_extractor.conv_layers[3].conv.weight
+    assert w3.grad is not None and float(w3.grad.abs().sum()) > 0
+
+
+def test_ema_update_is_in_place_and_survives_device_moves(dev):
+    model = BYOLSpeechModel(byol_config(golden_config())).to(dev)
+    with torch.no_grad():
+        for p in model.online_encoder.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+    ptrs = [p.data_ptr() for p in model.target_encoder.parameters()]
+    t0 = [p.detach().cpu().clone() for p in model.target_projector.parameters()]
+    model._update_target_network()
+    assert ptrs == [p.data_ptr() for p in model.target_encoder.parameters()]
+    want = oracle.ema_update([p.detach().cpu() for p in model.online_projector.parameters()], t0, 0.99)
+    for w, t in zip(want, model.target_projector.parameters()):
+        assert np.array_equal(w.numpy(), t.detach().cpu().numpy())
+    n_chunks = model._ema_plan.n_chunks
+    model.float()  # _apply => the plan is dropped and rebuilt
+    assert model._ema_plan is None
+    model._update_target_network()
+    assert model._ema_plan.n_chunks == n_chunks
+
+
+def test_gpu_batch_mixer_and_retry(dev):
+    B, L = 6, 4000
+    clean, noise, _, table = synthetic.waveforms(B, L, seed=4)
+    noise[2] = 0.0                                   # noise power < 1e-10 -> rejected (status 4) -> re-drawn
+    ds = TensorPairDataset(torch.from_numpy(clean), torch.from_numpy(noise), [2, 5, 10, 15, 20])
+    loader = torch.utils.data.DataLoader(ds, batch_size=B, shuffle=False)
+    mixed = MixedBatchLoader(loader, GpuBatchMixer([2, 5, 10, 15, 20], dev))
+    (batch,) = list(mixed)
+    assert batch["clean_input_values"].shape == (B, 1, L) and batch["noisy_input_values"].shape == (B, 1, L)
+    assert batch["clean_input_values"].device.type == "cuda" and batch["snr"].tolist() == [2, 5, 10, 15, 20, 2]
+    snr_idx = np.arange(B) % 5
+    c_ref, n_ref, st = oracle.mix_normalize_batch(clean, noise, snr_idx, table)
+    assert st.tolist() == [0, 0, 4, 0, 0, 0]
+    for b in (0, 1, 3, 4, 5):
+        assert rel_err(batch["noisy_input_values"][b, 0].cpu().numpy(), n_ref[b].numpy()) < 1e-6
+    # row 2 was re-mixed with the next row's noise
+    _, n2, st2 = oracle.mix_normalize_batch(clean[2:3], noise[3:4], snr_idx[2:3], table)
+    assert st2.tolist() == [0]
+    assert rel_err(batch["noisy_input_values"][2, 0].cpu().numpy(), n2[0].numpy()) < 1e-6
+
+
+def test_add_noise_to_speech_dropin(dev, golden):
+    g = golden("mix_edge")
+    for b in range(8):
+        s, n = torch.from_numpy(g["clean"][b:b + 1]), torch.from_numpy(g["noise"][b:b + 1])
+        got = add_noise_to_speech(s.to(dev), n.to(dev), 10)
+        want = oracle.add_noise_to_speech(s, n, 10)
+        assert (got is None) == (want is None) == bool(g["is_none"][b])
+        if want is not None:
+            assert got.shape == (1, 4000) and got.is_cuda
+            assert rel_err(got.cpu().numpy(), want.numpy()) < 1e-6
+    # CPU tensors are accepted (computed on the GPU, returned on the CPU); short noise is tiled
+    s, n = torch.from_numpy(g["clean"][6:7]), torch.from_numpy(g["noise"][6:7, :1500])
+    got = add_noise_to_speech(s, n, 5)
+    assert got.device.type == "cpu"
+    assert rel_err(got.numpy(), oracle.add_noise_to_speech(s, n, 5).numpy()) < 1e-6
+
+
+def test_train_and_validate_loops(dev):
+    torch.manual_seed(0)
+    cfg = byol_config(golden_config())
+    cfg.update({"data": {"snr_range": [2, 5, 10]}, "logging": {"level": "INFO"}})
+    model = BYOLSpeechModel(cfg).to(dev)
+    clean, noise, _, _ = synthetic.waveforms(8, 4000, seed=9)
+    ds = TensorPairDataset(torch.from_numpy(clean), torch.from_numpy(noise), [2, 5, 10])
+    loader = MixedBatchLoader(torch.utils.data.DataLoader(ds, batch_size=4), GpuBatchMixer([2, 5, 10], dev))
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=4)
+    l1 = train_one_epoch(model, loader, opt, sched, dev, cfg, check_interval=1)
+    l2 = train_one_epoch(model, loader, opt, sched, dev, cfg)
+    assert 0.0 < l1 <= 4.0 and 0.0 < l2 <= 4.0
+    sims = evaluate_embedding_similarity(model, loader, dev, cfg)
+    assert sorted(sims) == [2, 5, 10] and all(-1.0 <= v <= 1.0 for v in sims.values())
+    val_loss, metrics = validate_model(model, loader, dev, cfg)
+    assert 0.0 <= val_loss <= 4.0 and metrics["val_similarities"] == sims and not model.training
+    assert check_audio_tensor(torch.ones(4, device=dev), "ones", cfg)
+    assert not check_audio_tensor(torch.tensor([1.0, float("nan")], device=dev), "nan", cfg)
+    assert not check_audio_tensor(torch.zeros(4, device=dev), "zeros", cfg)

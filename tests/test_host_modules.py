@@ -1,0 +1,216 @@
+"""CPU tests of the host-side mirror of the reference surface: config, logging, dataset I/O, module/state-dict
+contract, and the data-parallel plumbing over a 2-rank gloo group.  No kernel is launched here."""
+import json
+import os
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from nrse_b200.config import get_config, load_config
+from nrse_b200.data import MixedBatchLoader, NoiseRobustSpeechDataset, TensorPairDataset, create_dataloaders
+from nrse_b200.data.noisy_speech_dataset import load_and_process_audio
+from nrse_b200.models import B200FeatureEncoder, BYOLSpeechModel, WavLMEncoder, wavlm_large_config
+from nrse_b200.train import EarlyStopping
+from nrse_b200.utils.setup_utils import set_seed
+
+
+def small_config(norm="layer"):
+    from transformers import WavLMConfig
+    return WavLMConfig(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+                       feat_extract_norm=norm, do_stable_layer_norm=(norm == "layer"), conv_bias=False,
+                       num_conv_pos_embeddings=16, num_conv_pos_embedding_groups=4)
+
+
+def golden_config():
+    """The configuration tests/golden/make_golden.py::gen_byol_step used: deterministic in train mode."""
+    cfg = small_config("layer")
+    for k in ("hidden_dropout", "activation_dropout", "attention_dropout", "feat_proj_dropout", "final_dropout",
+              "layerdrop", "mask_time_prob", "mask_feature_prob"):
+        setattr(cfg, k, 0.0)
+    cfg.apply_spec_augment = False
+    return cfg
+
+
+def byol_config(wavlm=None):
+    return {"model": {"name": wavlm or golden_config(), "projection_dim": 96, "prediction_dim": 128, "ema_decay": 0.99}}
+
+
+def test_state_dict_contract_matches_reference():
+    """Keys and shapes of BYOLSpeechModel.state_dict() are those of the reference's model (fixture written by
+    tests/golden/make_golden.py from the unmodified reference): checkpoints round-trip both ways."""
+    want = json.load(open(os.path.join(GOLDEN, "byol_state_dict_keys.json")))
+    model = BYOLSpeechModel(byol_config())
+    got = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert got == want
+    assert isinstance(model.online_encoder.model.feature_extractor, B200FeatureEncoder)
+    assert all(not p.requires_grad for p in model.target_encoder.parameters())
+    assert all(not p.requires_grad for p in model.target_projector.parameters())
+    assert all(p.requires_grad for p in model.online_predictor.parameters())
+    for o, t in zip(model.online_encoder.parameters(), model.target_encoder.parameters()):
+        assert torch.equal(o, t)  # target starts as a copy of the online weights
+    assert model.get_encoder() is model.online_encoder
+    # the emotion fine-tune loop unfreezes by substring match on parameter names (ref:src/models/emotion.py:126-129)
+    names = [n for n, _ in model.online_encoder.model.named_parameters()]
+    assert any("conv_layers.3" in n and "layers.3" in n for n in names)
+
+
+def test_frontend_conversion_keeps_parameters_and_modes():
+    from transformers.models.wavlm.modeling_wavlm import WavLMFeatureEncoder
+    for norm in ("layer", "group"):
+        fe = WavLMFeatureEncoder(small_config(norm))
+        before = {k: v.clone() for k, v in fe.state_dict().items()}
+        conv = B200FeatureEncoder.convert(fe)
+        assert conv is fe and isinstance(fe, B200FeatureEncoder) and fe.norm_mode == norm
+        assert list(fe.state_dict().keys()) == list(before.keys())
+        assert all(torch.equal(fe.state_dict()[k], v) for k, v in before.items())
+        fe._freeze_parameters()
+        assert not any(p.requires_grad for p in fe.parameters()) and fe._requires_grad is False
+    from transformers import WavLMConfig
+    with pytest.raises(ValueError):
+        B200FeatureEncoder.convert(WavLMFeatureEncoder(WavLMConfig(conv_bias=True)))
+    cfg = wavlm_large_config()
+    assert cfg.hidden_size == 1024 and cfg.feat_extract_norm == "layer" and tuple(cfg.conv_kernel) == (10, 3, 3, 3, 3, 2, 2)
+
+
+def test_encoder_wrapper_surface_cpu():
+    """frontend='hf' keeps the stock feature extractor, so the wrapper can be exercised without a GPU: it must behave
+    like the reference's WavLMEncoder (squeeze [B,1,L], ignore the mask, return last_hidden_state)."""
+    torch.manual_seed(0)
+    enc = WavLMEncoder(small_config(), frontend="hf").eval()
+    x = torch.randn(2, 1, 2000)
+    with torch.no_grad():
+        a = enc(x)
+        b = enc(x.squeeze(1), attention_mask=torch.ones(2, 2000))
+        c = enc.model(x.squeeze(1)).last_hidden_state
+    assert a.shape == (2, 6, 64) and enc.output_dim == 64
+    assert torch.equal(a, b) and torch.equal(a, c)
+    with pytest.raises(ValueError):
+        WavLMEncoder(small_config(), frontend="nope")
+
+
+def test_b200_frontend_refuses_cpu():
+    from nrse_b200._lib import NrseError
+    enc = WavLMEncoder(small_config(), frontend="b200").eval()
+    with pytest.raises(NrseError), torch.no_grad():
+        enc(torch.randn(1, 2000))
+
+
+def test_config_loader_and_overrides(tmp_path):
+    y = tmp_path / "c.yaml"
+    y.write_text("model:\n  name: m\n  ema_decay: 0.997\ntraining:\n  batch_size: 36\n  learning_rate: 1.0e-5\n"
+                 "data:\n  snr_range: [2, 5]\n")
+    cfg = load_config(str(y))
+    assert cfg["model"]["ema_decay"] == 0.997 and cfg["data"]["snr_range"] == [2, 5]
+    cfg = get_config(["--config", str(y), "--device", "cuda:1", "--batch_size", "8", "--epochs", "3", "--lr", "0.01"])
+    assert cfg["device"] == "cuda:1" and cfg["training"]["batch_size"] == 8
+    assert cfg["training"]["num_epochs"] == 3 and cfg["training"]["learning_rate"] == 0.01
+
+
+def test_early_stopping_and_seed():
+    es = EarlyStopping(patience=2, min_delta=0.01, mode="min")
+    assert [es(v) for v in (1.0, 0.9, 0.895, 0.894)] == [False, False, False, True]
+    es = EarlyStopping(patience=1, mode="max")
+    assert [es(v) for v in (0.5, 0.6, 0.6)] == [False, False, True]
+    set_seed(3); a = (torch.rand(2), np.random.rand())
+    set_seed(3); b = (torch.rand(2), np.random.rand())
+    assert torch.equal(a[0], b[0]) and a[1] == b[1]
+
+
+def _write_wav(path, samples, sr=16000):
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(sr)
+        w.writeframes((np.clip(samples, -1, 1) * 32767).astype("<i2").tobytes())
+
+
+def test_dataset_raw_items_from_wav_files(tmp_path):
+    rs = np.random.RandomState(0)
+    cdir, ndir = tmp_path / "clean", tmp_path / "noise"
+    cdir.mkdir(); ndir.mkdir()
+    _write_wav(cdir / "a.wav", 0.1 * rs.standard_normal(20000))
+    _write_wav(cdir / "b.wav", 0.1 * rs.standard_normal(3000))      # shorter than max length: zero padded
+    _write_wav(cdir / "silent.wav", np.zeros(8000))                  # rejected, dataset moves on to the next file
+    _write_wav(ndir / "n.wav", 0.3 * rs.standard_normal(9000))
+    (cdir / "notes.txt").write_text("x")
+    ds = NoiseRobustSpeechDataset(str(cdir), str(ndir), 16000, 0.5, [2, 5, 10])
+    assert len(ds) == 3 and ds.max_samples == 8000
+    set_seed(1)
+    for i in range(3):
+        item = ds[i]
+        assert item["clean_wave"].shape == (1, 8000) and item["noise_wave"].shape == (1, 8000)
+        assert item["snr"] in (2, 5, 10) and ds.snr_range[item["snr_idx"]] == item["snr"]
+        assert float(item["clean_wave"].abs().max()) > 1e-3
+    short = load_and_process_audio(str(cdir / "b.wav"), 16000, 0.5)
+    assert short.shape == (1, 8000) and not short[0, 3000:].any()
+    assert load_and_process_audio(str(cdir / "silent.wav"), 16000, 0.5) is None
+    assert load_and_process_audio(str(cdir / "missing.wav"), 16000, 0.5) is None
+
+
+def test_create_dataloaders_split_is_seeded():
+    clean, noise = torch.randn(20, 800), torch.randn(20, 800)
+    ds = TensorPairDataset(clean, noise, [2, 5, 10, 15, 20])
+    cfg = {"data": {"snr_range": [2, 5, 10, 15, 20], "validation_ratio": 0.15, "clean_data_path": "", "noise_data_path": "",
+                    "sample_rate": 16000, "max_audio_length": 0.05},
+           "training": {"batch_size": 4, "num_workers": 0, "seed": 42}, "device": "cpu"}
+    tr, va = create_dataloaders(cfg, dataset=ds)
+    tr2, va2 = create_dataloaders(cfg, dataset=ds)
+    assert isinstance(tr, MixedBatchLoader) and len(tr.dataset) == 17 and len(va.dataset) == 3 and len(tr) == 5
+    assert list(va.dataset.indices) == list(va2.dataset.indices)
+    item = ds[7]
+    assert item["snr"] == [2, 5, 10, 15, 20][7 % 5] and item["clean_wave"].shape == (1, 800)
+
+
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import oracle
+    from nrse_b200.train import init_distributed, wrap_data_parallel
+    r, w, lr = init_distributed("gloo")
+    assert (r, w, lr) == (rank, world, rank)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(32, 48), torch.nn.ReLU(), torch.nn.Linear(48, 16))
+    frozen = torch.nn.Linear(32, 16)  # stands for the target branch: no grad, never all-reduced
+    for p in frozen.parameters():
+        p.requires_grad = False
+    model = torch.nn.ModuleDict({"online": net, "target": frozen})
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(8, 32, generator=g)
+    shard = x[rank * 4:(rank + 1) * 4]  # batch sharded across ranks, no data-path collective
+
+    class Both(torch.nn.Module):  # online + (frozen) target branch behind one forward, like BYOLSpeechModel
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, v):
+            return self.m["online"](v), self.m["target"](v)
+
+    both = wrap_data_parallel(Both(model), torch.device("cpu"))
+    p, z = both(shard)
+    oracle.byol_loss(p, z.detach()).backward()
+    grads = torch.cat([q.grad.flatten() for q in net.parameters()])
+    # single-process reference on the full batch: per-rank means average to the global mean for equal shards
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(32, 48), torch.nn.ReLU(), torch.nn.Linear(48, 16))
+    oracle.byol_loss(ref(x), frozen(x).detach()).backward()
+    ref_grads = torch.cat([q.grad.flatten() for q in ref.parameters()])
+    ok = torch.allclose(grads, ref_grads, rtol=1e-5, atol=1e-7) and all(q.grad is None for q in frozen.parameters())
+    gathered = [torch.zeros_like(grads) for _ in range(world)]
+    dist.all_gather(gathered, grads)
+    same = all(torch.equal(gathered[0], t) for t in gathered)  # every rank holds the same averaged gradient
+    out[rank] = bool(ok and same)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_data_parallel_equivalence():
+    import torch.multiprocessing as mp
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: True, 1: True}
