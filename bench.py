@@ -236,11 +236,18 @@ def main_gpu(args):
     pooled_h = torch.empty(2, BATCH, 512, dtype=torch.float32).pin_memory()
     status_h = torch.empty(BATCH, dtype=torch.int32).pin_memory()
 
+    from nrse_b200.data import DevicePrefetcher
+    prefetch = DevicePrefetcher(dev, depth=2)
+    host_batch = {"clean": clean_h, "noise": noise_h, "snr": snr_h}
+    prefetch.put(host_batch)  # pipeline prologue: the first batch is in flight before step 0
+
     def step_e2e():
-        c = clean_h.to(dev, non_blocking=True)
-        n = noise_h.to(dev, non_blocking=True)
-        s = snr_h.to(dev, non_blocking=True)
-        y_o, y_t, st = hot_path(c, n, s)
+        # every step enqueues ONE H2D copy (the next step's inputs, on the copy stream, overlapping this step's
+        # kernels), runs the hot path on the batch copied one step earlier, and reads the result back to the host
+        prefetch.put(host_batch)
+        b = prefetch.get()
+        y_o, y_t, st = hot_path(b["clean"], b["noise"], b["snr"])
+        prefetch.release()
         pooled_h[0].copy_(y_o.float().mean(dim=1), non_blocking=True)  # the [B,H]-pooled result the BYOL heads consume
         pooled_h[1].copy_(y_t.float().mean(dim=1), non_blocking=True)
         status_h.copy_(st, non_blocking=True)
@@ -265,7 +272,10 @@ def main_gpu(args):
                    "weights": "random init, WavLM-large conv shapes", "parallelism": f"dp{world} (no data-path collective)",
                    "l2": "per-step working set 3.4 GB >> 126 MB L2: inputs are evicted between timed iterations"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e_total / args.steps},
+                "ms_per_step": ms_e2e_total / args.steps,
+                "how": "pinned host batch -> DevicePrefetcher (copy stream, depth 2: H2D of step i+1 overlaps the kernels "
+                       "of step i) -> ops.mix_normalize -> ops.conv_frontend x2 -> D2H of pooled features + status, "
+                       "host sync every step"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
     }

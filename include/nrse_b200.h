@@ -76,8 +76,11 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
                            float* clean_out, float* noisy_out, int32_t* status,
                            int B, int L, int L_noise, int peak_norm, nrse_stream_t stream);
 const char* nrse_mix_status_name(int status_code);
-/* 1 (default): rows staged once in shared memory by bulk async copies (used when 16-byte aligned, L % 4 == 0,
- * L_noise >= L and the row fits the cluster's shared memory); 0: always use the re-read-from-L2 kernel. */
+/* 3 (default): streaming -- one 1024-thread CTA (or a small cluster for small batches) per row, pass 1 from HBM, passes
+ * 2-3 from L2, streaming stores; 2: persistent clusters, rows double-buffered in shared memory by bulk async copies (the next row streams in
+ * while the current one is processed); 1: one row per cluster, single stage; 0: always the re-read-from-L2 kernel.
+ * 1, 2 and 3 need 16-byte aligned rows, L % 4 == 0, L_noise >= L and a row that fits the cluster's shared memory;
+ * otherwise the library falls back to the next lower variant by itself. */
 int nrse_mix_set_variant(int variant);
 
 /* ---------------------------------------------------------------------------------------------

@@ -325,79 +325,96 @@ __global__ void __launch_bounds__(kMixThreads) mix_normalize_kernel(const MixPar
 // first chunk lands); the second and third passes then run out of shared memory, so HBM/L2 see exactly the
 // algorithmic traffic (read 8 B, write 8 B per sample) whatever the batch size.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSmemThreads = 256;
+constexpr int kSmemThreads = 512;
 constexpr int kSmemWarps = kSmemThreads / 32;
 constexpr int kSmemMaxCluster = 8;
 constexpr int kSmemChunks = 4;
 
-template <int kN>
-__device__ __forceinline__ void block_sum_n(double (&v)[kN], double* scratch, int n_warps) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < kN; ++k) v[k] = warp_sum(v[k]);
-  __syncthreads();
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < kN; ++k) scratch[warp * kN + k] = v[k];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < kN; ++k) {
-    double s = 0.0;
-    for (int w = 0; w < n_warps; ++w) s += scratch[w * kN + k];
-    v[k] = s;
-  }
+// packed fp32x2 helpers (FFMA2 / FMUL2 / FADD2): same IEEE rounding per lane as the scalar instructions
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 f2_make(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_split(f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float f2_hsum(f2 v) {
+  float a, b;
+  f2_split(v, a, b);
+  return a + b;
+}
+// NaN-propagating |.| max: a NaN anywhere in the row surfaces in the reduced peak
+__device__ __forceinline__ float absmax_nan(float m, float x) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(m), "f"(fabsf(x)));
+  return r;
 }
 
-__device__ __forceinline__ float block_max_n(float v, float* scratch, int n_warps) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  v = warp_max(v);
-  __syncthreads();
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  float m = scratch[0];
-  for (int w = 1; w < n_warps; ++w) m = fmaxf(m, scratch[w]);
-  return m;
-}
+// Scalars every thread needs after a phase; computed once by thread 0 (fp64 divisions are ~40 instructions each)
+struct MixScalars {
+  float scale, inv_dc, inv_dn, a_c, b_c, a_n, b_n;
+  int st1;  // verdict of add_noise_to_speech (after pass 1)
+  int st;   // final verdict
+};
 
+// kStages = 2: PERSISTENT clusters -- cluster k processes rows k, k + n_clusters, ... and, while it runs the three
+// shared-memory passes of row i, the bulk copies of row i+1 are already streaming into the other stage, so HBM stays
+// busy through the compute / synchronisation phases (with one stage every CTA of the grid loads, computes and stores
+// in lock-step and the memory system idles a third of the time).  kStages = 1: one row per cluster (long rows whose
+// two stages would not fit in shared memory).
+template <int kStages>
 __global__ void __launch_bounds__(kSmemThreads) mix_normalize_smem_kernel(const MixParams p, int seg_vec) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = static_cast<int>(cluster.block_rank());
   const int cs = static_cast<int>(cluster.num_blocks());
-  const int row = blockIdx.x / cs;
-  const int tid = threadIdx.x;
+  const int cluster_id = blockIdx.x / cs;
+  const int n_clusters = gridDim.x / cs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   extern __shared__ __align__(128) unsigned char mix_smem[];
-  __shared__ __align__(8) unsigned long long bars[kSmemChunks];
-  __shared__ double red_d[kSmemWarps * 5];
-  __shared__ float red_f[kSmemWarps];
-  __shared__ double xch1_d[kSmemMaxCluster][5];
-  __shared__ float xch1_f[kSmemMaxCluster][2];
-  __shared__ float xch2_f[kSmemMaxCluster];
-  __shared__ unsigned xch2_u[kSmemMaxCluster];
+  __shared__ __align__(8) unsigned long long bars[kStages][kSmemChunks];
+  __shared__ double red_d[kSmemWarps][5];
+  __shared__ float red_f[kSmemWarps][2];
+  __shared__ double xch1_d[2][kSmemMaxCluster][5];
+  __shared__ float xch1_f[2][kSmemMaxCluster][2];
+  __shared__ float xch2_f[2][kSmemMaxCluster];
+  __shared__ MixScalars sc;
 
   const int L = p.L;
   const int nvec = L >> 2;  // L % 4 == 0 on this path
   const int v_begin = min(nvec, rank * seg_vec);
   const int v_end = min(nvec, v_begin + seg_vec);
   const int n_my = v_end - v_begin;
-  float4* s_c = reinterpret_cast<float4*>(mix_smem);
-  float4* s_n = s_c + seg_vec;
   const int chunk_vec = (seg_vec + kSmemChunks - 1) / kSmemChunks;
+  auto stage_c = [&](int stage) { return reinterpret_cast<float4*>(mix_smem) + static_cast<size_t>(stage) * 2 * seg_vec; };
 
-  // ---- bulk async loads: global -> shared, one mbarrier per chunk -------------------------------------------
-  if (tid == 0) {
-    for (int c = 0; c < kSmemChunks; ++c) {
-      const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[c]));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  // bulk async loads of one row segment: global -> shared, one mbarrier per chunk (issued by thread 0)
+  auto issue_loads = [&](int row, int stage) {
+    float4* d_c = stage_c(stage);
+    float4* d_n = d_c + seg_vec;
     const float4* g_c = reinterpret_cast<const float4*>(p.clean + static_cast<size_t>(row) * L) + v_begin;
     const float4* g_n = reinterpret_cast<const float4*>(p.noise + static_cast<size_t>(row) * p.Ln) + v_begin;
     for (int c = 0; c < kSmemChunks; ++c) {
       const int c0 = c * chunk_vec;
       const int len = min(chunk_vec, n_my - c0);
-      const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[c]));
+      const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[stage][c]));
       if (len <= 0) {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
         continue;
@@ -405,196 +422,551 @@ __global__ void __launch_bounds__(kSmemThreads) mix_normalize_smem_kernel(const 
       const unsigned bytes = static_cast<unsigned>(len) * 16u;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       static_cast<unsigned>(__cvta_generic_to_shared(s_c + c0))),
+                       static_cast<unsigned>(__cvta_generic_to_shared(d_c + c0))),
                    "l"(g_c + c0), "r"(bytes), "r"(bar)
                    : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       static_cast<unsigned>(__cvta_generic_to_shared(s_n + c0))),
+                       static_cast<unsigned>(__cvta_generic_to_shared(d_n + c0))),
                    "l"(g_n + c0), "r"(bytes), "r"(bar)
                    : "memory");
     }
-  }
-  __syncthreads();  // barrier inits visible to the waiting threads
+  };
 
-  // ---- pass 1 (shared memory, chunk by chunk as the copies land) ---------------------------------------------
-  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  float cmax = 0.f, nmax_in = 0.f;
-  for (int c = 0; c < kSmemChunks; ++c) {
-    const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[c]));
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
-        "@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}\n" ::"r"(bar)
-        : "memory");
-    const int c_end = min(n_my, (c + 1) * chunk_vec);
-    for (int v0 = c * chunk_vec + tid; v0 < c_end; v0 += 2 * kSmemThreads) {
-      float f[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int v = v0 + u * kSmemThreads;
-        if (v < c_end) {
-          const float4 cv = s_c[v], nv = s_n[v];
-          const float cc[4] = {cv.x, cv.y, cv.z, cv.w}, nn[4] = {nv.x, nv.y, nv.z, nv.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            f[0] = fmaf(cc[j], cc[j], f[0]);
-            f[1] = fmaf(nn[j], nn[j], f[1]);
-            f[2] += cc[j];
-            f[3] += nn[j];
-            f[4] = fmaf(cc[j], nn[j], f[4]);
-          }
-          cmax = absmax4(cmax, cc);
-          nmax_in = absmax4(nmax_in, nn);
+  if (tid == 0) {
+    for (int st = 0; st < kStages; ++st)
+      for (int c = 0; c < kSmemChunks; ++c) {
+        const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[st][c]));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (cluster_id < p.B) issue_loads(cluster_id, 0);
+  }
+
+  int it = 0;
+  for (int row = cluster_id; row < p.B; row += n_clusters, ++it) {
+    const int stage = it % kStages;
+    const unsigned parity = static_cast<unsigned>(it / kStages) & 1u;
+    const int xb = it & 1;  // exchange buffers alternate: a fast CTA may already be one row ahead of a slow one
+    float4* s_c = stage_c(stage);
+    float4* s_n = s_c + seg_vec;
+
+    // every thread is done with the other stage (previous row) and with `sc`: it may be refilled / rewritten
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (kStages == 2 && tid == 0 && row + n_clusters < p.B) issue_loads(row + n_clusters, stage ^ 1);
+
+    // ---- pass 1 (shared memory, chunk by chunk as the copies land): packed fp32 partial sums per thread ----------
+    const f2 zero2 = f2_make(0.f, 0.f);
+    f2 a_cc = zero2, a_nn = zero2, a_c1 = zero2, a_n1 = zero2, a_cn = zero2;
+    float cmax = 0.f, nmax_in = 0.f;
+    for (int c = 0; c < kSmemChunks; ++c) {
+      const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[stage][c]));
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+          "@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}\n" ::"r"(bar), "r"(parity)
+          : "memory");
+      const int c_end = min(n_my, (c + 1) * chunk_vec);
+  #pragma unroll 2
+      for (int v = c * chunk_vec + tid; v < c_end; v += kSmemThreads) {
+        const float4 cv = s_c[v], nv = s_n[v];
+        const f2 c01 = f2_make(cv.x, cv.y), c23 = f2_make(cv.z, cv.w);
+        const f2 n01 = f2_make(nv.x, nv.y), n23 = f2_make(nv.z, nv.w);
+        a_cc = f2_fma(c01, c01, a_cc); a_cc = f2_fma(c23, c23, a_cc);
+        a_nn = f2_fma(n01, n01, a_nn); a_nn = f2_fma(n23, n23, a_nn);
+        a_cn = f2_fma(c01, n01, a_cn); a_cn = f2_fma(c23, n23, a_cn);
+        a_c1 = f2_add(a_c1, c01); a_c1 = f2_add(a_c1, c23);
+        a_n1 = f2_add(a_n1, n01); a_n1 = f2_add(a_n1, n23);
+        cmax = fmaxf(fmaxf(cmax, fmaxf(fabsf(cv.x), fabsf(cv.y))), fmaxf(fabsf(cv.z), fabsf(cv.w)));
+        nmax_in = fmaxf(fmaxf(nmax_in, fmaxf(fabsf(nv.x), fabsf(nv.y))), fmaxf(fabsf(nv.z), fabsf(nv.w)));
+      }
+    }
+    // one merged block reduction: per-thread fp32 partials (a few dozen samples each) are combined in fp64
+    {
+      double acc[5] = {static_cast<double>(f2_hsum(a_cc)), static_cast<double>(f2_hsum(a_nn)),
+                       static_cast<double>(f2_hsum(a_c1)), static_cast<double>(f2_hsum(a_n1)),
+                       static_cast<double>(f2_hsum(a_cn))};
+  #pragma unroll
+      for (int k = 0; k < 5; ++k) acc[k] = warp_sum(acc[k]);
+      cmax = warp_max(cmax);
+      nmax_in = warp_max(nmax_in);
+      if (lane == 0) {
+  #pragma unroll
+        for (int k = 0; k < 5; ++k) red_d[warp][k] = acc[k];
+        red_f[warp][0] = cmax;
+        red_f[warp][1] = nmax_in;
+      }
+      __syncthreads();
+      if (tid < cs) {  // thread t sends this CTA's totals to CTA t of the cluster (all-to-all through DSMEM)
+        double tot[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        float m0 = 0.f, m1 = 0.f;
+        for (int w = 0; w < kSmemWarps; ++w) {
+  #pragma unroll
+          for (int k = 0; k < 5; ++k) tot[k] += red_d[w][k];
+          m0 = fmaxf(m0, red_f[w][0]);
+          m1 = fmaxf(m1, red_f[w][1]);
         }
+        double* dst_d = cluster.map_shared_rank(&xch1_d[xb][rank][0], tid);
+        float* dst_f = cluster.map_shared_rank(&xch1_f[xb][rank][0], tid);
+  #pragma unroll
+        for (int k = 0; k < 5; ++k) dst_d[k] = tot[k];
+        dst_f[0] = m0;
+        dst_f[1] = m1;
       }
-#pragma unroll
-      for (int k = 0; k < 5; ++k) acc[k] += static_cast<double>(f[k]);
-    }
-  }
-  block_sum_n<5>(acc, red_d, kSmemWarps);
-  cmax = block_max_n(cmax, red_f, kSmemWarps);
-  nmax_in = block_max_n(nmax_in, red_f, kSmemWarps);
-  if (tid < cs) {
-    double* dst_d = cluster.map_shared_rank(&xch1_d[rank][0], tid);
-    float* dst_f = cluster.map_shared_rank(&xch1_f[rank][0], tid);
-#pragma unroll
-    for (int k = 0; k < 5; ++k) dst_d[k] = acc[k];
-    dst_f[0] = cmax;
-    dst_f[1] = nmax_in;
-  }
-  cluster.sync();
-  double s_cc = 0.0, s_nn = 0.0, s_c1 = 0.0, s_n1 = 0.0, s_cn = 0.0;
-  cmax = 0.f;
-  nmax_in = 0.f;
-  for (int r = 0; r < cs; ++r) {
-    s_cc += xch1_d[r][0];
-    s_nn += xch1_d[r][1];
-    s_c1 += xch1_d[r][2];
-    s_n1 += xch1_d[r][3];
-    s_cn += xch1_d[r][4];
-    cmax = fmaxf(cmax, xch1_f[r][0]);
-    nmax_in = fmaxf(nmax_in, xch1_f[r][1]);
-  }
-
-  const double Ld = static_cast<double>(L);
-  const float Ps = static_cast<float>(s_cc / Ld);
-  const float Pn = static_cast<float>(s_nn / Ld);
-  int idx = p.snr_idx[row];
-  idx = idx < 0 ? 0 : (idx >= p.n_snr ? p.n_snr - 1 : idx);
-  const float scale = __fsqrt_rn(__fdiv_rn(Ps, __fmul_rn(Pn, p.snr_lin[idx])));
-  int st = 0;
-  if (isnan(Ps)) st = 1;
-  else if (isnan(Pn)) st = 2;
-  else if (Ps < 1e-10f) st = 3;
-  else if (Pn < 1e-10f) st = 4;
-  else if (isinf(scale) || isnan(scale)) st = 5;
-  else if (scale > 1e6f) st = 6;
-  else if (isinf(nmax_in)) st = 7;
-
-  float nmax = 0.f;
-  if (p.peak_norm && st == 0) {
-    // ---- pass 2 (shared memory): mix in place (noise slot <- noisy), peak of the mix, NaN flags ---------------
-    unsigned flags = 0;
-    for (int v = tid; v < n_my; v += kSmemThreads) {
-      const float4 cv = s_c[v], nv = s_n[v];
-      const float cc[4] = {cv.x, cv.y, cv.z, cv.w}, nn[4] = {nv.x, nv.y, nv.z, nv.w};
-      float y[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float sn = __fmul_rn(nn[j], scale);
-        y[j] = __fadd_rn(cc[j], sn);
-        flags |= (isnan(sn) ? 1u : 0u) | (isnan(y[j]) ? 2u : 0u);
-      }
-      nmax = absmax4(nmax, y);
-      s_n[v] = make_float4(y[0], y[1], y[2], y[3]);
-    }
-    nmax = block_max_n(nmax, red_f, kSmemWarps);
-    flags = __syncthreads_or(static_cast<int>(flags));
-    if (tid < cs) {
-      *cluster.map_shared_rank(&xch2_f[rank], tid) = nmax;
-      *cluster.map_shared_rank(&xch2_u[rank], tid) = flags;
     }
     cluster.sync();
-    nmax = 0.f;
-    flags = 0;
-    for (int r = 0; r < cs; ++r) {
-      nmax = fmaxf(nmax, xch2_f[r]);
-      flags |= xch2_u[r];
-    }
-    if (flags & 1u) st = 7;
-    else if (flags & 2u) st = 8;
-    else if (cmax < 1e-8f) st = 9;
-    else if (nmax < 1e-8f) st = 10;
-    else if (isinf(cmax)) st = 11;
-    else if (isinf(nmax)) st = 12;
-  }
 
-  const double s = static_cast<double>(scale);
-  float a_c = 0.f, b_c = 0.f, a_n = 0.f, b_n = 0.f, inv_dc = 1.f, inv_dn = 1.f;
-  const bool mixed = (st == 0);
-  if (p.peak_norm) {
-    if (st == 0) {
-      const double dc = static_cast<double>(__fadd_rn(cmax, 1e-8f));
-      const double dn = static_cast<double>(__fadd_rn(nmax, 1e-8f));
-      const double mc = s_c1 / Ld / dc;
-      const double vc = s_cc / Ld / (dc * dc) - mc * mc;
-      const double mn = (s_c1 + s * s_n1) / Ld / dn;
-      const double vn = (s_cc + 2.0 * s * s_cn + s * s * s_nn) / Ld / (dn * dn) - mn * mn;
-      const float vcf = static_cast<float>(vc), vnf = static_cast<float>(vn);
-      const float mcf = static_cast<float>(mc), mnf = static_cast<float>(mn);
-      if (!isfinite(mcf) || !isfinite(vcf)) st = 13;
-      else if (!isfinite(mnf) || !isfinite(vnf)) st = 14;
-      inv_dc = static_cast<float>(1.0 / dc);
-      inv_dn = static_cast<float>(1.0 / dn);
-      a_c = mcf;
-      b_c = 1.0f / __fsqrt_rn(__fadd_rn(vcf, 1e-7f));
-      a_n = mnf;
-      b_n = 1.0f / __fsqrt_rn(__fadd_rn(vnf, 1e-7f));
-    }
-  } else {
-    const double sw = mixed ? (s_c1 + s * s_n1) : s_c1;
-    const double sww = mixed ? (s_cc + 2.0 * s * s_cn + s * s * s_nn) : s_cc;
-    const double mn = sw / Ld;
-    const double vn = sww / Ld - mn * mn;
-    a_n = static_cast<float>(mn);
-    b_n = 1.0f / __fsqrt_rn(__fadd_rn(static_cast<float>(vn), 1e-7f));
-    if (p.raw) {  // (y - 0) * 1 is exact: the output is the mixed signal itself
-      a_n = 0.f;
-      b_n = 1.f;
-    }
-  }
-  if (rank == 0 && tid == 0) p.status[row] = st;
-
-  // ---- output pass: shared memory -> global, 128-bit coalesced stores ------------------------------------------
-  float4* co = p.clean_out ? reinterpret_cast<float4*>(p.clean_out + static_cast<size_t>(row) * L) + v_begin : nullptr;
-  float4* no = reinterpret_cast<float4*>(p.noisy_out + static_cast<size_t>(row) * L) + v_begin;
-  if (p.peak_norm && st != 0) {
-    for (int v = tid; v < n_my; v += kSmemThreads) {
-      co[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      no[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    return;
-  }
-  for (int v = tid; v < n_my; v += kSmemThreads) {
-    const float4 cv = s_c[v], yv = s_n[v];  // BYOL mode: the noise slot already holds the mixed signal
-    const float cc[4] = {cv.x, cv.y, cv.z, cv.w}, yy[4] = {yv.x, yv.y, yv.z, yv.w};
-    float oc[4], on[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (p.peak_norm) {
-        oc[j] = (__fmul_rn(cc[j], inv_dc) - a_c) * b_c;
-        on[j] = (__fmul_rn(yy[j], inv_dn) - a_n) * b_n;
-      } else {
-        const float y = mixed ? __fadd_rn(cc[j], __fmul_rn(yy[j], scale)) : cc[j];
-        on[j] = (y - a_n) * b_n;
+    // ---- add_noise_to_speech decisions (augment.py:7-51): thread 0, fixed summation order => same on every CTA ----
+    double s_cc = 0.0, s_nn = 0.0, s_c1 = 0.0, s_n1 = 0.0, s_cn = 0.0;
+    if (tid == 0) {
+      cmax = 0.f;
+      nmax_in = 0.f;
+      for (int r = 0; r < cs; ++r) {
+        s_cc += xch1_d[xb][r][0];
+        s_nn += xch1_d[xb][r][1];
+        s_c1 += xch1_d[xb][r][2];
+        s_n1 += xch1_d[xb][r][3];
+        s_cn += xch1_d[xb][r][4];
+        cmax = fmaxf(cmax, xch1_f[xb][r][0]);
+        nmax_in = fmaxf(nmax_in, xch1_f[xb][r][1]);
       }
+      const double Ld = static_cast<double>(L);
+      const float Ps = static_cast<float>(s_cc / Ld);
+      const float Pn = static_cast<float>(s_nn / Ld);
+      int idx = p.snr_idx[row];
+      idx = idx < 0 ? 0 : (idx >= p.n_snr ? p.n_snr - 1 : idx);
+      const float scale = __fsqrt_rn(__fdiv_rn(Ps, __fmul_rn(Pn, p.snr_lin[idx])));
+      int st = 0;
+      if (isnan(Ps)) st = 1;
+      else if (isnan(Pn)) st = 2;
+      else if (Ps < 1e-10f) st = 3;
+      else if (Pn < 1e-10f) st = 4;
+      else if (isinf(scale) || isnan(scale)) st = 5;
+      else if (scale > 1e6f) st = 6;
+      else if (isinf(nmax_in)) st = 7;  // inf * 0 -> NaN in noise * scale (augment.py:56)
+      sc.scale = scale;
+      sc.st1 = st;
     }
-    if (p.peak_norm) co[v] = make_float4(oc[0], oc[1], oc[2], oc[3]);
-    no[v] = make_float4(on[0], on[1], on[2], on[3]);
+    __syncthreads();
+    const float scale = sc.scale;
+    const int st1 = sc.st1;
+
+    float nmax = 0.f;
+    if (p.peak_norm && st1 == 0) {
+      // ---- pass 2 (shared memory): mix in place (noise slot <- noisy, augment.py:54,60), NaN-propagating peak ------
+      const f2 s2 = f2_make(scale, scale);
+  #pragma unroll 2
+      for (int v = tid; v < n_my; v += kSmemThreads) {
+        const float4 cv = s_c[v], nv = s_n[v];
+        float y0, y1, y2, y3;
+        f2_split(f2_add(f2_make(cv.x, cv.y), f2_mul(f2_make(nv.x, nv.y), s2)), y0, y1);  // mul and add round separately
+        f2_split(f2_add(f2_make(cv.z, cv.w), f2_mul(f2_make(nv.z, nv.w), s2)), y2, y3);
+        nmax = absmax_nan(absmax_nan(absmax_nan(absmax_nan(nmax, y0), y1), y2), y3);
+        s_n[v] = make_float4(y0, y1, y2, y3);
+      }
+  #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float other = __shfl_xor_sync(0xffffffffu, nmax, o);
+        asm("max.NaN.f32 %0, %0, %1;" : "+f"(nmax) : "f"(other));
+      }
+      if (lane == 0) red_f[warp][0] = nmax;
+      __syncthreads();
+      if (tid < cs) {
+        float m = red_f[0][0];
+        for (int w = 1; w < kSmemWarps; ++w) asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(red_f[w][0]));
+        *cluster.map_shared_rank(&xch2_f[xb][rank], tid) = m;
+      }
+      cluster.sync();
+    }
+
+    // ---- statistics of the normalised views, from the pass-1 sums (thread 0) ----------------------------------------
+    if (tid == 0) {
+      int st = st1;
+      const bool mixed0 = st == 0;
+      const double s = static_cast<double>(scale);
+      const double Ld = static_cast<double>(L);
+      float a_c = 0.f, b_c = 0.f, a_n = 0.f, b_n = 0.f, inv_dc = 1.f, inv_dn = 1.f;
+      if (p.peak_norm) {
+        if (st == 0) {
+          nmax = xch2_f[xb][0];
+          for (int r = 1; r < cs; ++r) asm("max.NaN.f32 %0, %0, %1;" : "+f"(nmax) : "f"(xch2_f[xb][r]));
+          if (isnan(nmax)) st = 8;                     // NaN in speech + scaled noise (augment.py:62)
+          else if (cmax < 1e-8f) st = 9;               // noisy_speech_dataset.py:95
+          else if (nmax < 1e-8f) st = 10;              // :99
+          else if (isinf(cmax)) st = 11;               // inf / inf -> NaN after the peak division (:107)
+          else if (isinf(nmax)) st = 12;               // (:111)
+        }
+        if (st == 0) {
+          const double dc = static_cast<double>(__fadd_rn(cmax, 1e-8f));
+          const double dn = static_cast<double>(__fadd_rn(nmax, 1e-8f));
+          const double mc = s_c1 / Ld / dc;
+          const double vc = s_cc / Ld / (dc * dc) - mc * mc;
+          const double mn = (s_c1 + s * s_n1) / Ld / dn;
+          const double vn = (s_cc + 2.0 * s * s_cn + s * s * s_nn) / Ld / (dn * dn) - mn * mn;
+          const float vcf = static_cast<float>(vc), vnf = static_cast<float>(vn);
+          const float mcf = static_cast<float>(mc), mnf = static_cast<float>(mn);
+          if (!isfinite(mcf) || !isfinite(vcf)) st = 13;
+          else if (!isfinite(mnf) || !isfinite(vnf)) st = 14;
+          inv_dc = static_cast<float>(1.0 / dc);
+          inv_dn = static_cast<float>(1.0 / dn);
+          a_c = mcf;
+          b_c = 1.0f / __fsqrt_rn(__fadd_rn(vcf, 1e-7f));
+          a_n = mnf;
+          b_n = 1.0f / __fsqrt_rn(__fadd_rn(vnf, 1e-7f));
+        }
+      } else {
+        const double sw = mixed0 ? (s_c1 + s * s_n1) : s_c1;
+        const double sww = mixed0 ? (s_cc + 2.0 * s * s_cn + s * s * s_nn) : s_cc;
+        const double mn = sw / Ld;
+        const double vn = sww / Ld - mn * mn;
+        a_n = static_cast<float>(mn);
+        b_n = 1.0f / __fsqrt_rn(__fadd_rn(static_cast<float>(vn), 1e-7f));
+        if (p.raw) {  // (y - 0) * 1 is exact: the output is the mixed signal itself
+          a_n = 0.f;
+          b_n = 1.f;
+        }
+      }
+      sc.inv_dc = inv_dc; sc.inv_dn = inv_dn;
+      sc.a_c = a_c; sc.b_c = b_c; sc.a_n = a_n; sc.b_n = b_n;
+      sc.st = st;
+      if (rank == 0) p.status[row] = st;
+    }
+    __syncthreads();
+    const int st = sc.st;
+    const bool mixed = st1 == 0;
+
+    // ---- output pass: shared memory -> global, 128-bit coalesced stores ------------------------------------------
+    float4* co = p.clean_out ? reinterpret_cast<float4*>(p.clean_out + static_cast<size_t>(row) * L) + v_begin : nullptr;
+    float4* no = reinterpret_cast<float4*>(p.noisy_out + static_cast<size_t>(row) * L) + v_begin;
+    if (p.peak_norm && st != 0) {
+      for (int v = tid; v < n_my; v += kSmemThreads) {
+        co[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        no[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      continue;
+    }
+    const f2 nac2 = f2_make(-sc.a_c, -sc.a_c), bc2 = f2_make(sc.b_c, sc.b_c), idc2 = f2_make(sc.inv_dc, sc.inv_dc);
+    const f2 nan2 = f2_make(-sc.a_n, -sc.a_n), bn2 = f2_make(sc.b_n, sc.b_n), idn2 = f2_make(sc.inv_dn, sc.inv_dn);
+    const f2 s2 = f2_make(scale, scale);
+  #pragma unroll 2
+    for (int v = tid; v < n_my; v += kSmemThreads) {
+      const float4 cv = s_c[v], yv = s_n[v];  // BYOL mode: the noise slot already holds the mixed signal
+      const f2 c01 = f2_make(cv.x, cv.y), c23 = f2_make(cv.z, cv.w);
+      f2 y01 = f2_make(yv.x, yv.y), y23 = f2_make(yv.z, yv.w);
+      float4 on;
+      if (p.peak_norm) {
+        float4 oc;
+        f2_split(f2_mul(f2_add(f2_mul(c01, idc2), nac2), bc2), oc.x, oc.y);  // (c/dc - mean) / std, 3 roundings
+        f2_split(f2_mul(f2_add(f2_mul(c23, idc2), nac2), bc2), oc.z, oc.w);
+        f2_split(f2_mul(f2_add(f2_mul(y01, idn2), nan2), bn2), on.x, on.y);
+        f2_split(f2_mul(f2_add(f2_mul(y23, idn2), nan2), bn2), on.z, on.w);
+        co[v] = oc;
+      } else {
+        if (mixed) {
+          y01 = f2_add(c01, f2_mul(y01, s2));
+          y23 = f2_add(c23, f2_mul(y23, s2));
+        } else {
+          y01 = c01;
+          y23 = c23;
+        }
+        f2_split(f2_mul(f2_add(y01, nan2), bn2), on.x, on.y);
+        f2_split(f2_mul(f2_add(y23, nan2), bn2), on.z, on.w);
+      }
+      no[v] = on;
+    }
   }
 }
 
-int g_mix_variant = 1;  // 1: shared-memory-resident rows (default), 0: re-read from L2
+// ---------------------------------------------------------------------------------------------------------
+// Streaming variant: ONE large CTA (or a small cluster when the batch cannot fill the machine) per utterance,
+// reading the row three times -- pass 1 from HBM, passes 2 and 3 from L2 (the rows in flight, <= 148 x 512 KB,
+// fit the 126 MB L2; outputs are written with streaming stores so they do not evict them).  Unlike the
+// shared-memory variants the number of rows in flight is not capped by shared-memory capacity, which is what
+// bounds those at ~60 % of HBM peak (per-row latency ~7 us x 6.5 TB/s needs > 90 rows resident).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kStreamThreads = 1024;
+constexpr int kStreamWarps = kStreamThreads / 32;
+constexpr int kStreamUnroll = 4;
+
+__device__ __forceinline__ void st_stream_cs_f4(float4* p, const float4& v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_l2_f4(const float4* p) {  // skip L1 (re-read comes from L2), keep in L2
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+__global__ void __launch_bounds__(kStreamThreads, 1) mix_normalize_stream_kernel(const MixParams p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int cs = static_cast<int>(cluster.num_blocks());
+  const int row = blockIdx.x / cs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  __shared__ double red_d[kStreamWarps][5];
+  __shared__ float red_f[kStreamWarps][2];
+  __shared__ double xch1_d[kSmemMaxCluster][5];
+  __shared__ float xch1_f[kSmemMaxCluster][2];
+  __shared__ float xch2_f[kSmemMaxCluster];
+  __shared__ MixScalars sc;
+
+  const int L = p.L;
+  const int nvec = L >> 2;
+  const int seg = (nvec + cs - 1) / cs;
+  const int v_begin = min(nvec, rank * seg);
+  const int v_end = min(nvec, v_begin + seg);
+  const float4* g_c = reinterpret_cast<const float4*>(p.clean + static_cast<size_t>(row) * L);
+  const float4* g_n = reinterpret_cast<const float4*>(p.noise + static_cast<size_t>(row) * p.Ln);
+
+  // ---- pass 1 (HBM) -------------------------------------------------------------------------------------------
+  const f2 zero2 = f2_make(0.f, 0.f);
+  f2 a_cc = zero2, a_nn = zero2, a_c1 = zero2, a_n1 = zero2, a_cn = zero2;
+  float cmax = 0.f, nmax_in = 0.f;
+  for (int v0 = v_begin + tid; v0 < v_end; v0 += kStreamUnroll * kStreamThreads) {
+    float4 cv[kStreamUnroll], nv[kStreamUnroll];
+#pragma unroll
+    for (int u = 0; u < kStreamUnroll; ++u) {
+      const int v = v0 + u * kStreamThreads;
+      if (v < v_end) {
+        cv[u] = ld_l2_f4(g_c + v);
+        nv[u] = ld_l2_f4(g_n + v);
+      } else {
+        cv[u] = nv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kStreamUnroll; ++u) {
+      const f2 c01 = f2_make(cv[u].x, cv[u].y), c23 = f2_make(cv[u].z, cv[u].w);
+      const f2 n01 = f2_make(nv[u].x, nv[u].y), n23 = f2_make(nv[u].z, nv[u].w);
+      a_cc = f2_fma(c01, c01, a_cc); a_cc = f2_fma(c23, c23, a_cc);
+      a_nn = f2_fma(n01, n01, a_nn); a_nn = f2_fma(n23, n23, a_nn);
+      a_cn = f2_fma(c01, n01, a_cn); a_cn = f2_fma(c23, n23, a_cn);
+      a_c1 = f2_add(a_c1, c01); a_c1 = f2_add(a_c1, c23);
+      a_n1 = f2_add(a_n1, n01); a_n1 = f2_add(a_n1, n23);
+      cmax = fmaxf(fmaxf(cmax, fmaxf(fabsf(cv[u].x), fabsf(cv[u].y))), fmaxf(fabsf(cv[u].z), fabsf(cv[u].w)));
+      nmax_in = fmaxf(fmaxf(nmax_in, fmaxf(fabsf(nv[u].x), fabsf(nv[u].y))), fmaxf(fabsf(nv[u].z), fabsf(nv[u].w)));
+    }
+  }
+  {
+    double acc[5] = {static_cast<double>(f2_hsum(a_cc)), static_cast<double>(f2_hsum(a_nn)),
+                     static_cast<double>(f2_hsum(a_c1)), static_cast<double>(f2_hsum(a_n1)),
+                     static_cast<double>(f2_hsum(a_cn))};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[k] = warp_sum(acc[k]);
+    cmax = warp_max(cmax);
+    nmax_in = warp_max(nmax_in);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) red_d[warp][k] = acc[k];
+      red_f[warp][0] = cmax;
+      red_f[warp][1] = nmax_in;
+    }
+    __syncthreads();
+    if (tid < cs) {
+      double tot[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      float m0 = 0.f, m1 = 0.f;
+      for (int w = 0; w < kStreamWarps; ++w) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) tot[k] += red_d[w][k];
+        m0 = fmaxf(m0, red_f[w][0]);
+        m1 = fmaxf(m1, red_f[w][1]);
+      }
+      double* dst_d = cluster.map_shared_rank(&xch1_d[rank][0], tid);
+      float* dst_f = cluster.map_shared_rank(&xch1_f[rank][0], tid);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) dst_d[k] = tot[k];
+      dst_f[0] = m0;
+      dst_f[1] = m1;
+    }
+  }
+  if (cs > 1) cluster.sync();
+  else __syncthreads();
+
+  double s_cc = 0.0, s_nn = 0.0, s_c1 = 0.0, s_n1 = 0.0, s_cn = 0.0;
+  const double inv_L = 1.0 / static_cast<double>(L);
+  if (tid == 0) {
+    cmax = 0.f;
+    nmax_in = 0.f;
+    for (int r = 0; r < cs; ++r) {
+      s_cc += xch1_d[r][0];
+      s_nn += xch1_d[r][1];
+      s_c1 += xch1_d[r][2];
+      s_n1 += xch1_d[r][3];
+      s_cn += xch1_d[r][4];
+      cmax = fmaxf(cmax, xch1_f[r][0]);
+      nmax_in = fmaxf(nmax_in, xch1_f[r][1]);
+    }
+    const float Ps = static_cast<float>(s_cc * inv_L);
+    const float Pn = static_cast<float>(s_nn * inv_L);
+    int idx = p.snr_idx[row];
+    idx = idx < 0 ? 0 : (idx >= p.n_snr ? p.n_snr - 1 : idx);
+    const float scale = __fsqrt_rn(__fdiv_rn(Ps, __fmul_rn(Pn, p.snr_lin[idx])));
+    int st = 0;
+    if (isnan(Ps)) st = 1;
+    else if (isnan(Pn)) st = 2;
+    else if (Ps < 1e-10f) st = 3;
+    else if (Pn < 1e-10f) st = 4;
+    else if (isinf(scale) || isnan(scale)) st = 5;
+    else if (scale > 1e6f) st = 6;
+    else if (isinf(nmax_in)) st = 7;
+    sc.scale = scale;
+    sc.st1 = st;
+  }
+  __syncthreads();
+  const float scale = sc.scale;
+  const int st1 = sc.st1;
+  const f2 s2 = f2_make(scale, scale);
+
+  float nmax = 0.f;
+  if (p.peak_norm && st1 == 0) {
+    // ---- pass 2 (L2): peak of the mixed signal ---------------------------------------------------------------------
+    for (int v0 = v_begin + tid; v0 < v_end; v0 += kStreamUnroll * kStreamThreads) {
+      float4 cv[kStreamUnroll], nv[kStreamUnroll];
+#pragma unroll
+      for (int u = 0; u < kStreamUnroll; ++u) {
+        const int v = v0 + u * kStreamThreads;
+        if (v < v_end) {
+          cv[u] = ld_l2_f4(g_c + v);
+          nv[u] = ld_l2_f4(g_n + v);
+        } else {
+          cv[u] = nv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kStreamUnroll; ++u) {
+        float y0, y1, y2, y3;
+        f2_split(f2_add(f2_make(cv[u].x, cv[u].y), f2_mul(f2_make(nv[u].x, nv[u].y), s2)), y0, y1);
+        f2_split(f2_add(f2_make(cv[u].z, cv[u].w), f2_mul(f2_make(nv[u].z, nv[u].w), s2)), y2, y3);
+        nmax = absmax_nan(absmax_nan(absmax_nan(absmax_nan(nmax, y0), y1), y2), y3);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float other = __shfl_xor_sync(0xffffffffu, nmax, o);
+      asm("max.NaN.f32 %0, %0, %1;" : "+f"(nmax) : "f"(other));
+    }
+    if (lane == 0) red_f[warp][0] = nmax;
+    __syncthreads();
+    if (tid < cs) {
+      float m = red_f[0][0];
+      for (int w = 1; w < kStreamWarps; ++w) asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(red_f[w][0]));
+      *cluster.map_shared_rank(&xch2_f[rank], tid) = m;
+    }
+    if (cs > 1) cluster.sync();
+    else __syncthreads();
+  }
+
+  if (tid == 0) {
+    int st = st1;
+    const bool mixed0 = st == 0;
+    const double s = static_cast<double>(scale);
+    float a_c = 0.f, b_c = 0.f, a_n = 0.f, b_n = 0.f, inv_dc = 1.f, inv_dn = 1.f;
+    if (p.peak_norm) {
+      if (st == 0) {
+        nmax = xch2_f[0];
+        for (int r = 1; r < cs; ++r) asm("max.NaN.f32 %0, %0, %1;" : "+f"(nmax) : "f"(xch2_f[r]));
+        if (isnan(nmax)) st = 8;
+        else if (cmax < 1e-8f) st = 9;
+        else if (nmax < 1e-8f) st = 10;
+        else if (isinf(cmax)) st = 11;
+        else if (isinf(nmax)) st = 12;
+      }
+      if (st == 0) {
+        const double rdc = 1.0 / static_cast<double>(__fadd_rn(cmax, 1e-8f));
+        const double rdn = 1.0 / static_cast<double>(__fadd_rn(nmax, 1e-8f));
+        const double mc = s_c1 * inv_L * rdc;
+        const double vc = s_cc * inv_L * rdc * rdc - mc * mc;
+        const double mn = (s_c1 + s * s_n1) * inv_L * rdn;
+        const double vn = (s_cc + 2.0 * s * s_cn + s * s * s_nn) * inv_L * rdn * rdn - mn * mn;
+        const float vcf = static_cast<float>(vc), vnf = static_cast<float>(vn);
+        const float mcf = static_cast<float>(mc), mnf = static_cast<float>(mn);
+        if (!isfinite(mcf) || !isfinite(vcf)) st = 13;
+        else if (!isfinite(mnf) || !isfinite(vnf)) st = 14;
+        inv_dc = static_cast<float>(rdc);
+        inv_dn = static_cast<float>(rdn);
+        a_c = mcf;
+        b_c = 1.0f / __fsqrt_rn(__fadd_rn(vcf, 1e-7f));
+        a_n = mnf;
+        b_n = 1.0f / __fsqrt_rn(__fadd_rn(vnf, 1e-7f));
+      }
+    } else {
+      const double sw = mixed0 ? (s_c1 + s * s_n1) : s_c1;
+      const double sww = mixed0 ? (s_cc + 2.0 * s * s_cn + s * s * s_nn) : s_cc;
+      const double mn = sw * inv_L;
+      const double vn = sww * inv_L - mn * mn;
+      a_n = static_cast<float>(mn);
+      b_n = 1.0f / __fsqrt_rn(__fadd_rn(static_cast<float>(vn), 1e-7f));
+      if (p.raw) {
+        a_n = 0.f;
+        b_n = 1.f;
+      }
+    }
+    sc.inv_dc = inv_dc; sc.inv_dn = inv_dn;
+    sc.a_c = a_c; sc.b_c = b_c; sc.a_n = a_n; sc.b_n = b_n;
+    sc.st = st;
+    if (rank == 0) p.status[row] = st;
+  }
+  __syncthreads();
+  const int st = sc.st;
+  const bool mixed = st1 == 0;
+
+  // ---- pass 3 (L2 -> HBM) ---------------------------------------------------------------------------------------------
+  float4* co = p.clean_out ? reinterpret_cast<float4*>(p.clean_out + static_cast<size_t>(row) * L) : nullptr;
+  float4* no = reinterpret_cast<float4*>(p.noisy_out + static_cast<size_t>(row) * L);
+  if (p.peak_norm && st != 0) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int v = v_begin + tid; v < v_end; v += kStreamThreads) {
+      st_stream_cs_f4(co + v, z);
+      st_stream_cs_f4(no + v, z);
+    }
+    return;
+  }
+  const f2 nac2 = f2_make(-sc.a_c, -sc.a_c), bc2 = f2_make(sc.b_c, sc.b_c), idc2 = f2_make(sc.inv_dc, sc.inv_dc);
+  const f2 nan2 = f2_make(-sc.a_n, -sc.a_n), bn2 = f2_make(sc.b_n, sc.b_n), idn2 = f2_make(sc.inv_dn, sc.inv_dn);
+  for (int v0 = v_begin + tid; v0 < v_end; v0 += kStreamUnroll * kStreamThreads) {
+    float4 cv[kStreamUnroll], nv[kStreamUnroll];
+#pragma unroll
+    for (int u = 0; u < kStreamUnroll; ++u) {
+      const int v = v0 + u * kStreamThreads;
+      if (v < v_end) {
+        cv[u] = ld_stream_f4(g_c + v);  // last use of the inputs
+        nv[u] = ld_stream_f4(g_n + v);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kStreamUnroll; ++u) {
+      const int v = v0 + u * kStreamThreads;
+      if (v >= v_end) break;
+      const f2 c01 = f2_make(cv[u].x, cv[u].y), c23 = f2_make(cv[u].z, cv[u].w);
+      f2 y01 = f2_make(nv[u].x, nv[u].y), y23 = f2_make(nv[u].z, nv[u].w);
+      if (mixed) {
+        y01 = f2_add(c01, f2_mul(y01, s2));  // augment.py:54,60 (mul and add round separately)
+        y23 = f2_add(c23, f2_mul(y23, s2));
+      } else {
+        y01 = c01;
+        y23 = c23;
+      }
+      float4 on;
+      if (p.peak_norm) {
+        float4 oc;
+        f2_split(f2_mul(f2_add(f2_mul(c01, idc2), nac2), bc2), oc.x, oc.y);
+        f2_split(f2_mul(f2_add(f2_mul(c23, idc2), nac2), bc2), oc.z, oc.w);
+        f2_split(f2_mul(f2_add(f2_mul(y01, idn2), nan2), bn2), on.x, on.y);
+        f2_split(f2_mul(f2_add(f2_mul(y23, idn2), nan2), bn2), on.z, on.w);
+        st_stream_cs_f4(co + v, oc);
+      } else {
+        f2_split(f2_mul(f2_add(y01, nan2), bn2), on.x, on.y);
+        f2_split(f2_mul(f2_add(y23, nan2), bn2), on.z, on.w);
+      }
+      st_stream_cs_f4(no + v, on);
+    }
+  }
+}
+
+int g_mix_variant = 3;  // 3: streaming, one large CTA (or small cluster) per row, passes 2-3 from L2 (default);
+                        // 2: persistent double-buffered shared-memory pipeline; 1: shared memory, one row per
+                        // cluster; 0: generic re-read-from-L2 kernel (also the fallback for unaligned rows)
 
 const char* const kMixStatusNames[] = {
     "ok", "speech_nan", "noise_nan", "speech_power_too_small", "noise_power_too_small", "scale_invalid",
@@ -607,7 +979,7 @@ const char* const kMixStatusNames[] = {
 extern "C" {
 
 int nrse_mix_set_variant(int variant) {
-  if (variant != 0 && variant != 1) return NRSE_ERR_INVALID_ARG;
+  if (variant < 0 || variant > 3) return NRSE_ERR_INVALID_ARG;
   nrse::g_mix_variant = variant;
   return NRSE_OK;
 }
@@ -648,26 +1020,51 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
   cfg.attrs = attr;
   cfg.numAttrs = 1;
 
-  if (vec && g_mix_variant == 1) {
-    // smallest power-of-two cluster that keeps a CTA's two row segments within 64 KB (3 CTAs per SM), up to 8
+  if (vec && g_mix_variant == 3) {
+    // one CTA of 1024 threads per row when the batch fills the machine, else the largest cluster (<= 8) that keeps
+    // B * cs within the SM count
+    int cs = 1;
+    while (cs < kSmemMaxCluster && B * cs * 2 <= kNumSMs) cs *= 2;
+    cfg.gridDim = dim3(static_cast<unsigned>(B) * cs);
+    cfg.blockDim = dim3(kStreamThreads);
+    cfg.dynamicSmemBytes = 0;
+    attr[0].val.clusterDim.x = cs;
+    NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_stream_kernel, p));
+    return NRSE_OK;
+  }
+  if (vec && g_mix_variant >= 1) {
+    // smallest power-of-two cluster (<= 8) whose per-CTA stage (both row segments) is <= 64 KB
     const size_t row_bytes = static_cast<size_t>(L) * 8;
     int cs = 1;
     while (cs < kSmemMaxCluster && row_bytes > static_cast<size_t>(cs) * 65536) cs *= 2;
     const int nvec = L / 4;
     const int seg_vec = ceil_div(nvec, cs);
-    const size_t smem = static_cast<size_t>(seg_vec) * 32;
-    if (smem <= 200 * 1024) {
-      static size_t attr_smem = 0;  // grows monotonically; benign race (idempotent attribute)
-      if (smem > attr_smem) {
-        NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           200 * 1024));
-        attr_smem = 200 * 1024;
-      }
+    const size_t stage_bytes = static_cast<size_t>(seg_vec) * 32;
+    const size_t kMaxSmem = 200 * 1024;
+    static bool attr_set = false;  // benign race: idempotent attributes
+    if (!attr_set) {
+      NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_smem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kMaxSmem)));
+      NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_smem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kMaxSmem)));
+      attr_set = true;
+    }
+    cfg.blockDim = dim3(kSmemThreads);
+    attr[0].val.clusterDim.x = cs;
+    if (g_mix_variant == 2 && 2 * stage_bytes <= kMaxSmem) {
+      // persistent: as many clusters as fit one CTA per SM (two stages of shared memory per CTA)
+      const int ctas_per_sm = static_cast<int>(kMaxSmem / (2 * stage_bytes)) >= 2 ? 2 : 1;
+      int n_clusters = kNumSMs * ctas_per_sm / cs;
+      n_clusters = n_clusters < B ? n_clusters : B;
+      cfg.gridDim = dim3(static_cast<unsigned>(n_clusters) * cs);
+      cfg.dynamicSmemBytes = 2 * stage_bytes;
+      NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_smem_kernel<2>, p, seg_vec));
+      return NRSE_OK;
+    }
+    if (stage_bytes <= kMaxSmem) {
       cfg.gridDim = dim3(static_cast<unsigned>(B) * cs);
-      cfg.blockDim = dim3(kSmemThreads);
-      cfg.dynamicSmemBytes = smem;
-      attr[0].val.clusterDim.x = cs;
-      NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_smem_kernel, p, seg_vec));
+      cfg.dynamicSmemBytes = stage_bytes;
+      NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_smem_kernel<1>, p, seg_vec));
       return NRSE_OK;
     }
   }

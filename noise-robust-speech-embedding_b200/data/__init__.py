@@ -6,3 +6,4 @@ from .noisy_speech_dataset import (  # noqa: F401
     TensorPairDataset,
     create_dataloaders,
 )
+from .prefetch import DevicePrefetcher  # noqa: F401

@@ -12,12 +12,12 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-6  # north star: mixing within 1e-6 relative (norm-relative)
 
 
-@pytest.fixture(params=[1, 0], ids=["smem", "l2"], autouse=True)
+@pytest.fixture(params=[3, 2, 1, 0], ids=["stream", "pipe", "smem", "l2"], autouse=True)
 def mix_variant(request):
     """Every test runs on both kernels: shared-memory-resident rows (default) and the re-read-from-L2 kernel."""
     ops.set_mix_variant(request.param)
     yield request.param
-    ops.set_mix_variant(1)
+    ops.set_mix_variant(3)
 
 
 def _run(dev, clean, noise, snr_idx, table, peak_norm=True):
