@@ -29,11 +29,14 @@ def init_distributed(backend: Optional[str] = None) -> tuple:
     return rank, world, local_rank
 
 
-def wrap_data_parallel(model: torch.nn.Module, device: torch.device, bucket_cap_mb: int = 100):
+def wrap_data_parallel(model: torch.nn.Module, device: torch.device, bucket_cap_mb: int = 100,
+                       find_unused_parameters: bool = True):
     """DDP over the trainable (online) parameters; BatchNorm buffers are NOT broadcast each step, so every rank keeps
-    the per-rank batch statistics the single-GPU reference would have on the same per-rank inputs."""
+    the per-rank batch statistics the single-GPU reference would have on the same per-rank inputs.
+    ``find_unused_parameters`` defaults to True because WavLM's LayerDrop (0.1 in wavlm-large) skips whole transformer
+    layers at random, per rank, in training mode: those parameters get no gradient in that iteration."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return model
     ids = [device.index] if device.type == "cuda" else None
     return DistributedDataParallel(model, device_ids=ids, broadcast_buffers=False, bucket_cap_mb=bucket_cap_mb,
-                                   gradient_as_bucket_view=True)
+                                   gradient_as_bucket_view=True, find_unused_parameters=find_unused_parameters)
