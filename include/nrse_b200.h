@@ -171,6 +171,49 @@ int nrse_conv_frontend_set_variant(int variant);
 /* Layer-0 kernel in LayerNorm mode: 0 = SIMT (warp per frame), 1 = tensor cores (hi/lo-split K=32 UMMA, default). */
 int nrse_conv_frontend_set_layer0_variant(int variant);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training forward and backward of the feature encoder (LayerNorm mode; wavlm-large).
+ * Replaces what autograd records through hf:models/wavlm/modeling_wavlm.py:703-727 x 7 for the online branch
+ * (ref:train_byol.py:66 `loss.backward()`).  The training forward additionally keeps, on a caller-provided tape,
+ * the bf16 activations of layers 0..5, the normalised pre-affine activation `xhat` and 1/std of every frame.
+ * Backward, per layer from 6 to 0:  dOut -> dZ (LayerNorm + GELU backward, also dgamma / dbeta), dW = dZ^T A
+ * (tcgen05, MN-major operands, split-K, fp32 atomics), dX = dZ W (two forward-like GEMMs over even/odd frames).
+ * Weight gradients come out as fp32 in the PACKED K order [512, tap*512 + c_in] (layer 0: [512, 10]); the input
+ * waveform gradient is not computed (the reference never uses it).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* wt_even[NRSE_FRONTEND_LAYERS - 1]; /* bf16 [512 c_in, n_even*512]: taps (0,2) for k=3, (0) for k=2 */
+  const void* wt_odd[NRSE_FRONTEND_LAYERS - 1];  /* bf16 [512 c_in, 512]: tap 1 */
+} nrse_frontend_bwd_weights;
+typedef struct {
+  float* dw0;                             /* [512, 10] */
+  float* dw[NRSE_FRONTEND_LAYERS - 1];    /* [512, k_i*512] packed K order */
+  float* dgamma[NRSE_FRONTEND_LAYERS];    /* [512] */
+  float* dbeta[NRSE_FRONTEND_LAYERS];
+} nrse_frontend_grads;
+
+size_t nrse_conv_frontend_tape_bytes(int B, int L);
+int nrse_conv_frontend_fwd_train(const float* x, const nrse_frontend_params* params_host, void* y, int y_dtype,
+                                 void* tape, size_t tape_bytes, int B, int L, nrse_stream_t stream);
+/* w [512,512,k] fp32 -> the two data-gradient operands described above */
+int nrse_conv_frontend_pack_weights_dgrad(const float* w, void* wt_even, void* wt_odd, int k, nrse_stream_t stream);
+size_t nrse_conv_frontend_bwd_workspace_bytes(int B, int L);
+/* dy [B*P_6, 512] fp32 with zeros in the pitch padding; every tensor of `grads` is overwritten. */
+int nrse_conv_frontend_bwd(const float* x, const nrse_frontend_params* params_host,
+                           const nrse_frontend_bwd_weights* bwd_weights_host, const void* tape, const float* dy,
+                           const nrse_frontend_grads* grads_host, void* workspace, size_t workspace_bytes, int B, int L,
+                           nrse_stream_t stream);
+/* building blocks (per-layer parity tests) */
+int nrse_ln_gelu_bwd(const void* dout, int dout_dtype, const void* xhat, const float* rstd, const float* gamma,
+                     const float* beta, void* dz, float* dgamma, float* dbeta, int64_t rows, int P, int T,
+                     nrse_stream_t stream);
+int nrse_conv_layer0_wgrad(const float* x, const void* dz0, float* dw0, int B, int L, int T0, int P0,
+                           nrse_stream_t stream);
+int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out, int k, float* dw_packed,
+                          nrse_stream_t stream);
+int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even, const void* wt_odd, int k, void* dx,
+                          nrse_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

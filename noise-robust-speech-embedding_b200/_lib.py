@@ -34,6 +34,17 @@ class FrontendParams(C.Structure):
     ]
 
 
+class FrontendBwdWeights(C.Structure):
+    """struct nrse_frontend_bwd_weights."""
+    _fields_ = [("wt_even", C.c_void_p * (N_LAYERS - 1)), ("wt_odd", C.c_void_p * (N_LAYERS - 1))]
+
+
+class FrontendGrads(C.Structure):
+    """struct nrse_frontend_grads."""
+    _fields_ = [("dw0", C.c_void_p), ("dw", C.c_void_p * (N_LAYERS - 1)), ("dgamma", C.c_void_p * N_LAYERS),
+                ("dbeta", C.c_void_p * N_LAYERS)]
+
+
 _i, _i64, _p, _sz, _f = C.c_int, C.c_int64, C.c_void_p, C.c_size_t, C.c_float
 
 # name -> (restype, argtypes); every symbol of include/nrse_b200.h
@@ -57,6 +68,16 @@ SIGNATURES = {
     "nrse_conv_layer_fwd": (_i, [_p, _i64, _p, _i, _i, _p, _p, _p, _i, _i64, _p]),
     "nrse_conv_frontend_set_variant": (_i, [_i]),
     "nrse_conv_frontend_set_layer0_variant": (_i, [_i]),
+    "nrse_conv_frontend_tape_bytes": (_sz, [_i, _i]),
+    "nrse_conv_frontend_fwd_train": (_i, [_p, C.POINTER(FrontendParams), _p, _i, _p, _sz, _i, _i, _p]),
+    "nrse_conv_frontend_pack_weights_dgrad": (_i, [_p, _p, _p, _i, _p]),
+    "nrse_conv_frontend_bwd_workspace_bytes": (_sz, [_i, _i]),
+    "nrse_conv_frontend_bwd": (_i, [_p, C.POINTER(FrontendParams), C.POINTER(FrontendBwdWeights), _p, _p,
+                                    C.POINTER(FrontendGrads), _p, _sz, _i, _i, _p]),
+    "nrse_ln_gelu_bwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p]),
+    "nrse_conv_layer0_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "nrse_conv_layer_wgrad": (_i, [_p, _p, _i64, _i, _p, _p]),
+    "nrse_conv_layer_dgrad": (_i, [_p, _i64, _p, _p, _i, _p, _p]),
 }
 
 _lib = None

@@ -74,6 +74,8 @@ struct L0Args {
   const float* beta;   //                              per-(b,c) shift  [B, 512]
   __nv_bfloat16* out;  // [B*P0, 512]
   int B, L, T0, P0;
+  __nv_bfloat16* xhat;  // nullable (training forward, LayerNorm mode): normalised pre-affine values [B*P0, 512]
+  float* rstd;          // nullable: [B*P0]
 };
 
 // lane owns channels [8*lane, 8*lane+8) and [256 + 8*lane, 256 + 8*lane + 8)
@@ -274,6 +276,15 @@ struct GemmArgs {
   int num_tiles;       // ceil(M_total / 128)
   int k_stages;        // k_i * 512 / 64
   int stride;          // s_i (frame parity dimension of the A tensor map)
+  // training forward: also keep the normalised pre-affine activation and 1/std of every frame for the backward
+  void* xhat;          // [M_total, 512] bf16 or nullptr
+  float* rstd;         // [M_total] or nullptr
+  // generalisations used by the data-gradient GEMM (mode 1): A is a plain 2-D [rows, 512] map whose K range is a
+  // concatenation of 512-wide blocks taken `a_row_off[block]` rows away; output row = m * out_row_mul + out_row_add
+  int mode;            // 0: LayerNorm + GELU forward epilogue, 1: plain bf16 store of the accumulator
+  int a_2d;
+  int a_row_off[2];
+  int out_row_mul, out_row_add;
 };
 
 // ---- epilogue of one accumulator row (shared by the GEMM layers and the tensor-core layer 0) ----------------
@@ -290,6 +301,8 @@ struct EpiCtx {
   bool has_norm, store, zero, out_f32;
   bool arm;                 // this thread arms the statistics barrier (expect_tx) for the tile
   void* out_row;            // first element of this row's channels [n0, n0 + kNPC)
+  __nv_bfloat16* xhat_row;  // nullable: normalised pre-affine values of this row (training forward)
+  float* rstd_out;          // nullable: where to put this row's 1/std
 };
 
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction) --------------
@@ -404,23 +417,38 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
     }
     mean = mean_c;
     rstd = rsqrtf(m2 * (1.0f / kC) + kNormEps);
+    if (e.rstd_out != nullptr && e.store) *e.rstd_out = rstd;
   }
 
   // pass 2: normalise, GELU, store this row's channels.  v = (x*rstd - mean*rstd) * gamma + beta
   const f2 rstd2 = f2_make(rstd, rstd);
   const f2 nmr2 = f2_make(-mean * rstd, -mean * rstd);
   auto emit32 = [&](const uint32_t (&r)[32], int c) {
-    uint32_t o16[16];
+    uint32_t o16[16], xh16[16];
     float o32[32];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       f2 x = f2_bits(r[2 * j], r[2 * j + 1]);
-      if (e.has_norm) x = f2_fma(f2_fma(x, rstd2, nmr2), s_gamma2[c * 16 + j], s_beta2[c * 16 + j]);
+      if (e.has_norm) {
+        x = f2_fma(x, rstd2, nmr2);
+        if (e.xhat_row != nullptr) {
+          float h0, h1;
+          f2_split(x, h0, h1);
+          xh16[j] = pack_bf16x2(h0, h1);
+        }
+        x = f2_fma(x, s_gamma2[c * 16 + j], s_beta2[c * 16 + j]);
+      }
       float y0, y1;
       f2_split(gelu2(x), y0, y1);
       o16[j] = pack_bf16x2(y0, y1);
       o32[2 * j] = y0;
       o32[2 * j + 1] = y1;
+    }
+    if (e.store && e.has_norm && e.xhat_row != nullptr) {
+      uint4* dst = reinterpret_cast<uint4*>(e.xhat_row + c * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dst[j] = e.zero ? make_uint4(0, 0, 0, 0) : make_uint4(xh16[4 * j], xh16[4 * j + 1], xh16[4 * j + 2], xh16[4 * j + 3]);
     }
     if (e.store) {
       if (e.out_f32) {
@@ -450,6 +478,40 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
       ptx::mbar_arrive(e.bar_tmem_empty);
     }
     emit32(rb, c + 1);
+  }
+}
+
+// Mode-1 epilogue (data-gradient GEMM): the accumulator row goes out as bf16, no normalisation, no exchange.
+template <int kClusterN>
+__device__ __forceinline__ void epilogue_plain_row(uint32_t taddr, uint32_t bar_tmem_empty, bool store,
+                                                   __nv_bfloat16* out_row) {
+  constexpr int kNPC = kC / kClusterN;
+  constexpr int kChunks = kNPC / 32;
+  uint32_t ra[32], rb[32];
+  auto emit = [&](const uint32_t (&r)[32], int c) {
+    if (!store) return;
+    uint4* dst = reinterpret_cast<uint4*>(out_row + c * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      dst[j] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])),
+                          pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                          pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
+                          pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+  };
+  ptx::tmem_ld32(taddr, ra);
+#pragma unroll 1
+  for (int c = 0; c < kChunks; c += 2) {
+    ptx::tmem_ld_wait();
+    ptx::tmem_ld32(taddr + (c + 1) * 32, rb);
+    emit(ra, c);
+    ptx::tmem_ld_wait();
+    if (c + 2 < kChunks) {
+      ptx::tmem_ld32(taddr + (c + 2) * 32, ra);
+    } else {
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_tmem_empty);
+    }
+    emit(rb, c + 1);
   }
 }
 
@@ -522,7 +584,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ptx::mbar_arrive_expect_tx(bar(kFull + stage), Cfg::kStageBytes);
           // input frame of tap j for output frame m is stride*m + j = stride*(m + j/stride) + j%stride
           const int tap = kb >> 3, c0 = (kb & 7) * kBlockK;
-          ptx::tma_load_3d(a_dst, &tmap_a, bar(kFull + stage), c0, tap % g.stride, m0 + tap / g.stride);
+          if (g.a_2d) ptx::tma_load_2d(a_dst, &tmap_a, bar(kFull + stage), c0, m0 + (tap == 0 ? g.a_row_off[0] : g.a_row_off[1]));
+          else ptx::tma_load_3d(a_dst, &tmap_a, bar(kFull + stage), c0, tap % g.stride, m0 + tap / g.stride);
 #pragma unroll
           for (int h = 0; h < Cfg::kNumMma; ++h)
             ptx::tma_load_2d(b_dst + h * (kUmmaN * kBlockK * 2), &tmap_w, bar(kFull + stage), kb * kBlockK,
@@ -583,6 +646,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * Cfg::kNPC);
 
+      if (g.mode == 1) {
+        const long long orow = m * g.out_row_mul + g.out_row_add;
+        epilogue_plain_row<kClusterN>(taddr, bar(kTmemEmpty + buf), m < g.M_total,
+                                      reinterpret_cast<__nv_bfloat16*>(g.out) + orow * kC + n0);
+        continue;
+      }
       const int slot = team * 2 + static_cast<int>(acc_phase);  // double-buffered per team
       EpiCtx ec;
       ec.taddr = taddr;
@@ -600,6 +669,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ec.out_f32 = g.out_f32 != 0;
       ec.out_row = g.out_f32 ? static_cast<void*>(reinterpret_cast<float*>(g.out) + m * kC + n0)
                              : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(g.out) + m * kC + n0);
+      ec.xhat_row = g.xhat ? reinterpret_cast<__nv_bfloat16*>(g.xhat) + m * kC + n0 : nullptr;
+      ec.rstd_out = (g.rstd && n0 == 0) ? g.rstd + m : nullptr;
       epilogue_row<kClusterN>(ec);
     }
   }
@@ -821,6 +892,8 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
       ec.zero = static_cast<int>(m % a.P0) >= a.T0;  // pitch padding is written as zeros
       ec.out_f32 = false;
       ec.out_row = a.out + m * kC + n0;
+      ec.xhat_row = a.xhat ? a.xhat + m * kC + n0 : nullptr;
+      ec.rstd_out = (a.rstd && n0 == 0) ? a.rstd + m : nullptr;
       epilogue_row<kClusterN>(ec);
     }
   }
@@ -832,6 +905,322 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
+}
+
+// =========================================================================================================
+// Backward (LayerNorm mode).  Per layer i, with Z = A W^T, xhat = (Z - mean) rstd, V = xhat gamma + beta, Out = GELU(V):
+//   ln_gelu_bwd_kernel : dOut -> dZ = rstd (dxh - mean(dxh) - xhat mean(dxh xhat)),  dxh = dOut gelu'(V) gamma;
+//                        dgamma += sum dV xhat, dbeta += sum dV.  xhat and rstd were saved by the training forward.
+//   conv_wgrad_kernel  : dW = dZ^T A   (tcgen05, both operands MN-major straight from their row-major homes, split-K)
+//   conv_gemm_kernel<mode 1> : dX = dZ W  as two forward-like GEMMs (even / odd input frames), no atomics
+//   layer0_wgrad_kernel: dW0[c, tap] = sum_m dZ0[m, c] x[5m + tap]   (SIMT)
+// Pitch-padding frames carry dZ = 0, which is what keeps them out of dW and dX.
+// =========================================================================================================
+constexpr int kLnBwdThreads = 256;
+constexpr int kLnBwdWarps = kLnBwdThreads / 32;
+
+struct LnBwdArgs {
+  const void* dout;  // [rows, 512] fp32 or bf16 (may alias dz)
+  int dout_f32;
+  const __nv_bfloat16* xhat;
+  const float* rstd;
+  const float* gamma;
+  const float* beta;
+  __nv_bfloat16* dz;
+  float* dgamma;  // [512], accumulated with atomics (zeroed by the caller)
+  float* dbeta;
+  long long rows;
+  int P, T;
+};
+
+// d/dv [ v Phi(v) ] = Phi(v) + v phi(v), Phi from the same erfc fit as the forward
+__device__ __forceinline__ float gelu_grad(float v) {
+  const float u = fminf(fabsf(v), 5.6f);
+  float q = fmaf(u, -0.0005235913558863103f, 0.007414255291223526f);
+  q = fmaf(q, u, -0.05259089171886444f);
+  q = fmaf(q, u, -0.4592348039150238f);
+  q = fmaf(q, u, -1.1510953903198242f);
+  float e, g;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q * u));                          // erfc(|v|/sqrt2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(v * v * (-0.5f * 1.44269504f)));  // exp(-v^2/2)
+  const float cdf = v >= 0.f ? fmaf(-0.5f, e, 1.0f) : 0.5f * e;
+  return fmaf(v * 0.3989422804f, g, cdf);
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& a, float (&x)[8]) {
+  const unsigned w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    x[2 * j] = __uint_as_float(w[j] << 16);
+    x[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+
+__global__ void __launch_bounds__(kLnBwdThreads) ln_gelu_bwd_kernel(const LnBwdArgs a) {
+  __shared__ __align__(16) float s_gamma[kC];
+  __shared__ __align__(16) float s_beta[kC];
+  __shared__ float s_acc[kLnBwdWarps][2 * kC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kC; i += kLnBwdThreads) {
+    s_gamma[i] = a.gamma[i];
+    s_beta[i] = a.beta[i];
+  }
+  __syncthreads();
+  float dg[16], db[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) dg[j] = db[j] = 0.f;
+
+  const long long warps_total = static_cast<long long>(gridDim.x) * kLnBwdWarps;
+  for (long long m = static_cast<long long>(blockIdx.x) * kLnBwdWarps + warp; m < a.rows; m += warps_total) {
+    uint4* zrow = reinterpret_cast<uint4*>(a.dz + m * kC);
+    if (static_cast<int>(m % a.P) >= a.T) {  // pitch padding: no gradient flows through it
+      zrow[lane] = make_uint4(0, 0, 0, 0);
+      zrow[32 + lane] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    float go[16], xh[16];
+    const uint4* xr = reinterpret_cast<const uint4*>(a.xhat + m * kC);
+    unpack_bf16x8(__ldg(xr + lane), *reinterpret_cast<float(*)[8]>(&xh[0]));
+    unpack_bf16x8(__ldg(xr + 32 + lane), *reinterpret_cast<float(*)[8]>(&xh[8]));
+    if (a.dout_f32) {
+      const float4* gr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.dout) + m * kC);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 p0 = gr[h * 64 + 2 * lane], p1 = gr[h * 64 + 2 * lane + 1];
+        go[h * 8 + 0] = p0.x; go[h * 8 + 1] = p0.y; go[h * 8 + 2] = p0.z; go[h * 8 + 3] = p0.w;
+        go[h * 8 + 4] = p1.x; go[h * 8 + 5] = p1.y; go[h * 8 + 6] = p1.z; go[h * 8 + 7] = p1.w;
+      }
+    } else {
+      const uint4* gr = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.dout) + m * kC);
+      unpack_bf16x8(gr[lane], *reinterpret_cast<float(*)[8]>(&go[0]));
+      unpack_bf16x8(gr[32 + lane], *reinterpret_cast<float(*)[8]>(&go[8]));
+    }
+    float dx[16], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = l0_channel(lane, j);
+      const float gm = s_gamma[c];
+      const float dv = go[j] * gelu_grad(fmaf(xh[j], gm, s_beta[c]));
+      dg[j] = fmaf(dv, xh[j], dg[j]);
+      db[j] += dv;
+      dx[j] = dv * gm;
+      s1 += dx[j];
+      s2 = fmaf(dx[j], xh[j], s2);
+    }
+    s1 = warp_sum(s1) * (1.0f / kC);
+    s2 = warp_sum(s2) * (1.0f / kC);
+    const float rs = __ldg(a.rstd + m);
+    float z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = rs * (dx[j] - s1 - xh[j] * s2);
+    zrow[lane] = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]),
+                            pack_bf16x2(z[6], z[7]));
+    zrow[32 + lane] = make_uint4(pack_bf16x2(z[8], z[9]), pack_bf16x2(z[10], z[11]), pack_bf16x2(z[12], z[13]),
+                                 pack_bf16x2(z[14], z[15]));
+  }
+  // CTA-level reduction of the affine gradients, then one atomic per channel per CTA
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    s_acc[warp][l0_channel(lane, j)] = dg[j];
+    s_acc[warp][kC + l0_channel(lane, j)] = db[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * kC; i += kLnBwdThreads) {
+    float t = 0.f;
+    for (int w = 0; w < kLnBwdWarps; ++w) t += s_acc[w][i];
+    atomicAdd(i < kC ? a.dgamma + i : a.dbeta + (i - kC), t);
+  }
+}
+
+// dW0[c, tap] += sum over frames of dZ0[m, c] * x[5 t + tap]; lane owns 16 channels x 10 taps
+__global__ void __launch_bounds__(kL0Threads, 1)
+layer0_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz, float* __restrict__ dw0, int B,
+                    int L, int T0, int P0) {
+  __shared__ float s_acc[kL0Warps][160 * 32 / 8];  // reduced in eight slices of 20 accumulators per lane
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[16][10];
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[j][k] = 0.f;
+  const long long rows = static_cast<long long>(B) * P0;
+  const long long warps_total = static_cast<long long>(gridDim.x) * kL0Warps;
+  for (long long m = static_cast<long long>(blockIdx.x) * kL0Warps + warp; m < rows; m += warps_total) {
+    const int b = static_cast<int>(m / P0), t = static_cast<int>(m % P0);
+    if (t >= T0) continue;
+    const float* xw = x + static_cast<size_t>(b) * L + 5 * t;
+    float xv[10], z[16];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) xv[k] = __ldg(xw + k);
+    const uint4* zr = reinterpret_cast<const uint4*>(dz + m * kC);
+    unpack_bf16x8(__ldg(zr + lane), *reinterpret_cast<float(*)[8]>(&z[0]));
+    unpack_bf16x8(__ldg(zr + 32 + lane), *reinterpret_cast<float(*)[8]>(&z[8]));
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+#pragma unroll
+      for (int k = 0; k < 10; ++k) acc[j][k] = fmaf(z[j], xv[k], acc[j][k]);
+  }
+  // reduce across the CTA's warps through shared memory, two channels (20 values per lane) at a time
+#pragma unroll
+  for (int part = 0; part < 8; ++part) {
+    __syncthreads();
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+      for (int k = 0; k < 10; ++k) s_acc[warp][(jj * 10 + k) * 32 + lane] = acc[part * 2 + jj][k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 20 * 32; i += kL0Threads) {
+      float t = 0.f;
+      for (int w = 0; w < kL0Warps; ++w) t += s_acc[w][i];
+      const int ln = i & 31, q = i >> 5, jj = q / 10, k = q % 10;
+      atomicAdd(dw0 + l0_channel(ln, part * 2 + jj) * 10 + k, t);
+    }
+  }
+}
+
+// ---- weight gradient: dW[n, kk] = sum_m dZ[m, n] * A[m, kk],  A[m, tap*512 + c] = X[2m + tap, c] -------------------
+// One CTA per (128 output channels) x (256 K columns) x (slice of the frame axis).  Both operands are MN-major:
+// the reduction index m runs over shared-memory rows of 128 bytes, exactly what TMA writes for a {64 elements, 64 rows}
+// box of the row-major dZ / X tensors, so no transposed copy of either is ever made.
+constexpr int kWgThreads = 192;
+constexpr int kWgStages = 4;
+constexpr int kWgKm = 64;                         // frames per pipeline stage
+constexpr int kWgABytes = 2 * kWgKm * 128;        // 128 channels = 2 boxes of 64
+constexpr int kWgBBytes = 4 * kWgKm * 128;        // 256 K columns = 4 boxes of 64
+constexpr int kWgStageBytes = kWgABytes + kWgBBytes;
+constexpr int kWgBarOff = kWgStages * kWgStageBytes;
+constexpr int kWgSmemBytes = kWgBarOff + (2 * kWgStages + 1) * 8 + 16 + 1024;
+
+struct WgradArgs {
+  float* dw;        // [512, K] fp32 (packed K order tap*512 + c), accumulated with atomics
+  int K;            // k * 512
+  int stride;       // 2
+  int n_stages;     // ceil(M / 64)
+  int split;        // number of frame-axis slices
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  // MN-major, 128B swizzle: 64-element MN blocks are 8 KB apart (LBO), 8-row K groups 1 KB apart (SBO)
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>((kWgKm * 128) >> 4) << 16) |
+         (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                  const WgradArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return smem_base + kWgBarOff + 8u * static_cast<uint32_t>(i); };
+  const int kFull = 0, kEmpty = kWgStages, kDone = 2 * kWgStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kWgBarOff + (2 * kWgStages + 1) * 8);
+
+  const int kk_tiles = g.K / 256;
+  const int tile = static_cast<int>(blockIdx.x) / g.split, slice = static_cast<int>(blockIdx.x) % g.split;
+  const int n0 = (tile / kk_tiles) * 128, kk0 = (tile % kk_tiles) * 256;
+  const int tap = kk0 / kC, c0 = kk0 % kC;
+  const int per = (g.n_stages + g.split - 1) / g.split;
+  const int st_begin = slice * per, st_end = min(g.n_stages, st_begin + per);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_g);
+    ptx::prefetch_tmap(&tmap_x);
+    for (int s = 0; s < kWgStages; ++s) {
+      ptx::mbar_init(bar(kFull + s), 1);
+      ptx::mbar_init(bar(kEmpty + s), 1);
+    }
+    ptx::mbar_init(bar(kDone), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int st = st_begin; st < st_end; ++st) {
+        const int m0 = st * kWgKm;
+        ptx::mbar_wait(bar(kEmpty + stage), phase ^ 1u);
+        const uint32_t a_dst = smem_base + stage * kWgStageBytes;
+        const uint32_t b_dst = a_dst + kWgABytes;
+        ptx::mbar_arrive_expect_tx(bar(kFull + stage), kWgStageBytes);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          ptx::tma_load_2d(a_dst + j * (kWgKm * 128), &tmap_g, bar(kFull + stage), n0 + 64 * j, m0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          ptx::tma_load_3d(b_dst + j * (kWgKm * 128), &tmap_x, bar(kFull + stage), c0 + 64 * j, tap % g.stride,
+                           m0 + tap / g.stride);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // both operands MN-major: bits 15 and 16 of the instruction descriptor
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 256) | (1u << 15) | (1u << 16);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int st = st_begin; st < st_end; ++st) {
+        ptx::mbar_wait(bar(kFull + stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t a_src = smem_base + stage * kWgStageBytes;
+        const uint32_t b_src = a_src + kWgABytes;
+#pragma unroll
+        for (int k = 0; k < kWgKm / kUmmaK; ++k)  // 16 frames (= 16 shared-memory rows = 2 KB) per instruction
+          ptx::umma_bf16(tmem_base, umma_desc_sw128_mn(a_src + k * (kUmmaK * 128)),
+                         umma_desc_sw128_mn(b_src + k * (kUmmaK * 128)), idesc, (st > st_begin || k > 0) ? 1u : 0u);
+        ptx::umma_commit(bar(kEmpty + stage));
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+      }
+      ptx::umma_commit(bar(kDone));
+    }
+    __syncwarp();
+  } else if (st_end > st_begin) {
+    // epilogue: TMEM -> fp32 atomics into dW (split-K partial sums meet in L2)
+    const int quad = warp & 3;
+    const int n = n0 + quad * 32 + lane;
+    ptx::mbar_wait(bar(kDone), 0);
+    ptx::tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    float* dst = g.dw + static_cast<size_t>(n) * g.K + kk0;
+#pragma unroll 1
+    for (int c = 0; c < 256; c += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld32(taddr + c, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(dst + c + j, __uint_as_float(r[j]));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// checkpoint layout [512 n, 512 c, k] fp32 -> data-gradient operands: even[c][j*512 + n] = w[n][c][even tap j],
+// odd[c][n] = w[n][c][1]; even taps are (0, 2) for k = 3 and (0) for k = 2
+__global__ void pack_weights_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ even,
+                                          __nv_bfloat16* __restrict__ odd, int k) {
+  const int c = blockIdx.x;
+  const int ne = k == 3 ? 2 : 1;
+  for (int i = threadIdx.x; i < ne * kC; i += blockDim.x) {
+    const int j = i / kC, n = i % kC;
+    even[static_cast<size_t>(c) * ne * kC + i] = __float2bfloat16_rn(w[(static_cast<size_t>(n) * kC + c) * k + 2 * j]);
+  }
+  for (int n = threadIdx.x; n < kC; n += blockDim.x)
+    odd[static_cast<size_t>(c) * kC + n] = __float2bfloat16_rn(w[(static_cast<size_t>(n) * kC + c) * k + 1]);
 }
 
 // ---- host side --------------------------------------------------------------------------------------------
@@ -852,13 +1241,13 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // A operand: previous activation [rows_prev, 512] bf16 seen as (channel, frame parity, frame pair).
-int make_tmap_a(CUtensorMap* m, const void* act_prev, int64_t rows_prev, int stride) {
+int make_tmap_a(CUtensorMap* m, const void* act_prev, int64_t rows_prev, int stride, int box_rows = kBlockM) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return NRSE_ERR_CUDA;
   const cuuint64_t dims[3] = {static_cast<cuuint64_t>(kC), static_cast<cuuint64_t>(stride),
                               static_cast<cuuint64_t>(rows_prev / stride)};
   const cuuint64_t strides[2] = {static_cast<cuuint64_t>(kC) * 2, static_cast<cuuint64_t>(kC) * 2 * stride};
-  const cuuint32_t box[3] = {kBlockK, 1, kBlockM};
+  const cuuint32_t box[3] = {kBlockK, 1, static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(act_prev), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -876,6 +1265,20 @@ int make_tmap_w(CUtensorMap* m, const void* w_packed, int K) {
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NRSE_OK : NRSE_ERR_CUDA;
+}
+
+// plain row-major [rows, 512] bf16 tensor, box = 64 channels x box_rows rows
+int make_tmap_rows(CUtensorMap* m, const void* ptr, int64_t rows, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return NRSE_ERR_CUDA;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kC), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kC) * 2};
+  const cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? NRSE_OK : NRSE_ERR_CUDA;
 }
@@ -960,6 +1363,25 @@ int geometry(int L, int32_t* T, int32_t* P) {
 
 size_t act_bytes(int B, int P) { return round_up(static_cast<size_t>(B) * P * kC * 2, static_cast<size_t>(1024)); }
 size_t gn_part_bytes(int B) { return round_up(static_cast<size_t>(B) * kGnSlots * 2 * kC * 4, static_cast<size_t>(1024)); }
+size_t rstd_bytes(int B, int P) { return round_up(static_cast<size_t>(B) * P * 4, static_cast<size_t>(1024)); }
+
+// Tape of a training forward: activations of layers 0..5, xhat of layers 0..6, rstd of layers 0..6
+struct Tape {
+  char* act[kLayers - 1];
+  char* xhat[kLayers];
+  float* rstd[kLayers];
+  size_t bytes;
+};
+Tape tape_layout(void* base, int B, const int32_t* P) {
+  Tape t;
+  char* p = reinterpret_cast<char*>(base);
+  for (int i = 0; i < kLayers - 1; ++i) { t.act[i] = p; p += act_bytes(B, P[i]); }
+  for (int i = 0; i < kLayers; ++i) { t.xhat[i] = p; p += act_bytes(B, P[i]); }
+  for (int i = 0; i < kLayers; ++i) { t.rstd[i] = reinterpret_cast<float*>(p); p += rstd_bytes(B, P[i]); }
+  t.bytes = static_cast<size_t>(p - reinterpret_cast<char*>(base));
+  return t;
+}
+
 size_t gn_affine_bytes(int B) { return round_up(static_cast<size_t>(B) * kC * 4, static_cast<size_t>(1024)); }
 
 }  // namespace
@@ -1001,8 +1423,9 @@ int nrse_conv_frontend_pack_weights(const float* w, void* w_packed, int k, nrse_
   return NRSE_OK;
 }
 
-int nrse_conv_layer0_fwd(const float* x, const float* w0, const float* gamma, const float* beta, int norm_mode,
-                         void* out, void* gn_scratch, int B, int L, int T0, int P0, nrse_stream_t stream) {
+static int layer0_fwd_impl(const float* x, const float* w0, const float* gamma, const float* beta, int norm_mode,
+                           void* out, void* gn_scratch, int B, int L, int T0, int P0, void* xhat, float* rstd,
+                           nrse_stream_t stream) {
   using namespace nrse;
   if (!x || !w0 || !gamma || !beta || !out || B < 1 || T0 < 1 || P0 < T0 || L < 5 * (T0 - 1) + 10)
     return NRSE_ERR_INVALID_ARG;
@@ -1012,11 +1435,13 @@ int nrse_conv_layer0_fwd(const float* x, const float* w0, const float* gamma, co
   a.x = x; a.w = w0; a.gamma = gamma; a.beta = beta;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   a.B = B; a.L = L; a.T0 = T0; a.P0 = P0;
+  a.xhat = reinterpret_cast<__nv_bfloat16*>(xhat);
+  a.rstd = rstd;
   const long long rows = static_cast<long long>(B) * P0;
   const long long want = ceil_div(rows, static_cast<long long>(kL0Warps));
   const unsigned grid = static_cast<unsigned>(want < kNumSMs ? want : kNumSMs);
   if (norm_mode == NRSE_NORM_LAYER) {
-    if (g_layer0_variant == 1) return g_variant == 2 ? launch_layer0_tc<2>(a, s) : launch_layer0_tc<1>(a, s);
+    if (g_layer0_variant == 1 || xhat != nullptr) return g_variant == 2 ? launch_layer0_tc<2>(a, s) : launch_layer0_tc<1>(a, s);
     layer0_kernel<false><<<grid, kL0Threads, 0, s>>>(a);
     NRSE_CHECK_LAUNCH();
     return NRSE_OK;
@@ -1036,9 +1461,14 @@ int nrse_conv_layer0_fwd(const float* x, const float* w0, const float* gamma, co
   return NRSE_OK;
 }
 
-int nrse_conv_layer_fwd(const void* act_prev, int64_t rows_prev, const void* w_packed, int k, int stride,
-                        const float* gamma, const float* beta, void* out, int out_dtype, int64_t rows_out,
-                        nrse_stream_t stream) {
+int nrse_conv_layer0_fwd(const float* x, const float* w0, const float* gamma, const float* beta, int norm_mode,
+                         void* out, void* gn_scratch, int B, int L, int T0, int P0, nrse_stream_t stream) {
+  return layer0_fwd_impl(x, w0, gamma, beta, norm_mode, out, gn_scratch, B, L, T0, P0, nullptr, nullptr, stream);
+}
+
+static int layer_fwd_impl(const void* act_prev, int64_t rows_prev, const void* w_packed, int k, int stride,
+                          const float* gamma, const float* beta, void* out, int out_dtype, int64_t rows_out,
+                          void* xhat, float* rstd, nrse_stream_t stream) {
   using namespace nrse;
   if (!act_prev || !w_packed || !out || (k != 2 && k != 3) || stride != 2) return NRSE_ERR_INVALID_ARG;
   if ((gamma == nullptr) != (beta == nullptr)) return NRSE_ERR_INVALID_ARG;
@@ -1059,7 +1489,21 @@ int nrse_conv_layer_fwd(const void* act_prev, int64_t rows_prev, const void* w_p
   g.num_tiles = static_cast<int>(ceil_div(rows_out, static_cast<int64_t>(kBlockM)));
   g.k_stages = k * kC / kBlockK;
   g.stride = stride;
+  g.xhat = xhat;
+  g.rstd = rstd;
+  g.mode = 0;
+  g.a_2d = 0;
+  g.a_row_off[0] = g.a_row_off[1] = 0;
+  g.out_row_mul = 1;
+  g.out_row_add = 0;
   return g_variant == 2 ? launch_gemm<2>(ta, tw, g, as_stream(stream)) : launch_gemm<1>(ta, tw, g, as_stream(stream));
+}
+
+int nrse_conv_layer_fwd(const void* act_prev, int64_t rows_prev, const void* w_packed, int k, int stride,
+                        const float* gamma, const float* beta, void* out, int out_dtype, int64_t rows_out,
+                        nrse_stream_t stream) {
+  return layer_fwd_impl(act_prev, rows_prev, w_packed, k, stride, gamma, beta, out, out_dtype, rows_out, nullptr, nullptr,
+                        stream);
 }
 
 int nrse_conv_frontend_fwd(const float* x, const nrse_frontend_params* prm, int norm_mode, void* y, int y_dtype,
@@ -1093,6 +1537,185 @@ int nrse_conv_frontend_fwd(const float* x, const nrse_frontend_params* prm, int 
     rc = nrse_conv_layer_fwd(act[i - 1], static_cast<int64_t>(B) * P[i - 1], prm->w_packed[i - 1], kKernel[i],
                              kStride[i], norm ? prm->gamma[i] : nullptr, norm ? prm->beta[i] : nullptr, act[i],
                              i == kLayers - 1 ? y_dtype : NRSE_DTYPE_BF16, static_cast<int64_t>(B) * P[i], stream);
+    if (rc != NRSE_OK) return rc;
+  }
+  return NRSE_OK;
+}
+
+/* ---- training forward + backward (LayerNorm mode) -------------------------------------------------------------- */
+size_t nrse_conv_frontend_tape_bytes(int B, int L) {
+  int32_t T[nrse::kLayers], P[nrse::kLayers];
+  if (B < 1 || nrse::geometry(L, T, P) != NRSE_OK) return 0;
+  return nrse::tape_layout(nullptr, B, P).bytes;
+}
+
+int nrse_conv_frontend_fwd_train(const float* x, const nrse_frontend_params* prm, void* y, int y_dtype, void* tape,
+                                 size_t tape_bytes, int B, int L, nrse_stream_t stream) {
+  using namespace nrse;
+  if (!x || !prm || !y || !tape || B < 1) return NRSE_ERR_INVALID_ARG;
+  if (reinterpret_cast<uintptr_t>(tape) & 1023u) return NRSE_ERR_INVALID_ARG;
+  int32_t T[kLayers], P[kLayers];
+  int rc = geometry(L, T, P);
+  if (rc != NRSE_OK) return rc;
+  const Tape t = tape_layout(tape, B, P);
+  if (tape_bytes < t.bytes) return NRSE_ERR_WORKSPACE;
+  rc = layer0_fwd_impl(x, prm->w0, prm->gamma[0], prm->beta[0], NRSE_NORM_LAYER, t.act[0], nullptr, B, L, T[0], P[0],
+                       t.xhat[0], t.rstd[0], stream);
+  if (rc != NRSE_OK) return rc;
+  for (int i = 1; i < kLayers; ++i) {
+    if (!prm->gamma[i] || !prm->beta[i]) return NRSE_ERR_INVALID_ARG;
+    void* out = i == kLayers - 1 ? y : static_cast<void*>(t.act[i]);
+    rc = layer_fwd_impl(t.act[i - 1], static_cast<int64_t>(B) * P[i - 1], prm->w_packed[i - 1], kKernel[i], kStride[i],
+                        prm->gamma[i], prm->beta[i], out, i == kLayers - 1 ? y_dtype : NRSE_DTYPE_BF16,
+                        static_cast<int64_t>(B) * P[i], t.xhat[i], t.rstd[i], stream);
+    if (rc != NRSE_OK) return rc;
+  }
+  return NRSE_OK;
+}
+
+int nrse_conv_frontend_pack_weights_dgrad(const float* w, void* even, void* odd, int k, nrse_stream_t stream) {
+  using namespace nrse;
+  if (!w || !even || !odd || (k != 2 && k != 3)) return NRSE_ERR_INVALID_ARG;
+  pack_weights_dgrad_kernel<<<kC, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(even),
+                                                                reinterpret_cast<__nv_bfloat16*>(odd), k);
+  NRSE_CHECK_LAUNCH();
+  return NRSE_OK;
+}
+
+int nrse_ln_gelu_bwd(const void* dout, int dout_dtype, const void* xhat, const float* rstd, const float* gamma,
+                     const float* beta, void* dz, float* dgamma, float* dbeta, int64_t rows, int P, int T,
+                     nrse_stream_t stream) {
+  using namespace nrse;
+  if (!dout || !xhat || !rstd || !gamma || !beta || !dz || !dgamma || !dbeta || rows < 1 || P < 1 || T < 1 || T > P)
+    return NRSE_ERR_INVALID_ARG;
+  LnBwdArgs a;
+  a.dout = dout; a.dout_f32 = dout_dtype == NRSE_DTYPE_F32 ? 1 : 0;
+  a.xhat = reinterpret_cast<const __nv_bfloat16*>(xhat);
+  a.rstd = rstd; a.gamma = gamma; a.beta = beta;
+  a.dz = reinterpret_cast<__nv_bfloat16*>(dz);
+  a.dgamma = dgamma; a.dbeta = dbeta; a.rows = rows; a.P = P; a.T = T;
+  const long long want = ceil_div(static_cast<long long>(rows), static_cast<long long>(kLnBwdWarps));
+  const unsigned grid = static_cast<unsigned>(want < 4 * kNumSMs ? want : 4 * kNumSMs);
+  ln_gelu_bwd_kernel<<<grid, kLnBwdThreads, 0, as_stream(stream)>>>(a);
+  NRSE_CHECK_LAUNCH();
+  return NRSE_OK;
+}
+
+int nrse_conv_layer0_wgrad(const float* x, const void* dz0, float* dw0, int B, int L, int T0, int P0,
+                           nrse_stream_t stream) {
+  using namespace nrse;
+  if (!x || !dz0 || !dw0 || B < 1 || T0 < 1 || P0 < T0) return NRSE_ERR_INVALID_ARG;
+  const long long rows = static_cast<long long>(B) * P0;
+  const long long want = ceil_div(rows, static_cast<long long>(kL0Warps));
+  const unsigned grid = static_cast<unsigned>(want < kNumSMs ? want : kNumSMs);
+  layer0_wgrad_kernel<<<grid, kL0Threads, 0, as_stream(stream)>>>(x, reinterpret_cast<const __nv_bfloat16*>(dz0), dw0, B,
+                                                                  L, T0, P0);
+  NRSE_CHECK_LAUNCH();
+  return NRSE_OK;
+}
+
+/* dW [512, k*512] fp32 (K order tap*512 + c) += dZ^T A.  dz [rows_out, 512] bf16, act_prev [2*rows_out, 512] bf16. */
+int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out, int k, float* dw_packed,
+                          nrse_stream_t stream) {
+  using namespace nrse;
+  if (!dz || !act_prev || !dw_packed || rows_out < 1 || (k != 2 && k != 3)) return NRSE_ERR_INVALID_ARG;
+  CUtensorMap tg, tx;
+  int rc = make_tmap_rows(&tg, dz, rows_out, kWgKm);
+  if (rc != NRSE_OK) return rc;
+  rc = make_tmap_a(&tx, act_prev, 2 * rows_out, 2, kWgKm);
+  if (rc != NRSE_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+    attr_set = true;
+  }
+  WgradArgs g;
+  g.dw = dw_packed;
+  g.K = k * kC;
+  g.stride = 2;
+  g.n_stages = static_cast<int>(ceil_div(rows_out, static_cast<int64_t>(kWgKm)));
+  const int tiles = 4 * (g.K / 256);
+  int split = kNumSMs / tiles;
+  if (split > g.n_stages) split = g.n_stages;
+  if (split < 1) split = 1;
+  g.split = split;
+  conv_wgrad_kernel<<<tiles * split, kWgThreads, kWgSmemBytes, as_stream(stream)>>>(tg, tx, g);
+  NRSE_CHECK_LAUNCH();
+  return NRSE_OK;
+}
+
+/* dX [2*rows_out, 512] bf16 = dZ W (transposed convolution, stride 2) as two GEMMs over even / odd input frames. */
+int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even, const void* wt_odd, int k, void* dx,
+                          nrse_stream_t stream) {
+  using namespace nrse;
+  if (!dz || !wt_even || !wt_odd || !dx || rows_out < 1 || (k != 2 && k != 3)) return NRSE_ERR_INVALID_ARG;
+  CUtensorMap ta, tw;
+  int rc = make_tmap_rows(&ta, dz, rows_out, kBlockM);
+  if (rc != NRSE_OK) return rc;
+  for (int parity = 0; parity < 2; ++parity) {
+    const int n_blocks = (parity == 0 && k == 3) ? 2 : 1;
+    rc = make_tmap_w(&tw, parity == 0 ? wt_even : wt_odd, n_blocks * kC);
+    if (rc != NRSE_OK) return rc;
+    GemmArgs g;
+    g.gamma = nullptr; g.beta = nullptr; g.out = dx; g.out_f32 = 0;
+    g.M_total = static_cast<int>(rows_out);
+    g.num_tiles = static_cast<int>(ceil_div(rows_out, static_cast<int64_t>(kBlockM)));
+    g.k_stages = n_blocks * kC / kBlockK;
+    g.stride = 2;
+    g.xhat = nullptr; g.rstd = nullptr;
+    g.mode = 1;
+    g.a_2d = 1;
+    g.a_row_off[0] = 0;    // even: tap 0 <- dZ[m];  odd: tap 1 <- dZ[m]
+    g.a_row_off[1] = -1;   // even, k = 3: tap 2 <- dZ[m - 1]
+    g.out_row_mul = 2;
+    g.out_row_add = parity;
+    rc = g_variant == 2 ? launch_gemm<2>(ta, tw, g, as_stream(stream)) : launch_gemm<1>(ta, tw, g, as_stream(stream));
+    if (rc != NRSE_OK) return rc;
+  }
+  return NRSE_OK;
+}
+
+size_t nrse_conv_frontend_bwd_workspace_bytes(int B, int L) {
+  int32_t T[nrse::kLayers], P[nrse::kLayers];
+  if (B < 1 || nrse::geometry(L, T, P) != NRSE_OK) return 0;
+  return nrse::act_bytes(B, P[0]) + nrse::act_bytes(B, P[1]);  // ping-pong gradient buffers (even / odd layers)
+}
+
+int nrse_conv_frontend_bwd(const float* x, const nrse_frontend_params* prm, const nrse_frontend_bwd_weights* wb,
+                           const void* tape, const float* dy, const nrse_frontend_grads* grads, void* workspace,
+                           size_t workspace_bytes, int B, int L, nrse_stream_t stream) {
+  using namespace nrse;
+  if (!x || !prm || !wb || !tape || !dy || !grads || !workspace || B < 1) return NRSE_ERR_INVALID_ARG;
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023u) return NRSE_ERR_INVALID_ARG;
+  int32_t T[kLayers], P[kLayers];
+  int rc = geometry(L, T, P);
+  if (rc != NRSE_OK) return rc;
+  if (workspace_bytes < nrse_conv_frontend_bwd_workspace_bytes(B, L)) return NRSE_ERR_WORKSPACE;
+  const Tape t = tape_layout(const_cast<void*>(tape), B, P);
+  char* buf[2] = {reinterpret_cast<char*>(workspace), reinterpret_cast<char*>(workspace) + act_bytes(B, P[0])};
+  cudaStream_t s = as_stream(stream);
+  for (int i = 0; i < kLayers; ++i) {
+    NRSE_CUDA_TRY(cudaMemsetAsync(grads->dgamma[i], 0, kC * sizeof(float), s));
+    NRSE_CUDA_TRY(cudaMemsetAsync(grads->dbeta[i], 0, kC * sizeof(float), s));
+    if (i == 0) NRSE_CUDA_TRY(cudaMemsetAsync(grads->dw0, 0, kC * 10 * sizeof(float), s));
+    else NRSE_CUDA_TRY(cudaMemsetAsync(grads->dw[i - 1], 0, static_cast<size_t>(kC) * kKernel[i] * kC * sizeof(float), s));
+  }
+  for (int i = kLayers - 1; i >= 0; --i) {
+    const int64_t rows = static_cast<int64_t>(B) * P[i];
+    char* dz = buf[i & 1];
+    // dOut_i (dy for the last layer, else the dgrad output already sitting in dz) -> dZ_i, in place
+    rc = nrse_ln_gelu_bwd(i == kLayers - 1 ? static_cast<const void*>(dy) : static_cast<const void*>(dz),
+                          i == kLayers - 1 ? NRSE_DTYPE_F32 : NRSE_DTYPE_BF16, t.xhat[i], t.rstd[i], prm->gamma[i],
+                          prm->beta[i], dz, grads->dgamma[i], grads->dbeta[i], rows, P[i], T[i], stream);
+    if (rc != NRSE_OK) return rc;
+    if (i == 0) {
+      rc = nrse_conv_layer0_wgrad(x, dz, grads->dw0, B, L, T[0], P[0], stream);
+      if (rc != NRSE_OK) return rc;
+      break;
+    }
+    rc = nrse_conv_layer_wgrad(dz, t.act[i - 1], rows, kKernel[i], grads->dw[i - 1], stream);
+    if (rc != NRSE_OK) return rc;
+    rc = nrse_conv_layer_dgrad(dz, rows, wb->wt_even[i - 1], wb->wt_odd[i - 1], kKernel[i], buf[(i - 1) & 1], stream);
     if (rc != NRSE_OK) return rc;
   }
   return NRSE_OK;

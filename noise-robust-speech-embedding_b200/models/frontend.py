@@ -6,10 +6,10 @@ substring matches (ref:src/models/emotion.py:126-129) and ``load_state_dict`` ke
 forward([B,L] fp32) -> [B,512,T] fp32, returned as a transposed VIEW of the kernels' channels-last [B,T,512]
 output -- ``WavLMModel.forward`` transposes it straight back (hf:...:1061), so no copy is ever made.
 
-Backward: the forward kernels are the product of this round.  When a conv parameter requires grad, gradients are
-obtained by re-running the layer stack with stock torch ops on the saved input (activation recomputation through
-cuDNN / ATen).  That keeps ``train_byol.py`` / ``train_emotion.py`` trainable; native dgrad/wgrad kernels are the
-next row of SURVEY.md 8 (see DESIGN.md "out of scope this round").
+Backward: in LayerNorm mode (wavlm-large) the training forward keeps a tape (bf16 activations, normalised
+pre-affine values, 1/std per frame) and the backward runs the native kernels -- LayerNorm+GELU backward, tcgen05
+weight-gradient GEMM with split-K, data-gradient GEMMs (``ops.conv_frontend_backward``).  GroupNorm mode (wavlm-base)
+and the rarely needed waveform gradient fall back to recomputation with stock torch ops (``_FrontendFn``).
 """
 from __future__ import annotations
 
@@ -35,7 +35,32 @@ def _torch_stack(x: torch.Tensor, conv_w, gammas, betas, norm_mode: str) -> torc
     return h
 
 
+class _FrontendNativeFn(torch.autograd.Function):
+    """LayerNorm-mode frontend with the native backward kernels (training forward keeps a tape of activations)."""
+
+    @staticmethod
+    def forward(ctx, x, packed_holder, *params):
+        conv_w, gammas, betas = params[:7], params[7:14], params[14:21]
+        y, tape = ops.conv_frontend_train(x, conv_w, list(gammas), list(betas), packed=packed_holder())
+        ctx.save_for_backward(x, *params)
+        ctx.tape = tape
+        return y.transpose(1, 2)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, *params = ctx.saved_tensors
+        conv_w, gammas, betas = params[:7], params[7:14], params[14:21]
+        dw, dg, db = ops.conv_frontend_backward(x, conv_w, list(gammas), list(betas), ctx.tape, grad_out.transpose(1, 2))
+        ctx.tape = None
+        grads = [*dw, *dg, *db]
+        need = ctx.needs_input_grad[2:]
+        # the waveform gradient is not produced (nothing upstream of the waveform is trainable in the reference)
+        return (None, None, *[g if n else None for g, n in zip(grads, need)])
+
+
 class _FrontendFn(torch.autograd.Function):
+    """Fallback used for GroupNorm mode (wavlm-base): gradients by recomputation with stock torch ops."""
+
     @staticmethod
     def forward(ctx, x, norm_mode, n_norm, packed_holder, *params):
         conv_w = params[:7]
@@ -119,6 +144,8 @@ class B200FeatureEncoder(WavLMFeatureEncoder):
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(
             p.requires_grad for p in (*conv_w, *gammas, *betas)))
         if needs_grad:
+            if self.norm_mode == "layer" and not x.requires_grad:
+                return _FrontendNativeFn.apply(x.float(), self._packed_weights, *conv_w, *gammas, *betas)
             return _FrontendFn.apply(x.float(), self.norm_mode, n_norm, self._packed_weights, *conv_w, *gammas, *betas)
         y = ops.conv_frontend(x, conv_w, gammas, betas, self.norm_mode, out_dtype=self.out_dtype,
                               packed=self._packed_weights())

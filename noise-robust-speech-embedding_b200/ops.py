@@ -13,7 +13,8 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import DTYPE_BF16, DTYPE_F32, NORM_GROUP, NORM_LAYER, FrontendParams, NrseError, check
+from ._lib import (DTYPE_BF16, DTYPE_F32, NORM_GROUP, NORM_LAYER, FrontendBwdWeights, FrontendGrads, FrontendParams,
+                   NrseError, check)
 
 CONV_KERNEL = (10, 3, 3, 3, 3, 2, 2)
 CONV_STRIDE = (5, 2, 2, 2, 2, 2, 2)
@@ -390,3 +391,135 @@ def conv_layer(act_prev: Tensor, w_packed: Tensor, k: int, gamma: Optional[Tenso
     check(lib.nrse_conv_layer_fwd(_ptr(act_prev), rows_prev, _ptr(w_packed), k, 2, _ptr(gamma), _ptr(beta), _ptr(out),
                                   _dtype_code(out), rows_out, _stream()), "nrse_conv_layer_fwd")
     return out
+
+
+# ---- training forward / backward of the conv feature encoder (LayerNorm mode) ------------------------------------------
+def pack_conv_weight_dgrad(w: Tensor) -> Tuple[Tensor, Tensor]:
+    """[512, 512, k] fp32 -> (even [512 c_in, n_even*512], odd [512 c_in, 512]) bf16 operands of the data-gradient GEMMs."""
+    _need_cuda(w)
+    lib = _lib.load()
+    k = w.shape[2]
+    w = w.detach().contiguous().float()
+    even = torch.empty(512, (2 if k == 3 else 1) * 512, dtype=torch.bfloat16, device=w.device)
+    odd = torch.empty(512, 512, dtype=torch.bfloat16, device=w.device)
+    check(lib.nrse_conv_frontend_pack_weights_dgrad(_ptr(w), _ptr(even), _ptr(odd), k, _stream()),
+          "nrse_conv_frontend_pack_weights_dgrad")
+    return even, odd
+
+
+def _frontend_params(w0: Tensor, packed: Sequence[Tensor], gammas: Sequence[Tensor], betas: Sequence[Tensor]) -> FrontendParams:
+    prm = FrontendParams()
+    prm.w0 = w0.data_ptr()
+    for i in range(6):
+        prm.w_packed[i] = packed[i].data_ptr()
+    for i in range(7):
+        prm.gamma[i] = gammas[i].data_ptr()
+        prm.beta[i] = betas[i].data_ptr()
+    return prm
+
+
+def conv_frontend_train(x: Tensor, conv_weights: Sequence[Tensor], gammas: Sequence[Tensor], betas: Sequence[Tensor],
+                        packed: Optional[Sequence[Tensor]] = None) -> Tuple[Tensor, Tensor]:
+    """Training forward (LayerNorm mode): returns (features [B, T, 512] fp32 view, tape).  The tape (uint8 tensor)
+    holds the activations, xhat and 1/std the backward needs; it belongs to the caller (autograd context)."""
+    _need_cuda(x)
+    lib = _lib.load()
+    x = x.contiguous().float()
+    B, L = x.shape
+    T, P = frontend_geometry(L)
+    w0 = conv_weights[0].detach().reshape(512, 10).contiguous().float()
+    if packed is None:
+        packed = [pack_conv_weight(w) for w in conv_weights[1:]]
+    g = [t.detach().contiguous().float() for t in gammas]
+    b = [t.detach().contiguous().float() for t in betas]
+    nbytes = lib.nrse_conv_frontend_tape_bytes(B, L)
+    tape = torch.empty(nbytes + 1024, dtype=torch.uint8, device=x.device)
+    tp, tl = _aligned(tape)
+    y = torch.empty(B, P[6], 512, dtype=torch.float32, device=x.device)
+    prm = _frontend_params(w0, packed, g, b)
+    check(lib.nrse_conv_frontend_fwd_train(_ptr(x), C.byref(prm), _ptr(y), DTYPE_F32, C.c_void_p(tp), tl, B, L, _stream()),
+          "nrse_conv_frontend_fwd_train")
+    return y[:, :T[6], :], tape
+
+
+def conv_frontend_backward(x: Tensor, conv_weights: Sequence[Tensor], gammas: Sequence[Tensor], betas: Sequence[Tensor],
+                           tape: Tensor, grad_features: Tensor,
+                           dgrad_packs: Optional[Sequence[Tuple[Tensor, Tensor]]] = None):
+    """Backward of ``conv_frontend_train``.  grad_features [B, T, 512] (any strides).  Returns
+    (dw: 7 tensors in checkpoint layout [512,1,10] / [512,512,k], dgamma: 7 x [512], dbeta: 7 x [512]), all fp32."""
+    lib = _lib.load()
+    x = x.contiguous().float()
+    B, L = x.shape
+    T, P = frontend_geometry(L)
+    dev = x.device
+    dy = torch.zeros(B, P[6], 512, dtype=torch.float32, device=dev)
+    dy[:, :T[6]] = grad_features
+    w0 = conv_weights[0].detach().reshape(512, 10).contiguous().float()
+    g = [t.detach().contiguous().float() for t in gammas]
+    b = [t.detach().contiguous().float() for t in betas]
+    if dgrad_packs is None:
+        dgrad_packs = [pack_conv_weight_dgrad(w) for w in conv_weights[1:]]
+    prm = FrontendParams()
+    prm.w0 = w0.data_ptr()
+    for i in range(7):
+        prm.gamma[i] = g[i].data_ptr()
+        prm.beta[i] = b[i].data_ptr()
+    wb = FrontendBwdWeights()
+    for i in range(6):
+        wb.wt_even[i] = dgrad_packs[i][0].data_ptr()
+        wb.wt_odd[i] = dgrad_packs[i][1].data_ptr()
+    dw0 = torch.empty(512, 10, dtype=torch.float32, device=dev)
+    dwp = [torch.empty(512, CONV_KERNEL[i] * 512, dtype=torch.float32, device=dev) for i in range(1, 7)]
+    dgam = [torch.empty(512, dtype=torch.float32, device=dev) for _ in range(7)]
+    dbet = [torch.empty(512, dtype=torch.float32, device=dev) for _ in range(7)]
+    gr = FrontendGrads()
+    gr.dw0 = dw0.data_ptr()
+    for i in range(6):
+        gr.dw[i] = dwp[i].data_ptr()
+    for i in range(7):
+        gr.dgamma[i] = dgam[i].data_ptr()
+        gr.dbeta[i] = dbet[i].data_ptr()
+    nbytes = lib.nrse_conv_frontend_bwd_workspace_bytes(B, L)
+    ws = _workspace(nbytes, dev)
+    wp, wl = _aligned(ws)
+    tp, _ = _aligned(tape)
+    check(lib.nrse_conv_frontend_bwd(_ptr(x), C.byref(prm), C.byref(wb), C.c_void_p(tp), _ptr(dy), C.byref(gr),
+                                     C.c_void_p(wp), wl, B, L, _stream()), "nrse_conv_frontend_bwd")
+    dw = [dw0.view(512, 1, 10)] + [d.view(512, CONV_KERNEL[i + 1], 512).permute(0, 2, 1).contiguous()
+                                    for i, d in enumerate(dwp)]
+    return dw, dgam, dbet
+
+
+# per-kernel hooks (parity tests)
+def ln_gelu_bwd(dout: Tensor, xhat: Tensor, rstd: Tensor, gamma: Tensor, beta: Tensor, P: int, T: int):
+    lib = _lib.load()
+    rows = xhat.shape[0]
+    dz = torch.empty(rows, 512, dtype=torch.bfloat16, device=xhat.device)
+    dg = torch.zeros(512, dtype=torch.float32, device=xhat.device)
+    db = torch.zeros(512, dtype=torch.float32, device=xhat.device)
+    check(lib.nrse_ln_gelu_bwd(_ptr(dout.contiguous()), _dtype_code(dout), _ptr(xhat), _ptr(rstd), _ptr(gamma), _ptr(beta),
+                               _ptr(dz), _ptr(dg), _ptr(db), rows, P, T, _stream()), "nrse_ln_gelu_bwd")
+    return dz, dg, db
+
+
+def conv_layer_wgrad(dz: Tensor, act_prev: Tensor, k: int) -> Tensor:
+    lib = _lib.load()
+    dw = torch.zeros(512, k * 512, dtype=torch.float32, device=dz.device)
+    check(lib.nrse_conv_layer_wgrad(_ptr(dz), _ptr(act_prev), dz.shape[0], k, _ptr(dw), _stream()), "nrse_conv_layer_wgrad")
+    return dw
+
+
+def conv_layer_dgrad(dz: Tensor, wt_even: Tensor, wt_odd: Tensor, k: int) -> Tensor:
+    lib = _lib.load()
+    dx = torch.empty(2 * dz.shape[0], 512, dtype=torch.bfloat16, device=dz.device)
+    check(lib.nrse_conv_layer_dgrad(_ptr(dz), dz.shape[0], _ptr(wt_even), _ptr(wt_odd), k, _ptr(dx), _stream()),
+          "nrse_conv_layer_dgrad")
+    return dx
+
+
+def conv_layer0_wgrad(x: Tensor, dz0: Tensor, T0: int, P0: int) -> Tensor:
+    lib = _lib.load()
+    B, L = x.shape
+    dw0 = torch.zeros(512, 10, dtype=torch.float32, device=x.device)
+    check(lib.nrse_conv_layer0_wgrad(_ptr(x), _ptr(dz0), _ptr(dw0), B, L, T0, P0, _stream()), "nrse_conv_layer0_wgrad")
+    return dw0
