@@ -376,7 +376,53 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
                     "achieved": 8.0 * B * 1024 / (t_loss * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s"})
     for kk in kernels:
         kk["frac"] = kk["achieved"] / kk["peak"]
-    return {"roofline": roofline, "kernels": kernels}
+
+    # training forward (tape-writing) + native backward of the frontend, and the same stack in stock torch on THIS GPU
+    # (cuDNN conv1d + ATen layer_norm / gelu): the "kernel to beat" of BASELINE.md section 4 (G0)
+    import torch.nn.functional as F
+    x = c
+    dpacks = [ops.pack_conv_weight_dgrad(w) for w in conv_w[1:]]
+    gy = torch.randn(B, T[6], 512, device=dev)
+
+    def plain(fn, n=3):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    y_t, tape = ops.conv_frontend_train(x, conv_w, gammas, betas, packed=packed)
+    t_train = plain(lambda: ops.conv_frontend_train(x, conv_w, gammas, betas, packed=packed))
+    t_bwd = plain(lambda: ops.conv_frontend_backward(x, conv_w, gammas, betas, tape, gy, dgrad_packs=dpacks))
+    t_inf = plain(lambda: ops.conv_frontend(x, conv_w, gammas, betas, "layer", out_dtype=torch.bfloat16, packed=packed))
+    ws = [w.clone().requires_grad_(True) for w in conv_w]
+    gs = [w.clone().requires_grad_(True) for w in gammas]
+    bs = [w.clone().requires_grad_(True) for w in betas]
+
+    def stock(xx):
+        h = xx[:, None]
+        for i, wt in enumerate(ws):
+            h = F.conv1d(h, wt, stride=ops.CONV_STRIDE[i])
+            h = F.gelu(F.layer_norm(h.transpose(1, 2), (512,), gs[i], bs[i], 1e-5).transpose(1, 2))
+        return h
+
+    stock_res = {}
+    for name, ac in (("fp32", False), ("bf16_autocast", True)):
+        def fo():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                return stock(x)
+
+        def fb():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                out = stock(x)
+            out.backward(gy.transpose(1, 2).to(out.dtype))
+        stock_res[name] = {"fwd_ms": plain(fo), "fwd_bwd_ms": plain(fb)}
+    frontend_train = {"shape": [B, L], "fwd_ms": t_inf, "train_fwd_ms": t_train, "bwd_ms": t_bwd,
+                      "fwd_bwd_ms": t_train + t_bwd, "stock_torch_same_gpu": stock_res,
+                      "note": "host-launched (not graph-timed): includes Python/launch overhead of the op wrappers"}
+    return {"roofline": roofline, "kernels": kernels, "frontend_train": frontend_train}
 
 
 def main():

@@ -7,6 +7,7 @@ Every function requires CUDA tensors on an sm_100 device and raises otherwise: t
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -253,6 +254,7 @@ def cosine_rows(a: Tensor, b: Tensor) -> Tensor:
 # --------------------------------------------------------------------------------------------------------------
 # conv feature encoder
 # --------------------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=256)
 def frontend_geometry(n_samples: int) -> Tuple[List[int], List[int]]:
     """(T_i, P_i): valid frames and per-utterance frame pitch of each conv layer's channels-last output."""
     lib = _lib.load()

@@ -1,0 +1,56 @@
+"""Device time of the conv feature encoder training forward + native backward at the BASELINE shape (64 x 4 s)."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from nrse_b200 import ops
+from nrse_b200.utils import synthetic
+
+dev = torch.device("cuda:0")
+B, L = 64, 64000
+layers = synthetic.frontend_weights("layer", seed=0)
+x = synthetic.waveforms(B, L, seed=1)[0]
+x = torch.from_numpy(((x - x.mean(1, keepdims=True)) / x.std(1, keepdims=True)).astype("float32")).to(dev)
+w = [torch.from_numpy(l["conv"]).to(dev) for l in layers]
+g = [torch.from_numpy(l["gamma"]).to(dev) for l in layers]
+b = [torch.from_numpy(l["beta"]).to(dev) for l in layers]
+packed = [ops.pack_conv_weight(t) for t in w[1:]]
+dpacks = [ops.pack_conv_weight_dgrad(t) for t in w[1:]]
+T, P = ops.frontend_geometry(L)
+gy = torch.randn(B, T[6], 512, device=dev)
+
+def timeit(fn, n=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        out = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n, out
+
+t_fwd, _ = timeit(lambda: ops.conv_frontend(x, w, g, b, "layer", out_dtype=torch.bfloat16, packed=packed))
+t_train, (y, tape) = timeit(lambda: ops.conv_frontend_train(x, w, g, b, packed=packed))
+t_bwd, _ = timeit(lambda: ops.conv_frontend_backward(x, w, g, b, tape, gy, dgrad_packs=dpacks))
+fwd_flops = sum(2.0 * B * T[i] * 512 * 512 * k for i, k in enumerate((10, 3, 3, 3, 3, 2, 2)) if i > 0)
+# stock torch (cuDNN / ATen) forward+backward of the same stack for comparison, fp32 and bf16 autocast
+import torch.nn.functional as F
+def torch_stack(xx, ws, gs, bs):
+    h = xx[:, None]
+    for i, wt in enumerate(ws):
+        h = F.conv1d(h, wt, stride=ops.CONV_STRIDE[i])
+        h = F.layer_norm(h.transpose(1, 2), (512,), gs[i], bs[i], 1e-5).transpose(1, 2)
+        h = F.gelu(h)
+    return h
+ws = [t.clone().requires_grad_(True) for t in w]; gs = [t.clone().requires_grad_(True) for t in g]; bs = [t.clone().requires_grad_(True) for t in b]
+res = {}
+for name, ac in (("fp32", False), ("bf16_autocast", True)):
+    def fb():
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+            out = torch_stack(x, ws, gs, bs)
+        out.backward(gy.transpose(1, 2).to(out.dtype))
+    def fo():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+            return torch_stack(x, ws, gs, bs)
+    res[name] = {"fwd_ms": timeit(fo, 3)[0], "fwd_bwd_ms": timeit(fb, 3)[0]}
+print(json.dumps({"shape": [B, L], "fwd_ms": t_fwd, "train_fwd_ms": t_train, "bwd_ms": t_bwd,
+                  "bwd_tflops_2x_fwd_gemm": 2 * fwd_flops / (t_bwd * 1e-3) / 1e12,
+                  "stock_torch_on_this_gpu": res}))

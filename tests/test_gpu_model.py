@@ -160,3 +160,20 @@ def test_train_and_validate_loops(dev):
     assert check_audio_tensor(torch.ones(4, device=dev), "ones", cfg)
     assert not check_audio_tensor(torch.tensor([1.0, float("nan")], device=dev), "nan", cfg)
     assert not check_audio_tensor(torch.zeros(4, device=dev), "zeros", cfg)
+
+
+def test_device_prefetcher_overlaps_and_preserves_batches(dev):
+    from nrse_b200.data import DevicePrefetcher
+    batches = [{"a": torch.full((4, 1000), float(i)).pin_memory(), "i": torch.tensor([i]).pin_memory()} for i in range(5)]
+    pf = DevicePrefetcher(dev, depth=2)
+    seen = []
+    for b in pf.iterate(batches):
+        assert b["a"].is_cuda
+        seen.append((int(b["i"].item()), float(b["a"].mean().item())))
+    assert seen == [(i, float(i)) for i in range(5)]
+    # manual put / get / release protocol used by bench.py
+    pf.put(batches[3]); pf.put(batches[4])
+    assert int(pf.get()["i"].item()) == 3
+    pf.release()
+    assert int(pf.get()["i"].item()) == 4
+    pf.release()

@@ -99,3 +99,23 @@ def test_synthetic_is_deterministic():
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
     assert synthetic.conv_out_lengths(64000) == [12799, 6399, 3199, 1599, 799, 399, 199]
+
+
+def test_single_mufu_gelu_fit_is_exact_gelu():
+    """The CUDA epilogue evaluates erf-GELU as relu(x) - 0.5*min(|x|,5.6)*2^-q(u) with a degree-5 fit q of
+    -log2 erfc(u/sqrt2) (csrc/frontend.cu::gelu2 / gelu_grad).  Pin that formula, evaluated in float32 on the CPU,
+    against torch's exact GELU and its derivative: the error must stay far below one bf16 ulp."""
+    c = np.array([1.1510953903198242, 0.4592348039150238, 0.05259089171886444, -0.007414255291223526,
+                  0.0005235913558863103], dtype=np.float32)
+    x = np.linspace(-9, 9, 200001).astype(np.float32)
+    u = np.minimum(np.abs(x), np.float32(5.6))
+    q = ((((c[4] * u + c[3]) * u + c[2]) * u + c[1]) * u + c[0]) * u
+    e = np.exp2(-q).astype(np.float32)                                    # erfc(u / sqrt 2)
+    gelu = np.maximum(x, 0) - np.float32(0.5) * u * e
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    ref = torch.nn.functional.gelu(xt)
+    ref.sum().backward()
+    assert np.abs(gelu - ref.detach().numpy()).max() < 3e-6               # bf16 ulp at |x|~1 is 4e-3
+    cdf = np.where(x >= 0, 1 - 0.5 * e, 0.5 * e)
+    grad = cdf + x * np.float32(0.3989422804) * np.exp(-0.5 * x.astype(np.float64) ** 2)
+    assert np.abs(grad - xt.grad.numpy()).max() < 3e-6
