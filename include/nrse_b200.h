@@ -170,6 +170,9 @@ int nrse_conv_layer_fwd(const void* act_prev, int64_t rows_prev, const void* w_p
 int nrse_conv_frontend_set_variant(int variant);
 /* Layer-0 kernel in LayerNorm mode: 0 = SIMT (warp per frame), 1 = tensor cores (hi/lo-split K=32 UMMA, default). */
 int nrse_conv_frontend_set_layer0_variant(int variant);
+/* 1: the TMA producer of the GEMM layers bulk-prefetches the next tile's input frames into L2 (default 0: measured
+ * 2-3 % slower at 64 x 4 s -- the operand feed is not HBM-latency bound). */
+int nrse_conv_frontend_set_l2_prefetch(int on);
 
 /* ---------------------------------------------------------------------------------------------
  * Training forward and backward of the feature encoder (LayerNorm mode; wavlm-large).

@@ -55,6 +55,14 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(fabsf(half_x), erf_abs, half_x);  // 0.5x + 0.5|x| erf(|x|/sqrt2) = 0.5x(1 + erf(x/sqrt2))
 }
 
+// 256-bit global store (STG.256 on sm_100): one full 32-byte sector per thread per instruction; p 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                              uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -285,6 +293,10 @@ struct GemmArgs {
   int a_2d;
   int a_row_off[2];
   int out_row_mul, out_row_add;
+  // L2 prefetch of the NEXT tile's A rows (they come from HBM; the weights are L2-resident): base pointer and row count
+  const char* a_ptr;
+  long long a_rows;
+  int l2_prefetch;
 };
 
 // ---- epilogue of one accumulator row (shared by the GEMM layers and the tensor-core layer 0) ----------------
@@ -360,7 +372,7 @@ __device__ __forceinline__ f2 gelu2(f2 x) {
   return f2_fma(f2_mul(u, f2_make(e0, e1)), f2_make(-0.5f, -0.5f), f2_make(r0, r1));
 }
 
-template <int kClusterN>
+template <int kClusterN, bool kSave>
 __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
   constexpr int kNPC = kC / kClusterN;
   constexpr int kChunks = kNPC / 32;
@@ -417,21 +429,24 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
     }
     mean = mean_c;
     rstd = rsqrtf(m2 * (1.0f / kC) + kNormEps);
-    if (e.rstd_out != nullptr && e.store) *e.rstd_out = rstd;
+    if constexpr (kSave) {
+      if (e.rstd_out != nullptr && e.store) *e.rstd_out = rstd;
+    }
   }
 
   // pass 2: normalise, GELU, store this row's channels.  v = (x*rstd - mean*rstd) * gamma + beta
   const f2 rstd2 = f2_make(rstd, rstd);
   const f2 nmr2 = f2_make(-mean * rstd, -mean * rstd);
   auto emit32 = [&](const uint32_t (&r)[32], int c) {
-    uint32_t o16[16], xh16[16];
+    uint32_t o16[16];
+    [[maybe_unused]] uint32_t xh16[kSave ? 16 : 1];
     float o32[32];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       f2 x = f2_bits(r[2 * j], r[2 * j + 1]);
       if (e.has_norm) {
         x = f2_fma(x, rstd2, nmr2);
-        if (e.xhat_row != nullptr) {
+        if constexpr (kSave) {
           float h0, h1;
           f2_split(x, h0, h1);
           xh16[j] = pack_bf16x2(h0, h1);
@@ -444,24 +459,36 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
       o32[2 * j] = y0;
       o32[2 * j + 1] = y1;
     }
-    if (e.store && e.has_norm && e.xhat_row != nullptr) {
-      uint4* dst = reinterpret_cast<uint4*>(e.xhat_row + c * 32);
+    if constexpr (kSave) {
+      if (e.store && e.has_norm && e.xhat_row != nullptr) {
+        char* dst = reinterpret_cast<char*>(e.xhat_row + c * 32);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        dst[j] = e.zero ? make_uint4(0, 0, 0, 0) : make_uint4(xh16[4 * j], xh16[4 * j + 1], xh16[4 * j + 2], xh16[4 * j + 3]);
+        for (int j = 0; j < 2; ++j) {
+          if (e.zero) st_global_256(dst + 32 * j, 0, 0, 0, 0, 0, 0, 0, 0);
+          else st_global_256(dst + 32 * j, xh16[8 * j], xh16[8 * j + 1], xh16[8 * j + 2], xh16[8 * j + 3], xh16[8 * j + 4],
+                             xh16[8 * j + 5], xh16[8 * j + 6], xh16[8 * j + 7]);
+        }
+      }
     }
     if (e.store) {
       if (e.out_f32) {
-        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out_row) + c * 32);
+        char* dst = reinterpret_cast<char*>(reinterpret_cast<float*>(e.out_row) + c * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = e.zero ? make_float4(0.f, 0.f, 0.f, 0.f)
-                          : make_float4(o32[4 * j], o32[4 * j + 1], o32[4 * j + 2], o32[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) {
+          if (e.zero) st_global_256(dst + 32 * j, 0, 0, 0, 0, 0, 0, 0, 0);
+          else st_global_256(dst + 32 * j, __float_as_uint(o32[8 * j]), __float_as_uint(o32[8 * j + 1]),
+                             __float_as_uint(o32[8 * j + 2]), __float_as_uint(o32[8 * j + 3]),
+                             __float_as_uint(o32[8 * j + 4]), __float_as_uint(o32[8 * j + 5]),
+                             __float_as_uint(o32[8 * j + 6]), __float_as_uint(o32[8 * j + 7]));
+        }
       } else {
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out_row) + c * 32);
+        char* dst = reinterpret_cast<char*>(reinterpret_cast<__nv_bfloat16*>(e.out_row) + c * 32);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[j] = e.zero ? make_uint4(0, 0, 0, 0) : make_uint4(o16[4 * j], o16[4 * j + 1], o16[4 * j + 2], o16[4 * j + 3]);
+        for (int j = 0; j < 2; ++j) {
+          if (e.zero) st_global_256(dst + 32 * j, 0, 0, 0, 0, 0, 0, 0, 0);
+          else st_global_256(dst + 32 * j, o16[8 * j], o16[8 * j + 1], o16[8 * j + 2], o16[8 * j + 3], o16[8 * j + 4],
+                             o16[8 * j + 5], o16[8 * j + 6], o16[8 * j + 7]);
+        }
       }
     }
   };
@@ -490,13 +517,14 @@ __device__ __forceinline__ void epilogue_plain_row(uint32_t taddr, uint32_t bar_
   uint32_t ra[32], rb[32];
   auto emit = [&](const uint32_t (&r)[32], int c) {
     if (!store) return;
-    uint4* dst = reinterpret_cast<uint4*>(out_row + c * 32);
+    char* dst = reinterpret_cast<char*>(out_row + c * 32);
+    uint32_t o[16];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      dst[j] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])),
-                          pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
-                          pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
-                          pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+    for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      st_global_256(dst + 32 * j, o[8 * j], o[8 * j + 1], o[8 * j + 2], o[8 * j + 3], o[8 * j + 4], o[8 * j + 5],
+                    o[8 * j + 6], o[8 * j + 7]);
   };
   ptx::tmem_ld32(taddr, ra);
 #pragma unroll 1
@@ -515,7 +543,7 @@ __device__ __forceinline__ void epilogue_plain_row(uint32_t taddr, uint32_t bar_
   }
 }
 
-template <int kClusterN>
+template <int kClusterN, bool kSave>
 __global__ void __launch_bounds__(GemmCfg<kClusterN>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const GemmArgs g) {
@@ -577,6 +605,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       for (int tile = first_tile; tile < g.num_tiles; tile += tile_step) {
         const int m0 = tile * kBlockM;
+        if (g.l2_prefetch && cta_rank == 0 && tile + tile_step < g.num_tiles) {
+          // the next tile's input frames are one contiguous range of the previous activation
+          const long long nm0 = static_cast<long long>(tile + tile_step) * kBlockM;
+          long long r0 = g.a_2d ? nm0 - 1 : nm0 * g.stride;
+          long long r1 = g.a_2d ? nm0 + kBlockM : (nm0 + kBlockM) * g.stride + 2;
+          r0 = r0 < 0 ? 0 : r0;
+          r1 = r1 > g.a_rows ? g.a_rows : r1;
+          const char* src = g.a_ptr + r0 * (kC * 2);
+          for (long long left = (r1 - r0) * (kC * 2); left > 0; left -= 65536, src += 65536)
+            ptx::prefetch_l2_bulk(src, static_cast<uint32_t>(left < 65536 ? left : 65536));
+        }
         for (int kb = 0; kb < g.k_stages; ++kb) {
           ptx::mbar_wait(bar(kEmpty + stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
@@ -671,7 +710,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                              : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(g.out) + m * kC + n0);
       ec.xhat_row = g.xhat ? reinterpret_cast<__nv_bfloat16*>(g.xhat) + m * kC + n0 : nullptr;
       ec.rstd_out = (g.rstd && n0 == 0) ? g.rstd + m : nullptr;
-      epilogue_row<kClusterN>(ec);
+      epilogue_row<kClusterN, kSave>(ec);
     }
   }
 
@@ -737,7 +776,7 @@ __device__ __forceinline__ void l0_split(const float (&v)[10], uint32_t (&hi)[5]
   }
 }
 
-template <int kClusterN>
+template <int kClusterN, bool kSave>
 __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_kernel(const L0Args a) {
   using Cfg = L0tcCfg<kClusterN>;
   extern __shared__ uint8_t smem_raw[];
@@ -894,7 +933,7 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
       ec.out_row = a.out + m * kC + n0;
       ec.xhat_row = a.xhat ? a.xhat + m * kC + n0 : nullptr;
       ec.rstd_out = (a.rstd && n0 == 0) ? a.rstd + m : nullptr;
-      epilogue_row<kClusterN>(ec);
+      epilogue_row<kClusterN, kSave>(ec);
     }
   }
 
@@ -1283,14 +1322,15 @@ int make_tmap_rows(CUtensorMap* m, const void* ptr, int64_t rows, int box_rows) 
   return r == CUDA_SUCCESS ? NRSE_OK : NRSE_ERR_CUDA;
 }
 
+int g_l2_prefetch = 0;  // 1: producer bulk-prefetches the next tile's A rows into L2 (measured 2-3 % slower: off)
 int g_variant = 2;  // 1: single CTA per tile, 2: 2-CTA cluster splitting the channels (default)
 
-template <int kClusterN>
+template <int kClusterN, bool kSave = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<kClusterN>;
   static bool attr_set = false;  // benign race: the attribute is idempotent
   if (!attr_set) {
-    NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<kClusterN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<kClusterN, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -1308,16 +1348,16 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmArgs& g,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<kClusterN>, ta, tw, g));
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<kClusterN, kSave>, ta, tw, g));
   return NRSE_OK;
 }
 
-template <int kClusterN>
+template <int kClusterN, bool kSave = false>
 int launch_layer0_tc(const L0Args& a, cudaStream_t stream) {
   using Cfg = L0tcCfg<kClusterN>;
   static bool attr_set = false;
   if (!attr_set) {
-    NRSE_CUDA_TRY(cudaFuncSetAttribute(layer0_tc_kernel<kClusterN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(layer0_tc_kernel<kClusterN, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -1337,7 +1377,7 @@ int launch_layer0_tc(const L0Args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, layer0_tc_kernel<kClusterN>, a));
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, layer0_tc_kernel<kClusterN, kSave>, a));
   return NRSE_OK;
 }
 
@@ -1409,6 +1449,11 @@ int nrse_conv_frontend_set_variant(int variant) {
   return NRSE_OK;
 }
 
+int nrse_conv_frontend_set_l2_prefetch(int on) {
+  nrse::g_l2_prefetch = on ? 1 : 0;
+  return NRSE_OK;
+}
+
 int nrse_conv_frontend_set_layer0_variant(int variant) {
   if (variant != 0 && variant != 1) return NRSE_ERR_INVALID_ARG;
   nrse::g_layer0_variant = variant;
@@ -1441,7 +1486,8 @@ static int layer0_fwd_impl(const float* x, const float* w0, const float* gamma, 
   const long long want = ceil_div(rows, static_cast<long long>(kL0Warps));
   const unsigned grid = static_cast<unsigned>(want < kNumSMs ? want : kNumSMs);
   if (norm_mode == NRSE_NORM_LAYER) {
-    if (g_layer0_variant == 1 || xhat != nullptr) return g_variant == 2 ? launch_layer0_tc<2>(a, s) : launch_layer0_tc<1>(a, s);
+    if (xhat != nullptr) return g_variant == 2 ? launch_layer0_tc<2, true>(a, s) : launch_layer0_tc<1, true>(a, s);
+    if (g_layer0_variant == 1) return g_variant == 2 ? launch_layer0_tc<2>(a, s) : launch_layer0_tc<1>(a, s);
     layer0_kernel<false><<<grid, kL0Threads, 0, s>>>(a);
     NRSE_CHECK_LAUNCH();
     return NRSE_OK;
@@ -1496,6 +1542,11 @@ static int layer_fwd_impl(const void* act_prev, int64_t rows_prev, const void* w
   g.a_row_off[0] = g.a_row_off[1] = 0;
   g.out_row_mul = 1;
   g.out_row_add = 0;
+  g.a_ptr = reinterpret_cast<const char*>(act_prev);
+  g.a_rows = rows_prev;
+  g.l2_prefetch = g_l2_prefetch;
+  if (xhat != nullptr)
+    return g_variant == 2 ? launch_gemm<2, true>(ta, tw, g, as_stream(stream)) : launch_gemm<1, true>(ta, tw, g, as_stream(stream));
   return g_variant == 2 ? launch_gemm<2>(ta, tw, g, as_stream(stream)) : launch_gemm<1>(ta, tw, g, as_stream(stream));
 }
 
@@ -1669,6 +1720,9 @@ int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even,
     g.a_row_off[1] = -1;   // even, k = 3: tap 2 <- dZ[m - 1]
     g.out_row_mul = 2;
     g.out_row_add = parity;
+    g.a_ptr = reinterpret_cast<const char*>(dz);
+    g.a_rows = rows_out;
+    g.l2_prefetch = g_l2_prefetch;
     rc = g_variant == 2 ? launch_gemm<2>(ta, tw, g, as_stream(stream)) : launch_gemm<1>(ta, tw, g, as_stream(stream));
     if (rc != NRSE_OK) return rc;
   }
