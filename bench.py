@@ -338,8 +338,15 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
         per_layer.append({"layer": i, "ms": t, "tflops": flops / (t * 1e-3) / 1e12})
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of the six launches, from the ncu capture
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["traffic_bytes_six_launches"], tj["source"]
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (layers 1-6, tcgen05 implicit GEMM + LayerNorm + GELU)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_unit": "bytes per 6 launches (one view)", "traffic_source": traffic_src,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed back to back)",
                 "launches": 6, "ms_per_view": gemm_ms, "algorithmic_flops_per_view": gemm_flops, "per_layer": per_layer}
 
