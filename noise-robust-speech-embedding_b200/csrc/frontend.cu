@@ -972,20 +972,6 @@ struct LnBwdArgs {
   int P, T;
 };
 
-// d/dv [ v Phi(v) ] = Phi(v) + v phi(v), Phi from the same erfc fit as the forward
-__device__ __forceinline__ float gelu_grad(float v) {
-  const float u = fminf(fabsf(v), 5.6f);
-  float q = fmaf(u, -0.0005235913558863103f, 0.007414255291223526f);
-  q = fmaf(q, u, -0.05259089171886444f);
-  q = fmaf(q, u, -0.4592348039150238f);
-  q = fmaf(q, u, -1.1510953903198242f);
-  float e, g;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q * u));                          // erfc(|v|/sqrt2)
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(v * v * (-0.5f * 1.44269504f)));  // exp(-v^2/2)
-  const float cdf = v >= 0.f ? fmaf(-0.5f, e, 1.0f) : 0.5f * e;
-  return fmaf(v * 0.3989422804f, g, cdf);
-}
-
 __device__ __forceinline__ void unpack_bf16x8(const uint4& a, float (&x)[8]) {
   const unsigned w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
@@ -993,6 +979,31 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& a, float (&x)[8]) {
     x[2 * j] = __uint_as_float(w[j] << 16);
     x[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
   }
+}
+
+// gelu'(v) for two values with ONE MUFU each:  for u = |v|,  1 - gelu'(u) = phi(u) (mills(u) - u)  and
+// gelu'(-u) = 1 - gelu'(u);  r(u) = 0.39894 (mills(u) - u) is a degree-6 fit on [0, 5.6] (max abs error of gelu'
+// 2.6e-5, two orders below bf16 resolution), so gelu'(v) = 0.5 + copysign(0.5 - exp(-v^2/2) r(|v|), v).
+__device__ __forceinline__ f2 gelu_grad2(f2 v) {
+  float v0, v1;
+  f2_split(v, v0, v1);
+  const f2 u = f2_make(fminf(fabsf(v0), 5.6f), fminf(fabsf(v1), 5.6f));
+  constexpr float k = 0.3989422804f;
+  f2 r = f2_fma(u, f2_make(k * 0.0016475850716233253f, k * 0.0016475850716233253f),
+                f2_make(k * -0.019207235425710678f, k * -0.019207235425710678f));
+  r = f2_fma(r, u, f2_make(k * 0.09663444012403488f, k * 0.09663444012403488f));
+  r = f2_fma(r, u, f2_make(k * -0.2893761098384857f, k * -0.2893761098384857f));
+  r = f2_fma(r, u, f2_make(k * 0.6104238033294678f, k * 0.6104238033294678f));
+  r = f2_fma(r, u, f2_make(k * -1.9976462125778198f, k * -1.9976462125778198f));
+  r = f2_fma(r, u, f2_make(k * 1.2532488107681274f, k * 1.2532488107681274f));
+  float q0, q1;
+  f2_split(f2_mul(f2_mul(u, u), f2_make(-0.72134752f, -0.72134752f)), q0, q1);  // -u^2/2 * log2(e)
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+  float h0, h1;
+  f2_split(f2_fma(f2_mul(f2_make(e0, e1), r), f2_make(-1.f, -1.f), f2_make(0.5f, 0.5f)), h0, h1);  // 0.5 - (1 - gelu'(u))
+  return f2_add(f2_make(0.5f, 0.5f), f2_make(copysignf(h0, v0), copysignf(h1, v1)));
 }
 
 __global__ void __launch_bounds__(kLnBwdThreads) ln_gelu_bwd_kernel(const LnBwdArgs a) {
@@ -1005,9 +1016,18 @@ __global__ void __launch_bounds__(kLnBwdThreads) ln_gelu_bwd_kernel(const LnBwdA
     s_beta[i] = a.beta[i];
   }
   __syncthreads();
-  float dg[16], db[16];
+  // lane owns channels [8 lane, 8 lane + 8) and [256 + 8 lane, ...): 8 adjacent pairs, processed as packed fp32x2
+  f2 g2[8], b2[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) dg[j] = db[j] = 0.f;
+  for (int j = 0; j < 8; ++j) {
+    const int c = l0_channel(lane, 2 * j);
+    g2[j] = f2_make(s_gamma[c], s_gamma[c + 1]);
+    b2[j] = f2_make(s_beta[c], s_beta[c + 1]);
+  }
+  const f2 zero2 = f2_make(0.f, 0.f);
+  f2 dg[8], db[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dg[j] = db[j] = zero2;
 
   const long long warps_total = static_cast<long long>(gridDim.x) * kLnBwdWarps;
   for (long long m = static_cast<long long>(blockIdx.x) * kLnBwdWarps + warp; m < a.rows; m += warps_total) {
@@ -1017,51 +1037,72 @@ __global__ void __launch_bounds__(kLnBwdThreads) ln_gelu_bwd_kernel(const LnBwdA
       zrow[32 + lane] = make_uint4(0, 0, 0, 0);
       continue;
     }
-    float go[16], xh[16];
-    const uint4* xr = reinterpret_cast<const uint4*>(a.xhat + m * kC);
-    unpack_bf16x8(__ldg(xr + lane), *reinterpret_cast<float(*)[8]>(&xh[0]));
-    unpack_bf16x8(__ldg(xr + 32 + lane), *reinterpret_cast<float(*)[8]>(&xh[8]));
+    f2 go[8], xh[8];
+    {
+      const uint4* xr = reinterpret_cast<const uint4*>(a.xhat + m * kC);
+      const uint4 x0 = __ldg(xr + lane), x1 = __ldg(xr + 32 + lane);
+      const unsigned w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xh[j] = f2_bits(w[j] << 16, w[j] & 0xffff0000u);
+    }
     if (a.dout_f32) {
       const float4* gr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.dout) + m * kC);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const float4 p0 = gr[h * 64 + 2 * lane], p1 = gr[h * 64 + 2 * lane + 1];
-        go[h * 8 + 0] = p0.x; go[h * 8 + 1] = p0.y; go[h * 8 + 2] = p0.z; go[h * 8 + 3] = p0.w;
-        go[h * 8 + 4] = p1.x; go[h * 8 + 5] = p1.y; go[h * 8 + 6] = p1.z; go[h * 8 + 7] = p1.w;
+        go[h * 4 + 0] = f2_make(p0.x, p0.y);
+        go[h * 4 + 1] = f2_make(p0.z, p0.w);
+        go[h * 4 + 2] = f2_make(p1.x, p1.y);
+        go[h * 4 + 3] = f2_make(p1.z, p1.w);
       }
     } else {
       const uint4* gr = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.dout) + m * kC);
-      unpack_bf16x8(gr[lane], *reinterpret_cast<float(*)[8]>(&go[0]));
-      unpack_bf16x8(gr[32 + lane], *reinterpret_cast<float(*)[8]>(&go[8]));
-    }
-    float dx[16], s1 = 0.f, s2 = 0.f;
+      const uint4 y0 = gr[lane], y1 = gr[32 + lane];
+      const unsigned w[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int c = l0_channel(lane, j);
-      const float gm = s_gamma[c];
-      const float dv = go[j] * gelu_grad(fmaf(xh[j], gm, s_beta[c]));
-      dg[j] = fmaf(dv, xh[j], dg[j]);
-      db[j] += dv;
-      dx[j] = dv * gm;
-      s1 += dx[j];
-      s2 = fmaf(dx[j], xh[j], s2);
+      for (int j = 0; j < 8; ++j) go[j] = f2_bits(w[j] << 16, w[j] & 0xffff0000u);
     }
-    s1 = warp_sum(s1) * (1.0f / kC);
-    s2 = warp_sum(s2) * (1.0f / kC);
+    f2 dx[8], s1 = zero2, s2 = zero2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const f2 dv = f2_mul(go[j], gelu_grad2(f2_fma(xh[j], g2[j], b2[j])));
+      dg[j] = f2_fma(dv, xh[j], dg[j]);
+      db[j] = f2_add(db[j], dv);
+      dx[j] = f2_mul(dv, g2[j]);
+      s1 = f2_add(s1, dx[j]);
+      s2 = f2_fma(dx[j], xh[j], s2);
+    }
+    float m1, m2;
+    {
+      float a0, a1, c0, c1;
+      f2_split(s1, a0, a1);
+      f2_split(s2, c0, c1);
+      m1 = warp_sum(a0 + a1) * (1.0f / kC);
+      m2 = warp_sum(c0 + c1) * (1.0f / kC);
+    }
     const float rs = __ldg(a.rstd + m);
-    float z[16];
+    const f2 rs2 = f2_make(rs, rs), nm1 = f2_make(-m1 * rs, -m1 * rs), nm2 = f2_make(-m2 * rs, -m2 * rs);
+    uint32_t z[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) z[j] = rs * (dx[j] - s1 - xh[j] * s2);
-    zrow[lane] = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]),
-                            pack_bf16x2(z[6], z[7]));
-    zrow[32 + lane] = make_uint4(pack_bf16x2(z[8], z[9]), pack_bf16x2(z[10], z[11]), pack_bf16x2(z[12], z[13]),
-                                 pack_bf16x2(z[14], z[15]));
+    for (int j = 0; j < 8; ++j) {  // rstd (dx - m1 - xhat m2)
+      float z0, z1;
+      f2_split(f2_fma(xh[j], nm2, f2_fma(dx[j], rs2, nm1)), z0, z1);
+      z[j] = pack_bf16x2(z0, z1);
+    }
+    zrow[lane] = make_uint4(z[0], z[1], z[2], z[3]);
+    zrow[32 + lane] = make_uint4(z[4], z[5], z[6], z[7]);
   }
   // CTA-level reduction of the affine gradients, then one atomic per channel per CTA
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    s_acc[warp][l0_channel(lane, j)] = dg[j];
-    s_acc[warp][kC + l0_channel(lane, j)] = db[j];
+  for (int j = 0; j < 8; ++j) {
+    const int c = l0_channel(lane, 2 * j);
+    float a0, a1;
+    f2_split(dg[j], a0, a1);
+    s_acc[warp][c] = a0;
+    s_acc[warp][c + 1] = a1;
+    f2_split(db[j], a0, a1);
+    s_acc[warp][kC + c] = a0;
+    s_acc[warp][kC + c + 1] = a1;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * kC; i += kLnBwdThreads) {
