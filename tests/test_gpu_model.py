@@ -169,7 +169,7 @@ def test_device_prefetcher_overlaps_and_preserves_batches(dev):
     seen = []
     for b in pf.iterate(batches):
         assert b["a"].is_cuda
-        seen.append((int(b["i"].item()), float(b["a"].mean().item())))
+        seen.append((int(b["i"].item()), float(b["a"][3, 999].item())))
     assert seen == [(i, float(i)) for i in range(5)]
     # manual put / get / release protocol used by bench.py
     pf.put(batches[3]); pf.put(batches[4])
@@ -177,3 +177,28 @@ def test_device_prefetcher_overlaps_and_preserves_batches(dev):
     pf.release()
     assert int(pf.get()["i"].item()) == 4
     pf.release()
+
+
+def test_partial_unfreeze_like_emotion_finetune(dev):
+    """ref:src/models/emotion.py:114-129 unfreezes encoder parameters whose NAME contains ``layers.{i}`` -- which also
+    matches ``feature_extractor.conv_layers.{i}``.  Only those conv layers must receive gradients, and they must agree
+    with the stock HF feature extractor on the same weights."""
+    from transformers.models.wavlm.modeling_wavlm import WavLMFeatureEncoder
+    torch.manual_seed(3)
+    hf = WavLMFeatureEncoder(small_config("layer")).to(dev)
+    mine = B200FeatureEncoder(small_config("layer")).to(dev)
+    mine.load_state_dict(hf.state_dict())
+    for m in (hf, mine):
+        for name, p in m.named_parameters():
+            p.requires_grad = any(f"layers.{i}" in name for i in (5, 6))
+    x = torch.randn(2, 8000, device=dev)
+    gy = torch.randn(2, 512, 24, device=dev)
+    hf.train(); mine.train()
+    hf._requires_grad = False  # HF would otherwise demand a gradient for the raw waveform
+    hf(x).backward(gy)
+    mine(x).backward(gy)
+    for (name, a), (_, b) in zip(hf.named_parameters(), mine.named_parameters()):
+        if a.requires_grad:
+            assert b.grad is not None and rel_err(b.grad.cpu().numpy(), a.grad.cpu().numpy()) < 3e-2, name
+        else:
+            assert b.grad is None, name
