@@ -241,18 +241,37 @@ def main_gpu(args):
     host_batch = {"clean": clean_h, "noise": noise_h, "snr": snr_h}
     prefetch.put(host_batch)  # pipeline prologue: the first batch is in flight before step 0
 
+    graphs = {}  # one CUDA graph per prefetch slot: the whole step (15 kernels + pooling + D2H) is ONE launch
+
+    def step_body(b):
+        y_o, y_t, st = hot_path(b["clean"], b["noise"], b["snr"])
+        pooled_h[0].copy_(y_o.float().mean(dim=1), non_blocking=True)  # the [B,H]-pooled result the BYOL heads consume
+        pooled_h[1].copy_(y_t.float().mean(dim=1), non_blocking=True)
+        status_h.copy_(st, non_blocking=True)
+        return y_o, y_t, st
+
     def step_e2e():
         # every step enqueues ONE H2D copy (the next step's inputs, on the copy stream, overlapping this step's
         # kernels), runs the hot path on the batch copied one step earlier, and reads the result back to the host
         prefetch.put(host_batch)
+        slot = prefetch.current_slot
         b = prefetch.get()
-        y_o, y_t, st = hot_path(b["clean"], b["noise"], b["snr"])
+        if args.no_graph:
+            out = step_body(b)
+        elif slot not in graphs:
+            step_body(b)  # eager warm-up on this slot's buffers, then capture the same calls
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = step_body(b)
+            graphs[slot] = (g, out)
+            g.replay()
+        else:
+            g, out = graphs[slot]
+            g.replay()
         prefetch.release()
-        pooled_h[0].copy_(y_o.float().mean(dim=1), non_blocking=True)  # the [B,H]-pooled result the BYOL heads consume
-        pooled_h[1].copy_(y_t.float().mean(dim=1), non_blocking=True)
-        status_h.copy_(st, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the result every step
-        return y_o, y_t, st
+        return out
 
     for _ in range(3):
         step_e2e()
@@ -275,7 +294,8 @@ def main_gpu(args):
                 "ms_per_step": ms_e2e_total / args.steps,
                 "how": "pinned host batch -> DevicePrefetcher (copy stream, depth 2: H2D of step i+1 overlaps the kernels "
                        "of step i) -> ops.mix_normalize -> ops.conv_frontend x2 -> D2H of pooled features + status, "
-                       "host sync every step"},
+                       "host sync every step; the op calls of a step are captured once per prefetch slot in a CUDA graph"
+                       + (" (disabled: --no-graph)" if args.no_graph else "")},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
     }
@@ -439,6 +459,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="e2e arm: launch the ops eagerly instead of one CUDA graph per step")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)

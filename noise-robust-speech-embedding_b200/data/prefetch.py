@@ -42,6 +42,11 @@ class DevicePrefetcher:
         torch.cuda.current_stream(self.device).wait_event(self._ready[i])
         return self._slots[i]
 
+    @property
+    def current_slot(self) -> int:
+        """Index of the slot the next ``get()`` returns (slot tensors keep their addresses: CUDA-graph friendly)."""
+        return self._n_get % self.depth
+
     def release(self) -> None:
         i = self._n_get % self.depth
         self._free[i].record(torch.cuda.current_stream(self.device))
