@@ -315,6 +315,8 @@ struct EpiCtx {
   void* out_row;            // first element of this row's channels [n0, n0 + kNPC)
   __nv_bfloat16* xhat_row;  // nullable: normalised pre-affine values of this row (training forward)
   float* rstd_out;          // nullable: where to put this row's 1/std
+  bool pre_stats;           // LayerNorm statistics supplied by the caller (layer 0): skip pass 1 and the exchange
+  float pre_mean, pre_rstd;
 };
 
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction) --------------
@@ -383,7 +385,13 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
   float mean = 0.f, rstd = 1.f;
 
   ptx::tmem_ld32(taddr, ra);
-  if (e.has_norm) {
+  if (e.has_norm && e.pre_stats) {
+    mean = e.pre_mean;
+    rstd = e.pre_rstd;
+    if constexpr (kSave) {
+      if (e.rstd_out != nullptr && e.store) *e.rstd_out = rstd;
+    }
+  } else if (e.has_norm) {
     if constexpr (kClusterN == 2) {
       if (e.arm) ptx::mbar_arrive_expect_tx(e.bar_stats, kBlockM * 8);  // 128 peer rows x (mean, M2)
     }
@@ -710,6 +718,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                              : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(g.out) + m * kC + n0);
       ec.xhat_row = g.xhat ? reinterpret_cast<__nv_bfloat16*>(g.xhat) + m * kC + n0 : nullptr;
       ec.rstd_out = (g.rstd && n0 == 0) ? g.rstd + m : nullptr;
+      ec.pre_stats = false;
+      ec.pre_mean = 0.f;
+      ec.pre_rstd = 1.f;
       epilogue_row<kClusterN, kSave>(ec);
     }
   }
@@ -747,9 +758,10 @@ struct L0tcCfg {
   static constexpr int kWOff = kL0AStages * kABytes;
   static constexpr int kWBytes = kNPC * 128;
   static constexpr int kGbOff = kWOff + kWBytes;
-  static constexpr int kStatsOff = kGbOff + kNPC * 8;
-  static constexpr int kBarOff = kStatsOff + 4 * kBlockM * 8;
-  static constexpr int kNumBars = 2 * kL0AStages + 2 * kAccBufs + 2;
+  static constexpr int kStatsOff = kGbOff + kNPC * 8;           // 4 slots x 128 rows x (mean, rstd) from the builders
+  static constexpr int kGramOff = kStatsOff + 4 * kBlockM * 8;  // 10 channel-mean taps + 55 Gram entries (fp32)
+  static constexpr int kBarOff = kGramOff + 72 * 4;
+  static constexpr int kNumBars = 2 * kL0AStages + 2 * kAccBufs + 2 + 4;  // + 4 statistics-slot barriers
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kSmemBytes = kTmemPtrOff + 16 + 1024;
 };
@@ -788,7 +800,7 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
 
   auto bar = [&](int i) { return smem_base + Cfg::kBarOff + 8u * static_cast<uint32_t>(i); };
   const int kFull = 0, kEmpty = kL0AStages, kTmemFull = 2 * kL0AStages, kTmemEmpty = kTmemFull + Cfg::kAccBufs,
-            kStats = kTmemEmpty + Cfg::kAccBufs;
+            kStats = kTmemEmpty + Cfg::kAccBufs, kPre = kStats + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + Cfg::kTmemPtrOff);
   float2* s_gb = reinterpret_cast<float2*>(smem + Cfg::kGbOff);
   float2* s_stats = reinterpret_cast<float2*>(smem + Cfg::kStatsOff);
@@ -804,6 +816,7 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
     }
     ptx::mbar_init(bar(kStats + 0), 1);
     ptx::mbar_init(bar(kStats + 1), 1);
+    for (int q = 0; q < 4; ++q) ptx::mbar_init(bar(kPre + q), kBlockM);  // builders -> epilogue: (mean, rstd) slot ready
     ptx::fence_mbar_init();
   }
   if (warp == 4) {
@@ -828,6 +841,25 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
     reinterpret_cast<float*>(s_gb)[n] = a.gamma[n0 + n];
     reinterpret_cast<float*>(s_gb)[Cfg::kNPC + n] = a.beta[n0 + n];
   }
+  // LayerNorm statistics of a layer-0 frame follow from its 10 input samples alone:
+  //   mean_c Z = wbar . x,   mean_c Z^2 = x^T G x,   wbar = mean_c W[c,:],  G = W^T W / 512   (all 512 channels)
+  // so the builders hand (mean, rstd) to the epilogue and the TMEM statistics pass + DSMEM exchange disappear.
+  float* s_gram = reinterpret_cast<float*>(smem + Cfg::kGramOff);  // [0,10): wbar; [10,65): G upper triangle (x2 off-diag)
+  if (threadIdx.x < 65) {
+    const int e = threadIdx.x;
+    int k = 0, l = 0;
+    if (e >= 10) {
+      int r = e - 10;
+      for (k = 0; r >= 10 - k; ++k) r -= 10 - k;
+      l = k + r;
+    }
+    float acc = 0.f;
+    for (int c = 0; c < kC; ++c) {
+      const float* wc = a.w + c * 10;
+      acc += e < 10 ? __ldg(wc + e) : __ldg(wc + k) * __ldg(wc + l);
+    }
+    s_gram[e] = acc * (1.0f / kC) * ((e >= 10 && k != l) ? 2.0f : 1.0f);
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
   ptx::tc_fence_before();
   if constexpr (kClusterN == 2) ptx::cluster_sync_all();
@@ -845,7 +877,13 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
     const int row = threadIdx.x;
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+    float wbar[10], gram[55];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) wbar[k] = s_gram[k];
+#pragma unroll
+    for (int k = 0; k < 55; ++k) gram[k] = s_gram[10 + k];
+    int it = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const long long m = static_cast<long long>(tile) * kBlockM + row;
       const int b = static_cast<int>(m / a.P0), t = static_cast<int>(m % a.P0);
       float x[10];
@@ -866,6 +904,22 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
         words[10 + j] = hi[j];
       }
       words[15] = 0;
+      {
+        float mean = 0.f, q = 0.f;
+        int e = 0;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          mean = fmaf(wbar[k], x[k], mean);
+          float t = 0.f;
+#pragma unroll
+          for (int l = k; l < 10; ++l) t = fmaf(gram[e++], x[l], t);
+          q = fmaf(t, x[k], q);
+        }
+        const float var = fmaxf(q - mean * mean, 0.f);
+        // slot it % 4: the epilogue of tile it-4 is long done when this thread gets here (see conv_gemm_kernel notes)
+        s_stats[(it & 3) * kBlockM + row] = make_float2(mean, rsqrtf(var + kNormEps));
+        ptx::mbar_arrive(bar(kPre + (it & 3)));
+      }
       ptx::mbar_wait(bar(kEmpty + stage), phase ^ 1u);
       l0_store_row(smem_base + stage * Cfg::kABytes, row, words);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -915,8 +969,15 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
       const long long m = static_cast<long long>(tile) * kBlockM + row;
       ptx::mbar_wait(bar(kTmemFull + buf), acc_phase);
       ptx::tc_fence_after();
+      // the builders' (mean, rstd) for this tile (slot it % 4 is not rewritten before tile it + 4, whose builders
+      // cannot run until this epilogue has released the accumulator)
+      ptx::mbar_wait(bar(kPre + (it & 3)), static_cast<uint32_t>(it >> 2) & 1u);
+      const float2 pre = s_stats[(it & 3) * kBlockM + row];
       const int slot = team * 2 + static_cast<int>(acc_phase);
       EpiCtx ec;
+      ec.pre_stats = true;
+      ec.pre_mean = pre.x;
+      ec.pre_rstd = pre.y;
       ec.taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * Cfg::kNPC);
       ec.bar_tmem_empty = bar(kTmemEmpty + buf);
       ec.stats_slot = smem_base + Cfg::kStatsOff + static_cast<uint32_t>((slot * kBlockM + row) * 8);
