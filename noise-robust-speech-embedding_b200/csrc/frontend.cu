@@ -1,4 +1,4 @@
-// WavLM convolutional feature encoder, forward (hf:models/wavlm/modeling_wavlm.py:682-789, reached from
+// WavLM convolutional feature encoder, forward and backward (hf:models/wavlm/modeling_wavlm.py:682-789, reached from
 // ref:src/models/encoder.py:25):  7 x { Conv1d(bias=False) ; LayerNorm over C | GroupNorm | none ; exact GELU }.
 //
 // Data layout.  Activations are channels-last bf16 [B * P_i, 512] with a per-utterance frame pitch P_i chosen
@@ -8,18 +8,24 @@
 // with no im2col buffer: A is addressed by a 3-D TMA tensor map (channel, frame parity, frame pair) of the
 // previous activation, weights are pre-packed [512, tap*512 + c_in] bf16.
 //
-// Kernels.
-//   layer 0   (C_in = 1, k = 10, stride 5): SIMT, a warp per output frame, 16 channels per lane with the
-//             10-tap filters held in registers; LayerNorm statistics by warp shuffles.  ALU/HBM-write bound.
-//   layers 1-6: warp-specialised tcgen05 kernel.  warp 0 = TMA producer (128B-swizzled A/W tiles into a
-//             multi-stage mbarrier ring), warp 1 = single-thread tcgen05.mma issuer (128 x 256 x 16 bf16 UMMA,
-//             fp32 accumulators in TMEM), warps 2-5 = epilogue (tcgen05.ld -> LayerNorm over the 512 channels
-//             -> exact-erf GELU -> bf16 -> global).  Two variants:
-//               kClusterN = 1: one CTA owns all 512 channels of a 128-frame tile (accumulator = all of TMEM).
-//               kClusterN = 2: a 2-CTA cluster splits the channels 256/256; each CTA double-buffers its
-//                              accumulator in TMEM so the epilogue of tile j overlaps the MMAs of tile j+1;
-//                              the per-frame LayerNorm partials (mean, M2) are exchanged through distributed
-//                              shared memory with a remote mbarrier arrive.
+// Kernels (forward).
+//   layer 0   (C_in = 1, k = 10, stride 5), LayerNorm mode: layer0_tc_kernel -- the 10-tap convolution as a K = 32
+//             UMMA on bf16 hi/lo splits (fp32-class accuracy), A rows built in shared memory by four builder warps,
+//             LayerNorm statistics computed analytically from the 10 input samples (mean = wbar.x, E[Z^2] = x^T G x),
+//             then the shared TMEM epilogue.  GroupNorm mode (wavlm-base): layer0_kernel (SIMT, warp per frame)
+//             with a two-kernel per-(utterance, channel) statistics pass.
+//   layers 1-6: conv_gemm_kernel, warp-specialised tcgen05.  warp 0 = TMA producer (128B-swizzled A/W tiles into a
+//             4-stage mbarrier ring), warp 1 = single-thread tcgen05.mma issuer (128 x 256 x 16 bf16 UMMA, fp32
+//             accumulators in TMEM), then one epilogue TEAM of 4 warps per TMEM accumulator buffer (tcgen05.ld,
+//             double-buffered -> LayerNorm over the 512 channels -> exact GELU with one MUFU, packed f32x2 math ->
+//             bf16 -> 256-bit global stores).  Two variants:
+//               kClusterN = 1: one CTA owns all 512 channels of a 128-frame tile (accumulator = all of TMEM, one team).
+//               kClusterN = 2 (default): a 2-CTA cluster splits the channels 256/256; each CTA double-buffers its
+//                              accumulator (two teams), so the epilogue of tile j overlaps the MMAs of tile j+1; the
+//                              per-frame LayerNorm partials (mean, M2) cross to the peer CTA as one 8-byte st.async
+//                              that completes bytes on the peer's mbarrier (no fence on either side).
+//   Mode 1 of the same kernel (plain bf16 epilogue, 2-D A map with per-block row offsets, output row 2m + parity) is
+//   the data-gradient GEMM of the backward; see the "Backward" block further down for the other backward kernels.
 #include <cuda.h>
 
 #include <cstdlib>
