@@ -103,7 +103,7 @@ def test_frontend_golden(dev, golden, variant, mode):
 
 
 @pytest.mark.parametrize("mode,B,L", [("layer", 3, 16000), ("group", 2, 16000), ("layer", 1, 400), ("layer", 2, 12345),
-                                      ("layer", 2, 32000), ("layer", 1, 192000), ("group", 1, 96000)])
+                                      ("layer", 2, 32000), ("layer", 1, 192000), ("group", 1, 96000), ("layer", 5, 80000)])
 def test_frontend_vs_oracle(dev, mode, B, L):
     layers = synthetic.frontend_weights(mode, seed=4)
     x = synthetic.waveforms(B, L, seed=21)[0]
