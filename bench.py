@@ -305,9 +305,9 @@ def main_gpu(args):
         line.update(kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w, gammas, betas, packed,
                                      T, P, max(3, min(args.steps, 10))))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cv, cdt, cores, threads = run_cpu(4, 3, 1)
+        cv, cdt, cores, threads = run_cpu(16, 4, 1)
         line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"4 of {BATCH} utterances x 4 s per step, 3 steps after 1 warm-up: oracle "
+                                "sample": f"16 of {BATCH} utterances x 4 s per step, 4 steps after 1 warm-up: oracle "
                                           f"(CPU port of the reference path: per-utterance mix+normalise, fp32 conv "
                                           f"frontend on both views), torch {threads} threads on {cores} host cores"}
     elif rank == 0:
@@ -455,7 +455,7 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
