@@ -38,21 +38,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// acquire at cluster scope: the data guarded by the barrier was written by the peer CTA
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-
 // ---- cluster / distributed shared memory ------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -63,12 +48,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t cta_
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
   return r;
-}
-__device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
 // 8-byte store into a peer CTA's shared memory that also performs complete_tx(8) on a peer mbarrier: the
 // receiver arms the barrier with expect_tx and simply waits on it -- no fence / L1 invalidate on either side.

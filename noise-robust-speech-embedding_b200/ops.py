@@ -319,12 +319,20 @@ def _conv_frontend_fwd(x: Tensor, w0: Tensor, w_packed: Sequence[Tensor], gammas
     return y
 
 
-@_conv_frontend_fwd.register_fake
-def _(x, w0, w_packed, gammas, betas, norm_mode, out_bf16):
-    t = x.shape[1]
+def _geometry_py(n_samples: int) -> Tuple[List[int], List[int]]:
+    """Pure-Python twin of nrse_conv_frontend_geometry (used for shape inference without touching the library)."""
+    T, t = [], int(n_samples)
     for k, s in zip(CONV_KERNEL, CONV_STRIDE):
         t = (t - k) // s + 1
-    return x.new_empty(x.shape[0], t + 1, 512, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        T.append(t)
+    p6 = max(-(-T[i] // (1 << (6 - i))) for i in range(7))
+    return T, [p6 << (6 - i) for i in range(7)]
+
+
+@_conv_frontend_fwd.register_fake
+def _(x, w0, w_packed, gammas, betas, norm_mode, out_bf16):
+    _, P = _geometry_py(x.shape[1])
+    return x.new_empty(x.shape[0], P[6], 512, dtype=torch.bfloat16 if out_bf16 else torch.float32)
 
 
 def conv_frontend(x: Tensor, conv_weights: Sequence[Tensor], gammas: Sequence[Optional[Tensor]],

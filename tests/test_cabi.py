@@ -57,6 +57,9 @@ def test_frontend_geometry_matches_hf_formula(lib):
             if i:
                 assert P[i - 1] == 2 * P[i]
         assert P[6] - T[6] <= 1 + T[0] // 64 - T[6] + 1
+    from nrse_b200 import ops
+    for L in (400, 4000, 64000, 12345, 192000):
+        assert ops._geometry_py(L) == ops.frontend_geometry(L)
     T = (C.c_int32 * 7)()
     P = (C.c_int32 * 7)()
     assert lib.nrse_conv_frontend_geometry(399, T, P) == -1  # empty output
