@@ -135,3 +135,20 @@ def test_frontend_full_size_batch_independence(dev):
     for b in (5, 63):
         ref = oracle.conv_frontend(torch.from_numpy(x[b:b + 1]), layers, "layer")
         assert rel_err(y[b].t().cpu().numpy(), ref[0].numpy()) < 1e-2
+
+
+def test_forward_paths_are_deterministic(dev):
+    """No atomics and fixed reduction orders in mix, conv frontend forward and loss: two runs are bit-identical."""
+    clean, noise, snr_idx, table = synthetic.waveforms(6, 16000, seed=77)
+    args = (torch.from_numpy(clean).to(dev), torch.from_numpy(noise).to(dev), torch.from_numpy(snr_idx).to(dev),
+            [float(v) for v in table])
+    c1, n1, _ = ops.mix_normalize(*args)
+    c2, n2, _ = ops.mix_normalize(*args)
+    assert torch.equal(c1, c2) and torch.equal(n1, n2)
+    layers = synthetic.frontend_weights("layer", seed=1)
+    w, g, b = _layer_params(layers, dev)
+    y1 = ops.conv_frontend(n1, w, g, b, "layer").clone()
+    y2 = ops.conv_frontend(n1, w, g, b, "layer")
+    assert torch.equal(y1, y2)
+    p, z = y1.mean(1), ops.conv_frontend(c1, w, g, b, "layer").mean(1)
+    assert torch.equal(ops.byol_loss(p, z), ops.byol_loss(p, z))
