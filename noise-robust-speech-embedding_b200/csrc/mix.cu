@@ -964,6 +964,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) mix_normalize_stream_kernel
   }
 }
 
+int g_mix_stream_cluster = 0;  // 0: automatic; 1/2/4/8 force the CTAs-per-row of the streaming variant (tuning)
 int g_mix_variant = 3;  // 3: streaming, one large CTA (or small cluster) per row, passes 2-3 from L2 (default);
                         // 2: persistent double-buffered shared-memory pipeline; 1: shared memory, one row per
                         // cluster; 0: generic re-read-from-L2 kernel (also the fallback for unaligned rows)
@@ -977,6 +978,11 @@ const char* const kMixStatusNames[] = {
 }  // namespace nrse
 
 extern "C" {
+
+int nrse_debug_mix_stream_cluster(int cs) {
+  nrse::g_mix_stream_cluster = cs;
+  return NRSE_OK;
+}
 
 int nrse_mix_set_variant(int variant) {
   if (variant < 0 || variant > 3) return NRSE_ERR_INVALID_ARG;
@@ -1023,8 +1029,18 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
   if (vec && g_mix_variant == 3) {
     // one CTA of 1024 threads per row when the batch fills the machine, else the largest cluster (<= 8) that keeps
     // B * cs within the SM count
+    // 1 CTA per SM (1024 threads x 64 registers): pick the cluster size (CTAs per row) that wastes the fewest SM-slots
+    // in the last wave, preferring fewer CTAs per row on ties (each extra CTA costs two cluster barriers per row)
     int cs = 1;
-    while (cs < kSmemMaxCluster && B * cs * 2 <= kNumSMs) cs *= 2;
+    double best = 1e30;
+    for (int c = 1; c <= kSmemMaxCluster; c *= 2) {
+      if ((L / 4) < c * 256) break;  // keep at least a quarter of the threads busy
+      const long long ctas = static_cast<long long>(B) * c;
+      const long long waves = (ctas + kNumSMs - 1) / kNumSMs;
+      const double cost = static_cast<double>(waves * kNumSMs) / static_cast<double>(ctas) * (1.0 + 0.03 * (c > 1 ? 1 : 0));
+      if (cost < best - 1e-9) { best = cost; cs = c; }
+    }
+    if (g_mix_stream_cluster > 0) cs = g_mix_stream_cluster;
     cfg.gridDim = dim3(static_cast<unsigned>(B) * cs);
     cfg.blockDim = dim3(kStreamThreads);
     cfg.dynamicSmemBytes = 0;
