@@ -341,6 +341,15 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n  # ms per call
 
+    def plain_time(fn, n=5):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
     B, L = clean_d.shape
     # the conv GEMM layers: run layer by layer on real activations so every launch can be bracketed by events
     c, n, _ = ops.mix_normalize(clean_d, noise_d, snr_d, snr_list, True)
@@ -404,6 +413,34 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
     for kk in kernels:
         kk["frac"] = kk["achieved"] / kk["peak"]
 
+    # the same three operations written with stock torch ops on THIS GPU (what the reference's arithmetic costs when it
+    # is simply moved to the device): batched mix + peak-norm + z-norm, the per-tensor EMA loop, the ~15-op loss
+    def stock_mix(cw, nw, snr_lin):
+        ps, pn = (cw ** 2).mean(1, keepdim=True), (nw ** 2).mean(1, keepdim=True)
+        y = cw + nw * torch.sqrt(ps / (pn * snr_lin))
+        outs = []
+        for v in (cw, y):
+            v = v / (v.abs().amax(1, keepdim=True) + 1e-8)
+            outs.append((v - v.mean(1, keepdim=True)) / torch.sqrt(v.var(1, unbiased=False, keepdim=True) + 1e-7))
+        return outs
+
+    snr_lin = torch.tensor([10 ** (snr_list[i] / 10) for i in snr_d.tolist()], device=dev)[:, None]
+    stock_ms = {"mix_ms": plain_time(lambda: stock_mix(clean_d, noise_d, snr_lin))}
+    on = [torch.randn(s, device=dev) for s in sizes]
+    tg = [torch.randn(s, device=dev) for s in sizes]
+
+    def stock_ema():
+        for i in range(len(on)):  # ref:src/models/byol.py:64-73, one tensor at a time
+            tg[i] = 0.996 * tg[i] + (1 - 0.996) * on[i]
+    stock_ms["ema_ms"] = plain_time(stock_ema)
+    del on, tg
+
+    def stock_loss():
+        a = torch.nn.functional.normalize(p.detach() + 1e-10, dim=1, eps=1e-10)
+        b_ = torch.nn.functional.normalize(z + 1e-10, dim=1, eps=1e-10)
+        return 2 - 2 * torch.clamp((a * b_).sum(1), -1.0, 1.0).mean()
+    stock_ms["loss_fwd_ms"] = plain_time(stock_loss)
+
     # training forward (tape-writing) + native backward of the frontend, and the same stack in stock torch on THIS GPU
     # (cuDNN conv1d + ATen layer_norm / gelu): the "kernel to beat" of BASELINE.md section 4 (G0)
     import torch.nn.functional as F
@@ -449,7 +486,8 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
     frontend_train = {"shape": [B, L], "fwd_ms": t_inf, "train_fwd_ms": t_train, "bwd_ms": t_bwd,
                       "fwd_bwd_ms": t_train + t_bwd, "stock_torch_same_gpu": stock_res,
                       "note": "host-launched (not graph-timed): includes Python/launch overhead of the op wrappers"}
-    return {"roofline": roofline, "kernels": kernels, "frontend_train": frontend_train}
+    return {"roofline": roofline, "kernels": kernels, "frontend_train": frontend_train,
+            "stock_torch_same_gpu_ms": stock_ms}
 
 
 def main():

@@ -76,12 +76,19 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
                            float* clean_out, float* noisy_out, int32_t* status,
                            int B, int L, int L_noise, int peak_norm, nrse_stream_t stream);
 const char* nrse_mix_status_name(int status_code);
-/* 3 (default): streaming -- one 1024-thread CTA (or a small cluster for small batches) per row, pass 1 from HBM, passes
- * 2-3 from L2, streaming stores; 2: persistent clusters, rows double-buffered in shared memory by bulk async copies (the next row streams in
- * while the current one is processed); 1: one row per cluster, single stage; 0: always the re-read-from-L2 kernel.
- * 1, 2 and 3 need 16-byte aligned rows, L % 4 == 0, L_noise >= L and a row that fits the cluster's shared memory;
+/* 4 (default): on-chip resident -- one 1024-thread CTA per SM keeps its segment of the row in registers (128 KB) and
+ * shared memory (<= 192 KB) between the three passes; a cluster of 1/2/4/8 CTAs per row, exchanges by st.async + mbarrier;
+ * rows up to 8 x 40960 samples (20 s), longer rows use variant 3.
+ * 3: streaming -- one 1024-thread CTA (or a small cluster for small batches) per row, pass 1 from HBM, passes
+ * 2-3 from L2, streaming stores; 2: persistent clusters, rows double-buffered in shared memory by bulk async copies (the
+ * next row streams in while the current one is processed); 1: one row per cluster, single stage; 0: always the
+ * re-read-from-L2 kernel.  1..4 need 16-byte aligned rows, L % 4 == 0, L_noise >= L and a row that fits the cluster;
  * otherwise the library falls back to the next lower variant by itself. */
 int nrse_mix_set_variant(int variant);
+/* tuning: CTAs per row for variants 3 and 4 (1..8); 0 = automatic (default) */
+int nrse_mix_set_cluster(int ctas_per_row);
+/* tuning: shared-memory carveout (percent of 228 KB) of the resident kernels; -1 = just what the CTAs need (default) */
+int nrse_mix_set_carveout(int percent);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-tensor EMA:  target = decay*target + one_minus_decay*online   (fp32, in place,
@@ -101,6 +108,44 @@ int64_t nrse_ema_plan_chunks_host(const uint64_t* target_ptrs_host, const uint64
 int nrse_ema_chunks_f32(const uint64_t* chunk_target, const uint64_t* chunk_online,
                         const int32_t* chunk_numel, int64_t n_chunks,
                         float decay, float one_minus_decay, nrse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused optimizer tail of the BYOL step: gradient-norm clip + AdamW + EMA of the target network, fp32,
+ * two launches (one read of every gradient for the norm, then ONE pass that reads p, g, m, v, t and
+ * writes p, m, v, t).  Replaces, in this order (ref:train_byol.py:67-71):
+ *   torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)       ref:train_byol.py:67
+ *   optimizer.step()   (torch.optim.AdamW, torch/optim/adam.py::_single_tensor_adam arithmetic)   :70
+ *   model._update_target_network()                                         ref:src/models/byol.py:62-73
+ *
+ * nrse_optim_plan_chunks_host splits n_tensors parameter tensors into chunks of <= chunk_elems elements.
+ *   Per tensor (HOST arrays of DEVICE addresses): p = parameter, g = gradient (0: no gradient this step,
+ *   AdamW skips the tensor as torch does), m / v = exp_avg / exp_avg_sq (required when g != 0), t = EMA
+ *   target twin (0: none).  Tensors with neither g nor t produce no chunk.  Returns the number of chunks;
+ *   when chunk_ptrs_host / chunk_numel_host are non-NULL it fills them: chunk_ptrs_host is FIVE
+ *   consecutive arrays of max_chunks entries (p | g | m | v | t), i.e. the pitch is max_chunks.
+ * nrse_grad_sqnorm_chunks_f32 reads every gradient of a table once and writes nrse_optim_partials_count()
+ *   fp64 partial sums of squares (one per CTA of a fixed grid; deterministic) to `partials`.
+ * nrse_clip_adamw_ema_chunks_f32 runs one optimizer step over a DEVICE copy of the table.
+ *   step >= 1 is the value of torch's state['step'] AFTER its increment (one value per call: parameters
+ *   whose step counts differ go into separate tables / calls, their norm partials side by side);
+ *   max_grad_norm <= 0 disables clipping, else every CTA sums partials[0..n_partials) in a fixed order and
+ *   scales the gradients by min(1, max_grad_norm / (norm + 1e-6)) on the fly;
+ *   grad_norm_out (nullable, device [1]) receives the total gradient norm clip_grad_norm_ returns.
+ *   The gradients themselves are not modified (the reference scales them in place; nothing reads them
+ *   afterwards: the next step starts with zero_grad).
+ * ------------------------------------------------------------------------------------------- */
+int64_t nrse_optim_plan_chunks_host(const uint64_t* p_host, const uint64_t* g_host, const uint64_t* m_host,
+                                    const uint64_t* v_host, const uint64_t* t_host, const int64_t* numel_host,
+                                    int n_tensors, int64_t chunk_elems, uint64_t* chunk_ptrs_host,
+                                    int32_t* chunk_numel_host, int64_t max_chunks);
+int nrse_optim_partials_count(void);
+int nrse_grad_sqnorm_chunks_f32(const uint64_t* chunk_g, const int32_t* chunk_numel, int64_t n_chunks,
+                                double* partials, nrse_stream_t stream);
+int nrse_clip_adamw_ema_chunks_f32(const uint64_t* chunk_ptrs, int64_t chunk_pitch, const int32_t* chunk_numel,
+                                   int64_t n_chunks, double lr, double beta1, double beta2, double eps,
+                                   double weight_decay, int64_t step, double max_grad_norm, double ema_decay,
+                                   const double* partials, int n_partials, float* grad_norm_out,
+                                   nrse_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BYOL loss with fused +1e-10, L2 normalisation (eps 1e-10), row dot product, clamp and mean.

@@ -16,6 +16,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -964,8 +965,357 @@ __global__ void __launch_bounds__(kStreamThreads, 1) mix_normalize_stream_kernel
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// On-chip-resident variant (default when the row fits): the whole row lives ON CHIP between the passes -- the first
+// 4096 float4 of each CTA's segment in REGISTERS (4 + 4 float4 per thread, 128 KB per SM: the register file is the
+// largest memory of the SM), the rest in shared memory (bulk async copies, <= 96 KB per array).  One 1024-thread CTA
+// per SM holds up to 320 KB of input, so a 4 s row needs a cluster of only two CTAs (74 rows in flight instead of the
+// 37 of the shared-memory-only design), every byte of the row is in flight the moment the CTA starts, and passes 2
+// and 3 touch neither L2 nor HBM for reads: the memory system sees exactly the algorithmic 16 B per sample.  (The
+// streaming variant pushes 4x that through the L2 slices, whose ~6300 B/clk cap is then as tight as HBM itself.)
+// ---------------------------------------------------------------------------------------------------------
+// Two shapes of the same kernel: 512 threads x 2 CTAs per SM (the default: the two co-resident CTAs belong to different
+// rows, so one CTA's reduction / exchange / scalar bubbles -- about 5 us per row, measured -- are covered by the other's
+// HBM phases) and 1024 threads x 1 CTA per SM (twice the capacity per CTA, for rows too long for eight small CTAs).
+constexpr int kResRegVec = 4;  // float4 per thread per array held in registers
+constexpr int kResChunks = 4;
+template <int kThreads>
+struct ResCfg {
+  static constexpr int kWarps = kThreads / 32;
+  static constexpr int kCtasPerSm = 1024 / kThreads;        // 1024 threads x 64 registers fill the register file
+  static constexpr int kRegCap = kResRegVec * kThreads;     // float4 per array in registers (64 B per thread)
+  static constexpr int kSmemCap = kThreads == 1024 ? 6144 : 3456;  // float4 per array in shared memory
+  static constexpr int kCap = kRegCap + kSmemCap;
+};
+
+template <int kResThreads>
+__global__ void __launch_bounds__(kResThreads, 1024 / kResThreads)
+mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
+  constexpr int kResWarps = ResCfg<kResThreads>::kWarps;
+  constexpr int kResRegCap = ResCfg<kResThreads>::kRegCap;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int cs = static_cast<int>(cluster.num_blocks());
+  const int row = blockIdx.x / cs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  extern __shared__ __align__(128) unsigned char mix_smem[];
+  __shared__ __align__(8) unsigned long long bars[kResChunks];
+  __shared__ __align__(8) unsigned long long xbar[2];  // cluster exchange 1 (sums, input peaks) and 2 (mixed peak)
+  __shared__ double red_d[kResWarps][5];
+  __shared__ float red_f[kResWarps][2];
+  __shared__ __align__(16) double xch1_d[kSmemMaxCluster][6];  // 5 sums, then {max|c|, max|n|} as two floats
+  __shared__ float xch2_f[kSmemMaxCluster];
+  __shared__ MixScalars sc;
+
+  const int L = p.L;
+  const int nvec = L >> 2;  // L % 4 == 0 on this path
+  const int v_begin = min(nvec, rank * seg_vec);
+  const int v_end = min(nvec, v_begin + seg_vec);
+  const int n_my = v_end - v_begin;
+  const int n_reg = min(n_my, kResRegCap);
+  const int n_sm = n_my - n_reg;  // local vectors [n_reg, n_my) live in shared memory
+  const int chunk_vec = (n_sm + kResChunks - 1) / kResChunks;
+  float4* s_c = reinterpret_cast<float4*>(mix_smem);
+  float4* s_n = s_c + smem_pitch;
+  const float4* g_c = reinterpret_cast<const float4*>(p.clean + static_cast<size_t>(row) * L) + v_begin;
+  const float4* g_n = reinterpret_cast<const float4*>(p.noise + static_cast<size_t>(row) * p.Ln) + v_begin;
+
+  // The cluster exchanges are st.async messages that complete_tx on the RECEIVER's mbarrier: no cluster barrier and no
+  // gpu-scope fence on the critical path (cg::cluster.sync() costs MEMBAR.GPU + ERRBAR twice per row).  Each CTA
+  // sends its partials to every CTA of the cluster (itself included), in both exchanges, before it waits for the
+  // second one -- so once a CTA has received everything nothing can still be addressed to it and it may exit.
+  const unsigned xbar1 = ptx::smem_u32(&xbar[0]), xbar2 = ptx::smem_u32(&xbar[1]);
+  if (tid == 0) {
+    for (int c = 0; c < kResChunks; ++c) ptx::mbar_init(ptx::smem_u32(&bars[c]), 1);
+    ptx::mbar_init(xbar1, 1);
+    ptx::mbar_init(xbar2, 1);
+    ptx::fence_mbar_init();
+    ptx::mbar_arrive_expect_tx(xbar1, static_cast<unsigned>(cs) * 48u);
+    ptx::mbar_arrive_expect_tx(xbar2, static_cast<unsigned>(cs) * 4u);
+    for (int c = 0; c < kResChunks; ++c) {
+      const int c0 = c * chunk_vec;
+      const int len = min(chunk_vec, n_sm - c0);
+      if (len <= 0) break;
+      const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[c]));
+      const unsigned bytes = static_cast<unsigned>(len) * 16u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       static_cast<unsigned>(__cvta_generic_to_shared(s_c + c0))),
+                   "l"(g_c + n_reg + c0), "r"(bytes), "r"(bar)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       static_cast<unsigned>(__cvta_generic_to_shared(s_n + c0))),
+                   "l"(g_n + n_reg + c0), "r"(bytes), "r"(bar)
+                   : "memory");
+    }
+  }
+
+  // ---- register part: 8 x 128-bit loads per thread, all in flight at once ---------------------------------------
+  float4 rc[kResRegVec], rn[kResRegVec];
+#pragma unroll
+  for (int u = 0; u < kResRegVec; ++u) {
+    const int v = u * kResThreads + tid;
+    if (v < n_reg) {
+      rc[u] = ld_stream_f4(g_c + v);
+      rn[u] = ld_stream_f4(g_n + v);
+    } else {
+      rc[u] = rn[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __syncthreads();  // mbarrier init visible to the waiting threads
+  if (cs > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");  // peers: my barriers exist
+
+  // ---- pass 1: packed fp32 partial sums per thread (<= 40 samples per lane-half), fp64 across ---------------------
+  const f2 zero2 = f2_make(0.f, 0.f);
+  f2 a_cc = zero2, a_nn = zero2, a_c1 = zero2, a_n1 = zero2, a_cn = zero2;
+  float cmax = 0.f, nmax_in = 0.f;
+  auto accum = [&](const float4& cv, const float4& nv) {
+    const f2 c01 = f2_make(cv.x, cv.y), c23 = f2_make(cv.z, cv.w);
+    const f2 n01 = f2_make(nv.x, nv.y), n23 = f2_make(nv.z, nv.w);
+    a_cc = f2_fma(c01, c01, a_cc); a_cc = f2_fma(c23, c23, a_cc);
+    a_nn = f2_fma(n01, n01, a_nn); a_nn = f2_fma(n23, n23, a_nn);
+    a_cn = f2_fma(c01, n01, a_cn); a_cn = f2_fma(c23, n23, a_cn);
+    a_c1 = f2_add(a_c1, c01); a_c1 = f2_add(a_c1, c23);
+    a_n1 = f2_add(a_n1, n01); a_n1 = f2_add(a_n1, n23);
+    cmax = fmaxf(fmaxf(cmax, fmaxf(fabsf(cv.x), fabsf(cv.y))), fmaxf(fabsf(cv.z), fabsf(cv.w)));
+    nmax_in = fmaxf(fmaxf(nmax_in, fmaxf(fabsf(nv.x), fabsf(nv.y))), fmaxf(fabsf(nv.z), fabsf(nv.w)));
+  };
+#pragma unroll
+  for (int u = 0; u < kResRegVec; ++u) accum(rc[u], rn[u]);
+  if (n_sm > 0) {
+    for (int c = 0; c < kResChunks; ++c) {
+      const int c0 = c * chunk_vec;
+      const int c_end = min(n_sm, c0 + chunk_vec);
+      if (c0 >= c_end) break;
+      const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[c]));
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tRES_WAIT_LOOP:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+          "@p bra RES_WAIT_DONE;\n\tbra RES_WAIT_LOOP;\n\tRES_WAIT_DONE:\n\t}\n" ::"r"(bar)
+          : "memory");
+      for (int v = c0 + tid; v < c_end; v += kResThreads) accum(s_c[v], s_n[v]);
+    }
+  }
+
+  // CTA-wide then cluster-wide combine.  Warp shuffles (xor butterfly: every lane ends with the same bits), one warp
+  // over the 32 warp partials, then every CTA receives every CTA's partial in rank order: deterministic, and all
+  // CTAs of the row derive bit-identical scalars.
+  {
+    double acc[5] = {static_cast<double>(f2_hsum(a_cc)), static_cast<double>(f2_hsum(a_nn)),
+                     static_cast<double>(f2_hsum(a_c1)), static_cast<double>(f2_hsum(a_n1)),
+                     static_cast<double>(f2_hsum(a_cn))};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[k] = warp_sum(acc[k]);
+    cmax = warp_max(cmax);
+    nmax_in = warp_max(nmax_in);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) red_d[warp][k] = acc[k];
+      red_f[warp][0] = cmax;
+      red_f[warp][1] = nmax_in;
+    }
+    __syncthreads();
+    if (cs > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc[k] = warp_sum(lane < kResWarps ? red_d[lane][k] : 0.0);
+      const float m0 = warp_max(lane < kResWarps ? red_f[lane][0] : 0.f);
+      const float m1 = warp_max(lane < kResWarps ? red_f[lane][1] : 0.f);
+      if (lane < cs) {
+        const unsigned dst = ptx::mapa(ptx::smem_u32(&xch1_d[rank][0]), lane);
+        const unsigned dbar = ptx::mapa(xbar1, lane);
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(
+                           dst + 8u * k),
+                       "l"(__double_as_longlong(acc[k])), "r"(dbar)
+                       : "memory");
+        ptx::st_async_f2(dst + 40u, m0, m1, dbar);
+      }
+    }
+  }
+  if (tid == 0) ptx::mbar_wait(xbar1, 0);
+
+  double s_cc = 0.0, s_nn = 0.0, s_c1 = 0.0, s_n1 = 0.0, s_cn = 0.0;
+  const double inv_L = 1.0 / static_cast<double>(L);
+  if (tid == 0) {
+    cmax = 0.f;
+    nmax_in = 0.f;
+    for (int r = 0; r < cs; ++r) {
+      s_cc += xch1_d[r][0];
+      s_nn += xch1_d[r][1];
+      s_c1 += xch1_d[r][2];
+      s_n1 += xch1_d[r][3];
+      s_cn += xch1_d[r][4];
+      const float2 pk = *reinterpret_cast<const float2*>(&xch1_d[r][5]);
+      cmax = fmaxf(cmax, pk.x);
+      nmax_in = fmaxf(nmax_in, pk.y);
+    }
+    const float Ps = static_cast<float>(s_cc * inv_L);
+    const float Pn = static_cast<float>(s_nn * inv_L);
+    int idx = p.snr_idx[row];
+    idx = idx < 0 ? 0 : (idx >= p.n_snr ? p.n_snr - 1 : idx);
+    const float scale = __fsqrt_rn(__fdiv_rn(Ps, __fmul_rn(Pn, p.snr_lin[idx])));
+    int st = 0;
+    if (isnan(Ps)) st = 1;
+    else if (isnan(Pn)) st = 2;
+    else if (Ps < 1e-10f) st = 3;
+    else if (Pn < 1e-10f) st = 4;
+    else if (isinf(scale) || isnan(scale)) st = 5;
+    else if (scale > 1e6f) st = 6;
+    else if (isinf(nmax_in)) st = 7;
+    sc.scale = scale;
+    sc.st1 = st;
+  }
+  __syncthreads();
+  const float scale = sc.scale;
+  const int st1 = sc.st1;
+  const bool mixed = st1 == 0;
+  const f2 s2 = f2_make(scale, scale);
+
+  // ---- pass 2 (on chip): y = c + s*n replaces n; peak of the mixed signal (BYOL mode) ----------------------------
+  float nmax = 0.f;
+  if (p.peak_norm && mixed) {
+    auto mix_in_place = [&](const float4& cv, float4& nv) {
+      f2_split(f2_add(f2_make(cv.x, cv.y), f2_mul(f2_make(nv.x, nv.y), s2)), nv.x, nv.y);  // augment.py:54,60
+      f2_split(f2_add(f2_make(cv.z, cv.w), f2_mul(f2_make(nv.z, nv.w), s2)), nv.z, nv.w);
+      nmax = absmax_nan(absmax_nan(absmax_nan(absmax_nan(nmax, nv.x), nv.y), nv.z), nv.w);
+    };
+#pragma unroll
+    for (int u = 0; u < kResRegVec; ++u) mix_in_place(rc[u], rn[u]);
+    for (int v = tid; v < n_sm; v += kResThreads) {
+      const float4 cv = s_c[v];
+      float4 nv = s_n[v];
+      mix_in_place(cv, nv);
+      s_n[v] = nv;  // re-read in pass 3 by the same thread
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float other = __shfl_xor_sync(0xffffffffu, nmax, o);
+      asm("max.NaN.f32 %0, %0, %1;" : "+f"(nmax) : "f"(other));
+    }
+    if (lane == 0) red_f[warp][0] = nmax;
+    __syncthreads();
+    if (warp == 0) {
+      float m = lane < kResWarps ? red_f[lane][0] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float other = __shfl_xor_sync(0xffffffffu, m, o);
+        asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(other));
+      }
+      if (lane < cs)
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(
+                         ptx::mapa(ptx::smem_u32(&xch2_f[rank]), lane)),
+                     "r"(__float_as_uint(m)), "r"(ptx::mapa(xbar2, lane))
+                     : "memory");
+    }
+    if (tid == 0) ptx::mbar_wait(xbar2, 0);
+  }
+
+  if (tid == 0) {
+    int st = st1;
+    const double s = static_cast<double>(scale);
+    float a_c = 0.f, b_c = 0.f, a_n = 0.f, b_n = 0.f, inv_dc = 1.f, inv_dn = 1.f;
+    if (p.peak_norm) {
+      if (st == 0) {
+        nmax = xch2_f[0];
+        for (int r = 1; r < cs; ++r) asm("max.NaN.f32 %0, %0, %1;" : "+f"(nmax) : "f"(xch2_f[r]));
+        if (isnan(nmax)) st = 8;
+        else if (cmax < 1e-8f) st = 9;
+        else if (nmax < 1e-8f) st = 10;
+        else if (isinf(cmax)) st = 11;
+        else if (isinf(nmax)) st = 12;
+      }
+      if (st == 0) {
+        const double rdc = 1.0 / static_cast<double>(__fadd_rn(cmax, 1e-8f));
+        const double rdn = 1.0 / static_cast<double>(__fadd_rn(nmax, 1e-8f));
+        const double mc = s_c1 * inv_L * rdc;
+        const double vc = s_cc * inv_L * rdc * rdc - mc * mc;
+        const double mn = (s_c1 + s * s_n1) * inv_L * rdn;
+        const double vn = (s_cc + 2.0 * s * s_cn + s * s * s_nn) * inv_L * rdn * rdn - mn * mn;
+        const float vcf = static_cast<float>(vc), vnf = static_cast<float>(vn);
+        const float mcf = static_cast<float>(mc), mnf = static_cast<float>(mn);
+        if (!isfinite(mcf) || !isfinite(vcf)) st = 13;
+        else if (!isfinite(mnf) || !isfinite(vnf)) st = 14;
+        inv_dc = static_cast<float>(rdc);
+        inv_dn = static_cast<float>(rdn);
+        a_c = mcf;
+        b_c = 1.0f / __fsqrt_rn(__fadd_rn(vcf, 1e-7f));
+        a_n = mnf;
+        b_n = 1.0f / __fsqrt_rn(__fadd_rn(vnf, 1e-7f));
+      }
+    } else {
+      const double sw = mixed ? (s_c1 + s * s_n1) : s_c1;
+      const double sww = mixed ? (s_cc + 2.0 * s * s_cn + s * s * s_nn) : s_cc;
+      const double mn = sw * inv_L;
+      const double vn = sww * inv_L - mn * mn;
+      a_n = static_cast<float>(mn);
+      b_n = 1.0f / __fsqrt_rn(__fadd_rn(static_cast<float>(vn), 1e-7f));
+      if (p.raw) {
+        a_n = 0.f;
+        b_n = 1.f;
+      }
+    }
+    sc.inv_dc = inv_dc; sc.inv_dn = inv_dn;
+    sc.a_c = a_c; sc.b_c = b_c; sc.a_n = a_n; sc.b_n = b_n;
+    sc.st = st;
+    if (rank == 0) p.status[row] = st;
+  }
+  __syncthreads();
+  const int st = sc.st;
+
+  // ---- pass 3 (on chip -> HBM) ---------------------------------------------------------------------------------------
+  float4* co = p.clean_out ? reinterpret_cast<float4*>(p.clean_out + static_cast<size_t>(row) * L) + v_begin : nullptr;
+  float4* no = reinterpret_cast<float4*>(p.noisy_out + static_cast<size_t>(row) * L) + v_begin;
+  if (p.peak_norm && st != 0) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int v = tid; v < n_my; v += kResThreads) {
+      st_stream_cs_f4(co + v, z);
+      st_stream_cs_f4(no + v, z);
+    }
+    return;
+  }
+  const f2 nac2 = f2_make(-sc.a_c, -sc.a_c), bc2 = f2_make(sc.b_c, sc.b_c), idc2 = f2_make(sc.inv_dc, sc.inv_dc);
+  const f2 nan2 = f2_make(-sc.a_n, -sc.a_n), bn2 = f2_make(sc.b_n, sc.b_n), idn2 = f2_make(sc.inv_dn, sc.inv_dn);
+  auto emit = [&](int v, const float4& cv, const float4& yv) {
+    const f2 c01 = f2_make(cv.x, cv.y), c23 = f2_make(cv.z, cv.w);
+    f2 y01 = f2_make(yv.x, yv.y), y23 = f2_make(yv.z, yv.w);
+    float4 on;
+    if (p.peak_norm) {  // the noise slot already holds the mixed signal
+      float4 oc;
+      f2_split(f2_mul(f2_add(f2_mul(c01, idc2), nac2), bc2), oc.x, oc.y);  // (c/dc - mean) / std, 3 roundings
+      f2_split(f2_mul(f2_add(f2_mul(c23, idc2), nac2), bc2), oc.z, oc.w);
+      f2_split(f2_mul(f2_add(f2_mul(y01, idn2), nan2), bn2), on.x, on.y);
+      f2_split(f2_mul(f2_add(f2_mul(y23, idn2), nan2), bn2), on.z, on.w);
+      st_stream_cs_f4(co + v, oc);
+    } else {
+      if (mixed) {
+        y01 = f2_add(c01, f2_mul(y01, s2));
+        y23 = f2_add(c23, f2_mul(y23, s2));
+      } else {
+        y01 = c01;
+        y23 = c23;
+      }
+      f2_split(f2_mul(f2_add(y01, nan2), bn2), on.x, on.y);
+      f2_split(f2_mul(f2_add(y23, nan2), bn2), on.z, on.w);
+    }
+    st_stream_cs_f4(no + v, on);
+  };
+#pragma unroll
+  for (int u = 0; u < kResRegVec; ++u) {
+    const int v = u * kResThreads + tid;
+    if (v < n_reg) emit(v, rc[u], rn[u]);
+  }
+  for (int v = tid; v < n_sm; v += kResThreads) emit(n_reg + v, s_c[v], s_n[v]);
+}
+
+int g_mix_carveout = -1;  // shared-memory carveout (percent) of the resident kernels; -1: just what the CTAs need
 int g_mix_stream_cluster = 0;  // 0: automatic; 1/2/4/8 force the CTAs-per-row of the streaming variant (tuning)
-int g_mix_variant = 3;  // 3: streaming, one large CTA (or small cluster) per row, passes 2-3 from L2 (default);
+int g_mix_variant = 4;  // 4: on-chip resident (registers + shared memory), default when the row fits 8 CTAs
+                        //    (5: the same, forcing the 1024-thread / one-CTA-per-SM shape);
+                        // 3: streaming, one large CTA (or small cluster) per row, passes 2-3 from L2;
                         // 2: persistent double-buffered shared-memory pipeline; 1: shared memory, one row per
                         // cluster; 0: generic re-read-from-L2 kernel (also the fallback for unaligned rows)
 
@@ -979,13 +1329,20 @@ const char* const kMixStatusNames[] = {
 
 extern "C" {
 
-int nrse_debug_mix_stream_cluster(int cs) {
-  nrse::g_mix_stream_cluster = cs;
+int nrse_mix_set_cluster(int ctas_per_row) {
+  if (ctas_per_row < 0 || ctas_per_row > nrse::kSmemMaxCluster) return NRSE_ERR_INVALID_ARG;
+  nrse::g_mix_stream_cluster = ctas_per_row;
+  return NRSE_OK;
+}
+
+int nrse_mix_set_carveout(int percent) {
+  if (percent < -1 || percent > 100) return NRSE_ERR_INVALID_ARG;
+  nrse::g_mix_carveout = percent;
   return NRSE_OK;
 }
 
 int nrse_mix_set_variant(int variant) {
-  if (variant < 0 || variant > 3) return NRSE_ERR_INVALID_ARG;
+  if (variant < 0 || variant > 5) return NRSE_ERR_INVALID_ARG;
   nrse::g_mix_variant = variant;
   return NRSE_OK;
 }
@@ -1026,7 +1383,71 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
   cfg.attrs = attr;
   cfg.numAttrs = 1;
 
-  if (vec && g_mix_variant == 3) {
+  if (vec && g_mix_variant >= 4) {
+    // CTAs per row (<= 8, any size; sweep in scripts/bench_mix_sweep.py, B200): the 512-thread shape with segments of
+    // <= 4096 float4 (half in registers, half in shared memory: 2 x 64 KB of shared memory per SM leaves ~100 KB of
+    // L1 for the register-bound loads in flight) is best at every length it can serve; segments that fill the whole
+    // shared-memory capacity (5334 float4: 61 % instead of 73 % at 4 s) or larger clusters than needed lose 5-15 %.
+    // Longer rows: 512 threads up to the full capacity, then the 1024-thread shape; rows beyond 8 x 40960 samples
+    // (20 s) go to the streaming variant.
+    const int nvec = L / 4;
+    auto min_cluster = [&](int cap) {
+      const int cs = ceil_div(nvec, cap);
+      return cs < 1 ? 1 : cs;
+    };
+    int threads = 512, cs = min_cluster(2 * ResCfg<512>::kRegCap);
+    if (cs > kSmemMaxCluster) cs = min_cluster(ResCfg<512>::kCap);
+    if (cs > kSmemMaxCluster || g_mix_variant == 5) {
+      threads = 1024;
+      cs = min_cluster(ResCfg<1024>::kCap);
+    }
+    if (cs <= kSmemMaxCluster) {
+      const int cap = threads == 512 ? ResCfg<512>::kCap : ResCfg<1024>::kCap;
+      const int reg_cap = threads == 512 ? ResCfg<512>::kRegCap : ResCfg<1024>::kRegCap;
+      if (g_mix_stream_cluster > 0 && ceil_div(nvec, g_mix_stream_cluster) <= cap) cs = g_mix_stream_cluster;
+      const int seg_vec = ceil_div(nvec, cs);
+      const int smem_pitch = seg_vec > reg_cap ? seg_vec - reg_cap : 0;
+      const size_t dyn = static_cast<size_t>(smem_pitch) * 32;
+      static bool res_attr_set = false;  // benign race: idempotent attributes
+      if (!res_attr_set) {
+        NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<512>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, ResCfg<512>::kSmemCap * 32));
+        NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<1024>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, ResCfg<1024>::kSmemCap * 32));
+        res_attr_set = true;
+      }
+      // Shared-memory carveout: just enough for the resident CTAs.  Whatever is left stays L1, and L1 is where the
+      // 128 KB of register-bound loads per SM land while in flight: with the carveout at 100 % the same kernel is
+      // 15-25 % slower (measured), the loads being throttled by the 28 KB of L1 that remain.
+      {
+        const int ctas_per_sm = threads == 512 ? 2 : 1;
+        const size_t need = ctas_per_sm * (dyn + 2048 + 1024);
+        int pct = g_mix_carveout >= 0 ? g_mix_carveout : static_cast<int>((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+        pct = pct > 100 ? 100 : pct;
+        static int last_pct[2] = {-1, -1};  // benign race: idempotent attribute
+        int& last = last_pct[threads == 512 ? 0 : 1];
+        if (pct != last) {
+          if (threads == 512)
+            NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<512>,
+                                               cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+          else
+            NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<1024>,
+                                               cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+          last = pct;
+        }
+      }
+      cfg.gridDim = dim3(static_cast<unsigned>(B) * cs);
+      cfg.blockDim = dim3(threads);
+      cfg.dynamicSmemBytes = dyn;
+      attr[0].val.clusterDim.x = cs;
+      if (threads == 512)
+        NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_resident_kernel<512>, p, seg_vec, smem_pitch));
+      else
+        NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_resident_kernel<1024>, p, seg_vec, smem_pitch));
+      return NRSE_OK;
+    }
+  }
+  if (vec && g_mix_variant >= 3) {
     // one CTA of 1024 threads per row when the batch fills the machine, else the largest cluster (<= 8) that keeps
     // B * cs within the SM count
     // 1 CTA per SM (1024 threads x 64 registers): pick the cluster size (CTAs per row) that wastes the fewest SM-slots

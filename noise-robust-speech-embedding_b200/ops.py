@@ -179,6 +179,88 @@ def ema_update_(online: Sequence[Tensor], target: Sequence[Tensor], decay: float
 
 
 # --------------------------------------------------------------------------------------------------------------
+# Fused optimizer tail: clip_grad_norm_ + AdamW + EMA  (ref:train_byol.py:67-71)
+# --------------------------------------------------------------------------------------------------------------
+class OptimChunkTable:
+    """Device chunk table over (param, grad, exp_avg, exp_avg_sq, EMA target twin) for ONE optimizer step count,
+    plus the two launches that consume it.  ``update`` rebuilds the table only when an address changed
+    (``zero_grad(set_to_none=True)`` re-allocates the gradients, but the caching allocator hands the same blocks
+    back, so in steady state the table is built once)."""
+
+    CHUNK_ELEMS = 16384
+
+    def __init__(self):
+        self._key = None
+        self.n_chunks = 0
+        self.numel = 0          # elements that take an AdamW update
+        self.ema_numel = 0      # elements that take an EMA update
+        self._ptrs = self._numel = None
+
+    @staticmethod
+    def partials_count() -> int:
+        return int(_lib.load().nrse_optim_partials_count())
+
+    def update(self, params: Sequence[Tensor], grads, exp_avgs, exp_avg_sqs, twins) -> None:
+        """``grads[i]`` may be None (AdamW skips the tensor; its twin, if any, is still averaged); ``twins[i]`` may
+        be None (no EMA for that parameter)."""
+        entries, dev = [], None
+        for p, g, m, v, t in zip(params, grads, exp_avgs, exp_avg_sqs, twins):
+            if g is None and t is None:
+                continue
+            ts = [x for x in ((p, g, m, v, t) if g is not None else (p, t)) if x is not None]
+            _need_cuda(*ts)
+            for x in ts:
+                if x.dtype != torch.float32 or not x.is_contiguous() or x.numel() != p.numel() or x.is_sparse:
+                    raise NrseError("OptimChunkTable: dense contiguous fp32 tensors of the parameter's size expected")
+            dev = p.device
+            entries.append((p.data_ptr(), 0 if g is None else g.data_ptr(), 0 if g is None else m.data_ptr(),
+                            0 if g is None else v.data_ptr(), 0 if t is None else t.data_ptr(), p.numel()))
+        key = tuple(entries)
+        if key == self._key:
+            return
+        self._key = key
+        lib = _lib.load()
+        n = len(entries)
+        self.numel = sum(e[5] for e in entries if e[1])
+        self.ema_numel = sum(e[5] for e in entries if e[4])
+        self.n_chunks = 0
+        if n == 0:
+            return
+        arr = lambda k: (C.c_uint64 * n)(*[e[k] for e in entries])
+        P, G, M, V, T = (arr(k) for k in range(5))
+        NE = (C.c_int64 * n)(*[e[5] for e in entries])
+        cnt = int(lib.nrse_optim_plan_chunks_host(P, G, M, V, T, NE, n, self.CHUNK_ELEMS, None, None, 0))
+        if cnt < 0:
+            check(cnt, "nrse_optim_plan_chunks_host")
+        if cnt == 0:
+            return
+        ptrs = (C.c_uint64 * (5 * cnt))()
+        cn = (C.c_int32 * cnt)()
+        got = lib.nrse_optim_plan_chunks_host(P, G, M, V, T, NE, n, self.CHUNK_ELEMS, ptrs, cn, cnt)
+        if got != cnt:
+            raise NrseError("nrse_optim_plan_chunks_host: inconsistent chunk count")
+        self._ptrs = torch.frombuffer(bytearray(bytes(ptrs)), dtype=torch.int64).to(dev)  # p | g | m | v | t
+        self._numel = torch.frombuffer(bytearray(bytes(cn)), dtype=torch.int32).to(dev)
+        self.n_chunks = cnt
+
+    def grad_sqnorm(self, partials: Tensor) -> None:
+        """Writes ``partials_count()`` fp64 partial sums of squares of this table's gradients into ``partials``."""
+        g_ptrs = None if self.n_chunks == 0 else C.c_void_p(self._ptrs.data_ptr() + 8 * self.n_chunks)
+        check(_lib.load().nrse_grad_sqnorm_chunks_f32(g_ptrs, _ptr(self._numel), self.n_chunks, _ptr(partials),
+                                                      _stream()), "nrse_grad_sqnorm_chunks_f32")
+
+    def clip_adamw_ema(self, *, lr: float, betas, eps: float, weight_decay: float, step: int, max_grad_norm: float,
+                       ema_decay: float, partials: Optional[Tensor], norm_out: Optional[Tensor]) -> None:
+        if self.n_chunks == 0:
+            return
+        check(_lib.load().nrse_clip_adamw_ema_chunks_f32(
+            _ptr(self._ptrs), self.n_chunks, _ptr(self._numel), self.n_chunks, float(lr), float(betas[0]),
+            float(betas[1]), float(eps), float(weight_decay), int(step), float(max_grad_norm), float(ema_decay),
+            _ptr(partials), 0 if partials is None else partials.numel(), _ptr(norm_out), _stream()),
+            "nrse_clip_adamw_ema_chunks_f32")
+
+
+# --------------------------------------------------------------------------------------------------------------
 # BYOL loss
 # --------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("nrse::byol_loss_fwd", mutates_args=())
@@ -366,6 +448,14 @@ def set_frontend_variant(variant: int) -> None:
 
 def set_mix_variant(variant: int) -> None:
     check(_lib.load().nrse_mix_set_variant(int(variant)), "nrse_mix_set_variant")
+
+
+def set_mix_cluster(ctas_per_row: int) -> None:
+    check(_lib.load().nrse_mix_set_cluster(int(ctas_per_row)), "nrse_mix_set_cluster")
+
+
+def set_mix_carveout(percent: int) -> None:
+    check(_lib.load().nrse_mix_set_carveout(int(percent)), "nrse_mix_set_carveout")
 
 
 def set_layer0_variant(variant: int) -> None:

@@ -7,3 +7,4 @@ from .byol import (  # noqa: F401
     validate_model,
 )
 from .distributed import init_distributed, wrap_data_parallel  # noqa: F401
+from .optim import FusedAdamWEma  # noqa: F401

@@ -19,6 +19,7 @@ import torch
 from .. import ops
 from ..models.byol import BYOLSpeechModel, byol_loss
 from ..utils.logging_utils import logger
+from .optim import FusedAdamWEma
 
 
 def _flags(t: torch.Tensor, max_threshold: float, min_threshold: float) -> torch.Tensor:
@@ -44,15 +45,21 @@ def check_audio_tensor(tensor: torch.Tensor, name: str, config, max_threshold: f
 def byol_step(model: BYOLSpeechModel, clean: torch.Tensor, noisy: torch.Tensor, optimizer, scheduler=None,
               max_grad_norm: float = 1.0) -> torch.Tensor:
     """forward -> byol_loss -> zero_grad -> backward -> clip_grad_norm_(1.0) -> optimizer.step -> EMA -> scheduler.step
-    (ref:train_byol.py:56-74).  Returns the detached loss (device tensor; no host sync)."""
+    (ref:train_byol.py:56-74).  Returns the detached loss (device tensor; no host sync).
+
+    With a ``FusedAdamWEma`` optimizer that has the clip and the EMA attached (``FusedAdamWEma.for_byol``) the three
+    tail stages are its two kernel launches; with any other optimizer they run as in the reference."""
     online_pred, target_proj = model(clean, noisy)
     loss = byol_loss(online_pred, target_proj)
     optimizer.zero_grad(set_to_none=True)
     loss.backward()
-    torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_grad_norm)
+    fused = isinstance(optimizer, FusedAdamWEma)
+    if not (fused and optimizer.max_grad_norm > 0):
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_grad_norm)
     optimizer.step()
-    inner = model.module if hasattr(model, "module") else model  # DistributedDataParallel wrapper
-    inner._update_target_network()
+    if not (fused and optimizer.has_ema):
+        inner = model.module if hasattr(model, "module") else model  # DistributedDataParallel wrapper
+        inner._update_target_network()
     if scheduler is not None:
         scheduler.step()
     return loss.detach()

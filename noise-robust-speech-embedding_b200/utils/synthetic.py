@@ -76,3 +76,9 @@ def embeddings(batch: int, dim: int = 1024, seed: int = 7):
     mix = rs.uniform(-1.0, 1.0, size=(batch, 1)).astype(np.float32)
     z = (mix * p + (1 - np.abs(mix)) * rs.standard_normal((batch, dim))).astype(np.float32)
     return p, z
+
+
+def optim_step_grad(seed: int, k: int, i: int, shape, scale: float) -> np.ndarray:
+    """Synthetic gradient of tensor ``i`` at step ``k`` of the optimizer fixture (same generator as
+    tests/golden/make_golden.py::optim_step_grad, so the fixture does not have to store the gradients)."""
+    return (scale * np.random.RandomState(seed * 100000 + k * 1000 + i).standard_normal(shape)).astype(np.float32)

@@ -14,7 +14,7 @@ copied.  Shims, all explicit below:
   3. ``load_and_process_audio`` -> in-memory tensors (torchaudio cannot decode in this image).
 Outputs (float arrays kept small; inputs are stored too so fixtures are self-contained):
   mix_byol.npz, mix_emotion.npz, mix_edge.npz, byol_loss.npz, ema.npz, frontend_layer.npz,
-  frontend_group.npz, byol_step.npz, byol_state_dict_keys.json
+  frontend_group.npz, byol_step.npz, byol_state_dict_keys.json, optim_step.npz
 """
 import os
 import random
@@ -290,6 +290,69 @@ def gen_byol_step(seed=51, B=4, L=4000):
         ref_encoder_mod.WavLMEncoder.forward = orig_fwd
 
 
+OPTIM_GRAD_SCALES = (3e-2, 1e-2, 1e-4)
+
+
+optim_step_grad = synthetic.optim_step_grad  # the tests rebuild the gradients with the same generator
+
+
+def gen_optim_step(seed=61, steps=3):
+    """ref:train_byol.py:67-71 on the shimmed tiny model with the REAL torch pieces: ``clip_grad_norm_`` +
+    ``torch.optim.AdamW(model.parameters(), lr, weight_decay)`` (CPU => single-tensor path) + the reference's
+    ``_update_target_network``; synthetic gradients (step 0 and 1 clip, step 2 does not); two parameters never get a
+    gradient (as ``masked_spec_embed`` does not in a real run)."""
+    cfg_small = WavLMConfig(hidden_size=32, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64,
+                            conv_dim=(16,) * 7, num_conv_pos_embeddings=8, num_conv_pos_embedding_groups=2,
+                            feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=False)
+    orig = ref_encoder_mod.AutoModel.from_pretrained
+    ref_encoder_mod.AutoModel.from_pretrained = staticmethod(lambda name: WavLMModel(cfg_small))
+    try:
+        torch.manual_seed(seed)
+        model = RefBYOL({"model": {"name": "shim", "projection_dim": 24, "prediction_dim": 48, "ema_decay": 0.996}})
+    finally:
+        ref_encoder_mod.AutoModel.from_pretrained = orig
+    rs = np.random.RandomState(seed)
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    no_grad = {named[0][0], named[5][0]}
+    lr, wd = 1e-3, 1e-2
+    opt = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=wd)
+    out = {"names": np.array([n for n, _ in named]), "no_grad": np.array(sorted(no_grad)),
+           "lr": np.array(lr), "weight_decay": np.array(wd), "ema_decay": np.array(model.ema_decay),
+           "steps": np.array(steps), "seed": np.array(seed), "grad_scales": np.array(OPTIM_GRAD_SCALES)}
+    pairs = list(zip(model.online_encoder.parameters(), model.target_encoder.parameters())) + \
+        list(zip(model.online_projector.parameters(), model.target_projector.parameters()))
+    twin = {id(o): t for o, t in pairs}
+    with torch.no_grad():
+        for o, t in pairs:  # make the targets differ from the online weights
+            t.add_(torch.from_numpy((0.02 * rs.standard_normal(tuple(t.shape))).astype(np.float32)))
+    for i, (n, p) in enumerate(named):
+        out[f"p0_{i}"] = p.detach().numpy().copy()
+        out[f"has_twin_{i}"] = np.array(id(p) in twin)
+        if id(p) in twin:
+            out[f"t0_{i}"] = twin[id(p)].detach().numpy().copy()
+    norms = []
+    for k, scale in zip(range(steps), OPTIM_GRAD_SCALES):
+        opt.zero_grad()
+        for i, (n, p) in enumerate(named):
+            if n in no_grad:
+                continue
+            g = optim_step_grad(seed, k, i, tuple(p.shape), scale)  # regenerated by the tests, not stored
+            p.grad = torch.from_numpy(g.copy())
+        norms.append(float(torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)))   # ref:train_byol.py:67
+        opt.step()                                                                               # :70
+        model._update_target_network()                                                           # :71
+    out["norms"] = np.array(norms, dtype=np.float32)
+    for i, (n, p) in enumerate(named):
+        out[f"p_{i}"] = p.detach().numpy().copy()
+        if id(p) in twin:
+            out[f"t_{i}"] = twin[id(p)].detach().numpy().copy()
+        if n not in no_grad:
+            st = opt.state[p]
+            out[f"m_{i}"], out[f"v_{i}"] = st["exp_avg"].numpy().copy(), st["exp_avg_sq"].numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "optim_step.npz"), **out)
+    print("optim_step: tensors", len(named), "elems", sum(p.numel() for _, p in named), "norms", norms)
+
+
 if __name__ == "__main__":
     print("transformers", transformers.__version__, "torch", torch.__version__, "numpy", np.__version__)
     gen_mix_byol()
@@ -300,4 +363,5 @@ if __name__ == "__main__":
     gen_frontend("layer")
     gen_frontend("group")
     gen_byol_step()
+    gen_optim_step()
     print("sizes:", {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")})

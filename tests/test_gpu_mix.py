@@ -12,12 +12,12 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-6  # north star: mixing within 1e-6 relative (norm-relative)
 
 
-@pytest.fixture(params=[3, 2, 1, 0], ids=["stream", "pipe", "smem", "l2"], autouse=True)
+@pytest.fixture(params=[4, 5, 3, 2, 1, 0], ids=["resident", "resident1024", "stream", "pipe", "smem", "l2"], autouse=True)
 def mix_variant(request):
     """Every test runs on both kernels: shared-memory-resident rows (default) and the re-read-from-L2 kernel."""
     ops.set_mix_variant(request.param)
     yield request.param
-    ops.set_mix_variant(3)
+    ops.set_mix_variant(4)
 
 
 def _run(dev, clean, noise, snr_idx, table, peak_norm=True):
@@ -73,7 +73,9 @@ def test_golden_edge_statuses(dev, golden):
 @pytest.mark.parametrize("B,L,Ln,peak", [(5, 4000, 4000, True), (3, 4001, 4001, True), (4, 3998, 1500, True),
                                          (3, 6000, 7003, False), (2, 401, 401, True), (7, 16000, 16000, False),
                                          (2, 64000, 64000, True), (2, 192000, 192000, True), (3, 32000, 32004, False),
-                                         (1, 240000, 240000, True), (9, 8, 8, True)])
+                                         (1, 240000, 240000, True), (9, 8, 8, True),
+                                         (1, 400000, 400000, True), (2, 80000, 80000, True),
+                                         (3, 16388, 16388, False), (2, 40960, 40960, True), (2, 40964, 40964, True)])
 def test_random_vs_oracle(dev, B, L, Ln, peak):
     clean, noise, snr_idx, table = synthetic.waveforms(B, L, seed=100 + L % 97, n_noise=Ln)
     c_ref, n_ref, st_ref = oracle.mix_normalize_batch(clean, noise, snr_idx, table, peak_norm=peak)
@@ -117,3 +119,21 @@ def test_full_size_properties(dev):
         coef, *_ = np.linalg.lstsq(A, nz, rcond=None)
         snr = 10 * np.log10((coef[0] ** 2 * (cz ** 2).mean()) / (coef[1] ** 2 * (noise[b].astype(np.float64) ** 2).mean()))
         assert abs(snr - table[snr_idx[b]]) < 1e-3
+
+
+@pytest.mark.parametrize("cs", [1, 2, 3, 4, 8])
+def test_forced_cluster_sizes(dev, mix_variant, cs):
+    """Variants 3 / 4 with every CTAs-per-row setting (incl. a non-power-of-two cluster): same result, so the
+    automatic choice is a pure performance knob."""
+    if mix_variant not in (3, 4, 5):
+        pytest.skip("cluster knob applies to the streaming / resident kernels")
+    clean, noise, snr_idx, table = synthetic.waveforms(3, 64000, seed=17)
+    c_ref, n_ref, st_ref = oracle.mix_normalize_batch(clean, noise, snr_idx, table)
+    ops.set_mix_cluster(cs)
+    try:
+        c, n, st = _run(dev, clean, noise, snr_idx, table)
+    finally:
+        ops.set_mix_cluster(0)
+    assert st.tolist() == st_ref.tolist()
+    for b in range(3):
+        assert rel_err(n[b], n_ref[b].numpy()) < TOL and rel_err(c[b], c_ref[b].numpy()) < TOL

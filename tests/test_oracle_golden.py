@@ -126,3 +126,37 @@ def test_single_mufu_gelu_fit_is_exact_gelu():
     ex = np.exp2(u * u * np.float32(-0.72134752)).astype(np.float32)
     grad = np.float32(0.5) + np.copysign(np.float32(0.5) - ex * r, x)
     assert np.abs(grad - xt.grad.numpy()).max() < 5e-5                    # bf16 resolution is 4e-3
+
+
+def _optim_fixture(g):
+    names = [str(n) for n in g["names"]]
+    no_grad = {str(n) for n in g["no_grad"]}
+    n = len(names)
+    params = [torch.from_numpy(g[f"p0_{i}"].copy()) for i in range(n)]
+    targets = [torch.from_numpy(g[f"t0_{i}"].copy()) if bool(g[f"has_twin_{i}"]) else None for i in range(n)]
+    has_grad = [names[i] not in no_grad for i in range(n)]
+
+    def grads(k):
+        return [torch.from_numpy(synthetic.optim_step_grad(int(g["seed"]), k, i, tuple(params[i].shape),
+                                                           float(g["grad_scales"][k]))) if has_grad[i] else None
+                for i in range(n)]
+    return names, params, targets, has_grad, grads
+
+
+def test_optim_step_matches_torch_adamw_and_reference_ema(golden):
+    """oracle.clip_adamw_ema_step == clip_grad_norm_ + torch.optim.AdamW + reference EMA, three steps, bit for bit."""
+    g = golden("optim_step")
+    names, params, targets, has_grad, grads = _optim_fixture(g)
+    m = [torch.zeros_like(p) for p in params]
+    v = [torch.zeros_like(p) for p in params]
+    for k in range(int(g["steps"])):
+        norm = oracle.clip_adamw_ema_step(params, grads(k), m, v, targets, k + 1, float(g["lr"]),
+                                          weight_decay=float(g["weight_decay"]), max_norm=1.0,
+                                          ema_decay=float(g["ema_decay"]))
+        assert abs(float(norm) - float(g["norms"][k])) <= 1e-6 * float(g["norms"][k])
+    for i in range(len(names)):
+        assert np.array_equal(params[i].numpy(), g[f"p_{i}"]), names[i]
+        if targets[i] is not None:
+            assert np.array_equal(targets[i].numpy(), g[f"t_{i}"]), names[i]
+        if has_grad[i]:
+            assert np.array_equal(m[i].numpy(), g[f"m_{i}"]) and np.array_equal(v[i].numpy(), g[f"v_{i}"]), names[i]
