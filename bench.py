@@ -405,6 +405,33 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
     kernels.append({"kernel": "ema_chunks_kernel (317.6 M params, 496 tensors, 1 launch)", "bound": "hbm", "ms": t_ema,
                     "achieved": 12.0 * plan.numel / (t_ema * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s"})
     del online, target, plan
+    # fused optimizer tail (clip_grad_norm_ + AdamW + EMA, ref:train_byol.py:67-71) at WavLM-large size: 325,958,336
+    # trainable parameters, of which 317,556,416 have an EMA twin; 4 B (norm read) + 28 B (p,g,m,v read; p,m,v write)
+    # per parameter + 8 B (t read, t write) per twin
+    from nrse_b200.train import FusedAdamWEma
+    pred_sizes = [1024 * 2048, 2048, 2048, 2048, 2048 * 2048, 2048, 2048, 2048, 2048 * 1024, 1024]
+    prm = [torch.nn.Parameter(torch.randn(s, device=dev) * 0.02) for s in sizes + pred_sizes]
+    twin = [torch.randn(s, device=dev) * 0.02 for s in sizes]
+    for q in prm:
+        q.grad = torch.randn_like(q) * 1e-3
+    fopt = FusedAdamWEma(prm, lr=1e-5, weight_decay=1e-5, max_grad_norm=1.0, ema_pairs=zip(prm[:len(twin)], twin),
+                         ema_decay=0.996)
+    fopt.step()
+    t_opt = ev_time(fopt.step, n=10)
+    n_upd, n_tw = sum(q.numel() for q in prm), sum(q.numel() for q in twin)
+    kernels.append({"kernel": "grad_sqnorm_chunks + adamw_ema_chunks (clip + AdamW + EMA, 325.9 M params, 2 launches)",
+                    "bound": "hbm", "ms": t_opt, "achieved": (32.0 * n_upd + 8.0 * n_tw) / (t_opt * 1e-3) / 1e9,
+                    "peak": hbm, "unit": "GB/s"})
+    ref_opt = torch.optim.AdamW(prm, lr=1e-5, weight_decay=1e-5)  # ref:train_byol.py:146; foreach on CUDA
+
+    def stock_tail():
+        torch.nn.utils.clip_grad_norm_(prm, 1.0)
+        ref_opt.step()
+        for i in range(len(twin)):
+            twin[i] = 0.996 * twin[i] + (1 - 0.996) * prm[i].data
+    t_stock_tail = plain_time(stock_tail, n=3)
+    del fopt, ref_opt, prm, twin
+    torch.cuda.empty_cache()
     p = torch.randn(B, 1024, device=dev, requires_grad=True)
     z = torch.randn(B, 1024, device=dev)
     t_loss = ev_time(lambda: ops.byol_loss(p, z))
@@ -440,6 +467,7 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
         b_ = torch.nn.functional.normalize(z + 1e-10, dim=1, eps=1e-10)
         return 2 - 2 * torch.clamp((a * b_).sum(1), -1.0, 1.0).mean()
     stock_ms["loss_fwd_ms"] = plain_time(stock_loss)
+    stock_ms["clip_adamw_ema_ms"] = t_stock_tail
 
     # training forward (tape-writing) + native backward of the frontend, and the same stack in stock torch on THIS GPU
     # (cuDNN conv1d + ATen layer_norm / gelu): the "kernel to beat" of BASELINE.md section 4 (G0)

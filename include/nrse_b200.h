@@ -89,6 +89,9 @@ int nrse_mix_set_variant(int variant);
 int nrse_mix_set_cluster(int ctas_per_row);
 /* tuning: shared-memory carveout (percent of 228 KB) of the resident kernels; -1 = just what the CTAs need (default) */
 int nrse_mix_set_carveout(int percent);
+/* tuning: start groups of a single-wave resident launch (rows start staggered so that one group's reduction bubbles
+ * overlap the next group's loads); -1 = automatic (default), 0 = off */
+int nrse_mix_set_stagger(int groups);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-tensor EMA:  target = decay*target + one_minus_decay*online   (fp32, in place,
@@ -146,6 +149,28 @@ int nrse_clip_adamw_ema_chunks_f32(const uint64_t* chunk_ptrs, int64_t chunk_pit
                                    double weight_decay, int64_t step, double max_grad_norm, double ema_decay,
                                    const double* partials, int n_partials, float* grad_norm_out,
                                    nrse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched Attentive Statistics Pooling, forward and backward (fp32).  Replaces the per-utterance loop of
+ * AttentiveStatisticsPooling.forward, ref:src/models/pool.py:37-58 (consumer of the encoder on the emotion
+ * fine-tune step, ref:src/models/emotion.py:60-79).  The linear layer `sap_linear` stays a library GEMM
+ * run by the caller over all B*T frames; these entry points do everything after it.
+ *   x, hl      [B,T,D] row-major fp32: encoder output and sap_linear(x) (pre-tanh); D % 4 == 0, T <= 4096
+ *   attention  [D]     the attention vector (ref:src/models/pool.py:33)
+ *   lens       [B]     int32 valid frames per utterance, min(compute_length_from_mask(mask), T)  (:44,47)
+ *   out        [B,2D]  (mu | rh):  w = softmax_t(tanh(hl) . attention) over t < len,  mu = sum_t w x,
+ *                      rh = sqrt(clamp(sum_t w x^2 - mu^2, min=1e-5))                  (:48-55)
+ *   weights    [B,T]   the softmax weights (0 for t >= len), kept for the backward
+ *   logits_ws / dw_ws  [B,T] fp32 scratch
+ * Backward: grad_x is the DIRECT gradient w.r.t. x (the path through sap_linear comes back from the
+ * caller's GEMM backward on grad_hl); grad_attention [D] is zeroed and accumulated here.
+ * ------------------------------------------------------------------------------------------- */
+int nrse_asp_pool_fwd(const float* x, const float* hl, const float* attention, const int32_t* lens, float* out,
+                      float* weights, float* logits_ws, int B, int T, int D, nrse_stream_t stream);
+int nrse_asp_pool_bwd(const float* x, const float* hl, const float* attention, const int32_t* lens,
+                      const float* out, const float* weights, const float* grad_out, float* grad_x,
+                      float* grad_hl, float* grad_attention, float* dw_ws, int B, int T, int D,
+                      nrse_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BYOL loss with fused +1e-10, L2 normalisation (eps 1e-10), row dot product, clamp and mean.

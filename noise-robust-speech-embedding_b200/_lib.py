@@ -58,6 +58,7 @@ SIGNATURES = {
     "nrse_mix_set_variant": (_i, [_i]),
     "nrse_mix_set_cluster": (_i, [_i]),
     "nrse_mix_set_carveout": (_i, [_i]),
+    "nrse_mix_set_stagger": (_i, [_i]),
     "nrse_ema_plan_chunks_host": (_i64, [_p, _p, _p, _i, _i64, _p, _p, _p, _i64]),
     "nrse_ema_chunks_f32": (_i, [_p, _p, _p, _i64, _f, _f, _p]),
     "nrse_optim_plan_chunks_host": (_i64, [_p, _p, _p, _p, _p, _p, _i, _i64, _p, _p, _i64]),
@@ -65,6 +66,8 @@ SIGNATURES = {
     "nrse_grad_sqnorm_chunks_f32": (_i, [_p, _p, _i64, _p, _p]),
     "nrse_clip_adamw_ema_chunks_f32": (_i, [_p, _i64, _p, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
                                            C.c_double, _i64, C.c_double, C.c_double, _p, _i, _p, _p]),
+    "nrse_asp_pool_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "nrse_asp_pool_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "nrse_byol_loss_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "nrse_byol_loss_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "nrse_conv_frontend_geometry": (_i, [_i, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnrse_b200.so")
-SOURCES = ["runtime.cu", "mix.cu", "ema.cu", "optim.cu", "loss.cu", "frontend.cu"]
+SOURCES = ["runtime.cu", "mix.cu", "ema.cu", "optim.cu", "pool.cu", "loss.cu", "frontend.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", os.path.join(ROOT, "include", "nrse_b200.h")]
 
 NVCC_FLAGS = [

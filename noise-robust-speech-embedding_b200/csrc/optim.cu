@@ -12,9 +12,10 @@
 //             first/second moment, bias-corrected step, and -- for parameters that have a target twin -- the EMA of
 //             the freshly updated value.  Reads p, g, m, v, t and writes p, m, v, t: 36 B/param (28 without a twin).
 // The arithmetic follows torch's single-tensor AdamW (torch/optim/adam.py::_single_tensor_adam with
-// decoupled_weight_decay) operation by operation, with the step-dependent scalars computed on the host in double exactly
-// as that code does; the EMA uses the reference's rounding (two products, one sum, no FMA), so given the updated
-// parameter the target is bit-identical to ref:src/models/byol.py:67-68.
+// decoupled_weight_decay), with the step-dependent scalars computed on the host in double exactly as that code does
+// (see adamw1 for the one deliberate deviation: approximate sqrt / reciprocal in the step term); the EMA uses the
+// reference's rounding (two products, one sum, no FMA), so given the updated parameter the target is bit-identical to
+// ref:src/models/byol.py:67-68.
 #include <cmath>
 
 #include "common.cuh"
@@ -25,6 +26,7 @@ namespace {
 constexpr int kOptThreads = 256;
 constexpr int kOptCtasPerSm = 8;
 constexpr int kNormUnroll = 4;
+constexpr int kOptUnroll = 2;  // float4 groups (p, g, m, v, t) per thread in flight
 
 struct OptTable {
   const uint64_t* p;
@@ -41,7 +43,7 @@ struct AdamScalars {
   float w1;           // 1 - beta1   (lerp weight)
   float beta2;
   float omb2;         // 1 - beta2
-  float bc2_sqrt;     // sqrt(1 - beta2^step)
+  float inv_bc2_sqrt; // 1 / sqrt(1 - beta2^step)
   float eps;
   float neg_step;     // -(lr / (1 - beta1^step))
   float ema_decay, ema_omd;
@@ -93,19 +95,36 @@ __global__ void __launch_bounds__(kOptThreads) grad_sqnorm_chunks_kernel(const u
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
+// One element of torch/optim/adam.py::_single_tensor_adam (decoupled weight decay).  The moments and the weight decay are
+// the same IEEE operations torch issues; the step itself, p += -step_size * m / (sqrt(v) / bc2_sqrt + eps), uses the
+// hardware approximations (MUFU.SQRT / MUFU.RCP, <= 2 ulp) and a reciprocal of bc2_sqrt: correctly rounded division and
+// square root cost ~25 instructions and two conditional slow-path calls per element, which made the kernel latency-
+// instead of HBM-bound (52 % of peak).  The approximation perturbs the update term by < 3e-7 of ITS size, i.e. the
+// parameter by < 3e-7 * lr relative -- three orders of magnitude inside the 1e-6 tolerance (torch's own CUDA kernels
+// differ from its CPU path by the same kind of rounding).
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void adamw1(float& p, float g, float& m, float& v, const AdamScalars& a, float coef) {
   g = __fmul_rn(g, coef);                                     // clip_grad_norm_: grads.mul_(clip_coef_clamped)
   p = __fmul_rn(p, a.decay_mul);                              // param.mul_(1 - lr * weight_decay)
   m = __fmaf_rn(a.w1, __fsub_rn(g, m), m);                    // exp_avg.lerp_(grad, 1 - beta1)
   v = __fadd_rn(__fmul_rn(v, a.beta2), __fmul_rn(__fmul_rn(a.omb2, g), g));  // mul_(beta2).addcmul_(g, g, 1 - beta2)
-  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), a.bc2_sqrt), a.eps);
-  p = __fadd_rn(p, __fmul_rn(a.neg_step, __fdiv_rn(m, denom)));  // param.addcdiv_(exp_avg, denom, value=-step_size)
+  const float denom = __fmaf_rn(sqrt_approx(v), a.inv_bc2_sqrt, a.eps);      // sqrt(v) / bc2_sqrt + eps
+  p = __fmaf_rn(a.neg_step, __fmul_rn(m, rcp_approx(denom)), p);             // param.addcdiv_(m, denom, -step_size)
 }
 __device__ __forceinline__ float ema1(float t, float o, float decay, float omd) {
   return __fadd_rn(__fmul_rn(decay, t), __fmul_rn(omd, o));
 }
 
-__global__ void __launch_bounds__(kOptThreads) adamw_ema_chunks_kernel(const OptTable tab, const AdamScalars a,
+__global__ void __launch_bounds__(kOptThreads, 4) adamw_ema_chunks_kernel(const OptTable tab, const AdamScalars a,
                                                                        const double* __restrict__ partials,
                                                                        int n_partials, float* __restrict__ out_norm) {
   __shared__ double scratch[kOptThreads / 32];
@@ -139,26 +158,37 @@ __global__ void __launch_bounds__(kOptThreads) adamw_ema_chunks_kernel(const Opt
                           reinterpret_cast<uintptr_t>(t);
     const int nvec = (all & 15u) == 0 ? (n >> 2) : 0;
     if (g) {
-      for (int i = threadIdx.x; i < nvec; i += kOptThreads) {
-        float4 pv = reinterpret_cast<float4*>(p)[i];
-        const float4 gv = ld_stream_f4(reinterpret_cast<const float4*>(g) + i);  // last use of the gradient
-        float4 mv = reinterpret_cast<float4*>(m)[i];
-        float4 vv = reinterpret_cast<float4*>(v)[i];
-        float4 tv;
-        if (t) tv = reinterpret_cast<float4*>(t)[i];
-        adamw1(pv.x, gv.x, mv.x, vv.x, a, coef);
-        adamw1(pv.y, gv.y, mv.y, vv.y, a, coef);
-        adamw1(pv.z, gv.z, mv.z, vv.z, a, coef);
-        adamw1(pv.w, gv.w, mv.w, vv.w, a, coef);
-        reinterpret_cast<float4*>(p)[i] = pv;
-        reinterpret_cast<float4*>(m)[i] = mv;
-        reinterpret_cast<float4*>(v)[i] = vv;
-        if (t) {
-          tv.x = ema1(tv.x, pv.x, a.ema_decay, a.ema_omd);
-          tv.y = ema1(tv.y, pv.y, a.ema_decay, a.ema_omd);
-          tv.z = ema1(tv.z, pv.z, a.ema_decay, a.ema_omd);
-          tv.w = ema1(tv.w, pv.w, a.ema_decay, a.ema_omd);
-          reinterpret_cast<float4*>(t)[i] = tv;
+      for (int i0 = threadIdx.x; i0 < nvec; i0 += kOptThreads * kOptUnroll) {
+        float4 pv[kOptUnroll], gv[kOptUnroll], mv[kOptUnroll], vv[kOptUnroll], tv[kOptUnroll];
+#pragma unroll
+        for (int u = 0; u < kOptUnroll; ++u) {  // all loads of the unrolled group in flight before any arithmetic
+          const int i = i0 + u * kOptThreads;
+          if (i < nvec) {
+            pv[u] = reinterpret_cast<float4*>(p)[i];
+            gv[u] = ld_stream_f4(reinterpret_cast<const float4*>(g) + i);  // last use of the gradient
+            mv[u] = reinterpret_cast<float4*>(m)[i];
+            vv[u] = reinterpret_cast<float4*>(v)[i];
+            if (t) tv[u] = reinterpret_cast<float4*>(t)[i];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kOptUnroll; ++u) {
+          const int i = i0 + u * kOptThreads;
+          if (i >= nvec) break;
+          adamw1(pv[u].x, gv[u].x, mv[u].x, vv[u].x, a, coef);
+          adamw1(pv[u].y, gv[u].y, mv[u].y, vv[u].y, a, coef);
+          adamw1(pv[u].z, gv[u].z, mv[u].z, vv[u].z, a, coef);
+          adamw1(pv[u].w, gv[u].w, mv[u].w, vv[u].w, a, coef);
+          reinterpret_cast<float4*>(p)[i] = pv[u];
+          reinterpret_cast<float4*>(m)[i] = mv[u];
+          reinterpret_cast<float4*>(v)[i] = vv[u];
+          if (t) {
+            tv[u].x = ema1(tv[u].x, pv[u].x, a.ema_decay, a.ema_omd);
+            tv[u].y = ema1(tv[u].y, pv[u].y, a.ema_decay, a.ema_omd);
+            tv[u].z = ema1(tv[u].z, pv[u].z, a.ema_decay, a.ema_omd);
+            tv[u].w = ema1(tv[u].w, pv[u].w, a.ema_decay, a.ema_omd);
+            reinterpret_cast<float4*>(t)[i] = tv[u];
+          }
         }
       }
       for (int i = (nvec << 2) + threadIdx.x; i < n; i += kOptThreads) {
@@ -263,7 +293,7 @@ int nrse_clip_adamw_ema_chunks_f32(const uint64_t* chunk_ptrs, int64_t chunk_pit
   a.w1 = static_cast<float>(1.0 - beta1);
   a.beta2 = static_cast<float>(beta2);
   a.omb2 = static_cast<float>(1.0 - beta2);
-  a.bc2_sqrt = static_cast<float>(std::sqrt(bc2));
+  a.inv_bc2_sqrt = static_cast<float>(1.0 / std::sqrt(bc2));
   a.eps = static_cast<float>(eps);
   a.neg_step = static_cast<float>(-(lr / bc1));
   a.ema_decay = static_cast<float>(ema_decay);

@@ -334,6 +334,75 @@ def cosine_rows(a: Tensor, b: Tensor) -> Tensor:
 
 
 # --------------------------------------------------------------------------------------------------------------
+# Attentive statistics pooling (ref:src/models/pool.py:37-58)
+# --------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("nrse::asp_pool_fwd", mutates_args=())
+def _asp_pool_fwd(x: Tensor, hl: Tensor, attention: Tensor, lens: Tensor) -> Tuple[Tensor, Tensor]:
+    _need_cuda(x, hl, attention, lens)
+    B, T, D = x.shape
+    out = torch.empty(B, 2 * D, dtype=torch.float32, device=x.device)
+    weights = torch.empty(B, T, dtype=torch.float32, device=x.device)
+    logits = torch.empty(B, T, dtype=torch.float32, device=x.device)
+    check(_lib.load().nrse_asp_pool_fwd(_ptr(x), _ptr(hl), _ptr(attention), _ptr(lens), _ptr(out), _ptr(weights),
+                                        _ptr(logits), B, T, D, _stream()), "nrse_asp_pool_fwd")
+    return out, weights
+
+
+@_asp_pool_fwd.register_fake
+def _(x, hl, attention, lens):
+    B, T, D = x.shape
+    return x.new_empty(B, 2 * D, dtype=torch.float32), x.new_empty(B, T, dtype=torch.float32)
+
+
+@torch.library.custom_op("nrse::asp_pool_bwd", mutates_args=())
+def _asp_pool_bwd(x: Tensor, hl: Tensor, attention: Tensor, lens: Tensor, out: Tensor, weights: Tensor,
+                  grad_out: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    B, T, D = x.shape
+    gx, gh = torch.empty_like(x), torch.empty_like(hl)
+    ga = torch.empty(D, dtype=torch.float32, device=x.device)
+    dw = torch.empty(B, T, dtype=torch.float32, device=x.device)
+    g = grad_out.to(torch.float32).contiguous()
+    check(_lib.load().nrse_asp_pool_bwd(_ptr(x), _ptr(hl), _ptr(attention), _ptr(lens), _ptr(out), _ptr(weights),
+                                        _ptr(g), _ptr(gx), _ptr(gh), _ptr(ga), _ptr(dw), B, T, D, _stream()),
+          "nrse_asp_pool_bwd")
+    return gx, gh, ga
+
+
+@_asp_pool_bwd.register_fake
+def _(x, hl, attention, lens, out, weights, grad_out):
+    return torch.empty_like(x), torch.empty_like(hl), x.new_empty(x.shape[2], dtype=torch.float32)
+
+
+def _asp_setup(ctx, inputs, output):
+    x, hl, attention, lens = inputs
+    ctx.save_for_backward(x, hl, attention, lens, output[0], output[1])
+
+
+def _asp_backward(ctx, g_out, g_weights):
+    x, hl, attention, lens, out, weights = ctx.saved_tensors
+    gx, gh, ga = _asp_pool_bwd(x, hl, attention, lens, out, weights, g_out)
+    return gx, gh, ga, None
+
+
+_asp_pool_fwd.register_autograd(_asp_backward, setup_context=_asp_setup)
+
+
+def asp_pool(x: Tensor, hl: Tensor, attention: Tensor, lens: Tensor) -> Tensor:
+    """[B,2D] = (weighted mean | weighted std) over the first ``lens[b]`` frames of each utterance, the weights being
+    ``softmax_t(tanh(hl) @ attention)`` -- everything of ref:src/models/pool.py:46-57 after ``sap_linear``, for the whole
+    batch in two launches (two more backward).  ``x``, ``hl``: [B,T,D] fp32; ``attention``: [D] or [D,1]; ``lens``: [B]."""
+    if x.dim() != 3 or x.shape != hl.shape:
+        raise NrseError("asp_pool expects x and hl of equal shape [B,T,D]")
+    if x.shape[2] % 4 != 0 or x.shape[1] > 4096:
+        raise NrseError("asp_pool: D must be a multiple of 4 and T <= 4096")
+    att = attention.reshape(-1)
+    if att.numel() != x.shape[2]:
+        raise NrseError("asp_pool: attention vector length must equal the feature dimension")
+    lens = lens.to(device=x.device, dtype=torch.int32).clamp(min=0, max=x.shape[1]).contiguous()
+    return _asp_pool_fwd(x.float().contiguous(), hl.float().contiguous(), att.float().contiguous(), lens)[0]
+
+
+# --------------------------------------------------------------------------------------------------------------
 # conv feature encoder
 # --------------------------------------------------------------------------------------------------------------
 @functools.lru_cache(maxsize=256)
@@ -452,6 +521,10 @@ def set_mix_variant(variant: int) -> None:
 
 def set_mix_cluster(ctas_per_row: int) -> None:
     check(_lib.load().nrse_mix_set_cluster(int(ctas_per_row)), "nrse_mix_set_cluster")
+
+
+def set_mix_stagger(groups: int) -> None:
+    check(_lib.load().nrse_mix_set_stagger(int(groups)), "nrse_mix_set_stagger")
 
 
 def set_mix_carveout(percent: int) -> None:

@@ -8,3 +8,4 @@ from .byol import (  # noqa: F401
 )
 from .distributed import init_distributed, wrap_data_parallel  # noqa: F401
 from .optim import FusedAdamWEma  # noqa: F401
+from .emotion import ccc_loss, compute_ccc, emotion_dim_step, train_one_epoch_dimensional  # noqa: F401

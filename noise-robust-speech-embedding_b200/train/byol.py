@@ -51,9 +51,9 @@ def byol_step(model: BYOLSpeechModel, clean: torch.Tensor, noisy: torch.Tensor, 
     tail stages are its two kernel launches; with any other optimizer they run as in the reference."""
     online_pred, target_proj = model(clean, noisy)
     loss = byol_loss(online_pred, target_proj)
-    optimizer.zero_grad(set_to_none=True)
-    loss.backward()
     fused = isinstance(optimizer, FusedAdamWEma)
+    optimizer.zero_grad(set_to_none=not fused)  # the fused tail keeps address tables: gradients stay allocated
+    loss.backward()
     if not (fused and optimizer.max_grad_norm > 0):
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_grad_norm)
     optimizer.step()

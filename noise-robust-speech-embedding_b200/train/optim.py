@@ -9,6 +9,11 @@ with ``step`` / ``exp_avg`` / ``exp_avg_sq``, so ``state_dict()`` / ``load_state
 interchangeable with the reference's checkpoints, ref:train_byol.py:188-196) whose ``step()`` runs
 ``ops.OptimChunkTable``: one read of every gradient for the global norm, then one pass that clips, applies AdamW and
 averages the updated parameter into its EMA target twin.
+
+The kernels work from a device table of raw addresses, rebuilt (host planning + a blocking upload) whenever a parameter
+or gradient address changes.  ``zero_grad(set_to_none=True)`` frees the gradients every step, and the allocator does
+not always hand the same blocks back: call ``zero_grad(set_to_none=False)`` (``byol_step`` / ``emotion_dim_step`` do) or
+let DDP own the gradients (``gradient_as_bucket_view=True``) so that the table is built once; ``table_builds`` counts.
 """
 from __future__ import annotations
 
@@ -32,7 +37,10 @@ class FusedAdamWEma(torch.optim.AdamW):
         self.max_grad_norm = float(max_grad_norm)
         self.ema_decay = ema_decay
         self._twins: Dict[int, torch.Tensor] = {}
-        self._tables: Dict[Tuple[int, int], ops.OptimChunkTable] = {}
+        self._tables: Dict[int, ops.OptimChunkTable] = {}
+        self._buckets: List[dict] = []
+        self._gkey = None
+        self.table_builds = 0  # how often the address tables were (re)built; steady state: stays constant
         self._partials = None
         self._norm = None
         self.last_grad_norm: Optional[torch.Tensor] = None  # device tensor, what clip_grad_norm_ would have returned
@@ -51,6 +59,7 @@ class FusedAdamWEma(torch.optim.AdamW):
                 raise ValueError("FusedAdamWEma: EMA pair with different shapes")
             self._twins[id(online)] = target
         self.ema_decay = float(decay)
+        self._gkey = None
 
     @property
     def has_ema(self) -> bool:
@@ -65,61 +74,105 @@ class FusedAdamWEma(torch.optim.AdamW):
         return cls(model.parameters(), lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm,
                    ema_pairs=zip(online, [t.data for t in target]), ema_decay=inner.ema_decay, **kw)
 
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """Defaults to keeping the gradient tensors (zeroed in place) so that the address tables stay valid."""
+        super().zero_grad(set_to_none=set_to_none)
+
+    # ---- step counters -------------------------------------------------------------------------------------------
+    # torch keeps one CPU tensor ``state['step']`` per parameter and increments each of them every step (~500 host ops
+    # for WavLM-large).  Here the counts live as Python ints per bucket and are written into ``state['step']`` only when
+    # somebody looks: ``state_dict()`` / ``sync_state()``.
+    def sync_state(self) -> None:
+        """Write the current step counts into ``state[p]['step']`` (what torch.optim.AdamW would hold)."""
+        for bucket in self._buckets:
+            for p in bucket["params"]:
+                self.state[p]["step"] = torch.tensor(float(bucket["step"]), dtype=torch.float32)
+
+    def state_dict(self):
+        self.sync_state()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        self._buckets = []  # the loaded step counts win: nothing to flush
+        super().load_state_dict(state_dict)
+        self._gkey = None   # rebuild the buckets from the loaded step counts
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        self._gkey = None
+
+    def _rebuild(self, params, grads):
+        """Bucket the parameters by (group, step count): one table / kernel call per bucket."""
+        self.table_builds += 1
+        self.sync_state()
+        buckets = {}
+        orphans = []  # no gradient this step, but an EMA twin
+        group_of = {id(p): gi for gi, g in enumerate(self.param_groups) for p in g["params"]}
+        for p, g in zip(params, grads):
+            twin = self._twins.get(id(p))
+            if g is None:
+                if twin is not None:
+                    orphans.append((p.data, None, None, None, twin))
+                continue
+            state = self.state[p]
+            if len(state) == 0:  # torch.optim.Adam._init_group
+                state["step"] = torch.tensor(0.0, dtype=torch.float32)
+                state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            key = (group_of[id(p)], int(state["step"]))
+            b = buckets.setdefault(key, {"group": key[0], "step": key[1], "params": [], "rows": []})
+            b["params"].append(p)
+            b["rows"].append((p.data, g, state["exp_avg"], state["exp_avg_sq"], twin))
+        self._buckets = [buckets[k] for k in sorted(buckets)]
+        if orphans:  # ride along with the first bucket (or alone, with a dummy step count)
+            if not self._buckets:
+                self._buckets = [{"group": 0, "step": 0, "params": [], "rows": []}]
+            self._buckets[0]["rows"] = self._buckets[0]["rows"] + orphans
+        for slot, b in enumerate(self._buckets):
+            tab = self._tables.get(slot)
+            if tab is None:
+                tab = self._tables[slot] = ops.OptimChunkTable()
+            tab.update(*zip(*b["rows"]))
+            b["table"] = tab
+            del b["rows"]
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        # bucket the parameters by (group, step count): one kernel call per bucket, the norm partials side by side
-        buckets: Dict[Tuple[int, int], List[tuple]] = {}
-        orphans: List[tuple] = []  # no gradient this step, but an EMA twin
-        for gi, group in enumerate(self.param_groups):
+        for group in self.param_groups:
             if group.get("amsgrad") or group.get("maximize"):
                 raise RuntimeError("FusedAdamWEma: amsgrad / maximize are not supported")
-            for p in group["params"]:
-                twin = self._twins.get(id(p))
-                if p.grad is None:
-                    if twin is not None:
-                        orphans.append((p.data, None, None, None, twin))
-                    continue
-                state = self.state[p]
-                if len(state) == 0:  # torch.optim.Adam._init_group
-                    state["step"] = torch.tensor(0.0, dtype=torch.float32)
-                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                state["step"] += 1
-                buckets.setdefault((gi, int(state["step"])), []).append(
-                    (p.data, p.grad, state["exp_avg"], state["exp_avg_sq"], twin))
-        if not buckets and not orphans:
+        params = [p for g in self.param_groups for p in g["params"]]
+        grads = [p.grad for p in params]
+        # the chunk tables hold raw addresses: rebuild when any parameter / gradient address (or the set of parameters
+        # that have a gradient) changed.  Moments are owned by this optimizer and only change via load_state_dict.
+        gkey = tuple([p.data_ptr() for p in params] + [0 if g is None else g.data_ptr() for g in grads])
+        if gkey != self._gkey:
+            self._rebuild(params, grads)
+            self._gkey = gkey
+        if not self._buckets:
             return loss
-        keys = sorted(buckets)
-        if orphans:  # ride along with the first bucket (or alone, with a dummy step count)
-            if keys:
-                buckets[keys[0]] = buckets[keys[0]] + orphans
-            else:
-                keys = [(-1, 1)]
-                buckets[keys[0]] = orphans
-        dev = buckets[keys[0]][0][0].device
+        dev = params[0].device
         clip = self.max_grad_norm > 0
         count = ops.OptimChunkTable.partials_count()
-        if clip and (self._partials is None or self._partials.numel() != count * len(keys) or self._partials.device != dev):
-            self._partials = torch.zeros(count * len(keys), dtype=torch.float64, device=dev)
+        n_b = len(self._buckets)
+        if clip and (self._partials is None or self._partials.numel() != count * n_b or self._partials.device != dev):
+            self._partials = torch.zeros(count * n_b, dtype=torch.float64, device=dev)
             self._norm = torch.zeros(1, dtype=torch.float32, device=dev)
-        tables = []
-        for slot, key in enumerate(keys):
-            tab = self._tables.get((key[0], slot))
-            if tab is None:
-                tab = self._tables[(key[0], slot)] = ops.OptimChunkTable()
-            tab.update(*zip(*buckets[key]))
-            tables.append(tab)
-            if clip:
-                tab.grad_sqnorm(self._partials[slot * count:(slot + 1) * count])
-        for key, tab in zip(keys, tables):
-            group = self.param_groups[max(key[0], 0)]
-            tab.clip_adamw_ema(lr=group["lr"], betas=group["betas"], eps=group["eps"],
-                               weight_decay=group["weight_decay"], step=key[1], max_grad_norm=self.max_grad_norm,
-                               ema_decay=self.ema_decay if self.ema_decay is not None else 0.0,
-                               partials=self._partials if clip else None, norm_out=self._norm if clip else None)
+        if clip:
+            for slot, b in enumerate(self._buckets):
+                b["table"].grad_sqnorm(self._partials[slot * count:(slot + 1) * count])
+        for b in self._buckets:
+            if b["params"]:
+                b["step"] += 1
+            group = self.param_groups[b["group"]]
+            b["table"].clip_adamw_ema(lr=group["lr"], betas=group["betas"], eps=group["eps"],
+                                      weight_decay=group["weight_decay"], step=max(b["step"], 1),
+                                      max_grad_norm=self.max_grad_norm,
+                                      ema_decay=self.ema_decay if self.ema_decay is not None else 0.0,
+                                      partials=self._partials if clip else None, norm_out=self._norm if clip else None)
         self.last_grad_norm = self._norm[0] if clip else None
         return loss

@@ -6,7 +6,8 @@ WavLM-large-shaped model (random init: no checkpoints offline), data-parallel wi
     torchrun --nproc-per-node N scripts/train_step_bench.py ...
 
 The hot-path kernels of this repository run inside it (GPU mix, conv frontend forward on both branches, fused loss,
-one-launch EMA); the 24-layer transformer, the heads, AdamW and the frontend backward are stock PyTorch.  Prints one
+fused clip + AdamW + EMA optimizer tail, native frontend backward); the 24-layer transformer and the heads are stock
+PyTorch.  Prints one
 JSON line per run with the step time, utterance-seconds/s, and the device time of the hot-path pieces.
 """
 import argparse
@@ -23,7 +24,7 @@ import torch.distributed as dist  # noqa: E402
 
 from nrse_b200.data import GpuBatchMixer  # noqa: E402
 from nrse_b200.models import BYOLSpeechModel, wavlm_large_config  # noqa: E402
-from nrse_b200.train import byol_step, init_distributed, wrap_data_parallel  # noqa: E402
+from nrse_b200.train import FusedAdamWEma, byol_step, init_distributed, wrap_data_parallel  # noqa: E402
 from nrse_b200.utils import synthetic  # noqa: E402
 
 
@@ -35,6 +36,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--layers", type=int, default=24, help="transformer layers (24 = wavlm-large)")
     ap.add_argument("--autocast", action="store_true", help="bf16 autocast for the stock transformer / heads")
+    ap.add_argument("--optimizer", choices=["fused", "torch"], default="fused",
+                    help="fused: FusedAdamWEma (clip + AdamW + EMA in two launches); torch: the reference's sequence")
     args = ap.parse_args()
 
     rank, world, local_rank = init_distributed()
@@ -48,7 +51,10 @@ def main():
     model = BYOLSpeechModel(cfg).to(dev)
     n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
     ddp = wrap_data_parallel(model, dev)
-    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-5, weight_decay=1e-5)
+    if args.optimizer == "fused":
+        opt = FusedAdamWEma.for_byol(model, lr=1e-5, weight_decay=1e-5, max_grad_norm=1.0)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-5, weight_decay=1e-5)  # ref:train_byol.py:146
     sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=1000)
     clean, noise, snr_idx, table = synthetic.waveforms(args.batch, L, seed=1234 + rank)
     raw = {"clean_wave": torch.from_numpy(clean)[:, None].pin_memory(), "noise_wave": torch.from_numpy(noise)[:, None].pin_memory(),
@@ -99,7 +105,8 @@ def main():
         print(json.dumps({
             "workload": "configs[2]: BYOL training step, WavLM-large shapes (random init), data-parallel",
             "n_gpus": world, "batch_per_gpu": args.batch, "seconds": args.seconds, "layers": args.layers,
-            "autocast_bf16": args.autocast, "trainable_params": n_params, "loss": float(loss),
+            "autocast_bf16": args.autocast, "optimizer": args.optimizer, "trainable_params": n_params,
+            "loss": float(loss), "optimizer_table_builds": getattr(opt, "table_builds", None),
             "ms_per_step": ms, "utterance_seconds_per_s": world * args.batch * args.seconds / (ms * 1e-3),
             "hot_path_ms": {"h2d+mix": t_mix, "conv_frontend_fwd_one_view": t_fe, "ema_update": t_ema},
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))

@@ -14,7 +14,8 @@ copied.  Shims, all explicit below:
   3. ``load_and_process_audio`` -> in-memory tensors (torchaudio cannot decode in this image).
 Outputs (float arrays kept small; inputs are stored too so fixtures are self-contained):
   mix_byol.npz, mix_emotion.npz, mix_edge.npz, byol_loss.npz, ema.npz, frontend_layer.npz,
-  frontend_group.npz, byol_step.npz, byol_state_dict_keys.json, optim_step.npz
+  frontend_group.npz, byol_step.npz, byol_state_dict_keys.json, optim_step.npz,
+  emotion.npz, emotion_state_dict_keys.json
 """
 import os
 import random
@@ -353,6 +354,74 @@ def gen_optim_step(seed=61, steps=3):
     print("optim_step: tensors", len(named), "elems", sum(p.numel() for _, p in named), "norms", norms)
 
 
+def gen_emotion(seed=71, B=5, T=37, D=64):
+    """The reference's ``AttentiveStatisticsPooling`` (outputs + autograd gradients, ragged masks incl. one longer than
+    T frames), ``ccc_loss`` (value + gradient) and the ``EmotionClassifier`` state-dict keys / a forward on the tiny
+    shimmed encoder.  ``src.train.dimentional_emotions`` imports wandb / matplotlib at module level: stubbed."""
+    import json
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn", "wandb"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    if not hasattr(sys.modules["matplotlib"], "pyplot"):
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    from src.models.pool import AttentiveStatisticsPooling as RefASP
+    from src.models.emotion import EmotionClassifier as RefEmotion
+    from src.train.dimentional_emotions import ccc_loss as ref_ccc_loss
+    torch.manual_seed(seed)
+    rs = np.random.RandomState(seed)
+    pool = RefASP(D)
+    xs = torch.from_numpy(rs.standard_normal((B, T, D)).astype(np.float32)).requires_grad_(True)
+    wav_lens = [T * 320 + 400, 12 * 320 + 1, 1, 20 * 320, 30 * 320 + 77]   # frames: >T (clipped), 13, 1, 20, 31
+    L = max(wav_lens)
+    mask = torch.zeros(B, L)
+    for b, n in enumerate(wav_lens):
+        mask[b, :n] = 1
+    out = pool(xs, mask)
+    gout = torch.from_numpy(rs.standard_normal(tuple(out.shape)).astype(np.float32))
+    out.backward(gout)
+    res = {"xs": xs.detach().numpy(), "mask_lens": np.array(wav_lens), "sap_w": pool.sap_linear.weight.detach().numpy(),
+           "sap_b": pool.sap_linear.bias.detach().numpy(), "attention": pool.attention.detach().numpy(),
+           "out": out.detach().numpy(), "gout": gout.numpy(), "dxs": xs.grad.numpy(),
+           "d_sap_w": pool.sap_linear.weight.grad.numpy(), "d_sap_b": pool.sap_linear.bias.grad.numpy(),
+           "d_attention": pool.attention.grad.numpy(),
+           "feat_lens": np.array(pool.compute_length_from_mask(mask))}
+    # a low-variance channel exercises the clamp(min=1e-5) branch
+    xs2 = xs.detach().clone()
+    xs2[:, :, 3] = 0.25
+    xs2[:, :, 7] = 1e-3 * xs2[:, :, 7]
+    xs2.requires_grad_(True)
+    pool.zero_grad()
+    out2 = pool(xs2, mask)
+    out2.backward(gout)
+    res.update({"out_clamped": out2.detach().numpy(), "dxs_clamped": xs2.grad.numpy()})
+    pred = torch.from_numpy(rs.standard_normal((16, 3)).astype(np.float32)).requires_grad_(True)
+    targ = torch.from_numpy((4 + 1.5 * rs.standard_normal((16, 3))).astype(np.float32))
+    loss = ref_ccc_loss(pred, targ)
+    loss.backward()
+    res.update({"ccc_pred": pred.detach().numpy(), "ccc_targ": targ.numpy(), "ccc_loss": loss.detach().numpy(),
+                "ccc_grad": pred.grad.numpy()})
+    np.savez_compressed(os.path.join(HERE, "emotion.npz"), **res)
+    # state-dict contract of the classifier (tiny shimmed encoder)
+    cfg = small_wavlm_config("layer")
+    orig = ref_encoder_mod.AutoModel.from_pretrained
+    ref_encoder_mod.AutoModel.from_pretrained = staticmethod(lambda name: WavLMModel(cfg))
+    try:
+        enc = ref_encoder_mod.WavLMEncoder("shim")
+    finally:
+        ref_encoder_mod.AutoModel.from_pretrained = orig
+    model = RefEmotion(enc, hidden_dim=48, dropout=0.3, num_emotions=8)
+    keys = {k: list(v.shape) for k, v in model.state_dict().items() if not k.startswith("encoder.")}
+    model.unfreeze_encoder_gradually([0, 1])
+    trainable = sorted(n for n, p in model.encoder.model.named_parameters() if p.requires_grad)
+    with open(os.path.join(HERE, "emotion_state_dict_keys.json"), "w") as f:
+        json.dump({"head_keys": keys, "unfreeze_0_1": trainable}, f, indent=0, sort_keys=True)
+    print("emotion: out", out.shape, "ccc_loss", float(loss), "head keys", len(keys), "unfrozen", len(trainable))
+
+
 if __name__ == "__main__":
     print("transformers", transformers.__version__, "torch", torch.__version__, "numpy", np.__version__)
     gen_mix_byol()
@@ -364,4 +433,5 @@ if __name__ == "__main__":
     gen_frontend("group")
     gen_byol_step()
     gen_optim_step()
+    gen_emotion()
     print("sizes:", {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")})

@@ -214,3 +214,26 @@ def test_two_rank_gloo_data_parallel_equivalence():
     out = mgr.dict()
     mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_emotion_classifier_contract_matches_reference():
+    """Head state-dict keys / shapes and the gradual-unfreeze substring match equal the reference's
+    (tests/golden/emotion_state_dict_keys.json, written from ref:src/models/emotion.py on the shimmed encoder)."""
+    from nrse_b200.models import EmotionClassifier
+    with open(os.path.join(GOLDEN, "emotion_state_dict_keys.json")) as f:
+        want = json.load(f)
+    enc = WavLMEncoder(golden_config())
+    model = EmotionClassifier(enc, hidden_dim=48, dropout=0.3, num_emotions=8)
+    got = {k: list(v.shape) for k, v in model.state_dict().items() if not k.startswith("encoder.")}
+    assert got == want["head_keys"]
+    model.unfreeze_encoder_gradually([0, 1])
+    trainable = sorted(n for n, p in model.encoder.model.named_parameters() if p.requires_grad)
+    assert trainable == want["unfreeze_0_1"]
+    model.freeze_encoder()
+    assert all(not p.requires_grad for p in model.encoder.parameters())
+    n_head = model.get_trainable_params()
+    model.unfreeze_encoder()
+    assert model.get_trainable_params() > n_head
+    # compute_length_from_mask: same numbers as the reference's list, but a device tensor
+    lens = model.pooling.compute_length_from_mask(torch.tensor([[1.0] * 640, [1.0] * 321 + [0.0] * 319]))
+    assert lens.tolist() == [2, 2] and lens.dtype == torch.int32

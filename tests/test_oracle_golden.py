@@ -160,3 +160,46 @@ def test_optim_step_matches_torch_adamw_and_reference_ema(golden):
             assert np.array_equal(targets[i].numpy(), g[f"t_{i}"]), names[i]
         if has_grad[i]:
             assert np.array_equal(m[i].numpy(), g[f"m_{i}"]) and np.array_equal(v[i].numpy(), g[f"v_{i}"]), names[i]
+
+
+def _emotion_mask(g):
+    lens = [int(v) for v in g["mask_lens"]]
+    mask = torch.zeros(len(lens), max(lens))
+    for b, n in enumerate(lens):
+        mask[b, :n] = 1
+    return mask
+
+
+def test_attentive_pooling_and_ccc_match_reference(golden):
+    g = golden("emotion")
+    mask = _emotion_mask(g)
+    assert oracle.compute_length_from_mask(mask) == [int(v) for v in g["feat_lens"]]
+    for xs_key, out_key, dx_key in (("xs", "out", "dxs"), (None, "out_clamped", "dxs_clamped")):
+        xs = torch.from_numpy(g["xs"].copy())
+        if xs_key is None:
+            xs[:, :, 3] = 0.25
+            xs[:, :, 7] = 1e-3 * xs[:, :, 7]
+        xs.requires_grad_(True)
+        w = torch.from_numpy(g["sap_w"]).requires_grad_(True)
+        b = torch.from_numpy(g["sap_b"]).requires_grad_(True)
+        a = torch.from_numpy(g["attention"]).requires_grad_(True)
+        out = oracle.attentive_statistics_pooling(xs, mask, w, b, a)
+        out.backward(torch.from_numpy(g["gout"]))
+        assert np.array_equal(out.detach().numpy(), g[out_key])
+        assert np.array_equal(xs.grad.numpy(), g[dx_key])
+        if xs_key is not None:
+            assert np.array_equal(w.grad.numpy(), g["d_sap_w"]) and np.array_equal(a.grad.numpy(), g["d_attention"])
+    pred = torch.from_numpy(g["ccc_pred"]).requires_grad_(True)
+    loss = oracle.ccc_loss(pred, torch.from_numpy(g["ccc_targ"]))
+    loss.backward()
+    assert np.array_equal(loss.detach().numpy(), g["ccc_loss"]) and np.array_equal(pred.grad.numpy(), g["ccc_grad"])
+    # the product's vectorised ccc_loss is plain torch: check it here on the CPU as well
+    from nrse_b200.train import ccc_loss, compute_ccc
+    pred2 = torch.from_numpy(g["ccc_pred"]).requires_grad_(True)
+    loss2 = ccc_loss(pred2, torch.from_numpy(g["ccc_targ"]))
+    loss2.backward()
+    assert rel_err(loss2.detach().numpy(), g["ccc_loss"]) < 1e-6 and rel_err(pred2.grad.numpy(), g["ccc_grad"]) < 1e-5
+    assert float(ccc_loss(pred2[:1], torch.from_numpy(g["ccc_targ"][:1]))) == 0.0
+    c = compute_ccc(g["ccc_pred"][:, 0], g["ccc_targ"][:, 0])
+    assert abs((1 - c) - float(oracle.ccc_loss(torch.from_numpy(g["ccc_pred"][:, :1]),
+                                               torch.from_numpy(g["ccc_targ"][:, :1])))) < 1e-6
