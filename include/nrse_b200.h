@@ -89,9 +89,6 @@ int nrse_mix_set_variant(int variant);
 int nrse_mix_set_cluster(int ctas_per_row);
 /* tuning: shared-memory carveout (percent of 228 KB) of the resident kernels; -1 = just what the CTAs need (default) */
 int nrse_mix_set_carveout(int percent);
-/* tuning: start groups of a single-wave resident launch (rows start staggered so that one group's reduction bubbles
- * overlap the next group's loads); -1 = automatic (default), 0 = off */
-int nrse_mix_set_stagger(int groups);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-tensor EMA:  target = decay*target + one_minus_decay*online   (fp32, in place,

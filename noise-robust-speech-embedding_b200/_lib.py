@@ -58,7 +58,6 @@ SIGNATURES = {
     "nrse_mix_set_variant": (_i, [_i]),
     "nrse_mix_set_cluster": (_i, [_i]),
     "nrse_mix_set_carveout": (_i, [_i]),
-    "nrse_mix_set_stagger": (_i, [_i]),
     "nrse_ema_plan_chunks_host": (_i64, [_p, _p, _p, _i, _i64, _p, _p, _p, _i64]),
     "nrse_ema_chunks_f32": (_i, [_p, _p, _p, _i64, _f, _f, _p]),
     "nrse_optim_plan_chunks_host": (_i64, [_p, _p, _p, _p, _p, _p, _i, _i64, _p, _p, _i64]),

@@ -991,8 +991,7 @@ struct ResCfg {
 
 template <int kResThreads>
 __global__ void __launch_bounds__(kResThreads, 1024 / kResThreads)
-mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch, int stagger_groups,
-                              int stagger_cycles) {
+mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
   constexpr int kResWarps = ResCfg<kResThreads>::kWarps;
   constexpr int kResRegCap = ResCfg<kResThreads>::kRegCap;
   cg::cluster_group cluster = cg::this_cluster();
@@ -1022,19 +1021,6 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch, in
   float4* s_n = s_c + smem_pitch;
   const float4* g_c = reinterpret_cast<const float4*>(p.clean + static_cast<size_t>(row) * L) + v_begin;
   const float4* g_n = reinterpret_cast<const float4*>(p.noise + static_cast<size_t>(row) * p.Ln) + v_begin;
-
-  // Single-wave launches (every CTA resident at once, e.g. 64 rows x 4 s) run in lock-step: everybody loads, then
-  // everybody sits in the reduction / exchange bubbles with HBM idle, then everybody stores.  Starting the rows in
-  // `stagger_groups` groups, `stagger_cycles` apart (the time HBM needs for one group's loads), lets one group's bubbles
-  // overlap the next group's loads.  Purely a scheduling hint: results do not depend on it.
-  if (stagger_groups > 1) {
-    const long long wait = static_cast<long long>(row % stagger_groups) * stagger_cycles;
-    if (tid == 0 && wait > 0) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < wait) {}
-    }
-    __syncthreads();
-  }
 
   // The cluster exchanges are st.async messages that complete_tx on the RECEIVER's mbarrier: no cluster barrier and no
   // gpu-scope fence on the critical path (cg::cluster.sync() costs MEMBAR.GPU + ERRBAR twice per row).  Each CTA
@@ -1325,7 +1311,6 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch, in
   for (int v = tid; v < n_sm; v += kResThreads) emit(n_reg + v, s_c[v], s_n[v]);
 }
 
-int g_mix_stagger = -1;   // start groups of a single-wave resident launch: -1 automatic (4), 0 off, n > 0 forced
 int g_mix_carveout = -1;  // shared-memory carveout (percent) of the resident kernels; -1: just what the CTAs need
 int g_mix_stream_cluster = 0;  // 0: automatic; 1/2/4/8 force the CTAs-per-row of the streaming variant (tuning)
 int g_mix_variant = 4;  // 4: on-chip resident (registers + shared memory), default when the row fits 8 CTAs
@@ -1347,12 +1332,6 @@ extern "C" {
 int nrse_mix_set_cluster(int ctas_per_row) {
   if (ctas_per_row < 0 || ctas_per_row > nrse::kSmemMaxCluster) return NRSE_ERR_INVALID_ARG;
   nrse::g_mix_stream_cluster = ctas_per_row;
-  return NRSE_OK;
-}
-
-int nrse_mix_set_stagger(int groups) {
-  if (groups < -1 || groups > 64) return NRSE_ERR_INVALID_ARG;
-  nrse::g_mix_stagger = groups;
   return NRSE_OK;
 }
 
@@ -1461,21 +1440,10 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
       cfg.blockDim = dim3(threads);
       cfg.dynamicSmemBytes = dyn;
       attr[0].val.clusterDim.x = cs;
-      // stagger only when the whole grid is resident at once (one wave); later waves desynchronise by themselves
-      const long long slots = static_cast<long long>(kNumSMs) * (threads == 512 ? 2 : 1);
-      int groups = 0, cycles = 0;
-      if (g_mix_stagger != 0 && static_cast<long long>(B) * cs <= slots && B >= 8) {
-        groups = g_mix_stagger > 0 ? g_mix_stagger : 4;
-        // time for HBM to deliver one group's inputs: 8 B per sample at ~6.5 TB/s, in SM cycles at ~1.9 GHz
-        const double ns = 8.0 * B * L / groups / 6500.0;
-        cycles = static_cast<int>(ns * 1.9);
-      }
       if (threads == 512)
-        NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_resident_kernel<512>, p, seg_vec, smem_pitch, groups,
-                                         cycles));
+        NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_resident_kernel<512>, p, seg_vec, smem_pitch));
       else
-        NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_resident_kernel<1024>, p, seg_vec, smem_pitch, groups,
-                                         cycles));
+        NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_resident_kernel<1024>, p, seg_vec, smem_pitch));
       return NRSE_OK;
     }
   }

@@ -183,9 +183,10 @@ def ema_update_(online: Sequence[Tensor], target: Sequence[Tensor], decay: float
 # --------------------------------------------------------------------------------------------------------------
 class OptimChunkTable:
     """Device chunk table over (param, grad, exp_avg, exp_avg_sq, EMA target twin) for ONE optimizer step count,
-    plus the two launches that consume it.  ``update`` rebuilds the table only when an address changed
-    (``zero_grad(set_to_none=True)`` re-allocates the gradients, but the caching allocator hands the same blocks
-    back, so in steady state the table is built once)."""
+    plus the two launches that consume it.  ``update`` rebuilds the table only when an address changed.  A rebuild is
+    host planning in C plus ONE non-blocking upload from a pinned staging buffer on the current stream (two staging
+    buffers, each guarded by an event), so even a step loop that frees its gradients every iteration
+    (``zero_grad(set_to_none=True)``) never synchronises the host with the device."""
 
     CHUNK_ELEMS = 16384
 
@@ -195,6 +196,9 @@ class OptimChunkTable:
         self.numel = 0          # elements that take an AdamW update
         self.ema_numel = 0      # elements that take an EMA update
         self._ptrs = self._numel = None
+        self._stage = [None, None]   # (pinned int64 tensor, event)
+        self._flip = 0
+        self._dev_buf = None
 
     @staticmethod
     def partials_count() -> int:
@@ -226,21 +230,37 @@ class OptimChunkTable:
         self.n_chunks = 0
         if n == 0:
             return
-        arr = lambda k: (C.c_uint64 * n)(*[e[k] for e in entries])
-        P, G, M, V, T = (arr(k) for k in range(5))
-        NE = (C.c_int64 * n)(*[e[5] for e in entries])
-        cnt = int(lib.nrse_optim_plan_chunks_host(P, G, M, V, T, NE, n, self.CHUNK_ELEMS, None, None, 0))
+        host = torch.tensor(entries, dtype=torch.int64).t().contiguous()  # [6, n]: p | g | m | v | t | numel
+        hp = host.data_ptr()
+        row = lambda k: C.c_void_p(hp + 8 * n * k)
+        cnt = int(lib.nrse_optim_plan_chunks_host(row(0), row(1), row(2), row(3), row(4), row(5), n, self.CHUNK_ELEMS,
+                                                  None, None, 0))
         if cnt < 0:
             check(cnt, "nrse_optim_plan_chunks_host")
         if cnt == 0:
             return
-        ptrs = (C.c_uint64 * (5 * cnt))()
-        cn = (C.c_int32 * cnt)()
-        got = lib.nrse_optim_plan_chunks_host(P, G, M, V, T, NE, n, self.CHUNK_ELEMS, ptrs, cn, cnt)
+        # staging layout (int64 words): 5 * cnt chunk addresses, then cnt int32 lengths packed in (cnt + 1) // 2 words
+        words = 5 * cnt + (cnt + 1) // 2
+        slot = self._flip
+        self._flip ^= 1
+        stage = self._stage[slot]
+        if stage is None or stage[0].numel() < words:
+            stage = (torch.empty(max(words, 1024), dtype=torch.int64).pin_memory(), torch.cuda.Event())
+            self._stage[slot] = stage
+        else:
+            stage[1].synchronize()  # the upload that last read this staging buffer (two rebuilds ago) has finished
+        buf, ev = stage
+        sp = buf.data_ptr()
+        got = lib.nrse_optim_plan_chunks_host(row(0), row(1), row(2), row(3), row(4), row(5), n, self.CHUNK_ELEMS,
+                                              C.c_void_p(sp), C.c_void_p(sp + 8 * 5 * cnt), cnt)
         if got != cnt:
             raise NrseError("nrse_optim_plan_chunks_host: inconsistent chunk count")
-        self._ptrs = torch.frombuffer(bytearray(bytes(ptrs)), dtype=torch.int64).to(dev)  # p | g | m | v | t
-        self._numel = torch.frombuffer(bytearray(bytes(cn)), dtype=torch.int32).to(dev)
+        if self._dev_buf is None or self._dev_buf.numel() < words or self._dev_buf.device != dev:
+            self._dev_buf = torch.empty(max(words, 1024), dtype=torch.int64, device=dev)
+        self._dev_buf[:words].copy_(buf[:words], non_blocking=True)  # stream-ordered before the kernels that read it
+        ev.record()
+        self._ptrs = self._dev_buf[:5 * cnt]
+        self._numel = self._dev_buf[5 * cnt:words].view(torch.int32)[:cnt]
         self.n_chunks = cnt
 
     def grad_sqnorm(self, partials: Tensor) -> None:
@@ -521,10 +541,6 @@ def set_mix_variant(variant: int) -> None:
 
 def set_mix_cluster(ctas_per_row: int) -> None:
     check(_lib.load().nrse_mix_set_cluster(int(ctas_per_row)), "nrse_mix_set_cluster")
-
-
-def set_mix_stagger(groups: int) -> None:
-    check(_lib.load().nrse_mix_set_stagger(int(groups)), "nrse_mix_set_stagger")
 
 
 def set_mix_carveout(percent: int) -> None:

@@ -52,7 +52,7 @@ def byol_step(model: BYOLSpeechModel, clean: torch.Tensor, noisy: torch.Tensor, 
     online_pred, target_proj = model(clean, noisy)
     loss = byol_loss(online_pred, target_proj)
     fused = isinstance(optimizer, FusedAdamWEma)
-    optimizer.zero_grad(set_to_none=not fused)  # the fused tail keeps address tables: gradients stay allocated
+    optimizer.zero_grad() if fused else optimizer.zero_grad(set_to_none=True)
     loss.backward()
     if not (fused and optimizer.max_grad_norm > 0):
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_grad_norm)

@@ -45,7 +45,7 @@ def emotion_dim_step(model, inputs: torch.Tensor, labels: torch.Tensor, optimize
         attention_mask = torch.ones(inputs.size(0), inputs.size(-1), device=inputs.device)
     _, values = model(inputs, attention_mask=attention_mask, task="dimensional")
     loss = ccc_loss(values, labels)
-    optimizer.zero_grad(set_to_none=not isinstance(optimizer, FusedAdamWEma))
+    optimizer.zero_grad() if isinstance(optimizer, FusedAdamWEma) else optimizer.zero_grad(set_to_none=True)
     loss.backward()
     if not (isinstance(optimizer, FusedAdamWEma) and optimizer.max_grad_norm > 0):
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_grad_norm)

@@ -10,10 +10,12 @@ interchangeable with the reference's checkpoints, ref:train_byol.py:188-196) who
 ``ops.OptimChunkTable``: one read of every gradient for the global norm, then one pass that clips, applies AdamW and
 averages the updated parameter into its EMA target twin.
 
-The kernels work from a device table of raw addresses, rebuilt (host planning + a blocking upload) whenever a parameter
-or gradient address changes.  ``zero_grad(set_to_none=True)`` frees the gradients every step, and the allocator does
-not always hand the same blocks back: call ``zero_grad(set_to_none=False)`` (``byol_step`` / ``emotion_dim_step`` do) or
-let DDP own the gradients (``gradient_as_bucket_view=True``) so that the table is built once; ``table_builds`` counts.
+The kernels work from a device table of raw addresses, rebuilt whenever a parameter or gradient address changes
+(``table_builds`` counts).  ``zero_grad(set_to_none=True)`` frees the gradients every step and the allocator does not
+always hand the same blocks back, so a rebuild is made cheap instead of rare: host planning in C and one non-blocking
+upload from pinned memory on the current stream -- no host/device synchronisation.  ``keep_grads=True`` makes
+``zero_grad()`` zero in place instead (stable addresses, but autograd then accumulates into the zeros: one extra
+read-modify-write per parameter in the backward).
 """
 from __future__ import annotations
 
@@ -40,6 +42,7 @@ class FusedAdamWEma(torch.optim.AdamW):
         self._tables: Dict[int, ops.OptimChunkTable] = {}
         self._buckets: List[dict] = []
         self._gkey = None
+        self.keep_grads = False  # True: zero_grad() zeroes in place, addresses (and tables) never change
         self.table_builds = 0  # how often the address tables were (re)built; steady state: stays constant
         self._partials = None
         self._norm = None
@@ -74,9 +77,9 @@ class FusedAdamWEma(torch.optim.AdamW):
         return cls(model.parameters(), lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm,
                    ema_pairs=zip(online, [t.data for t in target]), ema_decay=inner.ema_decay, **kw)
 
-    def zero_grad(self, set_to_none: bool = False) -> None:
-        """Defaults to keeping the gradient tensors (zeroed in place) so that the address tables stay valid."""
-        super().zero_grad(set_to_none=set_to_none)
+    def zero_grad(self, set_to_none: Optional[bool] = None) -> None:
+        """``set_to_none`` defaults to ``not self.keep_grads`` (torch's default, True, unless ``keep_grads`` is set)."""
+        super().zero_grad(set_to_none=(not self.keep_grads) if set_to_none is None else set_to_none)
 
     # ---- step counters -------------------------------------------------------------------------------------------
     # torch keeps one CPU tensor ``state['step']`` per parameter and increments each of them every step (~500 host ops

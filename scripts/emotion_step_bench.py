@@ -51,6 +51,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--autocast", action="store_true")
+    ap.add_argument("--layerdrop", type=float, default=0.1)
+    ap.add_argument("--keep-grads", action="store_true", help="fused optimizer: zero gradients in place (stable addresses)")
     ap.add_argument("--optimizer", choices=["fused", "torch"], default="fused")
     ap.add_argument("--stock-pool", action="store_true")
     args = ap.parse_args()
@@ -60,7 +62,7 @@ def main():
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
     L = int(args.seconds * 16000)
-    enc = WavLMEncoder(wavlm_large_config(num_hidden_layers=args.layers))
+    enc = WavLMEncoder(wavlm_large_config(num_hidden_layers=args.layers, layerdrop=args.layerdrop))
     model = EmotionClassifier(enc, hidden_dim=1024, dropout=0.3, num_emotions=8).to(dev)
     model.unfreeze_encoder_gradually(list(range(args.layers)))  # last fine-tuning epoch: every layer index
     if args.stock_pool:
@@ -71,6 +73,8 @@ def main():
         opt = FusedAdamWEma(model.parameters(), lr=5e-6, weight_decay=1e-4, max_grad_norm=1.0)
     else:
         opt = torch.optim.AdamW(model.parameters(), lr=5e-6, weight_decay=1e-4)
+    if args.optimizer == "fused":
+        opt.keep_grads = args.keep_grads
     clean, noise, snr_idx, table = synthetic.waveforms(args.batch, L, seed=1234 + rank)
     raw = {"clean_wave": torch.from_numpy(clean)[:, None].pin_memory(), "noise_wave": torch.from_numpy(noise)[:, None].pin_memory(),
            "snr_idx": torch.from_numpy(snr_idx), "snr": torch.tensor([table[i] for i in snr_idx])}
@@ -124,9 +128,9 @@ def main():
         print(json.dumps({
             "workload": "configs[3]: emotion-dimension fine-tune step, WavLM-large shapes (random init), data-parallel",
             "n_gpus": world, "batch_per_gpu": args.batch, "seconds": args.seconds, "layers": args.layers,
-            "autocast_bf16": args.autocast, "optimizer": args.optimizer, "stock_pool": args.stock_pool,
+            "autocast_bf16": args.autocast, "layerdrop": args.layerdrop, "optimizer": args.optimizer, "stock_pool": args.stock_pool,
             "trainable_params": n_params, "loss": float(loss), "ms_per_step": ms,
-            "optimizer_table_builds": getattr(opt, "table_builds", None),
+            "optimizer_table_builds": getattr(opt, "table_builds", None), "keep_grads": args.keep_grads,
             "utterance_seconds_per_s": world * args.batch * args.seconds / (ms * 1e-3),
             "hot_path_ms": {"attentive_pooling_fwd_bwd": t_pool},
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))

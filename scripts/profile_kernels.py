@@ -1,5 +1,6 @@
 """Small driver for ncu: every hot-path kernel at the BASELINE shape (64 x 4 s): mix (also at B=512), conv frontend
-forward, then one training forward + native backward."""
+forward, one training forward + native backward, the fused optimizer tail (clip + AdamW + EMA, 80 M parameters) and
+the batched attentive statistics pooling forward / backward (36 x 249 x 1024)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -26,5 +27,19 @@ for it in range(2):
     y = ops.conv_frontend(c, w, g, b, "layer", out_dtype=torch.bfloat16, packed=packed)
     yt, tape = ops.conv_frontend_train(c, w, g, b, packed=packed)
     grads = ops.conv_frontend_backward(c, w, g, b, tape, gy, dgrad_packs=dpacks)
+from nrse_b200.train import FusedAdamWEma
+from nrse_b200.models import AttentiveStatisticsPooling
+prm = [torch.nn.Parameter(torch.randn(n, device=dev) * 0.02) for n in [1 << 22] * 19 + [1000, 12, 4097]]
+twin = [torch.randn_like(p) for p in prm[:-1]]
+for p in prm:
+    p.grad = torch.randn_like(p) * 1e-3
+opt = FusedAdamWEma(prm, lr=1e-5, weight_decay=1e-5, max_grad_norm=1.0, ema_pairs=zip(prm[:-1], twin), ema_decay=0.996)
+pool = AttentiveStatisticsPooling(1024).to(dev)
+hx = torch.randn(36, 249, 1024, device=dev, requires_grad=True)
+mask = torch.ones(36, 80000, device=dev)
+mask[1::2, 50000:] = 0
+for it in range(2):
+    opt.step()
+    pool(hx, mask).sum().backward()
 torch.cuda.synchronize()
-print("ok", float(y.float().abs().mean()), float(grads[0][3].abs().mean()))
+print("ok", float(y.float().abs().mean()), float(grads[0][3].abs().mean()), float(opt.last_grad_norm))

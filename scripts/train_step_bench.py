@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--layers", type=int, default=24, help="transformer layers (24 = wavlm-large)")
     ap.add_argument("--autocast", action="store_true", help="bf16 autocast for the stock transformer / heads")
+    ap.add_argument("--layerdrop", type=float, default=0.1, help="WavLM LayerDrop (0.1 = wavlm-large; 0 for a "
+                    "deterministic amount of work per step when A/B-ing)")
+    ap.add_argument("--keep-grads", action="store_true", help="fused optimizer: zero gradients in place (stable addresses)")
     ap.add_argument("--optimizer", choices=["fused", "torch"], default="fused",
                     help="fused: FusedAdamWEma (clip + AdamW + EMA in two launches); torch: the reference's sequence")
     args = ap.parse_args()
@@ -45,7 +48,7 @@ def main():
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
     L = int(args.seconds * 16000)
-    cfg = {"model": {"name": wavlm_large_config(num_hidden_layers=args.layers), "projection_dim": 1024,
+    cfg = {"model": {"name": wavlm_large_config(num_hidden_layers=args.layers, layerdrop=args.layerdrop), "projection_dim": 1024,
                      "prediction_dim": 2048, "ema_decay": 0.997},
            "data": {"snr_range": [2, 5, 10, 15, 20]}}
     model = BYOLSpeechModel(cfg).to(dev)
@@ -56,6 +59,8 @@ def main():
     else:
         opt = torch.optim.AdamW(model.parameters(), lr=1e-5, weight_decay=1e-5)  # ref:train_byol.py:146
     sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=1000)
+    if args.optimizer == "fused":
+        opt.keep_grads = args.keep_grads
     clean, noise, snr_idx, table = synthetic.waveforms(args.batch, L, seed=1234 + rank)
     raw = {"clean_wave": torch.from_numpy(clean)[:, None].pin_memory(), "noise_wave": torch.from_numpy(noise)[:, None].pin_memory(),
            "snr_idx": torch.from_numpy(snr_idx), "snr": torch.tensor([table[i] for i in snr_idx])}
@@ -105,8 +110,8 @@ def main():
         print(json.dumps({
             "workload": "configs[2]: BYOL training step, WavLM-large shapes (random init), data-parallel",
             "n_gpus": world, "batch_per_gpu": args.batch, "seconds": args.seconds, "layers": args.layers,
-            "autocast_bf16": args.autocast, "optimizer": args.optimizer, "trainable_params": n_params,
-            "loss": float(loss), "optimizer_table_builds": getattr(opt, "table_builds", None),
+            "autocast_bf16": args.autocast, "layerdrop": args.layerdrop, "optimizer": args.optimizer, "trainable_params": n_params,
+            "loss": float(loss), "optimizer_table_builds": getattr(opt, "table_builds", None), "keep_grads": args.keep_grads,
             "ms_per_step": ms, "utterance_seconds_per_s": world * args.batch * args.seconds / (ms * 1e-3),
             "hot_path_ms": {"h2d+mix": t_mix, "conv_frontend_fwd_one_view": t_fe, "ema_update": t_ema},
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
