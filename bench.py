@@ -356,8 +356,10 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n  # ms per call
 
-    def plain_time(fn, n=5):
-        fn(); torch.cuda.synchronize()
+    def plain_time(fn, n=5, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
@@ -444,7 +446,7 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
         ref_opt.step()
         for i in range(len(twin)):
             twin[i] = 0.996 * twin[i] + (1 - 0.996) * prm[i].data
-    t_stock_tail = plain_time(stock_tail, n=3)
+    t_stock_tail = plain_time(stock_tail, n=3, warm=3)  # first calls build the AdamW state and settle the allocator
     del fopt, ref_opt, prm, twin
     torch.cuda.empty_cache()
     p = torch.randn(B, 1024, device=dev, requires_grad=True)

@@ -237,3 +237,64 @@ def test_emotion_classifier_contract_matches_reference():
     # compute_length_from_mask: same numbers as the reference's list, but a device tensor
     lens = model.pooling.compute_length_from_mask(torch.tensor([[1.0] * 640, [1.0] * 321 + [0.0] * 319]))
     assert lens.tolist() == [2, 2] and lens.dtype == torch.int32
+
+
+def test_fused_optimizer_host_logic_without_gpu(monkeypatch):
+    """FusedAdamWEma's bookkeeping (bucketing by step count, lazy step counters, state_dict interchange with
+    torch.optim.AdamW, EMA twins of gradient-less parameters) with the device table replaced by a recorder: no kernel
+    runs, so this covers the host side on the CPU; the arithmetic is covered by tests/test_gpu_optim.py."""
+    from nrse_b200.train import optim as O
+    calls = []
+
+    class Recorder:
+        @staticmethod
+        def partials_count():
+            return 4
+
+        def update(self, params, grads, m, v, twins):
+            calls.append(("update", [g is not None for g in grads], [t is not None for t in twins]))
+
+        def grad_sqnorm(self, partials):
+            calls.append(("norm", partials.numel()))
+
+        def clip_adamw_ema(self, **kw):
+            calls.append(("step", kw["step"], kw["max_grad_norm"], kw["ema_decay"], kw["lr"]))
+
+    monkeypatch.setattr(O.ops, "OptimChunkTable", Recorder)
+    P = [torch.nn.Parameter(torch.randn(5)) for _ in range(3)]
+    twin = torch.randn(5)
+    opt = O.FusedAdamWEma(P, lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0, ema_pairs=[(P[2], twin)], ema_decay=0.99)
+    assert opt.has_ema and isinstance(opt, torch.optim.AdamW)
+    with pytest.raises(ValueError):
+        opt.attach_ema([(torch.nn.Parameter(torch.randn(5)), twin)], 0.9)  # not owned by this optimizer
+    opt.attach_ema([(P[2], twin)], 0.99)
+    grads = [torch.randn(5) for _ in range(3)]
+    for k in range(3):
+        for i, p in enumerate(P):
+            p.grad = None if (k == 0 and i == 2) else grads[i]  # P[2] joins one step late; its twin is an orphan first
+        opt.step()
+    steps = [c for c in calls if c[0] == "step"]
+    assert [c[1] for c in steps] == [1, 1, 2, 2, 3]        # k=0: one bucket; k=1, k=2: P[2] one step behind
+    assert calls[0] == ("update", [True, True, False], [False, False, True])
+    assert all(c[2] == 1.0 and c[3] == 0.99 for c in steps)
+    assert opt.table_builds == 2                            # k=0 and k=1 (new gradient pattern); k=2 reuses the tables
+    sd = opt.state_dict()
+    assert {k: float(v["step"]) for k, v in sd["state"].items()} == {0: 3.0, 1: 3.0, 2: 2.0}
+    # a torch.optim.AdamW resumes from it, and vice versa
+    ref = torch.optim.AdamW(P, lr=1e-3, weight_decay=1e-2)
+    ref.load_state_dict(sd)
+    assert float(ref.state[P[2]]["step"]) == 2.0
+    opt2 = O.FusedAdamWEma(P, lr=1e-3, weight_decay=1e-2)
+    opt2.load_state_dict(ref.state_dict())
+    calls.clear()
+    opt2.step()
+    assert sorted(c[1] for c in calls if c[0] == "step") == [3, 4] and not any(c[0] == "norm" for c in calls)
+    # LR schedulers act on param_groups as usual
+    sched = torch.optim.lr_scheduler.StepLR(opt2, step_size=1, gamma=0.5)
+    sched.step()
+    calls.clear()
+    opt2.step()
+    assert all(abs(c[4] - 5e-4) < 1e-12 for c in calls if c[0] == "step")
+    # zero_grad follows torch's default unless keep_grads is set
+    opt2.zero_grad()
+    assert all(p.grad is None for p in P)
