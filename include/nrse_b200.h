@@ -158,16 +158,18 @@ int nrse_clip_adamw_ema_chunks_f32(const uint64_t* chunk_ptrs, int64_t chunk_pit
  *   out        [B,2D]  (mu | rh):  w = softmax_t(tanh(hl) . attention) over t < len,  mu = sum_t w x,
  *                      rh = sqrt(clamp(sum_t w x^2 - mu^2, min=1e-5))                  (:48-55)
  *   weights    [B,T]   the softmax weights (0 for t >= len), kept for the backward
- *   logits_ws / dw_ws  [B,T] fp32 scratch
+ *   logits_ws  [B,T]   fp32 scratch;  workspace: nrse_asp_pool_bwd_workspace_bytes(B, T, D) bytes of scratch
  * Backward: grad_x is the DIRECT gradient w.r.t. x (the path through sap_linear comes back from the
- * caller's GEMM backward on grad_hl); grad_attention [D] is zeroed and accumulated here.
+ * caller's GEMM backward on grad_hl); grad_attention [D] is written (not accumulated) from per-CTA partial
+ * rows summed in a fixed order: deterministic, no atomics.
  * ------------------------------------------------------------------------------------------- */
 int nrse_asp_pool_fwd(const float* x, const float* hl, const float* attention, const int32_t* lens, float* out,
                       float* weights, float* logits_ws, int B, int T, int D, nrse_stream_t stream);
+size_t nrse_asp_pool_bwd_workspace_bytes(int B, int T, int D);
 int nrse_asp_pool_bwd(const float* x, const float* hl, const float* attention, const int32_t* lens,
                       const float* out, const float* weights, const float* grad_out, float* grad_x,
-                      float* grad_hl, float* grad_attention, float* dw_ws, int B, int T, int D,
-                      nrse_stream_t stream);
+                      float* grad_hl, float* grad_attention, void* workspace, size_t workspace_bytes,
+                      int B, int T, int D, nrse_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BYOL loss with fused +1e-10, L2 normalisation (eps 1e-10), row dot product, clamp and mean.

@@ -66,7 +66,8 @@ SIGNATURES = {
     "nrse_clip_adamw_ema_chunks_f32": (_i, [_p, _i64, _p, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
                                            C.c_double, _i64, C.c_double, C.c_double, _p, _i, _p, _p]),
     "nrse_asp_pool_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
-    "nrse_asp_pool_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "nrse_asp_pool_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "nrse_asp_pool_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),
     "nrse_byol_loss_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "nrse_byol_loss_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "nrse_conv_frontend_geometry": (_i, [_i, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -1420,7 +1420,7 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
       // 128 KB of register-bound loads per SM land while in flight: with the carveout at 100 % the same kernel is
       // 15-25 % slower (measured), the loads being throttled by the 28 KB of L1 that remain.
       {
-        const int ctas_per_sm = threads == 512 ? 2 : 1;
+        const int ctas_per_sm = threads == 512 ? ResCfg<512>::kCtasPerSm : ResCfg<1024>::kCtasPerSm;
         const size_t need = ctas_per_sm * (dyn + 2048 + 1024);
         int pct = g_mix_carveout >= 0 ? g_mix_carveout : static_cast<int>((need * 100 + 228 * 1024 - 1) / (228 * 1024));
         pct = pct > 100 ? 100 : pct;

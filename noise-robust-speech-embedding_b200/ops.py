@@ -380,10 +380,12 @@ def _asp_pool_bwd(x: Tensor, hl: Tensor, attention: Tensor, lens: Tensor, out: T
     B, T, D = x.shape
     gx, gh = torch.empty_like(x), torch.empty_like(hl)
     ga = torch.empty(D, dtype=torch.float32, device=x.device)
-    dw = torch.empty(B, T, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    ws_bytes = int(lib.nrse_asp_pool_bwd_workspace_bytes(B, T, D))
+    ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=x.device)
     g = grad_out.to(torch.float32).contiguous()
-    check(_lib.load().nrse_asp_pool_bwd(_ptr(x), _ptr(hl), _ptr(attention), _ptr(lens), _ptr(out), _ptr(weights),
-                                        _ptr(g), _ptr(gx), _ptr(gh), _ptr(ga), _ptr(dw), B, T, D, _stream()),
+    check(lib.nrse_asp_pool_bwd(_ptr(x), _ptr(hl), _ptr(attention), _ptr(lens), _ptr(out), _ptr(weights), _ptr(g),
+                                _ptr(gx), _ptr(gh), _ptr(ga), _ptr(ws), ws_bytes, B, T, D, _stream()),
           "nrse_asp_pool_bwd")
     return gx, gh, ga
 
