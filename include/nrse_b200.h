@@ -237,7 +237,9 @@ int nrse_conv_layer_fwd(const void* act_prev, int64_t rows_prev, const void* w_p
 /* Tile decomposition of the tcgen05 kernel: 1 = one CTA owns all 512 channels of a 128-frame tile,
  * 2 = a 2-CTA cluster splits the channels and exchanges LayerNorm partials through DSMEM (default). */
 int nrse_conv_frontend_set_variant(int variant);
-/* Layer-0 kernel in LayerNorm mode: 0 = SIMT (warp per frame), 1 = tensor cores (hi/lo-split K=32 UMMA, default). */
+/* Layer-0 kernel in LayerNorm mode: 0 = SIMT (warp per frame); 1 = tensor cores (hi/lo-split K=32 UMMA, LayerNorm +
+ * GELU epilogue; always used by the training forward); 2 = tensor cores with LayerNorm folded into the GEMM operands
+ * (K=48, GELU-only epilogue; inference forward, default); 3 = 2 with 16 epilogue warps (tuning knob, slower). */
 int nrse_conv_frontend_set_layer0_variant(int variant);
 /* 1: the TMA producer of the GEMM layers bulk-prefetches the next tile's input frames into L2 (default 0: measured
  * 2-3 % slower at 64 x 4 s -- the operand feed is not HBM-latency bound). */

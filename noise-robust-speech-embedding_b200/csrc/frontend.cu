@@ -323,6 +323,7 @@ struct EpiCtx {
   float* rstd_out;          // nullable: where to put this row's 1/std
   bool pre_stats;           // LayerNorm statistics supplied by the caller (layer 0): skip pass 1 and the exchange
   float pre_mean, pre_rstd;
+  int gb_pair_off;          // first (gamma, beta) PAIR index of this thread's columns (0 unless the columns are split)
 };
 
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction) --------------
@@ -380,13 +381,15 @@ __device__ __forceinline__ f2 gelu2(f2 x) {
   return f2_fma(f2_mul(u, f2_make(e0, e1)), f2_make(-0.5f, -0.5f), f2_make(r0, r1));
 }
 
-template <int kClusterN, bool kSave>
+// kColsDiv = 2 (layer 0 only, statistics supplied by the caller): this thread handles kNPC / 2 columns of its row, the
+// other half belongs to the twin team working on the same accumulator buffer.
+template <int kClusterN, bool kSave, int kColsDiv = 1>
 __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
   constexpr int kNPC = kC / kClusterN;
-  constexpr int kChunks = kNPC / 32;
+  constexpr int kChunks = kNPC / 32 / kColsDiv;
   const uint32_t taddr = e.taddr;
-  const f2* s_gamma2 = reinterpret_cast<const f2*>(e.s_gb);           // [kNPC/2] pairs of gamma
-  const f2* s_beta2 = reinterpret_cast<const f2*>(e.s_gb) + kNPC / 2;  // [kNPC/2] pairs of beta
+  const f2* s_gamma2 = reinterpret_cast<const f2*>(e.s_gb) + e.gb_pair_off;            // [kNPC/2] pairs of gamma
+  const f2* s_beta2 = reinterpret_cast<const f2*>(e.s_gb) + kNPC / 2 + e.gb_pair_off;  // [kNPC/2] pairs of beta
   uint32_t ra[32], rb[32];  // two TMEM chunks in flight: the next load overlaps the math on the current one
   float mean = 0.f, rstd = 1.f;
 
@@ -506,19 +509,34 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
       }
     }
   };
+  if constexpr (kColsDiv > 1) {
+    // split columns (16 epilogue warps per SM): one TMEM chunk in flight per thread -- the other warps of the scheduler
+    // cover the load latency, and the 32 registers of the second chunk are what keeps 672 threads under the register file
 #pragma unroll 1
-  for (int c = 0; c < kChunks; c += 2) {
-    ptx::tmem_ld_wait();
-    ptx::tmem_ld32(taddr + (c + 1) * 32, rb);
-    emit32(ra, c);
-    ptx::tmem_ld_wait();
-    if (c + 2 < kChunks) {
-      ptx::tmem_ld32(taddr + (c + 2) * 32, ra);
-    } else {  // accumulator fully read: hand it back to the MMA warp
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(e.bar_tmem_empty);
+    for (int c = 0; c < kChunks; ++c) {
+      if (c > 0) ptx::tmem_ld32(taddr + c * 32, ra);
+      ptx::tmem_ld_wait();
+      if (c + 1 == kChunks) {  // this thread's columns are read: hand the accumulator back to the MMA warp
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(e.bar_tmem_empty);
+      }
+      emit32(ra, c);
     }
-    emit32(rb, c + 1);
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < kChunks; c += 2) {
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld32(taddr + (c + 1) * 32, rb);
+      emit32(ra, c);
+      ptx::tmem_ld_wait();
+      if (c + 2 < kChunks) {
+        ptx::tmem_ld32(taddr + (c + 2) * 32, ra);
+      } else {  // accumulator fully read: hand it back to the MMA warp
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(e.bar_tmem_empty);
+      }
+      emit32(rb, c + 1);
+    }
   }
 }
 
@@ -727,6 +745,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ec.pre_stats = false;
       ec.pre_mean = 0.f;
       ec.pre_rstd = 1.f;
+      ec.gb_pair_off = 0;
       epilogue_row<kClusterN, kSave>(ec);
     }
   }
@@ -753,29 +772,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // =========================================================================================================
 constexpr int kL0AStages = 2;  // warps 0-3: A-row builders, warp 4: MMA issuer, warps 5..: epilogue teams
 
-template <int kClusterN>
+constexpr int kL0PreSlots = 8;  // (mean, rstd) slots handed from the builders to the epilogue teams
+
+// kSplit = 2: TWO epilogue teams per accumulator buffer, each taking half of its columns (16 epilogue warps per SM
+// instead of 8).  Layer 0 has almost no MMA work (K = 32); its cost is the epilogue's 11 instructions per output element,
+// issued at IPC 1.9 by 8 warps -- two warps per scheduler cannot cover each other's TMEM-load and MUFU latencies.
+template <int kClusterN, int kSplit = 1>
 struct L0tcCfg {
   static constexpr int kNPC = kC / kClusterN;
   static constexpr int kNumMma = kNPC / kUmmaN;
   static constexpr int kAccBufs = 512 / kNPC;
-  static constexpr int kTeams = kAccBufs;
+  static constexpr int kTeams = kAccBufs * kSplit;
   static constexpr int kThreads = 160 + kTeams * kEpiThreads;
   static constexpr int kABytes = kBlockM * 128;  // 128-byte row pitch, K = 32 bf16 uses the first 64 bytes
   static constexpr int kWOff = kL0AStages * kABytes;
   static constexpr int kWBytes = kNPC * 128;
   static constexpr int kGbOff = kWOff + kWBytes;
-  static constexpr int kStatsOff = kGbOff + kNPC * 8;           // 4 slots x 128 rows x (mean, rstd) from the builders
-  static constexpr int kGramOff = kStatsOff + 4 * kBlockM * 8;  // 10 channel-mean taps + 55 Gram entries (fp32)
+  static constexpr int kStatsOff = kGbOff + kNPC * 8;           // kL0PreSlots x 128 rows x (mean, rstd) from the builders
+  static constexpr int kGramOff = kStatsOff + kL0PreSlots * kBlockM * 8;  // 10 channel-mean taps + 55 Gram entries
   static constexpr int kBarOff = kGramOff + 72 * 4;
-  static constexpr int kNumBars = 2 * kL0AStages + 2 * kAccBufs + 2 + 4;  // + 4 statistics-slot barriers
+  static constexpr int kNumBars = 2 * kL0AStages + 2 * kAccBufs + 2 + kL0PreSlots;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kSmemBytes = kTmemPtrOff + 16 + 1024;
 };
 
 // K layout of one operand row (32 bf16 = 16 words): [a_0..a_9 | b_0..b_9 | c_0..c_9 | 0 0]
-__device__ __forceinline__ void l0_store_row(uint32_t tile_base, int row, const uint32_t (&w)[16]) {
+template <int kWords>
+__device__ __forceinline__ void l0_store_row(uint32_t tile_base, int row, const uint32_t (&w)[kWords]) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < kWords / 4; ++c) {
     const uint32_t addr = tile_base + static_cast<uint32_t>(row * 128 + ((c ^ (row & 7)) << 4));  // SWIZZLE_128B
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * c]), "r"(w[4 * c + 1]),
                  "r"(w[4 * c + 2]), "r"(w[4 * c + 3])
@@ -794,9 +819,25 @@ __device__ __forceinline__ void l0_split(const float (&v)[10], uint32_t (&hi)[5]
   }
 }
 
-template <int kClusterN, bool kSave>
-__global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_kernel(const L0Args a) {
-  using Cfg = L0tcCfg<kClusterN>;
+// v -> (hi, lo) bf16 bit patterns with v = hi + lo (+ O(2^-17))
+__device__ __forceinline__ void l0_split1(float v, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+}
+
+// kFold (inference forward only): LayerNorm is folded INTO the GEMM operands.  The builders know (mean, rstd) of a frame
+// before the MMA runs (they follow from its 10 samples), so they scale the frame's samples by rstd and append
+// -mean*rstd and 1 to the A row; the filters are pre-multiplied by gamma and carry gamma and beta in the matching K
+// slots (K = 48 instead of 32; the tensor pipe is 4 % busy).  The accumulator then already holds
+//     rstd * gamma_c * z_c  -  mean * rstd * gamma_c  +  beta_c   =   LayerNorm(z)_c * gamma_c + beta_c
+// and the epilogue is GELU + store: no normalise FFMA2, no affine FFMA2, no gamma/beta shared-memory loads (the loads'
+// latency was the epilogue's main dependency stall).  All added operands get the same bf16 hi/lo split as the samples.
+template <int kClusterN, bool kSave, int kSplit = 1, bool kFold = false>
+__global__ void __launch_bounds__(L0tcCfg<kClusterN, kSplit>::kThreads, 1) layer0_tc_kernel(const L0Args a) {
+  static_assert(!(kFold && kSave), "the training forward needs the pre-affine activations: no folding");
+  using Cfg = L0tcCfg<kClusterN, kSplit>;
+  constexpr int kWords = kFold ? 24 : 16;  // 32-bit words (bf16 pairs) per operand row: K = 48 or 32
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -818,11 +859,11 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
     }
     for (int b = 0; b < Cfg::kAccBufs; ++b) {
       ptx::mbar_init(bar(kTmemFull + b), 1);
-      ptx::mbar_init(bar(kTmemEmpty + b), kEpiThreads);
+      ptx::mbar_init(bar(kTmemEmpty + b), kEpiThreads * kSplit);
     }
     ptx::mbar_init(bar(kStats + 0), 1);
     ptx::mbar_init(bar(kStats + 1), 1);
-    for (int q = 0; q < 4; ++q) ptx::mbar_init(bar(kPre + q), kBlockM);  // builders -> epilogue: (mean, rstd) slot ready
+    for (int q = 0; q < kL0PreSlots; ++q) ptx::mbar_init(bar(kPre + q), kBlockM);  // builders -> epilogue: (mean, rstd) slot ready
     ptx::fence_mbar_init();
   }
   if (warp == 4) {
@@ -830,11 +871,13 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
     ptx::tmem_relinquish();
   }
   // this CTA's filters, split hi/lo, as the B operand: [w_hi | w_hi | w_lo | 0 0] against A = [x_hi | x_lo | x_hi | 0 0]
+  // (kFold: w = gamma * w, and K slots 30..34 = [g_hi g_hi g_lo b_hi b_lo] against A = [s_hi s_lo s_hi 1 1], s = -mean*rstd)
   for (int n = threadIdx.x; n < Cfg::kNPC; n += Cfg::kThreads) {
     float w[10];
+    const float gam = a.gamma[n0 + n], bet = a.beta[n0 + n];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) w[k] = __ldg(a.w + (n0 + n) * 10 + k);
-    uint32_t hi[5], lo[5], words[16];
+    for (int k = 0; k < 10; ++k) w[k] = __ldg(a.w + (n0 + n) * 10 + k) * (kFold ? gam : 1.0f);
+    uint32_t hi[5], lo[5], words[kWords];
     l0_split(w, hi, lo);
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -843,9 +886,19 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
       words[10 + j] = lo[j];
     }
     words[15] = 0;
-    l0_store_row(smem_base + Cfg::kWOff, n, words);
-    reinterpret_cast<float*>(s_gb)[n] = a.gamma[n0 + n];
-    reinterpret_cast<float*>(s_gb)[Cfg::kNPC + n] = a.beta[n0 + n];
+    if constexpr (kFold) {
+      uint32_t g_hi, g_lo, b_hi, b_lo;
+      l0_split1(gam, g_hi, g_lo);
+      l0_split1(bet, b_hi, b_lo);
+      words[15] = g_hi | (g_hi << 16);
+      words[16] = g_lo | (b_hi << 16);
+      words[17] = b_lo;
+#pragma unroll
+      for (int j = 18; j < kWords; ++j) words[j] = 0;
+    }
+    l0_store_row<kWords>(smem_base + Cfg::kWOff, n, words);
+    reinterpret_cast<float*>(s_gb)[n] = gam;
+    reinterpret_cast<float*>(s_gb)[Cfg::kNPC + n] = bet;
   }
   // LayerNorm statistics of a layer-0 frame follow from its 10 input samples alone:
   //   mean_c Z = wbar . x,   mean_c Z^2 = x^T G x,   wbar = mean_c W[c,:],  G = W^T W / 512   (all 512 channels)
@@ -901,17 +954,10 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
 #pragma unroll
         for (int k = 0; k < 10; ++k) x[k] = 0.f;
       }
-      uint32_t hi[5], lo[5], words[16];
-      l0_split(x, hi, lo);
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        words[j] = hi[j];
-        words[5 + j] = lo[j];
-        words[10 + j] = hi[j];
-      }
-      words[15] = 0;
+      uint32_t hi[5], lo[5], words[kWords];
+      float mean = 0.f, rstd;
       {
-        float mean = 0.f, q = 0.f;
+        float q = 0.f;
         int e = 0;
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
@@ -922,12 +968,36 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
           q = fmaf(t, x[k], q);
         }
         const float var = fmaxf(q - mean * mean, 0.f);
-        // slot it % 4: the epilogue of tile it-4 is long done when this thread gets here (see conv_gemm_kernel notes)
-        s_stats[(it & 3) * kBlockM + row] = make_float2(mean, rsqrtf(var + kNormEps));
-        ptx::mbar_arrive(bar(kPre + (it & 3)));
+        rstd = rsqrtf(var + kNormEps);
+        // slot it % 8: a builder runs at most kL0AStages + kAccBufs + 1 <= 7 tiles ahead of the oldest epilogue that may
+        // still have to read its slot (A stage free <= MMA issued <= accumulator buffer released)
+        s_stats[(it & (kL0PreSlots - 1)) * kBlockM + row] = make_float2(mean, rstd);
+        ptx::mbar_arrive(bar(kPre + (it & (kL0PreSlots - 1))));
       }
-      ptx::mbar_wait(bar(kEmpty + stage), phase ^ 1u);
-      l0_store_row(smem_base + stage * Cfg::kABytes, row, words);
+      if constexpr (kFold) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) x[k] *= rstd;
+      }
+      l0_split(x, hi, lo);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        words[j] = hi[j];
+        words[5 + j] = lo[j];
+        words[10 + j] = hi[j];
+      }
+      words[15] = 0;
+      if constexpr (kFold) {
+        uint32_t s_hi, s_lo;
+        l0_split1(-mean * rstd, s_hi, s_lo);
+        constexpr uint32_t kOne = 0x3f80u;  // bf16 1.0
+        words[15] = s_hi | (s_lo << 16);
+        words[16] = s_hi | (kOne << 16);
+        words[17] = kOne;
+#pragma unroll
+        for (int j = 18; j < kWords; ++j) words[j] = 0;
+      }
+      ptx::mbar_wait_backoff(bar(kEmpty + stage), phase ^ 1u, 200);  // builders run ahead of the epilogue: wait politely
+      l0_store_row<kWords>(smem_base + stage * Cfg::kABytes, row, words);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       ptx::mbar_arrive(bar(kFull + stage));
       if (++stage == kL0AStages) { stage = 0; phase ^= 1u; }
@@ -942,13 +1012,13 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
       for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         const int buf = it % Cfg::kAccBufs;
         const uint32_t acc_phase = static_cast<uint32_t>(it / Cfg::kAccBufs) & 1u;
-        ptx::mbar_wait(bar(kTmemEmpty + buf), acc_phase ^ 1u);
-        ptx::mbar_wait(bar(kFull + stage), phase);
+        ptx::mbar_wait_backoff(bar(kTmemEmpty + buf), acc_phase ^ 1u, 100);
+        ptx::mbar_wait_backoff(bar(kFull + stage), phase, 100);
         ptx::tc_fence_after();
         const uint32_t a_src = smem_base + stage * Cfg::kABytes;
         const uint32_t w_src = smem_base + Cfg::kWOff;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {  // K = 32 = 2 x UMMA_K
+        for (int k = 0; k < kWords / 8; ++k) {  // K = 32 (48 when folded) = 2 (3) x UMMA_K
           const uint64_t da = ptx::umma_desc_sw128(a_src + k * (kUmmaK * 2));
 #pragma unroll
           for (int h = 0; h < Cfg::kNumMma; ++h) {
@@ -965,42 +1035,44 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN>::kThreads, 1) layer0_tc_ker
   } else {
     // ===== epilogue teams (see conv_gemm_kernel) ==========================================================
     const int team = (warp - 5) >> 2;
+    const int buf = team % Cfg::kAccBufs;   // teams buf and buf + kAccBufs share an accumulator buffer (kSplit = 2)
+    const int half = team / Cfg::kAccBufs;  // ... and split its columns
+    constexpr int kColsPerTeam = Cfg::kNPC / kSplit;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t peer = cta_rank ^ 1u;
-    for (int it = team, tile = first_tile + team * tile_step; tile < num_tiles;
-         it += Cfg::kTeams, tile += Cfg::kTeams * tile_step) {
-      const int buf = team;
+    for (int it = buf, tile = first_tile + buf * tile_step; tile < num_tiles;
+         it += Cfg::kAccBufs, tile += Cfg::kAccBufs * tile_step) {
       const uint32_t acc_phase = static_cast<uint32_t>(it / Cfg::kAccBufs) & 1u;
       const long long m = static_cast<long long>(tile) * kBlockM + row;
       ptx::mbar_wait(bar(kTmemFull + buf), acc_phase);
       ptx::tc_fence_after();
-      // the builders' (mean, rstd) for this tile (slot it % 4 is not rewritten before tile it + 4, whose builders
-      // cannot run until this epilogue has released the accumulator)
-      ptx::mbar_wait(bar(kPre + (it & 3)), static_cast<uint32_t>(it >> 2) & 1u);
-      const float2 pre = s_stats[(it & 3) * kBlockM + row];
-      const int slot = team * 2 + static_cast<int>(acc_phase);
+      // the builders' (mean, rstd) for this tile
+      ptx::mbar_wait(bar(kPre + (it & (kL0PreSlots - 1))), static_cast<uint32_t>(it / kL0PreSlots) & 1u);
+      const float2 pre = s_stats[(it & (kL0PreSlots - 1)) * kBlockM + row];
+      const int col0 = half * kColsPerTeam;
       EpiCtx ec;
       ec.pre_stats = true;
       ec.pre_mean = pre.x;
       ec.pre_rstd = pre.y;
-      ec.taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * Cfg::kNPC);
+      ec.gb_pair_off = col0 / 2;
+      ec.taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * Cfg::kNPC + col0);
       ec.bar_tmem_empty = bar(kTmemEmpty + buf);
-      ec.stats_slot = smem_base + Cfg::kStatsOff + static_cast<uint32_t>((slot * kBlockM + row) * 8);
-      ec.stats_local = s_stats + slot * kBlockM + row;
-      ec.bar_stats = bar(kStats + team);
+      ec.stats_slot = 0;          // statistics exchange is not used here (pre_stats)
+      ec.stats_local = s_stats;
+      ec.bar_stats = bar(kStats);
       ec.stats_parity = acc_phase;
-      ec.arm = row == 0;
+      ec.arm = false;
       ec.peer = peer;
       ec.s_gb = s_gb;
-      ec.has_norm = true;
+      ec.has_norm = !kFold;  // folded: the accumulator already holds the normalised, affine-transformed value
       ec.store = m < m_total;
       ec.zero = static_cast<int>(m % a.P0) >= a.T0;  // pitch padding is written as zeros
       ec.out_f32 = false;
-      ec.out_row = a.out + m * kC + n0;
-      ec.xhat_row = a.xhat ? a.xhat + m * kC + n0 : nullptr;
-      ec.rstd_out = (a.rstd && n0 == 0) ? a.rstd + m : nullptr;
-      epilogue_row<kClusterN, kSave>(ec);
+      ec.out_row = a.out + m * kC + n0 + col0;
+      ec.xhat_row = a.xhat ? a.xhat + m * kC + n0 + col0 : nullptr;
+      ec.rstd_out = (a.rstd && n0 == 0 && half == 0) ? a.rstd + m : nullptr;
+      epilogue_row<kClusterN, kSave, kSplit>(ec);
     }
   }
 
@@ -1460,13 +1532,13 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmArgs& g,
   return NRSE_OK;
 }
 
-template <int kClusterN, bool kSave = false>
+template <int kClusterN, bool kSave = false, int kSplit = 1, bool kFold = false>
 int launch_layer0_tc(const L0Args& a, cudaStream_t stream) {
-  using Cfg = L0tcCfg<kClusterN>;
+  using Cfg = L0tcCfg<kClusterN, kSplit>;
   static bool attr_set = false;
   if (!attr_set) {
-    NRSE_CUDA_TRY(cudaFuncSetAttribute(layer0_tc_kernel<kClusterN, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmemBytes));
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(layer0_tc_kernel<kClusterN, kSave, kSplit, kFold>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const long long m_total = static_cast<long long>(a.B) * a.P0;
@@ -1485,11 +1557,14 @@ int launch_layer0_tc(const L0Args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, layer0_tc_kernel<kClusterN, kSave>, a));
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, layer0_tc_kernel<kClusterN, kSave, kSplit, kFold>, a));
   return NRSE_OK;
 }
 
-int g_layer0_variant = 1;  // 0: SIMT kernel, 1: tensor-core kernel (LayerNorm mode only)
+int g_layer0_variant = 2;  // LayerNorm mode.  0: SIMT kernel; 1: tensor-core kernel; 2: tensor-core kernel with LayerNorm
+                           // folded into the GEMM operands (inference forward only; default); 3: 2 with 16 epilogue warps
+                           // (kSplit = 2, two teams per accumulator buffer: 80 registers per thread, measured 9 % slower
+                           // than 2 -- kept as a tuning knob)
 
 int geometry(int L, int32_t* T, int32_t* P) {
   long long t = L;
@@ -1563,7 +1638,7 @@ int nrse_conv_frontend_set_l2_prefetch(int on) {
 }
 
 int nrse_conv_frontend_set_layer0_variant(int variant) {
-  if (variant != 0 && variant != 1) return NRSE_ERR_INVALID_ARG;
+  if (variant < 0 || variant > 3) return NRSE_ERR_INVALID_ARG;
   nrse::g_layer0_variant = variant;
   return NRSE_OK;
 }
@@ -1594,8 +1669,12 @@ static int layer0_fwd_impl(const float* x, const float* w0, const float* gamma, 
   const long long want = ceil_div(rows, static_cast<long long>(kL0Warps));
   const unsigned grid = static_cast<unsigned>(want < kNumSMs ? want : kNumSMs);
   if (norm_mode == NRSE_NORM_LAYER) {
+    if (xhat == nullptr && g_variant == 2) {
+      if (g_layer0_variant == 2) return launch_layer0_tc<2, false, 1, true>(a, s);
+      if (g_layer0_variant == 3) return launch_layer0_tc<2, false, 2, true>(a, s);
+    }
     if (xhat != nullptr) return g_variant == 2 ? launch_layer0_tc<2, true>(a, s) : launch_layer0_tc<1, true>(a, s);
-    if (g_layer0_variant == 1) return g_variant == 2 ? launch_layer0_tc<2>(a, s) : launch_layer0_tc<1>(a, s);
+    if (g_layer0_variant >= 1) return g_variant == 2 ? launch_layer0_tc<2>(a, s) : launch_layer0_tc<1>(a, s);
     layer0_kernel<false><<<grid, kL0Threads, 0, s>>>(a);
     NRSE_CHECK_LAUNCH();
     return NRSE_OK;

@@ -21,8 +21,10 @@ def _layer_params(layers, dev):
     return w, g, b
 
 
-@pytest.mark.parametrize("mode,l0,variant", [("layer", 0, 2), ("layer", 1, 1), ("layer", 1, 2), ("group", 0, 2)],
-                         ids=["layer-simt", "layer-tc-v1", "layer-tc-v2", "group-simt"])
+@pytest.mark.parametrize("mode,l0,variant", [("layer", 0, 2), ("layer", 1, 1), ("layer", 1, 2), ("layer", 2, 2),
+                                             ("layer", 3, 2), ("group", 0, 2)],
+                         ids=["layer-simt", "layer-tc-v1", "layer-tc-v2", "layer-tc-fold", "layer-tc-fold-split",
+                              "group-simt"])
 def test_layer0_vs_oracle(dev, mode, l0, variant):
     ops.set_layer0_variant(l0)
     ops.set_frontend_variant(variant)
@@ -36,7 +38,7 @@ def test_layer0_vs_oracle(dev, mode, l0, variant):
     got = out[:, :T[0]].float().transpose(1, 2).cpu().numpy()
     assert rel_err(got, ref.numpy()) < 6e-3   # bf16 output rounding (2^-9) dominates
     assert not out[:, T[0]:].any()            # pitch padding is zero-filled
-    ops.set_layer0_variant(1)
+    ops.set_layer0_variant(2)
     ops.set_frontend_variant(2)
 
 
@@ -53,6 +55,20 @@ def test_layer0_tc_is_fp32_class(dev):
     diff = (got - ref).abs()
     assert float(diff.max()) <= 2 ** -7 * float(ref.abs().max())      # never more than ~1 bf16 ulp of the range
     assert float((diff > 0).float().mean()) < 0.05                     # and almost always bit-identical
+    for v in (2, 3):                                                   # LayerNorm folded into the GEMM operands
+        ops.set_layer0_variant(v)
+        fold = ops.conv_layer0(xd, w[0], g[0], b[0], "layer").float()
+        diff = (fold - ref).abs()
+        assert float(diff.max()) <= 2 ** -7 * float(ref.abs().max())
+        assert float((diff > 0).float().mean()) < 0.05
+    # DC offset 20x the signal: mean*rstd ~ 20, the folded operands must still cancel to fp32-class accuracy
+    xo = xd + 2.0
+    ops.set_layer0_variant(0)
+    ref = ops.conv_layer0(xo, w[0], g[0], b[0], "layer").float()
+    ops.set_layer0_variant(2)
+    fold = ops.conv_layer0(xo, w[0], g[0], b[0], "layer").float()
+    diff = (fold - ref).abs()
+    assert float(diff.max()) <= 2 ** -6 * float(ref.abs().max()) and float((diff > 0).float().mean()) < 0.10
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=["v1", "v2"])

@@ -90,8 +90,14 @@ def test_full_backward_vs_autograd(dev, B, L):
     xd = torch.from_numpy(x).to(dev)
     y, tape = ops.conv_frontend_train(xd, w, g, b)
     assert rel_err(y.transpose(1, 2).cpu().numpy(), y_ref.detach().numpy()) < 1e-2
+    # the tape-writing forward runs layer 0 with the un-folded epilogue (it has to save the pre-affine activations): with
+    # the same layer-0 kernel selected for inference the features are bit-identical, with the default (LayerNorm folded
+    # into the GEMM operands) they agree to bf16 rounding of the layer-0 output
+    ops.set_layer0_variant(1)
+    assert torch.equal(y, ops.conv_frontend(xd, w, g, b, "layer"))
+    ops.set_layer0_variant(2)
     y_plain = ops.conv_frontend(xd, w, g, b, "layer")
-    assert torch.equal(y, y_plain)                     # the tape-writing forward computes the same features
+    assert rel_err(y_plain.cpu().numpy(), y.cpu().numpy()) < 5e-3
     dw, dg, db = ops.conv_frontend_backward(xd, w, g, b, tape, gy.to(dev).transpose(1, 2))
     for i in range(7):
         e_w = rel_err(dw[i].cpu().numpy(), params[i]["conv"].grad.numpy())
