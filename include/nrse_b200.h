@@ -75,6 +75,16 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
                            const double* snr_db_table_host, int n_snr,
                            float* clean_out, float* noisy_out, int32_t* status,
                            int B, int L, int L_noise, int peak_norm, nrse_stream_t stream);
+/* Device-side retry ("try another noise file", ref:src/data/noisy_speech_dataset.py:58-84): same operation, but only
+ * rows whose status[b] != 0 on entry are processed -- with the noise of row (b + noise_row_shift) % B -- and get
+ * their outputs and status rewritten; all other rows are left untouched.  The CTAs of good rows exit at once, so a
+ * retry launch on a healthy batch costs a kernel launch and no memory traffic, and the host never has to read the
+ * status to decide whether to retry. */
+int nrse_mix_normalize_retry_f32(const float* clean, const float* noise, const int32_t* snr_idx,
+                                 const double* snr_db_table_host, int n_snr,
+                                 float* clean_out, float* noisy_out, int32_t* status,
+                                 int B, int L, int L_noise, int peak_norm, int noise_row_shift,
+                                 nrse_stream_t stream);
 const char* nrse_mix_status_name(int status_code);
 /* 4 (default): on-chip resident -- one 1024-thread CTA per SM keeps its segment of the row in registers (128 KB) and
  * shared memory (<= 192 KB) between the three passes; a cluster of 1/2/4/8 CTAs per row, exchanges by st.async + mbarrier;

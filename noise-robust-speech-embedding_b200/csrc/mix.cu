@@ -37,6 +37,8 @@ struct MixParams {
   int32_t* status;
   int B, L, Ln, peak_norm, n_snr;
   int raw;  // 1: write the un-normalised mix c + s*n (add_noise_to_speech alone); peak_norm must be 0
+  int retry;        // 1: only rows whose status is != 0 are processed (the others keep their outputs), ...
+  int noise_shift;  // ... with the noise of row (row + noise_shift) % B: the device-side "try another noise file"
   float snr_lin[kMaxSnr];  // float(10 ** (snr_db / 10)), ref:src/data/augment.py:39
 };
 
@@ -122,9 +124,10 @@ __global__ void __launch_bounds__(kMixThreads) mix_normalize_kernel(const MixPar
   __shared__ float xch2_f[kMixCluster];
   __shared__ unsigned xch2_u[kMixCluster];
 
+  if (p.retry && p.status[row] == 0) return;  // whole cluster (same row): nothing to redo
   const int L = p.L, Ln = p.Ln;
   const float* c_row = p.clean + static_cast<size_t>(row) * L;
-  const float* n_row = p.noise + static_cast<size_t>(row) * Ln;
+  const float* n_row = p.noise + static_cast<size_t>(p.retry ? (row + p.noise_shift) % p.B : row) * Ln;
   const int nvec = (L + 3) / 4;
   const int seg = (nvec + kMixCluster - 1) / kMixCluster;
   const int v_begin = rank * seg;
@@ -717,8 +720,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) mix_normalize_stream_kernel
   const int seg = (nvec + cs - 1) / cs;
   const int v_begin = min(nvec, rank * seg);
   const int v_end = min(nvec, v_begin + seg);
+  if (p.retry && p.status[row] == 0) return;  // whole cluster (same row): nothing to redo
   const float4* g_c = reinterpret_cast<const float4*>(p.clean + static_cast<size_t>(row) * L);
-  const float4* g_n = reinterpret_cast<const float4*>(p.noise + static_cast<size_t>(row) * p.Ln);
+  const float4* g_n = reinterpret_cast<const float4*>(
+      p.noise + static_cast<size_t>(p.retry ? (row + p.noise_shift) % p.B : row) * p.Ln);
 
   // ---- pass 1 (HBM) -------------------------------------------------------------------------------------------
   const f2 zero2 = f2_make(0.f, 0.f);
@@ -1019,8 +1024,10 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
   const int chunk_vec = (n_sm + kResChunks - 1) / kResChunks;
   float4* s_c = reinterpret_cast<float4*>(mix_smem);
   float4* s_n = s_c + smem_pitch;
+  if (p.retry && p.status[row] == 0) return;  // whole cluster (same row): nothing to redo
   const float4* g_c = reinterpret_cast<const float4*>(p.clean + static_cast<size_t>(row) * L) + v_begin;
-  const float4* g_n = reinterpret_cast<const float4*>(p.noise + static_cast<size_t>(row) * p.Ln) + v_begin;
+  const float4* g_n = reinterpret_cast<const float4*>(
+                          p.noise + static_cast<size_t>(p.retry ? (row + p.noise_shift) % p.B : row) * p.Ln) + v_begin;
 
   // The cluster exchanges are st.async messages that complete_tx on the RECEIVER's mbarrier: no cluster barrier and no
   // gpu-scope fence on the critical path (cg::cluster.sync() costs MEMBAR.GPU + ERRBAR twice per row).  Each CTA
@@ -1351,14 +1358,16 @@ const char* nrse_mix_status_name(int code) {
   return (code >= 0 && code <= 14) ? nrse::kMixStatusNames[code] : "unknown";
 }
 
-int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t* snr_idx,
-                           const double* snr_db_table_host, int n_snr, float* clean_out, float* noisy_out,
-                           int32_t* status, int B, int L, int L_noise, int peak_norm, nrse_stream_t stream) {
+static int mix_normalize_impl(const float* clean, const float* noise, const int32_t* snr_idx,
+                              const double* snr_db_table_host, int n_snr, float* clean_out, float* noisy_out,
+                              int32_t* status, int B, int L, int L_noise, int peak_norm, int retry, int noise_shift,
+                              nrse_stream_t stream) {
   using namespace nrse;
   if (!clean || !noise || !snr_idx || !snr_db_table_host || !noisy_out || !status) return NRSE_ERR_INVALID_ARG;
   if (B < 0 || L <= 0 || L_noise <= 0 || n_snr <= 0 || n_snr > kMaxSnr) return NRSE_ERR_INVALID_ARG;
   if (peak_norm < 0 || peak_norm > 2) return NRSE_ERR_INVALID_ARG;
   if (peak_norm == 1 && !clean_out) return NRSE_ERR_INVALID_ARG;
+  if (retry && noise_shift < 0) return NRSE_ERR_INVALID_ARG;
   if (B == 0) return NRSE_OK;
 
   MixParams p;
@@ -1367,6 +1376,10 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
   p.noisy_out = noisy_out; p.status = status;
   p.B = B; p.L = L; p.Ln = L_noise; p.peak_norm = peak_norm == 1 ? 1 : 0; p.n_snr = n_snr;
   p.raw = peak_norm == 2 ? 1 : 0;
+  p.retry = retry ? 1 : 0;
+  p.noise_shift = retry ? noise_shift % B : 0;
+  const int mix_variant = (retry && (g_mix_variant == 1 || g_mix_variant == 2)) ? 3 : g_mix_variant;  // the shared-
+  // memory variants walk several rows per cluster and do not implement the retry skip
   for (int i = 0; i < kMaxSnr; ++i)
     p.snr_lin[i] = i < n_snr ? static_cast<float>(std::pow(10.0, snr_db_table_host[i] / 10.0)) : 1.0f;
 
@@ -1383,7 +1396,7 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
   cfg.attrs = attr;
   cfg.numAttrs = 1;
 
-  if (vec && g_mix_variant >= 4) {
+  if (vec && mix_variant >= 4) {
     // CTAs per row (<= 8, any size; sweep in scripts/bench_mix_sweep.py, B200): the 512-thread shape with segments of
     // <= 4096 float4 (half in registers, half in shared memory: 2 x 64 KB of shared memory per SM leaves ~100 KB of
     // L1 for the register-bound loads in flight) is best at every length it can serve; segments that fill the whole
@@ -1397,7 +1410,7 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
     };
     int threads = 512, cs = min_cluster(2 * ResCfg<512>::kRegCap);
     if (cs > kSmemMaxCluster) cs = min_cluster(ResCfg<512>::kCap);
-    if (cs > kSmemMaxCluster || g_mix_variant == 5) {
+    if (cs > kSmemMaxCluster || mix_variant == 5) {
       threads = 1024;
       cs = min_cluster(ResCfg<1024>::kCap);
     }
@@ -1447,7 +1460,7 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
       return NRSE_OK;
     }
   }
-  if (vec && g_mix_variant >= 3) {
+  if (vec && mix_variant >= 3) {
     // one CTA of 1024 threads per row when the batch fills the machine, else the largest cluster (<= 8) that keeps
     // B * cs within the SM count
     // 1 CTA per SM (1024 threads x 64 registers): pick the cluster size (CTAs per row) that wastes the fewest SM-slots
@@ -1469,7 +1482,7 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
     NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_stream_kernel, p));
     return NRSE_OK;
   }
-  if (vec && g_mix_variant >= 1) {
+  if (vec && mix_variant >= 1) {
     // smallest power-of-two cluster (<= 8) whose per-CTA stage (both row segments) is <= 64 KB
     const size_t row_bytes = static_cast<size_t>(L) * 8;
     int cs = 1;
@@ -1488,7 +1501,7 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
     }
     cfg.blockDim = dim3(kSmemThreads);
     attr[0].val.clusterDim.x = cs;
-    if (g_mix_variant == 2 && 2 * stage_bytes <= kMaxSmem) {
+    if (mix_variant == 2 && 2 * stage_bytes <= kMaxSmem) {
       // persistent: as many clusters as fit one CTA per SM (two stages of shared memory per CTA)
       const int ctas_per_sm = static_cast<int>(kMaxSmem / (2 * stage_bytes)) >= 2 ? 2 : 1;
       int n_clusters = kNumSMs * ctas_per_sm / cs;
@@ -1512,6 +1525,21 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
   if (vec) NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_kernel<true>, p));
   else NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_kernel<false>, p));
   return NRSE_OK;
+}
+
+int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t* snr_idx,
+                           const double* snr_db_table_host, int n_snr, float* clean_out, float* noisy_out,
+                           int32_t* status, int B, int L, int L_noise, int peak_norm, nrse_stream_t stream) {
+  return mix_normalize_impl(clean, noise, snr_idx, snr_db_table_host, n_snr, clean_out, noisy_out, status, B, L, L_noise,
+                            peak_norm, 0, 0, stream);
+}
+
+int nrse_mix_normalize_retry_f32(const float* clean, const float* noise, const int32_t* snr_idx,
+                                 const double* snr_db_table_host, int n_snr, float* clean_out, float* noisy_out,
+                                 int32_t* status, int B, int L, int L_noise, int peak_norm, int noise_row_shift,
+                                 nrse_stream_t stream) {
+  return mix_normalize_impl(clean, noise, snr_idx, snr_db_table_host, n_snr, clean_out, noisy_out, status, B, L, L_noise,
+                            peak_norm, 1, noise_row_shift, stream);
 }
 
 }  // extern "C"

@@ -145,39 +145,76 @@ class TensorPairDataset(Dataset):
 
 
 class GpuBatchMixer:
-    """Raw batch -> reference-format batch on the device: one fused mix + peak-norm + z-norm launch per batch."""
+    """Raw batch -> reference-format batch on the device: one fused mix + peak-norm + z-norm launch per batch, and NO
+    host synchronisation.
 
-    def __init__(self, snr_range: Sequence[int], device, peak_norm: bool = True, max_attempts: int = 5):
+    The reference's ``__getitem__`` retries an item up to five times when ``add_noise_to_speech`` or the peak checks
+    reject it (ref:src/data/noisy_speech_dataset.py:55-149), synchronising the worker ~20 times per item to decide.  Here
+    the decision stays on the device: after the first launch, ``max_attempts - 1`` retry launches redo exactly the rows
+    whose status is non-zero with another row's noise crop (``ops.mix_normalize_retry_``); for a healthy batch their
+    CTAs exit immediately.  The host never reads the status on the critical path: a count of rows that are still bad is
+    copied to pinned memory asynchronously and looked at when the NEXT batch is prepared (by then it has long arrived).
+    Such rows (the reference would return ``None`` for them and crash the collate) stay in the batch zero-filled
+    (BYOL mode) / as the clean waveform (emotion mode) and are reported through ``batch["mix_status"]`` and the log.
+    ``drop_bad_rows=True`` restores the old behaviour -- read the status and drop those rows -- at the price of one host
+    synchronisation per batch."""
+
+    def __init__(self, snr_range: Sequence[int], device, peak_norm: bool = True, max_attempts: int = 5,
+                 drop_bad_rows: bool = False):
         self.snr_table = [float(v) for v in snr_range]
         self.device = torch.device(device)
         self.peak_norm = peak_norm
         self.max_attempts = max_attempts
+        self.drop_bad_rows = drop_bad_rows
+        self.rejected_rows = 0          # rows that stayed bad after all attempts, as far as already observed
+        self._pending = []              # [(pinned count tensor, event)] of batches not yet looked at
+
+    def _poll(self, block: bool = False) -> None:
+        keep = []
+        for cnt, ev in self._pending:
+            if block:
+                ev.synchronize()
+            if ev.query():
+                n = int(cnt.item())
+                if n:
+                    self.rejected_rows += n
+                    logger.error("%d row(s) failed all %d mix attempts and were left zero-filled / clean", n,
+                                 self.max_attempts)
+            else:
+                keep.append((cnt, ev))
+        self._pending = keep
+
+    def flush(self) -> int:
+        """Wait for the outstanding status counts (end of an epoch); returns the total number of rejected rows."""
+        self._poll(block=True)
+        return self.rejected_rows
 
     @torch.no_grad()
     def __call__(self, raw: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         dev = self.device
-        clean = raw["clean_wave"].to(dev, non_blocking=True).flatten(1)
-        noise = raw["noise_wave"].to(dev, non_blocking=True).flatten(1)
+        self._poll()
+        clean = raw["clean_wave"].to(dev, non_blocking=True).flatten(1).contiguous().float()
+        noise = raw["noise_wave"].to(dev, non_blocking=True).flatten(1).contiguous().float()
         snr_idx = torch.as_tensor(raw["snr_idx"]).to(dev, non_blocking=True).to(torch.int32)
         snr = torch.as_tensor(raw["snr"]).to(dev, non_blocking=True).to(torch.int64)
         c, n, status = ops.mix_normalize(clean, noise, snr_idx, self.snr_table, self.peak_norm)
-        bad = status != 0
-        attempt = 1
-        # one host read of the status vector per batch (the reference syncs ~20 times per ITEM)
-        while self.peak_norm and bool(bad.any()) and attempt < self.max_attempts:
-            rows = bad.nonzero().flatten()
-            logger.warning("mix rejected %d row(s) (status %s); re-drawing noise (attempt %d)", rows.numel(),
-                           sorted(set(status[rows].tolist())), attempt + 1)
-            donor = (rows + attempt) % clean.shape[0]  # another row's noise crop
-            c2, n2, st2 = ops.mix_normalize(clean[rows], noise[donor], snr_idx[rows], self.snr_table, True)
-            c[rows], n[rows], status[rows] = c2, n2, st2
+        if self.peak_norm and clean.shape[0] > 1:
+            for attempt in range(1, self.max_attempts):  # device-side retries: no-ops unless a row was rejected
+                ops.mix_normalize_retry_(clean, noise, snr_idx, self.snr_table, c, n, status, attempt, True)
+        if self.drop_bad_rows:
             bad = status != 0
-            attempt += 1
-        if self.peak_norm and bool(bad.any()):
-            keep = (~bad).nonzero().flatten()
-            logger.error("dropping %d row(s) that failed %d mix attempts", int(bad.sum()), self.max_attempts)
-            c, n, snr = c[keep], n[keep], snr[keep]
-        out = {"noisy_input_values": n.unsqueeze(1), "snr": snr}
+            if bool(bad.any()):  # host synchronisation
+                keep = (~bad).nonzero().flatten()
+                logger.error("dropping %d row(s) that failed %d mix attempts", int(bad.sum()), self.max_attempts)
+                self.rejected_rows += int(bad.sum())
+                c, n, snr, status = (c[keep] if c is not None else None), n[keep], snr[keep], status[keep]
+        elif self.peak_norm:
+            cnt = torch.empty(1, dtype=torch.int64).pin_memory()
+            cnt.copy_((status != 0).sum().reshape(1), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pending.append((cnt, ev))
+        out = {"noisy_input_values": n.unsqueeze(1), "snr": snr, "mix_status": status}
         if self.peak_norm:
             out["clean_input_values"] = c.unsqueeze(1)
         return out

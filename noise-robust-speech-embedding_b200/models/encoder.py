@@ -23,6 +23,50 @@ def wavlm_large_config(**overrides) -> WavLMConfig:
     return WavLMConfig(**kw)
 
 
+def _upload_mask(mask_np, device) -> torch.Tensor:
+    """numpy bool mask -> device tensor through pinned memory, non-blocking (``torch.tensor(np, device=cuda)`` is a
+    blocking copy from pageable memory: the host waits for everything queued on the stream before it)."""
+    host = torch.from_numpy(mask_np)
+    if device.type != "cuda":
+        return host.to(device)
+    return host.pin_memory().to(device, non_blocking=True)
+
+
+def install_sync_free_spec_augment(model: nn.Module) -> nn.Module:
+    """Replace ``WavLMModel._mask_hidden_states`` (hf:models/wavlm/modeling_wavlm.py, SpecAugment on the projected
+    features, active in training mode with wavlm-large's ``mask_time_prob`` = 0.075) by an equivalent that never
+    synchronises the host with the device.  The stock method synchronises twice per forward: the mask is uploaded with a
+    blocking ``torch.tensor(..., device=...)`` and applied with boolean-mask assignment (``index_put_`` -> ``nonzero``
+    -> device-to-host read).  Here the same ``_compute_mask_indices`` call (same numpy RNG stream, same arguments)
+    produces the mask, it travels through pinned memory, and ``torch.where`` applies it: same values, same gradients."""
+    from transformers.models.wavlm import modeling_wavlm as hf
+
+    def _mask_hidden_states(hidden_states, mask_time_indices=None, attention_mask=None):
+        cfg = model.config
+        if not getattr(cfg, "apply_spec_augment", True):
+            return hidden_states
+        batch_size, sequence_length, hidden_size = hidden_states.size()
+        embed = model.masked_spec_embed.to(hidden_states.dtype)
+        if mask_time_indices is not None:
+            hidden_states = torch.where(mask_time_indices.bool()[:, :, None], embed, hidden_states)
+        elif cfg.mask_time_prob > 0 and model.training:
+            mask = hf._compute_mask_indices((batch_size, sequence_length), mask_prob=cfg.mask_time_prob,
+                                            mask_length=cfg.mask_time_length, attention_mask=attention_mask,
+                                            min_masks=cfg.mask_time_min_masks)
+            mask = _upload_mask(mask, hidden_states.device)
+            hidden_states = torch.where(mask[:, :, None], embed, hidden_states)
+        if cfg.mask_feature_prob > 0 and model.training:
+            mask = hf._compute_mask_indices((batch_size, hidden_size), mask_prob=cfg.mask_feature_prob,
+                                            mask_length=cfg.mask_feature_length,
+                                            min_masks=getattr(cfg, "mask_feature_min_masks", 0))
+            mask = _upload_mask(mask, hidden_states.device)
+            hidden_states = hidden_states.masked_fill(mask[:, None, :], 0)
+        return hidden_states
+
+    model._mask_hidden_states = _mask_hidden_states
+    return model
+
+
 def install_b200_frontend(model: nn.Module) -> nn.Module:
     """Swap ``model.feature_extractor`` (HF WavLMFeatureEncoder) for the B200 implementation, in place."""
     B200FeatureEncoder.convert(model.feature_extractor)
@@ -40,6 +84,7 @@ class WavLMEncoder(nn.Module):
             self.model = AutoModel.from_pretrained(model_name)
         if frontend == "b200":
             install_b200_frontend(self.model)
+            install_sync_free_spec_augment(self.model)
         elif frontend != "hf":
             raise ValueError("frontend must be 'b200' or 'hf'")
         self.output_dim = self.model.config.hidden_size

@@ -90,6 +90,34 @@ def mix_normalize(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db_table: S
     return (c if peak_norm else None), n, st
 
 
+@torch.library.custom_op("nrse::mix_normalize_retry", mutates_args=("clean_out", "noisy_out", "status"))
+def _mix_retry_op(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db: Sequence[float], mode: int,
+                  clean_out: Tensor, noisy_out: Tensor, status: Tensor, noise_row_shift: int) -> None:
+    _need_cuda(clean, noise, snr_idx, noisy_out, status)
+    B, L = clean.shape
+    table = (C.c_double * len(snr_db))(*[float(v) for v in snr_db])
+    check(_lib.load().nrse_mix_normalize_retry_f32(
+        _ptr(clean), _ptr(noise), _ptr(snr_idx), table, len(snr_db), _ptr(clean_out) if mode == 1 else None,
+        _ptr(noisy_out), _ptr(status), B, L, noise.shape[1], int(mode), int(noise_row_shift), _stream()),
+        "nrse_mix_normalize_retry_f32")
+
+
+def mix_normalize_retry_(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db_table: Sequence[float],
+                         clean_out: Optional[Tensor], noisy_out: Tensor, status: Tensor, noise_row_shift: int,
+                         peak_norm: bool = True) -> None:
+    """In place: redo ``mix_normalize`` for the rows with ``status != 0`` using the noise of row
+    ``(b + noise_row_shift) % B`` -- the reference's "try another noise file" (ref:src/data/noisy_speech_dataset.py:
+    58-84) decided and executed on the device; rows that were fine are not touched and cost nothing."""
+    if not (clean.is_contiguous() and noise.is_contiguous() and noisy_out.is_contiguous() and status.is_contiguous()):
+        raise NrseError("mix_normalize_retry_ expects contiguous tensors (it works in place)")
+    if clean.dtype != torch.float32 or noise.dtype != torch.float32 or status.dtype != torch.int32:
+        raise NrseError("mix_normalize_retry_ expects fp32 waveforms and an int32 status")
+    snr_idx = snr_idx.to(device=clean.device, dtype=torch.int32).contiguous()
+    co = clean_out if peak_norm else clean.new_empty(0)
+    _mix_retry_op(clean, noise, snr_idx, [float(v) for v in snr_db_table], 1 if peak_norm else 0, co, noisy_out, status,
+                  int(noise_row_shift))
+
+
 def mix_status_name(code: int) -> str:
     return _lib.load().nrse_mix_status_name(int(code)).decode()
 

@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--autocast", action="store_true", help="bf16 autocast for the stock transformer / heads")
     ap.add_argument("--layerdrop", type=float, default=0.1, help="WavLM LayerDrop (0.1 = wavlm-large; 0 for a "
                     "deterministic amount of work per step when A/B-ing)")
+    ap.add_argument("--profile", action="store_true", help="also report the summed CUDA kernel time of one step "
+                    "(torch.profiler): step time >> kernel time means the step is host-launch-bound")
     ap.add_argument("--keep-grads", action="store_true", help="fused optimizer: zero gradients in place (stable addresses)")
     ap.add_argument("--optimizer", choices=["fused", "torch"], default="fused",
                     help="fused: FusedAdamWEma (clip + AdamW + EMA in two launches); torch: the reference's sequence")
@@ -91,6 +93,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
 
+    kernel_ms = top = None
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.key_averages() if e.device_time_total > 0 and e.device_type.name == "CUDA"]
+        kernel_ms = sum(e.device_time_total for e in evs) / 2 / 1e3
+        top = [(e.key[:60], round(e.device_time_total / 2 / 1e3, 2), e.count // 2)
+               for e in sorted(evs, key=lambda e: -e.device_time_total)[:12]]
+
     # device time of the hot-path pieces inside that step
     def ev(fn, n=5):
         fn(); torch.cuda.synchronize()
@@ -112,7 +127,8 @@ def main():
             "n_gpus": world, "batch_per_gpu": args.batch, "seconds": args.seconds, "layers": args.layers,
             "autocast_bf16": args.autocast, "layerdrop": args.layerdrop, "optimizer": args.optimizer, "trainable_params": n_params,
             "loss": float(loss), "optimizer_table_builds": getattr(opt, "table_builds", None), "keep_grads": args.keep_grads,
-            "ms_per_step": ms, "utterance_seconds_per_s": world * args.batch * args.seconds / (ms * 1e-3),
+            "ms_per_step": ms, "cuda_kernel_ms_per_step": kernel_ms, "top_kernels": top,
+            "utterance_seconds_per_s": world * args.batch * args.seconds / (ms * 1e-3),
             "hot_path_ms": {"h2d+mix": t_mix, "conv_frontend_fwd_one_view": t_fe, "ema_update": t_ema},
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
     if world > 1:

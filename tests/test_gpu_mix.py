@@ -137,3 +137,30 @@ def test_forced_cluster_sizes(dev, mix_variant, cs):
     assert st.tolist() == st_ref.tolist()
     for b in range(3):
         assert rel_err(n[b], n_ref[b].numpy()) < TOL and rel_err(c[b], c_ref[b].numpy()) < TOL
+
+
+def test_device_side_retry_touches_only_rejected_rows(dev, mix_variant):
+    """nrse_mix_normalize_retry_f32: rows with status 0 keep their outputs bit for bit; rejected rows are redone with
+    the shifted noise row and equal a fresh mix of (clean[b], noise[(b + shift) % B])."""
+    B, L = 6, 8000
+    clean, noise, snr_idx, table = synthetic.waveforms(B, L, seed=21)
+    noise[1] = 0.0          # status 4
+    noise[4] = np.nan       # status 2
+    cd, nd = torch.from_numpy(clean).to(dev), torch.from_numpy(noise).to(dev)
+    sd = torch.from_numpy(snr_idx).to(dev)
+    tab = [float(v) for v in table]
+    c, n, st = ops.mix_normalize(cd, nd, sd, tab, True)
+    assert st.tolist() == [0, 4, 0, 0, 2, 0]
+    c0, n0 = c.clone(), n.clone()
+    ops.mix_normalize_retry_(cd, nd, sd, tab, c, n, st, 2, True)   # row 1 <- noise[3], row 4 <- noise[0]
+    assert st.tolist() == [0] * B
+    for b in (0, 2, 3, 5):
+        assert torch.equal(c[b], c0[b]) and torch.equal(n[b], n0[b])
+    for b, donor in ((1, 3), (4, 0)):
+        cr, nr, sr = oracle.mix_normalize_batch(clean[b:b + 1], noise[donor:donor + 1], snr_idx[b:b + 1], table)
+        assert sr.tolist() == [0]
+        assert rel_err(n[b].cpu().numpy(), nr[0].numpy()) < TOL and rel_err(c[b].cpu().numpy(), cr[0].numpy()) < TOL
+    # a second retry on a healthy batch is a no-op
+    c1, n1 = c.clone(), n.clone()
+    ops.mix_normalize_retry_(cd, nd, sd, tab, c, n, st, 1, True)
+    assert torch.equal(c, c1) and torch.equal(n, n1) and st.tolist() == [0] * B

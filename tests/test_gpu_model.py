@@ -123,6 +123,28 @@ def test_gpu_batch_mixer_and_retry(dev):
     assert rel_err(batch["noisy_input_values"][2, 0].cpu().numpy(), n2[0].numpy()) < 1e-6
 
 
+def test_gpu_batch_mixer_persistent_failure_is_reported_without_sync(dev):
+    """A silent clean row is rejected on every attempt (speech power < 1e-10): it stays in the batch zero-filled, shows
+    up in batch['mix_status'] and in the mixer's lazily collected count; drop_bad_rows=True drops it instead."""
+    B, L = 5, 4000
+    clean, noise, _, table = synthetic.waveforms(B, L, seed=9)
+    clean[3] = 0.0
+    noise[1] = 0.0                                   # recoverable: another row's noise is fine
+    raw = {"clean_wave": torch.from_numpy(clean)[:, None], "noise_wave": torch.from_numpy(noise)[:, None],
+           "snr_idx": torch.arange(B) % 3, "snr": torch.tensor([2, 5, 10, 2, 5])}
+    mixer = GpuBatchMixer([2, 5, 10], dev)
+    batch = mixer(raw)
+    assert batch["mix_status"].tolist() == [0, 0, 0, 3, 0]
+    assert batch["clean_input_values"].shape == (B, 1, L)
+    assert not batch["noisy_input_values"][3].any() and not batch["clean_input_values"][3].any()
+    assert batch["noisy_input_values"][1].abs().sum() > 0
+    assert mixer.flush() == 1
+    dropper = GpuBatchMixer([2, 5, 10], dev, drop_bad_rows=True)
+    batch = dropper(raw)
+    assert batch["clean_input_values"].shape == (B - 1, 1, L) and batch["mix_status"].tolist() == [0, 0, 0, 0]
+    assert batch["snr"].tolist() == [2, 5, 10, 5] and dropper.rejected_rows == 1
+
+
 def test_add_noise_to_speech_dropin(dev, golden):
     g = golden("mix_edge")
     for b in range(8):

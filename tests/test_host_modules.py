@@ -298,3 +298,33 @@ def test_fused_optimizer_host_logic_without_gpu(monkeypatch):
     # zero_grad follows torch's default unless keep_grads is set
     opt2.zero_grad()
     assert all(p.grad is None for p in P)
+
+
+def test_sync_free_spec_augment_equals_stock_masking():
+    """The sync-free SpecAugment replacement produces the same hidden states and gradients as HF's
+    ``_mask_hidden_states`` for the same numpy RNG state (drawn time masks and explicit mask_time_indices)."""
+    from transformers import WavLMModel
+    from nrse_b200.models import install_sync_free_spec_augment
+    cfg = small_config("layer")
+    cfg.mask_time_prob, cfg.mask_time_length = 0.3, 2  # (feature masking: WavLMConfig lacks mask_feature_min_masks,
+    # the stock method raises there; wavlm-large has mask_feature_prob = 0)
+    torch.manual_seed(0)
+    stock = WavLMModel(cfg).train()
+    mine = WavLMModel(cfg).train()
+    mine.load_state_dict(stock.state_dict())
+    install_sync_free_spec_augment(mine)
+    h = torch.randn(3, 24, cfg.hidden_size)
+    for explicit in (None, torch.rand(3, 24) < 0.25):
+        a = h.clone().requires_grad_(True)
+        b = h.clone().requires_grad_(True)
+        np.random.seed(5)
+        want = stock._mask_hidden_states(a * 1.0, mask_time_indices=explicit)
+        np.random.seed(5)
+        got = mine._mask_hidden_states(b * 1.0, mask_time_indices=explicit)
+        assert torch.equal(got, want)
+        (want * want).sum().backward()
+        (got * got).sum().backward()
+        assert torch.equal(a.grad, b.grad)
+        assert mine.masked_spec_embed.grad is not None
+    mine.eval()
+    assert torch.equal(mine._mask_hidden_states(h.clone()), h)  # inference: no masking
