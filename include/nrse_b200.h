@@ -251,6 +251,10 @@ int nrse_conv_frontend_set_variant(int variant);
  * GELU epilogue; always used by the training forward); 2 = tensor cores with LayerNorm folded into the GEMM operands
  * (K=48, GELU-only epilogue; inference forward, default); 3 = 2 with 16 epilogue warps (tuning knob, slower). */
 int nrse_conv_frontend_set_layer0_variant(int variant);
+/* Tile order of the GEMM layers inside nrse_conv_frontend_fwd / _fwd_train: 1 (default) = consecutive layers walk their
+ * tiles in opposite directions (each layer starts on the rows its producer wrote last, which are still in L2);
+ * 0 = every layer first-to-last.  Results do not depend on it. */
+int nrse_conv_frontend_set_tile_order(int alternate);
 /* 1: the TMA producer of the GEMM layers bulk-prefetches the next tile's input frames into L2 (default 0: measured
  * 2-3 % slower at 64 x 4 s -- the operand feed is not HBM-latency bound). */
 int nrse_conv_frontend_set_l2_prefetch(int on);

@@ -79,6 +79,7 @@ SIGNATURES = {
     "nrse_conv_layer_fwd": (_i, [_p, _i64, _p, _i, _i, _p, _p, _p, _i, _i64, _p]),
     "nrse_conv_frontend_set_variant": (_i, [_i]),
     "nrse_conv_frontend_set_layer0_variant": (_i, [_i]),
+    "nrse_conv_frontend_set_tile_order": (_i, [_i]),
     "nrse_conv_frontend_set_l2_prefetch": (_i, [_i]),
     "nrse_conv_frontend_tape_bytes": (_sz, [_i, _i]),
     "nrse_conv_frontend_fwd_train": (_i, [_p, C.POINTER(FrontendParams), _p, _i, _p, _sz, _i, _i, _p]),

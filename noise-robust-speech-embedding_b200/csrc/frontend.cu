@@ -303,6 +303,7 @@ struct GemmArgs {
   const char* a_ptr;
   long long a_rows;
   int l2_prefetch;
+  int reverse;  // 1: walk the tiles from the last to the first (see g_tile_order)
 };
 
 // ---- epilogue of one accumulator row (shared by the GEMM layers and the tensor-core layer 0) ----------------
@@ -636,7 +637,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < g.num_tiles; tile += tile_step) {
-        const int m0 = tile * kBlockM;
+        const int m0 = (g.reverse ? g.num_tiles - 1 - tile : tile) * kBlockM;
         if (g.l2_prefetch && cta_rank == 0 && tile + tile_step < g.num_tiles) {
           // the next tile's input frames are one contiguous range of the previous activation
           const long long nm0 = static_cast<long long>(tile + tile_step) * kBlockM;
@@ -712,7 +713,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
          it += Cfg::kTeams, tile += Cfg::kTeams * tile_step) {
       const int buf = team;
       const uint32_t acc_phase = static_cast<uint32_t>(it / Cfg::kAccBufs) & 1u;
-      const long long m = static_cast<long long>(tile) * kBlockM + row;
+      const long long m = static_cast<long long>(g.reverse ? g.num_tiles - 1 - tile : tile) * kBlockM + row;
       ptx::mbar_wait(bar(kTmemFull + buf), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * Cfg::kNPC);
@@ -1502,6 +1503,8 @@ int make_tmap_rows(CUtensorMap* m, const void* ptr, int64_t rows, int box_rows) 
   return r == CUDA_SUCCESS ? NRSE_OK : NRSE_ERR_CUDA;
 }
 
+int g_tile_order = 1;   // 1: consecutive layers walk their tiles in opposite directions, so that every layer starts on the
+                        // rows its producer wrote last (still in L2) instead of the ones it wrote first (long evicted); 0: all forward
 int g_l2_prefetch = 0;  // 1: producer bulk-prefetches the next tile's A rows into L2 (measured 2-3 % slower: off)
 int g_variant = 2;  // 1: single CTA per tile, 2: 2-CTA cluster splitting the channels (default)
 
@@ -1632,6 +1635,11 @@ int nrse_conv_frontend_set_variant(int variant) {
   return NRSE_OK;
 }
 
+int nrse_conv_frontend_set_tile_order(int alternate) {
+  nrse::g_tile_order = alternate ? 1 : 0;
+  return NRSE_OK;
+}
+
 int nrse_conv_frontend_set_l2_prefetch(int on) {
   nrse::g_l2_prefetch = on ? 1 : 0;
   return NRSE_OK;
@@ -1701,7 +1709,7 @@ int nrse_conv_layer0_fwd(const float* x, const float* w0, const float* gamma, co
 
 static int layer_fwd_impl(const void* act_prev, int64_t rows_prev, const void* w_packed, int k, int stride,
                           const float* gamma, const float* beta, void* out, int out_dtype, int64_t rows_out,
-                          void* xhat, float* rstd, nrse_stream_t stream) {
+                          void* xhat, float* rstd, nrse_stream_t stream, int reverse = 0) {
   using namespace nrse;
   if (!act_prev || !w_packed || !out || (k != 2 && k != 3) || stride != 2) return NRSE_ERR_INVALID_ARG;
   if ((gamma == nullptr) != (beta == nullptr)) return NRSE_ERR_INVALID_ARG;
@@ -1732,6 +1740,7 @@ static int layer_fwd_impl(const void* act_prev, int64_t rows_prev, const void* w
   g.a_ptr = reinterpret_cast<const char*>(act_prev);
   g.a_rows = rows_prev;
   g.l2_prefetch = g_l2_prefetch;
+  g.reverse = reverse;
   if (xhat != nullptr)
     return g_variant == 2 ? launch_gemm<2, true>(ta, tw, g, as_stream(stream)) : launch_gemm<1, true>(ta, tw, g, as_stream(stream));
   return g_variant == 2 ? launch_gemm<2>(ta, tw, g, as_stream(stream)) : launch_gemm<1>(ta, tw, g, as_stream(stream));
@@ -1772,9 +1781,10 @@ int nrse_conv_frontend_fwd(const float* x, const nrse_frontend_params* prm, int 
   for (int i = 1; i < kLayers; ++i) {
     const bool norm = norm_mode == NRSE_NORM_LAYER;
     if (norm && (!prm->gamma[i] || !prm->beta[i])) return NRSE_ERR_INVALID_ARG;
-    rc = nrse_conv_layer_fwd(act[i - 1], static_cast<int64_t>(B) * P[i - 1], prm->w_packed[i - 1], kKernel[i],
-                             kStride[i], norm ? prm->gamma[i] : nullptr, norm ? prm->beta[i] : nullptr, act[i],
-                             i == kLayers - 1 ? y_dtype : NRSE_DTYPE_BF16, static_cast<int64_t>(B) * P[i], stream);
+    rc = layer_fwd_impl(act[i - 1], static_cast<int64_t>(B) * P[i - 1], prm->w_packed[i - 1], kKernel[i], kStride[i],
+                        norm ? prm->gamma[i] : nullptr, norm ? prm->beta[i] : nullptr, act[i],
+                        i == kLayers - 1 ? y_dtype : NRSE_DTYPE_BF16, static_cast<int64_t>(B) * P[i], nullptr, nullptr,
+                        stream, g_tile_order ? (i & 1) : 0);
     if (rc != NRSE_OK) return rc;
   }
   return NRSE_OK;
@@ -1805,7 +1815,7 @@ int nrse_conv_frontend_fwd_train(const float* x, const nrse_frontend_params* prm
     void* out = i == kLayers - 1 ? y : static_cast<void*>(t.act[i]);
     rc = layer_fwd_impl(t.act[i - 1], static_cast<int64_t>(B) * P[i - 1], prm->w_packed[i - 1], kKernel[i], kStride[i],
                         prm->gamma[i], prm->beta[i], out, i == kLayers - 1 ? y_dtype : NRSE_DTYPE_BF16,
-                        static_cast<int64_t>(B) * P[i], t.xhat[i], t.rstd[i], stream);
+                        static_cast<int64_t>(B) * P[i], t.xhat[i], t.rstd[i], stream, g_tile_order ? (i & 1) : 0);
     if (rc != NRSE_OK) return rc;
   }
   return NRSE_OK;

@@ -577,6 +577,10 @@ def set_mix_carveout(percent: int) -> None:
     check(_lib.load().nrse_mix_set_carveout(int(percent)), "nrse_mix_set_carveout")
 
 
+def set_tile_order(alternate: int) -> None:
+    check(_lib.load().nrse_conv_frontend_set_tile_order(int(alternate)), "nrse_conv_frontend_set_tile_order")
+
+
 def set_layer0_variant(variant: int) -> None:
     check(_lib.load().nrse_conv_frontend_set_layer0_variant(int(variant)), "nrse_conv_frontend_set_layer0_variant")
 

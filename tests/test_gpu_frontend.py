@@ -168,3 +168,21 @@ def test_forward_paths_are_deterministic(dev):
     assert torch.equal(y1, y2)
     p, z = y1.mean(1), ops.conv_frontend(c1, w, g, b, "layer").mean(1)
     assert torch.equal(ops.byol_loss(p, z), ops.byol_loss(p, z))
+
+
+def test_tile_order_is_a_pure_scheduling_knob(dev):
+    """Consecutive GEMM layers walk their tiles in opposite directions by default (L2 locality); forcing every layer
+    first-to-last gives bit-identical features, for the inference and the tape-writing forward."""
+    layers = synthetic.frontend_weights("layer", seed=4)
+    w, g, b = _layer_params(layers, dev)
+    x = torch.from_numpy(synthetic.waveforms(3, 20000, seed=5)[0] * 10).to(dev)
+    try:
+        ops.set_tile_order(0)
+        y0 = ops.conv_frontend(x, w, g, b, "layer")
+        t0, _ = ops.conv_frontend_train(x, w, g, b)
+        ops.set_tile_order(1)
+        y1 = ops.conv_frontend(x, w, g, b, "layer")
+        t1, _ = ops.conv_frontend_train(x, w, g, b)
+    finally:
+        ops.set_tile_order(1)
+    assert torch.equal(y0, y1) and torch.equal(t0, t1)
