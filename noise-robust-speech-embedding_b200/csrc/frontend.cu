@@ -1146,10 +1146,27 @@ __device__ __forceinline__ f2 gelu_grad2(f2 v) {
   return f2_add(f2_make(0.5f, 0.5f), f2_make(copysignf(h0, v0), copysignf(h1, v1)));
 }
 
-__global__ void __launch_bounds__(kLnBwdThreads) ln_gelu_bwd_kernel(const LnBwdArgs a) {
+// bf16 gradient input (every layer but the last): each warp keeps kLnStages rows in flight with per-lane cp.async copies
+// into its own shared-memory ring (a lane reads back exactly the 64 bytes it copied: no cross-lane synchronisation).
+// With direct loads a warp has one row (2 KB) in flight and, at 128 registers per thread, an SM holds 16 warps: 32 KB in
+// flight per SM is half of what HBM needs (40 % of peak measured); the ring costs no registers.
+constexpr int kLnStages = 4;
+constexpr int kLnStageBytes = 2 * kC * 2;  // xhat row + dOut row, bf16
+constexpr int kLnRingBytes = kLnBwdWarps * kLnStages * kLnStageBytes;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kN>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory"); }
+
+template <bool kDoutF32>
+__global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnBwdArgs a) {
   __shared__ __align__(16) float s_gamma[kC];
   __shared__ __align__(16) float s_beta[kC];
   __shared__ float s_acc[kLnBwdWarps][2 * kC];
+  extern __shared__ __align__(16) unsigned char ln_ring[];  // bf16 path only
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < kC; i += kLnBwdThreads) {
     s_gamma[i] = a.gamma[i];
@@ -1170,7 +1187,35 @@ __global__ void __launch_bounds__(kLnBwdThreads) ln_gelu_bwd_kernel(const LnBwdA
   for (int j = 0; j < 8; ++j) dg[j] = db[j] = zero2;
 
   const long long warps_total = static_cast<long long>(gridDim.x) * kLnBwdWarps;
-  for (long long m = static_cast<long long>(blockIdx.x) * kLnBwdWarps + warp; m < a.rows; m += warps_total) {
+  const long long m_first = static_cast<long long>(blockIdx.x) * kLnBwdWarps + warp;
+  const uint32_t ring = ptx::smem_u32(ln_ring) + static_cast<uint32_t>(warp * kLnStages * kLnStageBytes);
+  // issue the copies of row m into ring slot `slot` (nothing for rows past the end or in the pitch padding)
+  auto prefetch = [&](long long m, int slot) {
+    if constexpr (!kDoutF32) {
+      if (m < a.rows && static_cast<int>(m % a.P) < a.T) {
+        const uint32_t dst = ring + static_cast<uint32_t>(slot * kLnStageBytes);
+        const char* xr = reinterpret_cast<const char*>(a.xhat + m * kC);
+        const char* gr = reinterpret_cast<const char*>(reinterpret_cast<const __nv_bfloat16*>(a.dout) + m * kC);
+        cp_async16(dst + lane * 16, xr + lane * 16);
+        cp_async16(dst + 512 + lane * 16, xr + 512 + lane * 16);
+        cp_async16(dst + 1024 + lane * 16, gr + lane * 16);
+        cp_async16(dst + 1536 + lane * 16, gr + 512 + lane * 16);
+      }
+      cp_async_commit();
+    }
+  };
+  if constexpr (!kDoutF32) {
+#pragma unroll
+    for (int s = 0; s < kLnStages - 1; ++s) prefetch(m_first + s * warps_total, s);
+  }
+  int slot = 0;
+  for (long long m = m_first; m < a.rows; m += warps_total) {
+    if constexpr (!kDoutF32) {
+      prefetch(m + (kLnStages - 1) * warps_total, (slot + kLnStages - 1) % kLnStages);
+      cp_async_wait<kLnStages - 1>();  // this row's group has landed (groups complete in order)
+    }
+    const int cur = slot;
+    slot = (slot + 1) % kLnStages;
     uint4* zrow = reinterpret_cast<uint4*>(a.dz + m * kC);
     if (static_cast<int>(m % a.P) >= a.T) {  // pitch padding: no gradient flows through it
       zrow[lane] = make_uint4(0, 0, 0, 0);
@@ -1178,14 +1223,12 @@ __global__ void __launch_bounds__(kLnBwdThreads) ln_gelu_bwd_kernel(const LnBwdA
       continue;
     }
     f2 go[8], xh[8];
-    {
+    if constexpr (kDoutF32) {
       const uint4* xr = reinterpret_cast<const uint4*>(a.xhat + m * kC);
       const uint4 x0 = __ldg(xr + lane), x1 = __ldg(xr + 32 + lane);
       const unsigned w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) xh[j] = f2_bits(w[j] << 16, w[j] & 0xffff0000u);
-    }
-    if (a.dout_f32) {
       const float4* gr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.dout) + m * kC);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -1196,11 +1239,15 @@ __global__ void __launch_bounds__(kLnBwdThreads) ln_gelu_bwd_kernel(const LnBwdA
         go[h * 4 + 3] = f2_make(p1.z, p1.w);
       }
     } else {
-      const uint4* gr = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.dout) + m * kC);
-      const uint4 y0 = gr[lane], y1 = gr[32 + lane];
-      const unsigned w[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+      const uint4* st = reinterpret_cast<const uint4*>(ln_ring + (warp * kLnStages + cur) * kLnStageBytes);
+      const uint4 x0 = st[lane], x1 = st[32 + lane], y0 = st[64 + lane], y1 = st[96 + lane];
+      const unsigned wx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      const unsigned wy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) go[j] = f2_bits(w[j] << 16, w[j] & 0xffff0000u);
+      for (int j = 0; j < 8; ++j) {
+        xh[j] = f2_bits(wx[j] << 16, wx[j] & 0xffff0000u);
+        go[j] = f2_bits(wy[j] << 16, wy[j] & 0xffff0000u);
+      }
     }
     f2 dx[8], s1 = zero2, s2 = zero2;
 #pragma unroll
@@ -1232,6 +1279,7 @@ __global__ void __launch_bounds__(kLnBwdThreads) ln_gelu_bwd_kernel(const LnBwdA
     zrow[lane] = make_uint4(z[0], z[1], z[2], z[3]);
     zrow[32 + lane] = make_uint4(z[4], z[5], z[6], z[7]);
   }
+  if constexpr (!kDoutF32) cp_async_wait<0>();
   // CTA-level reduction of the affine gradients, then one atomic per channel per CTA
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -1252,11 +1300,23 @@ __global__ void __launch_bounds__(kLnBwdThreads) ln_gelu_bwd_kernel(const LnBwdA
   }
 }
 
-// dW0[c, tap] += sum over frames of dZ0[m, c] * x[5 t + tap]; lane owns 16 channels x 10 taps
+// dW0[c, tap] += sum over frames of dZ0[m, c] * x[5 t + tap]; lane owns 16 channels x 10 taps.
+// The 160 accumulators per lane leave room for one CTA of 8 warps per SM, and with direct loads each warp has a single
+// 1 KB gradient row in flight (19 % of HBM peak measured): every warp therefore keeps kL0WgStages rows in flight with
+// cp.async copies into its own shared-memory ring (dZ0 row: 32 lanes x 2 x 16 B; sample window: lanes 0..9 x 4 B).
+constexpr int kL0WgStages = 8;
+constexpr int kL0WgStageBytes = kC * 2 + 64;  // bf16 gradient row + the 10-sample window (padded to 64 B)
+constexpr int kL0WgRingBytes = kL0Warps * kL0WgStages * kL0WgStageBytes;
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
 __global__ void __launch_bounds__(kL0Threads, 1)
 layer0_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz, float* __restrict__ dw0, int B,
                     int L, int T0, int P0) {
   __shared__ float s_acc[kL0Warps][160 * 32 / 8];  // reduced in eight slices of 20 accumulators per lane
+  extern __shared__ __align__(16) unsigned char l0wg_ring[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float acc[16][10];
 #pragma unroll
@@ -1265,21 +1325,46 @@ layer0_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     for (int k = 0; k < 10; ++k) acc[j][k] = 0.f;
   const long long rows = static_cast<long long>(B) * P0;
   const long long warps_total = static_cast<long long>(gridDim.x) * kL0Warps;
-  for (long long m = static_cast<long long>(blockIdx.x) * kL0Warps + warp; m < rows; m += warps_total) {
-    const int b = static_cast<int>(m / P0), t = static_cast<int>(m % P0);
-    if (t >= T0) continue;
-    const float* xw = x + static_cast<size_t>(b) * L + 5 * t;
-    float xv[10], z[16];
+  const long long m_first = static_cast<long long>(blockIdx.x) * kL0Warps + warp;
+  unsigned char* my_ring = l0wg_ring + warp * kL0WgStages * kL0WgStageBytes;
+  const uint32_t ring = ptx::smem_u32(my_ring);
+  auto prefetch = [&](long long m, int slot) {
+    if (m < rows) {
+      const int b = static_cast<int>(m / P0), t = static_cast<int>(m % P0);
+      if (t < T0) {
+        const uint32_t dst = ring + static_cast<uint32_t>(slot * kL0WgStageBytes);
+        const char* zr = reinterpret_cast<const char*>(dz + m * kC);
+        cp_async16(dst + lane * 16, zr + lane * 16);
+        cp_async16(dst + 512 + lane * 16, zr + 512 + lane * 16);
+        if (lane < 10) cp_async4(dst + kC * 2 + lane * 4, x + static_cast<size_t>(b) * L + 5 * t + lane);
+      }
+    }
+    cp_async_commit();
+  };
 #pragma unroll
-    for (int k = 0; k < 10; ++k) xv[k] = __ldg(xw + k);
-    const uint4* zr = reinterpret_cast<const uint4*>(dz + m * kC);
-    unpack_bf16x8(__ldg(zr + lane), *reinterpret_cast<float(*)[8]>(&z[0]));
-    unpack_bf16x8(__ldg(zr + 32 + lane), *reinterpret_cast<float(*)[8]>(&z[8]));
+  for (int s = 0; s < kL0WgStages - 1; ++s) prefetch(m_first + s * warps_total, s);
+  int slot = 0;
+  for (long long m = m_first; m < rows; m += warps_total) {
+    prefetch(m + (kL0WgStages - 1) * warps_total, (slot + kL0WgStages - 1) % kL0WgStages);
+    cp_async_wait<kL0WgStages - 1>();
+    __syncwarp();  // the sample window was copied by lanes 0..9 and is read by every lane
+    const unsigned char* st = my_ring + slot * kL0WgStageBytes;
+    slot = (slot + 1) % kL0WgStages;
+    if (static_cast<int>(m % P0) >= T0) continue;
+    float xv[10], z[16];
+    const float* xs = reinterpret_cast<const float*>(st + kC * 2);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) xv[k] = xs[k];
+    const uint4* zr = reinterpret_cast<const uint4*>(st);
+    unpack_bf16x8(zr[lane], *reinterpret_cast<float(*)[8]>(&z[0]));
+    unpack_bf16x8(zr[32 + lane], *reinterpret_cast<float(*)[8]>(&z[8]));
 #pragma unroll
     for (int j = 0; j < 16; ++j)
 #pragma unroll
       for (int k = 0; k < 10; ++k) acc[j][k] = fmaf(z[j], xv[k], acc[j][k]);
+    __syncwarp();  // every lane has read the window before a later prefetch may overwrite this slot
   }
+  cp_async_wait<0>();
   // reduce across the CTA's warps through shared memory, two channels (20 values per lane) at a time
 #pragma unroll
   for (int part = 0; part < 8; ++part) {
@@ -1844,7 +1929,17 @@ int nrse_ln_gelu_bwd(const void* dout, int dout_dtype, const void* xhat, const f
   a.dgamma = dgamma; a.dbeta = dbeta; a.rows = rows; a.P = P; a.T = T;
   const long long want = ceil_div(static_cast<long long>(rows), static_cast<long long>(kLnBwdWarps));
   const unsigned grid = static_cast<unsigned>(want < 4 * kNumSMs ? want : 4 * kNumSMs);
-  ln_gelu_bwd_kernel<<<grid, kLnBwdThreads, 0, as_stream(stream)>>>(a);
+  if (a.dout_f32) {
+    ln_gelu_bwd_kernel<true><<<grid, kLnBwdThreads, 0, as_stream(stream)>>>(a);
+  } else {
+    static bool attr_set = false;  // benign race: idempotent attribute
+    if (!attr_set) {
+      NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kLnRingBytes));
+      attr_set = true;
+    }
+    ln_gelu_bwd_kernel<false><<<grid, kLnBwdThreads, kLnRingBytes, as_stream(stream)>>>(a);
+  }
   NRSE_CHECK_LAUNCH();
   return NRSE_OK;
 }
@@ -1856,8 +1951,13 @@ int nrse_conv_layer0_wgrad(const float* x, const void* dz0, float* dw0, int B, i
   const long long rows = static_cast<long long>(B) * P0;
   const long long want = ceil_div(rows, static_cast<long long>(kL0Warps));
   const unsigned grid = static_cast<unsigned>(want < kNumSMs ? want : kNumSMs);
-  layer0_wgrad_kernel<<<grid, kL0Threads, 0, as_stream(stream)>>>(x, reinterpret_cast<const __nv_bfloat16*>(dz0), dw0, B,
-                                                                  L, T0, P0);
+  static bool attr_set = false;  // benign race: idempotent attribute
+  if (!attr_set) {
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(layer0_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0WgRingBytes));
+    attr_set = true;
+  }
+  layer0_wgrad_kernel<<<grid, kL0Threads, kL0WgRingBytes, as_stream(stream)>>>(
+      x, reinterpret_cast<const __nv_bfloat16*>(dz0), dw0, B, L, T0, P0);
   NRSE_CHECK_LAUNCH();
   return NRSE_OK;
 }
