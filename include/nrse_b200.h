@@ -245,7 +245,9 @@ int nrse_conv_layer_fwd(const void* act_prev, int64_t rows_prev, const void* w_p
                         const float* gamma, const float* beta, void* out, int out_dtype, int64_t rows_out,
                         nrse_stream_t stream);
 /* Tile decomposition of the tcgen05 kernel: 1 = one CTA owns all 512 channels of a 128-frame tile,
- * 2 = a 2-CTA cluster splits the channels and exchanges LayerNorm partials through DSMEM (default). */
+ * 2 = a 2-CTA cluster splits the channels and exchanges LayerNorm partials through DSMEM (default),
+ * 3 = as 2, but the inference forward of the GEMM layers runs the 2-SM UMMA kernel (tcgen05.mma.cta_group::2: the CTA
+ *     pair splits the FRAMES, each CTA stages half of the weight rows; same results to bf16 rounding, measured on par). */
 int nrse_conv_frontend_set_variant(int variant);
 /* Layer-0 kernel in LayerNorm mode: 0 = SIMT (warp per frame); 1 = tensor cores (hi/lo-split K=32 UMMA, LayerNorm +
  * GELU epilogue; always used by the training forward); 2 = tensor cores with LayerNorm folded into the GEMM operands

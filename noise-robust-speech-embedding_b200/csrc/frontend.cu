@@ -325,6 +325,8 @@ struct EpiCtx {
   bool pre_stats;           // LayerNorm statistics supplied by the caller (layer 0): skip pass 1 and the exchange
   float pre_mean, pre_rstd;
   int gb_pair_off;          // first (gamma, beta) PAIR index of this thread's columns (0 unless the columns are split)
+  uint32_t stats_signal_bar;   // 0: signal the peer's copy of bar_stats; else the shared::cluster barrier to signal
+  uint32_t tmem_empty_cluster; // 0: bar_tmem_empty is local; else arrive on this shared::cluster barrier instead
 };
 
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction) --------------
@@ -438,7 +440,8 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
     float m2 = fmaxf(sum2 - sum1 * sum1 * kInvN, 0.f);
     if constexpr (kClusterN == 2) {
       // exchange (mean, M2) of my 256 channels with the peer CTA that holds the other 256 (Chan et al.)
-      ptx::st_async_f2(ptx::mapa(e.stats_slot, e.peer), mean_c, m2, ptx::mapa(e.bar_stats, e.peer));
+      ptx::st_async_f2(ptx::mapa(e.stats_slot, e.peer), mean_c, m2,
+                       e.stats_signal_bar ? e.stats_signal_bar : ptx::mapa(e.bar_stats, e.peer));
       ptx::mbar_wait(e.bar_stats, e.stats_parity);
       const float2 o = *e.stats_local;
       const float delta = mean_c - o.x;
@@ -519,7 +522,8 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
       ptx::tmem_ld_wait();
       if (c + 1 == kChunks) {  // this thread's columns are read: hand the accumulator back to the MMA warp
         ptx::tc_fence_before();
-        ptx::mbar_arrive(e.bar_tmem_empty);
+        if (e.tmem_empty_cluster) ptx::mbar_arrive_cluster(e.tmem_empty_cluster);
+        else ptx::mbar_arrive(e.bar_tmem_empty);
       }
       emit32(ra, c);
     }
@@ -534,7 +538,8 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
         ptx::tmem_ld32(taddr + (c + 2) * 32, ra);
       } else {  // accumulator fully read: hand it back to the MMA warp
         ptx::tc_fence_before();
-        ptx::mbar_arrive(e.bar_tmem_empty);
+        if (e.tmem_empty_cluster) ptx::mbar_arrive_cluster(e.tmem_empty_cluster);
+        else ptx::mbar_arrive(e.bar_tmem_empty);
       }
       emit32(rb, c + 1);
     }
@@ -747,6 +752,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ec.pre_mean = 0.f;
       ec.pre_rstd = 1.f;
       ec.gb_pair_off = 0;
+      ec.stats_signal_bar = 0;
+      ec.tmem_empty_cluster = 0;
       epilogue_row<kClusterN, kSave>(ec);
     }
   }
@@ -758,6 +765,318 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =========================================================================================================
+// 2-SM UMMA variant of the forward GEMM layer (tcgen05.mma.cta_group::2, M = 256).
+// The pair of CTAs owns 256 consecutive output frames and walks them as two work units, channels [0, 256) then [256, 512):
+// for a unit each CTA stages its own 128 rows of A and HALF (128) of the unit's 256 weight rows -- 32 KB per k-block
+// instead of the 1-SM kernel's 48 KB for the same 128 x 256 x 64 MACs per CTA, so six stages fit the ring instead of
+// four and the bytes entering the SM drop by a third: the L2 / HBM latency that bounds the 1-SM kernel (tensor pipe 72 %
+// active) is covered.  A CTA's TMEM holds its 128 frames x all 512 channels, one 256-column buffer per unit: LayerNorm
+// becomes CTA-local, epilogue team h owns buffer h, and the two teams exchange their partial statistics through the CTA's
+// own shared memory with the same st.async + mbarrier messages the 1-SM kernel sends to its peer CTA.  Team 0's statistics
+// pass overlaps the MMAs of unit 1; the normalise + GELU passes of both teams overlap the next frames' MMAs only from the
+// moment buffer 0 is released (~6 k cycles after unit 1 completes, vs ~26 k cycles of MMA per 256 frames).
+// =========================================================================================================
+// Epilogue of the 2-SM kernel for one frame (= one thread).  A CTA's TMEM holds the frame's 512 channels as two 256-column
+// buffers that complete one after the other; BOTH epilogue teams work on BOTH buffers, each on its half of the columns
+// (team t: channels [128 t, 128 t + 128) of buffer 0 and [256 + 128 t, ...) of buffer 1), so that after the second buffer
+// completes only a quarter of the row's statistics and an eighth of its normalise + GELU work stand between the MMA warp
+// and the release of buffer 0.
+struct Epi2Ctx {
+  uint32_t taddr0, taddr1;        // TMEM lane quadrant + first column of this thread's slice in buffer 0 / 1
+  uint32_t bar_full0, bar_full1;  // accumulator-complete barriers (local), waited with `parity`
+  uint32_t bar_empty0, bar_empty1;           // local accumulator-drained barriers (leader CTA) ...
+  uint32_t empty0_cluster, empty1_cluster;   // ... or their shared::cluster addresses in the leader (peer CTA), else 0
+  uint32_t parity;
+  uint32_t stats_slot;            // where this thread writes its (mean, M2): the partner team's slot of this row
+  const float2* stats_local;      // where the partner's (mean, M2) arrives
+  uint32_t bar_stats, stats_signal_bar;
+  bool arm, has_norm, store, out_f32;
+  const float* s_gamma;           // [512] in shared memory
+  const float* s_beta;            // [512]
+  int ch0, ch1;                   // first channel of this thread's slice in buffer 0 / 1
+  void* out_row;                  // this frame's output row (channel 0)
+};
+
+__device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
+  constexpr int kChunks = 4;  // 128 columns per buffer per thread
+  uint32_t ra[32], rb[32];
+  auto release = [&](uint32_t local, uint32_t cluster) {
+    ptx::tc_fence_before();
+    if (cluster) ptx::mbar_arrive_cluster(cluster);
+    else ptx::mbar_arrive(local);
+  };
+  // walk the 4 chunks of one buffer slice with two TMEM loads in flight; `last` runs once the slice is in registers
+  auto walk = [&](uint32_t taddr, auto&& body, auto&& last) {
+    ptx::tmem_ld32(taddr, ra);
+#pragma unroll 1
+    for (int c = 0; c < kChunks; c += 2) {
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld32(taddr + (c + 1) * 32, rb);
+      body(ra, c);
+      ptx::tmem_ld_wait();
+      if (c + 2 < kChunks) ptx::tmem_ld32(taddr + (c + 2) * 32, ra);
+      else last();
+      body(rb, c + 1);
+    }
+  };
+  ptx::mbar_wait(e.bar_full0, e.parity);
+  ptx::tc_fence_after();
+  float mean = 0.f, rstd = 1.f;
+  if (e.has_norm) {
+    if (e.arm) ptx::mbar_arrive_expect_tx(e.bar_stats, kBlockM * 8);  // 128 partner rows x (mean, M2)
+    // pass 1: shifted sums over this thread's 2 x 128 channels (shift = its first accumulator: no cancellation)
+    f2 s1 = f2_make(0.f, 0.f), s2 = s1, nshift = s1;
+    float shift = 0.f;
+    bool first = true;
+    auto stats32 = [&](const uint32_t (&r)[32], int) {
+      if (first) {
+        shift = __uint_as_float(r[0]);
+        nshift = f2_make(-shift, -shift);
+        first = false;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const f2 d = f2_add(f2_bits(r[2 * j], r[2 * j + 1]), nshift);
+        s1 = f2_add(s1, d);
+        s2 = f2_fma(d, d, s2);
+      }
+    };
+    walk(e.taddr0, stats32, [] {});
+    ptx::mbar_wait(e.bar_full1, e.parity);
+    ptx::tc_fence_after();
+    walk(e.taddr1, stats32, [] {});
+    float s1a, s1b, s2a, s2b;
+    f2_split(s1, s1a, s1b);
+    f2_split(s2, s2a, s2b);
+    const float sum1 = s1a + s1b, sum2 = s2a + s2b;
+    constexpr float kInvN = 1.0f / 256.0f;
+    float mean_c = shift + sum1 * kInvN;
+    float m2 = fmaxf(sum2 - sum1 * sum1 * kInvN, 0.f);
+    // exchange (mean, M2) of my 256 channels with the partner team's thread of the same frame (Chan et al.)
+    ptx::st_async_f2(e.stats_slot, mean_c, m2, e.stats_signal_bar);
+    ptx::mbar_wait(e.bar_stats, e.parity);
+    const float2 o = *e.stats_local;
+    const float delta = mean_c - o.x;
+    m2 = m2 + o.y + delta * delta * 128.0f;
+    mean = 0.5f * (mean_c + o.x);
+    rstd = rsqrtf(m2 * (1.0f / kC) + kNormEps);
+  } else {
+    ptx::mbar_wait(e.bar_full1, e.parity);
+    ptx::tc_fence_after();
+  }
+  // pass 2: normalise, affine, GELU, store
+  const f2 rstd2 = f2_make(rstd, rstd);
+  const f2 nmr2 = f2_make(-mean * rstd, -mean * rstd);
+  int ch_base = e.ch0;
+  auto emit32 = [&](const uint32_t (&r)[32], int c) {
+    const int ch = ch_base + c * 32;
+    const f2* g2 = reinterpret_cast<const f2*>(e.s_gamma + ch);
+    const f2* b2 = reinterpret_cast<const f2*>(e.s_beta + ch);
+    uint32_t o16[16];
+    float o32[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      f2 x = f2_bits(r[2 * j], r[2 * j + 1]);
+      if (e.has_norm) x = f2_fma(f2_fma(x, rstd2, nmr2), g2[j], b2[j]);
+      float y0, y1;
+      f2_split(gelu2(x), y0, y1);
+      o16[j] = pack_bf16x2(y0, y1);
+      o32[2 * j] = y0;
+      o32[2 * j + 1] = y1;
+    }
+    if (e.store) {
+      if (e.out_f32) {
+        char* dst = reinterpret_cast<char*>(reinterpret_cast<float*>(e.out_row) + ch);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_global_256(dst + 32 * j, __float_as_uint(o32[8 * j]), __float_as_uint(o32[8 * j + 1]),
+                        __float_as_uint(o32[8 * j + 2]), __float_as_uint(o32[8 * j + 3]), __float_as_uint(o32[8 * j + 4]),
+                        __float_as_uint(o32[8 * j + 5]), __float_as_uint(o32[8 * j + 6]), __float_as_uint(o32[8 * j + 7]));
+      } else {
+        char* dst = reinterpret_cast<char*>(reinterpret_cast<__nv_bfloat16*>(e.out_row) + ch);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          st_global_256(dst + 32 * j, o16[8 * j], o16[8 * j + 1], o16[8 * j + 2], o16[8 * j + 3], o16[8 * j + 4],
+                        o16[8 * j + 5], o16[8 * j + 6], o16[8 * j + 7]);
+      }
+    }
+  };
+  walk(e.taddr0, emit32, [&] { release(e.bar_empty0, e.empty0_cluster); });  // buffer 0 read: next frames' unit 0 may start
+  ch_base = e.ch1;
+  walk(e.taddr1, emit32, [&] { release(e.bar_empty1, e.empty1_cluster); });
+}
+
+struct Gemm2Cfg {
+  static constexpr int kThreads = 64 + 2 * kEpiThreads;  // warp 0 TMA, warp 1 MMA (leader CTA issues), 2 epilogue teams
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB: this CTA's 128 frames
+  static constexpr int kBHalfRows = kUmmaN / 2;           // 128 of the 256 weight rows of one MMA
+  static constexpr int kBHalfBytes = kBHalfRows * kBlockK * 2;  // 16 KB
+  static constexpr int kStageBytes = kABytes + kBHalfBytes;
+  static constexpr int kGbOff = kStages * kStageBytes;    // per team: gamma[256] then beta[256]
+  static constexpr int kStatsOff = kGbOff + kC * 8;
+  static constexpr int kBarOff = kStatsOff + 4 * kBlockM * 8;
+  static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2;
+  static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr int kSmemBytes = kTmemPtrOff + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(Gemm2Cfg::kThreads, 1)
+conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                  const GemmArgs g) {
+  using Cfg = Gemm2Cfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  auto bar = [&](int i) { return smem_base + Cfg::kBarOff + 8u * static_cast<uint32_t>(i); };
+  const int kFull = 0, kEmpty = Cfg::kStages, kTmemFull = 2 * Cfg::kStages, kTmemEmpty = kTmemFull + 2,
+            kStats = kTmemEmpty + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + Cfg::kTmemPtrOff);
+  float2* s_gb = reinterpret_cast<float2*>(smem + Cfg::kGbOff);
+  float2* s_stats = reinterpret_cast<float2*>(smem + Cfg::kStatsOff);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_w);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(bar(kFull + s), 1);   // used in the leader only: one expect_tx arrive, bytes from both CTAs
+      ptx::mbar_init(bar(kEmpty + s), 1);  // multicast commit of the leader's MMA thread
+    }
+    for (int h = 0; h < 2; ++h) {
+      ptx::mbar_init(bar(kTmemFull + h), 1);                 // multicast commit
+      ptx::mbar_init(bar(kTmemEmpty + h), 4 * kEpiThreads);  // leader only: every epilogue thread of both CTAs
+    }
+    ptx::mbar_init(bar(kStats + 0), 1);
+    ptx::mbar_init(bar(kStats + 1), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(ptx::smem_u32(tmem_ptr_smem), 512);
+    ptx::tmem_relinquish_2sm();
+  }
+  const bool has_norm = g.gamma != nullptr;
+  for (int i = threadIdx.x; i < kC; i += Cfg::kThreads) {  // gamma[512] then beta[512]
+    reinterpret_cast<float*>(s_gb)[i] = has_norm ? g.gamma[i] : 1.f;
+    reinterpret_cast<float*>(s_gb)[kC + i] = has_norm ? g.beta[i] : 0.f;
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_super = (g.num_tiles + 1) / 2;  // 256 frames per CTA pair
+  const int first = static_cast<int>(blockIdx.x) / 2;
+  const int step = static_cast<int>(gridDim.x) / 2;
+  auto tile_of = [&](int sup) { return (g.reverse ? num_super - 1 - sup : sup) * 2 + static_cast<int>(cta_rank); };
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; all bytes complete on the LEADER's full barrier) ==========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int sup = first; sup < num_super; sup += step) {
+        const int m0 = tile_of(sup) * kBlockM;
+        for (int h = 0; h < 2; ++h) {
+          for (int kb = 0; kb < g.k_stages; ++kb) {
+            ptx::mbar_wait(bar(kEmpty + stage), phase ^ 1u);
+            const uint32_t full_leader = ptx::mapa(bar(kFull + stage), 0);
+            if (leader) ptx::mbar_arrive_expect_tx(bar(kFull + stage), 2 * Cfg::kStageBytes);
+            const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+            const uint32_t b_dst = a_dst + Cfg::kABytes;
+            const int tap = kb >> 3, c0 = (kb & 7) * kBlockK;
+            ptx::tma_load_3d_2sm(a_dst, &tmap_a, full_leader, c0, tap % g.stride, m0 + tap / g.stride);
+            ptx::tma_load_2d_2sm(b_dst, &tmap_w, full_leader, kb * kBlockK,
+                                 h * kUmmaN + static_cast<int>(cta_rank) * Cfg::kBHalfRows);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA drives the tensor cores of both SMs ========================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * kBlockM, kUmmaN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int sup = first; sup < num_super; sup += step, ++it) {
+        for (int h = 0; h < 2; ++h) {
+          // team h of both CTAs has drained buffer h
+          ptx::mbar_wait(bar(kTmemEmpty + h), (static_cast<uint32_t>(it) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          for (int kb = 0; kb < g.k_stages; ++kb) {
+            ptx::mbar_wait(bar(kFull + stage), phase);
+            ptx::tc_fence_after();
+            const uint32_t a_src = smem_base + stage * Cfg::kStageBytes;
+            const uint32_t b_src = a_src + Cfg::kABytes;
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t da = ptx::umma_desc_sw128(a_src + k * (kUmmaK * 2));
+              const uint64_t db = ptx::umma_desc_sw128(b_src + k * (kUmmaK * 2));
+              ptx::umma_bf16_2sm(tmem_base + h * kUmmaN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit_2sm(bar(kEmpty + stage), 3);  // frees the slot in both CTAs
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          }
+          ptx::umma_commit_2sm(bar(kTmemFull + h), 3);  // buffer h complete in both CTAs -> team h
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: both teams on both buffers, team t takes the t-th 128 columns of each (see epilogue_row_2sm) =====
+    const int team = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int it = 0;
+    for (int sup = first; sup < num_super; sup += step, ++it) {
+      const uint32_t acc_phase = static_cast<uint32_t>(it) & 1u;
+      const long long m = static_cast<long long>(tile_of(sup)) * kBlockM + row;
+      const int mine = team * 2 + static_cast<int>(acc_phase), theirs = (1 - team) * 2 + static_cast<int>(acc_phase);
+      Epi2Ctx ec;
+      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      ec.taddr0 = lane_base + static_cast<uint32_t>(team * 128);
+      ec.taddr1 = lane_base + static_cast<uint32_t>(kUmmaN + team * 128);
+      ec.bar_full0 = bar(kTmemFull + 0);
+      ec.bar_full1 = bar(kTmemFull + 1);
+      ec.bar_empty0 = bar(kTmemEmpty + 0);
+      ec.bar_empty1 = bar(kTmemEmpty + 1);
+      ec.empty0_cluster = leader ? 0u : ptx::mapa(bar(kTmemEmpty + 0), 0);
+      ec.empty1_cluster = leader ? 0u : ptx::mapa(bar(kTmemEmpty + 1), 0);
+      ec.parity = acc_phase;
+      // statistics exchange with the OTHER TEAM of this CTA: write into its slot, signal its barrier, wait on mine
+      ec.stats_slot = ptx::mapa(smem_base + Cfg::kStatsOff + static_cast<uint32_t>((theirs * kBlockM + row) * 8), cta_rank);
+      ec.stats_local = s_stats + mine * kBlockM + row;
+      ec.bar_stats = bar(kStats + team);
+      ec.stats_signal_bar = ptx::mapa(bar(kStats + (1 - team)), cta_rank);
+      ec.arm = row == 0;
+      ec.has_norm = has_norm;
+      ec.store = m < g.M_total;
+      ec.out_f32 = g.out_f32 != 0;
+      ec.s_gamma = reinterpret_cast<const float*>(s_gb);
+      ec.s_beta = reinterpret_cast<const float*>(s_gb) + kC;
+      ec.ch0 = team * 128;
+      ec.ch1 = kUmmaN + team * 128;
+      ec.out_row = g.out_f32 ? static_cast<void*>(reinterpret_cast<float*>(g.out) + m * kC)
+                             : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(g.out) + m * kC);
+      epilogue_row_2sm(ec);
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still touch it
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 
@@ -1057,6 +1376,8 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN, kSplit>::kThreads, 1) layer
       ec.pre_mean = pre.x;
       ec.pre_rstd = pre.y;
       ec.gb_pair_off = col0 / 2;
+      ec.stats_signal_bar = 0;
+      ec.tmem_empty_cluster = 0;
       ec.taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * Cfg::kNPC + col0);
       ec.bar_tmem_empty = bar(kTmemEmpty + buf);
       ec.stats_slot = 0;          // statistics exchange is not used here (pre_stats)
@@ -1561,12 +1882,12 @@ int make_tmap_a(CUtensorMap* m, const void* act_prev, int64_t rows_prev, int str
 }
 
 // B operand: packed weights [512, K] bf16, box = 256 output channels x 64 K
-int make_tmap_w(CUtensorMap* m, const void* w_packed, int K) {
+int make_tmap_w(CUtensorMap* m, const void* w_packed, int K, int box_rows = kUmmaN) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return NRSE_ERR_CUDA;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(kC)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
-  const cuuint32_t box[2] = {kBlockK, kUmmaN};
+  const cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1591,7 +1912,34 @@ int make_tmap_rows(CUtensorMap* m, const void* ptr, int64_t rows, int box_rows) 
 int g_tile_order = 1;   // 1: consecutive layers walk their tiles in opposite directions, so that every layer starts on the
                         // rows its producer wrote last (still in L2) instead of the ones it wrote first (long evicted); 0: all forward
 int g_l2_prefetch = 0;  // 1: producer bulk-prefetches the next tile's A rows into L2 (measured 2-3 % slower: off)
-int g_variant = 2;  // 1: single CTA per tile, 2: 2-CTA cluster splitting the channels (default)
+int g_variant = 2;  // 1: single CTA per tile, 2: 2-CTA cluster splitting the channels (default), 3: as 2, but the inference
+                    // forward of the GEMM layers runs the 2-SM UMMA kernel (conv_gemm2_kernel)
+
+int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const GemmArgs& g, cudaStream_t stream) {
+  static bool attr_set = false;  // benign race: the attribute is idempotent
+  if (!attr_set) {
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Gemm2Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int num_super = (g.num_tiles + 1) / 2;
+  const int max_groups = kNumSMs / 2;
+  const int groups = num_super < max_groups ? num_super : max_groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
+  cfg.blockDim = dim3(Gemm2Cfg::kThreads);
+  cfg.dynamicSmemBytes = Gemm2Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel, ta, tw, g));
+  return NRSE_OK;
+}
 
 template <int kClusterN, bool kSave = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmArgs& g, cudaStream_t stream) {
@@ -1715,7 +2063,7 @@ size_t nrse_conv_frontend_workspace_bytes(int B, int L) {
 }
 
 int nrse_conv_frontend_set_variant(int variant) {
-  if (variant != 1 && variant != 2) return NRSE_ERR_INVALID_ARG;
+  if (variant < 1 || variant > 3) return NRSE_ERR_INVALID_ARG;
   nrse::g_variant = variant;
   return NRSE_OK;
 }
@@ -1762,12 +2110,12 @@ static int layer0_fwd_impl(const float* x, const float* w0, const float* gamma, 
   const long long want = ceil_div(rows, static_cast<long long>(kL0Warps));
   const unsigned grid = static_cast<unsigned>(want < kNumSMs ? want : kNumSMs);
   if (norm_mode == NRSE_NORM_LAYER) {
-    if (xhat == nullptr && g_variant == 2) {
+    if (xhat == nullptr && g_variant >= 2) {
       if (g_layer0_variant == 2) return launch_layer0_tc<2, false, 1, true>(a, s);
       if (g_layer0_variant == 3) return launch_layer0_tc<2, false, 2, true>(a, s);
     }
-    if (xhat != nullptr) return g_variant == 2 ? launch_layer0_tc<2, true>(a, s) : launch_layer0_tc<1, true>(a, s);
-    if (g_layer0_variant >= 1) return g_variant == 2 ? launch_layer0_tc<2>(a, s) : launch_layer0_tc<1>(a, s);
+    if (xhat != nullptr) return g_variant >= 2 ? launch_layer0_tc<2, true>(a, s) : launch_layer0_tc<1, true>(a, s);
+    if (g_layer0_variant >= 1) return g_variant >= 2 ? launch_layer0_tc<2>(a, s) : launch_layer0_tc<1>(a, s);
     layer0_kernel<false><<<grid, kL0Threads, 0, s>>>(a);
     NRSE_CHECK_LAUNCH();
     return NRSE_OK;
@@ -1803,10 +2151,11 @@ static int layer_fwd_impl(const void* act_prev, int64_t rows_prev, const void* w
   if ((reinterpret_cast<uintptr_t>(act_prev) | reinterpret_cast<uintptr_t>(w_packed) |
        reinterpret_cast<uintptr_t>(out)) & 15u)
     return NRSE_ERR_INVALID_ARG;
+  const bool two_sm = g_variant == 3 && xhat == nullptr;
   CUtensorMap ta, tw;
   int rc = make_tmap_a(&ta, act_prev, rows_prev, stride);
   if (rc != NRSE_OK) return rc;
-  rc = make_tmap_w(&tw, w_packed, k * kC);
+  rc = make_tmap_w(&tw, w_packed, k * kC, two_sm ? Gemm2Cfg::kBHalfRows : kUmmaN);
   if (rc != NRSE_OK) return rc;
   GemmArgs g;
   g.gamma = gamma; g.beta = beta; g.out = out;
@@ -1826,9 +2175,10 @@ static int layer_fwd_impl(const void* act_prev, int64_t rows_prev, const void* w
   g.a_rows = rows_prev;
   g.l2_prefetch = g_l2_prefetch;
   g.reverse = reverse;
+  if (two_sm) return launch_gemm2(ta, tw, g, as_stream(stream));
   if (xhat != nullptr)
-    return g_variant == 2 ? launch_gemm<2, true>(ta, tw, g, as_stream(stream)) : launch_gemm<1, true>(ta, tw, g, as_stream(stream));
-  return g_variant == 2 ? launch_gemm<2>(ta, tw, g, as_stream(stream)) : launch_gemm<1>(ta, tw, g, as_stream(stream));
+    return g_variant >= 2 ? launch_gemm<2, true>(ta, tw, g, as_stream(stream)) : launch_gemm<1, true>(ta, tw, g, as_stream(stream));
+  return g_variant >= 2 ? launch_gemm<2>(ta, tw, g, as_stream(stream)) : launch_gemm<1>(ta, tw, g, as_stream(stream));
 }
 
 int nrse_conv_layer_fwd(const void* act_prev, int64_t rows_prev, const void* w_packed, int k, int stride,
@@ -2020,7 +2370,7 @@ int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even,
     g.a_ptr = reinterpret_cast<const char*>(dz);
     g.a_rows = rows_out;
     g.l2_prefetch = g_l2_prefetch;
-    rc = g_variant == 2 ? launch_gemm<2>(ta, tw, g, as_stream(stream)) : launch_gemm<1>(ta, tw, g, as_stream(stream));
+    rc = g_variant >= 2 ? launch_gemm<2>(ta, tw, g, as_stream(stream)) : launch_gemm<1>(ta, tw, g, as_stream(stream));
     if (rc != NRSE_OK) return rc;
   }
   return NRSE_OK;

@@ -1,4 +1,5 @@
-"""Graph-timed device time of layer 0 and the six GEMM layers at 64 x 4 s, for tuning knobs (L2 prefetch on/off)."""
+"""Graph-timed device time of layer 0 and the six GEMM layers at 64 x 4 s, for the GEMM kernel variants: 2 = 1-SM UMMA,
+CTA pair splits the channels (default); 3 = 2-SM UMMA (cta_group::2), CTA pair splits the frames."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -31,8 +32,8 @@ def gtime(fn, n=10):
     return e0.elapsed_time(e1) / n
 
 lib = _lib.load()
-for pf in (0, 1, 0, 1):
-    lib.nrse_conv_frontend_set_l2_prefetch(pf)
+for pf in (2, 3, 2, 3):
+    ops.set_frontend_variant(pf)
     act = ops.conv_layer0(x, w[0], g[0], b[0], "layer").view(B * P[0], 512)
     t0 = gtime(lambda: ops.conv_layer0(x, w[0], g[0], b[0], "layer"))
     out = [f"l0={t0*1e3:.0f}us"]
@@ -44,4 +45,5 @@ for pf in (0, 1, 0, 1):
         f = 2.0 * B * T[i] * 512 * 512 * K[i]
         tot += t; fl += f
         out.append(f"l{i}={t*1e3:.0f}us/{f/(t*1e-3)/1e12:.0f}TF")
-    print(f"prefetch={pf}: " + " ".join(out) + f"  | gemm total {tot*1e3:.0f}us {fl/(tot*1e-3)/1e12:.0f} TF")
+    print(f"variant={pf}: " + " ".join(out) + f"  | gemm total {tot*1e3:.0f}us {fl/(tot*1e-3)/1e12:.0f} TF")
+ops.set_frontend_variant(2)

@@ -11,7 +11,7 @@ from nrse_b200 import ops
 from nrse_b200.utils import synthetic
 
 pytestmark = pytest.mark.gpu
-VARIANTS = (1, 2)
+VARIANTS = (1, 2, 3)  # 1-CTA tiles, CTA pair splitting the channels (default), 2-SM UMMA pair splitting the frames
 
 
 def _layer_params(layers, dev):
@@ -71,7 +71,7 @@ def test_layer0_tc_is_fp32_class(dev):
     assert float(diff.max()) <= 2 ** -6 * float(ref.abs().max()) and float((diff > 0).float().mean()) < 0.10
 
 
-@pytest.mark.parametrize("variant", VARIANTS, ids=["v1", "v2"])
+@pytest.mark.parametrize("variant", VARIANTS, ids=["v1", "v2", "v3-2sm"])
 @pytest.mark.parametrize("k,rows_out,norm", [(3, 128, True), (2, 128, True), (3, 1000, True), (2, 777, False),
                                              (3, 128 * 149 + 5, True)])
 def test_gemm_layer_vs_torch(dev, variant, k, rows_out, norm):
@@ -103,7 +103,7 @@ def test_gemm_layer_vs_torch(dev, variant, k, rows_out, norm):
     ops.set_frontend_variant(2)
 
 
-@pytest.mark.parametrize("variant", VARIANTS, ids=["v1", "v2"])
+@pytest.mark.parametrize("variant", VARIANTS, ids=["v1", "v2", "v3-2sm"])
 @pytest.mark.parametrize("mode", ["layer", "group"])
 def test_frontend_golden(dev, golden, variant, mode):
     ops.set_frontend_variant(variant)
