@@ -317,8 +317,15 @@ def main_gpu(args):
 
     # ---- per-kernel rooflines (rank 0 only, outside the headline timing) -------------------------------------------
     if rank == 0:
+        # the per-kernel numbers are "kernel timed alone" numbers: let the board leave the power-capped state of the long
+        # timed regions above first, and record the clocks this section actually ran at
+        torch.cuda.synchronize()
+        time.sleep(2.0)
+        ksampler = ClockSampler(local_rank)
+        ksampler.start()
         line.update(kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w, gammas, betas, packed,
                                      T, P, max(3, min(args.steps, 10))))
+        line["kernel_clocks"] = ksampler.stop()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cv, cdt, cores, threads = run_cpu(16, 4, 1)
         line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
