@@ -383,8 +383,12 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
     for i in range(1, 7):
         k = CONV_KERNEL[i]
         inp = act
+        # the per-layer entry point cannot know the layer: select what nrse_conv_frontend_fwd runs for it (default
+        # variant 4: the 2-SM UMMA kernel for layers 1-2, the 1-SM CTA-pair kernel for layers 3-6)
+        ops.set_frontend_variant(3 if i <= 2 else 2)
         t = ev_time(lambda: ops.conv_layer(inp, packed[i - 1], k, gammas[i], betas[i]))
         act = ops.conv_layer(inp, packed[i - 1], k, gammas[i], betas[i])
+        ops.set_frontend_variant(ops.DEFAULT_FRONTEND_VARIANT)
         flops = 2.0 * B * T[i] * 512 * (512 * k)  # algorithmic: valid frames only
         gemm_ms += t
         gemm_flops += flops
@@ -397,7 +401,7 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
         with open(tpath) as f:
             tj = json.load(f)
         traffic, traffic_src = tj["traffic_bytes_six_launches"], tj["source"]
-    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (layers 1-6, tcgen05 implicit GEMM + LayerNorm + GELU)",
+    roofline = {"bound": "tensor", "kernel": "conv_gemm2_kernel (layers 1-2, 2-SM UMMA) + conv_gemm_kernel (layers 3-6): tcgen05 implicit GEMM + LayerNorm + GELU",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_unit": "bytes per 6 launches (one view)", "traffic_source": traffic_src,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed back to back)",

@@ -245,13 +245,15 @@ int nrse_conv_layer_fwd(const void* act_prev, int64_t rows_prev, const void* w_p
                         const float* gamma, const float* beta, void* out, int out_dtype, int64_t rows_out,
                         nrse_stream_t stream);
 /* Tile decomposition of the tcgen05 kernel: 1 = one CTA owns all 512 channels of a 128-frame tile,
- * 2 = a 2-CTA cluster splits the channels and exchanges LayerNorm partials through DSMEM (default),
+ * 2 = a 2-CTA cluster splits the channels and exchanges LayerNorm partials through DSMEM,
  * 3 = as 2, but the inference forward of the GEMM layers runs the 2-SM UMMA kernel (tcgen05.mma.cta_group::2: the CTA
- *     pair splits the FRAMES, each CTA stages half of the weight rows; same results to bf16 rounding, measured on par). */
+ *     pair splits the FRAMES, each CTA stages half of the weight rows; same results to bf16 rounding),
+ * 4 = as 2, but nrse_conv_frontend_fwd runs layers 1 and 2 on the 2-SM kernel (default; the choice never depends on the
+ *     batch, so an utterance's features do not depend on what else is in the batch). */
 int nrse_conv_frontend_set_variant(int variant);
 /* Layer-0 kernel in LayerNorm mode: 0 = SIMT (warp per frame); 1 = tensor cores (hi/lo-split K=32 UMMA, LayerNorm +
  * GELU epilogue; always used by the training forward); 2 = tensor cores with LayerNorm folded into the GEMM operands
- * (K=48, GELU-only epilogue; inference forward, default); 3 = 2 with 16 epilogue warps (tuning knob, slower). */
+ * (K=48, GELU-only epilogue; inference forward); 3 = 2 with 16 epilogue warps (default). */
 int nrse_conv_frontend_set_layer0_variant(int variant);
 /* Tile order of the GEMM layers inside nrse_conv_frontend_fwd / _fwd_train: 1 (default) = consecutive layers walk their
  * tiles in opposite directions (each layer starts on the rows its producer wrote last, which are still in L2);

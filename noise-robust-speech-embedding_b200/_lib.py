@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libnrse_b200.so")
+# NRSE_B200_LIB: another build of the SAME library (A/B timing of kernel changes on one box, scripts/ only)
+LIB_PATH = os.environ.get("NRSE_B200_LIB") or os.path.join(_HERE, "csrc", "libnrse_b200.so")
 
 NRSE_OK = 0
 DTYPE_F32 = 0

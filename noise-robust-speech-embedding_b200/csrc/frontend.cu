@@ -28,6 +28,7 @@
 //   the data-gradient GEMM of the backward; see the "Backward" block further down for the other backward kernels.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -90,6 +91,7 @@ struct L0Args {
   int B, L, T0, P0;
   __nv_bfloat16* xhat;  // nullable (training forward, LayerNorm mode): normalised pre-affine values [B*P0, 512]
   float* rstd;          // nullable: [B*P0]
+  int exp_flags;        // timing experiments (NRSE_EXPERIMENT): 1 = no output stores
 };
 
 // lane owns channels [8*lane, 8*lane+8) and [256 + 8*lane, 256 + 8*lane + 8)
@@ -259,6 +261,44 @@ constexpr int kBlockK = 64;  // 64 bf16 = one 128-byte swizzled row
 constexpr int kUmmaK = 16;
 constexpr int kUmmaN = 256;
 constexpr int kEpiThreads = 128;  // one epilogue team = 4 warps = the 4 TMEM lane quadrants
+// Output path of the epilogues.  One thread owns one output row, so direct global stores are 32 rows x 32 bytes per warp
+// instruction: one L1 wavefront and one partial L2 line write per THREAD.  Measured (NRSE_EXPERIMENT=1, stores skipped):
+// that store path, not the arithmetic, is what the epilogues cost -- the GEMM layers run at 1.60 PFLOP/s without it against
+// 1.17 with it, layer 0 at 122 us against 224.  So bf16 outputs are staged: every epilogue warp owns a 2 KB shared-memory
+// buffer (32 rows x 32 channels, 64-byte rows, TMA's 64-byte swizzle so that the 16-byte row-owner writes are
+// conflict-free), and lane 0 hands it to the TMA engine (cp.async.bulk.tensor store), which writes whole sectors without
+// touching the LSU pipe.  The buffer is single: the wait for the engine to have READ it sits behind the arithmetic of the
+// next 32 channels, so registers are the second buffer.
+constexpr int kOutStageCols = 32;
+constexpr int kOutStageBytes = 32 * kOutStageCols * 2;
+struct OutStage {
+  const CUtensorMap* tmap;  // nullptr: direct global stores (fp32 outputs)
+  uint32_t smem;            // this warp's staging buffer (shared window, 1024-byte aligned)
+  int col0;                 // tensor-map column of this thread's first channel
+  int row0;                 // tensor-map row of lane 0 of this warp
+  int lane;
+  bool active;              // false: nothing of this warp is to be stored (rows past the end, timing experiments)
+  uint64_t policy;          // L2 eviction priority of the stored lines: evict-first -- a layer's output is far larger than
+                            // L2 (839 / 419 MB), so keeping it resident only delays its write-back and displaces the
+                            // operand stream (measured: GEMM layers -2 %, layer 0 -15 %); 0 = none (NRSE_EXPERIMENT 8)
+  int exp_flags;            // timing experiments: 64 = no proxy fence, 128 = no wait for the engine's read
+};
+// one 32-channel chunk of the warp's 32 rows: registers -> staging buffer -> TMA store (rows past the tensor's end are clipped)
+__device__ __forceinline__ void out_stage_store(const OutStage& o, const uint32_t (&v)[16], int col) {
+  if (o.lane == 0 && !(o.exp_flags & 128)) ptx::bulk_wait_read<0>();  // the engine has read the previous chunk
+  __syncwarp();
+  const uint32_t row = o.smem + static_cast<uint32_t>(o.lane) * 64u, sw = (static_cast<uint32_t>(o.lane) >> 1) & 3u;
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j)
+    ptx::st_shared_v4(row + ((j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  if (!(o.exp_flags & 64)) ptx::fence_proxy_async_smem();
+  __syncwarp();
+  if (o.lane == 0 && o.active) {
+    if (o.policy) ptx::tma_store_2d_hint(o.tmap, o.smem, o.col0 + col, o.row0, o.policy);
+    else ptx::tma_store_2d(o.tmap, o.smem, o.col0 + col, o.row0);
+    ptx::bulk_commit();
+  }
+}
 
 template <int kClusterN>
 struct GemmCfg {
@@ -273,7 +313,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   // after the stage ring: gamma/beta (float2 per channel), LN partials (2 teams x 2 slots x 128 rows x float2),
   // mbarriers, TMEM base address
-  static constexpr int kGbOff = kStages * kStageBytes;
+  static constexpr int kOutOff = kStages * kStageBytes;   // one output staging buffer per epilogue warp (see OutStage)
+  static constexpr int kGbOff = kOutOff + kTeams * 4 * kOutStageBytes;
   static constexpr int kStatsOff = kGbOff + kNPC * 8;
   static constexpr int kBarOff = kStatsOff + 4 * kBlockM * 8;
   static constexpr int kNumBars = 2 * kStages + 2 * kAccBufs + 2;
@@ -304,6 +345,8 @@ struct GemmArgs {
   long long a_rows;
   int l2_prefetch;
   int reverse;  // 1: walk the tiles from the last to the first (see g_tile_order)
+  int exp_flags;  // timing experiments (NRSE_EXPERIMENT, wrong results): 1 = no output stores, 2 = no statistics pass,
+                  // 4 = all output stores into the same 16 MB
 };
 
 // ---- epilogue of one accumulator row (shared by the GEMM layers and the tensor-core layer 0) ----------------
@@ -327,6 +370,7 @@ struct EpiCtx {
   int gb_pair_off;          // first (gamma, beta) PAIR index of this thread's columns (0 unless the columns are split)
   uint32_t stats_signal_bar;   // 0: signal the peer's copy of bar_stats; else the shared::cluster barrier to signal
   uint32_t tmem_empty_cluster; // 0: bar_tmem_empty is local; else arrive on this shared::cluster barrier instead
+  OutStage ost;             // bf16 output through the staging buffer + TMA store (ost.tmap != nullptr)
 };
 
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction) --------------
@@ -360,42 +404,66 @@ __device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
   return d;
 }
 
-// Exact (erf) GELU of two values with ONE MUFU each:
-//   gelu(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2) = 0.5 x + |x| (0.5 - 0.5 e),   e = erfc(u / sqrt 2) = 2^-q(u),  u = |x|,
-//   q(u) = u (c0 + c1 u + .. + c4 u^4)
-// q is a degree-5 fit of -log2 erfc(u/sqrt2) on [0, 5.6] (max abs error of erfc 6.5e-7, tests/test_oracle_golden.py
-// pins it against math.erfc); beyond 5.6 it keeps growing (q(7) = 40, q(22) = 1765), so e underflows to 0 by itself and no
-// clamp is needed.  The epilogues are bound by instruction DISPATCH (packed f32x2 and 16-lane ALU instructions take two
-// dispatch cycles each), so the form is chosen to avoid the ALU pipe: |x| is an FADD with an absolute-value operand
-// modifier (full-rate pipe) instead of FMNMX, and relu(x) is never formed -- 0.5 x + u h cancels to -0.5 u e for x < 0
-// with an absolute error below 1e-7 u.  NaN inputs propagate; +-inf is not expected behind a LayerNorm (-inf gives NaN).
-__device__ __forceinline__ f2 gelu2(f2 x) {
-  float x0, x1;
-  f2_split(x, x0, x1);
-  const f2 u = f2_make(fabsf(x0), fabsf(x1));
-  f2 p = f2_fma(u, f2_make(-0.0005235913558863103f, -0.0005235913558863103f),
-                f2_make(0.007414255291223526f, 0.007414255291223526f));
-  p = f2_fma(p, u, f2_make(-0.05259089171886444f, -0.05259089171886444f));
-  p = f2_fma(p, u, f2_make(-0.4592348039150238f, -0.4592348039150238f));
-  p = f2_fma(p, u, f2_make(-1.1510953903198242f, -1.1510953903198242f));
+// Exact (erf) GELU of two values with ONE MUFU each, written in the HALVED argument w = x / 2 (a = |w|):
+//   gelu(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2) = w + a (1 - e),   e = erfc(sqrt2 a) = 2^-q(a),   q(a) = a (c0 + c1 a + ..)
+// q is a fit of -log2 erfc(sqrt2 a) on [0, 2.8] that minimises the absolute error of gelu itself (weight a e ln 2):
+//   NRSE_GELU_DEG 5 (default): quintic q, 5 packed instructions, max |gelu error| 8.7e-7;
+//   NRSE_GELU_DEG 3:           cubic q, 3 packed instructions,  max |gelu error| 8.6e-5 (2 % of a bf16 ulp at 1) -- measured
+//                              no faster on the B200 (the epilogues are not instruction-bound), so unused;
+// tests/test_oracle_golden.py pins both against torch's erf GELU.  q keeps growing beyond the fit range (q(2.8) = 25.6,
+// q(6) > 126), so e flushes to 0 by itself: no clamp.
+// The epilogues are bound by instruction ISSUE (23.5 k warp instructions per 128 x 512 tile at IPC 1.9 before this form),
+// so everything that is not arithmetic on the value is moved out of the per-element path: the factor 1/2 lives in the
+// LayerNorm affine (shared memory holds gamma / 2 and beta / 2 -- exact, a power of two) or in the folded layer-0 operands,
+// |w| is an operand modifier of the packed instructions, relu(x) is never formed (w + a h cancels to -a e for x < 0 with an
+// absolute error below 1e-7 a).  NaN inputs propagate; +-inf is not expected behind a LayerNorm (-inf gives NaN).
+#ifndef NRSE_STATS_SHIFT
+#define NRSE_STATS_SHIFT 1  // 0 (timing experiments only): raw sums in the LayerNorm statistics pass
+#endif
+#ifndef NRSE_GELU_DEG
+#define NRSE_GELU_DEG 5
+#endif
+__device__ __forceinline__ f2 gelu2h(f2 w) {
+  float w0, w1;
+  f2_split(w, w0, w1);
+  const f2 a = f2_make(fabsf(w0), fabsf(w1));
+#define NRSE_F2C(v) f2_make(v, v)
+#if NRSE_GELU_DEG == 3
+  f2 p = f2_fma(a, NRSE_F2C(-0.2210327833890915f), NRSE_F2C(-1.9530425071716309f));
+  p = f2_fma(p, a, NRSE_F2C(-2.281832695007324f));
+#elif NRSE_GELU_DEG == 5
+  f2 p = f2_fma(a, NRSE_F2C(-0.015619270503520966f), NRSE_F2C(0.11517950147390366f));
+  p = f2_fma(p, a, NRSE_F2C(-0.4171730577945709f));
+  p = f2_fma(p, a, NRSE_F2C(-1.838383436203003f));
+  p = f2_fma(p, a, NRSE_F2C(-2.3020009994506836f));
+#else
+#error "NRSE_GELU_DEG must be 3 or 5"
+#endif
   float q0, q1;
-  f2_split(f2_mul(p, u), q0, q1);  // = -q(u)
+  f2_split(f2_mul(p, a), q0, q1);  // = -q(a)
   float e0, e1;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
-  const f2 h = f2_fma(f2_make(e0, e1), f2_make(-0.5f, -0.5f), f2_make(0.5f, 0.5f));
-  return f2_fma(u, h, f2_mul(x, f2_make(0.5f, 0.5f)));
+  const f2 h = f2_fma(f2_make(e0, e1), NRSE_F2C(-1.0f), NRSE_F2C(1.0f));
+#undef NRSE_F2C
+  return f2_fma(a, h, w);
 }
 
 // kColsDiv = 2 (layer 0 only, statistics supplied by the caller): this thread handles kNPC / 2 columns of its row, the
 // other half belongs to the twin team working on the same accumulator buffer.
-template <int kClusterN, bool kSave, int kColsDiv = 1>
+// kHalved (layer 0 with LayerNorm folded into the operands): the accumulator already holds w = (LN(z) gamma + beta) / 2,
+// the epilogue is GELU + store.  Otherwise pass 2 ALWAYS applies (x rstd - mean rstd) (gamma/2) + beta/2 -- without a
+// LayerNorm (GroupNorm-mode layers 1-6) the caller's shared memory holds gamma/2 = 0.5, beta/2 = 0 and (mean, rstd) stay
+// (0, 1), which is exact -- so the per-element path has no run-time branch (a predicated form cost 4 register moves per
+// pair of elements, a fifth of the pass).
+template <int kClusterN, bool kSave, int kColsDiv = 1, bool kHalved = false>
 __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
   constexpr int kNPC = kC / kClusterN;
   constexpr int kChunks = kNPC / 32 / kColsDiv;
   const uint32_t taddr = e.taddr;
-  const f2* s_gamma2 = reinterpret_cast<const f2*>(e.s_gb) + e.gb_pair_off;            // [kNPC/2] pairs of gamma
-  const f2* s_beta2 = reinterpret_cast<const f2*>(e.s_gb) + kNPC / 2 + e.gb_pair_off;  // [kNPC/2] pairs of beta
+  // [kNPC/4] quads of gamma/2, then of beta/2 (one 128-bit shared-memory load feeds two packed instructions)
+  const float4* s_gamma4 = reinterpret_cast<const float4*>(e.s_gb) + e.gb_pair_off / 2;
+  const float4* s_beta4 = reinterpret_cast<const float4*>(e.s_gb) + kNPC / 4 + e.gb_pair_off / 2;
   uint32_t ra[32], rb[32];  // two TMEM chunks in flight: the next load overlaps the math on the current one
   float mean = 0.f, rstd = 1.f;
 
@@ -416,7 +484,11 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
     auto stats32 = [&](const uint32_t (&r)[32]) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
+#if NRSE_STATS_SHIFT
         const f2 d = f2_add(f2_bits(r[2 * j], r[2 * j + 1]), nshift);
+#else
+        const f2 d = f2_bits(r[2 * j], r[2 * j + 1]);
+#endif
         s1 = f2_add(s1, d);
         s2 = f2_fma(d, d, s2);
       }
@@ -426,7 +498,7 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
       ptx::tmem_ld_wait();
       ptx::tmem_ld32(taddr + (c + 1) * 32, rb);
       if (c == 0) {
-        shift = __uint_as_float(ra[0]);
+        shift = NRSE_STATS_SHIFT ? __uint_as_float(ra[0]) : 0.f;
         nshift = f2_make(-shift, -shift);
       }
       stats32(ra);
@@ -466,22 +538,32 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
     [[maybe_unused]] uint32_t xh16[kSave ? 16 : 1];
     float o32[32];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      f2 x = f2_bits(r[2 * j], r[2 * j + 1]);
-      if (e.has_norm) {
-        x = f2_fma(x, rstd2, nmr2);
-        if constexpr (kSave) {
-          float h0, h1;
-          f2_split(x, h0, h1);
-          xh16[j] = pack_bf16x2(h0, h1);
-        }
-        x = f2_fma(x, s_gamma2[c * 16 + j], s_beta2[c * 16 + j]);
+    for (int jj = 0; jj < 8; ++jj) {
+      [[maybe_unused]] float4 g4, b4;
+      if constexpr (!kHalved) {
+        g4 = s_gamma4[c * 8 + jj];
+        b4 = s_beta4[c * 8 + jj];
       }
-      float y0, y1;
-      f2_split(gelu2(x), y0, y1);
-      o16[j] = pack_bf16x2(y0, y1);
-      o32[2 * j] = y0;
-      o32[2 * j + 1] = y1;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int j = 2 * jj + k;
+        f2 x = f2_bits(r[2 * j], r[2 * j + 1]);
+        if constexpr (!kHalved) {
+          x = f2_fma(x, rstd2, nmr2);
+          if constexpr (kSave) {
+            float h0, h1;
+            f2_split(x, h0, h1);
+            xh16[j] = pack_bf16x2(h0, h1);
+          }
+          x = k == 0 ? f2_fma(x, f2_make(g4.x, g4.y), f2_make(b4.x, b4.y))
+                     : f2_fma(x, f2_make(g4.z, g4.w), f2_make(b4.z, b4.w));
+        }
+        float y0, y1;
+        f2_split(gelu2h(x), y0, y1);
+        o16[j] = pack_bf16x2(y0, y1);
+        o32[2 * j] = y0;
+        o32[2 * j + 1] = y1;
+      }
     }
     if constexpr (kSave) {
       if (e.store && e.has_norm && e.xhat_row != nullptr) {
@@ -494,7 +576,13 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
         }
       }
     }
-    if (e.store) {
+    if (e.ost.tmap != nullptr) {
+      if (e.zero) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o16[j] = 0;
+      }
+      out_stage_store(e.ost, o16, c * 32);
+    } else if (e.store) {
       if (e.out_f32) {
         char* dst = reinterpret_cast<char*>(reinterpret_cast<float*>(e.out_row) + c * 32);
 #pragma unroll
@@ -552,16 +640,20 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
 // Mode-1 epilogue (data-gradient GEMM): the accumulator row goes out as bf16, no normalisation, no exchange.
 template <int kClusterN>
 __device__ __forceinline__ void epilogue_plain_row(uint32_t taddr, uint32_t bar_tmem_empty, bool store,
-                                                   __nv_bfloat16* out_row) {
+                                                   __nv_bfloat16* out_row, const OutStage& ost) {
   constexpr int kNPC = kC / kClusterN;
   constexpr int kChunks = kNPC / 32;
   uint32_t ra[32], rb[32];
   auto emit = [&](const uint32_t (&r)[32], int c) {
-    if (!store) return;
-    char* dst = reinterpret_cast<char*>(out_row + c * 32);
     uint32_t o[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+    if (ost.tmap != nullptr) {
+      out_stage_store(ost, o, c * 32);
+      return;
+    }
+    if (!store) return;
+    char* dst = reinterpret_cast<char*>(out_row + c * 32);
 #pragma unroll
     for (int j = 0; j < 2; ++j)
       st_global_256(dst + 32 * j, o[8 * j], o[8 * j + 1], o[8 * j + 2], o[8 * j + 3], o[8 * j + 4], o[8 * j + 5],
@@ -587,7 +679,7 @@ __device__ __forceinline__ void epilogue_plain_row(uint32_t taddr, uint32_t bar_
 template <int kClusterN, bool kSave>
 __global__ void __launch_bounds__(GemmCfg<kClusterN>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                 const GemmArgs g) {
+                 const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
   using Cfg = GemmCfg<kClusterN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment (in the shared window, which is what TMA/UMMA see)
@@ -597,6 +689,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = kClusterN == 2 ? ptx::cluster_ctarank() : 0u;
   const int n0 = static_cast<int>(cta_rank) * Cfg::kNPC;  // first channel owned by this CTA
+  long long dbg_c0 = 0;
+  unsigned long long dbg_t0 = 0;
+  if (g.exp_flags & 256) {  // timing experiment: report the SM clock this launch ran at
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
 
   auto bar = [&](int i) { return smem_base + Cfg::kBarOff + 8u * static_cast<uint32_t>(i); };
   const int kFull = 0, kEmpty = Cfg::kStages, kTmemFull = 2 * Cfg::kStages,
@@ -609,6 +707,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_w);
+    ptx::prefetch_tmap(&tmap_out);
     for (int s = 0; s < Cfg::kStages; ++s) {
       ptx::mbar_init(bar(kFull + s), 1);
       ptx::mbar_init(bar(kEmpty + s), 1);
@@ -626,9 +725,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     ptx::tmem_relinquish();
   }
   const bool has_norm = g.gamma != nullptr;
-  for (int i = threadIdx.x; i < Cfg::kNPC; i += Cfg::kThreads) {  // gamma[kNPC] then beta[kNPC]
-    reinterpret_cast<float*>(s_gb)[i] = has_norm ? g.gamma[n0 + i] : 1.f;
-    reinterpret_cast<float*>(s_gb)[Cfg::kNPC + i] = has_norm ? g.beta[n0 + i] : 0.f;
+  for (int i = threadIdx.x; i < Cfg::kNPC; i += Cfg::kThreads) {  // gamma[kNPC] / 2 then beta[kNPC] / 2 (see gelu2h)
+    reinterpret_cast<float*>(s_gb)[i] = has_norm ? 0.5f * g.gamma[n0 + i] : 0.5f;
+    reinterpret_cast<float*>(s_gb)[Cfg::kNPC + i] = has_norm ? 0.5f * g.beta[n0 + i] : 0.f;
   }
   ptx::tc_fence_before();
   if constexpr (kClusterN == 2) ptx::cluster_sync_all();  // peer barriers must be initialised before remote arrives
@@ -665,11 +764,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           // input frame of tap j for output frame m is stride*m + j = stride*(m + j/stride) + j%stride
           const int tap = kb >> 3, c0 = (kb & 7) * kBlockK;
           if (g.a_2d) ptx::tma_load_2d(a_dst, &tmap_a, bar(kFull + stage), c0, m0 + (tap == 0 ? g.a_row_off[0] : g.a_row_off[1]));
+          else if (g.exp_flags & 16) ptx::tma_load_3d_hint(a_dst, &tmap_a, bar(kFull + stage), c0, tap % g.stride, m0 + tap / g.stride, ptx::kL2EvictFirst);
           else ptx::tma_load_3d(a_dst, &tmap_a, bar(kFull + stage), c0, tap % g.stride, m0 + tap / g.stride);
 #pragma unroll
-          for (int h = 0; h < Cfg::kNumMma; ++h)
-            ptx::tma_load_2d(b_dst + h * (kUmmaN * kBlockK * 2), &tmap_w, bar(kFull + stage), kb * kBlockK,
-                             n0 + h * kUmmaN);
+          for (int h = 0; h < Cfg::kNumMma; ++h) {
+            if (g.exp_flags & 32)
+              ptx::tma_load_2d_hint(b_dst + h * (kUmmaN * kBlockK * 2), &tmap_w, bar(kFull + stage), kb * kBlockK,
+                                    n0 + h * kUmmaN, ptx::kL2EvictLast);
+            else
+              ptx::tma_load_2d(b_dst + h * (kUmmaN * kBlockK * 2), &tmap_w, bar(kFull + stage), kb * kBlockK,
+                               n0 + h * kUmmaN);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -725,11 +830,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::mbar_wait(bar(kTmemFull + buf), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * Cfg::kNPC);
+      // bf16 outputs leave through this warp's staging buffer and the TMA engine (tmap_out rows = output rows, also in
+      // mode 1, whose interleaved rows 2 m + parity are a tensor map with a doubled row stride)
+      OutStage ost;
+      ost.tmap = g.out_f32 ? nullptr : &tmap_out;
+      ost.smem = smem_base + Cfg::kOutOff + static_cast<uint32_t>((warp - 2) * kOutStageBytes);
+      ost.col0 = n0;
+      ost.row0 = static_cast<int>(m) - lane;
+      ost.lane = lane;
+      ost.active = ost.row0 < g.M_total && !(g.exp_flags & 1);
+      if (g.exp_flags & 4) ost.row0 &= 16383;  // timing experiment: every store lands in the same 16 MB (L2-resident)
+      ost.policy = (g.exp_flags & 8) ? 0ull : ptx::kL2EvictFirst;
+      ost.exp_flags = g.exp_flags;
 
       if (g.mode == 1) {
         const long long orow = m * g.out_row_mul + g.out_row_add;
-        epilogue_plain_row<kClusterN>(taddr, bar(kTmemEmpty + buf), m < g.M_total,
-                                      reinterpret_cast<__nv_bfloat16*>(g.out) + orow * kC + n0);
+        epilogue_plain_row<kClusterN>(taddr, bar(kTmemEmpty + buf), m < g.M_total && !(g.exp_flags & 1),
+                                      reinterpret_cast<__nv_bfloat16*>(g.out) + orow * kC + n0, ost);
         continue;
       }
       const int slot = team * 2 + static_cast<int>(acc_phase);  // double-buffered per team
@@ -743,8 +860,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ec.arm = row == 0;
       ec.peer = peer;
       ec.s_gb = s_gb;
-      ec.has_norm = has_norm;
-      ec.store = m < g.M_total;
+      ec.has_norm = has_norm && !(g.exp_flags & 2);
+      ec.store = m < g.M_total && !(g.exp_flags & 1);
       ec.zero = false;
       ec.out_f32 = g.out_f32 != 0;
       ec.out_row = g.out_f32 ? static_cast<void*>(reinterpret_cast<float*>(g.out) + m * kC + n0)
@@ -757,14 +874,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ec.gb_pair_off = 0;
       ec.stats_signal_bar = 0;
       ec.tmem_empty_cluster = 0;
+      ec.ost = ost;
       epilogue_row<kClusterN, kSave>(ec);
     }
+    if (lane == 0) ptx::bulk_wait<0>();  // this warp's output stores are complete before the CTA may exit
   }
 
   // ---- teardown -------------------------------------------------------------------------------------
   ptx::tc_fence_before();
   if constexpr (kClusterN == 2) ptx::cluster_sync_all();  // no CTA may exit while its peer can still write to it
   else __syncthreads();
+  if ((g.exp_flags & 256) && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    const long long c1 = clock64();
+    printf("[clk] tiles=%d cycles=%lld ns=%llu MHz=%.0f\n", g.num_tiles, c1 - dbg_c0, t1 - dbg_t0,
+           1e3 * static_cast<double>(c1 - dbg_c0) / static_cast<double>(t1 - dbg_t0));
+  }
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -802,6 +928,7 @@ struct Epi2Ctx {
   const float* s_beta;            // [512]
   int ch0, ch1;                   // first channel of this thread's slice in buffer 0 / 1
   void* out_row;                  // this frame's output row (channel 0)
+  OutStage ost;                   // bf16 output through the staging buffer + TMA store (col0 = 0)
 };
 
 __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
@@ -837,13 +964,17 @@ __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
     bool first = true;
     auto stats32 = [&](const uint32_t (&r)[32], int) {
       if (first) {
-        shift = __uint_as_float(r[0]);
+        shift = NRSE_STATS_SHIFT ? __uint_as_float(r[0]) : 0.f;
         nshift = f2_make(-shift, -shift);
         first = false;
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
+#if NRSE_STATS_SHIFT
         const f2 d = f2_add(f2_bits(r[2 * j], r[2 * j + 1]), nshift);
+#else
+        const f2 d = f2_bits(r[2 * j], r[2 * j + 1]);
+#endif
         s1 = f2_add(s1, d);
         s2 = f2_fma(d, d, s2);
       }
@@ -877,21 +1008,29 @@ __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
   int ch_base = e.ch0;
   auto emit32 = [&](const uint32_t (&r)[32], int c) {
     const int ch = ch_base + c * 32;
-    const f2* g2 = reinterpret_cast<const f2*>(e.s_gamma + ch);
-    const f2* b2 = reinterpret_cast<const f2*>(e.s_beta + ch);
+    const float4* g4p = reinterpret_cast<const float4*>(e.s_gamma + ch);  // gamma / 2, beta / 2: see epilogue_row
+    const float4* b4p = reinterpret_cast<const float4*>(e.s_beta + ch);
     uint32_t o16[16];
     float o32[32];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      f2 x = f2_bits(r[2 * j], r[2 * j + 1]);
-      if (e.has_norm) x = f2_fma(f2_fma(x, rstd2, nmr2), g2[j], b2[j]);
-      float y0, y1;
-      f2_split(gelu2(x), y0, y1);
-      o16[j] = pack_bf16x2(y0, y1);
-      o32[2 * j] = y0;
-      o32[2 * j + 1] = y1;
+    for (int jj = 0; jj < 8; ++jj) {
+      const float4 g4 = g4p[jj], b4 = b4p[jj];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int j = 2 * jj + k;
+        f2 x = f2_fma(f2_bits(r[2 * j], r[2 * j + 1]), rstd2, nmr2);
+        x = k == 0 ? f2_fma(x, f2_make(g4.x, g4.y), f2_make(b4.x, b4.y))
+                   : f2_fma(x, f2_make(g4.z, g4.w), f2_make(b4.z, b4.w));
+        float y0, y1;
+        f2_split(gelu2h(x), y0, y1);
+        o16[j] = pack_bf16x2(y0, y1);
+        o32[2 * j] = y0;
+        o32[2 * j + 1] = y1;
+      }
     }
-    if (e.store) {
+    if (e.ost.tmap != nullptr) {
+      out_stage_store(e.ost, o16, ch);
+    } else if (e.store) {
       if (e.out_f32) {
         char* dst = reinterpret_cast<char*>(reinterpret_cast<float*>(e.out_row) + ch);
 #pragma unroll
@@ -920,7 +1059,8 @@ struct Gemm2Cfg {
   static constexpr int kBHalfRows = kUmmaN / 2;           // 128 of the 256 weight rows of one MMA
   static constexpr int kBHalfBytes = kBHalfRows * kBlockK * 2;  // 16 KB
   static constexpr int kStageBytes = kABytes + kBHalfBytes;
-  static constexpr int kGbOff = kStages * kStageBytes;    // per team: gamma[256] then beta[256]
+  static constexpr int kOutOff = kStages * kStageBytes;   // one output staging buffer per epilogue warp (see OutStage)
+  static constexpr int kGbOff = kOutOff + 8 * kOutStageBytes;  // gamma[512] / 2 then beta[512] / 2
   static constexpr int kStatsOff = kGbOff + kC * 8;
   static constexpr int kBarOff = kStatsOff + 4 * kBlockM * 8;
   static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2;
@@ -930,7 +1070,7 @@ struct Gemm2Cfg {
 
 __global__ void __launch_bounds__(Gemm2Cfg::kThreads, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                  const GemmArgs g) {
+                  const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
   using Cfg = Gemm2Cfg;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -966,9 +1106,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     ptx::tmem_relinquish_2sm();
   }
   const bool has_norm = g.gamma != nullptr;
-  for (int i = threadIdx.x; i < kC; i += Cfg::kThreads) {  // gamma[512] then beta[512]
-    reinterpret_cast<float*>(s_gb)[i] = has_norm ? g.gamma[i] : 1.f;
-    reinterpret_cast<float*>(s_gb)[kC + i] = has_norm ? g.beta[i] : 0.f;
+  for (int i = threadIdx.x; i < kC; i += Cfg::kThreads) {  // gamma[512] / 2 then beta[512] / 2 (see gelu2h)
+    reinterpret_cast<float*>(s_gb)[i] = has_norm ? 0.5f * g.gamma[i] : 0.5f;
+    reinterpret_cast<float*>(s_gb)[kC + i] = has_norm ? 0.5f * g.beta[i] : 0.f;
   }
   ptx::tc_fence_before();
   ptx::cluster_sync_all();
@@ -1062,8 +1202,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       ec.bar_stats = bar(kStats + team);
       ec.stats_signal_bar = ptx::mapa(bar(kStats + (1 - team)), cta_rank);
       ec.arm = row == 0;
-      ec.has_norm = has_norm;
-      ec.store = m < g.M_total;
+      ec.has_norm = has_norm && !(g.exp_flags & 2);
+      ec.store = m < g.M_total && !(g.exp_flags & 1);
       ec.out_f32 = g.out_f32 != 0;
       ec.s_gamma = reinterpret_cast<const float*>(s_gb);
       ec.s_beta = reinterpret_cast<const float*>(s_gb) + kC;
@@ -1071,8 +1211,18 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       ec.ch1 = kUmmaN + team * 128;
       ec.out_row = g.out_f32 ? static_cast<void*>(reinterpret_cast<float*>(g.out) + m * kC)
                              : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(g.out) + m * kC);
+      ec.ost.tmap = g.out_f32 ? nullptr : &tmap_out;
+      ec.ost.smem = smem_base + Cfg::kOutOff + static_cast<uint32_t>((warp - 2) * kOutStageBytes);
+      ec.ost.col0 = 0;
+      ec.ost.row0 = static_cast<int>(m) - lane;
+      ec.ost.lane = lane;
+      ec.ost.active = ec.ost.row0 < g.M_total && !(g.exp_flags & 1);
+      if (g.exp_flags & 4) ec.ost.row0 &= 16383;
+      ec.ost.policy = (g.exp_flags & 8) ? 0ull : ptx::kL2EvictFirst;
+      ec.ost.exp_flags = g.exp_flags;
       epilogue_row_2sm(ec);
     }
+    if (lane == 0) ptx::bulk_wait<0>();  // this warp's output stores are complete before the CTA may exit
   }
 
   ptx::tc_fence_before();
@@ -1110,7 +1260,8 @@ struct L0tcCfg {
   static constexpr int kABytes = kBlockM * 128;  // 128-byte row pitch, K = 32 bf16 uses the first 64 bytes
   static constexpr int kWOff = kL0AStages * kABytes;
   static constexpr int kWBytes = kNPC * 128;
-  static constexpr int kGbOff = kWOff + kWBytes;
+  static constexpr int kOutOff = kWOff + kWBytes;               // one output staging buffer per epilogue warp (see OutStage)
+  static constexpr int kGbOff = kOutOff + kTeams * 4 * kOutStageBytes;
   static constexpr int kStatsOff = kGbOff + kNPC * 8;           // kL0PreSlots x 128 rows x (mean, rstd) from the builders
   static constexpr int kGramOff = kStatsOff + kL0PreSlots * kBlockM * 8;  // 10 channel-mean taps + 55 Gram entries
   static constexpr int kBarOff = kGramOff + 72 * 4;
@@ -1157,7 +1308,8 @@ __device__ __forceinline__ void l0_split1(float v, uint32_t& hi, uint32_t& lo) {
 // and the epilogue is GELU + store: no normalise FFMA2, no affine FFMA2, no gamma/beta shared-memory loads (the loads'
 // latency was the epilogue's main dependency stall).  All added operands get the same bf16 hi/lo split as the samples.
 template <int kClusterN, bool kSave, int kSplit = 1, bool kFold = false>
-__global__ void __launch_bounds__(L0tcCfg<kClusterN, kSplit>::kThreads, 1) layer0_tc_kernel(const L0Args a) {
+__global__ void __launch_bounds__(L0tcCfg<kClusterN, kSplit>::kThreads, 1)
+layer0_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const L0Args a) {
   static_assert(!(kFold && kSave), "the training forward needs the pre-affine activations: no folding");
   using Cfg = L0tcCfg<kClusterN, kSplit>;
   constexpr int kWords = kFold ? 24 : 16;  // 32-bit words (bf16 pairs) per operand row: K = 48 or 32
@@ -1197,7 +1349,8 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN, kSplit>::kThreads, 1) layer
   // (kFold: w = gamma * w, and K slots 30..34 = [g_hi g_hi g_lo b_hi b_lo] against A = [s_hi s_lo s_hi 1 1], s = -mean*rstd)
   for (int n = threadIdx.x; n < Cfg::kNPC; n += Cfg::kThreads) {
     float w[10];
-    const float gam = a.gamma[n0 + n], bet = a.beta[n0 + n];
+    // gamma / 2, beta / 2: the GELU epilogue works on the halved argument (gelu2h), exact for a power of two
+    const float gam = 0.5f * a.gamma[n0 + n], bet = 0.5f * a.beta[n0 + n];
 #pragma unroll
     for (int k = 0; k < 10; ++k) w[k] = __ldg(a.w + (n0 + n) * 10 + k) * (kFold ? gam : 1.0f);
     uint32_t hi[5], lo[5], words[kWords];
@@ -1391,14 +1544,24 @@ __global__ void __launch_bounds__(L0tcCfg<kClusterN, kSplit>::kThreads, 1) layer
       ec.peer = peer;
       ec.s_gb = s_gb;
       ec.has_norm = !kFold;  // folded: the accumulator already holds the normalised, affine-transformed value
-      ec.store = m < m_total;
+      ec.store = m < m_total && !(a.exp_flags & 1);
       ec.zero = static_cast<int>(m % a.P0) >= a.T0;  // pitch padding is written as zeros
       ec.out_f32 = false;
       ec.out_row = a.out + m * kC + n0 + col0;
       ec.xhat_row = a.xhat ? a.xhat + m * kC + n0 + col0 : nullptr;
       ec.rstd_out = (a.rstd && n0 == 0 && half == 0) ? a.rstd + m : nullptr;
-      epilogue_row<kClusterN, kSave, kSplit>(ec);
+      ec.ost.tmap = &tmap_out;
+      ec.ost.smem = smem_base + Cfg::kOutOff + static_cast<uint32_t>((warp - 5) * kOutStageBytes);
+      ec.ost.col0 = n0 + col0;
+      ec.ost.row0 = static_cast<int>(m) - lane;
+      ec.ost.lane = lane;
+      ec.ost.active = ec.ost.row0 < m_total && !(a.exp_flags & 1);
+      if (a.exp_flags & 4) ec.ost.row0 &= 16383;
+      ec.ost.policy = (a.exp_flags & 8) ? 0ull : ptx::kL2EvictFirst;
+      ec.ost.exp_flags = a.exp_flags;
+      epilogue_row<kClusterN, kSave, kSplit, kFold>(ec);
     }
+    if (lane == 0) ptx::bulk_wait<0>();  // this warp's output stores are complete before the CTA may exit
   }
 
   ptx::tc_fence_before();
@@ -1912,13 +2075,42 @@ int make_tmap_rows(CUtensorMap* m, const void* ptr, int64_t rows, int box_rows) 
   return r == CUDA_SUCCESS ? NRSE_OK : NRSE_ERR_CUDA;
 }
 
+// Output of an epilogue: bf16 rows of 512 channels, `row_mul` rows apart (1; 2 for the data-gradient GEMM, which writes rows
+// 2 m + parity: pass the pointer of row `parity`), box = one epilogue warp's staging buffer (32 channels x 32 rows, 64-byte
+// swizzle).  Rows past `rows` are clipped by the TMA engine.
+int make_tmap_out(CUtensorMap* m, const void* ptr, int64_t rows, int row_mul = 1) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return NRSE_ERR_CUDA;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kC), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kC) * 2 * row_mul};
+  const cuuint32_t box[2] = {kOutStageCols, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NRSE_OK : NRSE_ERR_CUDA;
+}
+
+// NRSE_EXPERIMENT (environment, read once): timing experiments that produce WRONG results -- never set outside scripts/
+int experiment_flags() {
+  static const int v = [] {
+    const char* e = getenv("NRSE_EXPERIMENT");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
 int g_tile_order = 1;   // 1: consecutive layers walk their tiles in opposite directions, so that every layer starts on the
                         // rows its producer wrote last (still in L2) instead of the ones it wrote first (long evicted); 0: all forward
 int g_l2_prefetch = 0;  // 1: producer bulk-prefetches the next tile's A rows into L2 (measured 2-3 % slower: off)
-int g_variant = 2;  // 1: single CTA per tile, 2: 2-CTA cluster splitting the channels (default), 3: as 2, but the inference
-                    // forward of the GEMM layers runs the 2-SM UMMA kernel (conv_gemm2_kernel)
+int g_variant = 4;  // 1: single CTA per tile, 2: 2-CTA cluster splitting the channels, 3: as 2, but the inference forward of
+                    // the GEMM layers runs the 2-SM UMMA kernel (conv_gemm2_kernel), 4 (default): as 2, but
+                    // nrse_conv_frontend_fwd runs layers 1 and 2 on the 2-SM kernel (507 + 256 us against 522 + 263 at
+                    // 64 x 4 s; the small layers lose on it: its pair owns 256 frames, so the tail wave is coarser).  The
+                    // choice depends on the layer, never on the batch: an utterance's features do not depend on what
+                    // else is in the batch (tests/test_gpu_frontend.py::test_frontend_full_size_batch_independence)
 
-int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const GemmArgs& g, cudaStream_t stream) {
+int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const GemmArgs& g,
+                 cudaStream_t stream) {
   static bool attr_set = false;  // benign race: the attribute is idempotent
   if (!attr_set) {
     NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1940,12 +2132,13 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const GemmArgs& g
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel, ta, tw, g));
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel, ta, tw, to, g));
   return NRSE_OK;
 }
 
 template <int kClusterN, bool kSave = false>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmArgs& g, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const GemmArgs& g,
+                cudaStream_t stream) {
   using Cfg = GemmCfg<kClusterN>;
   static bool attr_set = false;  // benign race: the attribute is idempotent
   if (!attr_set) {
@@ -1967,7 +2160,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmArgs& g,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<kClusterN, kSave>, ta, tw, g));
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<kClusterN, kSave>, ta, tw, to, g));
   return NRSE_OK;
 }
 
@@ -1996,14 +2189,17 @@ int launch_layer0_tc(const L0Args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, layer0_tc_kernel<kClusterN, kSave, kSplit, kFold>, a));
+  CUtensorMap to;
+  if (make_tmap_out(&to, a.out, m_total) != NRSE_OK) return NRSE_ERR_CUDA;
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, layer0_tc_kernel<kClusterN, kSave, kSplit, kFold>, to, a));
   return NRSE_OK;
 }
 
-int g_layer0_variant = 2;  // LayerNorm mode.  0: SIMT kernel; 1: tensor-core kernel; 2: tensor-core kernel with LayerNorm
-                           // folded into the GEMM operands (inference forward only; default); 3: 2 with 16 epilogue warps
-                           // (kSplit = 2, two teams per accumulator buffer: 80 registers per thread, measured 9 % slower
-                           // than 2 -- kept as a tuning knob)
+int g_layer0_variant = 3;  // LayerNorm mode.  0: SIMT kernel; 1: tensor-core kernel; 2: tensor-core kernel with LayerNorm
+                           // folded into the GEMM operands (inference forward only); 3 (default): 2 with 16 epilogue warps
+                           // (kSplit = 2, two teams per accumulator buffer, 80 registers per thread).  With direct global
+                           // stores 3 was 9 % slower than 2; with the staged TMA stores and the evict-first policy it is
+                           // the faster one (179 us against 223 at 64 x 4 s: more warps cover the staging barriers)
 
 int geometry(int L, int32_t* T, int32_t* P) {
   long long t = L;
@@ -2066,7 +2262,7 @@ size_t nrse_conv_frontend_workspace_bytes(int B, int L) {
 }
 
 int nrse_conv_frontend_set_variant(int variant) {
-  if (variant < 1 || variant > 3) return NRSE_ERR_INVALID_ARG;
+  if (variant < 1 || variant > 4) return NRSE_ERR_INVALID_ARG;
   nrse::g_variant = variant;
   return NRSE_OK;
 }
@@ -2104,6 +2300,7 @@ static int layer0_fwd_impl(const float* x, const float* w0, const float* gamma, 
   if (reinterpret_cast<uintptr_t>(out) & 15u) return NRSE_ERR_INVALID_ARG;
   cudaStream_t s = as_stream(stream);
   L0Args a;
+  a.exp_flags = experiment_flags();
   a.x = x; a.w = w0; a.gamma = gamma; a.beta = beta;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   a.B = B; a.L = L; a.T0 = T0; a.P0 = P0;
@@ -2145,7 +2342,7 @@ int nrse_conv_layer0_fwd(const float* x, const float* w0, const float* gamma, co
 
 static int layer_fwd_impl(const void* act_prev, int64_t rows_prev, const void* w_packed, int k, int stride,
                           const float* gamma, const float* beta, void* out, int out_dtype, int64_t rows_out,
-                          void* xhat, float* rstd, nrse_stream_t stream, int reverse = 0) {
+                          void* xhat, float* rstd, nrse_stream_t stream, int reverse = 0, bool big_layer = false) {
   using namespace nrse;
   if (!act_prev || !w_packed || !out || (k != 2 && k != 3) || stride != 2) return NRSE_ERR_INVALID_ARG;
   if ((gamma == nullptr) != (beta == nullptr)) return NRSE_ERR_INVALID_ARG;
@@ -2154,13 +2351,14 @@ static int layer_fwd_impl(const void* act_prev, int64_t rows_prev, const void* w
   if ((reinterpret_cast<uintptr_t>(act_prev) | reinterpret_cast<uintptr_t>(w_packed) |
        reinterpret_cast<uintptr_t>(out)) & 15u)
     return NRSE_ERR_INVALID_ARG;
-  const bool two_sm = g_variant == 3 && xhat == nullptr;
+  const bool two_sm = xhat == nullptr && (g_variant == 3 || (g_variant == 4 && big_layer));
   CUtensorMap ta, tw;
   int rc = make_tmap_a(&ta, act_prev, rows_prev, stride);
   if (rc != NRSE_OK) return rc;
   rc = make_tmap_w(&tw, w_packed, k * kC, two_sm ? Gemm2Cfg::kBHalfRows : kUmmaN);
   if (rc != NRSE_OK) return rc;
   GemmArgs g;
+  g.exp_flags = experiment_flags();
   g.gamma = gamma; g.beta = beta; g.out = out;
   g.out_f32 = out_dtype == NRSE_DTYPE_F32 ? 1 : 0;
   g.M_total = static_cast<int>(rows_out);
@@ -2178,10 +2376,14 @@ static int layer_fwd_impl(const void* act_prev, int64_t rows_prev, const void* w
   g.a_rows = rows_prev;
   g.l2_prefetch = g_l2_prefetch;
   g.reverse = reverse;
-  if (two_sm) return launch_gemm2(ta, tw, g, as_stream(stream));
+  CUtensorMap to;  // bf16 outputs only; an fp32 output (last layer on request) keeps direct stores and ignores the map
+  rc = make_tmap_out(&to, out, rows_out);
+  if (rc != NRSE_OK) return rc;
+  if (two_sm) return launch_gemm2(ta, tw, to, g, as_stream(stream));
   if (xhat != nullptr)
-    return g_variant >= 2 ? launch_gemm<2, true>(ta, tw, g, as_stream(stream)) : launch_gemm<1, true>(ta, tw, g, as_stream(stream));
-  return g_variant >= 2 ? launch_gemm<2>(ta, tw, g, as_stream(stream)) : launch_gemm<1>(ta, tw, g, as_stream(stream));
+    return g_variant >= 2 ? launch_gemm<2, true>(ta, tw, to, g, as_stream(stream))
+                          : launch_gemm<1, true>(ta, tw, to, g, as_stream(stream));
+  return g_variant >= 2 ? launch_gemm<2>(ta, tw, to, g, as_stream(stream)) : launch_gemm<1>(ta, tw, to, g, as_stream(stream));
 }
 
 int nrse_conv_layer_fwd(const void* act_prev, int64_t rows_prev, const void* w_packed, int k, int stride,
@@ -2222,7 +2424,7 @@ int nrse_conv_frontend_fwd(const float* x, const nrse_frontend_params* prm, int 
     rc = layer_fwd_impl(act[i - 1], static_cast<int64_t>(B) * P[i - 1], prm->w_packed[i - 1], kKernel[i], kStride[i],
                         norm ? prm->gamma[i] : nullptr, norm ? prm->beta[i] : nullptr, act[i],
                         i == kLayers - 1 ? y_dtype : NRSE_DTYPE_BF16, static_cast<int64_t>(B) * P[i], nullptr, nullptr,
-                        stream, g_tile_order ? (i & 1) : 0);
+                        stream, g_tile_order ? (i & 1) : 0, /*big_layer=*/i <= 2);
     if (rc != NRSE_OK) return rc;
   }
   return NRSE_OK;
@@ -2358,6 +2560,7 @@ int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even,
     rc = make_tmap_w(&tw, parity == 0 ? wt_even : wt_odd, n_blocks * kC);
     if (rc != NRSE_OK) return rc;
     GemmArgs g;
+    g.exp_flags = experiment_flags();
     g.gamma = nullptr; g.beta = nullptr; g.out = dx; g.out_f32 = 0;
     g.M_total = static_cast<int>(rows_out);
     g.num_tiles = static_cast<int>(ceil_div(rows_out, static_cast<int64_t>(kBlockM)));
@@ -2373,7 +2576,10 @@ int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even,
     g.a_ptr = reinterpret_cast<const char*>(dz);
     g.a_rows = rows_out;
     g.l2_prefetch = g_l2_prefetch;
-    rc = g_variant >= 2 ? launch_gemm<2>(ta, tw, g, as_stream(stream)) : launch_gemm<1>(ta, tw, g, as_stream(stream));
+    CUtensorMap to;  // rows 2 m + parity of dX
+    rc = make_tmap_out(&to, reinterpret_cast<const char*>(dx) + static_cast<size_t>(parity) * kC * 2, rows_out, 2);
+    if (rc != NRSE_OK) return rc;
+    rc = g_variant >= 2 ? launch_gemm<2>(ta, tw, to, g, as_stream(stream)) : launch_gemm<1>(ta, tw, to, g, as_stream(stream));
     if (rc != NRSE_OK) return rc;
   }
   return NRSE_OK;

@@ -561,6 +561,10 @@ def conv_frontend(x: Tensor, conv_weights: Sequence[Tensor], gammas: Sequence[Op
     return y[:, :T[6], :]
 
 
+DEFAULT_FRONTEND_VARIANT = 4  # see nrse_conv_frontend_set_variant (include/nrse_b200.h)
+DEFAULT_LAYER0_VARIANT = 3    # see nrse_conv_frontend_set_layer0_variant
+
+
 def set_frontend_variant(variant: int) -> None:
     check(_lib.load().nrse_conv_frontend_set_variant(int(variant)), "nrse_conv_frontend_set_variant")
 

@@ -46,4 +46,4 @@ for pf in (2, 3, 2, 3):
         tot += t; fl += f
         out.append(f"l{i}={t*1e3:.0f}us/{f/(t*1e-3)/1e12:.0f}TF")
     print(f"variant={pf}: " + " ".join(out) + f"  | gemm total {tot*1e3:.0f}us {fl/(tot*1e-3)/1e12:.0f} TF")
-ops.set_frontend_variant(2)
+ops.set_frontend_variant(ops.DEFAULT_FRONTEND_VARIANT)

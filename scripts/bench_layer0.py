@@ -30,4 +30,4 @@ for variant in (1, 2, 3, 0):
         best = min(best, e0.elapsed_time(e1) / 10)
     byt = 4.0 * B * L + 2.0 * 512 * B * T[0]
     print(f"layer0 variant {variant}: {best*1e3:.1f} us  {byt/(best*1e-3)/1e9:.0f} GB/s ({byt/(best*1e-3)/1e9/6555.2:.3f} of HBM peak)", flush=True)
-ops.set_layer0_variant(2)
+ops.set_layer0_variant(ops.DEFAULT_LAYER0_VARIANT)

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for e in 256 257 260 264; do
+  echo "=== NRSE_EXPERIMENT=$e"
+  NRSE_EXPERIMENT=$e timeout 300 python scripts/bench_gemm.py > gpurun_out/exp4_gemm_$e.log 2>&1
+  grep "tiles=3200" gpurun_out/exp4_gemm_$e.log | sort | uniq -c | sort -rn | head -6
+  grep "variant=" gpurun_out/exp4_gemm_$e.log | head -2 | cut -c1-200
+done

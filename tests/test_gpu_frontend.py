@@ -11,7 +11,8 @@ from nrse_b200 import ops
 from nrse_b200.utils import synthetic
 
 pytestmark = pytest.mark.gpu
-VARIANTS = (1, 2, 3)  # 1-CTA tiles, CTA pair splitting the channels (default), 2-SM UMMA pair splitting the frames
+VARIANTS = (1, 2, 3)  # 1-CTA tiles, CTA pair splitting the channels, 2-SM UMMA pair splitting the frames (the default, 4,
+                      # picks 2 or 3 per layer and runs in every test that does not select a variant)
 
 
 def _layer_params(layers, dev):
@@ -38,8 +39,8 @@ def test_layer0_vs_oracle(dev, mode, l0, variant):
     got = out[:, :T[0]].float().transpose(1, 2).cpu().numpy()
     assert rel_err(got, ref.numpy()) < 6e-3   # bf16 output rounding (2^-9) dominates
     assert not out[:, T[0]:].any()            # pitch padding is zero-filled
-    ops.set_layer0_variant(2)
-    ops.set_frontend_variant(2)
+    ops.set_layer0_variant(ops.DEFAULT_LAYER0_VARIANT)
+    ops.set_frontend_variant(ops.DEFAULT_FRONTEND_VARIANT)
 
 
 def test_layer0_tc_is_fp32_class(dev):
@@ -69,6 +70,7 @@ def test_layer0_tc_is_fp32_class(dev):
     fold = ops.conv_layer0(xo, w[0], g[0], b[0], "layer").float()
     diff = (fold - ref).abs()
     assert float(diff.max()) <= 2 ** -6 * float(ref.abs().max()) and float((diff > 0).float().mean()) < 0.10
+    ops.set_layer0_variant(ops.DEFAULT_LAYER0_VARIANT)
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=["v1", "v2", "v3-2sm"])
@@ -100,7 +102,7 @@ def test_gemm_layer_vs_torch(dev, variant, k, rows_out, norm):
     # bf16 output path
     out16 = ops.conv_layer(act.to(dev), wp, k, gamma.to(dev) if norm else None, beta.to(dev) if norm else None)
     assert rel_err(out16.float().cpu().numpy(), ref.numpy()) < 5e-3
-    ops.set_frontend_variant(2)
+    ops.set_frontend_variant(ops.DEFAULT_FRONTEND_VARIANT)
 
 
 @pytest.mark.parametrize("variant", VARIANTS, ids=["v1", "v2", "v3-2sm"])
@@ -115,7 +117,7 @@ def test_frontend_golden(dev, golden, variant, mode):
     got = y.transpose(1, 2).cpu().numpy()
     assert got.shape == g["y"].shape
     assert rel_err(got, g["y"]) < 1e-2
-    ops.set_frontend_variant(2)
+    ops.set_frontend_variant(ops.DEFAULT_FRONTEND_VARIANT)
 
 
 @pytest.mark.parametrize("mode,B,L", [("layer", 3, 16000), ("group", 2, 16000), ("layer", 1, 400), ("layer", 2, 12345),

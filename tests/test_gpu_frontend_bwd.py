@@ -94,10 +94,14 @@ def test_full_backward_vs_autograd(dev, B, L):
     # the same layer-0 kernel selected for inference the features are bit-identical, with the default (LayerNorm folded
     # into the GEMM operands) they agree to bf16 rounding of the layer-0 output
     ops.set_layer0_variant(1)
+    ops.set_frontend_variant(2)   # the tape-writing forward always runs the 1-SM kernels
     assert torch.equal(y, ops.conv_frontend(xd, w, g, b, "layer"))
-    ops.set_layer0_variant(2)
+    ops.set_frontend_variant(ops.DEFAULT_FRONTEND_VARIANT)
+    ops.set_layer0_variant(ops.DEFAULT_LAYER0_VARIANT)
     y_plain = ops.conv_frontend(xd, w, g, b, "layer")
-    assert rel_err(y_plain.cpu().numpy(), y.cpu().numpy()) < 5e-3
+    # two bf16 pipelines that differ in the rounding of layer 0, six layers later: each is within 1e-2 of the fp32 oracle
+    assert rel_err(y_plain.transpose(1, 2).cpu().numpy(), y_ref.detach().numpy()) < 1e-2
+    assert rel_err(y_plain.cpu().numpy(), y.cpu().numpy()) < 8e-3
     dw, dg, db = ops.conv_frontend_backward(xd, w, g, b, tape, gy.to(dev).transpose(1, 2))
     for i in range(7):
         e_w = rel_err(dw[i].cpu().numpy(), params[i]["conv"].grad.numpy())
