@@ -396,7 +396,7 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1c_ncu_traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of the six launches, from the ncu capture
         with open(tpath) as f:
             tj = json.load(f)

@@ -262,18 +262,23 @@ constexpr int kUmmaK = 16;
 constexpr int kUmmaN = 256;
 constexpr int kEpiThreads = 128;  // one epilogue team = 4 warps = the 4 TMEM lane quadrants
 // Output path of the epilogues.  One thread owns one output row, so direct global stores are 32 rows x 32 bytes per warp
-// instruction: one L1 wavefront and one partial L2 line write per THREAD.  Measured (NRSE_EXPERIMENT=1, stores skipped):
-// that store path, not the arithmetic, is what the epilogues cost -- the GEMM layers run at 1.60 PFLOP/s without it against
-// 1.17 with it, layer 0 at 122 us against 224.  So bf16 outputs are staged: every epilogue warp owns a 2 KB shared-memory
-// buffer (32 rows x 32 channels, 64-byte rows, TMA's 64-byte swizzle so that the 16-byte row-owner writes are
-// conflict-free), and lane 0 hands it to the TMA engine (cp.async.bulk.tensor store), which writes whole sectors without
-// touching the LSU pipe.  The buffer is single: the wait for the engine to have READ it sits behind the arithmetic of the
-// next 32 channels, so registers are the second buffer.
+// instruction: one L1 wavefront and one partial L2 line write per THREAD (layer 0, which writes 839 MB behind a K = 48
+// GEMM, had its L1 data pipe at 79 % in the ncu capture).  So bf16 outputs are staged: every epilogue warp owns a 2 KB
+// shared-memory buffer (32 rows x 32 channels, 64-byte rows, TMA's 64-byte swizzle so that the 16-byte row-owner writes
+// are conflict-free), and lane 0 hands it to the TMA engine (cp.async.bulk.tensor store), which writes whole sectors
+// without touching the LSU pipe.  The buffer is single: the wait for the engine to have READ it sits behind the arithmetic
+// of the next 32 channels, so registers are the second buffer.  Measured at 64 x 4 s (NRSE_EXPERIMENT hooks, DESIGN.md
+// section 4): layer 0 223 -> 179 us (with 16 epilogue warps and the evict-first policy below; 170 us with no global stores
+// at all), GEMM layers neutral to +2 % (their L1 data pipe was at 40-60 %; what they pay for the output is the SM clock,
+// which the board lowers by ~17 % while a kernel streams to HBM).
 constexpr int kOutStageCols = 32;
 constexpr int kOutStageBytes = 32 * kOutStageCols * 2;
 struct OutStage {
-  const CUtensorMap* tmap;  // nullptr: direct global stores (fp32 outputs)
-  uint32_t smem;            // this warp's staging buffer (shared window, 1024-byte aligned)
+  const CUtensorMap* tmap;  // nullptr: direct global stores (fp32 outputs, GEMM layers of the training forward)
+  const CUtensorMap* tmap2; // training forward of layer 0: second tensor (xhat) through a second buffer at smem + 2 KB;
+                            // nullptr otherwise.  A thread's own global stores and the staging do not mix: the proxy fence
+                            // waits for them (training forward 1.72 -> 2.76 ms when xhat went out directly next to it)
+  uint32_t smem;            // this warp's staging buffer(s) (shared window, 1024-byte aligned)
   int col0;                 // tensor-map column of this thread's first channel
   int row0;                 // tensor-map row of lane 0 of this warp
   int lane;
@@ -284,18 +289,27 @@ struct OutStage {
   int exp_flags;            // timing experiments: 64 = no proxy fence, 128 = no wait for the engine's read
 };
 // one 32-channel chunk of the warp's 32 rows: registers -> staging buffer -> TMA store (rows past the tensor's end are clipped)
-__device__ __forceinline__ void out_stage_store(const OutStage& o, const uint32_t (&v)[16], int col) {
-  if (o.lane == 0 && !(o.exp_flags & 128)) ptx::bulk_wait_read<0>();  // the engine has read the previous chunk
+// which = 0: the output through `tmap`; 1: the second tensor through `tmap2` (the two alternate, so "the previous store
+// into THIS buffer has been read" is "at most one bulk group pending")
+__device__ __forceinline__ void out_stage_store(const OutStage& o, const uint32_t (&v)[16], int col, int which = 0) {
+  if (o.lane == 0 && !(o.exp_flags & 128)) {  // the engine has read the previous chunk out of this buffer
+    if (o.tmap2 != nullptr) ptx::bulk_wait_read<1>();
+    else ptx::bulk_wait_read<0>();
+  }
   __syncwarp();
-  const uint32_t row = o.smem + static_cast<uint32_t>(o.lane) * 64u, sw = (static_cast<uint32_t>(o.lane) >> 1) & 3u;
+  const uint32_t buf = o.smem + static_cast<uint32_t>(which) * kOutStageBytes;
+  const uint32_t row = buf + static_cast<uint32_t>(o.lane) * 64u, sw = (static_cast<uint32_t>(o.lane) >> 1) & 3u;
 #pragma unroll
   for (uint32_t j = 0; j < 4; ++j)
     ptx::st_shared_v4(row + ((j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   if (!(o.exp_flags & 64)) ptx::fence_proxy_async_smem();
   __syncwarp();
-  if (o.lane == 0 && o.active) {
-    if (o.policy) ptx::tma_store_2d_hint(o.tmap, o.smem, o.col0 + col, o.row0, o.policy);
-    else ptx::tma_store_2d(o.tmap, o.smem, o.col0 + col, o.row0);
+  if (o.lane == 0) {  // an inactive warp still commits (empty) groups: the wait above counts groups
+    const CUtensorMap* tm = which ? o.tmap2 : o.tmap;
+    if (o.active) {
+      if (o.policy) ptx::tma_store_2d_hint(tm, buf, o.col0 + col, o.row0, o.policy);
+      else ptx::tma_store_2d(tm, buf, o.col0 + col, o.row0);
+    }
     ptx::bulk_commit();
   }
 }
@@ -566,7 +580,13 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
       }
     }
     if constexpr (kSave) {
-      if (e.store && e.has_norm && e.xhat_row != nullptr) {
+      if (e.ost.tmap2 != nullptr) {
+        if (e.zero) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xh16[j] = 0;
+        }
+        out_stage_store(e.ost, xh16, c * 32, 1);
+      } else if (e.store && e.has_norm && e.xhat_row != nullptr) {
         char* dst = reinterpret_cast<char*>(e.xhat_row + c * 32);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -833,7 +853,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // bf16 outputs leave through this warp's staging buffer and the TMA engine (tmap_out rows = output rows, also in
       // mode 1, whose interleaved rows 2 m + parity are a tensor map with a doubled row stride)
       OutStage ost;
-      ost.tmap = g.out_f32 ? nullptr : &tmap_out;
+      ost.tmap = (g.out_f32 || kSave) ? nullptr : &tmap_out;  // training forward: direct stores (see OutStage::tmap2)
+      ost.tmap2 = nullptr;
       ost.smem = smem_base + Cfg::kOutOff + static_cast<uint32_t>((warp - 2) * kOutStageBytes);
       ost.col0 = n0;
       ost.row0 = static_cast<int>(m) - lane;
@@ -1212,6 +1233,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       ec.out_row = g.out_f32 ? static_cast<void*>(reinterpret_cast<float*>(g.out) + m * kC)
                              : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(g.out) + m * kC);
       ec.ost.tmap = g.out_f32 ? nullptr : &tmap_out;
+      ec.ost.tmap2 = nullptr;
       ec.ost.smem = smem_base + Cfg::kOutOff + static_cast<uint32_t>((warp - 2) * kOutStageBytes);
       ec.ost.col0 = 0;
       ec.ost.row0 = static_cast<int>(m) - lane;
@@ -1261,7 +1283,7 @@ struct L0tcCfg {
   static constexpr int kWOff = kL0AStages * kABytes;
   static constexpr int kWBytes = kNPC * 128;
   static constexpr int kOutOff = kWOff + kWBytes;               // one output staging buffer per epilogue warp (see OutStage)
-  static constexpr int kGbOff = kOutOff + kTeams * 4 * kOutStageBytes;
+  static constexpr int kGbOff = kOutOff + kTeams * 4 * 2 * kOutStageBytes;  // two per warp: output and (training) xhat
   static constexpr int kStatsOff = kGbOff + kNPC * 8;           // kL0PreSlots x 128 rows x (mean, rstd) from the builders
   static constexpr int kGramOff = kStatsOff + kL0PreSlots * kBlockM * 8;  // 10 channel-mean taps + 55 Gram entries
   static constexpr int kBarOff = kGramOff + 72 * 4;
@@ -1309,7 +1331,8 @@ __device__ __forceinline__ void l0_split1(float v, uint32_t& hi, uint32_t& lo) {
 // latency was the epilogue's main dependency stall).  All added operands get the same bf16 hi/lo split as the samples.
 template <int kClusterN, bool kSave, int kSplit = 1, bool kFold = false>
 __global__ void __launch_bounds__(L0tcCfg<kClusterN, kSplit>::kThreads, 1)
-layer0_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const L0Args a) {
+layer0_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_xhat,
+                 const L0Args a) {
   static_assert(!(kFold && kSave), "the training forward needs the pre-affine activations: no folding");
   using Cfg = L0tcCfg<kClusterN, kSplit>;
   constexpr int kWords = kFold ? 24 : 16;  // 32-bit words (bf16 pairs) per operand row: K = 48 or 32
@@ -1551,7 +1574,8 @@ layer0_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const L0Args a) {
       ec.xhat_row = a.xhat ? a.xhat + m * kC + n0 + col0 : nullptr;
       ec.rstd_out = (a.rstd && n0 == 0 && half == 0) ? a.rstd + m : nullptr;
       ec.ost.tmap = &tmap_out;
-      ec.ost.smem = smem_base + Cfg::kOutOff + static_cast<uint32_t>((warp - 5) * kOutStageBytes);
+      ec.ost.tmap2 = (kSave && a.xhat != nullptr) ? &tmap_xhat : nullptr;
+      ec.ost.smem = smem_base + Cfg::kOutOff + static_cast<uint32_t>((warp - 5) * 2 * kOutStageBytes);
       ec.ost.col0 = n0 + col0;
       ec.ost.row0 = static_cast<int>(m) - lane;
       ec.ost.lane = lane;
@@ -2189,9 +2213,10 @@ int launch_layer0_tc(const L0Args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CUtensorMap to;
+  CUtensorMap to, tx;
   if (make_tmap_out(&to, a.out, m_total) != NRSE_OK) return NRSE_ERR_CUDA;
-  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, layer0_tc_kernel<kClusterN, kSave, kSplit, kFold>, to, a));
+  if (make_tmap_out(&tx, a.xhat != nullptr ? static_cast<const void*>(a.xhat) : a.out, m_total) != NRSE_OK) return NRSE_ERR_CUDA;
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, layer0_tc_kernel<kClusterN, kSave, kSplit, kFold>, to, tx, a));
   return NRSE_OK;
 }
 
