@@ -171,6 +171,9 @@ def main_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    for var in ("NRSE_EXPERIMENT", "NRSE_B200_LIB"):  # timing-experiment hooks of scripts/: never in a measured number
+        if os.environ.get(var):
+            raise SystemExit(f"bench.py refuses to run with {var} set (experiment hook: wrong results / another build)")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -384,8 +387,8 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
         k = CONV_KERNEL[i]
         inp = act
         # the per-layer entry point cannot know the layer: select what nrse_conv_frontend_fwd runs for it (default
-        # variant 4: the 2-SM UMMA kernel for layers 1-2, the 1-SM CTA-pair kernel for layers 3-6)
-        ops.set_frontend_variant(3 if i <= 2 else 2)
+        # variant 4: the 2-SM UMMA kernel for layers 1-3, the 1-SM CTA-pair kernel for layers 4-6)
+        ops.set_frontend_variant(3 if i <= 3 else 2)
         t = ev_time(lambda: ops.conv_layer(inp, packed[i - 1], k, gammas[i], betas[i]))
         act = ops.conv_layer(inp, packed[i - 1], k, gammas[i], betas[i])
         ops.set_frontend_variant(ops.DEFAULT_FRONTEND_VARIANT)
@@ -401,7 +404,7 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
         with open(tpath) as f:
             tj = json.load(f)
         traffic, traffic_src = tj["traffic_bytes_six_launches"], tj["source"]
-    roofline = {"bound": "tensor", "kernel": "conv_gemm2_kernel (layers 1-2, 2-SM UMMA) + conv_gemm_kernel (layers 3-6): tcgen05 implicit GEMM + LayerNorm + GELU",
+    roofline = {"bound": "tensor", "kernel": "conv_gemm2_kernel (layers 1-3, 2-SM UMMA) + conv_gemm_kernel (layers 4-6): tcgen05 implicit GEMM + LayerNorm + GELU",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_unit": "bytes per 6 launches (one view)", "traffic_source": traffic_src,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed back to back)",

@@ -248,7 +248,7 @@ int nrse_conv_layer_fwd(const void* act_prev, int64_t rows_prev, const void* w_p
  * 2 = a 2-CTA cluster splits the channels and exchanges LayerNorm partials through DSMEM,
  * 3 = as 2, but the inference forward of the GEMM layers runs the 2-SM UMMA kernel (tcgen05.mma.cta_group::2: the CTA
  *     pair splits the FRAMES, each CTA stages half of the weight rows; same results to bf16 rounding),
- * 4 = as 2, but nrse_conv_frontend_fwd runs layers 1 and 2 on the 2-SM kernel (default; the choice never depends on the
+ * 4 = as 2, but nrse_conv_frontend_fwd runs layers 1-3 on the 2-SM kernel (default; the choice never depends on the
  *     batch, so an utterance's features do not depend on what else is in the batch). */
 int nrse_conv_frontend_set_variant(int variant);
 /* Layer-0 kernel in LayerNorm mode: 0 = SIMT (warp per frame); 1 = tensor cores (hi/lo-split K=32 UMMA, LayerNorm +

@@ -954,6 +954,12 @@ struct Epi2Ctx {
 
 __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
   constexpr int kChunks = 4;  // 128 columns per buffer per thread
+  // This thread's slice of buffer 0 is read ONCE and kept in registers (128 of the ~200 a 320-thread CTA can give a
+  // thread) from the statistics pass to the normalise + GELU pass, so buffer 0 goes back to the MMA warp while the MMAs
+  // of unit 1 are still running and the next frames' unit 0 never waits for the epilogue.  (Re-reading it in pass 2, as
+  // the 1-SM kernel does, released it only after the second buffer's statistics, the exchange and most of its own pass 2:
+  // the MMA thread spent ~27 % of the kernel polling that barrier -- ncu source view of r1c.)
+  uint32_t a0[32], a1[32], a2[32], a3[32];
   uint32_t ra[32], rb[32];
   auto release = [&](uint32_t local, uint32_t cluster) {
     ptx::tc_fence_before();
@@ -974,21 +980,31 @@ __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
       body(rb, c + 1);
     }
   };
+  // the same walk with ONE load in flight (while a0..a3 are live there are no registers for a second chunk)
+  auto walk1 = [&](uint32_t taddr, auto&& body) {
+#pragma unroll 1
+    for (int c = 0; c < kChunks; ++c) {
+      ptx::tmem_ld32(taddr + c * 32, ra);
+      ptx::tmem_ld_wait();
+      body(ra, c);
+    }
+  };
   ptx::mbar_wait(e.bar_full0, e.parity);
   ptx::tc_fence_after();
+  ptx::tmem_ld32(e.taddr0, a0);
+  ptx::tmem_ld32(e.taddr0 + 32, a1);
+  ptx::tmem_ld32(e.taddr0 + 64, a2);
+  ptx::tmem_ld32(e.taddr0 + 96, a3);
+  ptx::tmem_ld_wait();
+  release(e.bar_empty0, e.empty0_cluster);  // buffer 0 is in registers: the next frames' unit 0 may start
   float mean = 0.f, rstd = 1.f;
   if (e.has_norm) {
     if (e.arm) ptx::mbar_arrive_expect_tx(e.bar_stats, kBlockM * 8);  // 128 partner rows x (mean, M2)
     // pass 1: shifted sums over this thread's 2 x 128 channels (shift = its first accumulator: no cancellation)
-    f2 s1 = f2_make(0.f, 0.f), s2 = s1, nshift = s1;
-    float shift = 0.f;
-    bool first = true;
+    const float shift = NRSE_STATS_SHIFT ? __uint_as_float(a0[0]) : 0.f;
+    const f2 nshift = f2_make(-shift, -shift);
+    f2 s1 = f2_make(0.f, 0.f), s2 = s1;
     auto stats32 = [&](const uint32_t (&r)[32], int) {
-      if (first) {
-        shift = NRSE_STATS_SHIFT ? __uint_as_float(r[0]) : 0.f;
-        nshift = f2_make(-shift, -shift);
-        first = false;
-      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
 #if NRSE_STATS_SHIFT
@@ -1000,10 +1016,13 @@ __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
         s2 = f2_fma(d, d, s2);
       }
     };
-    walk(e.taddr0, stats32, [] {});
+    stats32(a0, 0);
+    stats32(a1, 1);
+    stats32(a2, 2);
+    stats32(a3, 3);
     ptx::mbar_wait(e.bar_full1, e.parity);
     ptx::tc_fence_after();
-    walk(e.taddr1, stats32, [] {});
+    walk1(e.taddr1, stats32);
     float s1a, s1b, s2a, s2b;
     f2_split(s1, s1a, s1b);
     f2_split(s2, s2a, s2b);
@@ -1068,7 +1087,10 @@ __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
       }
     }
   };
-  walk(e.taddr0, emit32, [&] { release(e.bar_empty0, e.empty0_cluster); });  // buffer 0 read: next frames' unit 0 may start
+  emit32(a0, 0);  // buffer 0 from registers
+  emit32(a1, 1);
+  emit32(a2, 2);
+  emit32(a3, 3);
   ch_base = e.ch1;
   walk(e.taddr1, emit32, [&] { release(e.bar_empty1, e.empty1_cluster); });
 }
@@ -2128,8 +2150,8 @@ int g_tile_order = 1;   // 1: consecutive layers walk their tiles in opposite di
 int g_l2_prefetch = 0;  // 1: producer bulk-prefetches the next tile's A rows into L2 (measured 2-3 % slower: off)
 int g_variant = 4;  // 1: single CTA per tile, 2: 2-CTA cluster splitting the channels, 3: as 2, but the inference forward of
                     // the GEMM layers runs the 2-SM UMMA kernel (conv_gemm2_kernel), 4 (default): as 2, but
-                    // nrse_conv_frontend_fwd runs layers 1 and 2 on the 2-SM kernel (507 + 256 us against 522 + 263 at
-                    // 64 x 4 s; the small layers lose on it: its pair owns 256 frames, so the tail wave is coarser).  The
+                    // nrse_conv_frontend_fwd runs layers 1-3 on the 2-SM kernel (487 + 248 + 131 us against 531 + 266 + 136
+                    // at 64 x 4 s; the small layers lose on it: its pair owns 256 frames, so the tail wave is coarser).  The
                     // choice depends on the layer, never on the batch: an utterance's features do not depend on what
                     // else is in the batch (tests/test_gpu_frontend.py::test_frontend_full_size_batch_independence)
 
@@ -2449,7 +2471,7 @@ int nrse_conv_frontend_fwd(const float* x, const nrse_frontend_params* prm, int 
     rc = layer_fwd_impl(act[i - 1], static_cast<int64_t>(B) * P[i - 1], prm->w_packed[i - 1], kKernel[i], kStride[i],
                         norm ? prm->gamma[i] : nullptr, norm ? prm->beta[i] : nullptr, act[i],
                         i == kLayers - 1 ? y_dtype : NRSE_DTYPE_BF16, static_cast<int64_t>(B) * P[i], nullptr, nullptr,
-                        stream, g_tile_order ? (i & 1) : 0, /*big_layer=*/i <= 2);
+                        stream, g_tile_order ? (i & 1) : 0, /*big_layer=*/i <= 3);
     if (rc != NRSE_OK) return rc;
   }
   return NRSE_OK;

@@ -41,3 +41,19 @@ def test_b200_arm_fails_loudly_without_a_gpu():
         return  # meaningful only in the CPU container
     r = _run("--steps", "1", "--warmup", "1")
     assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout)
+
+
+def test_experiment_hooks_stay_out_of_the_product_path():
+    """NRSE_EXPERIMENT (kernels that skip work for timing) and NRSE_B200_LIB (another build of the library) exist for
+    scripts/ only: the package never sets them, bench.py and smoke() refuse to run with them, and only _lib.py reads the
+    library override."""
+    import glob
+    pkg = os.path.join(ROOT, "noise-robust-speech-embedding_b200")
+    for path in glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True):
+        src = open(path).read()
+        assert "NRSE_EXPERIMENT" not in src, path
+        if not path.endswith("_lib.py"):
+            assert "NRSE_B200_LIB" not in src, path
+    for name in ("bench.py", "__graft_entry__.py"):
+        src = open(os.path.join(ROOT, name)).read()
+        assert 'for var in ("NRSE_EXPERIMENT", "NRSE_B200_LIB")' in src, name
