@@ -28,7 +28,6 @@
 //   the data-gradient GEMM of the backward; see the "Backward" block further down for the other backward kernels.
 #include <cuda.h>
 
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -360,7 +359,10 @@ struct GemmArgs {
   int l2_prefetch;
   int reverse;  // 1: walk the tiles from the last to the first (see g_tile_order)
   int exp_flags;  // timing experiments (NRSE_EXPERIMENT, wrong results): 1 = no output stores, 2 = no statistics pass,
-                  // 4 = all output stores into the same 16 MB
+                  // 4 = all output stores into the same 16 MB, 8 = no evict-first policy, 16 / 32 = L2 hints on the A / W loads,
+                  // 64 / 128 = no proxy fence / no wait for the TMA engine's read (host side: 512 = no programmatic
+                  // dependent launch).  The SM-clock read-out behind profiles/r1c_epilogue_experiments.txt (flag 256, a
+                  // clock64 / globaltimer printf at kernel end) lived in commit 5ed733e only
 };
 
 // ---- epilogue of one accumulator row (shared by the GEMM layers and the tensor-core layer 0) ----------------
@@ -709,12 +711,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = kClusterN == 2 ? ptx::cluster_ctarank() : 0u;
   const int n0 = static_cast<int>(cta_rank) * Cfg::kNPC;  // first channel owned by this CTA
-  long long dbg_c0 = 0;
-  unsigned long long dbg_t0 = 0;
-  if (g.exp_flags & 256) {  // timing experiment: report the SM clock this launch ran at
-    dbg_c0 = clock64();
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
-  }
+
 
   auto bar = [&](int i) { return smem_base + Cfg::kBarOff + 8u * static_cast<uint32_t>(i); };
   const int kFull = 0, kEmpty = Cfg::kStages, kTmemFull = 2 * Cfg::kStages,
@@ -744,6 +741,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 512);
     ptx::tmem_relinquish();
   }
+  // programmatic dependent launch: barrier / TMEM set-up above overlaps the tail of the previous kernel in the stream; nothing
+  // below may run before that kernel's memory is visible (parameters too: an optimizer kernel may have just written them)
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const bool has_norm = g.gamma != nullptr;
   for (int i = threadIdx.x; i < Cfg::kNPC; i += Cfg::kThreads) {  // gamma[kNPC] / 2 then beta[kNPC] / 2 (see gelu2h)
     reinterpret_cast<float*>(s_gb)[i] = has_norm ? 0.5f * g.gamma[n0 + i] : 0.5f;
@@ -905,13 +906,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   ptx::tc_fence_before();
   if constexpr (kClusterN == 2) ptx::cluster_sync_all();  // no CTA may exit while its peer can still write to it
   else __syncthreads();
-  if ((g.exp_flags & 256) && blockIdx.x == 0 && threadIdx.x == 0) {
-    unsigned long long t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    const long long c1 = clock64();
-    printf("[clk] tiles=%d cycles=%lld ns=%llu MHz=%.0f\n", g.num_tiles, c1 - dbg_c0, t1 - dbg_t0,
-           1e3 * static_cast<double>(c1 - dbg_c0) / static_cast<double>(t1 - dbg_t0));
-  }
+
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -1148,6 +1143,10 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     ptx::tmem_alloc_2sm(ptx::smem_u32(tmem_ptr_smem), 512);
     ptx::tmem_relinquish_2sm();
   }
+  // programmatic dependent launch: barrier / TMEM set-up above overlaps the tail of the previous kernel in the stream; nothing
+  // below may run before that kernel's memory is visible (parameters too: an optimizer kernel may have just written them)
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const bool has_norm = g.gamma != nullptr;
   for (int i = threadIdx.x; i < kC; i += Cfg::kThreads) {  // gamma[512] / 2 then beta[512] / 2 (see gelu2h)
     reinterpret_cast<float*>(s_gb)[i] = has_norm ? 0.5f * g.gamma[i] : 0.5f;
@@ -1390,6 +1389,10 @@ layer0_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
     ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 512);
     ptx::tmem_relinquish();
   }
+  // programmatic dependent launch: barrier / TMEM set-up above overlaps the tail of the previous kernel in the stream; nothing
+  // below may run before that kernel's memory is visible (parameters too: an optimizer kernel may have just written them)
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   // this CTA's filters, split hi/lo, as the B operand: [w_hi | w_hi | w_lo | 0 0] against A = [x_hi | x_lo | x_hi | 0 0]
   // (kFold: w = gamma * w, and K slots 30..34 = [g_hi g_hi g_lo b_hi b_lo] against A = [s_hi s_lo s_hi 1 1], s = -mean*rstd)
   for (int n = threadIdx.x; n < Cfg::kNPC; n += Cfg::kThreads) {
@@ -2171,13 +2174,15 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap
   cfg.blockDim = dim3(Gemm2Cfg::kThreads);
   cfg.dynamicSmemBytes = Gemm2Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (experiment_flags() & 512) ? 1 : 2;  // 512: no programmatic dependent launch (A/B timing)
   NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel, ta, tw, to, g));
   return NRSE_OK;
 }
@@ -2199,13 +2204,15 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
   cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kClusterN;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (experiment_flags() & 512) ? 1 : 2;  // 512: no programmatic dependent launch (A/B timing)
   NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<kClusterN, kSave>, ta, tw, to, g));
   return NRSE_OK;
 }
@@ -2228,13 +2235,15 @@ int launch_layer0_tc(const L0Args& a, cudaStream_t stream) {
   cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kClusterN;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (experiment_flags() & 512) ? 1 : 2;  // 512: no programmatic dependent launch (A/B timing)
   CUtensorMap to, tx;
   if (make_tmap_out(&to, a.out, m_total) != NRSE_OK) return NRSE_ERR_CUDA;
   if (make_tmap_out(&tx, a.xhat != nullptr ? static_cast<const void*>(a.xhat) : a.out, m_total) != NRSE_OK) return NRSE_ERR_CUDA;

@@ -1,4 +1,6 @@
 #!/bin/bash
+# SM clock inside the layer-1 GEMM launches (NRSE_EXPERIMENT flag 256: clock64 / globaltimer printf at kernel end).  The hook
+# was removed from the kernels after the measurement (profiles/r1c_epilogue_experiments.txt); check out commit 5ed733e to re-run.
 mkdir -p gpurun_out
 for e in 256 257 260 264; do
   echo "=== NRSE_EXPERIMENT=$e"
