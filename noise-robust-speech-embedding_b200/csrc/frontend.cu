@@ -18,12 +18,18 @@
 //             4-stage mbarrier ring), warp 1 = single-thread tcgen05.mma issuer (128 x 256 x 16 bf16 UMMA, fp32
 //             accumulators in TMEM), then one epilogue TEAM of 4 warps per TMEM accumulator buffer (tcgen05.ld,
 //             double-buffered -> LayerNorm over the 512 channels -> exact GELU with one MUFU, packed f32x2 math ->
-//             bf16 -> 256-bit global stores).  Two variants:
+//             bf16 -> per-warp staging buffer -> TMA store with an evict-first L2 policy; fp32 outputs and the
+//             tape-writing forward keep 256-bit global stores).  Variants:
 //               kClusterN = 1: one CTA owns all 512 channels of a 128-frame tile (accumulator = all of TMEM, one team).
 //               kClusterN = 2 (default): a 2-CTA cluster splits the channels 256/256; each CTA double-buffers its
 //                              accumulator (two teams), so the epilogue of tile j overlaps the MMAs of tile j+1; the
 //                              per-frame LayerNorm partials (mean, M2) cross to the peer CTA as one 8-byte st.async
 //                              that completes bytes on the peer's mbarrier (no fence on either side).
+//               conv_gemm2_kernel (layers 1-3 of the inference forward by default): 2-SM UMMA (cta_group::2), the CTA
+//                              pair splits the FRAMES; every epilogue thread keeps its slice of accumulator buffer 0 in
+//                              registers, so the buffer returns to the MMA warp before the second one completes.
+//   All three are launched with programmatic stream serialization: barrier / TMEM set-up runs before
+//   griddepcontrol.wait (it overlaps the previous kernel's tail), every global access after it.
 //   Mode 1 of the same kernel (plain bf16 epilogue, 2-D A map with per-block row offsets, output row 2m + parity) is
 //   the data-gradient GEMM of the backward; see the "Backward" block further down for the other backward kernels.
 #include <cuda.h>
