@@ -34,6 +34,7 @@
 //   the data-gradient GEMM of the backward; see the "Backward" block further down for the other backward kernels.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -2150,7 +2151,10 @@ int make_tmap_out(CUtensorMap* m, const void* ptr, int64_t rows, int row_mul = 1
 int experiment_flags() {
   static const int v = [] {
     const char* e = getenv("NRSE_EXPERIMENT");
-    return e ? atoi(e) : 0;
+    const int f = e ? atoi(e) : 0;
+    if (f != 0)
+      fprintf(stderr, "nrse_b200: NRSE_EXPERIMENT=%d is set -- timing experiment, the conv frontend's results may be WRONG\n", f);
+    return f;
   }();
   return v;
 }
