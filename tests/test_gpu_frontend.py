@@ -188,3 +188,31 @@ def test_tile_order_is_a_pure_scheduling_knob(dev):
     finally:
         ops.set_tile_order(1)
     assert torch.equal(y0, y1) and torch.equal(t0, t1)
+
+
+def test_launch_overlap_and_l2_policy_do_not_change_results(dev):
+    """Programmatic dependent launch (set-up of a layer's kernel overlaps the previous kernel's tail) and the evict-first
+    policy of the output stores are performance features: switching them off through the timing hooks (NRSE_EXPERIMENT 512 /
+    8, read once per process) must give bit-identical features.  A race between consecutive layers would show up here."""
+    import hashlib, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, hashlib, torch; sys.path.insert(0, %r);"
+        "from nrse_b200 import ops; from nrse_b200.utils import synthetic;"
+        "d = torch.device('cuda:0'); L = synthetic.frontend_weights('layer', seed=4);"
+        "x = torch.from_numpy(synthetic.waveforms(24, 48000, seed=3)[0]).to(d) * 10;"
+        "w = [torch.from_numpy(l['conv']).to(d) for l in L]; g = [torch.from_numpy(l['gamma']).to(d) for l in L];"
+        "b = [torch.from_numpy(l['beta']).to(d) for l in L];"
+        "h = hashlib.sha256();"
+        "[h.update(ops.conv_frontend(x, w, g, b, 'layer', out_dtype=torch.bfloat16).view(torch.int16).cpu().numpy().tobytes())"
+        " for _ in range(3)];"
+        "print('SHA', h.hexdigest())" % root)
+    digests = {}
+    for flags in (0, 8, 512, 520):
+        env = dict(os.environ, NRSE_EXPERIMENT=str(flags))
+        if flags == 0:
+            env.pop("NRSE_EXPERIMENT")
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests[flags] = [l for l in r.stdout.splitlines() if l.startswith("SHA")][-1]
+    assert len(set(digests.values())) == 1, digests
