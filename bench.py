@@ -15,6 +15,7 @@ path and prints the same JSON shape.
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -52,7 +53,11 @@ def measured_peaks():
 # clocks
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons / power every 50 ms while a timed region runs.  The sampler process is started
+    (and has delivered its first sample) BEFORE the warm-up steps, so that its start-up -- NVML initialisation takes the
+    driver's locks for a while -- does not fall into the timed region; samples are time-stamped and only those taken
+    between ``mark_begin()`` and ``stop()`` are reported."""
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -60,8 +65,9 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.path = f"/tmp/nrse_clocks_{os.getpid()}.csv"
+        self.t_begin = None
 
-    def start(self):
+    def start(self, wait_first_sample_s: float = 3.0):
         try:
             self.out = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
@@ -69,37 +75,64 @@ class ClockSampler:
                                          stdout=self.out, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+            return
+        t0 = time.time()
+        while time.time() - t0 < wait_first_sample_s:  # nvidia-smi is up and sampling before anything is timed
+            try:
+                if os.path.getsize(self.path) > 0:
+                    break
+            except OSError:
+                pass
+            if self.proc.poll() is not None:
+                break
+            time.sleep(0.01)
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    @staticmethod
+    def parse_line(line: str):
+        """One csv line -> (unix time or None, sm MHz, max sm MHz, power W, [active reason names]) or None."""
+        f = [x.strip() for x in line.split(",")]
+        if len(f) < 10:
+            return None
+        try:
+            sm, smax, power = float(f[2]), float(f[3]), float(f[4])
+        except ValueError:
+            return None
+        ts = None
+        for fmt in ("%Y/%m/%d %H:%M:%S.%f", "%Y/%m/%d %H:%M:%S"):
+            try:
+                ts = datetime.datetime.strptime(f[0], fmt).timestamp()
+                break
+            except ValueError:
+                continue
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [name for name, val in zip(names, f[6:10]) if val.lower().startswith("active")]
+        return ts, sm, smax, power, reasons
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.time()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
         self.out.close()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+        rows = [r for r in (self.parse_line(line) for line in open(self.path)) if r is not None]
         try:
             os.remove(self.path)
         except OSError:
             pass
-        if not sm:
+        inside = [r for r in rows if r[0] is None or self.t_begin is None or self.t_begin - 0.05 <= r[0] <= t_end + 0.05]
+        used = inside if inside else rows[-1:]  # a region shorter than the sampling period: the closest sample
+        if not used:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                "power_w_max": max(power), "samples": len(sm)}
+        reasons = sorted({name for r in used for name in r[4]})
+        return {"sm_mhz": statistics.median(r[1] for r in used), "sm_max_mhz": max(r[2] for r in used), "reasons": reasons,
+                "power_w_max": max(r[3] for r in used), "samples": len(used)}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -238,11 +271,12 @@ def main_gpu(args):
 
     # ---- value: inputs resident in HBM ----------------------------------------------------------------------------
     step_dev = lambda: hot_path(clean_d, noise_d, snr_d)
-    for _ in range(max(args.warmup, 3)):
-        step_dev()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # up and sampling before the warm-up: its start-up must not perturb the timed region
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sampler.mark_begin()
     ms_total, out = timed(step_dev, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     assert int(out[2].abs().sum().item()) == 0, "synthetic batch produced rejected rows"

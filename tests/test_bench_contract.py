@@ -57,3 +57,18 @@ def test_experiment_hooks_stay_out_of_the_product_path():
     for name in ("bench.py", "__graft_entry__.py"):
         src = open(os.path.join(ROOT, name)).read()
         assert 'for var in ("NRSE_EXPERIMENT", "NRSE_B200_LIB")' in src, name
+
+
+def test_clock_sampler_parses_time_stamped_samples():
+    """bench.py samples nvidia-smi during the timed region (the sampler is started before the warm-up and its samples are
+    time-stamped, so its start-up neither perturbs nor pollutes the region): the line parser on a captured line."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("nrse_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    line = "2026/10/18 17:03:21.123, 0, 1485, 1965, 615.03, 0x0000000000000004, Not Active, Not Active, Not Active, Active"
+    ts, sm, smax, power, reasons = bench.ClockSampler.parse_line(line)
+    assert (sm, smax, power, reasons) == (1485.0, 1965.0, 615.03, ["sw_power_cap"]) and ts is not None
+    assert bench.ClockSampler.parse_line("N/A, 0, [N/A]") is None
+    s = bench.ClockSampler(0)
+    assert s.stop()["reasons"] == ["nvidia-smi unavailable"]   # never started: reported, not raised
