@@ -52,6 +52,35 @@ const char* nrse_strerror(int status);
 int nrse_last_cuda_error(void);
 /* 0 if the current device is compute capability 10.x, else NRSE_ERR_NO_DEVICE / NRSE_ERR_CUDA. */
 int nrse_check_device(void);
+/* 1 if this library was built with -DNRSE_EXPERIMENTS (scripts-only timing build whose NRSE_EXPERIMENT environment
+ * hooks produce wrong results), 0 for the product build.  smoke() and bench.py refuse a library that returns 1. */
+int nrse_experiments_build(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused tensor health check: one launch over n_tensors <= NRSE_CHECK_MAX_TENSORS fp32 tensors, one 64-byte record
+ * per tensor.  Replaces check_audio_tensor, ref:src/utils/debugging_utils.py:4-30 (called four times per step,
+ * ref:train_byol.py:52-59; >= 4 passes and >= 4 host synchronisations per tensor in the reference).
+ *   tensors_host / numel_host  HOST arrays of device pointers (4-byte aligned) and element counts
+ *   out     DEVICE [n_tensors] records; flags bit 0 = NaN present, bit 1 = Inf present, bit 2 = sum|x| < min_threshold,
+ *           bit 3 = max|x| > max_threshold -- the reference's four tests, which it reports in this order;
+ *           abs_max / max / min / abs_sum / sum / sumsq / numel are what its DEBUG statistics are derived from
+ *           (mean = sum / numel, unbiased std from sumsq).  One cudaMemsetAsync + one kernel on `stream`.
+ * ------------------------------------------------------------------------------------------- */
+#define NRSE_CHECK_MAX_TENSORS 8
+typedef struct {
+  int32_t flags;
+  float abs_max;
+  float max;
+  float min;
+  double abs_sum;
+  double sum;
+  double sumsq;
+  int64_t numel;
+  int64_t reserved;
+  int64_t reserved2;
+} nrse_tensor_check;
+int nrse_check_tensors_f32(const float* const* tensors_host, const int64_t* numel_host, int n_tensors,
+                           float max_threshold, float min_threshold, nrse_tensor_check* out, nrse_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused SNR mix + peak normalisation + z-normalisation.
@@ -75,27 +104,34 @@ int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t
                            const double* snr_db_table_host, int n_snr,
                            float* clean_out, float* noisy_out, int32_t* status,
                            int B, int L, int L_noise, int peak_norm, nrse_stream_t stream);
-/* Device-side retry ("try another noise file", ref:src/data/noisy_speech_dataset.py:58-84): same operation, but only
- * rows whose status[b] != 0 on entry are processed -- with the noise of row (b + noise_row_shift) % B -- and get
- * their outputs and status rewritten; all other rows are left untouched.  The CTAs of good rows exit at once, so a
- * retry launch on a healthy batch costs a kernel launch and no memory traffic, and the host never has to read the
- * status to decide whether to retry. */
+/* Device-side retry ("try another noise file, draw another SNR", ref:src/data/noisy_speech_dataset.py:58-84): same
+ * operation, but only rows whose status[b] != 0 on entry are processed -- with the noise AND the SNR index of row
+ * (b + noise_row_shift) % B, i.e. an independent re-draw of both, as the reference's next attempt makes -- and get their
+ * outputs and status rewritten; all other rows are left untouched.  snr_idx itself is never modified;
+ * snr_idx_used (nullable, [B]) receives, for every row processed by THIS call, the table index it was mixed at (seed
+ * it with a copy of snr_idx), so that the batch's "snr" labels follow the re-draw.  The CTAs of good rows exit at
+ * once, so a retry launch on a healthy batch costs a kernel launch and no memory traffic, and the host never has to
+ * read the status to decide whether to retry. */
 int nrse_mix_normalize_retry_f32(const float* clean, const float* noise, const int32_t* snr_idx,
                                  const double* snr_db_table_host, int n_snr,
-                                 float* clean_out, float* noisy_out, int32_t* status,
+                                 float* clean_out, float* noisy_out, int32_t* status, int32_t* snr_idx_used,
                                  int B, int L, int L_noise, int peak_norm, int noise_row_shift,
                                  nrse_stream_t stream);
+/* After the retries: every row whose status is still != 0 takes over clean_out / noisy_out (and snr_idx_used) of the
+ * nearest following good row of the batch -- the reference moves on to the next item when one is unusable
+ * (ref:src/data/noisy_speech_dataset.py:60-66) and never emits a zero waveform.  status is left as it is (it keeps
+ * reporting why the row failed).  Good rows' CTAs exit at once: no data moves on a healthy batch, no host sync ever.
+ * clean_out and snr_idx_used are nullable. */
+int nrse_mix_substitute_rows_f32(float* clean_out, float* noisy_out, const int32_t* status, int32_t* snr_idx_used, int B,
+                                 int L, nrse_stream_t stream);
 const char* nrse_mix_status_name(int status_code);
-/* 4 (default): on-chip resident -- one 1024-thread CTA per SM keeps its segment of the row in registers (128 KB) and
- * shared memory (<= 192 KB) between the three passes; a cluster of 1/2/4/8 CTAs per row, exchanges by st.async + mbarrier;
- * rows up to 8 x 40960 samples (20 s), longer rows use variant 3.
- * 3: streaming -- one 1024-thread CTA (or a small cluster for small batches) per row, pass 1 from HBM, passes
- * 2-3 from L2, streaming stores; 2: persistent clusters, rows double-buffered in shared memory by bulk async copies (the
- * next row streams in while the current one is processed); 1: one row per cluster, single stage; 0: always the
- * re-read-from-L2 kernel.  1..4 need 16-byte aligned rows, L % 4 == 0, L_noise >= L and a row that fits the cluster;
- * otherwise the library falls back to the next lower variant by itself. */
+/* 4 (default): on-chip resident -- the CTAs of a cluster (1..8 per row) keep their segment of the row in registers and
+ * shared memory between the three passes, exchanges by st.async + mbarrier; needs 16-byte aligned rows, L % 4 == 0,
+ * L_noise >= L and a row of at most 8 x 40960 samples (20 s).  5: the same, forcing the 1024-thread one-CTA-per-SM shape.
+ * 0: always the generic kernel (4 CTAs per row, pass 1 from HBM, passes 2-3 re-read from L2), which is also what rows
+ * outside the resident kernel's limits (unaligned, tiled noise, > 20 s) fall back to by themselves. */
 int nrse_mix_set_variant(int variant);
-/* tuning: CTAs per row for variants 3 and 4 (1..8); 0 = automatic (default) */
+/* tuning: CTAs per row of the resident kernel (1..8); 0 = automatic (default) */
 int nrse_mix_set_cluster(int ctas_per_row);
 /* tuning: shared-memory carveout (percent of 228 KB) of the resident kernels; -1 = just what the CTAs need (default) */
 int nrse_mix_set_carveout(int percent);
@@ -188,9 +224,12 @@ int nrse_asp_pool_bwd(const float* x, const float* hl, const float* attention, c
  *   loss   [1] fp32 = 2 - 2*mean_b clamp(<p^,z^>, -1, 1)
  *   saved  [B,4] fp32 = (||p+1e-10||, ||z+1e-10||, unclamped similarity, 0) for the backward
  *   row_sim (nullable) [B] fp32 clamped similarities (evaluate_byol.py:55 uses these per row)
+ *   flags  (nullable) [1] int32: the reference's two diagnostics (ref:src/models/byol.py:109-122), evaluated inside
+ *          the same launch: bit 0 / 1 = NaN in p / z before normalisation, bit 2 / 3 = NaN in p / z after it
+ *          (an input NaN, or an Inf that normalises to Inf / Inf)
  * Backward w.r.t. p only (the target branch is under no_grad, ref:src/models/byol.py:94-96).
  * ------------------------------------------------------------------------------------------- */
-int nrse_byol_loss_fwd(const void* p, const void* z, float* loss, float* saved, float* row_sim,
+int nrse_byol_loss_fwd(const void* p, const void* z, float* loss, float* saved, float* row_sim, int32_t* flags,
                        int B, int D, int dtype, nrse_stream_t stream);
 int nrse_byol_loss_bwd(const void* p, const void* z, const float* saved, const float* grad_loss,
                        void* grad_p, int B, int D, int dtype, nrse_stream_t stream);
@@ -264,44 +303,61 @@ int nrse_conv_frontend_set_tile_order(int alternate);
 int nrse_conv_frontend_set_l2_prefetch(int on);
 
 /* ---------------------------------------------------------------------------------------------
- * Training forward and backward of the feature encoder (LayerNorm mode; wavlm-large).
- * Replaces what autograd records through hf:models/wavlm/modeling_wavlm.py:703-727 x 7 for the online branch
- * (ref:train_byol.py:66 `loss.backward()`).  The training forward additionally keeps, on a caller-provided tape,
- * the bf16 activations of layers 0..5, the normalised pre-affine activation `xhat` and 1/std of every frame.
- * Backward, per layer from 6 to 0:  dOut -> dZ (LayerNorm + GELU backward, also dgamma / dbeta), dW = dZ^T A
- * (tcgen05, MN-major operands, split-K, fp32 atomics), dX = dZ W (two forward-like GEMMs over even/odd frames).
- * Weight gradients come out as fp32 in the PACKED K order [512, tap*512 + c_in] (layer 0: [512, 10]); the input
- * waveform gradient is not computed (the reference never uses it).
+ * Training forward and backward of the feature encoder, both norm modes.
+ * Replaces what autograd records through hf:models/wavlm/modeling_wavlm.py:703-727 x 7 (LayerNorm mode, wavlm-large)
+ * or :730-751 + :682-700 x 6 (GroupNorm mode, wavlm-base) for the online branch (ref:train_byol.py:66
+ * `loss.backward()`; partial unfreeze: ref:src/models/emotion.py:114-129).  The training forward additionally keeps,
+ * on a caller-provided tape, the bf16 activations of layers 0..5, `xhat` of every layer (the normalised pre-affine
+ * activation; for a layer without a normalisation the pre-GELU activation itself) and the statistics the backward
+ * needs (1/std per frame in LayerNorm mode, 1/std per (utterance, channel) of layer 0 in GroupNorm mode).
+ * Backward, per layer from 6 down:  dOut -> dZ (norm + GELU backward, also dgamma / dbeta), dW = dZ^T A (tcgen05,
+ * MN-major operands, split-K, fp32 atomics), dX = dZ W (two forward-like GEMMs over even / odd frames).  Layer 0:
+ * SIMT weight gradient (LayerNorm mode) / one fused pass that never materialises dZ (GroupNorm mode).
+ * The input waveform gradient is not computed (nothing upstream of the waveform is trainable in the reference).
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   const void* wt_even[NRSE_FRONTEND_LAYERS - 1]; /* bf16 [512 c_in, n_even*512]: taps (0,2) for k=3, (0) for k=2 */
   const void* wt_odd[NRSE_FRONTEND_LAYERS - 1];  /* bf16 [512 c_in, 512]: tap 1 */
 } nrse_frontend_bwd_weights;
+/* Gradients, fp32, in the CHECKPOINT layouts.  Every pointer is nullable: NULL = "this tensor needs no gradient"
+ * (frozen parameter).  Nothing below the lowest layer that wants a gradient is computed, and a layer's weight-gradient
+ * GEMM is skipped when its dw is NULL.  Non-NULL tensors are ACCUMULATED into (+=): the caller zeroes them (one memset
+ * over its gradient arena).  dgamma[i] / dbeta[i] must be both NULL or both set; GroupNorm mode has them for layer 0 only. */
 typedef struct {
-  float* dw0;                             /* [512, 10] */
-  float* dw[NRSE_FRONTEND_LAYERS - 1];    /* [512, k_i*512] packed K order */
+  float* dw0;                             /* [512, 1, 10] */
+  float* dw[NRSE_FRONTEND_LAYERS - 1];    /* [512, 512, k_i] */
   float* dgamma[NRSE_FRONTEND_LAYERS];    /* [512] */
   float* dbeta[NRSE_FRONTEND_LAYERS];
 } nrse_frontend_grads;
 
 size_t nrse_conv_frontend_tape_bytes(int B, int L);
-int nrse_conv_frontend_fwd_train(const float* x, const nrse_frontend_params* params_host, void* y, int y_dtype,
-                                 void* tape, size_t tape_bytes, int B, int L, nrse_stream_t stream);
+int nrse_conv_frontend_fwd_train(const float* x, const nrse_frontend_params* params_host, int norm_mode, void* y,
+                                 int y_dtype, void* tape, size_t tape_bytes, int B, int L, nrse_stream_t stream);
 /* w [512,512,k] fp32 -> the two data-gradient operands described above */
 int nrse_conv_frontend_pack_weights_dgrad(const float* w, void* wt_even, void* wt_odd, int k, nrse_stream_t stream);
 size_t nrse_conv_frontend_bwd_workspace_bytes(int B, int L);
-/* dy [B*P_6, 512] fp32 with zeros in the pitch padding; every tensor of `grads` is overwritten. */
+/* dy [B, dy_pitch, 512] fp32: the gradient of the features; frame (b, t < T_6) at row b * dy_pitch + t (dy_pitch = T_6 for
+ * a compact gradient, P_6 for a pitch-padded one; rows t >= T_6 are never read). */
 int nrse_conv_frontend_bwd(const float* x, const nrse_frontend_params* params_host,
-                           const nrse_frontend_bwd_weights* bwd_weights_host, const void* tape, const float* dy,
-                           const nrse_frontend_grads* grads_host, void* workspace, size_t workspace_bytes, int B, int L,
-                           nrse_stream_t stream);
-/* building blocks (per-layer parity tests) */
-int nrse_ln_gelu_bwd(const void* dout, int dout_dtype, const void* xhat, const float* rstd, const float* gamma,
-                     const float* beta, void* dz, float* dgamma, float* dbeta, int64_t rows, int P, int T,
-                     nrse_stream_t stream);
+                           const nrse_frontend_bwd_weights* bwd_weights_host, int norm_mode, const void* tape,
+                           const float* dy, int dy_pitch, const nrse_frontend_grads* grads_host, void* workspace,
+                           size_t workspace_bytes, int B, int L, nrse_stream_t stream);
+/* building blocks (per-layer parity tests).
+ *   nrse_ln_gelu_bwd: dOut -> dZ.  dout bf16 [rows, 512] (may alias dz) or fp32 [B, dout_pitch, 512]; gamma == NULL
+ *     selects the no-norm form dZ = dOut gelu'(xhat) (xhat = the pre-GELU activation); dgamma / dbeta nullable, accumulated.
+ *   nrse_conv_layer_wgrad: dW += dZ^T A, fp32, packed K order [512, tap*512 + c] or (ckpt_layout) [512, 512, k].
+ *   nrse_conv_layer0_gn_bwd: GroupNorm-mode layer 0, dOut0 bf16 [B*P0, 512] + xhat0 + per-(b,c) 1/std [B,512] ->
+ *     dw0 / dgamma / dbeta (nullable, accumulated); scratch = nrse_conv_layer0_gn_bwd_scratch_bytes(B) bytes. */
+int nrse_ln_gelu_bwd(const void* dout, int dout_dtype, int dout_pitch, const void* xhat, const float* rstd,
+                     const float* gamma, const float* beta, void* dz, float* dgamma, float* dbeta, int64_t rows, int P,
+                     int T, nrse_stream_t stream);
 int nrse_conv_layer0_wgrad(const float* x, const void* dz0, float* dw0, int B, int L, int T0, int P0,
                            nrse_stream_t stream);
-int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out, int k, float* dw_packed,
+size_t nrse_conv_layer0_gn_bwd_scratch_bytes(int B);
+int nrse_conv_layer0_gn_bwd(const float* x, const void* dout0, const void* xhat0, const float* gn_rstd,
+                            const float* gamma, const float* beta, float* dw0, float* dgamma, float* dbeta,
+                            void* scratch, int B, int L, int T0, int P0, nrse_stream_t stream);
+int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out, int k, float* dw, int ckpt_layout,
                           nrse_stream_t stream);
 int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even, const void* wt_odd, int k, void* dx,
                           nrse_stream_t stream);

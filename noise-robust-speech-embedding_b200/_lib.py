@@ -40,6 +40,13 @@ class FrontendBwdWeights(C.Structure):
     _fields_ = [("wt_even", C.c_void_p * (N_LAYERS - 1)), ("wt_odd", C.c_void_p * (N_LAYERS - 1))]
 
 
+class TensorCheck(C.Structure):
+    """struct nrse_tensor_check (64 bytes)."""
+    _fields_ = [("flags", C.c_int32), ("abs_max", C.c_float), ("max", C.c_float), ("min", C.c_float),
+                ("abs_sum", C.c_double), ("sum", C.c_double), ("sumsq", C.c_double), ("numel", C.c_int64),
+                ("reserved", C.c_int64), ("reserved2", C.c_int64)]
+
+
 class FrontendGrads(C.Structure):
     """struct nrse_frontend_grads."""
     _fields_ = [("dw0", C.c_void_p), ("dw", C.c_void_p * (N_LAYERS - 1)), ("dgamma", C.c_void_p * N_LAYERS),
@@ -54,8 +61,11 @@ SIGNATURES = {
     "nrse_strerror": (C.c_char_p, [_i]),
     "nrse_last_cuda_error": (_i, []),
     "nrse_check_device": (_i, []),
+    "nrse_experiments_build": (_i, []),
+    "nrse_check_tensors_f32": (_i, [_p, _p, _i, _f, _f, _p, _p]),
     "nrse_mix_normalize_f32": (_i, [_p, _p, _p, C.POINTER(C.c_double), _i, _p, _p, _p, _i, _i, _i, _i, _p]),
-    "nrse_mix_normalize_retry_f32": (_i, [_p, _p, _p, C.POINTER(C.c_double), _i, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "nrse_mix_normalize_retry_f32": (_i, [_p, _p, _p, C.POINTER(C.c_double), _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "nrse_mix_substitute_rows_f32": (_i, [_p, _p, _p, _p, _i, _i, _p]),
     "nrse_mix_status_name": (C.c_char_p, [_i]),
     "nrse_mix_set_variant": (_i, [_i]),
     "nrse_mix_set_cluster": (_i, [_i]),
@@ -70,7 +80,7 @@ SIGNATURES = {
     "nrse_asp_pool_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "nrse_asp_pool_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "nrse_asp_pool_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i, _i, _i, _p]),
-    "nrse_byol_loss_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "nrse_byol_loss_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "nrse_byol_loss_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "nrse_conv_frontend_geometry": (_i, [_i, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "nrse_conv_frontend_workspace_bytes": (_sz, [_i, _i]),
@@ -83,14 +93,16 @@ SIGNATURES = {
     "nrse_conv_frontend_set_tile_order": (_i, [_i]),
     "nrse_conv_frontend_set_l2_prefetch": (_i, [_i]),
     "nrse_conv_frontend_tape_bytes": (_sz, [_i, _i]),
-    "nrse_conv_frontend_fwd_train": (_i, [_p, C.POINTER(FrontendParams), _p, _i, _p, _sz, _i, _i, _p]),
+    "nrse_conv_frontend_fwd_train": (_i, [_p, C.POINTER(FrontendParams), _i, _p, _i, _p, _sz, _i, _i, _p]),
     "nrse_conv_frontend_pack_weights_dgrad": (_i, [_p, _p, _p, _i, _p]),
     "nrse_conv_frontend_bwd_workspace_bytes": (_sz, [_i, _i]),
-    "nrse_conv_frontend_bwd": (_i, [_p, C.POINTER(FrontendParams), C.POINTER(FrontendBwdWeights), _p, _p,
+    "nrse_conv_frontend_bwd": (_i, [_p, C.POINTER(FrontendParams), C.POINTER(FrontendBwdWeights), _i, _p, _p, _i,
                                     C.POINTER(FrontendGrads), _p, _sz, _i, _i, _p]),
-    "nrse_ln_gelu_bwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p]),
+    "nrse_ln_gelu_bwd": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p]),
     "nrse_conv_layer0_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
-    "nrse_conv_layer_wgrad": (_i, [_p, _p, _i64, _i, _p, _p]),
+    "nrse_conv_layer0_gn_bwd_scratch_bytes": (_sz, [_i]),
+    "nrse_conv_layer0_gn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "nrse_conv_layer_wgrad": (_i, [_p, _p, _i64, _i, _p, _i, _p]),
     "nrse_conv_layer_dgrad": (_i, [_p, _i64, _p, _p, _i, _p, _p]),
 }
 

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnrse_b200.so")
-SOURCES = ["runtime.cu", "mix.cu", "ema.cu", "optim.cu", "pool.cu", "loss.cu", "frontend.cu"]
+SOURCES = ["runtime.cu", "check.cu", "mix.cu", "ema.cu", "optim.cu", "pool.cu", "loss.cu", "frontend.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", os.path.join(ROOT, "include", "nrse_b200.h")]
 
 NVCC_FLAGS = [
@@ -41,16 +41,23 @@ def _newer(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(BUILD, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+    """Product library: csrc/libnrse_b200.so.  ``experiments=True`` builds the scripts-only timing variant
+    csrc/build_exp/libnrse_b200_exp.so with -DNRSE_EXPERIMENTS (its NRSE_EXPERIMENT environment hooks skip stores /
+    statistics and produce WRONG results; select it with NRSE_B200_LIB from scripts/, never from tests or bench.py --
+    both refuse a library whose nrse_experiments_build() returns 1)."""
+    build_dir = os.path.join(HERE, "build_exp") if experiments else BUILD
+    lib = os.path.join(build_dir, "libnrse_b200_exp.so") if experiments else LIB
+    flags = NVCC_FLAGS + (["-DNRSE_EXPERIMENTS"] if experiments else [])
+    os.makedirs(build_dir, exist_ok=True)
     nvcc = _nvcc()
     headers = [h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS] + [os.path.abspath(__file__)]
 
     def compile_one(src: str):
-        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+        obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         if not force and not _newer(obj, [os.path.join(HERE, src)] + headers):
             return obj, ""
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(HERE, src), "-o", obj]
+        cmd = [nvcc, *flags, "-c", os.path.join(HERE, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -63,13 +70,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for _, log in results:
             if log:
                 print(log)
-    if force or _newer(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    if force or _newer(lib, objs):
+        cmd = [nvcc, "-shared", "-o", lib, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, experiments="--experiments" in sys.argv))

@@ -41,6 +41,16 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+// Timing experiments that deliberately produce WRONG results (skipped stores / statistics, redirected outputs) exist only
+// in the scripts-only build `csrc/build.py --experiments` (-DNRSE_EXPERIMENTS, libnrse_b200_exp.so, selected with
+// NRSE_B200_LIB): there the NRSE_EXPERIMENT environment variable supplies the flags.  In the product library the macro
+// below is the constant `false`, the flag tests fold away and no environment variable is ever read.
+#ifdef NRSE_EXPERIMENTS
+#define NRSE_EXP(flags, bit) (((flags) & (bit)) != 0)
+#else
+#define NRSE_EXP(flags, bit) (false)
+#endif
+
 namespace nrse {
 namespace {
 
@@ -95,8 +105,10 @@ struct L0Args {
   const float* beta;   //                              per-(b,c) shift  [B, 512]
   __nv_bfloat16* out;  // [B*P0, 512]
   int B, L, T0, P0;
-  __nv_bfloat16* xhat;  // nullable (training forward, LayerNorm mode): normalised pre-affine values [B*P0, 512]
-  float* rstd;          // nullable: [B*P0]
+  __nv_bfloat16* xhat;  // nullable (training forward): normalised pre-affine values [B*P0, 512]
+  float* rstd;          // nullable (LayerNorm mode): [B*P0]
+  const float* gn_rstd; // GroupNorm-mode training forward: per-(b,c) 1/std and mean/std [B, 512] (layer0_gn_finalize_kernel)
+  const float* gn_mr;
   int exp_flags;        // timing experiments (NRSE_EXPERIMENT): 1 = no output stores
 };
 
@@ -180,13 +192,27 @@ __global__ void __launch_bounds__(kL0Threads, 1) layer0_kernel(const L0Args a) {
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const float4* g4 = reinterpret_cast<const float4*>(a.gamma + static_cast<size_t>(b) * kC + h * 256 + 8 * lane);
-        const float4* b4 = reinterpret_cast<const float4*>(a.beta + static_cast<size_t>(b) * kC + h * 256 + 8 * lane);
+        const size_t off = static_cast<size_t>(b) * kC + h * 256 + 8 * lane;
+        const float4* g4 = reinterpret_cast<const float4*>(a.gamma + off);
+        const float4* b4 = reinterpret_cast<const float4*>(a.beta + off);
         const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[h * 8 + j] = fmaf(y[h * 8 + j], g[j], bb[j]);
+        if (a.xhat != nullptr) {  // training forward: keep (z - mean_bc) / std_bc for the backward
+          const float4* r4 = reinterpret_cast<const float4*>(a.gn_rstd + off);
+          const float4* m4 = reinterpret_cast<const float4*>(a.gn_mr + off);
+          const float4 r0 = __ldg(r4), r1 = __ldg(r4 + 1), m0 = __ldg(m4), m1 = __ldg(m4 + 1);
+          const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          const float mr[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          float xh[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xh[j] = fmaf(y[h * 8 + j], r[j], -mr[j]);
+          reinterpret_cast<uint4*>(a.xhat + m * kC)[h * 32 + lane] =
+              make_uint4(pack_bf16x2(xh[0], xh[1]), pack_bf16x2(xh[2], xh[3]), pack_bf16x2(xh[4], xh[5]),
+                         pack_bf16x2(xh[6], xh[7]));
+        }
       }
     }
 #pragma unroll
@@ -230,7 +256,8 @@ __global__ void __launch_bounds__(kL0Threads, 1) layer0_gn_partial_kernel(const 
 // (sum, sumsq) partials -> per-(b,c) scale = gamma * rstd, shift = beta - mean * scale
 __global__ void layer0_gn_finalize_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
                                           const float* __restrict__ beta, float* __restrict__ scale,
-                                          float* __restrict__ shift, int B, int T0) {
+                                          float* __restrict__ shift, float* __restrict__ rstd_out,
+                                          float* __restrict__ mr_out, int B, int T0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * kC) return;
   const int b = i / kC, c = i % kC;
@@ -246,6 +273,10 @@ __global__ void layer0_gn_finalize_kernel(const float* __restrict__ part, const 
   const float sc = gamma[c] * rstd;
   scale[i] = sc;
   shift[i] = beta[c] - static_cast<float>(mean) * sc;
+  if (rstd_out != nullptr) {  // training forward: kept on the tape for the backward
+    rstd_out[i] = rstd;
+    mr_out[i] = static_cast<float>(mean) * rstd;
+  }
 }
 
 // =========================================================================================================
@@ -298,7 +329,7 @@ struct OutStage {
 // which = 0: the output through `tmap`; 1: the second tensor through `tmap2` (the two alternate, so "the previous store
 // into THIS buffer has been read" is "at most one bulk group pending")
 __device__ __forceinline__ void out_stage_store(const OutStage& o, const uint32_t (&v)[16], int col, int which = 0) {
-  if (o.lane == 0 && !(o.exp_flags & 128)) {  // the engine has read the previous chunk out of this buffer
+  if (o.lane == 0 && !NRSE_EXP(o.exp_flags, 128)) {  // the engine has read the previous chunk out of this buffer
     if (o.tmap2 != nullptr) ptx::bulk_wait_read<1>();
     else ptx::bulk_wait_read<0>();
   }
@@ -308,7 +339,7 @@ __device__ __forceinline__ void out_stage_store(const OutStage& o, const uint32_
 #pragma unroll
   for (uint32_t j = 0; j < 4; ++j)
     ptx::st_shared_v4(row + ((j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  if (!(o.exp_flags & 64)) ptx::fence_proxy_async_smem();
+  if (!NRSE_EXP(o.exp_flags, 64)) ptx::fence_proxy_async_smem();
   __syncwarp();
   if (o.lane == 0) {  // an inactive warp still commits (empty) groups: the wait above counts groups
     const CUtensorMap* tm = which ? o.tmap2 : o.tmap;
@@ -595,7 +626,7 @@ __device__ __forceinline__ void epilogue_row(const EpiCtx& e) {
           for (int j = 0; j < 16; ++j) xh16[j] = 0;
         }
         out_stage_store(e.ost, xh16, c * 32, 1);
-      } else if (e.store && e.has_norm && e.xhat_row != nullptr) {
+      } else if (e.store && e.xhat_row != nullptr) {  // without a norm (GroupNorm-mode layers 1-6) this is Z itself
         char* dst = reinterpret_cast<char*>(e.xhat_row + c * 32);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -792,11 +823,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           // input frame of tap j for output frame m is stride*m + j = stride*(m + j/stride) + j%stride
           const int tap = kb >> 3, c0 = (kb & 7) * kBlockK;
           if (g.a_2d) ptx::tma_load_2d(a_dst, &tmap_a, bar(kFull + stage), c0, m0 + (tap == 0 ? g.a_row_off[0] : g.a_row_off[1]));
-          else if (g.exp_flags & 16) ptx::tma_load_3d_hint(a_dst, &tmap_a, bar(kFull + stage), c0, tap % g.stride, m0 + tap / g.stride, ptx::kL2EvictFirst);
+          else if (NRSE_EXP(g.exp_flags, 16)) ptx::tma_load_3d_hint(a_dst, &tmap_a, bar(kFull + stage), c0, tap % g.stride, m0 + tap / g.stride, ptx::kL2EvictFirst);
           else ptx::tma_load_3d(a_dst, &tmap_a, bar(kFull + stage), c0, tap % g.stride, m0 + tap / g.stride);
 #pragma unroll
           for (int h = 0; h < Cfg::kNumMma; ++h) {
-            if (g.exp_flags & 32)
+            if NRSE_EXP(g.exp_flags, 32)
               ptx::tma_load_2d_hint(b_dst + h * (kUmmaN * kBlockK * 2), &tmap_w, bar(kFull + stage), kb * kBlockK,
                                     n0 + h * kUmmaN, ptx::kL2EvictLast);
             else
@@ -867,14 +898,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ost.col0 = n0;
       ost.row0 = static_cast<int>(m) - lane;
       ost.lane = lane;
-      ost.active = ost.row0 < g.M_total && !(g.exp_flags & 1);
-      if (g.exp_flags & 4) ost.row0 &= 16383;  // timing experiment: every store lands in the same 16 MB (L2-resident)
-      ost.policy = (g.exp_flags & 8) ? 0ull : ptx::kL2EvictFirst;
+      ost.active = ost.row0 < g.M_total && !NRSE_EXP(g.exp_flags, 1);
+      if NRSE_EXP(g.exp_flags, 4) ost.row0 &= 16383;  // timing experiment: every store lands in the same 16 MB (L2-resident)
+      ost.policy = NRSE_EXP(g.exp_flags, 8) ? 0ull : ptx::kL2EvictFirst;
       ost.exp_flags = g.exp_flags;
 
       if (g.mode == 1) {
         const long long orow = m * g.out_row_mul + g.out_row_add;
-        epilogue_plain_row<kClusterN>(taddr, bar(kTmemEmpty + buf), m < g.M_total && !(g.exp_flags & 1),
+        epilogue_plain_row<kClusterN>(taddr, bar(kTmemEmpty + buf), m < g.M_total && !NRSE_EXP(g.exp_flags, 1),
                                       reinterpret_cast<__nv_bfloat16*>(g.out) + orow * kC + n0, ost);
         continue;
       }
@@ -889,8 +920,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ec.arm = row == 0;
       ec.peer = peer;
       ec.s_gb = s_gb;
-      ec.has_norm = has_norm && !(g.exp_flags & 2);
-      ec.store = m < g.M_total && !(g.exp_flags & 1);
+      ec.has_norm = has_norm && !NRSE_EXP(g.exp_flags, 2);
+      ec.store = m < g.M_total && !NRSE_EXP(g.exp_flags, 1);
       ec.zero = false;
       ec.out_f32 = g.out_f32 != 0;
       ec.out_row = g.out_f32 ? static_cast<void*>(reinterpret_cast<float*>(g.out) + m * kC + n0)
@@ -951,9 +982,14 @@ struct Epi2Ctx {
   const float* s_beta;            // [512]
   int ch0, ch1;                   // first channel of this thread's slice in buffer 0 / 1
   void* out_row;                  // this frame's output row (channel 0)
-  OutStage ost;                   // bf16 output through the staging buffer + TMA store (col0 = 0)
+  float* rstd_out;                // training forward: where this frame's 1/std goes (one team writes it), else nullptr
+  OutStage ost;                   // bf16 output through the staging buffer + TMA store (col0 = 0); training forward:
+                                  // ost.tmap2 = the xhat tensor, through the warp's second staging buffer
 };
 
+// kSave (training forward): also keep the normalised pre-affine activation xhat (bf16; without a norm: the pre-GELU
+// activation itself) and 1/std of every frame for the backward.
+template <bool kSave>
 __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
   constexpr int kChunks = 4;  // 128 columns per buffer per thread
   // This thread's slice of buffer 0 is read ONCE and kept in registers (128 of the ~200 a 320-thread CTA can give a
@@ -1040,6 +1076,9 @@ __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
     m2 = m2 + o.y + delta * delta * 128.0f;
     mean = 0.5f * (mean_c + o.x);
     rstd = rsqrtf(m2 * (1.0f / kC) + kNormEps);
+    if constexpr (kSave) {
+      if (e.rstd_out != nullptr && e.store) *e.rstd_out = rstd;
+    }
   } else {
     ptx::mbar_wait(e.bar_full1, e.parity);
     ptx::tc_fence_after();
@@ -1053,6 +1092,7 @@ __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
     const float4* g4p = reinterpret_cast<const float4*>(e.s_gamma + ch);  // gamma / 2, beta / 2: see epilogue_row
     const float4* b4p = reinterpret_cast<const float4*>(e.s_beta + ch);
     uint32_t o16[16];
+    [[maybe_unused]] uint32_t xh16[kSave ? 16 : 1];
     float o32[32];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
@@ -1061,6 +1101,11 @@ __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
       for (int k = 0; k < 2; ++k) {
         const int j = 2 * jj + k;
         f2 x = f2_fma(f2_bits(r[2 * j], r[2 * j + 1]), rstd2, nmr2);
+        if constexpr (kSave) {
+          float h0, h1;
+          f2_split(x, h0, h1);
+          xh16[j] = pack_bf16x2(h0, h1);
+        }
         x = k == 0 ? f2_fma(x, f2_make(g4.x, g4.y), f2_make(b4.x, b4.y))
                    : f2_fma(x, f2_make(g4.z, g4.w), f2_make(b4.z, b4.w));
         float y0, y1;
@@ -1070,6 +1115,7 @@ __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
         o32[2 * j + 1] = y1;
       }
     }
+    if constexpr (kSave) out_stage_store(e.ost, xh16, ch, 1);  // training forward: bf16 output only (ost.tmap set)
     if (e.ost.tmap != nullptr) {
       out_stage_store(e.ost, o16, ch);
     } else if (e.store) {
@@ -1097,26 +1143,32 @@ __device__ __forceinline__ void epilogue_row_2sm(const Epi2Ctx& e) {
   walk(e.taddr1, emit32, [&] { release(e.bar_empty1, e.empty1_cluster); });
 }
 
-struct Gemm2Cfg {
+template <bool kSave>
+struct Gemm2CfgT {
   static constexpr int kThreads = 64 + 2 * kEpiThreads;  // warp 0 TMA, warp 1 MMA (leader CTA issues), 2 epilogue teams
-  static constexpr int kStages = 6;
+  static constexpr int kStages = kSave ? 5 : 6;           // the training forward's second staging buffers cost one stage
+  static constexpr int kOutBufs = kSave ? 2 : 1;          // staging buffers per epilogue warp (output, xhat)
   static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB: this CTA's 128 frames
   static constexpr int kBHalfRows = kUmmaN / 2;           // 128 of the 256 weight rows of one MMA
   static constexpr int kBHalfBytes = kBHalfRows * kBlockK * 2;  // 16 KB
   static constexpr int kStageBytes = kABytes + kBHalfBytes;
   static constexpr int kOutOff = kStages * kStageBytes;   // one output staging buffer per epilogue warp (see OutStage)
-  static constexpr int kGbOff = kOutOff + 8 * kOutStageBytes;  // gamma[512] / 2 then beta[512] / 2
+  static constexpr int kGbOff = kOutOff + 8 * kOutBufs * kOutStageBytes;  // gamma[512] / 2 then beta[512] / 2
   static constexpr int kStatsOff = kGbOff + kC * 8;
   static constexpr int kBarOff = kStatsOff + 4 * kBlockM * 8;
   static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kSmemBytes = kTmemPtrOff + 16 + 1024;
 };
+using Gemm2Cfg = Gemm2CfgT<false>;
+static_assert(Gemm2CfgT<true>::kSmemBytes <= 227 * 1024 && Gemm2CfgT<false>::kSmemBytes <= 227 * 1024, "shared memory");
 
-__global__ void __launch_bounds__(Gemm2Cfg::kThreads, 1)
+template <bool kSave>
+__global__ void __launch_bounds__(Gemm2CfgT<kSave>::kThreads, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                  const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
-  using Cfg = Gemm2Cfg;
+                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_xhat,
+                  const GemmArgs g) {
+  using Cfg = Gemm2CfgT<kSave>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -1134,6 +1186,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_w);
+    ptx::prefetch_tmap(&tmap_out);
+    if constexpr (kSave) ptx::prefetch_tmap(&tmap_xhat);
     for (int s = 0; s < Cfg::kStages; ++s) {
       ptx::mbar_init(bar(kFull + s), 1);   // used in the leader only: one expect_tx arrive, bytes from both CTAs
       ptx::mbar_init(bar(kEmpty + s), 1);  // multicast commit of the leader's MMA thread
@@ -1251,8 +1305,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       ec.bar_stats = bar(kStats + team);
       ec.stats_signal_bar = ptx::mapa(bar(kStats + (1 - team)), cta_rank);
       ec.arm = row == 0;
-      ec.has_norm = has_norm && !(g.exp_flags & 2);
-      ec.store = m < g.M_total && !(g.exp_flags & 1);
+      ec.has_norm = has_norm && !NRSE_EXP(g.exp_flags, 2);
+      ec.store = m < g.M_total && !NRSE_EXP(g.exp_flags, 1);
       ec.out_f32 = g.out_f32 != 0;
       ec.s_gamma = reinterpret_cast<const float*>(s_gb);
       ec.s_beta = reinterpret_cast<const float*>(s_gb) + kC;
@@ -1260,17 +1314,18 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       ec.ch1 = kUmmaN + team * 128;
       ec.out_row = g.out_f32 ? static_cast<void*>(reinterpret_cast<float*>(g.out) + m * kC)
                              : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(g.out) + m * kC);
+      ec.rstd_out = (kSave && g.rstd != nullptr && team == 0) ? g.rstd + m : nullptr;
       ec.ost.tmap = g.out_f32 ? nullptr : &tmap_out;
-      ec.ost.tmap2 = nullptr;
-      ec.ost.smem = smem_base + Cfg::kOutOff + static_cast<uint32_t>((warp - 2) * kOutStageBytes);
+      ec.ost.tmap2 = kSave ? &tmap_xhat : nullptr;
+      ec.ost.smem = smem_base + Cfg::kOutOff + static_cast<uint32_t>((warp - 2) * Cfg::kOutBufs * kOutStageBytes);
       ec.ost.col0 = 0;
       ec.ost.row0 = static_cast<int>(m) - lane;
       ec.ost.lane = lane;
-      ec.ost.active = ec.ost.row0 < g.M_total && !(g.exp_flags & 1);
-      if (g.exp_flags & 4) ec.ost.row0 &= 16383;
-      ec.ost.policy = (g.exp_flags & 8) ? 0ull : ptx::kL2EvictFirst;
+      ec.ost.active = ec.ost.row0 < g.M_total && !NRSE_EXP(g.exp_flags, 1);
+      if NRSE_EXP(g.exp_flags, 4) ec.ost.row0 &= 16383;
+      ec.ost.policy = NRSE_EXP(g.exp_flags, 8) ? 0ull : ptx::kL2EvictFirst;
       ec.ost.exp_flags = g.exp_flags;
-      epilogue_row_2sm(ec);
+      epilogue_row_2sm<kSave>(ec);
     }
     if (lane == 0) ptx::bulk_wait<0>();  // this warp's output stores are complete before the CTA may exit
   }
@@ -1599,7 +1654,7 @@ layer0_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
       ec.peer = peer;
       ec.s_gb = s_gb;
       ec.has_norm = !kFold;  // folded: the accumulator already holds the normalised, affine-transformed value
-      ec.store = m < m_total && !(a.exp_flags & 1);
+      ec.store = m < m_total && !NRSE_EXP(a.exp_flags, 1);
       ec.zero = static_cast<int>(m % a.P0) >= a.T0;  // pitch padding is written as zeros
       ec.out_f32 = false;
       ec.out_row = a.out + m * kC + n0 + col0;
@@ -1611,9 +1666,9 @@ layer0_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
       ec.ost.col0 = n0 + col0;
       ec.ost.row0 = static_cast<int>(m) - lane;
       ec.ost.lane = lane;
-      ec.ost.active = ec.ost.row0 < m_total && !(a.exp_flags & 1);
-      if (a.exp_flags & 4) ec.ost.row0 &= 16383;
-      ec.ost.policy = (a.exp_flags & 8) ? 0ull : ptx::kL2EvictFirst;
+      ec.ost.active = ec.ost.row0 < m_total && !NRSE_EXP(a.exp_flags, 1);
+      if NRSE_EXP(a.exp_flags, 4) ec.ost.row0 &= 16383;
+      ec.ost.policy = NRSE_EXP(a.exp_flags, 8) ? 0ull : ptx::kL2EvictFirst;
       ec.ost.exp_flags = a.exp_flags;
       epilogue_row<kClusterN, kSave, kSplit, kFold>(ec);
     }
@@ -1642,14 +1697,15 @@ constexpr int kLnBwdThreads = 256;
 constexpr int kLnBwdWarps = kLnBwdThreads / 32;
 
 struct LnBwdArgs {
-  const void* dout;  // [rows, 512] fp32 or bf16 (may alias dz)
+  const void* dout;  // bf16: [rows, 512] (may alias dz); fp32: [B, dout_P, 512], frame (b, t) at row b * dout_P + t
   int dout_f32;
-  const __nv_bfloat16* xhat;
+  int dout_P;        // fp32 only: rows per utterance of `dout` (T for a compact gradient, P for a pitch-padded one)
+  const __nv_bfloat16* xhat;  // kNorm: normalised pre-affine activation; else the pre-GELU activation Z itself
   const float* rstd;
   const float* gamma;
   const float* beta;
   __nv_bfloat16* dz;
-  float* dgamma;  // [512], accumulated with atomics (zeroed by the caller)
+  float* dgamma;  // nullable (both or neither): [512], accumulated with atomics
   float* dbeta;
   long long rows;
   int P, T;
@@ -1704,7 +1760,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kN>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory"); }
 
-template <bool kDoutF32>
+// kNorm = false: layers without a normalisation (GroupNorm-mode layers 1-6, hf:...modeling_wavlm.py:682-700):
+// dZ = dOut gelu'(Z), `xhat` holds Z, no row statistics, no affine gradients.
+template <bool kDoutF32, bool kNorm>
 __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnBwdArgs a) {
   __shared__ __align__(16) float s_gamma[kC];
   __shared__ __align__(16) float s_beta[kC];
@@ -1712,8 +1770,8 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
   extern __shared__ __align__(16) unsigned char ln_ring[];  // bf16 path only
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < kC; i += kLnBwdThreads) {
-    s_gamma[i] = a.gamma[i];
-    s_beta[i] = a.beta[i];
+    s_gamma[i] = kNorm ? a.gamma[i] : 1.0f;
+    s_beta[i] = kNorm ? a.beta[i] : 0.0f;
   }
   __syncthreads();
   // lane owns channels [8 lane, 8 lane + 8) and [256 + 8 lane, ...): 8 adjacent pairs, processed as packed fp32x2
@@ -1772,7 +1830,8 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
       const unsigned w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) xh[j] = f2_bits(w[j] << 16, w[j] & 0xffff0000u);
-      const float4* gr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.dout) + m * kC);
+      const long long drow = (m / a.P) * a.dout_P + (m % a.P);
+      const float4* gr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.dout) + drow * kC);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const float4 p0 = gr[h * 64 + 2 * lane], p1 = gr[h * 64 + 2 * lane + 1];
@@ -1791,6 +1850,18 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
         xh[j] = f2_bits(wx[j] << 16, wx[j] & 0xffff0000u);
         go[j] = f2_bits(wy[j] << 16, wy[j] & 0xffff0000u);
       }
+    }
+    if constexpr (!kNorm) {
+      uint32_t z[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float z0, z1;
+        f2_split(f2_mul(go[j], gelu_grad2(xh[j])), z0, z1);
+        z[j] = pack_bf16x2(z0, z1);
+      }
+      zrow[lane] = make_uint4(z[0], z[1], z[2], z[3]);
+      zrow[32 + lane] = make_uint4(z[4], z[5], z[6], z[7]);
+      continue;
     }
     f2 dx[8], s1 = zero2, s2 = zero2;
 #pragma unroll
@@ -1823,6 +1894,7 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
     zrow[32 + lane] = make_uint4(z[4], z[5], z[6], z[7]);
   }
   if constexpr (!kDoutF32) cp_async_wait<0>();
+  if (!kNorm || a.dgamma == nullptr) return;  // uniform over the grid
   // CTA-level reduction of the affine gradients, then one atomic per channel per CTA
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -1926,6 +1998,129 @@ layer0_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
   }
 }
 
+// ---- GroupNorm-mode (wavlm-base) layer 0 backward ---------------------------------------------------------------
+// Layer 0 there is conv -> GroupNorm(512 groups of one channel: statistics over TIME per (utterance, channel)) -> GELU
+// (hf:models/wavlm/modeling_wavlm.py:730-751).  With xhat = (z - mean_bc) rstd_bc, v = xhat gamma_c + beta_c, dv = dOut gelu'(v):
+//   dgamma_c = sum_{b,t} dv xhat,   dbeta_c = sum_{b,t} dv,
+//   dz = rstd_bc gamma_c (dv - mean_t dv - xhat mean_t (dv xhat)),   dW0[c, tap] = sum_{b,t} dz x[5t + tap].
+// dz is never materialised: per (b, c) ONE pass over time accumulates D1 = sum dv, D2 = sum dv xhat, Av[tap] = sum dv x_tap,
+// H[tap] = sum xhat x_tap and (per b) X[tap] = sum x_tap, and the finalize kernel combines
+//   dW0[c, tap] += sum_b rstd_bc gamma_c (Av - D1 X / T - D2 H / T).
+// Warp (b, slot, half) walks frames slot, slot + kGnBwdSlots, ...; a lane owns 8 consecutive channels of its half; partials
+// go to a scratch buffer, one owner per element: no atomics, deterministic.
+constexpr int kGnBwdSlots = 8;
+constexpr int kGnBwdVals = 22;  // Av[10] | H[10] | D1 | D2 per (b, slot, c)
+size_t gn_bwd_scratch_bytes(int B) {
+  return round_up(static_cast<size_t>(B) * kGnBwdSlots * (kC * kGnBwdVals + 16) * 4, static_cast<size_t>(1024));
+}
+
+__global__ void __launch_bounds__(kL0Threads, 1)
+layer0_gn_bwd_partial_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dout,
+                             const __nv_bfloat16* __restrict__ xhat, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float* __restrict__ part, float* __restrict__ xsum, int B,
+                             int L, int T0, int P0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * kL0Warps + warp;
+  const int half = gw & 1, slot = (gw >> 1) % kGnBwdSlots, b = (gw >> 1) / kGnBwdSlots;
+  if (b >= B) return;
+  const int c0 = half * 256 + 8 * lane;
+  f2 g2[4], b2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    g2[j] = f2_make(__ldg(gamma + c0 + 2 * j), __ldg(gamma + c0 + 2 * j + 1));
+    b2[j] = f2_make(__ldg(beta + c0 + 2 * j), __ldg(beta + c0 + 2 * j + 1));
+  }
+  float av[8][10], hh[8][10], d1[8], d2[8], xs[10];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    d1[j] = d2[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) av[j][k] = hh[j][k] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) xs[k] = 0.f;
+  const float* xb = x + static_cast<size_t>(b) * L;
+  for (int t = slot; t < T0; t += kGnBwdSlots) {
+    const size_t m = static_cast<size_t>(b) * P0 + t;
+    const uint4 go4 = __ldg(reinterpret_cast<const uint4*>(dout + m * kC + c0));
+    const uint4 xh4 = __ldg(reinterpret_cast<const uint4*>(xhat + m * kC + c0));
+    float xv[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) xv[k] = __ldg(xb + 5 * t + k);  // warp-uniform address
+    const unsigned wg[4] = {go4.x, go4.y, go4.z, go4.w}, wx[4] = {xh4.x, xh4.y, xh4.z, xh4.w};
+    float dv[8], xh[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const f2 xh2 = f2_bits(wx[j] << 16, wx[j] & 0xffff0000u);
+      const f2 dv2 = f2_mul(f2_bits(wg[j] << 16, wg[j] & 0xffff0000u), gelu_grad2(f2_fma(xh2, g2[j], b2[j])));
+      f2_split(xh2, xh[2 * j], xh[2 * j + 1]);
+      f2_split(dv2, dv[2 * j], dv[2 * j + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) xs[k] += xv[k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      d1[j] += dv[j];
+      d2[j] = fmaf(dv[j], xh[j], d2[j]);
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        av[j][k] = fmaf(dv[j], xv[k], av[j][k]);
+        hh[j][k] = fmaf(xh[j], xv[k], hh[j][k]);
+      }
+    }
+  }
+  const size_t bs = static_cast<size_t>(b) * kGnBwdSlots + slot;
+  float* dst = part + (bs * kC + c0) * kGnBwdVals;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      dst[j * kGnBwdVals + k] = av[j][k];
+      dst[j * kGnBwdVals + 10 + k] = hh[j][k];
+    }
+    dst[j * kGnBwdVals + 20] = d1[j];
+    dst[j * kGnBwdVals + 21] = d2[j];
+  }
+  if (half == 0 && lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) xsum[bs * 16 + k] = xs[k];
+  }
+}
+
+// grid = 512 channels, 32 threads: thread k < 10 owns dW0[c, k], thread 10 dgamma[c], thread 11 dbeta[c]; all ACCUMULATE
+__global__ void layer0_gn_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ xsum,
+                                              const float* __restrict__ gn_rstd, const float* __restrict__ gamma,
+                                              float* __restrict__ dw0, float* __restrict__ dgamma,
+                                              float* __restrict__ dbeta, int B, int T0) {
+  const int c = blockIdx.x, k = threadIdx.x;
+  if (k >= 12) return;
+  const double inv_t = 1.0 / T0;
+  double acc = 0.0;
+  for (int b = 0; b < B; ++b) {
+    double a = 0.0, h = 0.0, s1 = 0.0, s2 = 0.0, xk = 0.0;
+    for (int slot = 0; slot < kGnBwdSlots; ++slot) {
+      const size_t bs = static_cast<size_t>(b) * kGnBwdSlots + slot;
+      const float* p = part + (bs * kC + c) * kGnBwdVals;
+      s1 += p[20];
+      s2 += p[21];
+      if (k < 10) {
+        a += p[k];
+        h += p[10 + k];
+        xk += xsum[bs * 16 + k];
+      }
+    }
+    if (k < 10) acc += static_cast<double>(gn_rstd[static_cast<size_t>(b) * kC + c]) * (a - s1 * inv_t * xk - s2 * inv_t * h);
+    else acc += k == 10 ? s2 : s1;
+  }
+  if (k < 10) {
+    if (dw0 != nullptr) dw0[c * 10 + k] += static_cast<float>(acc * gamma[c]);
+  } else if (k == 10) {
+    if (dgamma != nullptr) dgamma[c] += static_cast<float>(acc);
+  } else if (dbeta != nullptr) {
+    dbeta[c] += static_cast<float>(acc);
+  }
+}
+
 // ---- weight gradient: dW[n, kk] = sum_m dZ[m, n] * A[m, kk],  A[m, tap*512 + c] = X[2m + tap, c] -------------------
 // One CTA per (128 output channels) x (256 K columns) x (slice of the frame axis).  Both operands are MN-major:
 // the reduction index m runs over shared-memory rows of 128 bytes, exactly what TMA writes for a {64 elements, 64 rows}
@@ -1940,7 +2135,9 @@ constexpr int kWgBarOff = kWgStages * kWgStageBytes;
 constexpr int kWgSmemBytes = kWgBarOff + (2 * kWgStages + 1) * 8 + 16 + 1024;
 
 struct WgradArgs {
-  float* dw;        // [512, K] fp32 (packed K order tap*512 + c), accumulated with atomics
+  float* dw;        // fp32, accumulated with atomics: [512, K] in the packed K order tap*512 + c, or (ckpt) the
+                    // checkpoint layout [512 n, 512 c, k taps] of conv_layers.{i}.conv.weight
+  int ckpt;
   int K;            // k * 512
   int stride;       // 2
   int n_stages;     // ceil(M / 64)
@@ -2039,14 +2236,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     ptx::mbar_wait(bar(kDone), 0);
     ptx::tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    float* dst = g.dw + static_cast<size_t>(n) * g.K + kk0;
+    // packed: element (n, kk0 + c);  checkpoint layout: element (n, c0 + c, tap) of [512, 512, k]
+    const int kt = g.K / kC;
+    float* dst = g.ckpt ? g.dw + (static_cast<size_t>(n) * kC + c0) * kt + tap : g.dw + static_cast<size_t>(n) * g.K + kk0;
+    const int cstep = g.ckpt ? kt : 1;
 #pragma unroll 1
     for (int c = 0; c < 256; c += 32) {
       uint32_t r[32];
       ptx::tmem_ld32(taddr + c, r);
       ptx::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(dst + c + j, __uint_as_float(r[j]));
+      for (int j = 0; j < 32; ++j) atomicAdd(dst + (c + j) * cstep, __uint_as_float(r[j]));
     }
   }
   ptx::tc_fence_before();
@@ -2147,17 +2347,22 @@ int make_tmap_out(CUtensorMap* m, const void* ptr, int64_t rows, int row_mul = 1
   return r == CUDA_SUCCESS ? NRSE_OK : NRSE_ERR_CUDA;
 }
 
-// NRSE_EXPERIMENT (environment, read once): timing experiments that produce WRONG results -- never set outside scripts/
+// Experiment flags: the constant 0 in the product library; NRSE_EXPERIMENT (environment, read once) in the scripts-only
+// -DNRSE_EXPERIMENTS build (see the top of this file)
+#ifdef NRSE_EXPERIMENTS
 int experiment_flags() {
   static const int v = [] {
     const char* e = getenv("NRSE_EXPERIMENT");
     const int f = e ? atoi(e) : 0;
     if (f != 0)
-      fprintf(stderr, "nrse_b200: NRSE_EXPERIMENT=%d is set -- timing experiment, the conv frontend's results may be WRONG\n", f);
+      fprintf(stderr, "nrse_b200 (experiments build): NRSE_EXPERIMENT=%d -- the conv frontend's results may be WRONG\n", f);
     return f;
   }();
   return v;
 }
+#else
+constexpr int experiment_flags() { return 0; }
+#endif
 int g_tile_order = 1;   // 1: consecutive layers walk their tiles in opposite directions, so that every layer starts on the
                         // rows its producer wrote last (still in L2) instead of the ones it wrote first (long evicted); 0: all forward
 int g_l2_prefetch = 0;  // 1: producer bulk-prefetches the next tile's A rows into L2 (measured 2-3 % slower: off)
@@ -2168,12 +2373,14 @@ int g_variant = 4;  // 1: single CTA per tile, 2: 2-CTA cluster splitting the ch
                     // choice depends on the layer, never on the batch: an utterance's features do not depend on what
                     // else is in the batch (tests/test_gpu_frontend.py::test_frontend_full_size_batch_independence)
 
-int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const GemmArgs& g,
-                 cudaStream_t stream) {
+template <bool kSave = false>
+int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tx,
+                 const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = Gemm2CfgT<kSave>;
   static bool attr_set = false;  // benign race: the attribute is idempotent
   if (!attr_set) {
-    NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Gemm2Cfg::kSmemBytes));
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_gemm2_kernel<kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
     attr_set = true;
   }
   const int num_super = (g.num_tiles + 1) / 2;
@@ -2181,8 +2388,8 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap
   const int groups = num_super < max_groups ? num_super : max_groups;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
-  cfg.blockDim = dim3(Gemm2Cfg::kThreads);
-  cfg.dynamicSmemBytes = Gemm2Cfg::kSmemBytes;
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -2192,8 +2399,8 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (experiment_flags() & 512) ? 1 : 2;  // 512: no programmatic dependent launch (A/B timing)
-  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel, ta, tw, to, g));
+  cfg.numAttrs = NRSE_EXP(experiment_flags(), 512) ? 1 : 2;  // 512: no programmatic dependent launch (A/B timing)
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<kSave>, ta, tw, to, tx, g));
   return NRSE_OK;
 }
 
@@ -2222,7 +2429,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (experiment_flags() & 512) ? 1 : 2;  // 512: no programmatic dependent launch (A/B timing)
+  cfg.numAttrs = NRSE_EXP(experiment_flags(), 512) ? 1 : 2;  // 512: no programmatic dependent launch (A/B timing)
   NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<kClusterN, kSave>, ta, tw, to, g));
   return NRSE_OK;
 }
@@ -2253,7 +2460,7 @@ int launch_layer0_tc(const L0Args& a, cudaStream_t stream) {
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (experiment_flags() & 512) ? 1 : 2;  // 512: no programmatic dependent launch (A/B timing)
+  cfg.numAttrs = NRSE_EXP(experiment_flags(), 512) ? 1 : 2;  // 512: no programmatic dependent launch (A/B timing)
   CUtensorMap to, tx;
   if (make_tmap_out(&to, a.out, m_total) != NRSE_OK) return NRSE_ERR_CUDA;
   if (make_tmap_out(&tx, a.xhat != nullptr ? static_cast<const void*>(a.xhat) : a.out, m_total) != NRSE_OK) return NRSE_ERR_CUDA;
@@ -2289,11 +2496,16 @@ size_t act_bytes(int B, int P) { return round_up(static_cast<size_t>(B) * P * kC
 size_t gn_part_bytes(int B) { return round_up(static_cast<size_t>(B) * kGnSlots * 2 * kC * 4, static_cast<size_t>(1024)); }
 size_t rstd_bytes(int B, int P) { return round_up(static_cast<size_t>(B) * P * 4, static_cast<size_t>(1024)); }
 
-// Tape of a training forward: activations of layers 0..5, xhat of layers 0..6, rstd of layers 0..6
+size_t gn_affine_bytes(int B) { return round_up(static_cast<size_t>(B) * kC * 4, static_cast<size_t>(1024)); }
+
+// Tape of a training forward: activations of layers 0..5, xhat of layers 0..6 (without a normalisation: the pre-GELU
+// activation itself), rstd of layers 0..6 (LayerNorm mode), and the GroupNorm region of layer 0 (partials | scale | shift |
+// per-(b,c) 1/std | mean/std; GroupNorm mode).  One layout for both modes.
 struct Tape {
   char* act[kLayers - 1];
   char* xhat[kLayers];
   float* rstd[kLayers];
+  char* gn;
   size_t bytes;
 };
 Tape tape_layout(void* base, int B, const int32_t* P) {
@@ -2302,11 +2514,12 @@ Tape tape_layout(void* base, int B, const int32_t* P) {
   for (int i = 0; i < kLayers - 1; ++i) { t.act[i] = p; p += act_bytes(B, P[i]); }
   for (int i = 0; i < kLayers; ++i) { t.xhat[i] = p; p += act_bytes(B, P[i]); }
   for (int i = 0; i < kLayers; ++i) { t.rstd[i] = reinterpret_cast<float*>(p); p += rstd_bytes(B, P[i]); }
+  t.gn = p;
+  p += gn_part_bytes(B) + 4 * gn_affine_bytes(B);
   t.bytes = static_cast<size_t>(p - reinterpret_cast<char*>(base));
   return t;
 }
-
-size_t gn_affine_bytes(int B) { return round_up(static_cast<size_t>(B) * kC * 4, static_cast<size_t>(1024)); }
+float* tape_gn_rstd(const Tape& t, int B) { return reinterpret_cast<float*>(t.gn + gn_part_bytes(B) + 2 * gn_affine_bytes(B)); }
 
 }  // namespace
 }  // namespace nrse
@@ -2372,6 +2585,8 @@ static int layer0_fwd_impl(const float* x, const float* w0, const float* gamma, 
   a.B = B; a.L = L; a.T0 = T0; a.P0 = P0;
   a.xhat = reinterpret_cast<__nv_bfloat16*>(xhat);
   a.rstd = rstd;
+  a.gn_rstd = nullptr;
+  a.gn_mr = nullptr;
   const long long rows = static_cast<long long>(B) * P0;
   const long long want = ceil_div(rows, static_cast<long long>(kL0Warps));
   const unsigned grid = static_cast<unsigned>(want < kNumSMs ? want : kNumSMs);
@@ -2387,15 +2602,20 @@ static int layer0_fwd_impl(const float* x, const float* w0, const float* gamma, 
     return NRSE_OK;
   }
   if (norm_mode != NRSE_NORM_GROUP || !gn_scratch) return NRSE_ERR_INVALID_ARG;
+  // gn_scratch: partial sums | scale | shift, and for the training forward (xhat != nullptr) | 1/std | mean/std
   float* part = reinterpret_cast<float*>(gn_scratch);
   float* scale = reinterpret_cast<float*>(reinterpret_cast<char*>(gn_scratch) + gn_part_bytes(B));
   float* shift = reinterpret_cast<float*>(reinterpret_cast<char*>(scale) + gn_affine_bytes(B));
+  float* gn_rstd = xhat ? reinterpret_cast<float*>(reinterpret_cast<char*>(shift) + gn_affine_bytes(B)) : nullptr;
+  float* gn_mr = xhat ? reinterpret_cast<float*>(reinterpret_cast<char*>(gn_rstd) + gn_affine_bytes(B)) : nullptr;
   layer0_gn_partial_kernel<<<ceil_div(B * kGnSlots, kL0Warps), kL0Threads, 0, s>>>(a, part);
   NRSE_CHECK_LAUNCH();
-  layer0_gn_finalize_kernel<<<ceil_div(B * kC, 256), 256, 0, s>>>(part, gamma, beta, scale, shift, B, T0);
+  layer0_gn_finalize_kernel<<<ceil_div(B * kC, 256), 256, 0, s>>>(part, gamma, beta, scale, shift, gn_rstd, gn_mr, B, T0);
   NRSE_CHECK_LAUNCH();
   a.gamma = scale;
   a.beta = shift;
+  a.gn_rstd = gn_rstd;
+  a.gn_mr = gn_mr;
   layer0_kernel<true><<<grid, kL0Threads, 0, s>>>(a);
   NRSE_CHECK_LAUNCH();
   return NRSE_OK;
@@ -2417,7 +2637,8 @@ static int layer_fwd_impl(const void* act_prev, int64_t rows_prev, const void* w
   if ((reinterpret_cast<uintptr_t>(act_prev) | reinterpret_cast<uintptr_t>(w_packed) |
        reinterpret_cast<uintptr_t>(out)) & 15u)
     return NRSE_ERR_INVALID_ARG;
-  const bool two_sm = xhat == nullptr && (g_variant == 3 || (g_variant == 4 && big_layer));
+  // the 2-SM kernel's training variant stores output and xhat through TMA staging buffers: bf16 outputs only
+  const bool two_sm = (g_variant == 3 || (g_variant == 4 && big_layer)) && (xhat == nullptr || out_dtype == NRSE_DTYPE_BF16);
   CUtensorMap ta, tw;
   int rc = make_tmap_a(&ta, act_prev, rows_prev, stride);
   if (rc != NRSE_OK) return rc;
@@ -2445,7 +2666,13 @@ static int layer_fwd_impl(const void* act_prev, int64_t rows_prev, const void* w
   CUtensorMap to;  // bf16 outputs only; an fp32 output (last layer on request) keeps direct stores and ignores the map
   rc = make_tmap_out(&to, out, rows_out);
   if (rc != NRSE_OK) return rc;
-  if (two_sm) return launch_gemm2(ta, tw, to, g, as_stream(stream));
+  if (two_sm) {
+    if (xhat == nullptr) return launch_gemm2<false>(ta, tw, to, to, g, as_stream(stream));
+    CUtensorMap tx;
+    rc = make_tmap_out(&tx, xhat, rows_out);
+    if (rc != NRSE_OK) return rc;
+    return launch_gemm2<true>(ta, tw, to, tx, g, as_stream(stream));
+  }
   if (xhat != nullptr)
     return g_variant >= 2 ? launch_gemm<2, true>(ta, tw, to, g, as_stream(stream))
                           : launch_gemm<1, true>(ta, tw, to, g, as_stream(stream));
@@ -2496,32 +2723,35 @@ int nrse_conv_frontend_fwd(const float* x, const nrse_frontend_params* prm, int 
   return NRSE_OK;
 }
 
-/* ---- training forward + backward (LayerNorm mode) -------------------------------------------------------------- */
+/* ---- training forward + backward -------------------------------------------------------------------------------- */
 size_t nrse_conv_frontend_tape_bytes(int B, int L) {
   int32_t T[nrse::kLayers], P[nrse::kLayers];
   if (B < 1 || nrse::geometry(L, T, P) != NRSE_OK) return 0;
   return nrse::tape_layout(nullptr, B, P).bytes;
 }
 
-int nrse_conv_frontend_fwd_train(const float* x, const nrse_frontend_params* prm, void* y, int y_dtype, void* tape,
-                                 size_t tape_bytes, int B, int L, nrse_stream_t stream) {
+int nrse_conv_frontend_fwd_train(const float* x, const nrse_frontend_params* prm, int norm_mode, void* y, int y_dtype,
+                                 void* tape, size_t tape_bytes, int B, int L, nrse_stream_t stream) {
   using namespace nrse;
   if (!x || !prm || !y || !tape || B < 1) return NRSE_ERR_INVALID_ARG;
+  if (norm_mode != NRSE_NORM_LAYER && norm_mode != NRSE_NORM_GROUP) return NRSE_ERR_INVALID_ARG;
   if (reinterpret_cast<uintptr_t>(tape) & 1023u) return NRSE_ERR_INVALID_ARG;
   int32_t T[kLayers], P[kLayers];
   int rc = geometry(L, T, P);
   if (rc != NRSE_OK) return rc;
   const Tape t = tape_layout(tape, B, P);
   if (tape_bytes < t.bytes) return NRSE_ERR_WORKSPACE;
-  rc = layer0_fwd_impl(x, prm->w0, prm->gamma[0], prm->beta[0], NRSE_NORM_LAYER, t.act[0], nullptr, B, L, T[0], P[0],
-                       t.xhat[0], t.rstd[0], stream);
+  const bool norm = norm_mode == NRSE_NORM_LAYER;
+  rc = layer0_fwd_impl(x, prm->w0, prm->gamma[0], prm->beta[0], norm_mode, t.act[0], t.gn, B, L, T[0], P[0], t.xhat[0],
+                       norm ? t.rstd[0] : nullptr, stream);
   if (rc != NRSE_OK) return rc;
   for (int i = 1; i < kLayers; ++i) {
-    if (!prm->gamma[i] || !prm->beta[i]) return NRSE_ERR_INVALID_ARG;
+    if (norm && (!prm->gamma[i] || !prm->beta[i])) return NRSE_ERR_INVALID_ARG;
     void* out = i == kLayers - 1 ? y : static_cast<void*>(t.act[i]);
     rc = layer_fwd_impl(t.act[i - 1], static_cast<int64_t>(B) * P[i - 1], prm->w_packed[i - 1], kKernel[i], kStride[i],
-                        prm->gamma[i], prm->beta[i], out, i == kLayers - 1 ? y_dtype : NRSE_DTYPE_BF16,
-                        static_cast<int64_t>(B) * P[i], t.xhat[i], t.rstd[i], stream, g_tile_order ? (i & 1) : 0);
+                        norm ? prm->gamma[i] : nullptr, norm ? prm->beta[i] : nullptr, out,
+                        i == kLayers - 1 ? y_dtype : NRSE_DTYPE_BF16, static_cast<int64_t>(B) * P[i], t.xhat[i],
+                        norm ? t.rstd[i] : nullptr, stream, g_tile_order ? (i & 1) : 0, /*big_layer=*/i <= 3);
     if (rc != NRSE_OK) return rc;
   }
   return NRSE_OK;
@@ -2536,30 +2766,39 @@ int nrse_conv_frontend_pack_weights_dgrad(const float* w, void* even, void* odd,
   return NRSE_OK;
 }
 
-int nrse_ln_gelu_bwd(const void* dout, int dout_dtype, const void* xhat, const float* rstd, const float* gamma,
-                     const float* beta, void* dz, float* dgamma, float* dbeta, int64_t rows, int P, int T,
-                     nrse_stream_t stream) {
+int nrse_ln_gelu_bwd(const void* dout, int dout_dtype, int dout_pitch, const void* xhat, const float* rstd,
+                     const float* gamma, const float* beta, void* dz, float* dgamma, float* dbeta, int64_t rows, int P,
+                     int T, nrse_stream_t stream) {
   using namespace nrse;
-  if (!dout || !xhat || !rstd || !gamma || !beta || !dz || !dgamma || !dbeta || rows < 1 || P < 1 || T < 1 || T > P)
-    return NRSE_ERR_INVALID_ARG;
+  if (!dout || !xhat || !dz || rows < 1 || P < 1 || T < 1 || T > P) return NRSE_ERR_INVALID_ARG;
+  const bool norm = gamma != nullptr;
+  if (norm && (!beta || !rstd)) return NRSE_ERR_INVALID_ARG;
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return NRSE_ERR_INVALID_ARG;
   LnBwdArgs a;
   a.dout = dout; a.dout_f32 = dout_dtype == NRSE_DTYPE_F32 ? 1 : 0;
+  a.dout_P = a.dout_f32 ? dout_pitch : P;
+  if (a.dout_f32 && dout_pitch < T) return NRSE_ERR_INVALID_ARG;
   a.xhat = reinterpret_cast<const __nv_bfloat16*>(xhat);
   a.rstd = rstd; a.gamma = gamma; a.beta = beta;
   a.dz = reinterpret_cast<__nv_bfloat16*>(dz);
   a.dgamma = dgamma; a.dbeta = dbeta; a.rows = rows; a.P = P; a.T = T;
   const long long want = ceil_div(static_cast<long long>(rows), static_cast<long long>(kLnBwdWarps));
   const unsigned grid = static_cast<unsigned>(want < 4 * kNumSMs ? want : 4 * kNumSMs);
+  cudaStream_t s = as_stream(stream);
   if (a.dout_f32) {
-    ln_gelu_bwd_kernel<true><<<grid, kLnBwdThreads, 0, as_stream(stream)>>>(a);
+    if (norm) ln_gelu_bwd_kernel<true, true><<<grid, kLnBwdThreads, 0, s>>>(a);
+    else ln_gelu_bwd_kernel<true, false><<<grid, kLnBwdThreads, 0, s>>>(a);
   } else {
     static bool attr_set = false;  // benign race: idempotent attribute
     if (!attr_set) {
-      NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kLnRingBytes));
+      NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kLnRingBytes));
       attr_set = true;
     }
-    ln_gelu_bwd_kernel<false><<<grid, kLnBwdThreads, kLnRingBytes, as_stream(stream)>>>(a);
+    if (norm) ln_gelu_bwd_kernel<false, true><<<grid, kLnBwdThreads, kLnRingBytes, s>>>(a);
+    else ln_gelu_bwd_kernel<false, false><<<grid, kLnBwdThreads, kLnRingBytes, s>>>(a);
   }
   NRSE_CHECK_LAUNCH();
   return NRSE_OK;
@@ -2583,11 +2822,34 @@ int nrse_conv_layer0_wgrad(const float* x, const void* dz0, float* dw0, int B, i
   return NRSE_OK;
 }
 
-/* dW [512, k*512] fp32 (K order tap*512 + c) += dZ^T A.  dz [rows_out, 512] bf16, act_prev [2*rows_out, 512] bf16. */
-int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out, int k, float* dw_packed,
+size_t nrse_conv_layer0_gn_bwd_scratch_bytes(int B) { return B < 1 ? 0 : nrse::gn_bwd_scratch_bytes(B); }
+
+/* GroupNorm-mode layer 0: dOut0 [B*P0, 512] bf16 -> dW0 / dgamma0 / dbeta0 (each nullable, ACCUMULATED). */
+int nrse_conv_layer0_gn_bwd(const float* x, const void* dout0, const void* xhat0, const float* gn_rstd,
+                            const float* gamma, const float* beta, float* dw0, float* dgamma, float* dbeta,
+                            void* scratch, int B, int L, int T0, int P0, nrse_stream_t stream) {
+  using namespace nrse;
+  if (!x || !dout0 || !xhat0 || !gn_rstd || !gamma || !beta || !scratch || B < 1 || T0 < 1 || P0 < T0)
+    return NRSE_ERR_INVALID_ARG;
+  if (L < 5 * (T0 - 1) + 10) return NRSE_ERR_INVALID_ARG;
+  float* part = reinterpret_cast<float*>(scratch);
+  float* xsum = part + static_cast<size_t>(B) * kGnBwdSlots * kC * kGnBwdVals;
+  const int warps = B * kGnBwdSlots * 2;
+  layer0_gn_bwd_partial_kernel<<<ceil_div(warps, kL0Warps), kL0Threads, 0, as_stream(stream)>>>(
+      x, reinterpret_cast<const __nv_bfloat16*>(dout0), reinterpret_cast<const __nv_bfloat16*>(xhat0), gamma, beta, part,
+      xsum, B, L, T0, P0);
+  NRSE_CHECK_LAUNCH();
+  layer0_gn_bwd_finalize_kernel<<<kC, 32, 0, as_stream(stream)>>>(part, xsum, gn_rstd, gamma, dw0, dgamma, dbeta, B, T0);
+  NRSE_CHECK_LAUNCH();
+  return NRSE_OK;
+}
+
+/* dW += dZ^T A.  dz [rows_out, 512] bf16, act_prev [2*rows_out, 512] bf16; dW fp32 [512, k*512] in the packed K order
+ * (tap*512 + c), or with ckpt_layout the checkpoint layout [512, 512, k]. */
+int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out, int k, float* dw, int ckpt_layout,
                           nrse_stream_t stream) {
   using namespace nrse;
-  if (!dz || !act_prev || !dw_packed || rows_out < 1 || (k != 2 && k != 3)) return NRSE_ERR_INVALID_ARG;
+  if (!dz || !act_prev || !dw || rows_out < 1 || (k != 2 && k != 3)) return NRSE_ERR_INVALID_ARG;
   CUtensorMap tg, tx;
   int rc = make_tmap_rows(&tg, dz, rows_out, kWgKm);
   if (rc != NRSE_OK) return rc;
@@ -2599,7 +2861,8 @@ int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out
     attr_set = true;
   }
   WgradArgs g;
-  g.dw = dw_packed;
+  g.dw = dw;
+  g.ckpt = ckpt_layout ? 1 : 0;
   g.K = k * kC;
   g.stride = 2;
   g.n_stages = static_cast<int>(ceil_div(rows_out, static_cast<int64_t>(kWgKm)));
@@ -2642,6 +2905,7 @@ int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even,
     g.a_ptr = reinterpret_cast<const char*>(dz);
     g.a_rows = rows_out;
     g.l2_prefetch = g_l2_prefetch;
+    g.reverse = 0;
     CUtensorMap to;  // rows 2 m + parity of dX
     rc = make_tmap_out(&to, reinterpret_cast<const char*>(dx) + static_cast<size_t>(parity) * kC * 2, rows_out, 2);
     if (rc != NRSE_OK) return rc;
@@ -2654,45 +2918,65 @@ int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even,
 size_t nrse_conv_frontend_bwd_workspace_bytes(int B, int L) {
   int32_t T[nrse::kLayers], P[nrse::kLayers];
   if (B < 1 || nrse::geometry(L, T, P) != NRSE_OK) return 0;
-  return nrse::act_bytes(B, P[0]) + nrse::act_bytes(B, P[1]);  // ping-pong gradient buffers (even / odd layers)
+  // ping-pong gradient buffers (even / odd layers) + the partial sums of the GroupNorm-mode layer-0 backward
+  return nrse::act_bytes(B, P[0]) + nrse::act_bytes(B, P[1]) + nrse::gn_bwd_scratch_bytes(B);
 }
 
 int nrse_conv_frontend_bwd(const float* x, const nrse_frontend_params* prm, const nrse_frontend_bwd_weights* wb,
-                           const void* tape, const float* dy, const nrse_frontend_grads* grads, void* workspace,
-                           size_t workspace_bytes, int B, int L, nrse_stream_t stream) {
+                           int norm_mode, const void* tape, const float* dy, int dy_pitch,
+                           const nrse_frontend_grads* grads, void* workspace, size_t workspace_bytes, int B, int L,
+                           nrse_stream_t stream) {
   using namespace nrse;
   if (!x || !prm || !wb || !tape || !dy || !grads || !workspace || B < 1) return NRSE_ERR_INVALID_ARG;
+  if (norm_mode != NRSE_NORM_LAYER && norm_mode != NRSE_NORM_GROUP) return NRSE_ERR_INVALID_ARG;
   if (reinterpret_cast<uintptr_t>(workspace) & 1023u) return NRSE_ERR_INVALID_ARG;
   int32_t T[kLayers], P[kLayers];
   int rc = geometry(L, T, P);
   if (rc != NRSE_OK) return rc;
+  if (dy_pitch < T[kLayers - 1]) return NRSE_ERR_INVALID_ARG;
   if (workspace_bytes < nrse_conv_frontend_bwd_workspace_bytes(B, L)) return NRSE_ERR_WORKSPACE;
+  const bool norm = norm_mode == NRSE_NORM_LAYER;
+  // which layers want what; `stop` = the lowest layer that wants anything: nothing below it is computed
+  bool need_w[kLayers], need_aff[kLayers];
+  int stop = kLayers;
+  for (int i = kLayers - 1; i >= 0; --i) {
+    need_w[i] = (i == 0 ? grads->dw0 : grads->dw[i - 1]) != nullptr;
+    const bool has_aff = norm || i == 0;
+    if ((grads->dgamma[i] == nullptr) != (grads->dbeta[i] == nullptr)) return NRSE_ERR_INVALID_ARG;
+    if (!has_aff && grads->dgamma[i] != nullptr) return NRSE_ERR_INVALID_ARG;
+    need_aff[i] = grads->dgamma[i] != nullptr;
+    if (need_w[i] || need_aff[i]) stop = i;
+  }
+  if (stop == kLayers) return NRSE_OK;
   const Tape t = tape_layout(const_cast<void*>(tape), B, P);
   char* buf[2] = {reinterpret_cast<char*>(workspace), reinterpret_cast<char*>(workspace) + act_bytes(B, P[0])};
-  cudaStream_t s = as_stream(stream);
-  for (int i = 0; i < kLayers; ++i) {
-    NRSE_CUDA_TRY(cudaMemsetAsync(grads->dgamma[i], 0, kC * sizeof(float), s));
-    NRSE_CUDA_TRY(cudaMemsetAsync(grads->dbeta[i], 0, kC * sizeof(float), s));
-    if (i == 0) NRSE_CUDA_TRY(cudaMemsetAsync(grads->dw0, 0, kC * 10 * sizeof(float), s));
-    else NRSE_CUDA_TRY(cudaMemsetAsync(grads->dw[i - 1], 0, static_cast<size_t>(kC) * kKernel[i] * kC * sizeof(float), s));
-  }
-  for (int i = kLayers - 1; i >= 0; --i) {
+  void* gn_scratch = buf[1] + act_bytes(B, P[1]);
+  for (int i = kLayers - 1; i >= stop; --i) {
     const int64_t rows = static_cast<int64_t>(B) * P[i];
     char* dz = buf[i & 1];
+    const bool last = i == kLayers - 1;
+    if (!norm && i == 0) {  // GroupNorm over time: dOut_0 (already in dz, bf16) -> dW0, dgamma0, dbeta0 in one pass
+      return nrse_conv_layer0_gn_bwd(x, dz, t.xhat[0], tape_gn_rstd(t, B), prm->gamma[0], prm->beta[0], grads->dw0,
+                                     grads->dgamma[0], grads->dbeta[0], gn_scratch, B, L, T[0], P[0], stream);
+    }
     // dOut_i (dy for the last layer, else the dgrad output already sitting in dz) -> dZ_i, in place
-    rc = nrse_ln_gelu_bwd(i == kLayers - 1 ? static_cast<const void*>(dy) : static_cast<const void*>(dz),
-                          i == kLayers - 1 ? NRSE_DTYPE_F32 : NRSE_DTYPE_BF16, t.xhat[i], t.rstd[i], prm->gamma[i],
-                          prm->beta[i], dz, grads->dgamma[i], grads->dbeta[i], rows, P[i], T[i], stream);
+    rc = nrse_ln_gelu_bwd(last ? static_cast<const void*>(dy) : static_cast<const void*>(dz),
+                          last ? NRSE_DTYPE_F32 : NRSE_DTYPE_BF16, last ? dy_pitch : P[i], t.xhat[i],
+                          norm ? t.rstd[i] : nullptr, norm ? prm->gamma[i] : nullptr, norm ? prm->beta[i] : nullptr, dz,
+                          grads->dgamma[i], grads->dbeta[i], rows, P[i], T[i], stream);
     if (rc != NRSE_OK) return rc;
     if (i == 0) {
-      rc = nrse_conv_layer0_wgrad(x, dz, grads->dw0, B, L, T[0], P[0], stream);
-      if (rc != NRSE_OK) return rc;
-      break;
+      if (need_w[0]) rc = nrse_conv_layer0_wgrad(x, dz, grads->dw0, B, L, T[0], P[0], stream);
+      return rc;
     }
-    rc = nrse_conv_layer_wgrad(dz, t.act[i - 1], rows, kKernel[i], grads->dw[i - 1], stream);
-    if (rc != NRSE_OK) return rc;
-    rc = nrse_conv_layer_dgrad(dz, rows, wb->wt_even[i - 1], wb->wt_odd[i - 1], kKernel[i], buf[(i - 1) & 1], stream);
-    if (rc != NRSE_OK) return rc;
+    if (need_w[i]) {
+      rc = nrse_conv_layer_wgrad(dz, t.act[i - 1], rows, kKernel[i], grads->dw[i - 1], /*ckpt_layout=*/1, stream);
+      if (rc != NRSE_OK) return rc;
+    }
+    if (i > stop) {
+      rc = nrse_conv_layer_dgrad(dz, rows, wb->wt_even[i - 1], wb->wt_odd[i - 1], kKernel[i], buf[(i - 1) & 1], stream);
+      if (rc != NRSE_OK) return rc;
+    }
   }
   return NRSE_OK;
 }

@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(kLossThreads) byol_loss_fwd_kernel(const void*
                                                                      const void* __restrict__ z,
                                                                      float* __restrict__ loss,
                                                                      float* __restrict__ saved,
-                                                                     float* __restrict__ row_sim, int B, int D) {
+                                                                     float* __restrict__ row_sim,
+                                                                     int32_t* __restrict__ flags_out, int B, int D) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = static_cast<int>(cluster.block_rank());
   const int n_cta = static_cast<int>(cluster.num_blocks());
@@ -60,6 +61,9 @@ __global__ void __launch_bounds__(kLossThreads) byol_loss_fwd_kernel(const void*
 
   __shared__ float warp_part[kLossWarps];
   __shared__ float cta_part[kLossMaxCluster];
+  __shared__ unsigned warp_flags[kLossWarps];
+  __shared__ unsigned cta_flags[kLossMaxCluster];
+  unsigned flags = 0;  // bit 0 / 1: NaN in p / z; bit 2 / 3: Inf in p / z (NaN after normalisation), byol.py:109-122
 
   const int nvec = D / 8;
   float sim_sum = 0.f;  // this warp's clamped similarities (lane 0 holds the value)
@@ -74,6 +78,7 @@ __global__ void __launch_bounds__(kLossThreads) byol_loss_fwd_kernel(const void*
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float x = a[j] + kEps, y = b[j] + kEps;  // byol.py:113-114
+        flags |= (x != x ? 1u : 0u) | (y != y ? 2u : 0u) | (fabsf(x) == INFINITY ? 4u : 0u) | (fabsf(y) == INFINITY ? 8u : 0u);
         pp = fmaf(x, x, pp);
         zz = fmaf(y, y, zz);
         pz = fmaf(x, y, pz);
@@ -81,6 +86,7 @@ __global__ void __launch_bounds__(kLossThreads) byol_loss_fwd_kernel(const void*
     }
     for (int i = nvec * 8 + lane; i < D; i += 32) {
       const float x = load1<kDtype>(pr, i) + kEps, y = load1<kDtype>(zr, i) + kEps;
+      flags |= (x != x ? 1u : 0u) | (y != y ? 2u : 0u) | (fabsf(x) == INFINITY ? 4u : 0u) | (fabsf(y) == INFINITY ? 8u : 0u);
       pp = fmaf(x, x, pp);
       zz = fmaf(y, y, zz);
       pz = fmaf(x, y, pz);
@@ -97,18 +103,33 @@ __global__ void __launch_bounds__(kLossThreads) byol_loss_fwd_kernel(const void*
       sim_sum += sc;
     }
   }
-  if (lane == 0) warp_part[warp] = sim_sum;
+  flags = warp_or(flags);
+  if (lane == 0) {
+    warp_part[warp] = sim_sum;
+    warp_flags[warp] = flags;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     float s = 0.f;
-    for (int w = 0; w < kLossWarps; ++w) s += warp_part[w];
+    unsigned f = 0;
+    for (int w = 0; w < kLossWarps; ++w) {
+      s += warp_part[w];
+      f |= warp_flags[w];
+    }
     *cluster.map_shared_rank(&cta_part[rank], 0) = s;  // DSMEM write into the rank-0 CTA
+    *cluster.map_shared_rank(&cta_flags[rank], 0) = f;
   }
   cluster.sync();
   if (rank == 0 && threadIdx.x == 0) {
     float s = 0.f;
-    for (int r = 0; r < n_cta; ++r) s += cta_part[r];
+    unsigned f = 0;
+    for (int r = 0; r < n_cta; ++r) {
+      s += cta_part[r];
+      f |= cta_flags[r];
+    }
     *loss = 2.f - 2.f * (s / static_cast<float>(B));  // byol.py:127
+    // before normalisation: NaN present; after: a NaN stays NaN and an Inf becomes Inf / Inf = NaN
+    if (flags_out != nullptr) *flags_out = static_cast<int32_t>((f & 3u) | (((f | (f >> 2)) & 3u) << 2));
   }
 }
 
@@ -173,8 +194,8 @@ bool loss_args_ok(const void* p, const void* z, int B, int D, int dtype) {
 
 extern "C" {
 
-int nrse_byol_loss_fwd(const void* p, const void* z, float* loss, float* saved, float* row_sim, int B, int D,
-                       int dtype, nrse_stream_t stream) {
+int nrse_byol_loss_fwd(const void* p, const void* z, float* loss, float* saved, float* row_sim, int32_t* flags, int B,
+                       int D, int dtype, nrse_stream_t stream) {
   using namespace nrse;
   if (!loss_args_ok(p, z, B, D, dtype) || !loss) return NRSE_ERR_INVALID_ARG;
   if (saved && (reinterpret_cast<uintptr_t>(saved) & 15u)) return NRSE_ERR_INVALID_ARG;
@@ -192,9 +213,9 @@ int nrse_byol_loss_fwd(const void* p, const void* z, float* loss, float* saved, 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (dtype == NRSE_DTYPE_F32)
-    NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, byol_loss_fwd_kernel<NRSE_DTYPE_F32>, p, z, loss, saved, row_sim, B, D));
+    NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, byol_loss_fwd_kernel<NRSE_DTYPE_F32>, p, z, loss, saved, row_sim, flags, B, D));
   else
-    NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, byol_loss_fwd_kernel<NRSE_DTYPE_BF16>, p, z, loss, saved, row_sim, B, D));
+    NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, byol_loss_fwd_kernel<NRSE_DTYPE_BF16>, p, z, loss, saved, row_sim, flags, B, D));
   return NRSE_OK;
 }
 

@@ -35,10 +35,12 @@ struct MixParams {
   float* clean_out;
   float* noisy_out;
   int32_t* status;
+  int32_t* snr_used;  // nullable [B]: the table index a processed row was mixed at (a retry re-draws it, see noise_shift)
   int B, L, Ln, peak_norm, n_snr;
   int raw;  // 1: write the un-normalised mix c + s*n (add_noise_to_speech alone); peak_norm must be 0
   int retry;        // 1: only rows whose status is != 0 are processed (the others keep their outputs), ...
-  int noise_shift;  // ... with the noise of row (row + noise_shift) % B: the device-side "try another noise file"
+  int noise_shift;  // ... with the noise AND the SNR draw of row (row + noise_shift) % B: the device-side "try another
+                    // noise file, draw another SNR" of ref:src/data/noisy_speech_dataset.py:69-81
   float snr_lin[kMaxSnr];  // float(10 ** (snr_db / 10)), ref:src/data/augment.py:39
 };
 
@@ -197,8 +199,9 @@ __global__ void __launch_bounds__(kMixThreads) mix_normalize_kernel(const MixPar
   const double Ld = static_cast<double>(L);
   const float Ps = static_cast<float>(s_cc / Ld);  // torch.mean(speech ** 2)
   const float Pn = static_cast<float>(s_nn / Ld);
-  int idx = p.snr_idx[row];
+  int idx = p.snr_idx[p.retry ? (row + p.noise_shift) % p.B : row];
   idx = idx < 0 ? 0 : (idx >= p.n_snr ? p.n_snr - 1 : idx);
+  if (rank == 0 && tid == 0 && p.snr_used != nullptr) p.snr_used[row] = idx;
   const float scale = __fsqrt_rn(__fdiv_rn(Ps, __fmul_rn(Pn, p.snr_lin[idx])));  // augment.py:40, fp32
   int st = 0;
   if (isnan(Ps)) st = 1;                         // isnan(speech).any()
@@ -323,16 +326,9 @@ __global__ void __launch_bounds__(kMixThreads) mix_normalize_kernel(const MixPar
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Shared-memory-resident variant (the default when the row fits): each CTA of the cluster pulls its segment of
-// the clean and noise rows into shared memory ONCE with bulk async copies (cp.async.bulk + mbarrier
-// complete_tx, issued by one thread, several chunks in flight so the statistics pass starts as soon as the
-// first chunk lands); the second and third passes then run out of shared memory, so HBM/L2 see exactly the
-// algorithmic traffic (read 8 B, write 8 B per sample) whatever the batch size.
+// Helpers of the on-chip-resident kernel below (packed fp32x2 arithmetic, NaN-propagating peaks, streaming stores).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSmemThreads = 512;
-constexpr int kSmemWarps = kSmemThreads / 32;
-constexpr int kSmemMaxCluster = 8;
-constexpr int kSmemChunks = 4;
+constexpr int kSmemMaxCluster = 8;  // CTAs per row (portable cluster limit)
 
 // packed fp32x2 helpers (FFMA2 / FMUL2 / FADD2): same IEEE rounding per lane as the scalar instructions
 typedef unsigned long long f2;
@@ -378,598 +374,10 @@ struct MixScalars {
   int st;   // final verdict
 };
 
-// kStages = 2: PERSISTENT clusters -- cluster k processes rows k, k + n_clusters, ... and, while it runs the three
-// shared-memory passes of row i, the bulk copies of row i+1 are already streaming into the other stage, so HBM stays
-// busy through the compute / synchronisation phases (with one stage every CTA of the grid loads, computes and stores
-// in lock-step and the memory system idles a third of the time).  kStages = 1: one row per cluster (long rows whose
-// two stages would not fit in shared memory).
-template <int kStages>
-__global__ void __launch_bounds__(kSmemThreads) mix_normalize_smem_kernel(const MixParams p, int seg_vec) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = static_cast<int>(cluster.block_rank());
-  const int cs = static_cast<int>(cluster.num_blocks());
-  const int cluster_id = blockIdx.x / cs;
-  const int n_clusters = gridDim.x / cs;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  extern __shared__ __align__(128) unsigned char mix_smem[];
-  __shared__ __align__(8) unsigned long long bars[kStages][kSmemChunks];
-  __shared__ double red_d[kSmemWarps][5];
-  __shared__ float red_f[kSmemWarps][2];
-  __shared__ double xch1_d[2][kSmemMaxCluster][5];
-  __shared__ float xch1_f[2][kSmemMaxCluster][2];
-  __shared__ float xch2_f[2][kSmemMaxCluster];
-  __shared__ MixScalars sc;
-
-  const int L = p.L;
-  const int nvec = L >> 2;  // L % 4 == 0 on this path
-  const int v_begin = min(nvec, rank * seg_vec);
-  const int v_end = min(nvec, v_begin + seg_vec);
-  const int n_my = v_end - v_begin;
-  const int chunk_vec = (seg_vec + kSmemChunks - 1) / kSmemChunks;
-  auto stage_c = [&](int stage) { return reinterpret_cast<float4*>(mix_smem) + static_cast<size_t>(stage) * 2 * seg_vec; };
-
-  // bulk async loads of one row segment: global -> shared, one mbarrier per chunk (issued by thread 0)
-  auto issue_loads = [&](int row, int stage) {
-    float4* d_c = stage_c(stage);
-    float4* d_n = d_c + seg_vec;
-    const float4* g_c = reinterpret_cast<const float4*>(p.clean + static_cast<size_t>(row) * L) + v_begin;
-    const float4* g_n = reinterpret_cast<const float4*>(p.noise + static_cast<size_t>(row) * p.Ln) + v_begin;
-    for (int c = 0; c < kSmemChunks; ++c) {
-      const int c0 = c * chunk_vec;
-      const int len = min(chunk_vec, n_my - c0);
-      const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[stage][c]));
-      if (len <= 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-        continue;
-      }
-      const unsigned bytes = static_cast<unsigned>(len) * 16u;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       static_cast<unsigned>(__cvta_generic_to_shared(d_c + c0))),
-                   "l"(g_c + c0), "r"(bytes), "r"(bar)
-                   : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       static_cast<unsigned>(__cvta_generic_to_shared(d_n + c0))),
-                   "l"(g_n + c0), "r"(bytes), "r"(bar)
-                   : "memory");
-    }
-  };
-
-  if (tid == 0) {
-    for (int st = 0; st < kStages; ++st)
-      for (int c = 0; c < kSmemChunks; ++c) {
-        const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[st][c]));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-      }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (cluster_id < p.B) issue_loads(cluster_id, 0);
-  }
-
-  int it = 0;
-  for (int row = cluster_id; row < p.B; row += n_clusters, ++it) {
-    const int stage = it % kStages;
-    const unsigned parity = static_cast<unsigned>(it / kStages) & 1u;
-    const int xb = it & 1;  // exchange buffers alternate: a fast CTA may already be one row ahead of a slow one
-    float4* s_c = stage_c(stage);
-    float4* s_n = s_c + seg_vec;
-
-    // every thread is done with the other stage (previous row) and with `sc`: it may be refilled / rewritten
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (kStages == 2 && tid == 0 && row + n_clusters < p.B) issue_loads(row + n_clusters, stage ^ 1);
-
-    // ---- pass 1 (shared memory, chunk by chunk as the copies land): packed fp32 partial sums per thread ----------
-    const f2 zero2 = f2_make(0.f, 0.f);
-    f2 a_cc = zero2, a_nn = zero2, a_c1 = zero2, a_n1 = zero2, a_cn = zero2;
-    float cmax = 0.f, nmax_in = 0.f;
-    for (int c = 0; c < kSmemChunks; ++c) {
-      const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[stage][c]));
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-          "@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}\n" ::"r"(bar), "r"(parity)
-          : "memory");
-      const int c_end = min(n_my, (c + 1) * chunk_vec);
-  #pragma unroll 2
-      for (int v = c * chunk_vec + tid; v < c_end; v += kSmemThreads) {
-        const float4 cv = s_c[v], nv = s_n[v];
-        const f2 c01 = f2_make(cv.x, cv.y), c23 = f2_make(cv.z, cv.w);
-        const f2 n01 = f2_make(nv.x, nv.y), n23 = f2_make(nv.z, nv.w);
-        a_cc = f2_fma(c01, c01, a_cc); a_cc = f2_fma(c23, c23, a_cc);
-        a_nn = f2_fma(n01, n01, a_nn); a_nn = f2_fma(n23, n23, a_nn);
-        a_cn = f2_fma(c01, n01, a_cn); a_cn = f2_fma(c23, n23, a_cn);
-        a_c1 = f2_add(a_c1, c01); a_c1 = f2_add(a_c1, c23);
-        a_n1 = f2_add(a_n1, n01); a_n1 = f2_add(a_n1, n23);
-        cmax = fmaxf(fmaxf(cmax, fmaxf(fabsf(cv.x), fabsf(cv.y))), fmaxf(fabsf(cv.z), fabsf(cv.w)));
-        nmax_in = fmaxf(fmaxf(nmax_in, fmaxf(fabsf(nv.x), fabsf(nv.y))), fmaxf(fabsf(nv.z), fabsf(nv.w)));
-      }
-    }
-    // one merged block reduction: per-thread fp32 partials (a few dozen samples each) are combined in fp64
-    {
-      double acc[5] = {static_cast<double>(f2_hsum(a_cc)), static_cast<double>(f2_hsum(a_nn)),
-                       static_cast<double>(f2_hsum(a_c1)), static_cast<double>(f2_hsum(a_n1)),
-                       static_cast<double>(f2_hsum(a_cn))};
-  #pragma unroll
-      for (int k = 0; k < 5; ++k) acc[k] = warp_sum(acc[k]);
-      cmax = warp_max(cmax);
-      nmax_in = warp_max(nmax_in);
-      if (lane == 0) {
-  #pragma unroll
-        for (int k = 0; k < 5; ++k) red_d[warp][k] = acc[k];
-        red_f[warp][0] = cmax;
-        red_f[warp][1] = nmax_in;
-      }
-      __syncthreads();
-      if (tid < cs) {  // thread t sends this CTA's totals to CTA t of the cluster (all-to-all through DSMEM)
-        double tot[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        float m0 = 0.f, m1 = 0.f;
-        for (int w = 0; w < kSmemWarps; ++w) {
-  #pragma unroll
-          for (int k = 0; k < 5; ++k) tot[k] += red_d[w][k];
-          m0 = fmaxf(m0, red_f[w][0]);
-          m1 = fmaxf(m1, red_f[w][1]);
-        }
-        double* dst_d = cluster.map_shared_rank(&xch1_d[xb][rank][0], tid);
-        float* dst_f = cluster.map_shared_rank(&xch1_f[xb][rank][0], tid);
-  #pragma unroll
-        for (int k = 0; k < 5; ++k) dst_d[k] = tot[k];
-        dst_f[0] = m0;
-        dst_f[1] = m1;
-      }
-    }
-    cluster.sync();
-
-    // ---- add_noise_to_speech decisions (augment.py:7-51): thread 0, fixed summation order => same on every CTA ----
-    double s_cc = 0.0, s_nn = 0.0, s_c1 = 0.0, s_n1 = 0.0, s_cn = 0.0;
-    if (tid == 0) {
-      cmax = 0.f;
-      nmax_in = 0.f;
-      for (int r = 0; r < cs; ++r) {
-        s_cc += xch1_d[xb][r][0];
-        s_nn += xch1_d[xb][r][1];
-        s_c1 += xch1_d[xb][r][2];
-        s_n1 += xch1_d[xb][r][3];
-        s_cn += xch1_d[xb][r][4];
-        cmax = fmaxf(cmax, xch1_f[xb][r][0]);
-        nmax_in = fmaxf(nmax_in, xch1_f[xb][r][1]);
-      }
-      const double Ld = static_cast<double>(L);
-      const float Ps = static_cast<float>(s_cc / Ld);
-      const float Pn = static_cast<float>(s_nn / Ld);
-      int idx = p.snr_idx[row];
-      idx = idx < 0 ? 0 : (idx >= p.n_snr ? p.n_snr - 1 : idx);
-      const float scale = __fsqrt_rn(__fdiv_rn(Ps, __fmul_rn(Pn, p.snr_lin[idx])));
-      int st = 0;
-      if (isnan(Ps)) st = 1;
-      else if (isnan(Pn)) st = 2;
-      else if (Ps < 1e-10f) st = 3;
-      else if (Pn < 1e-10f) st = 4;
-      else if (isinf(scale) || isnan(scale)) st = 5;
-      else if (scale > 1e6f) st = 6;
-      else if (isinf(nmax_in)) st = 7;  // inf * 0 -> NaN in noise * scale (augment.py:56)
-      sc.scale = scale;
-      sc.st1 = st;
-    }
-    __syncthreads();
-    const float scale = sc.scale;
-    const int st1 = sc.st1;
-
-    float nmax = 0.f;
-    if (p.peak_norm && st1 == 0) {
-      // ---- pass 2 (shared memory): mix in place (noise slot <- noisy, augment.py:54,60), NaN-propagating peak ------
-      const f2 s2 = f2_make(scale, scale);
-  #pragma unroll 2
-      for (int v = tid; v < n_my; v += kSmemThreads) {
-        const float4 cv = s_c[v], nv = s_n[v];
-        float y0, y1, y2, y3;
-        f2_split(f2_add(f2_make(cv.x, cv.y), f2_mul(f2_make(nv.x, nv.y), s2)), y0, y1);  // mul and add round separately
-        f2_split(f2_add(f2_make(cv.z, cv.w), f2_mul(f2_make(nv.z, nv.w), s2)), y2, y3);
-        nmax = absmax_nan(absmax_nan(absmax_nan(absmax_nan(nmax, y0), y1), y2), y3);
-        s_n[v] = make_float4(y0, y1, y2, y3);
-      }
-  #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float other = __shfl_xor_sync(0xffffffffu, nmax, o);
-        asm("max.NaN.f32 %0, %0, %1;" : "+f"(nmax) : "f"(other));
-      }
-      if (lane == 0) red_f[warp][0] = nmax;
-      __syncthreads();
-      if (tid < cs) {
-        float m = red_f[0][0];
-        for (int w = 1; w < kSmemWarps; ++w) asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(red_f[w][0]));
-        *cluster.map_shared_rank(&xch2_f[xb][rank], tid) = m;
-      }
-      cluster.sync();
-    }
-
-    // ---- statistics of the normalised views, from the pass-1 sums (thread 0) ----------------------------------------
-    if (tid == 0) {
-      int st = st1;
-      const bool mixed0 = st == 0;
-      const double s = static_cast<double>(scale);
-      const double Ld = static_cast<double>(L);
-      float a_c = 0.f, b_c = 0.f, a_n = 0.f, b_n = 0.f, inv_dc = 1.f, inv_dn = 1.f;
-      if (p.peak_norm) {
-        if (st == 0) {
-          nmax = xch2_f[xb][0];
-          for (int r = 1; r < cs; ++r) asm("max.NaN.f32 %0, %0, %1;" : "+f"(nmax) : "f"(xch2_f[xb][r]));
-          if (isnan(nmax)) st = 8;                     // NaN in speech + scaled noise (augment.py:62)
-          else if (cmax < 1e-8f) st = 9;               // noisy_speech_dataset.py:95
-          else if (nmax < 1e-8f) st = 10;              // :99
-          else if (isinf(cmax)) st = 11;               // inf / inf -> NaN after the peak division (:107)
-          else if (isinf(nmax)) st = 12;               // (:111)
-        }
-        if (st == 0) {
-          const double dc = static_cast<double>(__fadd_rn(cmax, 1e-8f));
-          const double dn = static_cast<double>(__fadd_rn(nmax, 1e-8f));
-          const double mc = s_c1 / Ld / dc;
-          const double vc = s_cc / Ld / (dc * dc) - mc * mc;
-          const double mn = (s_c1 + s * s_n1) / Ld / dn;
-          const double vn = (s_cc + 2.0 * s * s_cn + s * s * s_nn) / Ld / (dn * dn) - mn * mn;
-          const float vcf = static_cast<float>(vc), vnf = static_cast<float>(vn);
-          const float mcf = static_cast<float>(mc), mnf = static_cast<float>(mn);
-          if (!isfinite(mcf) || !isfinite(vcf)) st = 13;
-          else if (!isfinite(mnf) || !isfinite(vnf)) st = 14;
-          inv_dc = static_cast<float>(1.0 / dc);
-          inv_dn = static_cast<float>(1.0 / dn);
-          a_c = mcf;
-          b_c = 1.0f / __fsqrt_rn(__fadd_rn(vcf, 1e-7f));
-          a_n = mnf;
-          b_n = 1.0f / __fsqrt_rn(__fadd_rn(vnf, 1e-7f));
-        }
-      } else {
-        const double sw = mixed0 ? (s_c1 + s * s_n1) : s_c1;
-        const double sww = mixed0 ? (s_cc + 2.0 * s * s_cn + s * s * s_nn) : s_cc;
-        const double mn = sw / Ld;
-        const double vn = sww / Ld - mn * mn;
-        a_n = static_cast<float>(mn);
-        b_n = 1.0f / __fsqrt_rn(__fadd_rn(static_cast<float>(vn), 1e-7f));
-        if (p.raw) {  // (y - 0) * 1 is exact: the output is the mixed signal itself
-          a_n = 0.f;
-          b_n = 1.f;
-        }
-      }
-      sc.inv_dc = inv_dc; sc.inv_dn = inv_dn;
-      sc.a_c = a_c; sc.b_c = b_c; sc.a_n = a_n; sc.b_n = b_n;
-      sc.st = st;
-      if (rank == 0) p.status[row] = st;
-    }
-    __syncthreads();
-    const int st = sc.st;
-    const bool mixed = st1 == 0;
-
-    // ---- output pass: shared memory -> global, 128-bit coalesced stores ------------------------------------------
-    float4* co = p.clean_out ? reinterpret_cast<float4*>(p.clean_out + static_cast<size_t>(row) * L) + v_begin : nullptr;
-    float4* no = reinterpret_cast<float4*>(p.noisy_out + static_cast<size_t>(row) * L) + v_begin;
-    if (p.peak_norm && st != 0) {
-      for (int v = tid; v < n_my; v += kSmemThreads) {
-        co[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        no[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      continue;
-    }
-    const f2 nac2 = f2_make(-sc.a_c, -sc.a_c), bc2 = f2_make(sc.b_c, sc.b_c), idc2 = f2_make(sc.inv_dc, sc.inv_dc);
-    const f2 nan2 = f2_make(-sc.a_n, -sc.a_n), bn2 = f2_make(sc.b_n, sc.b_n), idn2 = f2_make(sc.inv_dn, sc.inv_dn);
-    const f2 s2 = f2_make(scale, scale);
-  #pragma unroll 2
-    for (int v = tid; v < n_my; v += kSmemThreads) {
-      const float4 cv = s_c[v], yv = s_n[v];  // BYOL mode: the noise slot already holds the mixed signal
-      const f2 c01 = f2_make(cv.x, cv.y), c23 = f2_make(cv.z, cv.w);
-      f2 y01 = f2_make(yv.x, yv.y), y23 = f2_make(yv.z, yv.w);
-      float4 on;
-      if (p.peak_norm) {
-        float4 oc;
-        f2_split(f2_mul(f2_add(f2_mul(c01, idc2), nac2), bc2), oc.x, oc.y);  // (c/dc - mean) / std, 3 roundings
-        f2_split(f2_mul(f2_add(f2_mul(c23, idc2), nac2), bc2), oc.z, oc.w);
-        f2_split(f2_mul(f2_add(f2_mul(y01, idn2), nan2), bn2), on.x, on.y);
-        f2_split(f2_mul(f2_add(f2_mul(y23, idn2), nan2), bn2), on.z, on.w);
-        co[v] = oc;
-      } else {
-        if (mixed) {
-          y01 = f2_add(c01, f2_mul(y01, s2));
-          y23 = f2_add(c23, f2_mul(y23, s2));
-        } else {
-          y01 = c01;
-          y23 = c23;
-        }
-        f2_split(f2_mul(f2_add(y01, nan2), bn2), on.x, on.y);
-        f2_split(f2_mul(f2_add(y23, nan2), bn2), on.z, on.w);
-      }
-      no[v] = on;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Streaming variant: ONE large CTA (or a small cluster when the batch cannot fill the machine) per utterance,
-// reading the row three times -- pass 1 from HBM, passes 2 and 3 from L2 (the rows in flight, <= 148 x 512 KB,
-// fit the 126 MB L2; outputs are written with streaming stores so they do not evict them).  Unlike the
-// shared-memory variants the number of rows in flight is not capped by shared-memory capacity, which is what
-// bounds those at ~60 % of HBM peak (per-row latency ~7 us x 6.5 TB/s needs > 90 rows resident).
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kStreamThreads = 1024;
-constexpr int kStreamWarps = kStreamThreads / 32;
-constexpr int kStreamUnroll = 4;
 
 __device__ __forceinline__ void st_stream_cs_f4(float4* p, const float4& v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-__device__ __forceinline__ float4 ld_l2_f4(const float4* p) {  // skip L1 (re-read comes from L2), keep in L2
-  float4 r;
-  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-
-__global__ void __launch_bounds__(kStreamThreads, 1) mix_normalize_stream_kernel(const MixParams p) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = static_cast<int>(cluster.block_rank());
-  const int cs = static_cast<int>(cluster.num_blocks());
-  const int row = blockIdx.x / cs;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  __shared__ double red_d[kStreamWarps][5];
-  __shared__ float red_f[kStreamWarps][2];
-  __shared__ double xch1_d[kSmemMaxCluster][5];
-  __shared__ float xch1_f[kSmemMaxCluster][2];
-  __shared__ float xch2_f[kSmemMaxCluster];
-  __shared__ MixScalars sc;
-
-  const int L = p.L;
-  const int nvec = L >> 2;
-  const int seg = (nvec + cs - 1) / cs;
-  const int v_begin = min(nvec, rank * seg);
-  const int v_end = min(nvec, v_begin + seg);
-  if (p.retry && p.status[row] == 0) return;  // whole cluster (same row): nothing to redo
-  const float4* g_c = reinterpret_cast<const float4*>(p.clean + static_cast<size_t>(row) * L);
-  const float4* g_n = reinterpret_cast<const float4*>(
-      p.noise + static_cast<size_t>(p.retry ? (row + p.noise_shift) % p.B : row) * p.Ln);
-
-  // ---- pass 1 (HBM) -------------------------------------------------------------------------------------------
-  const f2 zero2 = f2_make(0.f, 0.f);
-  f2 a_cc = zero2, a_nn = zero2, a_c1 = zero2, a_n1 = zero2, a_cn = zero2;
-  float cmax = 0.f, nmax_in = 0.f;
-  for (int v0 = v_begin + tid; v0 < v_end; v0 += kStreamUnroll * kStreamThreads) {
-    float4 cv[kStreamUnroll], nv[kStreamUnroll];
-#pragma unroll
-    for (int u = 0; u < kStreamUnroll; ++u) {
-      const int v = v0 + u * kStreamThreads;
-      if (v < v_end) {
-        cv[u] = ld_l2_f4(g_c + v);
-        nv[u] = ld_l2_f4(g_n + v);
-      } else {
-        cv[u] = nv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kStreamUnroll; ++u) {
-      const f2 c01 = f2_make(cv[u].x, cv[u].y), c23 = f2_make(cv[u].z, cv[u].w);
-      const f2 n01 = f2_make(nv[u].x, nv[u].y), n23 = f2_make(nv[u].z, nv[u].w);
-      a_cc = f2_fma(c01, c01, a_cc); a_cc = f2_fma(c23, c23, a_cc);
-      a_nn = f2_fma(n01, n01, a_nn); a_nn = f2_fma(n23, n23, a_nn);
-      a_cn = f2_fma(c01, n01, a_cn); a_cn = f2_fma(c23, n23, a_cn);
-      a_c1 = f2_add(a_c1, c01); a_c1 = f2_add(a_c1, c23);
-      a_n1 = f2_add(a_n1, n01); a_n1 = f2_add(a_n1, n23);
-      cmax = fmaxf(fmaxf(cmax, fmaxf(fabsf(cv[u].x), fabsf(cv[u].y))), fmaxf(fabsf(cv[u].z), fabsf(cv[u].w)));
-      nmax_in = fmaxf(fmaxf(nmax_in, fmaxf(fabsf(nv[u].x), fabsf(nv[u].y))), fmaxf(fabsf(nv[u].z), fabsf(nv[u].w)));
-    }
-  }
-  {
-    double acc[5] = {static_cast<double>(f2_hsum(a_cc)), static_cast<double>(f2_hsum(a_nn)),
-                     static_cast<double>(f2_hsum(a_c1)), static_cast<double>(f2_hsum(a_n1)),
-                     static_cast<double>(f2_hsum(a_cn))};
-#pragma unroll
-    for (int k = 0; k < 5; ++k) acc[k] = warp_sum(acc[k]);
-    cmax = warp_max(cmax);
-    nmax_in = warp_max(nmax_in);
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) red_d[warp][k] = acc[k];
-      red_f[warp][0] = cmax;
-      red_f[warp][1] = nmax_in;
-    }
-    __syncthreads();
-    if (tid < cs) {
-      double tot[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-      float m0 = 0.f, m1 = 0.f;
-      for (int w = 0; w < kStreamWarps; ++w) {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) tot[k] += red_d[w][k];
-        m0 = fmaxf(m0, red_f[w][0]);
-        m1 = fmaxf(m1, red_f[w][1]);
-      }
-      double* dst_d = cluster.map_shared_rank(&xch1_d[rank][0], tid);
-      float* dst_f = cluster.map_shared_rank(&xch1_f[rank][0], tid);
-#pragma unroll
-      for (int k = 0; k < 5; ++k) dst_d[k] = tot[k];
-      dst_f[0] = m0;
-      dst_f[1] = m1;
-    }
-  }
-  if (cs > 1) cluster.sync();
-  else __syncthreads();
-
-  double s_cc = 0.0, s_nn = 0.0, s_c1 = 0.0, s_n1 = 0.0, s_cn = 0.0;
-  const double inv_L = 1.0 / static_cast<double>(L);
-  if (tid == 0) {
-    cmax = 0.f;
-    nmax_in = 0.f;
-    for (int r = 0; r < cs; ++r) {
-      s_cc += xch1_d[r][0];
-      s_nn += xch1_d[r][1];
-      s_c1 += xch1_d[r][2];
-      s_n1 += xch1_d[r][3];
-      s_cn += xch1_d[r][4];
-      cmax = fmaxf(cmax, xch1_f[r][0]);
-      nmax_in = fmaxf(nmax_in, xch1_f[r][1]);
-    }
-    const float Ps = static_cast<float>(s_cc * inv_L);
-    const float Pn = static_cast<float>(s_nn * inv_L);
-    int idx = p.snr_idx[row];
-    idx = idx < 0 ? 0 : (idx >= p.n_snr ? p.n_snr - 1 : idx);
-    const float scale = __fsqrt_rn(__fdiv_rn(Ps, __fmul_rn(Pn, p.snr_lin[idx])));
-    int st = 0;
-    if (isnan(Ps)) st = 1;
-    else if (isnan(Pn)) st = 2;
-    else if (Ps < 1e-10f) st = 3;
-    else if (Pn < 1e-10f) st = 4;
-    else if (isinf(scale) || isnan(scale)) st = 5;
-    else if (scale > 1e6f) st = 6;
-    else if (isinf(nmax_in)) st = 7;
-    sc.scale = scale;
-    sc.st1 = st;
-  }
-  __syncthreads();
-  const float scale = sc.scale;
-  const int st1 = sc.st1;
-  const f2 s2 = f2_make(scale, scale);
-
-  float nmax = 0.f;
-  if (p.peak_norm && st1 == 0) {
-    // ---- pass 2 (L2): peak of the mixed signal ---------------------------------------------------------------------
-    for (int v0 = v_begin + tid; v0 < v_end; v0 += kStreamUnroll * kStreamThreads) {
-      float4 cv[kStreamUnroll], nv[kStreamUnroll];
-#pragma unroll
-      for (int u = 0; u < kStreamUnroll; ++u) {
-        const int v = v0 + u * kStreamThreads;
-        if (v < v_end) {
-          cv[u] = ld_l2_f4(g_c + v);
-          nv[u] = ld_l2_f4(g_n + v);
-        } else {
-          cv[u] = nv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kStreamUnroll; ++u) {
-        float y0, y1, y2, y3;
-        f2_split(f2_add(f2_make(cv[u].x, cv[u].y), f2_mul(f2_make(nv[u].x, nv[u].y), s2)), y0, y1);
-        f2_split(f2_add(f2_make(cv[u].z, cv[u].w), f2_mul(f2_make(nv[u].z, nv[u].w), s2)), y2, y3);
-        nmax = absmax_nan(absmax_nan(absmax_nan(absmax_nan(nmax, y0), y1), y2), y3);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float other = __shfl_xor_sync(0xffffffffu, nmax, o);
-      asm("max.NaN.f32 %0, %0, %1;" : "+f"(nmax) : "f"(other));
-    }
-    if (lane == 0) red_f[warp][0] = nmax;
-    __syncthreads();
-    if (tid < cs) {
-      float m = red_f[0][0];
-      for (int w = 1; w < kStreamWarps; ++w) asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(red_f[w][0]));
-      *cluster.map_shared_rank(&xch2_f[rank], tid) = m;
-    }
-    if (cs > 1) cluster.sync();
-    else __syncthreads();
-  }
-
-  if (tid == 0) {
-    int st = st1;
-    const bool mixed0 = st == 0;
-    const double s = static_cast<double>(scale);
-    float a_c = 0.f, b_c = 0.f, a_n = 0.f, b_n = 0.f, inv_dc = 1.f, inv_dn = 1.f;
-    if (p.peak_norm) {
-      if (st == 0) {
-        nmax = xch2_f[0];
-        for (int r = 1; r < cs; ++r) asm("max.NaN.f32 %0, %0, %1;" : "+f"(nmax) : "f"(xch2_f[r]));
-        if (isnan(nmax)) st = 8;
-        else if (cmax < 1e-8f) st = 9;
-        else if (nmax < 1e-8f) st = 10;
-        else if (isinf(cmax)) st = 11;
-        else if (isinf(nmax)) st = 12;
-      }
-      if (st == 0) {
-        const double rdc = 1.0 / static_cast<double>(__fadd_rn(cmax, 1e-8f));
-        const double rdn = 1.0 / static_cast<double>(__fadd_rn(nmax, 1e-8f));
-        const double mc = s_c1 * inv_L * rdc;
-        const double vc = s_cc * inv_L * rdc * rdc - mc * mc;
-        const double mn = (s_c1 + s * s_n1) * inv_L * rdn;
-        const double vn = (s_cc + 2.0 * s * s_cn + s * s * s_nn) * inv_L * rdn * rdn - mn * mn;
-        const float vcf = static_cast<float>(vc), vnf = static_cast<float>(vn);
-        const float mcf = static_cast<float>(mc), mnf = static_cast<float>(mn);
-        if (!isfinite(mcf) || !isfinite(vcf)) st = 13;
-        else if (!isfinite(mnf) || !isfinite(vnf)) st = 14;
-        inv_dc = static_cast<float>(rdc);
-        inv_dn = static_cast<float>(rdn);
-        a_c = mcf;
-        b_c = 1.0f / __fsqrt_rn(__fadd_rn(vcf, 1e-7f));
-        a_n = mnf;
-        b_n = 1.0f / __fsqrt_rn(__fadd_rn(vnf, 1e-7f));
-      }
-    } else {
-      const double sw = mixed0 ? (s_c1 + s * s_n1) : s_c1;
-      const double sww = mixed0 ? (s_cc + 2.0 * s * s_cn + s * s * s_nn) : s_cc;
-      const double mn = sw * inv_L;
-      const double vn = sww * inv_L - mn * mn;
-      a_n = static_cast<float>(mn);
-      b_n = 1.0f / __fsqrt_rn(__fadd_rn(static_cast<float>(vn), 1e-7f));
-      if (p.raw) {
-        a_n = 0.f;
-        b_n = 1.f;
-      }
-    }
-    sc.inv_dc = inv_dc; sc.inv_dn = inv_dn;
-    sc.a_c = a_c; sc.b_c = b_c; sc.a_n = a_n; sc.b_n = b_n;
-    sc.st = st;
-    if (rank == 0) p.status[row] = st;
-  }
-  __syncthreads();
-  const int st = sc.st;
-  const bool mixed = st1 == 0;
-
-  // ---- pass 3 (L2 -> HBM) ---------------------------------------------------------------------------------------------
-  float4* co = p.clean_out ? reinterpret_cast<float4*>(p.clean_out + static_cast<size_t>(row) * L) : nullptr;
-  float4* no = reinterpret_cast<float4*>(p.noisy_out + static_cast<size_t>(row) * L);
-  if (p.peak_norm && st != 0) {
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int v = v_begin + tid; v < v_end; v += kStreamThreads) {
-      st_stream_cs_f4(co + v, z);
-      st_stream_cs_f4(no + v, z);
-    }
-    return;
-  }
-  const f2 nac2 = f2_make(-sc.a_c, -sc.a_c), bc2 = f2_make(sc.b_c, sc.b_c), idc2 = f2_make(sc.inv_dc, sc.inv_dc);
-  const f2 nan2 = f2_make(-sc.a_n, -sc.a_n), bn2 = f2_make(sc.b_n, sc.b_n), idn2 = f2_make(sc.inv_dn, sc.inv_dn);
-  for (int v0 = v_begin + tid; v0 < v_end; v0 += kStreamUnroll * kStreamThreads) {
-    float4 cv[kStreamUnroll], nv[kStreamUnroll];
-#pragma unroll
-    for (int u = 0; u < kStreamUnroll; ++u) {
-      const int v = v0 + u * kStreamThreads;
-      if (v < v_end) {
-        cv[u] = ld_stream_f4(g_c + v);  // last use of the inputs
-        nv[u] = ld_stream_f4(g_n + v);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kStreamUnroll; ++u) {
-      const int v = v0 + u * kStreamThreads;
-      if (v >= v_end) break;
-      const f2 c01 = f2_make(cv[u].x, cv[u].y), c23 = f2_make(cv[u].z, cv[u].w);
-      f2 y01 = f2_make(nv[u].x, nv[u].y), y23 = f2_make(nv[u].z, nv[u].w);
-      if (mixed) {
-        y01 = f2_add(c01, f2_mul(y01, s2));  // augment.py:54,60 (mul and add round separately)
-        y23 = f2_add(c23, f2_mul(y23, s2));
-      } else {
-        y01 = c01;
-        y23 = c23;
-      }
-      float4 on;
-      if (p.peak_norm) {
-        float4 oc;
-        f2_split(f2_mul(f2_add(f2_mul(c01, idc2), nac2), bc2), oc.x, oc.y);
-        f2_split(f2_mul(f2_add(f2_mul(c23, idc2), nac2), bc2), oc.z, oc.w);
-        f2_split(f2_mul(f2_add(f2_mul(y01, idn2), nan2), bn2), on.x, on.y);
-        f2_split(f2_mul(f2_add(f2_mul(y23, idn2), nan2), bn2), on.z, on.w);
-        st_stream_cs_f4(co + v, oc);
-      } else {
-        f2_split(f2_mul(f2_add(y01, nan2), bn2), on.x, on.y);
-        f2_split(f2_mul(f2_add(y23, nan2), bn2), on.z, on.w);
-      }
-      st_stream_cs_f4(no + v, on);
-    }
-  }
-}
-
 
 // ---------------------------------------------------------------------------------------------------------
 // On-chip-resident variant (default when the row fits): the whole row lives ON CHIP between the passes -- the first
@@ -1162,8 +570,9 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
     }
     const float Ps = static_cast<float>(s_cc * inv_L);
     const float Pn = static_cast<float>(s_nn * inv_L);
-    int idx = p.snr_idx[row];
+    int idx = p.snr_idx[p.retry ? (row + p.noise_shift) % p.B : row];
     idx = idx < 0 ? 0 : (idx >= p.n_snr ? p.n_snr - 1 : idx);
+    if (rank == 0 && p.snr_used != nullptr) p.snr_used[row] = idx;
     const float scale = __fsqrt_rn(__fdiv_rn(Ps, __fmul_rn(Pn, p.snr_lin[idx])));
     int st = 0;
     if (isnan(Ps)) st = 1;
@@ -1318,13 +727,49 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
   for (int v = tid; v < n_sm; v += kResThreads) emit(n_reg + v, s_c[v], s_n[v]);
 }
 
-int g_mix_carveout = -1;  // shared-memory carveout (percent) of the resident kernels; -1: just what the CTAs need
-int g_mix_stream_cluster = 0;  // 0: automatic; 1/2/4/8 force the CTAs-per-row of the streaming variant (tuning)
-int g_mix_variant = 4;  // 4: on-chip resident (registers + shared memory), default when the row fits 8 CTAs
-                        //    (5: the same, forcing the 1024-thread / one-CTA-per-SM shape);
-                        // 3: streaming, one large CTA (or small cluster) per row, passes 2-3 from L2;
-                        // 2: persistent double-buffered shared-memory pipeline; 1: shared memory, one row per
-                        // cluster; 0: generic re-read-from-L2 kernel (also the fallback for unaligned rows)
+// Rows that failed every attempt (status != 0 after the retries) take over the outputs of the nearest following good row
+// of the batch -- the device-side form of the reference's "move on to the next item" (ref:src/data/
+// noisy_speech_dataset.py:60-66) -- so that no all-zero waveform reaches BatchNorm statistics or the loss mean.  One CTA
+// per row; the CTAs of good rows exit at once: on a healthy batch the launch moves no data.  `status` is not modified (it
+// keeps reporting why the row failed); a batch without any good row is left as it is.
+__global__ void __launch_bounds__(256) mix_substitute_kernel(float* __restrict__ clean_out, float* __restrict__ noisy_out,
+                                                             const int32_t* __restrict__ status,
+                                                             int32_t* __restrict__ snr_used, int B, int L) {
+  const int row = blockIdx.x;
+  if (status[row] == 0) return;
+  __shared__ int s_src;
+  if (threadIdx.x == 0) {
+    int src = -1;
+    for (int d = 1; d < B; ++d) {
+      const int r = (row + d) % B;
+      if (status[r] == 0) { src = r; break; }
+    }
+    s_src = src;
+    if (src >= 0 && snr_used != nullptr) snr_used[row] = snr_used[src];  // good rows' entries are never written here
+  }
+  __syncthreads();
+  const int src = s_src;
+  if (src < 0) return;
+  for (int k = 0; k < 2; ++k) {
+    float* base = k == 0 ? clean_out : noisy_out;
+    if (base == nullptr) continue;
+    const float* from = base + static_cast<size_t>(src) * L;
+    float* to = base + static_cast<size_t>(row) * L;
+    if (((reinterpret_cast<uintptr_t>(from) | reinterpret_cast<uintptr_t>(to)) & 15u) == 0 && L % 4 == 0) {
+      for (int v = threadIdx.x; v < L / 4; v += blockDim.x)
+        reinterpret_cast<float4*>(to)[v] = reinterpret_cast<const float4*>(from)[v];
+    } else {
+      for (int i = threadIdx.x; i < L; i += blockDim.x) to[i] = from[i];
+    }
+  }
+}
+
+int g_mix_carveout = -1;  // shared-memory carveout (percent) of the resident kernel; -1: just what the CTAs need
+int g_mix_cluster = 0;    // 0: automatic; 1..8 force the CTAs per row of the resident kernel (tuning)
+int g_mix_variant = 4;    // 4: on-chip resident (registers + shared memory) whenever the row fits 8 CTAs (default);
+                          // 5: the same, forcing the 1024-thread / one-CTA-per-SM shape;
+                          // 0: always the generic re-read-from-L2 kernel (the fallback for unaligned rows, tiled noise
+                          //    and rows beyond 8 x 40960 samples)
 
 const char* const kMixStatusNames[] = {
     "ok", "speech_nan", "noise_nan", "speech_power_too_small", "noise_power_too_small", "scale_invalid",
@@ -1338,7 +783,7 @@ extern "C" {
 
 int nrse_mix_set_cluster(int ctas_per_row) {
   if (ctas_per_row < 0 || ctas_per_row > nrse::kSmemMaxCluster) return NRSE_ERR_INVALID_ARG;
-  nrse::g_mix_stream_cluster = ctas_per_row;
+  nrse::g_mix_cluster = ctas_per_row;
   return NRSE_OK;
 }
 
@@ -1349,7 +794,7 @@ int nrse_mix_set_carveout(int percent) {
 }
 
 int nrse_mix_set_variant(int variant) {
-  if (variant < 0 || variant > 5) return NRSE_ERR_INVALID_ARG;
+  if (variant != 0 && variant != 4 && variant != 5) return NRSE_ERR_INVALID_ARG;
   nrse::g_mix_variant = variant;
   return NRSE_OK;
 }
@@ -1360,8 +805,8 @@ const char* nrse_mix_status_name(int code) {
 
 static int mix_normalize_impl(const float* clean, const float* noise, const int32_t* snr_idx,
                               const double* snr_db_table_host, int n_snr, float* clean_out, float* noisy_out,
-                              int32_t* status, int B, int L, int L_noise, int peak_norm, int retry, int noise_shift,
-                              nrse_stream_t stream) {
+                              int32_t* status, int32_t* snr_used, int B, int L, int L_noise, int peak_norm, int retry,
+                              int noise_shift, nrse_stream_t stream) {
   using namespace nrse;
   if (!clean || !noise || !snr_idx || !snr_db_table_host || !noisy_out || !status) return NRSE_ERR_INVALID_ARG;
   if (B < 0 || L <= 0 || L_noise <= 0 || n_snr <= 0 || n_snr > kMaxSnr) return NRSE_ERR_INVALID_ARG;
@@ -1373,13 +818,11 @@ static int mix_normalize_impl(const float* clean, const float* noise, const int3
   MixParams p;
   p.clean = clean; p.noise = noise; p.snr_idx = snr_idx;
   p.clean_out = peak_norm == 1 ? clean_out : nullptr;
-  p.noisy_out = noisy_out; p.status = status;
+  p.noisy_out = noisy_out; p.status = status; p.snr_used = snr_used;
   p.B = B; p.L = L; p.Ln = L_noise; p.peak_norm = peak_norm == 1 ? 1 : 0; p.n_snr = n_snr;
   p.raw = peak_norm == 2 ? 1 : 0;
   p.retry = retry ? 1 : 0;
   p.noise_shift = retry ? noise_shift % B : 0;
-  const int mix_variant = (retry && (g_mix_variant == 1 || g_mix_variant == 2)) ? 3 : g_mix_variant;  // the shared-
-  // memory variants walk several rows per cluster and do not implement the retry skip
   for (int i = 0; i < kMaxSnr; ++i)
     p.snr_lin[i] = i < n_snr ? static_cast<float>(std::pow(10.0, snr_db_table_host[i] / 10.0)) : 1.0f;
 
@@ -1396,13 +839,13 @@ static int mix_normalize_impl(const float* clean, const float* noise, const int3
   cfg.attrs = attr;
   cfg.numAttrs = 1;
 
-  if (vec && mix_variant >= 4) {
+  if (vec && g_mix_variant >= 4) {
     // CTAs per row (<= 8, any size; sweep in scripts/bench_mix_sweep.py, B200): the 512-thread shape with segments of
     // <= 4096 float4 (half in registers, half in shared memory: 2 x 64 KB of shared memory per SM leaves ~100 KB of
     // L1 for the register-bound loads in flight) is best at every length it can serve; segments that fill the whole
     // shared-memory capacity (5334 float4: 61 % instead of 73 % at 4 s) or larger clusters than needed lose 5-15 %.
     // Longer rows: 512 threads up to the full capacity, then the 1024-thread shape; rows beyond 8 x 40960 samples
-    // (20 s) go to the streaming variant.
+    // (20 s) go to the generic kernel.
     const int nvec = L / 4;
     auto min_cluster = [&](int cap) {
       const int cs = ceil_div(nvec, cap);
@@ -1410,14 +853,14 @@ static int mix_normalize_impl(const float* clean, const float* noise, const int3
     };
     int threads = 512, cs = min_cluster(2 * ResCfg<512>::kRegCap);
     if (cs > kSmemMaxCluster) cs = min_cluster(ResCfg<512>::kCap);
-    if (cs > kSmemMaxCluster || mix_variant == 5) {
+    if (cs > kSmemMaxCluster || g_mix_variant == 5) {
       threads = 1024;
       cs = min_cluster(ResCfg<1024>::kCap);
     }
     if (cs <= kSmemMaxCluster) {
       const int cap = threads == 512 ? ResCfg<512>::kCap : ResCfg<1024>::kCap;
       const int reg_cap = threads == 512 ? ResCfg<512>::kRegCap : ResCfg<1024>::kRegCap;
-      if (g_mix_stream_cluster > 0 && ceil_div(nvec, g_mix_stream_cluster) <= cap) cs = g_mix_stream_cluster;
+      if (g_mix_cluster > 0 && ceil_div(nvec, g_mix_cluster) <= cap) cs = g_mix_cluster;
       const int seg_vec = ceil_div(nvec, cs);
       const int smem_pitch = seg_vec > reg_cap ? seg_vec - reg_cap : 0;
       const size_t dyn = static_cast<size_t>(smem_pitch) * 32;
@@ -1460,64 +903,8 @@ static int mix_normalize_impl(const float* clean, const float* noise, const int3
       return NRSE_OK;
     }
   }
-  if (vec && mix_variant >= 3) {
-    // one CTA of 1024 threads per row when the batch fills the machine, else the largest cluster (<= 8) that keeps
-    // B * cs within the SM count
-    // 1 CTA per SM (1024 threads x 64 registers): pick the cluster size (CTAs per row) that wastes the fewest SM-slots
-    // in the last wave, preferring fewer CTAs per row on ties (each extra CTA costs two cluster barriers per row)
-    int cs = 1;
-    double best = 1e30;
-    for (int c = 1; c <= kSmemMaxCluster; c *= 2) {
-      if ((L / 4) < c * 256) break;  // keep at least a quarter of the threads busy
-      const long long ctas = static_cast<long long>(B) * c;
-      const long long waves = (ctas + kNumSMs - 1) / kNumSMs;
-      const double cost = static_cast<double>(waves * kNumSMs) / static_cast<double>(ctas) * (1.0 + 0.03 * (c > 1 ? 1 : 0));
-      if (cost < best - 1e-9) { best = cost; cs = c; }
-    }
-    if (g_mix_stream_cluster > 0) cs = g_mix_stream_cluster;
-    cfg.gridDim = dim3(static_cast<unsigned>(B) * cs);
-    cfg.blockDim = dim3(kStreamThreads);
-    cfg.dynamicSmemBytes = 0;
-    attr[0].val.clusterDim.x = cs;
-    NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_stream_kernel, p));
-    return NRSE_OK;
-  }
-  if (vec && mix_variant >= 1) {
-    // smallest power-of-two cluster (<= 8) whose per-CTA stage (both row segments) is <= 64 KB
-    const size_t row_bytes = static_cast<size_t>(L) * 8;
-    int cs = 1;
-    while (cs < kSmemMaxCluster && row_bytes > static_cast<size_t>(cs) * 65536) cs *= 2;
-    const int nvec = L / 4;
-    const int seg_vec = ceil_div(nvec, cs);
-    const size_t stage_bytes = static_cast<size_t>(seg_vec) * 32;
-    const size_t kMaxSmem = 200 * 1024;
-    static bool attr_set = false;  // benign race: idempotent attributes
-    if (!attr_set) {
-      NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_smem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kMaxSmem)));
-      NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_smem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kMaxSmem)));
-      attr_set = true;
-    }
-    cfg.blockDim = dim3(kSmemThreads);
-    attr[0].val.clusterDim.x = cs;
-    if (mix_variant == 2 && 2 * stage_bytes <= kMaxSmem) {
-      // persistent: as many clusters as fit one CTA per SM (two stages of shared memory per CTA)
-      const int ctas_per_sm = static_cast<int>(kMaxSmem / (2 * stage_bytes)) >= 2 ? 2 : 1;
-      int n_clusters = kNumSMs * ctas_per_sm / cs;
-      n_clusters = n_clusters < B ? n_clusters : B;
-      cfg.gridDim = dim3(static_cast<unsigned>(n_clusters) * cs);
-      cfg.dynamicSmemBytes = 2 * stage_bytes;
-      NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_smem_kernel<2>, p, seg_vec));
-      return NRSE_OK;
-    }
-    if (stage_bytes <= kMaxSmem) {
-      cfg.gridDim = dim3(static_cast<unsigned>(B) * cs);
-      cfg.dynamicSmemBytes = stage_bytes;
-      NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_smem_kernel<1>, p, seg_vec));
-      return NRSE_OK;
-    }
-  }
+  // generic kernel: a fixed cluster of 4 CTAs per row, pass 1 from HBM, passes 2-3 re-read from L2; any alignment, any
+  // length, tiled noise
   cfg.gridDim = dim3(static_cast<unsigned>(B) * kMixCluster);
   cfg.blockDim = dim3(kMixThreads);
   cfg.dynamicSmemBytes = 0;
@@ -1527,19 +914,29 @@ static int mix_normalize_impl(const float* clean, const float* noise, const int3
   return NRSE_OK;
 }
 
+int nrse_mix_substitute_rows_f32(float* clean_out, float* noisy_out, const int32_t* status, int32_t* snr_idx_used, int B,
+                                 int L, nrse_stream_t stream) {
+  using namespace nrse;
+  if (!noisy_out || !status || B < 0 || L <= 0) return NRSE_ERR_INVALID_ARG;
+  if (B < 2) return NRSE_OK;  // nothing to substitute from
+  mix_substitute_kernel<<<B, 256, 0, as_stream(stream)>>>(clean_out, noisy_out, status, snr_idx_used, B, L);
+  NRSE_CHECK_LAUNCH();
+  return NRSE_OK;
+}
+
 int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t* snr_idx,
                            const double* snr_db_table_host, int n_snr, float* clean_out, float* noisy_out,
                            int32_t* status, int B, int L, int L_noise, int peak_norm, nrse_stream_t stream) {
-  return mix_normalize_impl(clean, noise, snr_idx, snr_db_table_host, n_snr, clean_out, noisy_out, status, B, L, L_noise,
-                            peak_norm, 0, 0, stream);
+  return mix_normalize_impl(clean, noise, snr_idx, snr_db_table_host, n_snr, clean_out, noisy_out, status, nullptr, B, L,
+                            L_noise, peak_norm, 0, 0, stream);
 }
 
 int nrse_mix_normalize_retry_f32(const float* clean, const float* noise, const int32_t* snr_idx,
                                  const double* snr_db_table_host, int n_snr, float* clean_out, float* noisy_out,
-                                 int32_t* status, int B, int L, int L_noise, int peak_norm, int noise_row_shift,
-                                 nrse_stream_t stream) {
-  return mix_normalize_impl(clean, noise, snr_idx, snr_db_table_host, n_snr, clean_out, noisy_out, status, B, L, L_noise,
-                            peak_norm, 1, noise_row_shift, stream);
+                                 int32_t* status, int32_t* snr_idx_used, int B, int L, int L_noise, int peak_norm,
+                                 int noise_row_shift, nrse_stream_t stream) {
+  return mix_normalize_impl(clean, noise, snr_idx, snr_db_table_host, n_snr, clean_out, noisy_out, status, snr_idx_used,
+                            B, L, L_noise, peak_norm, 1, noise_row_shift, stream);
 }
 
 }  // extern "C"

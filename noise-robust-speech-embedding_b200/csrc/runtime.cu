@@ -8,7 +8,15 @@ void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
 
 extern "C" {
 
-int nrse_version(void) { return 100; /* 0.1.0 */ }
+int nrse_version(void) { return 200; /* 0.2.0 */ }
+
+int nrse_experiments_build(void) {
+#ifdef NRSE_EXPERIMENTS
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 const char* nrse_strerror(int status) {
   switch (status) {

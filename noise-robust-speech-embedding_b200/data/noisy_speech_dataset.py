@@ -10,7 +10,7 @@ mix + peak-norm + z-norm kernel once per batch.  The batches the training loop s
 
 The reference's retry policy (up to 5 re-draws when ``add_noise_to_speech`` / normalisation rejects an item,
 :56-148) is kept: the kernel reports one status word per row, the mixer re-draws the noise of rejected rows from the
-other rows of the batch, and rows that still fail after ``max_attempts`` are dropped from the batch.
+other rows of the batch, and rows that still fail after ``max_attempts`` are replaced by the nearest good row of the batch (``GpuBatchMixer``).
 """
 from __future__ import annotations
 
@@ -149,25 +149,43 @@ class GpuBatchMixer:
     host synchronisation.
 
     The reference's ``__getitem__`` retries an item up to five times when ``add_noise_to_speech`` or the peak checks
-    reject it (ref:src/data/noisy_speech_dataset.py:55-149), synchronising the worker ~20 times per item to decide.  Here
-    the decision stays on the device: after the first launch, ``max_attempts - 1`` retry launches redo exactly the rows
-    whose status is non-zero with another row's noise crop (``ops.mix_normalize_retry_``); for a healthy batch their
-    CTAs exit immediately.  The host never reads the status on the critical path: a count of rows that are still bad is
-    copied to pinned memory asynchronously and looked at when the NEXT batch is prepared (by then it has long arrived).
-    Such rows (the reference would return ``None`` for them and crash the collate) stay in the batch zero-filled
-    (BYOL mode) / as the clean waveform (emotion mode) and are reported through ``batch["mix_status"]`` and the log.
-    ``drop_bad_rows=True`` restores the old behaviour -- read the status and drop those rows -- at the price of one host
-    synchronisation per batch."""
+    reject it, drawing another noise file AND another SNR each time (ref:src/data/noisy_speech_dataset.py:55-149), and
+    never emits an unusable item.  Here the decisions stay on the device:
+
+    * after the first launch, ``max_attempts - 1`` retry launches redo exactly the rows whose status is non-zero with
+      another row's noise crop and SNR draw (``ops.mix_normalize_retry_``); for a healthy batch their CTAs exit at once;
+    * rows that are still bad after that (a silent or NaN CLEAN crop can never recover) are handled by ``bad_rows``:
+      ``"substitute"`` (default) -- one more no-op-when-healthy launch copies the nearest following good row over them
+      (``ops.mix_substitute_rows_``), the device-side form of the reference's "move on to the next item"
+      (:60-66): the batch keeps its size, no all-zero waveform reaches BatchNorm statistics or the loss mean, and the
+      host still never waits; ``"drop"`` -- read the status and remove the rows (one host synchronisation per batch);
+      ``"keep"`` -- leave them zero-filled (BYOL mode) / as the clean waveform (emotion mode).
+    * ``batch["snr"]`` follows the SNR index every row was finally mixed at; ``batch["mix_status"]`` keeps the failure
+      code of every row that was ever rejected for good, and a count of such rows is copied to pinned memory
+      asynchronously and logged when the NEXT batch is prepared (by then it has long arrived).
+
+    With a single-row batch there is no other row to borrow noise or outputs from: such a row stays as the kernel left it.
+    """
 
     def __init__(self, snr_range: Sequence[int], device, peak_norm: bool = True, max_attempts: int = 5,
-                 drop_bad_rows: bool = False):
+                 bad_rows: str = "substitute", drop_bad_rows: Optional[bool] = None):
+        if drop_bad_rows is not None:  # older spelling
+            bad_rows = "drop" if drop_bad_rows else "keep"
+        if bad_rows not in ("substitute", "drop", "keep"):
+            raise ValueError("bad_rows must be 'substitute', 'drop' or 'keep'")
         self.snr_table = [float(v) for v in snr_range]
         self.device = torch.device(device)
         self.peak_norm = peak_norm
         self.max_attempts = max_attempts
-        self.drop_bad_rows = drop_bad_rows
+        self.bad_rows = bad_rows
         self.rejected_rows = 0          # rows that stayed bad after all attempts, as far as already observed
         self._pending = []              # [(pinned count tensor, event)] of batches not yet looked at
+        self._free = []                 # pinned counters / events to reuse (cudaHostAlloc per batch would cost ~100 us)
+        self._snr_values = None
+
+    @property
+    def drop_bad_rows(self) -> bool:
+        return self.bad_rows == "drop"
 
     def _poll(self, block: bool = False) -> None:
         keep = []
@@ -178,8 +196,8 @@ class GpuBatchMixer:
                 n = int(cnt.item())
                 if n:
                     self.rejected_rows += n
-                    logger.error("%d row(s) failed all %d mix attempts and were left zero-filled / clean", n,
-                                 self.max_attempts)
+                    logger.error("%d row(s) failed all %d mix attempts (policy: %s)", n, self.max_attempts, self.bad_rows)
+                self._free.append((cnt, ev))
             else:
                 keep.append((cnt, ev))
         self._pending = keep
@@ -195,13 +213,22 @@ class GpuBatchMixer:
         self._poll()
         clean = raw["clean_wave"].to(dev, non_blocking=True).flatten(1).contiguous().float()
         noise = raw["noise_wave"].to(dev, non_blocking=True).flatten(1).contiguous().float()
-        snr_idx = torch.as_tensor(raw["snr_idx"]).to(dev, non_blocking=True).to(torch.int32)
-        snr = torch.as_tensor(raw["snr"]).to(dev, non_blocking=True).to(torch.int64)
+        snr_idx = torch.as_tensor(raw["snr_idx"]).to(dev, non_blocking=True).to(torch.int32).contiguous()
         c, n, status = ops.mix_normalize(clean, noise, snr_idx, self.snr_table, self.peak_norm)
-        if self.peak_norm and clean.shape[0] > 1:
+        retried = self.peak_norm and clean.shape[0] > 1 and self.max_attempts > 1
+        snr_used = snr_idx.clone() if retried else snr_idx
+        if retried:
             for attempt in range(1, self.max_attempts):  # device-side retries: no-ops unless a row was rejected
-                ops.mix_normalize_retry_(clean, noise, snr_idx, self.snr_table, c, n, status, attempt, True)
-        if self.drop_bad_rows:
+                ops.mix_normalize_retry_(clean, noise, snr_idx, self.snr_table, c, n, status, attempt, True, snr_used)
+            if self.bad_rows == "substitute":
+                ops.mix_substitute_rows_(c, n, status, snr_used)
+        if self._snr_values is None or self._snr_values.device != clean.device:
+            self._snr_values = torch.tensor([int(round(v)) if float(v).is_integer() else v for v in self.snr_table],
+                                            device=clean.device)
+        # the label every row was FINALLY mixed at (a retry re-draws the SNR, as the reference's next attempt does)
+        snr = self._snr_values[snr_used.long()].to(torch.int64) if retried else \
+            torch.as_tensor(raw["snr"]).to(dev, non_blocking=True).to(torch.int64)
+        if self.bad_rows == "drop":
             bad = status != 0
             if bool(bad.any()):  # host synchronisation
                 keep = (~bad).nonzero().flatten()
@@ -209,9 +236,8 @@ class GpuBatchMixer:
                 self.rejected_rows += int(bad.sum())
                 c, n, snr, status = (c[keep] if c is not None else None), n[keep], snr[keep], status[keep]
         elif self.peak_norm:
-            cnt = torch.empty(1, dtype=torch.int64).pin_memory()
+            cnt, ev = self._free.pop() if self._free else (torch.empty(1, dtype=torch.int64).pin_memory(), torch.cuda.Event())
             cnt.copy_((status != 0).sum().reshape(1), non_blocking=True)
-            ev = torch.cuda.Event()
             ev.record()
             self._pending.append((cnt, ev))
         out = {"noisy_input_values": n.unsqueeze(1), "snr": snr, "mix_status": status}
@@ -230,6 +256,12 @@ class MixedBatchLoader:
 
     def __len__(self) -> int:
         return len(self.loader)
+
+    def set_epoch(self, epoch: int) -> None:
+        """Forwarded to the ``DistributedSampler`` (if any) so that every epoch is shuffled differently across ranks."""
+        sampler = getattr(self.loader, "sampler", None)
+        if hasattr(sampler, "set_epoch"):
+            sampler.set_epoch(epoch)
 
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
         for raw in self.loader:
@@ -252,6 +284,16 @@ def create_dataloaders(config, feature_extractor=None, device=None, dataset: Opt
     device = device or config.get("device", "cuda:0")
     mixer = GpuBatchMixer(data["snr_range"], device)
     kw = dict(batch_size=training["batch_size"], num_workers=training.get("num_workers", 4), pin_memory=True)
-    train = DataLoader(train_ds, shuffle=True, **kw)
-    val = DataLoader(val_ds, shuffle=False, **kw)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        # data parallel: every rank iterates its own 1/world shard of both splits (``batch_size`` is per rank); call
+        # ``train_loader.set_epoch(epoch)`` each epoch.  Without this every rank would draw the SAME batches (same seed)
+        # and the all-reduce would average N copies of one gradient.
+        from torch.utils.data.distributed import DistributedSampler
+        seed = training.get("seed", 42)
+        train = DataLoader(train_ds, sampler=DistributedSampler(train_ds, shuffle=True, seed=seed), **kw)
+        val = DataLoader(val_ds, sampler=DistributedSampler(val_ds, shuffle=False, seed=seed), **kw)
+    else:
+        train = DataLoader(train_ds, shuffle=True, **kw)
+        val = DataLoader(val_ds, shuffle=False, **kw)
     return MixedBatchLoader(train, mixer), MixedBatchLoader(val, mixer)

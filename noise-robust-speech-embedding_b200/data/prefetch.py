@@ -10,6 +10,8 @@ import torch
 
 class DevicePrefetcher:
     def __init__(self, device, depth: int = 2):
+        if depth < 2:
+            raise ValueError("DevicePrefetcher needs depth >= 2 (one slot being consumed, one being filled)")
         self.device = torch.device(device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.depth = depth

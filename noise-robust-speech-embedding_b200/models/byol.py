@@ -90,9 +90,20 @@ class BYOLSpeechModel(nn.Module):
         return self.online_encoder
 
 
+def log_loss_flags(flags: int) -> None:
+    """The reference's two diagnostics (ref:src/models/byol.py:109-122) from the loss kernel's flag word."""
+    if flags & 0x3:
+        logger.error("NaN detected in tensors before normalization!")
+    if flags & 0xC:
+        logger.error("NaN detected in tensors after normalization!")
+
+
 def byol_loss(online_pred: torch.Tensor, target_proj: torch.Tensor, check_finite: bool = False) -> torch.Tensor:
-    """2 - 2 * mean_b clamp(<normalize(p + 1e-10), normalize(z + 1e-10)>, -1, 1)  (ref:src/models/byol.py:104-129)."""
-    loss = ops.byol_loss(online_pred, target_proj)
-    if check_finite and not bool(torch.isfinite(loss)):
-        logger.error("NaN detected in BYOL loss inputs!")
+    """2 - 2 * mean_b clamp(<normalize(p + 1e-10), normalize(z + 1e-10)>, -1, 1)  (ref:src/models/byol.py:104-129).
+    ``check_finite=True`` reproduces the reference's two NaN diagnostics on the INPUTS (before / after normalisation):
+    the same launch writes a flag word, and reading it is one host synchronisation (the reference pays four)."""
+    if not check_finite:
+        return ops.byol_loss(online_pred, target_proj)
+    loss, flags = ops.byol_loss_with_flags(online_pred, target_proj)
+    log_loss_flags(int(flags.item()))
     return loss

@@ -1,98 +1,65 @@
-"""Drop-in replacement of HF ``WavLMFeatureEncoder`` (hf:models/wavlm/modeling_wavlm.py:754-789) whose forward runs
-the B200 kernels.  It IS a ``WavLMFeatureEncoder`` (same ``conv_layers`` ModuleList, same parameter names/shapes,
-``_freeze_parameters``, ``_requires_grad``, ``gradient_checkpointing``), so checkpoints, ``named_parameters()``
-substring matches (ref:src/models/emotion.py:126-129) and ``load_state_dict`` keep working; only ``forward`` differs.
+"""Drop-in replacement of HF ``WavLMFeatureEncoder`` (hf:models/wavlm/modeling_wavlm.py:754-789) whose forward AND
+backward run the B200 kernels.  It IS a ``WavLMFeatureEncoder`` (same ``conv_layers`` ModuleList, same parameter
+names/shapes, ``_freeze_parameters``, ``_requires_grad``, ``gradient_checkpointing``), so checkpoints,
+``named_parameters()`` substring matches (ref:src/models/emotion.py:126-129) and ``load_state_dict`` keep working; only
+``forward`` differs.
 
 forward([B,L] fp32) -> [B,512,T] fp32, returned as a transposed VIEW of the kernels' channels-last [B,T,512]
 output -- ``WavLMModel.forward`` transposes it straight back (hf:...:1061), so no copy is ever made.
 
-Backward: in LayerNorm mode (wavlm-large) the training forward keeps a tape (bf16 activations, normalised
-pre-affine values, 1/std per frame) and the backward runs the native kernels -- LayerNorm+GELU backward, tcgen05
-weight-gradient GEMM with split-K, data-gradient GEMMs (``ops.conv_frontend_backward``).  GroupNorm mode (wavlm-base)
-and the rarely needed waveform gradient fall back to recomputation with stock torch ops (``_FrontendFn``).
+Backward (both norm modes: LayerNorm on every layer = wavlm-large, GroupNorm on layer 0 only = wavlm-base): the training
+forward keeps a tape (bf16 activations, normalised pre-affine values, statistics) and the backward runs the native
+kernels (``ops.conv_frontend_backward``): norm + GELU backward, tcgen05 weight-gradient GEMMs with split-K, data-gradient
+GEMMs.  Only the gradients autograd actually asks for are computed -- a partially unfrozen encoder
+(ref:src/models/emotion.py:114-129) stops at its lowest trainable conv layer.  The waveform gradient is not implemented
+(nothing upstream of the waveform is trainable anywhere in the reference) and asking for it raises.
+
+The bf16 weight packs the kernels consume are cached and keyed on (parameter address, ``tensor._version``,
+``ops.param_generation()``): torch-side writers bump ``_version``; the multi-tensor kernels (``FusedAdamWEma``,
+``EmaPlan``) write through raw pointers and bump the generation counter instead.
 """
 from __future__ import annotations
 
-from typing import List, Optional
-
 import torch
-import torch.nn.functional as F
 from transformers.models.wavlm.modeling_wavlm import WavLMFeatureEncoder
 
 from .. import ops
 
 
-def _torch_stack(x: torch.Tensor, conv_w, gammas, betas, norm_mode: str) -> torch.Tensor:
-    """Stock-torch restatement of the conv stack, used ONLY to differentiate (recompute in backward)."""
-    h = x[:, None]
-    for i, w in enumerate(conv_w):
-        h = F.conv1d(h, w, stride=ops.CONV_STRIDE[i])
-        if norm_mode == "layer":
-            h = F.layer_norm(h.transpose(1, 2), (h.shape[1],), gammas[i], betas[i], 1e-5).transpose(1, 2)
-        elif i == 0:
-            h = F.group_norm(h, h.shape[1], gammas[0], betas[0], 1e-5)
-        h = F.gelu(h)
-    return h
-
-
-class _FrontendNativeFn(torch.autograd.Function):
-    """LayerNorm-mode frontend with the native backward kernels (training forward keeps a tape of activations)."""
-
-    @staticmethod
-    def forward(ctx, x, packed_holder, *params):
-        conv_w, gammas, betas = params[:7], params[7:14], params[14:21]
-        y, tape = ops.conv_frontend_train(x, conv_w, list(gammas), list(betas), packed=packed_holder())
-        ctx.save_for_backward(x, *params)
-        ctx.tape = tape
-        return y.transpose(1, 2)
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        x, *params = ctx.saved_tensors
-        conv_w, gammas, betas = params[:7], params[7:14], params[14:21]
-        dw, dg, db = ops.conv_frontend_backward(x, conv_w, list(gammas), list(betas), ctx.tape, grad_out.transpose(1, 2))
-        ctx.tape = None
-        grads = [*dw, *dg, *db]
-        need = ctx.needs_input_grad[2:]
-        # the waveform gradient is not produced (nothing upstream of the waveform is trainable in the reference)
-        return (None, None, *[g if n else None for g, n in zip(grads, need)])
-
-
 class _FrontendFn(torch.autograd.Function):
-    """Fallback used for GroupNorm mode (wavlm-base): gradients by recomputation with stock torch ops."""
+    """Training forward (keeps a tape) + native backward, both norm modes."""
 
     @staticmethod
-    def forward(ctx, x, norm_mode, n_norm, packed_holder, *params):
-        conv_w = params[:7]
-        gammas, betas = params[7:7 + n_norm], params[7 + n_norm:7 + 2 * n_norm]
-        y = ops.conv_frontend(x, conv_w, list(gammas), list(betas), norm_mode, out_dtype=torch.float32,
-                              packed=packed_holder())
+    def forward(ctx, x, module, norm_mode, n_norm, *params):
+        conv_w, gammas, betas = params[:7], params[7:7 + n_norm], params[7 + n_norm:7 + 2 * n_norm]
+        y, tape = ops.conv_frontend_train(x, conv_w, list(gammas), list(betas), norm_mode, packed=module._packed_weights())
         ctx.save_for_backward(x, *params)
-        ctx.norm_mode, ctx.n_norm = norm_mode, n_norm
+        ctx.tape, ctx.module, ctx.norm_mode, ctx.n_norm = tape, module, norm_mode, n_norm
         return y.transpose(1, 2)
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.tape is None:
+            raise RuntimeError("B200FeatureEncoder: the tape of this forward was freed by its first backward "
+                               "(retain_graph / a second backward through the conv frontend is not supported)")
         x, *params = ctx.saved_tensors
         n_norm = ctx.n_norm
-        need = [i for i, g in enumerate(ctx.needs_input_grad[4:]) if g]
-        with torch.enable_grad():
-            ps = [p.detach().requires_grad_(i in need) for i, p in enumerate(params)]
-            xin = x.detach().requires_grad_(ctx.needs_input_grad[0])
-            y = _torch_stack(xin, ps[:7], ps[7:7 + n_norm], ps[7 + n_norm:], ctx.norm_mode)
-            wrt = ([xin] if ctx.needs_input_grad[0] else []) + [ps[i] for i in need]
-            grads = torch.autograd.grad(y, wrt, grad_out, allow_unused=True)
-        grads = list(grads)
-        gx = grads.pop(0) if ctx.needs_input_grad[0] else None
-        out: List[Optional[torch.Tensor]] = [None] * len(params)
-        for i, g in zip(need, grads):
-            out[i] = g
-        return (gx, None, None, None, *out)
+        conv_w, gammas, betas = params[:7], params[7:7 + n_norm], params[7 + n_norm:7 + 2 * n_norm]
+        need = ctx.needs_input_grad[4:]
+        need_w, need_g, need_b = need[:7], need[7:7 + n_norm], need[7 + n_norm:7 + 2 * n_norm]
+        need_aff = [g or b for g, b in zip(need_g, need_b)]
+        lowest = min([i for i, v in enumerate(need_w) if v] + [i for i, v in enumerate(need_aff) if v], default=7)
+        dw, dg, db = ops.conv_frontend_backward(x, conv_w, list(gammas), list(betas), ctx.tape, grad_out.transpose(1, 2),
+                                                ctx.norm_mode, dgrad_packs=ctx.module._dgrad_packs(lowest),
+                                                need_w=need_w, need_affine=need_aff)
+        ctx.tape = None
+        grads = [*dw, *[g if n else None for g, n in zip(dg, need_g)], *[b if n else None for b, n in zip(db, need_b)]]
+        return (None, None, None, None, *grads)
 
 
 class B200FeatureEncoder(WavLMFeatureEncoder):
-    """``WavLMFeatureEncoder`` with the sm_100a forward.  Build one with ``B200FeatureEncoder(config)`` or convert an
-    existing HF module in place with ``B200FeatureEncoder.convert(module)`` (keeps its parameters)."""
+    """``WavLMFeatureEncoder`` with the sm_100a forward and backward.  Build one with ``B200FeatureEncoder(config)`` or
+    convert an existing HF module in place with ``B200FeatureEncoder.convert(module)`` (keeps its parameters)."""
 
     out_dtype = torch.float32
 
@@ -107,14 +74,18 @@ class B200FeatureEncoder(WavLMFeatureEncoder):
         if any(l.conv.bias is not None for l in module.conv_layers):
             raise ValueError("conv_bias=True is not supported (WavLM uses bias-free convolutions)")
         module.__class__ = cls
-        module._packed, module._packed_key = None, None
+        module._reset_packs()
         return module
 
     def __init__(self, config):
         super().__init__(config)
-        self._packed, self._packed_key = None, None
+        self._reset_packs()
 
     # -- helpers ---------------------------------------------------------------------------------------------------
+    def _reset_packs(self) -> None:
+        self._packed, self._packed_key = None, None
+        self._dpacks, self._dpacks_key = None, None
+
     @property
     def norm_mode(self) -> str:
         return "layer" if hasattr(self.conv_layers[1], "layer_norm") else "group"
@@ -126,27 +97,42 @@ class B200FeatureEncoder(WavLMFeatureEncoder):
         betas = [self.conv_layers[i].layer_norm.bias for i in range(n_norm)]
         return conv_w, gammas, betas, n_norm
 
-    def _packed_weights(self):
-        """bf16 [512, k*512] copies of conv weights 1..6, re-packed only when a weight changed (version counter)."""
+    def _weights_key(self):
+        """Changes whenever a conv weight of layers 1..6 may have changed: torch-side in-place writes bump ``_version``;
+        the raw-pointer writers (fused optimizer / EMA kernels) bump ``ops.param_generation()``."""
         ws = [l.conv.weight for l in self.conv_layers[1:]]
-        key = tuple((w.data_ptr(), w._version) for w in ws)
+        return (ops.param_generation(), tuple((w.data_ptr(), w._version) for w in ws))
+
+    def _packed_weights(self):
+        """bf16 [512, k*512] copies of conv weights 1..6 (forward operands), re-packed when a weight changed."""
+        key = self._weights_key()
         if getattr(self, "_packed_key", None) != key:
             with torch.no_grad():
-                self._packed = [ops.pack_conv_weight(w) for w in ws]
+                self._packed = [ops.pack_conv_weight(l.conv.weight) for l in self.conv_layers[1:]]
             self._packed_key = key
         return self._packed
+
+    def _dgrad_packs(self, lowest: int = 0):
+        """Data-gradient operands of layers 1..6 (same cache key); layers at or below ``lowest`` never propagate a data
+        gradient and get ``None``."""
+        key = (self._weights_key(), lowest)
+        if getattr(self, "_dpacks_key", None) != key:
+            with torch.no_grad():
+                self._dpacks = [ops.pack_conv_weight_dgrad(l.conv.weight) if i > lowest else None
+                                for i, l in enumerate(self.conv_layers) if i >= 1]
+            self._dpacks_key = key
+        return self._dpacks
 
     def forward(self, input_values: torch.Tensor) -> torch.Tensor:
         conv_w, gammas, betas, n_norm = self._params()
         x = input_values
         if x.dim() == 3:
             x = x.squeeze(1)
-        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(
-            p.requires_grad for p in (*conv_w, *gammas, *betas)))
-        if needs_grad:
-            if self.norm_mode == "layer" and not x.requires_grad:
-                return _FrontendNativeFn.apply(x.float(), self._packed_weights, *conv_w, *gammas, *betas)
-            return _FrontendFn.apply(x.float(), self.norm_mode, n_norm, self._packed_weights, *conv_w, *gammas, *betas)
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("B200FeatureEncoder does not compute the waveform gradient (the reference never "
+                                      "trains anything upstream of the waveform); detach the input")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in (*conv_w, *gammas, *betas)):
+            return _FrontendFn.apply(x.float(), self, self.norm_mode, n_norm, *conv_w, *gammas, *betas)
         y = ops.conv_frontend(x, conv_w, gammas, betas, self.norm_mode, out_dtype=self.out_dtype,
                               packed=self._packed_weights())
         return y.transpose(1, 2)

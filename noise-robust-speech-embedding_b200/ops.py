@@ -20,6 +20,20 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, NORM_GROUP, NORM_LAYER, FrontendBwdWei
 CONV_KERNEL = (10, 3, 3, 3, 3, 2, 2)
 CONV_STRIDE = (5, 2, 2, 2, 2, 2, 2)
 
+# Parameter generation.  The multi-tensor kernels (EMA, fused AdamW) write parameters through raw device pointers,
+# which does NOT bump ``tensor._version``; every such writer bumps this counter instead, and everything derived from
+# parameter values (the bf16 weight packs of the conv frontend) is keyed on it.
+_param_generation = 0
+
+
+def param_generation() -> int:
+    return _param_generation
+
+
+def bump_param_generation() -> None:
+    global _param_generation
+    _param_generation += 1
+
 
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -90,32 +104,59 @@ def mix_normalize(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db_table: S
     return (c if peak_norm else None), n, st
 
 
-@torch.library.custom_op("nrse::mix_normalize_retry", mutates_args=("clean_out", "noisy_out", "status"))
+@torch.library.custom_op("nrse::mix_normalize_retry", mutates_args=("clean_out", "noisy_out", "status", "snr_used"))
 def _mix_retry_op(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db: Sequence[float], mode: int,
-                  clean_out: Tensor, noisy_out: Tensor, status: Tensor, noise_row_shift: int) -> None:
+                  clean_out: Tensor, noisy_out: Tensor, status: Tensor, snr_used: Tensor, noise_row_shift: int) -> None:
     _need_cuda(clean, noise, snr_idx, noisy_out, status)
     B, L = clean.shape
     table = (C.c_double * len(snr_db))(*[float(v) for v in snr_db])
     check(_lib.load().nrse_mix_normalize_retry_f32(
         _ptr(clean), _ptr(noise), _ptr(snr_idx), table, len(snr_db), _ptr(clean_out) if mode == 1 else None,
-        _ptr(noisy_out), _ptr(status), B, L, noise.shape[1], int(mode), int(noise_row_shift), _stream()),
-        "nrse_mix_normalize_retry_f32")
+        _ptr(noisy_out), _ptr(status), _ptr(snr_used) if snr_used.numel() else None, B, L, noise.shape[1], int(mode),
+        int(noise_row_shift), _stream()), "nrse_mix_normalize_retry_f32")
 
 
 def mix_normalize_retry_(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db_table: Sequence[float],
                          clean_out: Optional[Tensor], noisy_out: Tensor, status: Tensor, noise_row_shift: int,
-                         peak_norm: bool = True) -> None:
-    """In place: redo ``mix_normalize`` for the rows with ``status != 0`` using the noise of row
-    ``(b + noise_row_shift) % B`` -- the reference's "try another noise file" (ref:src/data/noisy_speech_dataset.py:
-    58-84) decided and executed on the device; rows that were fine are not touched and cost nothing."""
+                         peak_norm: bool = True, snr_idx_used: Optional[Tensor] = None) -> None:
+    """In place: redo ``mix_normalize`` for the rows with ``status != 0`` using the noise AND the SNR index of row
+    ``(b + noise_row_shift) % B`` -- the reference's next attempt draws another noise file and another SNR
+    (ref:src/data/noisy_speech_dataset.py:58-84) -- decided and executed on the device; rows that were fine are not
+    touched and cost nothing.  ``snr_idx`` is never modified; ``snr_idx_used`` (int32 [B], seeded by the caller with a
+    copy of ``snr_idx``) receives the index every re-done row was finally mixed at."""
     if not (clean.is_contiguous() and noise.is_contiguous() and noisy_out.is_contiguous() and status.is_contiguous()):
         raise NrseError("mix_normalize_retry_ expects contiguous tensors (it works in place)")
     if clean.dtype != torch.float32 or noise.dtype != torch.float32 or status.dtype != torch.int32:
         raise NrseError("mix_normalize_retry_ expects fp32 waveforms and an int32 status")
+    if snr_idx_used is not None and (snr_idx_used.dtype != torch.int32 or not snr_idx_used.is_contiguous()
+                                     or snr_idx_used.numel() != clean.shape[0]):
+        raise NrseError("mix_normalize_retry_: snr_idx_used must be a contiguous int32 [B] tensor")
     snr_idx = snr_idx.to(device=clean.device, dtype=torch.int32).contiguous()
     co = clean_out if peak_norm else clean.new_empty(0)
+    su = snr_idx_used if snr_idx_used is not None else status.new_empty(0)
     _mix_retry_op(clean, noise, snr_idx, [float(v) for v in snr_db_table], 1 if peak_norm else 0, co, noisy_out, status,
-                  int(noise_row_shift))
+                  su, int(noise_row_shift))
+
+
+@torch.library.custom_op("nrse::mix_substitute_rows", mutates_args=("clean_out", "noisy_out", "snr_used"))
+def _mix_substitute_op(clean_out: Tensor, noisy_out: Tensor, status: Tensor, snr_used: Tensor) -> None:
+    _need_cuda(noisy_out, status)
+    B, L = noisy_out.shape
+    check(_lib.load().nrse_mix_substitute_rows_f32(
+        _ptr(clean_out) if clean_out.numel() else None, _ptr(noisy_out), _ptr(status),
+        _ptr(snr_used) if snr_used.numel() else None, B, L, _stream()), "nrse_mix_substitute_rows_f32")
+
+
+def mix_substitute_rows_(clean_out: Optional[Tensor], noisy_out: Tensor, status: Tensor,
+                         snr_idx_used: Optional[Tensor] = None) -> None:
+    """In place, no host sync: rows whose ``status`` is still non-zero after the retries take over the outputs (and the
+    SNR index) of the nearest following good row -- the reference moves on to the next item instead of emitting an
+    unusable one (ref:src/data/noisy_speech_dataset.py:60-66).  On a healthy batch the launch moves no data."""
+    if not (noisy_out.is_contiguous() and status.is_contiguous() and (clean_out is None or clean_out.is_contiguous())):
+        raise NrseError("mix_substitute_rows_ expects contiguous tensors (it works in place)")
+    empty = status.new_empty(0)
+    _mix_substitute_op(clean_out if clean_out is not None else noisy_out.new_empty(0), noisy_out, status,
+                       snr_idx_used if snr_idx_used is not None else empty)
 
 
 def mix_status_name(code: int) -> str:
@@ -199,6 +240,7 @@ class EmaPlan:
         # `(1 - self.ema_decay) * online_param.data` (ref:src/models/byol.py:67-68)
         check(lib.nrse_ema_chunks_f32(_ptr(self._ct), _ptr(self._co), _ptr(self._cn), self.n_chunks,
                                       float(decay), float(1 - decay), _stream()), "nrse_ema_chunks_f32")
+        bump_param_generation()  # targets were written behind autograd's back (no _version bump)
 
 
 def ema_update_(online: Sequence[Tensor], target: Sequence[Tensor], decay: float) -> None:
@@ -306,29 +348,31 @@ class OptimChunkTable:
             float(betas[1]), float(eps), float(weight_decay), int(step), float(max_grad_norm), float(ema_decay),
             _ptr(partials), 0 if partials is None else partials.numel(), _ptr(norm_out), _stream()),
             "nrse_clip_adamw_ema_chunks_f32")
+        bump_param_generation()  # parameters (and EMA twins) were written through raw pointers
 
 
 # --------------------------------------------------------------------------------------------------------------
 # BYOL loss
 # --------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("nrse::byol_loss_fwd", mutates_args=())
-def _byol_loss_fwd(p: Tensor, z: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+def _byol_loss_fwd(p: Tensor, z: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     _need_cuda(p, z)
     lib = _lib.load()
     B, D = p.shape
     loss = torch.empty((), dtype=torch.float32, device=p.device)
     saved = torch.empty(B, 4, dtype=torch.float32, device=p.device)
     row_sim = torch.empty(B, dtype=torch.float32, device=p.device)
-    check(lib.nrse_byol_loss_fwd(_ptr(p), _ptr(z), _ptr(loss), _ptr(saved), _ptr(row_sim), B, D, _dtype_code(p),
-                                 _stream()), "nrse_byol_loss_fwd")
-    return loss, saved, row_sim
+    flags = torch.empty((), dtype=torch.int32, device=p.device)
+    check(lib.nrse_byol_loss_fwd(_ptr(p), _ptr(z), _ptr(loss), _ptr(saved), _ptr(row_sim), _ptr(flags), B, D,
+                                 _dtype_code(p), _stream()), "nrse_byol_loss_fwd")
+    return loss, saved, row_sim, flags
 
 
 @_byol_loss_fwd.register_fake
 def _(p, z):
     B = p.shape[0]
     return (p.new_empty((), dtype=torch.float32), p.new_empty(B, 4, dtype=torch.float32),
-            p.new_empty(B, dtype=torch.float32))
+            p.new_empty(B, dtype=torch.float32), p.new_empty((), dtype=torch.int32))
 
 
 @torch.library.custom_op("nrse::byol_loss_bwd", mutates_args=())
@@ -352,7 +396,7 @@ def _loss_setup(ctx, inputs, output):
     ctx.save_for_backward(p, z, output[1])
 
 
-def _loss_backward(ctx, g_loss, g_saved, g_rowsim):
+def _loss_backward(ctx, g_loss, g_saved, g_rowsim, g_flags):
     p, z, saved = ctx.saved_tensors
     return _byol_loss_bwd(p, z, saved, g_loss), None  # no gradient to the target branch (byol.py:94-96)
 
@@ -375,10 +419,66 @@ def byol_loss(online_pred: Tensor, target_proj: Tensor) -> Tensor:
     return _byol_loss_fwd(p, z)[0]
 
 
+def byol_loss_with_flags(online_pred: Tensor, target_proj: Tensor) -> Tuple[Tensor, Tensor]:
+    """(loss, flags): ``flags`` is a 0-d int32 device tensor written by the same launch -- bit 0 / 1: NaN in
+    ``online_pred`` / ``target_proj`` before normalisation, bit 2 / 3: NaN after it (the two diagnostics of
+    ref:src/models/byol.py:109-122).  Reading it is the caller's (only) host synchronisation."""
+    p, z = _loss_inputs(online_pred, target_proj)
+    out = _byol_loss_fwd(p, z)
+    return out[0], out[3]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Fused tensor health check (ref:src/utils/debugging_utils.py:4-30)
+# --------------------------------------------------------------------------------------------------------------
+CHECK_MAX_TENSORS = 8
+CHECK_NAN, CHECK_INF, CHECK_SMALL, CHECK_LARGE = 1, 2, 4, 8
+
+
+def check_tensors(tensors: Sequence[Tensor], max_threshold: float = 1e6, min_threshold: float = 1e-6) -> Tensor:
+    """One launch over up to 8 tensors.  Returns a device uint8 tensor [n, 64]: one ``nrse_tensor_check`` record per
+    tensor (decode with ``decode_tensor_checks`` after copying it to the host -- that copy is the only synchronisation)."""
+    if not 1 <= len(tensors) <= CHECK_MAX_TENSORS:
+        raise NrseError(f"check_tensors takes 1..{CHECK_MAX_TENSORS} tensors")
+    ts = [t.detach().contiguous().float() for t in tensors]
+    _need_cuda(*ts)
+    n = len(ts)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    numel = (C.c_int64 * n)(*[t.numel() for t in ts])
+    out = torch.empty(n, 64, dtype=torch.uint8, device=ts[0].device)
+    check(_lib.load().nrse_check_tensors_f32(ptrs, numel, n, float(max_threshold), float(min_threshold), _ptr(out),
+                                             _stream()), "nrse_check_tensors_f32")
+    return out
+
+
+def decode_tensor_checks(records_host: Tensor) -> List[dict]:
+    """Host copy of ``check_tensors``' output -> list of dicts (flags, abs_max, max, min, abs_sum, mean, std)."""
+    raw = bytes(records_host.contiguous().cpu().numpy().tobytes())
+    out = []
+    for i in range(len(raw) // 64):
+        r = _lib.TensorCheck.from_buffer_copy(raw[64 * i:64 * (i + 1)])
+        n = max(int(r.numel), 1)
+        mean = r.sum / n
+        var = (r.sumsq - r.sum * r.sum / n) / (n - 1) if n > 1 else float("nan")  # torch.std: unbiased
+        out.append({"flags": int(r.flags), "abs_max": float(r.abs_max), "max": float(r.max), "min": float(r.min),
+                    "abs_sum": float(r.abs_sum), "mean": mean, "std": max(var, 0.0) ** 0.5 if var == var else var,
+                    "numel": int(r.numel)})
+    return out
+
+
 def cosine_rows(a: Tensor, b: Tensor) -> Tensor:
     """Per-row clamped cosine similarity [B] (what ref:evaluate_byol.py:51-55 computes with F.normalize + sum)."""
     p, z = _loss_inputs(a.detach(), b)
     return _byol_loss_fwd(p, z)[2]
+
+
+def cosine_rows_plain(a: Tensor, b: Tensor) -> Tensor:
+    """Per-row cosine similarity as ref:evaluate_byol.py:51-55 writes it -- ``F.normalize(dim=1)`` on both, row dot
+    product, NO clamp: the loss kernel's saved unclamped similarity, same single launch.  Differences to the reference
+    expression are confined to degenerate rows: the kernel's +1e-10 offset is below half an ulp of any |x| > 2e-3, and
+    its norm floor is 1e-10 where ``F.normalize`` defaults to 1e-12 (only rows whose norm is below 1e-10 can tell)."""
+    p, z = _loss_inputs(a.detach().float(), b.float())
+    return _byol_loss_fwd(p, z)[1][:, 2]
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -638,101 +738,141 @@ def _frontend_params(w0: Tensor, packed: Sequence[Tensor], gammas: Sequence[Tens
     prm = FrontendParams()
     prm.w0 = w0.data_ptr()
     for i in range(6):
-        prm.w_packed[i] = packed[i].data_ptr()
+        prm.w_packed[i] = packed[i].data_ptr() if packed is not None else None
     for i in range(7):
-        prm.gamma[i] = gammas[i].data_ptr()
-        prm.beta[i] = betas[i].data_ptr()
+        prm.gamma[i] = gammas[i].data_ptr() if i < len(gammas) else None
+        prm.beta[i] = betas[i].data_ptr() if i < len(betas) else None
     return prm
 
 
+def _norm_code(norm_mode: str) -> int:
+    return {"layer": NORM_LAYER, "group": NORM_GROUP}[norm_mode]
+
+
 def conv_frontend_train(x: Tensor, conv_weights: Sequence[Tensor], gammas: Sequence[Tensor], betas: Sequence[Tensor],
-                        packed: Optional[Sequence[Tensor]] = None) -> Tuple[Tensor, Tensor]:
-    """Training forward (LayerNorm mode): returns (features [B, T, 512] fp32 view, tape).  The tape (uint8 tensor)
-    holds the activations, xhat and 1/std the backward needs; it belongs to the caller (autograd context)."""
+                        norm_mode: str = "layer", packed: Optional[Sequence[Tensor]] = None) -> Tuple[Tensor, Tensor]:
+    """Training forward, both norm modes: returns (features [B, T, 512] fp32 view, tape).  The tape (uint8 tensor) holds
+    the activations, xhat and the statistics the backward needs; it belongs to the caller (autograd context).
+    ``gammas`` / ``betas``: 7 tensors in LayerNorm mode, 1 (layer 0's GroupNorm affine) in GroupNorm mode."""
     _need_cuda(x)
     lib = _lib.load()
+    mode = _norm_code(norm_mode)
+    n_norm = 7 if mode == NORM_LAYER else 1
     x = x.contiguous().float()
     B, L = x.shape
     T, P = frontend_geometry(L)
     w0 = conv_weights[0].detach().reshape(512, 10).contiguous().float()
     if packed is None:
         packed = [pack_conv_weight(w) for w in conv_weights[1:]]
-    g = [t.detach().contiguous().float() for t in gammas]
-    b = [t.detach().contiguous().float() for t in betas]
+    g = [gammas[i].detach().contiguous().float() for i in range(n_norm)]
+    b = [betas[i].detach().contiguous().float() for i in range(n_norm)]
     nbytes = lib.nrse_conv_frontend_tape_bytes(B, L)
     tape = torch.empty(nbytes + 1024, dtype=torch.uint8, device=x.device)
     tp, tl = _aligned(tape)
     y = torch.empty(B, P[6], 512, dtype=torch.float32, device=x.device)
     prm = _frontend_params(w0, packed, g, b)
-    check(lib.nrse_conv_frontend_fwd_train(_ptr(x), C.byref(prm), _ptr(y), DTYPE_F32, C.c_void_p(tp), tl, B, L, _stream()),
-          "nrse_conv_frontend_fwd_train")
+    check(lib.nrse_conv_frontend_fwd_train(_ptr(x), C.byref(prm), mode, _ptr(y), DTYPE_F32, C.c_void_p(tp), tl, B, L,
+                                           _stream()), "nrse_conv_frontend_fwd_train")
     return y[:, :T[6], :], tape
 
 
 def conv_frontend_backward(x: Tensor, conv_weights: Sequence[Tensor], gammas: Sequence[Tensor], betas: Sequence[Tensor],
-                           tape: Tensor, grad_features: Tensor,
-                           dgrad_packs: Optional[Sequence[Tuple[Tensor, Tensor]]] = None):
+                           tape: Tensor, grad_features: Tensor, norm_mode: str = "layer",
+                           dgrad_packs: Optional[Sequence[Tuple[Tensor, Tensor]]] = None,
+                           need_w: Optional[Sequence[bool]] = None, need_affine: Optional[Sequence[bool]] = None):
     """Backward of ``conv_frontend_train``.  grad_features [B, T, 512] (any strides).  Returns
-    (dw: 7 tensors in checkpoint layout [512,1,10] / [512,512,k], dgamma: 7 x [512], dbeta: 7 x [512]), all fp32."""
+    (dw: 7 tensors in checkpoint layout [512,1,10] / [512,512,k], dgamma: n_norm x [512], dbeta: n_norm x [512]), all
+    fp32 views of ONE zero-initialised buffer; entries that were not asked for (``need_w[i]`` / ``need_affine[i]``
+    False: frozen parameters, ref:src/models/emotion.py:114-129) are ``None`` and cost nothing -- the kernels stop at
+    the lowest layer that wants a gradient and skip the weight-gradient GEMM of every layer that does not."""
     lib = _lib.load()
+    mode = _norm_code(norm_mode)
+    n_norm = 7 if mode == NORM_LAYER else 1
+    need_w = [True] * 7 if need_w is None else [bool(v) for v in need_w]
+    need_affine = [True] * n_norm if need_affine is None else [bool(v) for v in need_affine]
     x = x.contiguous().float()
     B, L = x.shape
     T, P = frontend_geometry(L)
     dev = x.device
-    dy = torch.zeros(B, P[6], 512, dtype=torch.float32, device=dev)
-    dy[:, :T[6]] = grad_features
+    if tape is None:
+        raise NrseError("conv_frontend_backward: the tape of this forward has already been consumed")
+    if tuple(grad_features.shape) != (B, T[6], 512):
+        raise NrseError(f"conv_frontend_backward: grad_features must be [{B}, {T[6]}, 512]")
+    dy = grad_features.contiguous().float()
+    if not any(need_w) and not any(need_affine):
+        return [None] * 7, [None] * n_norm, [None] * n_norm
+    lowest = min([i for i, v in enumerate(need_w) if v] + [i for i, v in enumerate(need_affine) if v])
     w0 = conv_weights[0].detach().reshape(512, 10).contiguous().float()
-    g = [t.detach().contiguous().float() for t in gammas]
-    b = [t.detach().contiguous().float() for t in betas]
-    if dgrad_packs is None:
-        dgrad_packs = [pack_conv_weight_dgrad(w) for w in conv_weights[1:]]
-    prm = FrontendParams()
-    prm.w0 = w0.data_ptr()
-    for i in range(7):
-        prm.gamma[i] = g[i].data_ptr()
-        prm.beta[i] = b[i].data_ptr()
+    g = [gammas[i].detach().contiguous().float() for i in range(n_norm)]
+    b = [betas[i].detach().contiguous().float() for i in range(n_norm)]
+    if dgrad_packs is None:  # only the layers above the lowest one propagate a data gradient
+        dgrad_packs = [pack_conv_weight_dgrad(conv_weights[i]) if i > lowest else None for i in range(1, 7)]
+    prm = _frontend_params(w0, None, g, b)
     wb = FrontendBwdWeights()
     for i in range(6):
-        wb.wt_even[i] = dgrad_packs[i][0].data_ptr()
-        wb.wt_odd[i] = dgrad_packs[i][1].data_ptr()
-    dw0 = torch.empty(512, 10, dtype=torch.float32, device=dev)
-    dwp = [torch.empty(512, CONV_KERNEL[i] * 512, dtype=torch.float32, device=dev) for i in range(1, 7)]
-    dgam = [torch.empty(512, dtype=torch.float32, device=dev) for _ in range(7)]
-    dbet = [torch.empty(512, dtype=torch.float32, device=dev) for _ in range(7)]
-    gr = FrontendGrads()
-    gr.dw0 = dw0.data_ptr()
-    for i in range(6):
-        gr.dw[i] = dwp[i].data_ptr()
+        pk = dgrad_packs[i]
+        wb.wt_even[i] = pk[0].data_ptr() if pk is not None else None
+        wb.wt_odd[i] = pk[1].data_ptr() if pk is not None else None
+    sizes_w = [512 * 10] + [512 * 512 * CONV_KERNEL[i] for i in range(1, 7)]
+    total = sum(sz for sz, nd in zip(sizes_w, need_w) if nd) + 1024 * sum(need_affine)
+    flat = torch.zeros(total, dtype=torch.float32, device=dev)  # the kernels accumulate: one memset for everything
+    off = 0
+    dw: List[Optional[Tensor]] = []
     for i in range(7):
-        gr.dgamma[i] = dgam[i].data_ptr()
-        gr.dbeta[i] = dbet[i].data_ptr()
+        if need_w[i]:
+            shape = (512, 1, 10) if i == 0 else (512, 512, CONV_KERNEL[i])
+            dw.append(flat[off:off + sizes_w[i]].view(shape))
+            off += sizes_w[i]
+        else:
+            dw.append(None)
+    dgam: List[Optional[Tensor]] = []
+    dbet: List[Optional[Tensor]] = []
+    for i in range(n_norm):
+        if need_affine[i]:
+            dgam.append(flat[off:off + 512])
+            dbet.append(flat[off + 512:off + 1024])
+            off += 1024
+        else:
+            dgam.append(None)
+            dbet.append(None)
+    gr = FrontendGrads()
+    gr.dw0 = dw[0].data_ptr() if dw[0] is not None else None
+    for i in range(6):
+        gr.dw[i] = dw[i + 1].data_ptr() if dw[i + 1] is not None else None
+    for i in range(7):
+        gr.dgamma[i] = dgam[i].data_ptr() if i < n_norm and dgam[i] is not None else None
+        gr.dbeta[i] = dbet[i].data_ptr() if i < n_norm and dbet[i] is not None else None
     nbytes = lib.nrse_conv_frontend_bwd_workspace_bytes(B, L)
     ws = _workspace(nbytes, dev)
     wp, wl = _aligned(ws)
     tp, _ = _aligned(tape)
-    check(lib.nrse_conv_frontend_bwd(_ptr(x), C.byref(prm), C.byref(wb), C.c_void_p(tp), _ptr(dy), C.byref(gr),
-                                     C.c_void_p(wp), wl, B, L, _stream()), "nrse_conv_frontend_bwd")
-    dw = [dw0.view(512, 1, 10)] + [d.view(512, CONV_KERNEL[i + 1], 512).permute(0, 2, 1).contiguous()
-                                    for i, d in enumerate(dwp)]
+    check(lib.nrse_conv_frontend_bwd(_ptr(x), C.byref(prm), C.byref(wb), mode, C.c_void_p(tp), _ptr(dy), T[6],
+                                     C.byref(gr), C.c_void_p(wp), wl, B, L, _stream()), "nrse_conv_frontend_bwd")
     return dw, dgam, dbet
 
 
 # per-kernel hooks (parity tests)
-def ln_gelu_bwd(dout: Tensor, xhat: Tensor, rstd: Tensor, gamma: Tensor, beta: Tensor, P: int, T: int):
+def ln_gelu_bwd(dout: Tensor, xhat: Tensor, rstd: Optional[Tensor], gamma: Optional[Tensor], beta: Optional[Tensor],
+                P: int, T: int, dout_pitch: Optional[int] = None):
+    """dOut -> dZ.  ``gamma is None``: the no-norm form (GroupNorm-mode layers 1-6), ``xhat`` = the pre-GELU activation."""
     lib = _lib.load()
     rows = xhat.shape[0]
     dz = torch.empty(rows, 512, dtype=torch.bfloat16, device=xhat.device)
-    dg = torch.zeros(512, dtype=torch.float32, device=xhat.device)
-    db = torch.zeros(512, dtype=torch.float32, device=xhat.device)
-    check(lib.nrse_ln_gelu_bwd(_ptr(dout.contiguous()), _dtype_code(dout), _ptr(xhat), _ptr(rstd), _ptr(gamma), _ptr(beta),
-                               _ptr(dz), _ptr(dg), _ptr(db), rows, P, T, _stream()), "nrse_ln_gelu_bwd")
+    dg = torch.zeros(512, dtype=torch.float32, device=xhat.device) if gamma is not None else None
+    db = torch.zeros(512, dtype=torch.float32, device=xhat.device) if gamma is not None else None
+    check(lib.nrse_ln_gelu_bwd(_ptr(dout.contiguous()), _dtype_code(dout), int(dout_pitch if dout_pitch is not None else P),
+                               _ptr(xhat), _ptr(rstd), _ptr(gamma), _ptr(beta), _ptr(dz), _ptr(dg), _ptr(db), rows, P, T,
+                               _stream()), "nrse_ln_gelu_bwd")
     return dz, dg, db
 
 
-def conv_layer_wgrad(dz: Tensor, act_prev: Tensor, k: int) -> Tensor:
+def conv_layer_wgrad(dz: Tensor, act_prev: Tensor, k: int, ckpt_layout: bool = False) -> Tensor:
+    """dW = dZ^T A: fp32 [512, k*512] in the packed K order, or [512, 512, k] (checkpoint layout)."""
     lib = _lib.load()
-    dw = torch.zeros(512, k * 512, dtype=torch.float32, device=dz.device)
-    check(lib.nrse_conv_layer_wgrad(_ptr(dz), _ptr(act_prev), dz.shape[0], k, _ptr(dw), _stream()), "nrse_conv_layer_wgrad")
+    shape = (512, 512, k) if ckpt_layout else (512, k * 512)
+    dw = torch.zeros(shape, dtype=torch.float32, device=dz.device)
+    check(lib.nrse_conv_layer_wgrad(_ptr(dz), _ptr(act_prev), dz.shape[0], k, _ptr(dw), 1 if ckpt_layout else 0,
+                                    _stream()), "nrse_conv_layer_wgrad")
     return dw
 
 

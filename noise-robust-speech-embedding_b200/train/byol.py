@@ -4,8 +4,9 @@
 What is different underneath:
 * batches arrive already mixed/normalised on the device (``MixedBatchLoader``); ``.to(device)`` is a no-op there and
   the reference's CPU-tensor batches still work;
-* ``check_audio_tensor`` (ref:src/utils/debugging_utils.py:4-30, >= 4 host syncs per tensor, called 4x per step) is
-  evaluated as ONE fused flag vector per step and read back once -- and only every ``check_interval`` steps;
+* ``check_audio_tensor`` (ref:src/utils/debugging_utils.py:4-30, >= 4 host syncs per tensor, called 4x per step) is ONE
+  fused kernel launch per group of tensors (``ops.check_tensors``: one status record per tensor) and ONE host read per
+  checked step -- and only every ``check_interval`` steps;
 * ``byol_loss`` and the EMA update are single kernel launches (ops.byol_loss, ops.EmaPlan);
 * the loss is accumulated on the device; ``.item()`` is called once per epoch, not once per step;
 * the per-item ``.item()`` loop of ``evaluate_embedding_similarity`` is a per-SNR masked mean on the device.
@@ -17,40 +18,72 @@ from typing import Dict, Iterable, Optional, Tuple
 import torch
 
 from .. import ops
-from ..models.byol import BYOLSpeechModel, byol_loss
+from ..models.byol import BYOLSpeechModel, byol_loss, log_loss_flags
 from ..utils.logging_utils import logger
 from .optim import FusedAdamWEma
 
 
-def _flags(t: torch.Tensor, max_threshold: float, min_threshold: float) -> torch.Tensor:
-    a = t.detach().abs()
-    return torch.stack([torch.isnan(t).any(), torch.isinf(t).any(), a.sum() < min_threshold, a.max() > max_threshold])
+_CHECK_MESSAGES = ((ops.CHECK_NAN, "NaN values"), (ops.CHECK_INF, "Inf values"), (ops.CHECK_SMALL, "very small values"),
+                   (ops.CHECK_LARGE, "very large values"))
+
+
+def _report_checks(infos, names, config) -> list:
+    """Log lines and verdicts of ref:src/utils/debugging_utils.py:4-30 from decoded check records."""
+    verdicts = []
+    debug = config.get("logging", {}).get("level") == "DEBUG"
+    for info, name in zip(infos, names):
+        bad = next((what for bit, what in _CHECK_MESSAGES if info["flags"] & bit), None)
+        if bad is not None:
+            if bad == "very large values":
+                logger.warning("WARNING: %s contains very large values! Max abs value: %s", name, info["abs_max"])
+            else:
+                logger.warning("WARNING: %s contains %s!", name, bad)
+            verdicts.append(False)
+            continue
+        if debug:
+            logger.debug("Stats for %s: mean=%.4f, std=%.4f, min=%.4f, max=%.4f", name, info["mean"], info["std"],
+                         info["min"], info["max"])
+        verdicts.append(True)
+    return verdicts
+
+
+def check_audio_tensors(named, config, max_threshold: float = 1e6, min_threshold: float = 1e-6) -> list:
+    """``check_audio_tensor`` for up to 8 (tensor, name) pairs at once: ONE kernel launch reads every tensor once and
+    writes one status record per tensor, ONE device-to-host copy brings the records back.  Same verdicts and log lines as
+    the reference (ref:src/utils/debugging_utils.py:4-30), which spends >= 4 passes and >= 4 host synchronisations per
+    tensor, four tensors per step (ref:train_byol.py:52-59)."""
+    records = ops.check_tensors([t for t, _ in named], max_threshold, min_threshold)
+    return _report_checks(ops.decode_tensor_checks(records.cpu()), [n for _, n in named], config)
 
 
 def check_audio_tensor(tensor: torch.Tensor, name: str, config, max_threshold: float = 1e6,
                        min_threshold: float = 1e-6) -> bool:
-    """Same verdicts and log lines as ref:src/utils/debugging_utils.py:4-30, with one host read instead of >= 4."""
-    f = _flags(tensor, max_threshold, min_threshold).tolist()
-    for bad, what in zip(f, ("NaN values", "Inf values", "very small values", "very large values")):
-        if bad:
-            logger.warning("WARNING: %s contains %s!", name, what)
-            return False
-    if config.get("logging", {}).get("level") == "DEBUG":
-        t = tensor.detach().float()
-        stats = torch.stack([t.mean(), t.std(), t.min(), t.max()]).tolist()
-        logger.debug("Stats for %s: mean=%.4f, std=%.4f, min=%.4f, max=%.4f", name, *stats)
-    return True
+    """Drop-in for ref:src/utils/debugging_utils.py:4-30: one fused launch, one host read."""
+    return check_audio_tensors([(tensor, name)], config, max_threshold, min_threshold)[0]
 
 
 def byol_step(model: BYOLSpeechModel, clean: torch.Tensor, noisy: torch.Tensor, optimizer, scheduler=None,
-              max_grad_norm: float = 1.0) -> torch.Tensor:
+              max_grad_norm: float = 1.0, check_config=None) -> torch.Tensor:
     """forward -> byol_loss -> zero_grad -> backward -> clip_grad_norm_(1.0) -> optimizer.step -> EMA -> scheduler.step
     (ref:train_byol.py:56-74).  Returns the detached loss (device tensor; no host sync).
 
     With a ``FusedAdamWEma`` optimizer that has the clip and the EMA attached (``FusedAdamWEma.for_byol``) the three
-    tail stages are its two kernel launches; with any other optimizer they run as in the reference."""
+    tail stages are its two kernel launches; with any other optimizer they run as in the reference.
+
+    ``check_config`` (the config dict) switches the reference's diagnostics on for this step (ref:train_byol.py:52-59,
+    ref:src/models/byol.py:109-122): the four ``check_audio_tensor`` verdicts and the two NaN messages of ``byol_loss``,
+    from two fused check launches + the loss kernel's flag word, read back together in ONE host synchronisation."""
+    rec_in = ops.check_tensors([clean, noisy]) if check_config is not None else None
     online_pred, target_proj = model(clean, noisy)
-    loss = byol_loss(online_pred, target_proj)
+    if check_config is not None:
+        rec_out = ops.check_tensors([online_pred, target_proj])
+        loss, flags = ops.byol_loss_with_flags(online_pred, target_proj)
+        packed = torch.cat([rec_in.flatten(), rec_out.flatten(), flags.reshape(1).view(torch.uint8)]).cpu()  # the one sync
+        _report_checks(ops.decode_tensor_checks(packed[:256].view(4, 64)),
+                       ["clean_input_values", "noisy_input_values", "online_pred", "target_proj"], check_config)
+        log_loss_flags(int(packed[256:260].view(torch.int32).item()))
+    else:
+        loss = byol_loss(online_pred, target_proj)
     fused = isinstance(optimizer, FusedAdamWEma)
     optimizer.zero_grad() if fused else optimizer.zero_grad(set_to_none=True)
     loss.backward()
@@ -67,7 +100,9 @@ def byol_step(model: BYOLSpeechModel, clean: torch.Tensor, noisy: torch.Tensor, 
 
 def train_one_epoch(model, dataloader: Iterable, optimizer, scheduler, device, config, check_interval: int = 0) -> float:
     """Average training loss over the epoch (ref:train_byol.py:20-79).  ``check_interval`` > 0 runs the reference's
-    four ``check_audio_tensor`` calls every that many steps (0 = never: no host sync inside the epoch)."""
+    diagnostics -- its four ``check_audio_tensor`` calls and the NaN messages of ``byol_loss`` -- every that many steps
+    at the price of ONE host synchronisation in such a step (the reference runs them every step and pays >= 20);
+    0 = never: no host sync inside the epoch."""
     device = torch.device(device)
     model.train()
     total = torch.zeros((), device=device)
@@ -75,10 +110,8 @@ def train_one_epoch(model, dataloader: Iterable, optimizer, scheduler, device, c
     for step, batch in enumerate(dataloader):
         clean = batch["clean_input_values"].to(device, non_blocking=True)
         noisy = batch["noisy_input_values"].to(device, non_blocking=True)
-        if check_interval and step % check_interval == 0:
-            check_audio_tensor(clean, "clean_input_values", config)
-            check_audio_tensor(noisy, "noisy_input_values", config)
-        total += byol_step(model, clean, noisy, optimizer, scheduler)
+        checked = bool(check_interval) and step % check_interval == 0
+        total += byol_step(model, clean, noisy, optimizer, scheduler, check_config=config if checked else None)
         n += 1
     return float(total.item()) / max(n, 1)
 
@@ -99,7 +132,7 @@ def evaluate_embedding_similarity(model, dataloader: Iterable, device, config) -
         noisy = batch["noisy_input_values"].to(device, non_blocking=True)
         snr = torch.as_tensor(batch["snr"]).to(device)
         ce, ne = inner._pool(encoder(clean)), inner._pool(encoder(noisy))
-        sim = ops.cosine_rows(ce.float(), ne.float()).double()  # F.normalize(dim=1) + row dot, one launch
+        sim = ops.cosine_rows_plain(ce.float(), ne.float()).double()  # F.normalize(dim=1) + row dot (no clamp), one launch
         onehot = (snr[:, None] == snr_t[None, :]).double()
         sums += (onehot * sim[:, None]).sum(0)
         counts += onehot.sum(0)

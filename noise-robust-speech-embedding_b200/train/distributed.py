@@ -40,3 +40,88 @@ def wrap_data_parallel(model: torch.nn.Module, device: torch.device, bucket_cap_
     ids = [device.index] if device.type == "cuda" else None
     return DistributedDataParallel(model, device_ids=ids, broadcast_buffers=False, bucket_cap_mb=bucket_cap_mb,
                                    gradient_as_bucket_view=True, find_unused_parameters=find_unused_parameters)
+
+
+class GradArena:
+    """Gradients of a list of parameter GROUPS in ONE flat fp32 buffer, all-reduced in a few large buckets.
+
+    What ``DistributedDataParallel(gradient_as_bucket_view=True)`` does with hooks, written out so that the step loop
+    decides WHEN each group is reduced (and so that gradients which do not come out of autograd -- the fused kernels write
+    through raw pointers -- take part):
+
+    * every ``p.grad`` is a view into the arena: addresses never change, so ``FusedAdamWEma`` builds its chunk table once
+      (set ``optimizer.keep_grads = True``), ``zero_(group)`` is one memset, and a group is contiguous -- its all-reduce
+      is ``ceil(bytes / bucket_bytes)`` NCCL calls on views, no flatten / unflatten copies;
+    * ``all_reduce_async(group)`` enqueues the group's buckets with ``async_op=True`` (NCCL's own stream: the collective
+      overlaps whatever the compute stream does next, e.g. the conv-frontend backward) and ``wait()`` makes the compute
+      stream wait for everything outstanding.  Averaging: ``ReduceOp.AVG`` on NCCL, SUM + divide elsewhere (gloo).
+
+    Groups are reduced in the order the caller asks for: in the BYOL step the transformer / head gradients are complete
+    long before the conv frontend's (the frontend is the FIRST layer, its backward runs last), so their buckets travel
+    while the frontend backward computes and only the frontend's 16.8 MB are the un-overlappable tail.
+    """
+
+    def __init__(self, param_groups, bucket_bytes: int = 256 << 20, process_group=None):
+        self.groups = [list(g) for g in param_groups]
+        params = [p for g in self.groups for p in g]
+        if not params:
+            raise ValueError("GradArena needs at least one parameter")
+        dev = params[0].device
+        for p in params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("GradArena: fp32 parameters on one device expected")
+        self.process_group = process_group
+        self.bucket_elems = max(int(bucket_bytes) // 4, 1)
+        # 4-element (16-byte) alignment of every view keeps the vectorised kernels on their fast path
+        offsets, off, self.group_ranges = [], 0, []
+        for g in self.groups:
+            start = off
+            for p in g:
+                offsets.append(off)
+                off += (p.numel() + 3) // 4 * 4
+            self.group_ranges.append((start, off))
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        for p, o in zip(params, offsets):
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+        self._works = []
+
+    @property
+    def numel(self) -> int:
+        return self.flat.numel()
+
+    def group_bytes(self, group: int) -> int:
+        a, b = self.group_ranges[group]
+        return (b - a) * 4
+
+    def zero_(self, group: Optional[int] = None) -> None:
+        if group is None:
+            self.flat.zero_()
+        else:
+            a, b = self.group_ranges[group]
+            self.flat[a:b].zero_()
+
+    def buckets(self, group: int):
+        a, b = self.group_ranges[group]
+        return [self.flat[s:min(s + self.bucket_elems, b)] for s in range(a, b, self.bucket_elems)]
+
+    def all_reduce_async(self, group: int) -> int:
+        """Enqueue the all-reduce (mean over ranks) of one group; returns the number of collectives issued."""
+        if not dist.is_initialized() or dist.get_world_size(self.process_group) == 1:
+            return 0
+        avg = dist.get_backend(self.process_group) == "nccl"
+        n = 0
+        for view in self.buckets(group):
+            work = dist.all_reduce(view, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.process_group,
+                                   async_op=True)
+            self._works.append((work, None if avg else view))
+            n += 1
+        return n
+
+    def wait(self) -> None:
+        """The current stream (CUDA) / the caller (CPU backends) waits for every outstanding collective."""
+        world = dist.get_world_size(self.process_group) if dist.is_initialized() else 1
+        for work, view in self._works:
+            work.wait()
+            if view is not None:
+                view.div_(world)
+        self._works = []

@@ -32,3 +32,4 @@ from .byol import byol_loss, ema_update  # noqa: F401
 from .frontend import conv_frontend, conv_out_lengths  # noqa: F401
 from .emotion import attentive_statistics_pooling, ccc_loss, compute_length_from_mask  # noqa: F401
 from .optim import adamw_step, clip_adamw_ema_step, clip_grad_norm  # noqa: F401
+from .evaluate import embedding_similarity, validation_metrics  # noqa: F401

@@ -15,7 +15,7 @@ copied.  Shims, all explicit below:
 Outputs (float arrays kept small; inputs are stored too so fixtures are self-contained):
   mix_byol.npz, mix_emotion.npz, mix_edge.npz, byol_loss.npz, ema.npz, frontend_layer.npz,
   frontend_group.npz, byol_step.npz, byol_state_dict_keys.json, optim_step.npz,
-  emotion.npz, emotion_state_dict_keys.json
+  emotion.npz, emotion_state_dict_keys.json, evaluate_byol.npz
 """
 import os
 import random
@@ -291,6 +291,65 @@ def gen_byol_step(seed=51, B=4, L=4000):
         ref_encoder_mod.WavLMEncoder.forward = orig_fwd
 
 
+def gen_evaluate_byol(seed=81, n_batches=3, B=4, L=4000):
+    """The reference's OWN ``evaluate_embedding_similarity`` and ``validate_model`` (ref:evaluate_byol.py:12-123, imported
+    unmodified; matplotlib / tqdm are only imported at its module level: stubbed when absent) on the shimmed BYOL model of
+    ``gen_byol_step`` and an in-memory "loader" of reference-format batches: per-SNR mean cosine similarity of the clean /
+    noisy embeddings, validation loss, metrics dict."""
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn", "wandb"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    if not hasattr(sys.modules["matplotlib"], "pyplot"):
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    import evaluate_byol as ref_eval
+    cfg = small_wavlm_config("layer")
+    for k in ("hidden_dropout", "activation_dropout", "attention_dropout", "feat_proj_dropout", "final_dropout",
+              "layerdrop", "mask_time_prob", "mask_feature_prob"):
+        setattr(cfg, k, 0.0)
+    cfg.apply_spec_augment = False
+    orig_from = ref_encoder_mod.AutoModel.from_pretrained
+    orig_fwd = ref_encoder_mod.WavLMEncoder.forward
+    ref_encoder_mod.AutoModel.from_pretrained = staticmethod(lambda name: WavLMModel(cfg))
+    ref_encoder_mod.WavLMEncoder.forward = lambda self, x, attention_mask=None: orig_fwd(self, x, attention_mask).mean(dim=1)
+    try:
+        torch.manual_seed(seed)
+        model = RefBYOL({"model": {"name": "shim", "projection_dim": 96, "prediction_dim": 128, "ema_decay": 0.99}})
+        # a trained model has diverged online / target branches: perturb the online branch so that the similarity and the
+        # loss are not the degenerate values of two identical networks
+        with torch.no_grad():
+            g = torch.Generator().manual_seed(seed)
+            for p in model.online_encoder.parameters():
+                p.add_(0.02 * p.abs().mean() * torch.randn(p.shape, generator=g))
+        import oracle
+        snr_range = [2, 5, 10, 15]   # 15 never drawn below: the reference reports 0 for an empty bucket
+        out = {"seed": np.array(seed), "snr_range": np.array(snr_range)}
+        loader = []
+        for i in range(n_batches):
+            clean, noise, snr_idx, _ = synthetic.waveforms(B, L, seed=seed + 1 + i, snr_range=snr_range[:3])
+            c, n, st = oracle.mix_normalize_batch(clean, noise, snr_idx, np.asarray(snr_range[:3], dtype=np.float64),
+                                                  peak_norm=True)
+            assert not st.any()
+            snr = torch.tensor([snr_range[j] for j in snr_idx], dtype=torch.int64)
+            loader.append({"clean_input_values": c[:, None], "noisy_input_values": n[:, None], "snr": snr})
+            out[f"clean_{i}"], out[f"noisy_{i}"], out[f"snr_{i}"] = c.numpy(), n.numpy(), snr.numpy()
+        config = {"data": {"snr_range": snr_range}}
+        sims = ref_eval.evaluate_embedding_similarity(model, loader, torch.device("cpu"), config)
+        val_loss, metrics = ref_eval.validate_model(model, loader, torch.device("cpu"), config)
+        assert metrics["val_similarities"] == sims
+        out["similarities"] = np.array([sims[s] for s in snr_range], dtype=np.float64)
+        out["val_loss"] = np.array(val_loss, dtype=np.float64)
+        out["val_avg_similarity"] = np.array(metrics["val_avg_similarity"], dtype=np.float64)
+        np.savez_compressed(os.path.join(HERE, "evaluate_byol.npz"), **out)
+        print("evaluate_byol: similarities", sims, "val_loss", val_loss)
+    finally:
+        ref_encoder_mod.AutoModel.from_pretrained = orig_from
+        ref_encoder_mod.WavLMEncoder.forward = orig_fwd
+
+
 OPTIM_GRAD_SCALES = (3e-2, 1e-2, 1e-4)
 
 
@@ -434,4 +493,5 @@ if __name__ == "__main__":
     gen_byol_step()
     gen_optim_step()
     gen_emotion()
+    gen_evaluate_byol()
     print("sizes:", {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")})

@@ -51,12 +51,19 @@ def test_experiment_hooks_stay_out_of_the_product_path():
     pkg = os.path.join(ROOT, "noise-robust-speech-embedding_b200")
     for path in glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True):
         src = open(path).read()
-        assert "NRSE_EXPERIMENT" not in src, path
-        if not path.endswith("_lib.py"):
+        if not path.endswith(os.path.join("csrc", "build.py")):  # build.py names the -DNRSE_EXPERIMENTS switch of its scripts-only variant
+            assert "NRSE_EXPERIMENT" not in src, path
+        if not path.endswith("_lib.py") and not path.endswith(os.path.join("csrc", "build.py")):
             assert "NRSE_B200_LIB" not in src, path
     for name in ("bench.py", "__graft_entry__.py"):
         src = open(os.path.join(ROOT, name)).read()
         assert 'for var in ("NRSE_EXPERIMENT", "NRSE_B200_LIB")' in src, name
+        assert "nrse_experiments_build" in src, name
+    # the shipped binary itself: the hooks are compiled in only with -DNRSE_EXPERIMENTS (csrc/build.py --experiments,
+    # a separate scripts-only library); the product library never reads the environment variable
+    lib = os.path.join(pkg, "csrc", "libnrse_b200.so")
+    if os.path.exists(lib):
+        assert b"NRSE_EXPERIMENT" not in open(lib, "rb").read()
 
 
 def test_clock_sampler_parses_time_stamped_samples():

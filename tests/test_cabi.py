@@ -36,7 +36,8 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_version_and_errors(lib):
-    assert lib.nrse_version() == 100
+    assert lib.nrse_version() == 200
+    assert lib.nrse_experiments_build() == 0   # the product library carries no results-corrupting timing hooks
     assert lib.nrse_strerror(0) == b"ok"
     assert b"invalid" in lib.nrse_strerror(-1)
     assert lib.nrse_mix_status_name(0) == b"ok"

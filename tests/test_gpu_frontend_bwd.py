@@ -37,6 +37,26 @@ def test_ln_gelu_bwd_vs_autograd(dev):
         assert rel_err(dg.cpu().numpy(), gamma.grad.numpy()) < tol
         assert rel_err(db.cpu().numpy(), beta.grad.numpy()) < tol
         assert not dz.float().cpu()[~valid].any()          # pitch padding carries zero gradient
+    # fp32 gradient in the COMPACT layout [B, T, 512] (what autograd hands over: no zero-padded copy is ever made)
+    compact = dout.view(B, P, 512)[:, :T].contiguous()
+    dz, dg, db = ops.ln_gelu_bwd(compact.to(dev), xhat.to(dev), rstd.flatten().to(dev), gamma.detach().to(dev),
+                                 beta.detach().to(dev), P, T, dout_pitch=T)
+    assert rel_err(dz.float().cpu().numpy(), z.grad.numpy()) < 1e-2
+    assert rel_err(dg.cpu().numpy(), gamma.grad.numpy()) < 1e-2 and rel_err(db.cpu().numpy(), beta.grad.numpy()) < 1e-2
+
+
+def test_gelu_bwd_without_norm_vs_autograd(dev):
+    """GroupNorm-mode layers 1-6 have no normalisation (hf:...modeling_wavlm.py:682-700): dZ = dOut gelu'(Z)."""
+    torch.manual_seed(1)
+    P, T, B = 24, 21, 4
+    rows = B * P
+    z = (torch.randn(rows, 512) * 1.5).bfloat16().float().requires_grad_(True)
+    dout = torch.randn(rows, 512).bfloat16().float() * ((torch.arange(rows) % P) < T)[:, None]
+    F.gelu(z).backward(dout)
+    for dtype in (torch.float32, torch.bfloat16):
+        dz, dg, db = ops.ln_gelu_bwd(dout.to(dtype).to(dev), z.detach().bfloat16().to(dev), None, None, None, P, T)
+        assert dg is None and db is None
+        assert rel_err(dz.float().cpu().numpy(), z.grad.numpy()) < 6e-3   # bf16 output rounding + the gelu' fit (2.6e-5)
 
 
 @pytest.mark.parametrize("k,rows_out", [(3, 128), (2, 192), (3, 1000), (2, 64 * 131 + 7)])
@@ -55,6 +75,9 @@ def test_wgrad_and_dgrad_vs_autograd(dev, k, rows_out):
     dw = ops.conv_layer_wgrad(dz.to(dev), act.to(dev), k)
     got_dw = dw.view(512, k, 512).permute(0, 2, 1).cpu()
     assert rel_err(got_dw.numpy(), dw_ref.numpy()) < 1e-3
+    # the same accumulators written straight into the checkpoint layout [512, 512, k] (what the full backward uses)
+    dw_ck = ops.conv_layer_wgrad(dz.to(dev), act.to(dev), k, ckpt_layout=True).cpu()
+    assert dw_ck.shape == dw_ref.shape and rel_err(dw_ck.numpy(), dw_ref.numpy()) < 1e-3
     even, odd = ops.pack_conv_weight_dgrad(w.to(dev))
     dx = ops.conv_layer_dgrad(dz.to(dev), even, odd, k)
     assert rel_err(dx.float().cpu().numpy(), dx_ref.numpy()) < 6e-3   # bf16 output rounding
@@ -74,39 +97,148 @@ def test_layer0_wgrad_vs_autograd(dev):
     assert rel_err(got.cpu().numpy(), w.grad[:, 0].numpy()) < 1e-4
 
 
+def _oracle_grads(x, layers, norm_mode, gy):
+    params = [{k: (torch.from_numpy(v).requires_grad_(True) if v is not None else None) for k, v in l.items()} for l in layers]
+    y_ref = oracle.conv_frontend(torch.from_numpy(x), params, norm_mode)          # [B, 512, T]
+    y_ref.backward(gy)
+    return y_ref.detach(), params
+
+
+def _dev_params(layers, dev, n_norm):
+    w = [torch.from_numpy(l["conv"]).to(dev) for l in layers]
+    g = [torch.from_numpy(layers[i]["gamma"]).to(dev) for i in range(n_norm)]
+    b = [torch.from_numpy(layers[i]["beta"]).to(dev) for i in range(n_norm)]
+    return w, g, b
+
+
+# Tolerance of the FULL backward against autograd on the fp32 oracle graph.  The gradient reaches layer i through
+# (6 - i) data-gradient GEMMs with bf16 operands and bf16 gradient buffers, on top of a forward whose bf16 activations are
+# themselves within 5e-3 of the oracle; the per-kernel tests on identical operands are held to 1e-3 (wgrad), 6e-3 (dgrad)
+# and 1e-2 (norm + GELU backward).  Bound per tensor: the north star's bf16 tolerance 1e-2 for the top layers, growing
+# with depth; measured values are printed by the test and recorded in profiles/README.md.
+FULL_BWD_TOL = {6: 1.0e-2, 5: 1.2e-2, 4: 1.5e-2, 3: 1.5e-2, 2: 2.0e-2, 1: 2.0e-2, 0: 2.0e-2}
+
+
 @pytest.mark.parametrize("B,L", [(2, 4000), (3, 16000)])
 def test_full_backward_vs_autograd(dev, B, L):
     layers = synthetic.frontend_weights("layer", seed=9)
     x = synthetic.waveforms(B, L, seed=5)[0]
     x = ((x - x.mean(1, keepdims=True)) / x.std(1, keepdims=True)).astype(np.float32)
-    params = [{k: (torch.from_numpy(v).requires_grad_(True) if v is not None else None) for k, v in l.items()} for l in layers]
-    y_ref = oracle.conv_frontend(torch.from_numpy(x), params, "layer")          # [B, 512, T]
-    gy = torch.from_numpy(np.random.RandomState(1).standard_normal(tuple(y_ref.shape)).astype(np.float32))
-    y_ref.backward(gy)
-
-    w = [torch.from_numpy(l["conv"]).to(dev) for l in layers]
-    g = [torch.from_numpy(l["gamma"]).to(dev) for l in layers]
-    b = [torch.from_numpy(l["beta"]).to(dev) for l in layers]
+    T, _ = ops.frontend_geometry(L)
+    gy = torch.from_numpy(np.random.RandomState(1).standard_normal((B, 512, T[6])).astype(np.float32))
+    y_ref, params = _oracle_grads(x, layers, "layer", gy)
+    w, g, b = _dev_params(layers, dev, 7)
     xd = torch.from_numpy(x).to(dev)
     y, tape = ops.conv_frontend_train(xd, w, g, b)
-    assert rel_err(y.transpose(1, 2).cpu().numpy(), y_ref.detach().numpy()) < 1e-2
-    # the tape-writing forward runs layer 0 with the un-folded epilogue (it has to save the pre-affine activations): with
-    # the same layer-0 kernel selected for inference the features are bit-identical, with the default (LayerNorm folded
-    # into the GEMM operands) they agree to bf16 rounding of the layer-0 output
+    assert rel_err(y.transpose(1, 2).cpu().numpy(), y_ref.numpy()) < 1e-2
+    # the tape-writing forward runs layer 0 with the un-folded epilogue (it has to save the pre-affine activations) and
+    # the same GEMM kernels as inference (2-SM for layers 1-3): with the un-folded layer-0 kernel selected for inference
+    # the features are bit-identical, with the default (LayerNorm folded into the GEMM operands) they agree to bf16
+    # rounding of the layer-0 output
     ops.set_layer0_variant(1)
-    ops.set_frontend_variant(2)   # the tape-writing forward always runs the 1-SM kernels
     assert torch.equal(y, ops.conv_frontend(xd, w, g, b, "layer"))
-    ops.set_frontend_variant(ops.DEFAULT_FRONTEND_VARIANT)
     ops.set_layer0_variant(ops.DEFAULT_LAYER0_VARIANT)
     y_plain = ops.conv_frontend(xd, w, g, b, "layer")
     # two bf16 pipelines that differ in the rounding of layer 0, six layers later: each is within 1e-2 of the fp32 oracle
-    assert rel_err(y_plain.transpose(1, 2).cpu().numpy(), y_ref.detach().numpy()) < 1e-2
+    assert rel_err(y_plain.transpose(1, 2).cpu().numpy(), y_ref.numpy()) < 1e-2
     assert rel_err(y_plain.cpu().numpy(), y.cpu().numpy()) < 8e-3
     dw, dg, db = ops.conv_frontend_backward(xd, w, g, b, tape, gy.to(dev).transpose(1, 2))
     for i in range(7):
         e_w = rel_err(dw[i].cpu().numpy(), params[i]["conv"].grad.numpy())
         e_g = rel_err(dg[i].cpu().numpy(), params[i]["gamma"].grad.numpy())
         e_b = rel_err(db[i].cpu().numpy(), params[i]["beta"].grad.numpy())
+        print(f"full backward {B}x{L} layer {i}: dW {e_w:.2e} dgamma {e_g:.2e} dbeta {e_b:.2e}")
         assert dw[i].shape == params[i]["conv"].shape
-        # bf16 activations + bf16 gradient buffers across up to 7 layers: measured ~1e-2; bound 3e-2
-        assert max(e_w, e_g, e_b) < 3e-2, (i, e_w, e_g, e_b)
+        assert max(e_w, e_g, e_b) < FULL_BWD_TOL[i], (i, e_w, e_g, e_b)
+
+
+@pytest.mark.parametrize("B,L", [(2, 4000), (3, 9000)])
+def test_full_backward_group_mode_vs_autograd(dev, B, L):
+    """GroupNorm mode (wavlm-base, hf:...modeling_wavlm.py:730-751 + :682-700): native training forward + backward --
+    GELU-only backward for layers 1-6, one fused pass for layer 0 (GroupNorm-over-time backward + dW0)."""
+    layers = synthetic.frontend_weights("group", seed=4)
+    x = synthetic.waveforms(B, L, seed=6)[0]
+    x = ((x - x.mean(1, keepdims=True)) / x.std(1, keepdims=True)).astype(np.float32)
+    T, _ = ops.frontend_geometry(L)
+    gy = torch.from_numpy(np.random.RandomState(2).standard_normal((B, 512, T[6])).astype(np.float32))
+    y_ref, params = _oracle_grads(x, layers, "group", gy)
+    w, g, b = _dev_params(layers, dev, 1)
+    xd = torch.from_numpy(x).to(dev)
+    y, tape = ops.conv_frontend_train(xd, w, g, b, "group")
+    assert rel_err(y.transpose(1, 2).cpu().numpy(), y_ref.numpy()) < 1e-2
+    assert torch.equal(y, ops.conv_frontend(xd, w, g, b, "group"))   # same kernels, the tape is extra stores
+    dw, dg, db = ops.conv_frontend_backward(xd, w, g, b, tape, gy.to(dev).transpose(1, 2), "group")
+    assert len(dg) == 1 and len(db) == 1
+    for i in range(7):
+        e = rel_err(dw[i].cpu().numpy(), params[i]["conv"].grad.numpy())
+        print(f"group-mode backward {B}x{L} layer {i}: dW {e:.2e}")
+        assert dw[i].shape == params[i]["conv"].shape and e < FULL_BWD_TOL[i], (i, e)
+    e_g = rel_err(dg[0].cpu().numpy(), params[0]["gamma"].grad.numpy())
+    e_b = rel_err(db[0].cpu().numpy(), params[0]["beta"].grad.numpy())
+    assert max(e_g, e_b) < FULL_BWD_TOL[0], (e_g, e_b)
+
+
+def test_backward_honours_needs_grad_mask(dev):
+    """Partial unfreeze (ref:src/models/emotion.py:114-129): only what is asked for is computed; what IS computed equals
+    the corresponding tensors of the full backward (same kernels, same order), the rest comes back as None."""
+    B, L = 2, 6000
+    layers = synthetic.frontend_weights("layer", seed=9)
+    x = synthetic.waveforms(B, L, seed=8)[0]
+    w, g, b = _dev_params(layers, dev, 7)
+    xd = torch.from_numpy(x).to(dev)
+    T, _ = ops.frontend_geometry(L)
+    gy = torch.randn(B, T[6], 512, device=dev)
+    _, tape = ops.conv_frontend_train(xd, w, g, b)
+    full = ops.conv_frontend_backward(xd, w, g, b, tape, gy)
+    need_w = [False, False, False, False, True, False, True]
+    need_a = [False, False, False, False, False, True, True]
+    dw, dg, db = ops.conv_frontend_backward(xd, w, g, b, tape, gy, need_w=need_w, need_affine=need_a)
+    for i in range(7):
+        assert (dw[i] is not None) == need_w[i] and (dg[i] is not None) == need_a[i] and (db[i] is not None) == need_a[i]
+        if need_w[i]:  # split-K partial sums meet through fp32 atomics: equal up to summation order
+            assert rel_err(dw[i].cpu().numpy(), full[0][i].cpu().numpy()) < 1e-5
+        if need_a[i]:
+            assert rel_err(dg[i].cpu().numpy(), full[1][i].cpu().numpy()) < 1e-5
+            assert rel_err(db[i].cpu().numpy(), full[2][i].cpu().numpy()) < 1e-5
+    nothing = ops.conv_frontend_backward(xd, w, g, b, tape, gy, need_w=[False] * 7, need_affine=[False] * 7)
+    assert all(t is None for part in nothing for t in part)
+
+
+def test_full_size_backward(dev):
+    """BASELINE shape 64 x 64 000 (split-K weight gradients over M = 409 536 frames, fp32 atomics, 3.3 GB tape).
+    (1) Frame independence: the gradients of the whole batch equal the SUM of the gradients of its eight 8-utterance
+    chunks run separately (differences = fp32 summation order only).  (2) Chunk 0 against torch autograd on the fp32
+    oracle graph at full utterance length, every tensor of every layer, at the tolerance of the small-shape test."""
+    B, L, CH = 64, 64000, 8
+    layers = synthetic.frontend_weights("layer", seed=0)
+    x = synthetic.waveforms(B, L, seed=1234)[0]
+    x = ((x - x.mean(1, keepdims=True)) / x.std(1, keepdims=True)).astype(np.float32)
+    T, _ = ops.frontend_geometry(L)
+    gy = torch.from_numpy(np.random.RandomState(11).standard_normal((B, T[6], 512)).astype(np.float32))
+    w, g, b = _dev_params(layers, dev, 7)
+    xd, gyd = torch.from_numpy(x).to(dev), gy.to(dev)
+    _, tape = ops.conv_frontend_train(xd, w, g, b)
+    full = ops.conv_frontend_backward(xd, w, g, b, tape, gyd)
+    full = [[t.clone() for t in part] for part in full]
+    del tape
+    acc = None
+    first = None
+    for c0 in range(0, B, CH):
+        _, tp = ops.conv_frontend_train(xd[c0:c0 + CH], w, g, b)
+        part = ops.conv_frontend_backward(xd[c0:c0 + CH], w, g, b, tp, gyd[c0:c0 + CH])
+        part = [[t.double() for t in p] for p in part]
+        if first is None:
+            first = [[t.clone() for t in p] for p in part]
+        acc = part if acc is None else [[a + t for a, t in zip(pa, pt)] for pa, pt in zip(acc, part)]
+        del tp
+    for name, fa, aa in zip(("dW", "dgamma", "dbeta"), full, acc):
+        for i in range(7):
+            e = rel_err(fa[i].cpu().numpy(), aa[i].cpu().numpy())
+            assert e < 2e-4, (name, i, e)
+    _, params = _oracle_grads(x[:CH], layers, "layer", gy[:CH].transpose(1, 2).contiguous())
+    for i in range(7):
+        e_w = rel_err(first[0][i].cpu().numpy(), params[i]["conv"].grad.numpy())
+        e_g = rel_err(first[1][i].cpu().numpy(), params[i]["gamma"].grad.numpy())
+        e_b = rel_err(first[2][i].cpu().numpy(), params[i]["beta"].grad.numpy())
+        print(f"full-size backward (8 x 64000 vs oracle) layer {i}: dW {e_w:.2e} dgamma {e_g:.2e} dbeta {e_b:.2e}")
+        assert max(e_w, e_g, e_b) < FULL_BWD_TOL[i], (i, e_w, e_g, e_b)

@@ -10,9 +10,10 @@ from conftest import rel_err
 from nrse_b200 import ops
 from nrse_b200.data import GpuBatchMixer, MixedBatchLoader, TensorPairDataset, add_noise_to_speech
 from nrse_b200.models import B200FeatureEncoder, BYOLSpeechModel, WavLMEncoder, byol_loss
-from nrse_b200.train import byol_step, check_audio_tensor, evaluate_embedding_similarity, train_one_epoch, validate_model
+from nrse_b200.train import (FusedAdamWEma, byol_step, check_audio_tensor, check_audio_tensors,
+                             evaluate_embedding_similarity, train_one_epoch, validate_model)
 from nrse_b200.utils import synthetic
-from test_host_modules import byol_config, golden_config, small_config
+from test_host_modules import byol_config, golden_config, perturbed_eval_model, small_config
 
 pytestmark = pytest.mark.gpu
 
@@ -111,21 +112,23 @@ def test_gpu_batch_mixer_and_retry(dev):
     mixed = MixedBatchLoader(loader, GpuBatchMixer([2, 5, 10, 15, 20], dev))
     (batch,) = list(mixed)
     assert batch["clean_input_values"].shape == (B, 1, L) and batch["noisy_input_values"].shape == (B, 1, L)
-    assert batch["clean_input_values"].device.type == "cuda" and batch["snr"].tolist() == [2, 5, 10, 15, 20, 2]
+    # row 2 is re-drawn with row 3's noise AND row 3's SNR (the reference's next attempt re-draws both): its label follows
+    assert batch["clean_input_values"].device.type == "cuda" and batch["snr"].tolist() == [2, 5, 15, 15, 20, 2]
     snr_idx = np.arange(B) % 5
     c_ref, n_ref, st = oracle.mix_normalize_batch(clean, noise, snr_idx, table)
     assert st.tolist() == [0, 0, 4, 0, 0, 0]
     for b in (0, 1, 3, 4, 5):
         assert rel_err(batch["noisy_input_values"][b, 0].cpu().numpy(), n_ref[b].numpy()) < 1e-6
-    # row 2 was re-mixed with the next row's noise
-    _, n2, st2 = oracle.mix_normalize_batch(clean[2:3], noise[3:4], snr_idx[2:3], table)
+    # row 2 was re-mixed with the next row's noise and SNR draw
+    _, n2, st2 = oracle.mix_normalize_batch(clean[2:3], noise[3:4], snr_idx[3:4], table)
     assert st2.tolist() == [0]
     assert rel_err(batch["noisy_input_values"][2, 0].cpu().numpy(), n2[0].numpy()) < 1e-6
 
 
 def test_gpu_batch_mixer_persistent_failure_is_reported_without_sync(dev):
-    """A silent clean row is rejected on every attempt (speech power < 1e-10): it stays in the batch zero-filled, shows
-    up in batch['mix_status'] and in the mixer's lazily collected count; drop_bad_rows=True drops it instead."""
+    """A silent clean row is rejected on every attempt (speech power < 1e-10).  Default policy: the nearest following
+    good row takes its place on the device (no zero waveform reaches BatchNorm / the loss, no host sync), the status and
+    the lazily collected count still report it; 'keep' leaves it zero-filled; 'drop' removes it (one host sync)."""
     B, L = 5, 4000
     clean, noise, _, table = synthetic.waveforms(B, L, seed=9)
     clean[3] = 0.0
@@ -136,13 +139,82 @@ def test_gpu_batch_mixer_persistent_failure_is_reported_without_sync(dev):
     batch = mixer(raw)
     assert batch["mix_status"].tolist() == [0, 0, 0, 3, 0]
     assert batch["clean_input_values"].shape == (B, 1, L)
-    assert not batch["noisy_input_values"][3].any() and not batch["clean_input_values"][3].any()
+    assert torch.equal(batch["noisy_input_values"][3], batch["noisy_input_values"][4])
+    assert torch.equal(batch["clean_input_values"][3], batch["clean_input_values"][4])
     assert batch["noisy_input_values"][1].abs().sum() > 0
+    assert batch["snr"].tolist() == [2, 10, 10, 5, 5]   # row 1 re-drawn at row 2's SNR, row 3 substituted by row 4
     assert mixer.flush() == 1
+    keeper = GpuBatchMixer([2, 5, 10], dev, bad_rows="keep")
+    batch = keeper(raw)
+    assert not batch["noisy_input_values"][3].any() and not batch["clean_input_values"][3].any()
+    assert keeper.flush() == 1
     dropper = GpuBatchMixer([2, 5, 10], dev, drop_bad_rows=True)
     batch = dropper(raw)
     assert batch["clean_input_values"].shape == (B - 1, 1, L) and batch["mix_status"].tolist() == [0, 0, 0, 0]
-    assert batch["snr"].tolist() == [2, 5, 10, 5] and dropper.rejected_rows == 1
+    assert batch["snr"].tolist() == [2, 10, 10, 5] and dropper.rejected_rows == 1
+
+
+def test_fused_optimizer_and_ema_invalidate_the_packed_weights(dev):
+    """FusedAdamWEma / EmaPlan write parameters through raw device pointers (no ``_version`` bump): after every step BOTH
+    encoders' bf16 weight packs must equal pack(current fp32 weight), and the conv outputs must move with the weights."""
+    torch.manual_seed(0)
+    model = BYOLSpeechModel(byol_config(golden_config())).to(dev).train()
+    opt = FusedAdamWEma.for_byol(model, lr=1e-3, weight_decay=1e-5)
+    clean, noise, _, _ = synthetic.waveforms(4, 4000, seed=2)
+    c, n = torch.from_numpy(clean).to(dev), torch.from_numpy(noise).to(dev)
+    fes = [model.online_encoder.model.feature_extractor, model.target_encoder.model.feature_extractor]
+    feats = []
+    for step in range(3):
+        with torch.no_grad():
+            feats.append([fe(c).clone() for fe in fes])
+        for fe in fes:
+            for packed, layer in zip(fe._packed_weights(), fe.conv_layers[1:]):
+                assert torch.equal(packed, ops.pack_conv_weight(layer.conv.weight)), step
+        byol_step(model, c, n, opt)
+    for k in range(2):   # online moves by ~lr per step, the target by (1 - decay) of that: both must be visible
+        assert not torch.equal(feats[0][k], feats[1][k]) and not torch.equal(feats[1][k], feats[2][k]), k
+    # the plain EMA path (torch optimizer + model._update_target_network) as well
+    fe_t = fes[1]
+    before = [p.clone() for p in fe_t._packed_weights()]
+    with torch.no_grad():
+        for p in model.online_encoder.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    model._update_target_network()
+    after = fe_t._packed_weights()
+    assert any(not torch.equal(a, b) for a, b in zip(before, after))
+    for packed, layer in zip(after, fe_t.conv_layers[1:]):
+        assert torch.equal(packed, ops.pack_conv_weight(layer.conv.weight))
+
+
+def test_check_audio_tensors_fused(dev):
+    """One launch, one host read for several tensors; verdicts of ref:src/utils/debugging_utils.py:4-30 in its order."""
+    cfg = {"logging": {"level": "DEBUG"}}
+    big = torch.randn(64, 1, 64000, device=dev)
+    nan = big.clone(); nan[5, 0, 123] = float("nan")
+    inf = big.clone(); inf[63, 0, 63999] = float("inf")
+    odd = torch.randn(1001, device=dev)[1:]            # 4-byte aligned only: scalar path
+    verdicts = check_audio_tensors([(big, "big"), (nan, "nan"), (inf, "inf"), (torch.zeros(7, device=dev), "zeros"),
+                                    (2e6 * torch.ones(3, 5, device=dev), "large"), (odd, "odd")], cfg)
+    assert verdicts == [True, False, False, False, False, True]
+    info = ops.decode_tensor_checks(ops.check_tensors([big, nan, inf, odd]).cpu())
+    assert [i["flags"] & 3 for i in info] == [0, 1, 2, 0]
+    b64 = big.double()
+    assert abs(info[0]["mean"] - float(b64.mean())) < 1e-6 and abs(info[0]["std"] - float(b64.std())) < 1e-6
+    assert info[0]["max"] == float(big.max()) and info[0]["min"] == float(big.min())
+    assert info[0]["abs_max"] == float(big.abs().max()) and info[0]["numel"] == big.numel()
+    assert abs(info[3]["abs_sum"] - float(odd.double().abs().sum())) < 1e-6 * odd.numel()
+    assert info[3]["min"] == float(odd.min()) and info[3]["max"] == float(odd.max())
+
+
+def test_byol_loss_input_flags(dev):
+    p = torch.randn(8, 1024, device=dev)
+    z = torch.randn(8, 1024, device=dev)
+    assert int(ops.byol_loss_with_flags(p, z)[1]) == 0
+    pn = p.clone(); pn[3, 7] = float("nan")
+    assert int(ops.byol_loss_with_flags(pn, z)[1]) == 0b0101      # NaN before and after normalisation, online side
+    zi = z.clone(); zi[0, 0] = float("inf")
+    assert int(ops.byol_loss_with_flags(p, zi)[1]) == 0b1000      # Inf normalises to NaN: target side, after only
+    assert torch.isfinite(byol_loss(p, z, check_finite=True))
 
 
 def test_add_noise_to_speech_dropin(dev, golden):
@@ -182,6 +254,32 @@ def test_train_and_validate_loops(dev):
     assert check_audio_tensor(torch.ones(4, device=dev), "ones", cfg)
     assert not check_audio_tensor(torch.tensor([1.0, float("nan")], device=dev), "nan", cfg)
     assert not check_audio_tensor(torch.zeros(4, device=dev), "zeros", cfg)
+    with pytest.raises(ValueError):
+        from nrse_b200.data import DevicePrefetcher
+        DevicePrefetcher(dev, depth=1)
+
+
+def test_evaluate_and_validate_match_reference_fixture(dev, golden):
+    """evaluate_embedding_similarity / validate_model on the B200 path against the values the reference's own functions
+    (ref:evaluate_byol.py:12-123, imported unmodified by tests/golden/make_golden.py::gen_evaluate_byol) produced on the
+    same model and batches: per-SNR mean cosine, empty bucket -> 0, validation loss, average similarity.  Tolerance: the
+    north star's 1e-2 for everything behind the bf16 conv frontend (measured values are far inside)."""
+    g = golden("evaluate_byol")
+    model = perturbed_eval_model(g, "b200").to(dev)
+    snr_range = g["snr_range"].tolist()
+    loader = [{"clean_input_values": torch.from_numpy(g[f"clean_{i}"])[:, None],
+               "noisy_input_values": torch.from_numpy(g[f"noisy_{i}"])[:, None],
+               "snr": torch.from_numpy(g[f"snr_{i}"])} for i in range(3)]
+    cfg = {"data": {"snr_range": snr_range}}
+    sims = evaluate_embedding_similarity(model, loader, dev, cfg)
+    val_loss, metrics = validate_model(model, loader, dev, cfg)
+    want = dict(zip(snr_range, g["similarities"].tolist()))
+    assert sorted(sims) == sorted(snr_range) and sims[15] == 0.0
+    for s in snr_range[:3]:
+        assert abs(sims[s] - want[s]) < 1e-2 * abs(want[s]), (s, sims[s], want[s])
+    assert abs(val_loss - float(g["val_loss"])) < 1e-2 * float(g["val_loss"])
+    assert abs(metrics["val_avg_similarity"] - float(g["val_avg_similarity"])) < 1e-2
+    assert metrics["val_similarities"] == sims and metrics["val_loss"] == val_loss
 
 
 def test_device_prefetcher_overlaps_and_preserves_batches(dev):
@@ -221,6 +319,34 @@ def test_partial_unfreeze_like_emotion_finetune(dev):
     mine(x).backward(gy)
     for (name, a), (_, b) in zip(hf.named_parameters(), mine.named_parameters()):
         if a.requires_grad:
-            assert b.grad is not None and rel_err(b.grad.cpu().numpy(), a.grad.cpu().numpy()) < 3e-2, name
+            assert b.grad is not None and rel_err(b.grad.cpu().numpy(), a.grad.cpu().numpy()) < 1.2e-2, name
         else:
             assert b.grad is None, name
+    with pytest.raises(RuntimeError, match="tape"):   # the tape is freed by the first backward
+        y = mine(x)
+        y.backward(gy, retain_graph=True)
+        y.backward(gy)
+    with pytest.raises(NotImplementedError):          # no waveform gradient
+        mine(x.clone().requires_grad_(True))
+
+
+def test_group_mode_module_backward_matches_hf(dev):
+    """wavlm-base(-plus) geometry (GroupNorm on layer 0, no norm on layers 1-6; the reference's own smoke test uses it,
+    ref:src/models/encoder.py:36): forward and every parameter gradient of the module against stock HF autograd."""
+    from transformers.models.wavlm.modeling_wavlm import WavLMFeatureEncoder
+    torch.manual_seed(5)
+    hf = WavLMFeatureEncoder(small_config("group")).to(dev).train()
+    mine = B200FeatureEncoder(small_config("group")).to(dev).train()
+    mine.load_state_dict(hf.state_dict())
+    assert mine.norm_mode == "group"
+    x = torch.randn(3, 8000, device=dev)
+    gy = torch.randn(3, 512, 24, device=dev)
+    hf._requires_grad = False
+    y_hf = hf(x)
+    y_hf.backward(gy)
+    y = mine(x)
+    y.backward(gy)
+    assert rel_err(y.detach().cpu().numpy(), y_hf.detach().cpu().numpy()) < 1e-2
+    for (name, a), (_, b) in zip(hf.named_parameters(), mine.named_parameters()):
+        assert b.grad is not None and b.grad.shape == a.grad.shape, name
+        assert rel_err(b.grad.cpu().numpy(), a.grad.cpu().numpy()) < 2e-2, name

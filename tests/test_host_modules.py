@@ -162,6 +162,48 @@ def test_create_dataloaders_split_is_seeded():
     assert item["snr"] == [2, 5, 10, 15, 20][7 % 5] and item["clean_wave"].shape == (1, 800)
 
 
+def perturbed_eval_model(g, frontend):
+    """The model of tests/golden/make_golden.py::gen_evaluate_byol: seeded construction, then the same seeded
+    perturbation of the online encoder (so that online / target branches differ like in a trained model)."""
+    torch.manual_seed(int(g["seed"]))
+    cfg = byol_config(golden_config())
+    cfg["model"]["frontend"] = frontend
+    model = BYOLSpeechModel(cfg)
+    with torch.no_grad():
+        gen = torch.Generator().manual_seed(int(g["seed"]))
+        for p in model.online_encoder.parameters():
+            p.add_(0.02 * p.abs().mean() * torch.randn(p.shape, generator=gen))
+    return model
+
+
+def test_evaluate_oracle_matches_reference_fixture():
+    """oracle.embedding_similarity / validation_metrics against the values the reference's own
+    evaluate_embedding_similarity / validate_model (ref:evaluate_byol.py:12-123) produced -- through this repository's
+    BYOLSpeechModel with the stock HF frontend on the CPU (same state-dict, same seeded init)."""
+    g = np.load(os.path.join(GOLDEN, "evaluate_byol.npz"))
+    model = perturbed_eval_model(g, "hf").eval()
+    snr_range = g["snr_range"].tolist()
+    embs, pairs = [], []
+    with torch.no_grad():
+        for i in range(3):
+            c, n = torch.from_numpy(g[f"clean_{i}"])[:, None], torch.from_numpy(g[f"noisy_{i}"])[:, None]
+            enc = model.get_encoder()
+            embs.append((model._pool(enc(c)), model._pool(enc(n)), g[f"snr_{i}"]))
+            pairs.append(model(c, n))
+    sims = oracle_mod().embedding_similarity(embs, snr_range)
+    val_loss, metrics = oracle_mod().validation_metrics(pairs, sims)
+    want = dict(zip(snr_range, g["similarities"].tolist()))
+    for s in snr_range:
+        assert abs(sims[s] - want[s]) < 1e-5, (s, sims[s], want[s])
+    assert sims[15] == 0 and abs(val_loss - float(g["val_loss"])) < 1e-5
+    assert abs(metrics["val_avg_similarity"] - float(g["val_avg_similarity"])) < 1e-5
+
+
+def oracle_mod():
+    import oracle
+    return oracle
+
+
 def _ddp_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
@@ -213,6 +255,71 @@ def test_two_rank_gloo_data_parallel_equivalence():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: True, 1: True}
+
+
+def _arena_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import oracle
+    from nrse_b200.data import TensorPairDataset
+    from nrse_b200.train import GradArena, init_distributed
+    init_distributed("gloo")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(32, 48), torch.nn.ReLU(), torch.nn.Linear(48, 15))
+    extra = [torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(3, 5))]  # grads written by hand
+    arena = GradArena([extra, list(net.parameters())], bucket_bytes=1024)   # several buckets per group
+    ptrs = [p.grad.data_ptr() for p in net.parameters()]
+    assert all(p.grad.data_ptr() % 16 == 0 for g in arena.groups for p in g)
+    g = torch.Generator().manual_seed(1)
+    x, z = torch.randn(8, 32, generator=g), torch.randn(8, 15, generator=g)
+    ok = True
+    for step in range(2):
+        arena.zero_(1)
+        for i, p in enumerate(extra):
+            p.grad.fill_(float(rank + 1 + i))                       # group 0: not from autograd
+        n0 = arena.all_reduce_async(0)                               # travels while the "backward" below runs
+        oracle.byol_loss(net(x[rank * 4:(rank + 1) * 4]), z[rank * 4:(rank + 1) * 4]).backward()   # accumulates into the views
+        n1 = arena.all_reduce_async(1)
+        arena.wait()
+        ok &= n0 >= 1 and n1 >= 2 and [p.grad.data_ptr() for p in net.parameters()] == ptrs
+        torch.manual_seed(0)
+        ref = torch.nn.Sequential(torch.nn.Linear(32, 48), torch.nn.ReLU(), torch.nn.Linear(48, 15))
+        oracle.byol_loss(ref(x), z).backward()
+        for a, b in zip(net.parameters(), ref.parameters()):
+            ok &= torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-7)
+        for i, p in enumerate(extra):
+            ok &= torch.allclose(p.grad, torch.full_like(p, (1 + 2) / 2 + i))
+    # create_dataloaders shards the dataset across ranks (DistributedSampler) once a process group exists
+    from nrse_b200.data import noisy_speech_dataset as nsd
+    class _NoMixer:  # the GPU mixer is not under test here
+        def __init__(self, *a, **k): pass
+        def __call__(self, raw): return raw
+    nsd.GpuBatchMixer = _NoMixer
+    ds = TensorPairDataset(torch.arange(40.0)[:, None].repeat(1, 8), torch.zeros(40, 8), [2, 5])
+    cfg = {"data": {"snr_range": [2, 5], "validation_ratio": 0.2}, "training": {"batch_size": 4, "num_workers": 0, "seed": 3}}
+    tr, va = nsd.create_dataloaders(cfg, device="cpu", dataset=ds)
+    tr.set_epoch(0)
+    mine = sorted(int(v) for b in tr for v in b["clean_wave"][:, 0, 0].tolist())
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    ok &= len(mine) == 16 and not set(gathered[0]) & set(gathered[1]) and len(set(gathered[0]) | set(gathered[1])) == 32
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_grad_arena_and_sharded_loader():
+    """GradArena: gradients live in one flat buffer (stable addresses), groups are all-reduced asynchronously in several
+    buckets, the mean over ranks equals the full-batch gradient; hand-written gradients take part.  create_dataloaders
+    hands every rank a disjoint shard."""
+    import torch.multiprocessing as mp
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_arena_worker, args=(2, port, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
 
 
