@@ -362,6 +362,31 @@ int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out
 int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even, const void* wt_odd, int k, void* dx,
                           nrse_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Feature projection: LayerNorm(512) + Linear(512 -> 1024) on the conv features, forward and backward.
+ * Replaces WavLMFeatureProjection.forward, hf:models/wavlm/modeling_wavlm.py:93-105 (reached from
+ * ref:src/models/encoder.py:25 through WavLMModel.forward, hf:...:1061-1064); the dropout behind it stays with the caller.
+ *   pack     projection.weight [1024, 512] fp32 -> bf16 copy (forward operand) and its transpose [512, 1024] (backward)
+ *   fwd      feats [B, feats_pitch, 512] fp32 / bf16 -- the conv frontend's channels-last output, read in place
+ *            (feats_pitch = P_6 for the pitched kernel output, T for a compact tensor) -> hidden [B*T, 1024] fp32
+ *            (= projection(layer_norm(feats)) + bias), norm_hidden (nullable) [B*T, 512] fp32 = layer_norm(feats), HF's
+ *            second output.  One LayerNorm launch (writes the bf16 GEMM operand into `tape`) + one tcgen05 GEMM launch.
+ *            tape: nrse_feature_projection_tape_bytes(B*T) bytes, 1024-aligned; always needed (it holds the GEMM operand);
+ *            training != 0 additionally keeps xhat / rstd there for the backward.
+ *   bwd      d_hidden [rows, 1024] fp32 -> d_feats [rows, 512] fp32 (nullable; the `dy` of nrse_conv_frontend_bwd with
+ *            dy_pitch = T), d_ln_gamma / d_ln_beta [512], d_w [1024, 512], d_bias [1024]: all nullable, ACCUMULATED.
+ *            workspace: nrse_feature_projection_bwd_workspace_bytes(rows) bytes, 1024-aligned.
+ * ------------------------------------------------------------------------------------------- */
+int nrse_feature_projection_pack(const float* w, void* w_bf16, void* wt_bf16, nrse_stream_t stream);
+size_t nrse_feature_projection_tape_bytes(int64_t rows);
+int nrse_feature_projection_fwd(const void* feats, int feats_dtype, int B, int T, int feats_pitch, const float* ln_gamma,
+                                const float* ln_beta, float eps, const void* w_bf16, const float* bias, float* hidden,
+                                float* norm_hidden, void* tape, int training, nrse_stream_t stream);
+size_t nrse_feature_projection_bwd_workspace_bytes(int64_t rows);
+int nrse_feature_projection_bwd(const float* d_hidden, const void* tape, const float* ln_gamma, const float* ln_beta,
+                                const void* wt_bf16, float* d_feats, float* d_ln_gamma, float* d_ln_beta, float* d_w,
+                                float* d_bias, void* workspace, int64_t rows, nrse_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,6 +104,11 @@ SIGNATURES = {
     "nrse_conv_layer0_gn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "nrse_conv_layer_wgrad": (_i, [_p, _p, _i64, _i, _p, _i, _p]),
     "nrse_conv_layer_dgrad": (_i, [_p, _i64, _p, _p, _i, _p, _p]),
+    "nrse_feature_projection_pack": (_i, [_p, _p, _p, _p]),
+    "nrse_feature_projection_tape_bytes": (_sz, [_i64]),
+    "nrse_feature_projection_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p, _p, _p, _i, _p]),
+    "nrse_feature_projection_bwd_workspace_bytes": (_sz, [_i64]),
+    "nrse_feature_projection_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
 }
 
 _lib = None

@@ -387,10 +387,17 @@ struct GemmArgs {
   float* rstd;         // [M_total] or nullptr
   // generalisations used by the data-gradient GEMM (mode 1): A is a plain 2-D [rows, 512] map whose K range is a
   // concatenation of 512-wide blocks taken `a_row_off[block]` rows away; output row = m * out_row_mul + out_row_add
-  int mode;            // 0: LayerNorm + GELU forward epilogue, 1: plain bf16 store of the accumulator
+  int mode;            // 0: LayerNorm + GELU forward epilogue, 1: plain bf16 store of the accumulator,
+                       // 2: fp32 store of accumulator + bias (linear layer: the feature projection)
   int a_2d;
   int a_row_off[2];
   int out_row_mul, out_row_add;
+  // linear-layer generalisations (modes 1 / 2 with a_2d): a_wide = the K range walks the COLUMNS of a [rows, K] A map
+  // (instead of 512-wide blocks taken from shifted rows); n_split = number of 512-wide groups of output columns, tile t
+  // covers frames tile (t / n_split) and column group (t % n_split) (num_tiles counts both); out_pitch = elements per
+  // output row (mode 2); bias = [n_split * 512] fp32 (mode 2)
+  int a_wide, n_split, out_pitch;
+  const float* bias;
   // L2 prefetch of the NEXT tile's A rows (they come from HBM; the weights are L2-resident): base pointer and row count
   const char* a_ptr;
   long long a_rows;
@@ -736,6 +743,44 @@ __device__ __forceinline__ void epilogue_plain_row(uint32_t taddr, uint32_t bar_
   }
 }
 
+// Mode-2 epilogue (linear layer): accumulator + bias goes out as fp32 (256-bit row-owner stores: these launches are small).
+template <int kClusterN>
+__device__ __forceinline__ void epilogue_bias_f32_row(uint32_t taddr, uint32_t bar_tmem_empty, bool store, float* out_row,
+                                                      const float* __restrict__ bias) {
+  constexpr int kNPC = kC / kClusterN;
+  constexpr int kChunks = kNPC / 32;
+  uint32_t ra[32], rb[32];
+  auto emit = [&](const uint32_t (&r)[32], int c) {
+    if (!store) return;
+    char* dst = reinterpret_cast<char*>(out_row + c * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + 8 * j));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + 8 * j + 4));
+      st_global_256(dst + 32 * j, __float_as_uint(__uint_as_float(r[8 * j]) + b0.x),
+                    __float_as_uint(__uint_as_float(r[8 * j + 1]) + b0.y), __float_as_uint(__uint_as_float(r[8 * j + 2]) + b0.z),
+                    __float_as_uint(__uint_as_float(r[8 * j + 3]) + b0.w), __float_as_uint(__uint_as_float(r[8 * j + 4]) + b1.x),
+                    __float_as_uint(__uint_as_float(r[8 * j + 5]) + b1.y), __float_as_uint(__uint_as_float(r[8 * j + 6]) + b1.z),
+                    __float_as_uint(__uint_as_float(r[8 * j + 7]) + b1.w));
+    }
+  };
+  ptx::tmem_ld32(taddr, ra);
+#pragma unroll 1
+  for (int c = 0; c < kChunks; c += 2) {
+    ptx::tmem_ld_wait();
+    ptx::tmem_ld32(taddr + (c + 1) * 32, rb);
+    emit(ra, c);
+    ptx::tmem_ld_wait();
+    if (c + 2 < kChunks) {
+      ptx::tmem_ld32(taddr + (c + 2) * 32, ra);
+    } else {
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_tmem_empty);
+    }
+    emit(rb, c + 1);
+  }
+}
+
 template <int kClusterN, bool kSave>
 __global__ void __launch_bounds__(GemmCfg<kClusterN>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -802,8 +847,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const int m_tiles = g.num_tiles / g.n_split;
       for (int tile = first_tile; tile < g.num_tiles; tile += tile_step) {
-        const int m0 = (g.reverse ? g.num_tiles - 1 - tile : tile) * kBlockM;
+        const int mt = tile / g.n_split, ng = tile - mt * g.n_split;
+        const int m0 = (g.reverse ? m_tiles - 1 - mt : mt) * kBlockM;
         if (g.l2_prefetch && cta_rank == 0 && tile + tile_step < g.num_tiles) {
           // the next tile's input frames are one contiguous range of the previous activation
           const long long nm0 = static_cast<long long>(tile + tile_step) * kBlockM;
@@ -822,17 +869,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ptx::mbar_arrive_expect_tx(bar(kFull + stage), Cfg::kStageBytes);
           // input frame of tap j for output frame m is stride*m + j = stride*(m + j/stride) + j%stride
           const int tap = kb >> 3, c0 = (kb & 7) * kBlockK;
-          if (g.a_2d) ptx::tma_load_2d(a_dst, &tmap_a, bar(kFull + stage), c0, m0 + (tap == 0 ? g.a_row_off[0] : g.a_row_off[1]));
+          if (g.a_wide) ptx::tma_load_2d(a_dst, &tmap_a, bar(kFull + stage), kb * kBlockK, m0 + g.a_row_off[0]);
+          else if (g.a_2d) ptx::tma_load_2d(a_dst, &tmap_a, bar(kFull + stage), c0, m0 + (tap == 0 ? g.a_row_off[0] : g.a_row_off[1]));
           else if (NRSE_EXP(g.exp_flags, 16)) ptx::tma_load_3d_hint(a_dst, &tmap_a, bar(kFull + stage), c0, tap % g.stride, m0 + tap / g.stride, ptx::kL2EvictFirst);
           else ptx::tma_load_3d(a_dst, &tmap_a, bar(kFull + stage), c0, tap % g.stride, m0 + tap / g.stride);
 #pragma unroll
           for (int h = 0; h < Cfg::kNumMma; ++h) {
             if NRSE_EXP(g.exp_flags, 32)
               ptx::tma_load_2d_hint(b_dst + h * (kUmmaN * kBlockK * 2), &tmap_w, bar(kFull + stage), kb * kBlockK,
-                                    n0 + h * kUmmaN, ptx::kL2EvictLast);
+                                    ng * kC + n0 + h * kUmmaN, ptx::kL2EvictLast);
             else
               ptx::tma_load_2d(b_dst + h * (kUmmaN * kBlockK * 2), &tmap_w, bar(kFull + stage), kb * kBlockK,
-                               n0 + h * kUmmaN);
+                               ng * kC + n0 + h * kUmmaN);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
@@ -885,7 +933,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
          it += Cfg::kTeams, tile += Cfg::kTeams * tile_step) {
       const int buf = team;
       const uint32_t acc_phase = static_cast<uint32_t>(it / Cfg::kAccBufs) & 1u;
-      const long long m = static_cast<long long>(g.reverse ? g.num_tiles - 1 - tile : tile) * kBlockM + row;
+      const int mt = tile / g.n_split, ng = tile - mt * g.n_split;
+      const long long m = static_cast<long long>(g.reverse ? g.num_tiles / g.n_split - 1 - mt : mt) * kBlockM + row;
       ptx::mbar_wait(bar(kTmemFull + buf), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * Cfg::kNPC);
@@ -903,6 +952,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ost.policy = NRSE_EXP(g.exp_flags, 8) ? 0ull : ptx::kL2EvictFirst;
       ost.exp_flags = g.exp_flags;
 
+      if (g.mode == 2) {
+        epilogue_bias_f32_row<kClusterN>(taddr, bar(kTmemEmpty + buf), m < g.M_total,
+                                         reinterpret_cast<float*>(g.out) + m * g.out_pitch + ng * kC + n0,
+                                         g.bias + ng * kC + n0);
+        continue;
+      }
       if (g.mode == 1) {
         const long long orow = m * g.out_row_mul + g.out_row_add;
         epilogue_plain_row<kClusterN>(taddr, bar(kTmemEmpty + buf), m < g.M_total && !NRSE_EXP(g.exp_flags, 1),
@@ -1704,7 +1759,8 @@ struct LnBwdArgs {
   const float* rstd;
   const float* gamma;
   const float* beta;
-  __nv_bfloat16* dz;
+  __nv_bfloat16* dz;  // bf16 [rows, 512] (pitch-padding rows zeroed), or with dz_f32: fp32, frame (b, t) at row b * dz_P + t
+  int dz_f32, dz_P;
   float* dgamma;  // nullable (both or neither): [512], accumulated with atomics
   float* dbeta;
   long long rows;
@@ -1762,7 +1818,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // kNorm = false: layers without a normalisation (GroupNorm-mode layers 1-6, hf:...modeling_wavlm.py:682-700):
 // dZ = dOut gelu'(Z), `xhat` holds Z, no row statistics, no affine gradients.
-template <bool kDoutF32, bool kNorm>
+// kGelu = false: a plain LayerNorm backward (the feature projection's LayerNorm, hf:...modeling_wavlm.py:93-105).
+template <bool kDoutF32, bool kNorm, bool kGelu = true>
 __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnBwdArgs a) {
   __shared__ __align__(16) float s_gamma[kC];
   __shared__ __align__(16) float s_beta[kC];
@@ -1819,8 +1876,10 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
     slot = (slot + 1) % kLnStages;
     uint4* zrow = reinterpret_cast<uint4*>(a.dz + m * kC);
     if (static_cast<int>(m % a.P) >= a.T) {  // pitch padding: no gradient flows through it
-      zrow[lane] = make_uint4(0, 0, 0, 0);
-      zrow[32 + lane] = make_uint4(0, 0, 0, 0);
+      if (!a.dz_f32) {
+        zrow[lane] = make_uint4(0, 0, 0, 0);
+        zrow[32 + lane] = make_uint4(0, 0, 0, 0);
+      }
       continue;
     }
     f2 go[8], xh[8];
@@ -1866,7 +1925,7 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
     f2 dx[8], s1 = zero2, s2 = zero2;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const f2 dv = f2_mul(go[j], gelu_grad2(f2_fma(xh[j], g2[j], b2[j])));
+      const f2 dv = kGelu ? f2_mul(go[j], gelu_grad2(f2_fma(xh[j], g2[j], b2[j]))) : go[j];
       dg[j] = f2_fma(dv, xh[j], dg[j]);
       db[j] = f2_add(db[j], dv);
       dx[j] = f2_mul(dv, g2[j]);
@@ -1884,14 +1943,22 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
     const float rs = __ldg(a.rstd + m);
     const f2 rs2 = f2_make(rs, rs), nm1 = f2_make(-m1 * rs, -m1 * rs), nm2 = f2_make(-m2 * rs, -m2 * rs);
     uint32_t z[8];
+    float zf[16];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {  // rstd (dx - m1 - xhat m2)
-      float z0, z1;
-      f2_split(f2_fma(xh[j], nm2, f2_fma(dx[j], rs2, nm1)), z0, z1);
-      z[j] = pack_bf16x2(z0, z1);
+      f2_split(f2_fma(xh[j], nm2, f2_fma(dx[j], rs2, nm1)), zf[2 * j], zf[2 * j + 1]);
+      z[j] = pack_bf16x2(zf[2 * j], zf[2 * j + 1]);
     }
-    zrow[lane] = make_uint4(z[0], z[1], z[2], z[3]);
-    zrow[32 + lane] = make_uint4(z[4], z[5], z[6], z[7]);
+    if (a.dz_f32) {  // small tensors only (the feature projection): fp32 rows in the caller's layout
+      float4* fr = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.dz) + ((m / a.P) * a.dz_P + (m % a.P)) * kC);
+      fr[2 * lane] = make_float4(zf[0], zf[1], zf[2], zf[3]);
+      fr[2 * lane + 1] = make_float4(zf[4], zf[5], zf[6], zf[7]);
+      fr[64 + 2 * lane] = make_float4(zf[8], zf[9], zf[10], zf[11]);
+      fr[64 + 2 * lane + 1] = make_float4(zf[12], zf[13], zf[14], zf[15]);
+    } else {
+      zrow[lane] = make_uint4(z[0], z[1], z[2], z[3]);
+      zrow[32 + lane] = make_uint4(z[4], z[5], z[6], z[7]);
+    }
   }
   if constexpr (!kDoutF32) cp_async_wait<0>();
   if (!kNorm || a.dgamma == nullptr) return;  // uniform over the grid
@@ -2271,6 +2338,119 @@ __global__ void pack_weights_dgrad_kernel(const float* __restrict__ w, __nv_bflo
     odd[static_cast<size_t>(c) * kC + n] = __float2bfloat16_rn(w[(static_cast<size_t>(n) * kC + c) * k + 1]);
 }
 
+// =========================================================================================================
+// Feature projection: LayerNorm(512) + Linear(512 -> 1024), the step right behind the conv stack
+// (hf:models/wavlm/modeling_wavlm.py:93-105, reached from ref:src/models/encoder.py:25).
+//   forward : featproj_ln_kernel (LayerNorm of every frame straight from the pitched layer-6 output -> bf16 GEMM operand,
+//             compact rows; optionally the fp32 `norm_hidden_states` HF returns and the tape of the backward) +
+//             conv_gemm_kernel mode 2 (tcgen05 GEMM [rows, 512] x [512, 1024], fp32 + bias epilogue, two column groups)
+//   backward: featproj_bwd_prep_kernel (d_hidden fp32 -> bf16 operand, d_bias) + conv_wgrad_kernel (dW = dH^T xn) +
+//             conv_gemm_kernel mode 1 (dxn = dH W, K = 1024) + ln_gelu_bwd_kernel<kGelu = false> (LayerNorm backward,
+//             fp32 gradient of the conv features = the `dy` of nrse_conv_frontend_bwd)
+// =========================================================================================================
+struct FeatLnArgs {
+  const void* feats;   // [B, feats_pitch, 512] fp32 or bf16: frame (b, t) at row b * feats_pitch + t
+  int feats_f32, feats_pitch;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  __nv_bfloat16* xn;    // [B*T, 512] LayerNorm output (the GEMM's A operand)
+  float* norm_out;      // nullable [B*T, 512] fp32 (HF's second output, `extract_features`)
+  __nv_bfloat16* xhat;  // nullable (training): normalised pre-affine values
+  float* rstd;          // nullable (training): [B*T]
+  int B, T;
+};
+
+__global__ void __launch_bounds__(256) featproj_ln_kernel(const FeatLnArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long rows = static_cast<long long>(a.B) * a.T;
+  const long long warps_total = static_cast<long long>(gridDim.x) * 8;
+  for (long long m = static_cast<long long>(blockIdx.x) * 8 + warp; m < rows; m += warps_total) {
+    const long long src = (m / a.T) * a.feats_pitch + (m % a.T);
+    float v[16];
+    if (a.feats_f32) {
+      const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.feats) + src * kC);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 p0 = __ldg(r + h * 64 + 2 * lane), p1 = __ldg(r + h * 64 + 2 * lane + 1);
+        v[h * 8 + 0] = p0.x; v[h * 8 + 1] = p0.y; v[h * 8 + 2] = p0.z; v[h * 8 + 3] = p0.w;
+        v[h * 8 + 4] = p1.x; v[h * 8 + 5] = p1.y; v[h * 8 + 6] = p1.z; v[h * 8 + 7] = p1.w;
+      }
+    } else {
+      const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.feats) + src * kC);
+      unpack_bf16x8(__ldg(r + lane), *reinterpret_cast<float(*)[8]>(&v[0]));
+      unpack_bf16x8(__ldg(r + 32 + lane), *reinterpret_cast<float(*)[8]>(&v[8]));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += v[j];
+    const float mean = warp_sum(s) * (1.0f / kC);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float d = v[j] - mean;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / kC) + a.eps);
+    float xh[16], xo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = l0_channel(lane, j);
+      xh[j] = (v[j] - mean) * rstd;
+      xo[j] = fmaf(xh[j], __ldg(a.gamma + c), __ldg(a.beta + c));
+    }
+    uint4* xr = reinterpret_cast<uint4*>(a.xn + m * kC);
+    xr[lane] = make_uint4(pack_bf16x2(xo[0], xo[1]), pack_bf16x2(xo[2], xo[3]), pack_bf16x2(xo[4], xo[5]), pack_bf16x2(xo[6], xo[7]));
+    xr[32 + lane] = make_uint4(pack_bf16x2(xo[8], xo[9]), pack_bf16x2(xo[10], xo[11]), pack_bf16x2(xo[12], xo[13]),
+                               pack_bf16x2(xo[14], xo[15]));
+    if (a.norm_out != nullptr) {
+      float4* nr = reinterpret_cast<float4*>(a.norm_out + m * kC);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        nr[h * 64 + 2 * lane] = make_float4(xo[h * 8], xo[h * 8 + 1], xo[h * 8 + 2], xo[h * 8 + 3]);
+        nr[h * 64 + 2 * lane + 1] = make_float4(xo[h * 8 + 4], xo[h * 8 + 5], xo[h * 8 + 6], xo[h * 8 + 7]);
+      }
+    }
+    if (a.xhat != nullptr) {
+      uint4* hr = reinterpret_cast<uint4*>(a.xhat + m * kC);
+      hr[lane] = make_uint4(pack_bf16x2(xh[0], xh[1]), pack_bf16x2(xh[2], xh[3]), pack_bf16x2(xh[4], xh[5]), pack_bf16x2(xh[6], xh[7]));
+      hr[32 + lane] = make_uint4(pack_bf16x2(xh[8], xh[9]), pack_bf16x2(xh[10], xh[11]), pack_bf16x2(xh[12], xh[13]),
+                                 pack_bf16x2(xh[14], xh[15]));
+      if (lane == 0) a.rstd[m] = rstd;
+    }
+  }
+}
+
+// d_hidden [rows, 1024] fp32 -> bf16 GEMM operand, and d_bias[o] += sum_m d_hidden[m, o] (nullable).  One CTA walks rows
+// blockIdx.x, + gridDim.x, ...; thread t owns columns 4t .. 4t+3.
+__global__ void __launch_bounds__(256) featproj_bwd_prep_kernel(const float* __restrict__ dh, __nv_bfloat16* __restrict__ dhb,
+                                                                float* __restrict__ dbias, long long rows) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long m = blockIdx.x; m < rows; m += gridDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(dh + m * 1024) + threadIdx.x);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    reinterpret_cast<uint2*>(dhb + m * 1024)[threadIdx.x] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+  if (dbias != nullptr) {
+    atomicAdd(dbias + 4 * threadIdx.x, acc.x);
+    atomicAdd(dbias + 4 * threadIdx.x + 1, acc.y);
+    atomicAdd(dbias + 4 * threadIdx.x + 2, acc.z);
+    atomicAdd(dbias + 4 * threadIdx.x + 3, acc.w);
+  }
+}
+
+// projection.weight [1024 o, 512 c] fp32 -> bf16 copy (forward B operand, K = c) and its transpose [512 c, 1024 o] (the
+// data-gradient GEMM's B operand, K = o)
+__global__ void featproj_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w16,
+                                     __nv_bfloat16* __restrict__ wt16) {
+  const int o = blockIdx.x;
+  for (int c = threadIdx.x; c < kC; c += blockDim.x) {
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[static_cast<size_t>(o) * kC + c]);
+    w16[static_cast<size_t>(o) * kC + c] = v;
+    wt16[static_cast<size_t>(c) * 1024 + o] = v;
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -2304,10 +2484,10 @@ int make_tmap_a(CUtensorMap* m, const void* act_prev, int64_t rows_prev, int str
 }
 
 // B operand: packed weights [512, K] bf16, box = 256 output channels x 64 K
-int make_tmap_w(CUtensorMap* m, const void* w_packed, int K, int box_rows = kUmmaN) {
+int make_tmap_w(CUtensorMap* m, const void* w_packed, int K, int box_rows = kUmmaN, int n_rows = kC) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return NRSE_ERR_CUDA;
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(kC)};
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(n_rows)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
   const cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
@@ -2318,11 +2498,11 @@ int make_tmap_w(CUtensorMap* m, const void* w_packed, int K, int box_rows = kUmm
 }
 
 // plain row-major [rows, 512] bf16 tensor, box = 64 channels x box_rows rows
-int make_tmap_rows(CUtensorMap* m, const void* ptr, int64_t rows, int box_rows) {
+int make_tmap_rows(CUtensorMap* m, const void* ptr, int64_t rows, int box_rows, int cols = kC) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return NRSE_ERR_CUDA;
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kC), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kC) * 2};
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
   const cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -2655,6 +2835,7 @@ static int layer_fwd_impl(const void* act_prev, int64_t rows_prev, const void* w
   g.xhat = xhat;
   g.rstd = rstd;
   g.mode = 0;
+  g.a_wide = 0; g.n_split = 1; g.out_pitch = kC; g.bias = nullptr;
   g.a_2d = 0;
   g.a_row_off[0] = g.a_row_off[1] = 0;
   g.out_row_mul = 1;
@@ -2782,6 +2963,7 @@ int nrse_ln_gelu_bwd(const void* dout, int dout_dtype, int dout_pitch, const voi
   a.rstd = rstd; a.gamma = gamma; a.beta = beta;
   a.dz = reinterpret_cast<__nv_bfloat16*>(dz);
   a.dgamma = dgamma; a.dbeta = dbeta; a.rows = rows; a.P = P; a.T = T;
+  a.dz_f32 = 0; a.dz_P = P;
   const long long want = ceil_div(static_cast<long long>(rows), static_cast<long long>(kLnBwdWarps));
   const unsigned grid = static_cast<unsigned>(want < 4 * kNumSMs ? want : 4 * kNumSMs);
   cudaStream_t s = as_stream(stream);
@@ -2844,16 +3026,14 @@ int nrse_conv_layer0_gn_bwd(const float* x, const void* dout0, const void* xhat0
   return NRSE_OK;
 }
 
-/* dW += dZ^T A.  dz [rows_out, 512] bf16, act_prev [2*rows_out, 512] bf16; dW fp32 [512, k*512] in the packed K order
- * (tap*512 + c), or with ckpt_layout the checkpoint layout [512, 512, k]. */
-int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out, int k, float* dw, int ckpt_layout,
-                          nrse_stream_t stream) {
+/* dW[n, kk] += sum_m G[m, n] X[m, kk]: G [rows, N] bf16, X addressed by a (512, stride, rows) map, N % 128 == 0, K % 256 == 0 */
+static int launch_wgrad(const void* g_rows, int N, const void* x_rows, int64_t x_rows_total, int stride, int64_t rows,
+                        int K, float* dw, int ckpt, nrse_stream_t stream) {
   using namespace nrse;
-  if (!dz || !act_prev || !dw || rows_out < 1 || (k != 2 && k != 3)) return NRSE_ERR_INVALID_ARG;
   CUtensorMap tg, tx;
-  int rc = make_tmap_rows(&tg, dz, rows_out, kWgKm);
+  int rc = make_tmap_rows(&tg, g_rows, rows, kWgKm, N);
   if (rc != NRSE_OK) return rc;
-  rc = make_tmap_a(&tx, act_prev, 2 * rows_out, 2, kWgKm);
+  rc = make_tmap_a(&tx, x_rows, x_rows_total, stride, kWgKm);
   if (rc != NRSE_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -2862,11 +3042,11 @@ int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out
   }
   WgradArgs g;
   g.dw = dw;
-  g.ckpt = ckpt_layout ? 1 : 0;
-  g.K = k * kC;
-  g.stride = 2;
-  g.n_stages = static_cast<int>(ceil_div(rows_out, static_cast<int64_t>(kWgKm)));
-  const int tiles = 4 * (g.K / 256);
+  g.ckpt = ckpt;
+  g.K = K;
+  g.stride = stride;
+  g.n_stages = static_cast<int>(ceil_div(rows, static_cast<int64_t>(kWgKm)));
+  const int tiles = (N / 128) * (K / 256);
   int split = kNumSMs / tiles;
   if (split > g.n_stages) split = g.n_stages;
   if (split < 1) split = 1;
@@ -2874,6 +3054,14 @@ int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out
   conv_wgrad_kernel<<<tiles * split, kWgThreads, kWgSmemBytes, as_stream(stream)>>>(tg, tx, g);
   NRSE_CHECK_LAUNCH();
   return NRSE_OK;
+}
+
+/* dW += dZ^T A.  dz [rows_out, 512] bf16, act_prev [2*rows_out, 512] bf16; dW fp32 [512, k*512] in the packed K order
+ * (tap*512 + c), or with ckpt_layout the checkpoint layout [512, 512, k]. */
+int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out, int k, float* dw, int ckpt_layout,
+                          nrse_stream_t stream) {
+  if (!dz || !act_prev || !dw || rows_out < 1 || (k != 2 && k != 3)) return NRSE_ERR_INVALID_ARG;
+  return launch_wgrad(dz, nrse::kC, act_prev, 2 * rows_out, 2, rows_out, k * nrse::kC, dw, ckpt_layout ? 1 : 0, stream);
 }
 
 /* dX [2*rows_out, 512] bf16 = dZ W (transposed convolution, stride 2) as two GEMMs over even / odd input frames. */
@@ -2897,6 +3085,7 @@ int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even,
     g.stride = 2;
     g.xhat = nullptr; g.rstd = nullptr;
     g.mode = 1;
+    g.a_wide = 0; g.n_split = 1; g.out_pitch = kC; g.bias = nullptr;
     g.a_2d = 1;
     g.a_row_off[0] = 0;    // even: tap 0 <- dZ[m];  odd: tap 1 <- dZ[m]
     g.a_row_off[1] = -1;   // even, k = 3: tap 2 <- dZ[m - 1]
@@ -2978,6 +3167,161 @@ int nrse_conv_frontend_bwd(const float* x, const nrse_frontend_params* prm, cons
       if (rc != NRSE_OK) return rc;
     }
   }
+  return NRSE_OK;
+}
+
+
+/* ---- feature projection ----------------------------------------------------------------------------- */
+int nrse_feature_projection_pack(const float* w, void* w_bf16, void* wt_bf16, nrse_stream_t stream) {
+  using namespace nrse;
+  if (!w || !w_bf16 || !wt_bf16) return NRSE_ERR_INVALID_ARG;
+  featproj_pack_kernel<<<1024, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(w_bf16),
+                                                            reinterpret_cast<__nv_bfloat16*>(wt_bf16));
+  NRSE_CHECK_LAUNCH();
+  return NRSE_OK;
+}
+
+static size_t featproj_rows_bytes(int64_t rows, int cols, int elem) {
+  return nrse::round_up(static_cast<size_t>(rows) * cols * elem, static_cast<size_t>(1024));
+}
+
+/* tape: xn bf16 [rows, 512] | xhat bf16 [rows, 512] | rstd f32 [rows] */
+size_t nrse_feature_projection_tape_bytes(int64_t rows) {
+  return rows < 1 ? 0 : 2 * featproj_rows_bytes(rows, 512, 2) + featproj_rows_bytes(rows, 1, 4);
+}
+
+int nrse_feature_projection_fwd(const void* feats, int feats_dtype, int B, int T, int feats_pitch, const float* ln_gamma,
+                                const float* ln_beta, float eps, const void* w_bf16, const float* bias, float* hidden,
+                                float* norm_hidden, void* tape, int training, nrse_stream_t stream) {
+  using namespace nrse;
+  if (!feats || !ln_gamma || !ln_beta || !w_bf16 || !bias || !hidden || !tape || B < 1 || T < 1 || feats_pitch < T)
+    return NRSE_ERR_INVALID_ARG;
+  if (feats_dtype != NRSE_DTYPE_F32 && feats_dtype != NRSE_DTYPE_BF16) return NRSE_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(tape) & 1023u) || (reinterpret_cast<uintptr_t>(feats) & 15u) ||
+      (reinterpret_cast<uintptr_t>(hidden) & 31u) || (reinterpret_cast<uintptr_t>(w_bf16) & 15u) ||
+      (reinterpret_cast<uintptr_t>(bias) & 15u))
+    return NRSE_ERR_INVALID_ARG;
+  const int64_t rows = static_cast<int64_t>(B) * T;
+  char* tp = reinterpret_cast<char*>(tape);
+  FeatLnArgs a;
+  a.feats = feats; a.feats_f32 = feats_dtype == NRSE_DTYPE_F32 ? 1 : 0; a.feats_pitch = feats_pitch;
+  a.gamma = ln_gamma; a.beta = ln_beta; a.eps = eps;
+  a.xn = reinterpret_cast<__nv_bfloat16*>(tp);
+  a.norm_out = norm_hidden;
+  a.xhat = training ? reinterpret_cast<__nv_bfloat16*>(tp + featproj_rows_bytes(rows, 512, 2)) : nullptr;
+  a.rstd = training ? reinterpret_cast<float*>(tp + 2 * featproj_rows_bytes(rows, 512, 2)) : nullptr;
+  a.B = B; a.T = T;
+  const long long want = ceil_div(static_cast<long long>(rows), 8ll);
+  featproj_ln_kernel<<<static_cast<unsigned>(want < 4 * kNumSMs ? want : 4 * kNumSMs), 256, 0, as_stream(stream)>>>(a);
+  NRSE_CHECK_LAUNCH();
+  CUtensorMap ta, tw, to;
+  int rc = make_tmap_rows(&ta, a.xn, rows, kBlockM);
+  if (rc != NRSE_OK) return rc;
+  rc = make_tmap_w(&tw, w_bf16, kC, kUmmaN, 1024);
+  if (rc != NRSE_OK) return rc;
+  rc = make_tmap_out(&to, a.xn, rows);  // unused by mode 2 (fp32 row-owner stores); any valid map
+  if (rc != NRSE_OK) return rc;
+  GemmArgs g;
+  g.exp_flags = 0;
+  g.gamma = nullptr; g.beta = nullptr; g.out = hidden; g.out_f32 = 1;
+  g.M_total = static_cast<int>(rows);
+  g.n_split = 2;
+  g.num_tiles = static_cast<int>(ceil_div(rows, static_cast<int64_t>(kBlockM))) * g.n_split;
+  g.k_stages = kC / kBlockK;
+  g.stride = 1;
+  g.xhat = nullptr; g.rstd = nullptr;
+  g.mode = 2;
+  g.a_2d = 1; g.a_wide = 1;
+  g.a_row_off[0] = g.a_row_off[1] = 0;
+  g.out_row_mul = 1; g.out_row_add = 0;
+  g.out_pitch = 1024;
+  g.bias = bias;
+  g.a_ptr = reinterpret_cast<const char*>(a.xn);
+  g.a_rows = rows;
+  g.l2_prefetch = 0;
+  g.reverse = 0;
+  return g_variant >= 2 ? launch_gemm<2>(ta, tw, to, g, as_stream(stream)) : launch_gemm<1>(ta, tw, to, g, as_stream(stream));
+}
+
+/* workspace: d_hidden as bf16 [rows, 1024] | dxn bf16 [rows, 512] */
+size_t nrse_feature_projection_bwd_workspace_bytes(int64_t rows) {
+  return rows < 1 ? 0 : featproj_rows_bytes(rows, 1024, 2) + featproj_rows_bytes(rows, 512, 2);
+}
+
+int nrse_feature_projection_bwd(const float* d_hidden, const void* tape, const float* ln_gamma, const float* ln_beta,
+                                const void* wt_bf16, float* d_feats, float* d_ln_gamma, float* d_ln_beta, float* d_w,
+                                float* d_bias, void* workspace, int64_t rows, nrse_stream_t stream) {
+  using namespace nrse;
+  if (!d_hidden || !tape || !ln_gamma || !ln_beta || !wt_bf16 || !workspace || rows < 1 || rows > (1ll << 30))
+    return NRSE_ERR_INVALID_ARG;
+  if ((d_ln_gamma == nullptr) != (d_ln_beta == nullptr)) return NRSE_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(tape) | reinterpret_cast<uintptr_t>(workspace)) & 1023u) return NRSE_ERR_INVALID_ARG;
+  if (reinterpret_cast<uintptr_t>(d_hidden) & 15u) return NRSE_ERR_INVALID_ARG;
+  const char* tp = reinterpret_cast<const char*>(tape);
+  const __nv_bfloat16* xn = reinterpret_cast<const __nv_bfloat16*>(tp);
+  const __nv_bfloat16* xhat = reinterpret_cast<const __nv_bfloat16*>(tp + featproj_rows_bytes(rows, 512, 2));
+  const float* rstd = reinterpret_cast<const float*>(tp + 2 * featproj_rows_bytes(rows, 512, 2));
+  __nv_bfloat16* dhb = reinterpret_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* dxn = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(workspace) + featproj_rows_bytes(rows, 1024, 2));
+  cudaStream_t s = as_stream(stream);
+  featproj_bwd_prep_kernel<<<static_cast<unsigned>(rows < 2 * kNumSMs ? rows : 2 * kNumSMs), 256, 0, s>>>(d_hidden, dhb, d_bias,
+                                                                                                            rows);
+  NRSE_CHECK_LAUNCH();
+  int rc;
+  if (d_w != nullptr) {  // dW[o, c] += sum_m dH[m, o] xn[m, c]: projection.weight's own [1024, 512] layout
+    rc = launch_wgrad(dhb, 1024, xn, rows, 1, rows, kC, d_w, 0, stream);
+    if (rc != NRSE_OK) return rc;
+  }
+  if (d_feats == nullptr && d_ln_gamma == nullptr) return NRSE_OK;
+  {  // dxn[m, c] = sum_o dH[m, o] W[o, c]
+    CUtensorMap ta, tw, to;
+    rc = make_tmap_rows(&ta, dhb, rows, kBlockM, 1024);
+    if (rc != NRSE_OK) return rc;
+    rc = make_tmap_w(&tw, wt_bf16, 1024);
+    if (rc != NRSE_OK) return rc;
+    rc = make_tmap_out(&to, dxn, rows);
+    if (rc != NRSE_OK) return rc;
+    GemmArgs g;
+    g.exp_flags = 0;
+    g.gamma = nullptr; g.beta = nullptr; g.out = dxn; g.out_f32 = 0;
+    g.M_total = static_cast<int>(rows);
+    g.n_split = 1;
+    g.num_tiles = static_cast<int>(ceil_div(rows, static_cast<int64_t>(kBlockM)));
+    g.k_stages = 1024 / kBlockK;
+    g.stride = 1;
+    g.xhat = nullptr; g.rstd = nullptr;
+    g.mode = 1;
+    g.a_2d = 1; g.a_wide = 1;
+    g.a_row_off[0] = g.a_row_off[1] = 0;
+    g.out_row_mul = 1; g.out_row_add = 0;
+    g.out_pitch = kC;
+    g.bias = nullptr;
+    g.a_ptr = reinterpret_cast<const char*>(dhb);
+    g.a_rows = rows;
+    g.l2_prefetch = 0;
+    g.reverse = 0;
+    rc = g_variant >= 2 ? launch_gemm<2>(ta, tw, to, g, s) : launch_gemm<1>(ta, tw, to, g, s);
+    if (rc != NRSE_OK) return rc;
+  }
+  // LayerNorm backward: dxn -> d_feats (fp32, compact rows), d_ln_gamma / d_ln_beta accumulated
+  LnBwdArgs a;
+  a.dout = dxn; a.dout_f32 = 0; a.dout_P = 1;
+  a.xhat = xhat; a.rstd = rstd; a.gamma = ln_gamma; a.beta = ln_beta;
+  // without d_feats the kernel still needs somewhere to put dZ: dxn itself (bf16, in place)
+  a.dz = d_feats != nullptr ? reinterpret_cast<__nv_bfloat16*>(d_feats) : dxn;
+  a.dz_f32 = d_feats != nullptr ? 1 : 0;
+  a.dz_P = 1;
+  a.dgamma = d_ln_gamma; a.dbeta = d_ln_beta; a.rows = rows; a.P = 1; a.T = 1;
+  const long long want = ceil_div(static_cast<long long>(rows), static_cast<long long>(kLnBwdWarps));
+  const unsigned grid = static_cast<unsigned>(want < 4 * kNumSMs ? want : 4 * kNumSMs);
+  static bool attr_set = false;  // benign race: idempotent attribute
+  if (!attr_set) {
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kLnRingBytes));
+    attr_set = true;
+  }
+  ln_gelu_bwd_kernel<false, true, false><<<grid, kLnBwdThreads, kLnRingBytes, s>>>(a);
+  NRSE_CHECK_LAUNCH();
   return NRSE_OK;
 }
 

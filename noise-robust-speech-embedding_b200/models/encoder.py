@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 from transformers import AutoModel, WavLMConfig, WavLMModel
 
+from .featproj import B200FeatureProjection
 from .frontend import B200FeatureEncoder
 
 
@@ -68,8 +69,11 @@ def install_sync_free_spec_augment(model: nn.Module) -> nn.Module:
 
 
 def install_b200_frontend(model: nn.Module) -> nn.Module:
-    """Swap ``model.feature_extractor`` (HF WavLMFeatureEncoder) for the B200 implementation, in place."""
+    """Swap ``model.feature_extractor`` (HF WavLMFeatureEncoder) for the B200 implementation, in place, and -- for the
+    wavlm-large geometry (512 -> 1024) -- ``model.feature_projection`` too; other sizes keep HF's."""
     B200FeatureEncoder.convert(model.feature_extractor)
+    if B200FeatureProjection.supports(getattr(model, "feature_projection", None)):
+        B200FeatureProjection.convert(model.feature_projection)
     return model
 
 

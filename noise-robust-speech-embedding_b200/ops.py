@@ -890,3 +890,84 @@ def conv_layer0_wgrad(x: Tensor, dz0: Tensor, T0: int, P0: int) -> Tensor:
     dw0 = torch.zeros(512, 10, dtype=torch.float32, device=x.device)
     check(lib.nrse_conv_layer0_wgrad(_ptr(x), _ptr(dz0), _ptr(dw0), B, L, T0, P0, _stream()), "nrse_conv_layer0_wgrad")
     return dw0
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Feature projection: LayerNorm(512) + Linear(512 -> 1024)  (hf:models/wavlm/modeling_wavlm.py:93-105)
+# --------------------------------------------------------------------------------------------------------------
+def pack_feature_projection(weight: Tensor) -> Tuple[Tensor, Tensor]:
+    """projection.weight [1024, 512] fp32 -> (bf16 copy, bf16 transpose [512, 1024]): forward / backward GEMM operands."""
+    _need_cuda(weight)
+    if tuple(weight.shape) != (1024, 512):
+        raise NrseError("pack_feature_projection expects projection.weight of shape [1024, 512]")
+    w = weight.detach().contiguous().float()
+    w16 = torch.empty(1024, 512, dtype=torch.bfloat16, device=w.device)
+    wt16 = torch.empty(512, 1024, dtype=torch.bfloat16, device=w.device)
+    check(_lib.load().nrse_feature_projection_pack(_ptr(w), _ptr(w16), _ptr(wt16), _stream()), "nrse_feature_projection_pack")
+    return w16, wt16
+
+
+def _channels_last_rows(x: Tensor) -> Tuple[Tensor, int]:
+    """[B, T, 512] -> (tensor whose frames (b, t) sit at row b * pitch + t of a dense [.., 512] buffer, pitch): the conv
+    frontend hands out a [B, T, 512] view of its pitched [B, P, 512] output, which is read in place."""
+    B, T, Cc = x.shape
+    if x.stride(2) == 1 and x.stride(1) == Cc and x.stride(0) % Cc == 0 and x.stride(0) >= T * Cc and \
+            x.data_ptr() % 16 == 0:
+        return x, x.stride(0) // Cc
+    return x.contiguous(), T
+
+
+def feature_projection_fwd(feats: Tensor, ln_weight: Tensor, ln_bias: Tensor, eps: float, w16: Tensor, bias: Tensor,
+                           training: bool, want_norm: bool = True) -> Tuple[Tensor, Optional[Tensor], Tensor]:
+    """feats [B, T, 512] (fp32 / bf16, channels-last; a pitched view is read in place) -> (hidden [B, T, 1024] fp32,
+    norm_hidden [B, T, 512] fp32 | None, tape)."""
+    lib = _lib.load()
+    _need_cuda(feats, w16)
+    if feats.dim() != 3 or feats.shape[2] != 512:
+        raise NrseError("feature_projection_fwd expects [B, T, 512] channels-last conv features")
+    if feats.dtype not in (torch.float32, torch.bfloat16):
+        feats = feats.float()
+    x, pitch = _channels_last_rows(feats)
+    B, T, _ = x.shape
+    rows = B * T
+    hidden = torch.empty(B, T, 1024, dtype=torch.float32, device=x.device)
+    norm = torch.empty(B, T, 512, dtype=torch.float32, device=x.device) if want_norm else None
+    tape = torch.empty(lib.nrse_feature_projection_tape_bytes(rows) + 1024, dtype=torch.uint8, device=x.device)
+    tp, _ = _aligned(tape)
+    check(lib.nrse_feature_projection_fwd(_ptr(x), _dtype_code(x), B, T, pitch, _ptr(ln_weight.detach().contiguous().float()),
+                                          _ptr(ln_bias.detach().contiguous().float()), float(eps), _ptr(w16),
+                                          _ptr(bias.detach().contiguous().float()), _ptr(hidden), _ptr(norm),
+                                          C.c_void_p(tp), 1 if training else 0, _stream()), "nrse_feature_projection_fwd")
+    return hidden, norm, tape
+
+
+def feature_projection_bwd(d_hidden: Tensor, tape: Tensor, ln_weight: Tensor, ln_bias: Tensor, wt16: Tensor,
+                           need_feats: bool = True, need_ln: bool = True, need_w: bool = True, need_bias: bool = True):
+    """Backward of ``feature_projection_fwd(training=True)``: d_hidden [B, T, 1024] -> (d_feats [B, T, 512] fp32 | None,
+    d_ln_weight, d_ln_bias, d_weight [1024, 512], d_bias [1024]); entries not asked for are None and cost nothing."""
+    lib = _lib.load()
+    B, T, _ = d_hidden.shape
+    rows = B * T
+    dev = d_hidden.device
+    dh = d_hidden.contiguous().float()
+    d_feats = torch.empty(B, T, 512, dtype=torch.float32, device=dev) if need_feats else None
+    n_acc = (1024 if need_ln else 0) + (1024 * 512 if need_w else 0) + (1024 if need_bias else 0)
+    flat = torch.zeros(max(n_acc, 4), dtype=torch.float32, device=dev)  # the kernels accumulate
+    off = 0
+    d_g = d_b = d_w = d_bias = None
+    if need_ln:
+        d_g, d_b = flat[0:512], flat[512:1024]
+        off = 1024
+    if need_w:
+        d_w = flat[off:off + 1024 * 512].view(1024, 512)
+        off += 1024 * 512
+    if need_bias:
+        d_bias = flat[off:off + 1024]
+    ws = _workspace(lib.nrse_feature_projection_bwd_workspace_bytes(rows), dev)
+    wp, _ = _aligned(ws)
+    tp, _ = _aligned(tape)
+    check(lib.nrse_feature_projection_bwd(_ptr(dh), C.c_void_p(tp), _ptr(ln_weight.detach().contiguous().float()),
+                                          _ptr(ln_bias.detach().contiguous().float()), _ptr(wt16), _ptr(d_feats), _ptr(d_g),
+                                          _ptr(d_b), _ptr(d_w), _ptr(d_bias), C.c_void_p(wp), rows, _stream()),
+          "nrse_feature_projection_bwd")
+    return d_feats, d_g, d_b, d_w, d_bias

@@ -15,7 +15,7 @@ copied.  Shims, all explicit below:
 Outputs (float arrays kept small; inputs are stored too so fixtures are self-contained):
   mix_byol.npz, mix_emotion.npz, mix_edge.npz, byol_loss.npz, ema.npz, frontend_layer.npz,
   frontend_group.npz, byol_step.npz, byol_state_dict_keys.json, optim_step.npz,
-  emotion.npz, emotion_state_dict_keys.json, evaluate_byol.npz
+  emotion.npz, emotion_state_dict_keys.json, evaluate_byol.npz, feature_projection.npz
 """
 import os
 import random
@@ -350,6 +350,55 @@ def gen_evaluate_byol(seed=81, n_batches=3, B=4, L=4000):
         ref_encoder_mod.WavLMEncoder.forward = orig_fwd
 
 
+def featproj_wavlm_config():
+    """wavlm-large's conv stack AND feature projection (512 -> 1024); one tiny transformer layer behind it."""
+    cfg = WavLMConfig(hidden_size=1024, num_hidden_layers=1, num_attention_heads=16, intermediate_size=64,
+                      feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=False,
+                      num_conv_pos_embeddings=16, num_conv_pos_embedding_groups=4)
+    for k in ("hidden_dropout", "activation_dropout", "attention_dropout", "feat_proj_dropout", "final_dropout",
+              "layerdrop", "mask_time_prob", "mask_feature_prob"):
+        setattr(cfg, k, 0.0)
+    cfg.apply_spec_augment = False
+    return cfg
+
+
+def gen_feature_projection(seed=91, B=2, L=6000):
+    """Through the reference's ``WavLMEncoder`` (ref:src/models/encoder.py:5-32): the outputs of
+    ``model.feature_projection`` (hf:models/wavlm/modeling_wavlm.py:93-105; captured with a forward hook), the encoder's
+    ``last_hidden_state``, and the autograd gradients of the feature projection's parameters and of the last conv
+    layer's weight for the loss sum(last_hidden_state * G)."""
+    cfg = featproj_wavlm_config()
+    orig = ref_encoder_mod.AutoModel.from_pretrained
+    ref_encoder_mod.AutoModel.from_pretrained = staticmethod(lambda name: WavLMModel(cfg))
+    try:
+        torch.manual_seed(seed)
+        enc = ref_encoder_mod.WavLMEncoder("shim")
+    finally:
+        ref_encoder_mod.AutoModel.from_pretrained = orig
+    x = synthetic.waveforms(B, L, seed=seed)[0]
+    x = ((x - x.mean(1, keepdims=True)) / x.std(1, keepdims=True)).astype(np.float32)
+    captured = {}
+    h = enc.model.feature_projection.register_forward_hook(lambda m, i, o: captured.update(hidden=o[0], norm=o[1]))
+    enc.train()  # dropout / layerdrop / SpecAugment are zero in this config: deterministic
+    for p in enc.parameters():
+        p.requires_grad_(True)
+    y = enc(torch.from_numpy(x)[:, None])
+    h.remove()
+    G = torch.from_numpy(np.random.RandomState(seed).standard_normal(tuple(y.shape)).astype(np.float32))
+    (y * G).sum().backward()
+    fp = enc.model.feature_projection
+    out = {"x": x, "seed": np.array(seed), "G": G.numpy(), "hidden": captured["hidden"].detach().numpy(),
+           "norm": captured["norm"].detach().numpy(), "last_hidden": y.detach().numpy(),
+           "d_ln_weight": fp.layer_norm.weight.grad.numpy(), "d_ln_bias": fp.layer_norm.bias.grad.numpy(),
+           "d_proj_bias": fp.projection.bias.grad.numpy(),
+           "d_proj_weight_rows": fp.projection.weight.grad.numpy()[::64].copy(),      # 16 of the 1024 rows
+           "d_conv6_weight_rows": enc.model.feature_extractor.conv_layers[6].conv.weight.grad.numpy()[::64].copy(),
+           "d_conv0_weight": enc.model.feature_extractor.conv_layers[0].conv.weight.grad.numpy()}
+    np.savez_compressed(os.path.join(HERE, "feature_projection.npz"), **out)
+    print("feature_projection: hidden", tuple(captured["hidden"].shape), "last_hidden", tuple(y.shape),
+          "|d_proj_weight|", float(fp.projection.weight.grad.abs().mean()))
+
+
 OPTIM_GRAD_SCALES = (3e-2, 1e-2, 1e-4)
 
 
@@ -494,4 +543,5 @@ if __name__ == "__main__":
     gen_optim_step()
     gen_emotion()
     gen_evaluate_byol()
+    gen_feature_projection()
     print("sizes:", {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")})

@@ -213,3 +213,28 @@ def test_attentive_pooling_and_ccc_match_reference(golden):
     c = compute_ccc(g["ccc_pred"][:, 0], g["ccc_targ"][:, 0])
     assert abs((1 - c) - float(oracle.ccc_loss(torch.from_numpy(g["ccc_pred"][:, :1]),
                                                torch.from_numpy(g["ccc_targ"][:, :1])))) < 1e-6
+
+
+def featproj_wavlm_config():
+    """The configuration tests/golden/make_golden.py::gen_feature_projection used."""
+    from transformers import WavLMConfig
+    cfg = WavLMConfig(hidden_size=1024, num_hidden_layers=1, num_attention_heads=16, intermediate_size=64,
+                      feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=False,
+                      num_conv_pos_embeddings=16, num_conv_pos_embedding_groups=4)
+    for k in ("hidden_dropout", "activation_dropout", "attention_dropout", "feat_proj_dropout", "final_dropout",
+              "layerdrop", "mask_time_prob", "mask_feature_prob"):
+        setattr(cfg, k, 0.0)
+    cfg.apply_spec_augment = False
+    return cfg
+
+
+def test_feature_projection_fixture_matches_installed_transformers(golden):
+    """The fixture written through the reference's WavLMEncoder equals the installed transformers classes on the same
+    seeded weights (the GPU box has the same transformers: the seeded init is reproducible there)."""
+    from transformers import WavLMModel
+    g = golden("feature_projection")
+    torch.manual_seed(int(g["seed"]))
+    model = WavLMModel(featproj_wavlm_config()).train()
+    out = model(torch.from_numpy(g["x"]))
+    assert rel_err(out.last_hidden_state.detach().numpy(), g["last_hidden"]) < 1e-5
+    assert rel_err(out.extract_features.detach().numpy(), g["norm"]) < 1e-5
