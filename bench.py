@@ -261,6 +261,31 @@ def main_gpu(args):
     raw_d = {k: v.to(dev) for k, v in raw_h.items()}
     clean_d, noise_d, snr_d = raw_d["clean_wave"], raw_d["noise_wave"], raw_d["snr_idx"]
 
+    if args.train_only:  # tuning runs of the training-step leg alone
+        def timed_only(fn, steps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                out = fn()
+            e1.record()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()), out
+        res = train_step_leg(args, dev, world, rank, layers, raw_d, snr_table, timed_only)
+        if rank == 0:
+            print(json.dumps({"train_step": res}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
     # ---- the module surface a user of the reference calls (INTEGRATION.md level 1) -------------------------------------
     # GpuBatchMixer = the GPU half of NoiseRobustSpeechDataset.__getitem__ (mix + peak-norm + z-norm with the reference's
     # retry policy on the device); B200FeatureEncoder = WavLMModel.feature_extractor.  One encoder serves both views here:
@@ -437,6 +462,7 @@ def train_step_leg(args, dev, world, rank, layers, raw_d, snr_table, timed):
     heads' and the frontend's backward; the frontend + heads group follows the backward and is the un-overlappable tail."""
     import torch.distributed as dist
 
+    from nrse_b200 import ops
     from nrse_b200.data import GpuBatchMixer
     from nrse_b200.models import B200FeatureEncoder, PredictionHead, ProjectionHead, byol_loss, wavlm_large_config
     from nrse_b200.train import FusedAdamWEma, GradArena
@@ -456,7 +482,9 @@ def train_step_leg(args, dev, world, rank, layers, raw_d, snr_table, timed):
         for shape in wavlm_large_ballast_shapes():
             ballast.append(torch.nn.Parameter(torch.randn(shape, device=dev) * 0.02))
             ballast_twin.append(ballast[-1].detach().clone())
-    arena = GradArena([ballast, hot] if ballast else [hot])
+    arena = GradArena([ballast, hot] if ballast else [hot], bucket_bytes=args.train_bucket_mb << 20,
+                      multimem={"auto": "auto", "multimem": True, "nccl": False}[args.train_allreduce_impl],
+                      multimem_ctas=args.train_multimem_ctas)
     g_ballast, g_hot = (0, 1) if ballast else (None, 0)
     if ballast:
         arena.flat[:arena.group_ranges[0][1]].normal_(0.0, 1e-4)  # the transformer's gradients: constant synthetic values
@@ -475,12 +503,19 @@ def train_step_leg(args, dev, world, rank, layers, raw_d, snr_table, timed):
         with torch.no_grad():
             tproj = target_proj(target_fe(batch["noisy_input_values"]).mean(dim=2))
         loss = byol_loss(pred, tproj)
-        if sync and g_ballast is not None:
+        overlap = sync and world > 1
+        if overlap and g_ballast is not None:
+            # the persistent conv kernels leave a few SMs to NCCL while the collective is in flight (a machine filled
+            # with one resident CTA per SM would make NCCL's kernels wait for the end of every kernel)
+            if args.train_sm_reserve:
+                ops.set_sm_budget(148 - args.train_sm_reserve)
             arena.all_reduce_async(g_ballast)   # travels while the backward below computes
         loss.backward()
-        if sync:
+        if overlap:
             arena.all_reduce_async(g_hot)
             arena.wait()
+            if args.train_sm_reserve:
+                ops.set_sm_budget(148)
         opt.step()
         return loss
 
@@ -507,7 +542,8 @@ def train_step_leg(args, dev, world, rank, layers, raw_d, snr_table, timed):
         "allreduce_exposed_ms": (ms_sync - ms_nosync) / steps if world > 1 else 0.0,
         "ms_per_step_no_allreduce_runs": [ms_a / steps, ms_b / steps],
         "allreduce_bytes_per_rank": arena.numel * 4 if world > 1 else 0, "allreduce_collectives_per_step": n_coll,
-        "allreduce_dtype": "f32", "bucket_bytes": arena.bucket_elems * 4, "world": world,
+        "allreduce_dtype": "f32", "allreduce_impl": arena.impl, "bucket_bytes": arena.bucket_elems * 4, "world": world,
+        "sm_reserved_for_nccl": args.train_sm_reserve if world > 1 else 0,
         "trainable_params": n_hot + n_ballast, "hot_path_params": n_hot, "ema_params": sum(t.numel() for _, t in ema_pairs),
         "batch_per_gpu": BATCH, "n_samples": N_SAMPLES, "loss": float(loss.item()),
         "gpu_launches_per_step": launches,
@@ -762,6 +798,14 @@ def main():
     ap.add_argument("--sustain-seconds", type=float, default=2.5,
                     help="length of the second, sustained timed region of the device-resident loop (0 = skip)")
     ap.add_argument("--no-train-step", action="store_true", help="skip the hot-path training-step leg")
+    ap.add_argument("--train-only", action="store_true", help="only the training-step leg (tuning runs; not a bench line)")
+    ap.add_argument("--train-sm-reserve", type=int, default=32,
+                    help="SMs the conv kernels leave to NCCL while the gradient all-reduce overlaps the backward (N > 1)")
+    ap.add_argument("--train-bucket-mb", type=int, default=256, help="all-reduce bucket size of the training-step leg")
+    ap.add_argument("--train-allreduce-impl", default="nccl", choices=["auto", "multimem", "nccl"],
+                    help="gradient all-reduce of the training-step leg: this repository's NVSwitch-multicast kernel (auto: "
+                         "when available) or NCCL all-reduce calls")
+    ap.add_argument("--train-multimem-ctas", type=int, default=0, help="CTAs of the multicast all-reduce kernel (0 = 148)")
     ap.add_argument("--train-allreduce", default="full", choices=["full", "hotpath"],
                     help="gradient set of the training-step leg: WavLM-large BYOL's full 326 M parameters (default) or "
                          "only the hot path's own trainable parameters")

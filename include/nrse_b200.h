@@ -298,6 +298,10 @@ int nrse_conv_frontend_set_layer0_variant(int variant);
  * tiles in opposite directions (each layer starts on the rows its producer wrote last, which are still in L2);
  * 0 = every layer first-to-last.  Results do not depend on it. */
 int nrse_conv_frontend_set_tile_order(int alternate);
+/* Number of SMs (8..148, default 148) the persistent kernels of the conv frontend / feature projection spread over.  The
+ * data-parallel training step lowers it while the gradient all-reduce is in flight: NCCL's kernels need SMs of their own,
+ * and a machine filled with one resident persistent CTA per SM would make them wait for the end of every kernel. */
+int nrse_conv_frontend_set_sm_budget(int sms);
 /* 1: the TMA producer of the GEMM layers bulk-prefetches the next tile's input frames into L2 (default 0: measured
  * 2-3 % slower at 64 x 4 s -- the operand feed is not HBM-latency bound). */
 int nrse_conv_frontend_set_l2_prefetch(int on);
@@ -386,6 +390,44 @@ size_t nrse_feature_projection_bwd_workspace_bytes(int64_t rows);
 int nrse_feature_projection_bwd(const float* d_hidden, const void* tape, const float* ln_gamma, const float* ln_beta,
                                 const void* wt_bf16, float* d_feats, float* d_ln_gamma, float* d_ln_beta, float* d_w,
                                 float* d_bias, void* workspace, int64_t rows, nrse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Positional convolution embedding: Conv1d(1024, 1024, k = 128, padding = 64, groups = 16) with
+ * weight-norm over dim 2, last frame dropped, exact GELU; forward and backward.
+ * Replaces WavLMPositionalConvEmbedding.forward, hf:models/wavlm/modeling_wavlm.py:48-90 (the consumer of the feature
+ * projection inside the encoder; reached from ref:src/models/encoder.py:25 and, on the emotion fine-tune step, from
+ * ref:src/models/emotion.py:60-79).  wavlm-large geometry only (hidden 1024, 16 groups, 128 taps).
+ *   pack   v [1024, 64, 128] = conv.parametrizations.weight.original1, g [128] = ...original0  ->  w = g v / ||v||_tap as
+ *          two bf16 GEMM operand packs of nrse_pos_conv_pack_bytes() bytes each (forward; tap-reversed + transposed for the
+ *          data gradient) and normsq [128] fp32 = ||v[:, :, tap]||^2 (kept for the backward).
+ *   fwd    x [B, T, 1024] fp32 contiguous -> y [B, T, 1024] fp32; x_bf16 [B*T, 1024] receives the bf16 operand copy of x
+ *          (the backward's weight gradient reads it again); z_save (nullable) [B*T, 1024] bf16 = the pre-GELU activation.
+ *          One cast launch + one tcgen05 implicit-GEMM launch (no padded copy: the TMA engine zero-fills frames < 0, >= T).
+ *   bwd    d_y [B, T, 1024] fp32 -> d_x (nullable) [B, T, 1024] fp32 written; d_v [1024, 64, 128], d_g [128] (both or
+ *          neither), d_bias [1024] (nullable) ACCUMULATED.  workspace: nrse_pos_conv_bwd_workspace_bytes(B, T), 1024-aligned.
+ * ------------------------------------------------------------------------------------------- */
+size_t nrse_pos_conv_pack_bytes(void);
+int nrse_pos_conv_pack(const float* v, const float* g, void* w_fwd, void* w_bwd, float* normsq, nrse_stream_t stream);
+int nrse_pos_conv_fwd(const float* x, const void* w_fwd, const float* bias, float* y, void* x_bf16, void* z_save, int B, int T,
+                      nrse_stream_t stream);
+size_t nrse_pos_conv_bwd_workspace_bytes(int B, int T);
+int nrse_pos_conv_bwd(const float* d_y, const void* x_bf16, const void* z_save, const void* w_bwd, const float* v,
+                      const float* g, const float* normsq, float* d_x, float* d_v, float* d_g, float* d_bias,
+                      void* workspace, int B, int T, nrse_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gradient all-reduce (mean over ranks) through NVSwitch multicast memory: the one collective of the data-parallel step
+ * (what DistributedDataParallel's all-reduce computes around ref:train_byol.py:66-70).
+ *   multicast_ptr  the MULTICAST address of a symmetric fp32 allocation present on all `world` ranks (host side:
+ *                  torch.distributed._symmetric_memory.rendezvous(...).multicast_ptr)
+ *   elem_offset / numel  the range to reduce (multiples of 4 elements); rank r sums and rewrites the r-th slice of it:
+ *                  multimem.ld_reduce.add (the switch returns the sum over the ranks) -> x 1/world -> multimem.st (the
+ *                  switch stores to every rank).  One launch of <= max_ctas (0 = 148) register-light CTAs that co-reside
+ *                  with the persistent conv kernels running concurrently on another stream.
+ * The caller orders the ranks: a symmetric-memory barrier on `stream` before the launch (every rank's gradients are
+ * written) and after it (every slice is stored). */
+int nrse_multimem_allreduce_mean_f32(void* multicast_ptr, int64_t elem_offset, int64_t numel, int rank, int world,
+                                     int max_ctas, nrse_stream_t stream);
 
 #ifdef __cplusplus
 }

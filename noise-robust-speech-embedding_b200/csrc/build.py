@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnrse_b200.so")
-SOURCES = ["runtime.cu", "check.cu", "mix.cu", "ema.cu", "optim.cu", "pool.cu", "loss.cu", "frontend.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", os.path.join(ROOT, "include", "nrse_b200.h")]
+SOURCES = ["runtime.cu", "check.cu", "mix.cu", "ema.cu", "optim.cu", "pool.cu", "loss.cu", "allreduce.cu", "posconv.cu", "frontend.cu"]
+HEADERS = ["common.cuh", "ptx.cuh", "epilogue_math.cuh", os.path.join(ROOT, "include", "nrse_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

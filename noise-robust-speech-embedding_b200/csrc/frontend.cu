@@ -39,6 +39,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "epilogue_math.cuh"
 #include "ptx.cuh"
 
 // Timing experiments that deliberately produce WRONG results (skipped stores / statistics, redirected outputs) exist only
@@ -76,19 +77,6 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float erf_abs = fmaf(-poly * t, e, 1.0f);  // erf(|x|/sqrt2)
   const float half_x = 0.5f * x;
   return fmaf(fabsf(half_x), erf_abs, half_x);  // 0.5x + 0.5|x| erf(|x|/sqrt2) = 0.5x(1 + erf(x/sqrt2))
-}
-
-// 256-bit global store (STG.256 on sm_100): one full 32-byte sector per thread per instruction; p 32-byte aligned
-__device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
-                                              uint32_t a5, uint32_t a6, uint32_t a7) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
-               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
-               : "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // =========================================================================================================
@@ -433,82 +421,6 @@ struct EpiCtx {
   uint32_t tmem_empty_cluster; // 0: bar_tmem_empty is local; else arrive on this shared::cluster barrier instead
   OutStage ost;             // bf16 output through the staging buffer + TMA store (ost.tmap != nullptr)
 };
-
-// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction) --------------
-typedef unsigned long long f2;
-__device__ __forceinline__ f2 f2_make(float lo, float hi) {
-  f2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ f2 f2_bits(uint32_t lo, uint32_t hi) {
-  f2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_split(f2 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
-  f2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
-  f2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
-  f2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-// Exact (erf) GELU of two values with ONE MUFU each, written in the HALVED argument w = x / 2 (a = |w|):
-//   gelu(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2) = w + a (1 - e),   e = erfc(sqrt2 a) = 2^-q(a),   q(a) = a (c0 + c1 a + ..)
-// q is a fit of -log2 erfc(sqrt2 a) on [0, 2.8] that minimises the absolute error of gelu itself (weight a e ln 2):
-//   NRSE_GELU_DEG 5 (default): quintic q, 5 packed instructions, max |gelu error| 8.7e-7;
-//   NRSE_GELU_DEG 3:           cubic q, 3 packed instructions,  max |gelu error| 8.6e-5 (2 % of a bf16 ulp at 1) -- measured
-//                              no faster on the B200 (the epilogues are not instruction-bound), so unused;
-// tests/test_oracle_golden.py pins both against torch's erf GELU.  q keeps growing beyond the fit range (q(2.8) = 25.6,
-// q(6) > 126), so e flushes to 0 by itself: no clamp.
-// The epilogues are bound by instruction ISSUE (23.5 k warp instructions per 128 x 512 tile at IPC 1.9 before this form),
-// so everything that is not arithmetic on the value is moved out of the per-element path: the factor 1/2 lives in the
-// LayerNorm affine (shared memory holds gamma / 2 and beta / 2 -- exact, a power of two) or in the folded layer-0 operands,
-// |w| is an operand modifier of the packed instructions, relu(x) is never formed (w + a h cancels to -a e for x < 0 with an
-// absolute error below 1e-7 a).  NaN inputs propagate; +-inf is not expected behind a LayerNorm (-inf gives NaN).
-#ifndef NRSE_STATS_SHIFT
-#define NRSE_STATS_SHIFT 1  // 0 (timing experiments only): raw sums in the LayerNorm statistics pass
-#endif
-#ifndef NRSE_GELU_DEG
-#define NRSE_GELU_DEG 5
-#endif
-__device__ __forceinline__ f2 gelu2h(f2 w) {
-  float w0, w1;
-  f2_split(w, w0, w1);
-  const f2 a = f2_make(fabsf(w0), fabsf(w1));
-#define NRSE_F2C(v) f2_make(v, v)
-#if NRSE_GELU_DEG == 3
-  f2 p = f2_fma(a, NRSE_F2C(-0.2210327833890915f), NRSE_F2C(-1.9530425071716309f));
-  p = f2_fma(p, a, NRSE_F2C(-2.281832695007324f));
-#elif NRSE_GELU_DEG == 5
-  f2 p = f2_fma(a, NRSE_F2C(-0.015619270503520966f), NRSE_F2C(0.11517950147390366f));
-  p = f2_fma(p, a, NRSE_F2C(-0.4171730577945709f));
-  p = f2_fma(p, a, NRSE_F2C(-1.838383436203003f));
-  p = f2_fma(p, a, NRSE_F2C(-2.3020009994506836f));
-#else
-#error "NRSE_GELU_DEG must be 3 or 5"
-#endif
-  float q0, q1;
-  f2_split(f2_mul(p, a), q0, q1);  // = -q(a)
-  float e0, e1;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
-  const f2 h = f2_fma(f2_make(e0, e1), NRSE_F2C(-1.0f), NRSE_F2C(1.0f));
-#undef NRSE_F2C
-  return f2_fma(a, h, w);
-}
 
 // kColsDiv = 2 (layer 0 only, statistics supplied by the caller): this thread handles kNPC / 2 columns of its row, the
 // other half belongs to the twin team working on the same accumulator buffer.
@@ -1767,40 +1679,6 @@ struct LnBwdArgs {
   int P, T;
 };
 
-__device__ __forceinline__ void unpack_bf16x8(const uint4& a, float (&x)[8]) {
-  const unsigned w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    x[2 * j] = __uint_as_float(w[j] << 16);
-    x[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
-  }
-}
-
-// gelu'(v) for two values with ONE MUFU each:  for u = |v|,  1 - gelu'(u) = phi(u) (mills(u) - u)  and
-// gelu'(-u) = 1 - gelu'(u);  r(u) = 0.39894 (mills(u) - u) is a degree-6 fit on [0, 5.6] (max abs error of gelu'
-// 2.6e-5, two orders below bf16 resolution), so gelu'(v) = 0.5 + copysign(0.5 - exp(-v^2/2) r(|v|), v).
-__device__ __forceinline__ f2 gelu_grad2(f2 v) {
-  float v0, v1;
-  f2_split(v, v0, v1);
-  const f2 u = f2_make(fminf(fabsf(v0), 5.6f), fminf(fabsf(v1), 5.6f));
-  constexpr float k = 0.3989422804f;
-  f2 r = f2_fma(u, f2_make(k * 0.0016475850716233253f, k * 0.0016475850716233253f),
-                f2_make(k * -0.019207235425710678f, k * -0.019207235425710678f));
-  r = f2_fma(r, u, f2_make(k * 0.09663444012403488f, k * 0.09663444012403488f));
-  r = f2_fma(r, u, f2_make(k * -0.2893761098384857f, k * -0.2893761098384857f));
-  r = f2_fma(r, u, f2_make(k * 0.6104238033294678f, k * 0.6104238033294678f));
-  r = f2_fma(r, u, f2_make(k * -1.9976462125778198f, k * -1.9976462125778198f));
-  r = f2_fma(r, u, f2_make(k * 1.2532488107681274f, k * 1.2532488107681274f));
-  float q0, q1;
-  f2_split(f2_mul(f2_mul(u, u), f2_make(-0.72134752f, -0.72134752f)), q0, q1);  // -u^2/2 * log2(e)
-  float e0, e1;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
-  float h0, h1;
-  f2_split(f2_fma(f2_mul(f2_make(e0, e1), r), f2_make(-1.f, -1.f), f2_make(0.5f, 0.5f)), h0, h1);  // 0.5 - (1 - gelu'(u))
-  return f2_add(f2_make(0.5f, 0.5f), f2_make(copysignf(h0, v0), copysignf(h1, v1)));
-}
-
 // bf16 gradient input (every layer but the last): each warp keeps kLnStages rows in flight with per-lane cp.async copies
 // into its own shared-memory ring (a lane reads back exactly the 64 bytes it copied: no cross-lane synchronisation).
 // With direct loads a warp has one row (2 KB) in flight and, at 128 registers per thread, an SM holds 16 warps: 32 KB in
@@ -1920,8 +1798,7 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
       }
       zrow[lane] = make_uint4(z[0], z[1], z[2], z[3]);
       zrow[32 + lane] = make_uint4(z[4], z[5], z[6], z[7]);
-      continue;
-    }
+    } else {
     f2 dx[8], s1 = zero2, s2 = zero2;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1959,26 +1836,29 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
       zrow[lane] = make_uint4(z[0], z[1], z[2], z[3]);
       zrow[32 + lane] = make_uint4(z[4], z[5], z[6], z[7]);
     }
+    }  // kNorm
   }
   if constexpr (!kDoutF32) cp_async_wait<0>();
-  if (!kNorm || a.dgamma == nullptr) return;  // uniform over the grid
-  // CTA-level reduction of the affine gradients, then one atomic per channel per CTA
+  if constexpr (kNorm) {
+    if (a.dgamma == nullptr) return;  // uniform over the grid
+    // CTA-level reduction of the affine gradients, then one atomic per channel per CTA
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = l0_channel(lane, 2 * j);
-    float a0, a1;
-    f2_split(dg[j], a0, a1);
-    s_acc[warp][c] = a0;
-    s_acc[warp][c + 1] = a1;
-    f2_split(db[j], a0, a1);
-    s_acc[warp][kC + c] = a0;
-    s_acc[warp][kC + c + 1] = a1;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * kC; i += kLnBwdThreads) {
-    float t = 0.f;
-    for (int w = 0; w < kLnBwdWarps; ++w) t += s_acc[w][i];
-    atomicAdd(i < kC ? a.dgamma + i : a.dbeta + (i - kC), t);
+    for (int j = 0; j < 8; ++j) {
+      const int c = l0_channel(lane, 2 * j);
+      float a0, a1;
+      f2_split(dg[j], a0, a1);
+      s_acc[warp][c] = a0;
+      s_acc[warp][c + 1] = a1;
+      f2_split(db[j], a0, a1);
+      s_acc[warp][kC + c] = a0;
+      s_acc[warp][kC + c + 1] = a1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * kC; i += kLnBwdThreads) {
+      float t = 0.f;
+      for (int w = 0; w < kLnBwdWarps; ++w) t += s_acc[w][i];
+      atomicAdd(i < kC ? a.dgamma + i : a.dbeta + (i - kC), t);
+    }
   }
 }
 
@@ -2062,6 +1942,160 @@ layer0_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
       const int ln = i & 31, q = i >> 5, jj = q / 10, k = q % 10;
       atomicAdd(dw0 + l0_channel(ln, part * 2 + jj) * 10 + k, t);
     }
+  }
+}
+
+// ---- layer-0 weight gradient on the tensor cores ---------------------------------------------------------------------
+// dW0[c, tap] = sum_m dZ0[m, c] x[5 t + tap] is a GEMM with M = 512 channels, N = 10 taps and K = all B*P0 frames: 4 GFMA
+// behind an 839 MB read, i.e. HBM-bound work (0.13 ms) that the SIMT kernel above runs at a third of the HBM rate (160
+// accumulators per lane leave one 8-warp CTA per SM).  Here the gradient rows never pass through registers: dZ0 tiles
+// {64 channels, 64 frames} arrive by TMA in exactly the MN-major shared-memory layout the UMMA A operand wants (as in
+// conv_wgrad_kernel), two builder warps write the B operand -- per frame the 10-sample window as bf16 hi | lo halves
+// (x = hi + lo to 2^-17: fp32-class accuracy), N = 64 with zero padding -- and one thread issues 128 x 64 x 16 UMMAs that
+// accumulate the whole frame slice of the CTA in TMEM; the epilogue adds hi + lo columns and sends 512 x 10 atomics per CTA.
+constexpr int kL0WtStages = 3;
+constexpr int kL0WtKm = 64;                                   // frames per stage
+constexpr int kL0WtABytes = 8 * kL0WtKm * 128;                 // 512 channels = 8 boxes of {64 channels, 64 frames}
+constexpr int kL0WtBBytes = kL0WtKm * 128;                     // 64 frames x 64 (10 hi | 10 lo | 0...) bf16
+constexpr int kL0WtStageBytes = kL0WtABytes + kL0WtBBytes;     // 72 KB
+constexpr int kL0WtBarOff = kL0WtStages * kL0WtStageBytes;
+constexpr int kL0WtSmemBytes = kL0WtBarOff + (2 * kL0WtStages + 1) * 8 + 16 + 1024;
+constexpr int kL0WtThreads = 256;  // warp 0 TMA, warp 1 MMA, warps 2-3 B builders (one thread per frame), warps 4-7 epilogue
+static_assert(kL0WtSmemBytes <= 227 * 1024, "shared memory");
+
+__device__ __forceinline__ uint64_t l0wt_desc_mn(uint32_t smem_addr) {
+  // MN-major, 128B swizzle: 64-element MN blocks are 8 KB apart (LBO), 8-row K groups 1 KB apart (SBO)
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>((kL0WtKm * 128) >> 4) << 16) |
+         (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(kL0WtThreads, 1)
+layer0_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const float* __restrict__ x, float* __restrict__ dw0, int B,
+                       int L, int T0, int P0) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return smem_base + kL0WtBarOff + 8u * static_cast<uint32_t>(i); };
+  const int kFull = 0, kEmpty = kL0WtStages, kDone = 2 * kL0WtStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kL0WtBarOff + (2 * kL0WtStages + 1) * 8);
+  const long long rows = static_cast<long long>(B) * P0;
+  const int n_stages = static_cast<int>((rows + kL0WtKm - 1) / kL0WtKm);
+  const int per = (n_stages + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int st_begin = static_cast<int>(blockIdx.x) * per;
+  const int st_end = min(n_stages, st_begin + per);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_dz);
+    for (int s = 0; s < kL0WtStages; ++s) {
+      ptx::mbar_init(bar(kFull + s), 1 + kL0WtKm);  // the TMA producer's expect_tx arrive + one arrive per builder thread
+      ptx::mbar_init(bar(kEmpty + s), 1);
+    }
+    ptx::mbar_init(bar(kDone), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 256);
+    ptx::tmem_relinquish();
+  }
+  // the B tiles' zero padding (logical 16-byte chunks 3..7 of every row) is written once: the builders only touch chunks 0..2
+  for (int i = threadIdx.x; i < kL0WtStages * kL0WtKm * 8; i += kL0WtThreads) {
+    const int s = i / (kL0WtKm * 8), r = (i / 8) % kL0WtKm, c = i % 8;
+    *reinterpret_cast<uint4*>(smem + s * kL0WtStageBytes + kL0WtABytes + r * 128 + ((c ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int st = st_begin; st < st_end; ++st) {
+        ptx::mbar_wait(bar(kEmpty + stage), phase ^ 1u);
+        const uint32_t a_dst = smem_base + stage * kL0WtStageBytes;
+        ptx::mbar_arrive_expect_tx(bar(kFull + stage), kL0WtABytes);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // rows past the end of the tensor are zero-filled
+          ptx::tma_load_2d(a_dst + j * (kL0WtKm * 128), &tmap_dz, bar(kFull + stage), 64 * j, st * kL0WtKm);
+        if (++stage == kL0WtStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);  // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int st = st_begin; st < st_end; ++st) {
+        ptx::mbar_wait(bar(kFull + stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t a_src = smem_base + stage * kL0WtStageBytes;
+        const uint32_t b_src = a_src + kL0WtABytes;
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+          for (int k = 0; k < kL0WtKm / kUmmaK; ++k)  // 16 frames (= 16 shared-memory rows = 2 KB) per instruction
+            ptx::umma_bf16(tmem_base + static_cast<uint32_t>(mb * 64), l0wt_desc_mn(a_src + mb * (2 * kL0WtKm * 128) + k * (kUmmaK * 128)),
+                           l0wt_desc_mn(b_src + k * (kUmmaK * 128)), idesc, (st > st_begin || k > 0) ? 1u : 0u);
+        ptx::umma_commit(bar(kEmpty + stage));
+        if (++stage == kL0WtStages) { stage = 0; phase ^= 1u; }
+      }
+      ptx::umma_commit(bar(kDone));
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // B builders: thread = frame of the stage.  Row r of the tile = [x_hi[0..9] | x_lo[0..9] | 0 ...] (bf16), 128-byte swizzle
+    const int r = threadIdx.x - 64;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int st = st_begin; st < st_end; ++st) {
+      const long long m = static_cast<long long>(st) * kL0WtKm + r;
+      float xv[10];
+      const int b = static_cast<int>(m / P0), t = static_cast<int>(m % P0);
+      if (m < rows && t < T0) {
+        const float* xw = x + static_cast<size_t>(b) * L + 5 * t;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) xv[k] = __ldg(xw + k);
+      } else {  // pitch padding / past the end: dZ0 is zero there
+#pragma unroll
+        for (int k = 0; k < 10; ++k) xv[k] = 0.f;
+      }
+      uint32_t hi[5], lo[5];
+      l0_split(xv, hi, lo);
+      ptx::mbar_wait(bar(kEmpty + stage), phase ^ 1u);
+      const uint32_t row = smem_base + stage * kL0WtStageBytes + kL0WtABytes + static_cast<uint32_t>(r * 128);
+      const uint32_t sw = static_cast<uint32_t>(r & 7);
+      // elements 0..7 = hi[0..3], 8..15 = hi[4] lo[0..2], 16..23 = lo[3..4] 0 0
+      ptx::st_shared_v4(row + ((0u ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+      ptx::st_shared_v4(row + ((1u ^ sw) << 4), hi[4], lo[0], lo[1], lo[2]);
+      ptx::st_shared_v4(row + ((2u ^ sw) << 4), lo[3], lo[4], 0u, 0u);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      ptx::mbar_arrive(bar(kFull + stage));
+      if (++stage == kL0WtStages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (st_end > st_begin) {
+    // epilogue: TMEM lane = channel within a block of 128; columns 0..9 = hi products, 10..19 = lo products
+    const int quad = warp & 3;
+    ptx::mbar_wait(bar(kDone), 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int mb = 0; mb < 4; ++mb) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(mb * 64), r);
+      ptx::tmem_ld_wait();
+      float* dst = dw0 + (mb * 128 + quad * 32 + lane) * 10;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) atomicAdd(dst + k, __uint_as_float(r[k]) + __uint_as_float(r[10 + k]));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -2543,6 +2577,9 @@ int experiment_flags() {
 #else
 constexpr int experiment_flags() { return 0; }
 #endif
+int g_sm_budget = kNumSMs;  // SMs the persistent kernels of this file spread over (nrse_conv_frontend_set_sm_budget): the
+                           // training step leaves a few SMs to the NCCL all-reduce kernels that run concurrently with
+                           // the backward (a resident persistent CTA per SM would otherwise starve them until a kernel ends)
 int g_tile_order = 1;   // 1: consecutive layers walk their tiles in opposite directions, so that every layer starts on the
                         // rows its producer wrote last (still in L2) instead of the ones it wrote first (long evicted); 0: all forward
 int g_l2_prefetch = 0;  // 1: producer bulk-prefetches the next tile's A rows into L2 (measured 2-3 % slower: off)
@@ -2564,7 +2601,7 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap
     attr_set = true;
   }
   const int num_super = (g.num_tiles + 1) / 2;
-  const int max_groups = kNumSMs / 2;
+  const int max_groups = g_sm_budget / 2;
   const int groups = num_super < max_groups ? num_super : max_groups;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
@@ -2594,7 +2631,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
                                        Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int max_groups = kNumSMs / kClusterN;  // persistent: one CTA (or CTA pair) per SM (pair)
+  const int max_groups = g_sm_budget / kClusterN;  // persistent: one CTA (or CTA pair) per SM (pair)
   const int groups = g.num_tiles < max_groups ? g.num_tiles : max_groups;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * kClusterN));
@@ -2625,7 +2662,7 @@ int launch_layer0_tc(const L0Args& a, cudaStream_t stream) {
   }
   const long long m_total = static_cast<long long>(a.B) * a.P0;
   const int num_tiles = static_cast<int>((m_total + kBlockM - 1) / kBlockM);
-  const int max_groups = kNumSMs / kClusterN;
+  const int max_groups = g_sm_budget / kClusterN;
   const int groups = num_tiles < max_groups ? num_tiles : max_groups;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(groups * kClusterN));
@@ -2726,6 +2763,12 @@ int nrse_conv_frontend_set_variant(int variant) {
   return NRSE_OK;
 }
 
+int nrse_conv_frontend_set_sm_budget(int sms) {
+  if (sms < 8 || sms > nrse::kNumSMs) return NRSE_ERR_INVALID_ARG;
+  nrse::g_sm_budget = sms & ~1;  // CTA pairs
+  return NRSE_OK;
+}
+
 int nrse_conv_frontend_set_tile_order(int alternate) {
   nrse::g_tile_order = alternate ? 1 : 0;
   return NRSE_OK;
@@ -2769,7 +2812,7 @@ static int layer0_fwd_impl(const float* x, const float* w0, const float* gamma, 
   a.gn_mr = nullptr;
   const long long rows = static_cast<long long>(B) * P0;
   const long long want = ceil_div(rows, static_cast<long long>(kL0Warps));
-  const unsigned grid = static_cast<unsigned>(want < kNumSMs ? want : kNumSMs);
+  const unsigned grid = static_cast<unsigned>(want < g_sm_budget ? want : g_sm_budget);
   if (norm_mode == NRSE_NORM_LAYER) {
     if (xhat == nullptr && g_variant >= 2) {
       if (g_layer0_variant == 2) return launch_layer0_tc<2, false, 1, true>(a, s);
@@ -2965,7 +3008,7 @@ int nrse_ln_gelu_bwd(const void* dout, int dout_dtype, int dout_pitch, const voi
   a.dgamma = dgamma; a.dbeta = dbeta; a.rows = rows; a.P = P; a.T = T;
   a.dz_f32 = 0; a.dz_P = P;
   const long long want = ceil_div(static_cast<long long>(rows), static_cast<long long>(kLnBwdWarps));
-  const unsigned grid = static_cast<unsigned>(want < 4 * kNumSMs ? want : 4 * kNumSMs);
+  const unsigned grid = static_cast<unsigned>(want < 4 * g_sm_budget ? want : 4 * g_sm_budget);
   cudaStream_t s = as_stream(stream);
   if (a.dout_f32) {
     if (norm) ln_gelu_bwd_kernel<true, true><<<grid, kLnBwdThreads, 0, s>>>(a);
@@ -2989,10 +3032,27 @@ int nrse_ln_gelu_bwd(const void* dout, int dout_dtype, int dout_pitch, const voi
 int nrse_conv_layer0_wgrad(const float* x, const void* dz0, float* dw0, int B, int L, int T0, int P0,
                            nrse_stream_t stream) {
   using namespace nrse;
-  if (!x || !dz0 || !dw0 || B < 1 || T0 < 1 || P0 < T0) return NRSE_ERR_INVALID_ARG;
+  if (!x || !dz0 || !dw0 || B < 1 || T0 < 1 || P0 < T0 || L < 5 * (T0 - 1) + 10) return NRSE_ERR_INVALID_ARG;
   const long long rows = static_cast<long long>(B) * P0;
+  if (g_layer0_variant >= 1 && (reinterpret_cast<uintptr_t>(dz0) & 15u) == 0) {
+    // tensor cores (default): HBM-bound read of dZ0 through TMA, see layer0_wgrad_tc_kernel
+    CUtensorMap tz;
+    int rc = make_tmap_rows(&tz, dz0, rows, kL0WtKm);
+    if (rc != NRSE_OK) return rc;
+    static bool attr_tc = false;  // benign race: idempotent attribute
+    if (!attr_tc) {
+      NRSE_CUDA_TRY(cudaFuncSetAttribute(layer0_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0WtSmemBytes));
+      attr_tc = true;
+    }
+    const int n_stages = static_cast<int>(ceil_div(rows, static_cast<long long>(kL0WtKm)));
+    const int grid = n_stages < g_sm_budget ? n_stages : g_sm_budget;
+    layer0_wgrad_tc_kernel<<<grid, kL0WtThreads, kL0WtSmemBytes, as_stream(stream)>>>(
+        tz, x, dw0, B, L, T0, P0);
+    NRSE_CHECK_LAUNCH();
+    return NRSE_OK;
+  }
   const long long want = ceil_div(rows, static_cast<long long>(kL0Warps));
-  const unsigned grid = static_cast<unsigned>(want < kNumSMs ? want : kNumSMs);
+  const unsigned grid = static_cast<unsigned>(want < g_sm_budget ? want : g_sm_budget);
   static bool attr_set = false;  // benign race: idempotent attribute
   if (!attr_set) {
     NRSE_CUDA_TRY(cudaFuncSetAttribute(layer0_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0WgRingBytes));
@@ -3047,7 +3107,7 @@ static int launch_wgrad(const void* g_rows, int N, const void* x_rows, int64_t x
   g.stride = stride;
   g.n_stages = static_cast<int>(ceil_div(rows, static_cast<int64_t>(kWgKm)));
   const int tiles = (N / 128) * (K / 256);
-  int split = kNumSMs / tiles;
+  int split = g_sm_budget / tiles;
   if (split > g.n_stages) split = g.n_stages;
   if (split < 1) split = 1;
   g.split = split;
@@ -3212,7 +3272,7 @@ int nrse_feature_projection_fwd(const void* feats, int feats_dtype, int B, int T
   a.rstd = training ? reinterpret_cast<float*>(tp + 2 * featproj_rows_bytes(rows, 512, 2)) : nullptr;
   a.B = B; a.T = T;
   const long long want = ceil_div(static_cast<long long>(rows), 8ll);
-  featproj_ln_kernel<<<static_cast<unsigned>(want < 4 * kNumSMs ? want : 4 * kNumSMs), 256, 0, as_stream(stream)>>>(a);
+  featproj_ln_kernel<<<static_cast<unsigned>(want < 4 * g_sm_budget ? want : 4 * g_sm_budget), 256, 0, as_stream(stream)>>>(a);
   NRSE_CHECK_LAUNCH();
   CUtensorMap ta, tw, to;
   int rc = make_tmap_rows(&ta, a.xn, rows, kBlockM);
@@ -3264,7 +3324,7 @@ int nrse_feature_projection_bwd(const float* d_hidden, const void* tape, const f
   __nv_bfloat16* dhb = reinterpret_cast<__nv_bfloat16*>(workspace);
   __nv_bfloat16* dxn = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(workspace) + featproj_rows_bytes(rows, 1024, 2));
   cudaStream_t s = as_stream(stream);
-  featproj_bwd_prep_kernel<<<static_cast<unsigned>(rows < 2 * kNumSMs ? rows : 2 * kNumSMs), 256, 0, s>>>(d_hidden, dhb, d_bias,
+  featproj_bwd_prep_kernel<<<static_cast<unsigned>(rows < 2 * g_sm_budget ? rows : 2 * g_sm_budget), 256, 0, s>>>(d_hidden, dhb, d_bias,
                                                                                                             rows);
   NRSE_CHECK_LAUNCH();
   int rc;
@@ -3313,7 +3373,7 @@ int nrse_feature_projection_bwd(const float* d_hidden, const void* tape, const f
   a.dz_P = 1;
   a.dgamma = d_ln_gamma; a.dbeta = d_ln_beta; a.rows = rows; a.P = 1; a.T = 1;
   const long long want = ceil_div(static_cast<long long>(rows), static_cast<long long>(kLnBwdWarps));
-  const unsigned grid = static_cast<unsigned>(want < 4 * kNumSMs ? want : 4 * kNumSMs);
+  const unsigned grid = static_cast<unsigned>(want < 4 * g_sm_budget ? want : 4 * g_sm_budget);
   static bool attr_set = false;  // benign race: idempotent attribute
   if (!attr_set) {
     NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -12,6 +12,7 @@ from transformers import AutoModel, WavLMConfig, WavLMModel
 
 from .featproj import B200FeatureProjection
 from .frontend import B200FeatureEncoder
+from .posconv import B200PositionalConvEmbedding
 
 
 def wavlm_large_config(**overrides) -> WavLMConfig:
@@ -70,10 +71,14 @@ def install_sync_free_spec_augment(model: nn.Module) -> nn.Module:
 
 def install_b200_frontend(model: nn.Module) -> nn.Module:
     """Swap ``model.feature_extractor`` (HF WavLMFeatureEncoder) for the B200 implementation, in place, and -- for the
-    wavlm-large geometry (512 -> 1024) -- ``model.feature_projection`` too; other sizes keep HF's."""
+    wavlm-large geometry -- ``model.feature_projection`` (512 -> 1024) and
+    ``model.encoder.pos_conv_embed`` (1024 channels, 16 groups, 128 taps, 8f-4) too; other sizes keep HF's modules."""
     B200FeatureEncoder.convert(model.feature_extractor)
     if B200FeatureProjection.supports(getattr(model, "feature_projection", None)):
         B200FeatureProjection.convert(model.feature_projection)
+    pos = getattr(getattr(model, "encoder", None), "pos_conv_embed", None)
+    if B200PositionalConvEmbedding.supports(pos):   # SURVEY.md 8f-4: wavlm-large's grouped positional convolution
+        B200PositionalConvEmbedding.convert(pos)
     return model
 
 

@@ -681,6 +681,22 @@ def set_mix_carveout(percent: int) -> None:
     check(_lib.load().nrse_mix_set_carveout(int(percent)), "nrse_mix_set_carveout")
 
 
+def multimem_allreduce_mean_(multicast_ptr: int, elem_offset: int, numel: int, rank: int, world: int,
+                             max_ctas: int = 0) -> None:
+    """In place, on the current stream: mean over the ranks of ``numel`` fp32 elements at ``elem_offset`` of a symmetric
+    allocation, through its NVSwitch multicast address (csrc/allreduce.cu).  The caller brackets the call with
+    symmetric-memory barriers on the same stream."""
+    check(_lib.load().nrse_multimem_allreduce_mean_f32(C.c_void_p(int(multicast_ptr)), int(elem_offset), int(numel), int(rank),
+                                                       int(world), int(max_ctas), _stream()),
+          "nrse_multimem_allreduce_mean_f32")
+
+
+def set_sm_budget(sms: int) -> None:
+    """SMs the persistent conv-frontend kernels spread over (148 = all).  The data-parallel step lowers it while a
+    gradient all-reduce is in flight so that NCCL's kernels find free SMs (see include/nrse_b200.h)."""
+    check(_lib.load().nrse_conv_frontend_set_sm_budget(int(sms)), "nrse_conv_frontend_set_sm_budget")
+
+
 def set_tile_order(alternate: int) -> None:
     check(_lib.load().nrse_conv_frontend_set_tile_order(int(alternate)), "nrse_conv_frontend_set_tile_order")
 
@@ -971,3 +987,62 @@ def feature_projection_bwd(d_hidden: Tensor, tape: Tensor, ln_weight: Tensor, ln
                                           _ptr(d_b), _ptr(d_w), _ptr(d_bias), C.c_void_p(wp), rows, _stream()),
           "nrse_feature_projection_bwd")
     return d_feats, d_g, d_b, d_w, d_bias
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Positional convolution embedding (hf:models/wavlm/modeling_wavlm.py:48-90)
+# --------------------------------------------------------------------------------------------------------------
+def pack_pos_conv(v: Tensor, g: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """weight-norm parameters (v [1024, 64, 128], g [1, 1, 128]) -> (forward pack, data-gradient pack, ||v||^2 per tap)."""
+    _need_cuda(v, g)
+    if tuple(v.shape) != (1024, 64, 128) or g.numel() != 128:
+        raise NrseError("pack_pos_conv expects v [1024, 64, 128] and g with 128 elements (wavlm-large positional conv)")
+    lib = _lib.load()
+    n = lib.nrse_pos_conv_pack_bytes()
+    wf = torch.empty(n // 2, dtype=torch.bfloat16, device=v.device)
+    wb = torch.empty(n // 2, dtype=torch.bfloat16, device=v.device)
+    normsq = torch.empty(128, dtype=torch.float32, device=v.device)
+    check(lib.nrse_pos_conv_pack(_ptr(v.detach().contiguous().float()), _ptr(g.detach().reshape(-1).contiguous().float()),
+                                 _ptr(wf), _ptr(wb), _ptr(normsq), _stream()), "nrse_pos_conv_pack")
+    return wf, wb, normsq
+
+
+def pos_conv_fwd(x: Tensor, w_fwd: Tensor, bias: Tensor, training: bool) -> Tuple[Tensor, Tensor, Optional[Tensor]]:
+    """x [B, T, 1024] -> (y [B, T, 1024] fp32 = GELU(grouped conv), bf16 copy of x, pre-GELU activation bf16 | None)."""
+    _need_cuda(x, w_fwd)
+    if x.dim() != 3 or x.shape[2] != 1024:
+        raise NrseError("pos_conv_fwd expects hidden states [B, T, 1024]")
+    x = x.contiguous().float()
+    B, T, _ = x.shape
+    y = torch.empty_like(x)
+    xb = torch.empty(B * T, 1024, dtype=torch.bfloat16, device=x.device)
+    z = torch.empty(B * T, 1024, dtype=torch.bfloat16, device=x.device) if training else None
+    check(_lib.load().nrse_pos_conv_fwd(_ptr(x), _ptr(w_fwd), _ptr(bias.detach().contiguous().float()), _ptr(y), _ptr(xb),
+                                        _ptr(z), B, T, _stream()), "nrse_pos_conv_fwd")
+    return y, xb, z
+
+
+def pos_conv_bwd(d_y: Tensor, xb: Tensor, z: Tensor, w_bwd: Tensor, v: Tensor, g: Tensor, normsq: Tensor,
+                 need_x: bool = True, need_w: bool = True, need_bias: bool = True):
+    """-> (d_x [B, T, 1024] | None, d_v [1024, 64, 128] | None, d_g [1, 1, 128] | None, d_bias [1024] | None)."""
+    lib = _lib.load()
+    B, T, _ = d_y.shape
+    dev = d_y.device
+    dy = d_y.contiguous().float()
+    d_x = torch.empty(B, T, 1024, dtype=torch.float32, device=dev) if need_x else None
+    flat = torch.zeros((1024 * 64 * 128 + 128 if need_w else 0) + (1024 if need_bias else 0) + 4, dtype=torch.float32,
+                       device=dev)  # the kernels accumulate
+    off = 0
+    d_v = d_g = d_b = None
+    if need_w:
+        d_v = flat[:1024 * 64 * 128].view(1024, 64, 128)
+        d_g = flat[1024 * 64 * 128:1024 * 64 * 128 + 128].view(1, 1, 128)
+        off = 1024 * 64 * 128 + 128
+    if need_bias:
+        d_b = flat[off:off + 1024]
+    ws = _workspace(lib.nrse_pos_conv_bwd_workspace_bytes(B, T), dev)
+    wp, _ = _aligned(ws)
+    check(lib.nrse_pos_conv_bwd(_ptr(dy), _ptr(xb), _ptr(z), _ptr(w_bwd), _ptr(v.detach().contiguous().float()),
+                                _ptr(g.detach().reshape(-1).contiguous().float()), _ptr(normsq), _ptr(d_x), _ptr(d_v),
+                                _ptr(d_g), _ptr(d_b), C.c_void_p(wp), B, T, _stream()), "nrse_pos_conv_bwd")
+    return d_x, d_v, d_g, d_b

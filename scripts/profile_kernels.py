@@ -25,8 +25,8 @@ for it in range(2):
     c, n, st = ops.mix_normalize(c_d, n_d, s_d, tab, True)
     ops.mix_normalize(cb, nb, sb, tab, True)
     y = ops.conv_frontend(c, w, g, b, "layer", out_dtype=torch.bfloat16, packed=packed)
-    yt, tape = ops.conv_frontend_train(c, w, g, b, packed=packed)
-    grads = ops.conv_frontend_backward(c, w, g, b, tape, gy, dgrad_packs=dpacks)
+    yt, tape = ops.conv_frontend_train(c, w, g, b, "layer", packed=packed)
+    grads = ops.conv_frontend_backward(c, w, g, b, tape, gy, "layer", dgrad_packs=dpacks)
 from nrse_b200.train import FusedAdamWEma
 from nrse_b200.models import AttentiveStatisticsPooling
 prm = [torch.nn.Parameter(torch.randn(n, device=dev) * 0.02) for n in [1 << 22] * 19 + [1000, 12, 4097]]
