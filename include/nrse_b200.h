@@ -13,7 +13,7 @@
  *   - no entry point allocates device memory or synchronises the stream;
  *   - `stream` is a cudaStream_t (CUstream), e.g. torch.cuda.current_stream().cuda_stream;
  *   - re-entrant per stream; the only global state is the lazily resolved driver entry point for TMA
- *     descriptor encoding, one-time kernel attributes and the tuning knob nrse_conv_frontend_set_variant.
+ *     descriptor encoding, one-time kernel attributes and the tuning knobs (nrse_*_set_*).
  *   - sm_100a only.  There is no CPU or other-arch fallback.
  */
 #ifndef NRSE_B200_H_

@@ -1686,6 +1686,9 @@ struct LnBwdArgs {
 constexpr int kLnStages = 4;
 constexpr int kLnStageBytes = 2 * kC * 2;  // xhat row + dOut row, bf16
 constexpr int kLnRingBytes = kLnBwdWarps * kLnStages * kLnStageBytes;
+constexpr int kLnAccBytes = kLnBwdWarps * 2 * kC * 4;                       // affine-gradient reduction buffer
+constexpr int kLnDynBytes = kLnRingBytes > kLnAccBytes ? kLnRingBytes : kLnAccBytes;
+constexpr int kLnDynBytesF32 = kLnAccBytes;                                 // fp32-gradient variant: no ring
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -1701,8 +1704,10 @@ template <bool kDoutF32, bool kNorm, bool kGelu = true>
 __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnBwdArgs a) {
   __shared__ __align__(16) float s_gamma[kC];
   __shared__ __align__(16) float s_beta[kC];
-  __shared__ float s_acc[kLnBwdWarps][2 * kC];
-  extern __shared__ __align__(16) unsigned char ln_ring[];  // bf16 path only
+  // dynamic shared memory: the cp.async ring of the bf16 path while rows stream; afterwards the [warps][2 x 512] buffer of
+  // the affine-gradient reduction (kLnDynBytes covers both)
+  extern __shared__ __align__(16) unsigned char ln_ring[];
+  float (*s_acc)[2 * kC] = reinterpret_cast<float (*)[2 * kC]>(ln_ring);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < kC; i += kLnBwdThreads) {
     s_gamma[i] = kNorm ? a.gamma[i] : 1.0f;
@@ -1725,10 +1730,19 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
   const long long warps_total = static_cast<long long>(gridDim.x) * kLnBwdWarps;
   const long long m_first = static_cast<long long>(blockIdx.x) * kLnBwdWarps + warp;
   const uint32_t ring = ptx::smem_u32(ln_ring) + static_cast<uint32_t>(warp * kLnStages * kLnStageBytes);
-  // issue the copies of row m into ring slot `slot` (nothing for rows past the end or in the pitch padding)
-  auto prefetch = [&](long long m, int slot) {
+  // (utterance, frame) of a row are tracked INCREMENTALLY: a 64-bit `m % P` per row and per prefetch cost ~100 of the ~420
+  // instructions this issue-bound kernel spent on a row (ncu: IPC 2.0, 341 M warp instructions for layer 0)
+  const int step_b = static_cast<int>(warps_total / a.P), step_t = static_cast<int>(warps_total % a.P);
+  auto advance = [&](int& b, int& t) {
+    b += step_b;
+    t += step_t;
+    if (t >= a.P) { t -= a.P; ++b; }
+  };
+  // issue the copies of row m (frame t_m of its utterance) into ring slot `slot` (nothing for rows past the end or in the
+  // pitch padding)
+  auto prefetch = [&](long long m, int t_m, int slot) {
     if constexpr (!kDoutF32) {
-      if (m < a.rows && static_cast<int>(m % a.P) < a.T) {
+      if (m < a.rows && t_m < a.T) {
         const uint32_t dst = ring + static_cast<uint32_t>(slot * kLnStageBytes);
         const char* xr = reinterpret_cast<const char*>(a.xhat + m * kC);
         const char* gr = reinterpret_cast<const char*>(reinterpret_cast<const __nv_bfloat16*>(a.dout) + m * kC);
@@ -1740,20 +1754,31 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
       cp_async_commit();
     }
   };
+  int b_cur = static_cast<int>(m_first / a.P), t_cur = static_cast<int>(m_first % a.P);  // the only divisions
+  int b_pf = b_cur, t_pf = t_cur;
+  long long m_pf = m_first;
   if constexpr (!kDoutF32) {
 #pragma unroll
-    for (int s = 0; s < kLnStages - 1; ++s) prefetch(m_first + s * warps_total, s);
+    for (int s = 0; s < kLnStages - 1; ++s) {
+      prefetch(m_pf, t_pf, s);
+      m_pf += warps_total;
+      advance(b_pf, t_pf);
+    }
   }
   int slot = 0;
   for (long long m = m_first; m < a.rows; m += warps_total) {
     if constexpr (!kDoutF32) {
-      prefetch(m + (kLnStages - 1) * warps_total, (slot + kLnStages - 1) % kLnStages);
+      prefetch(m_pf, t_pf, (slot + kLnStages - 1) % kLnStages);
+      m_pf += warps_total;
+      advance(b_pf, t_pf);
       cp_async_wait<kLnStages - 1>();  // this row's group has landed (groups complete in order)
     }
     const int cur = slot;
     slot = (slot + 1) % kLnStages;
+    const int b_row = b_cur, t_row = t_cur;
+    advance(b_cur, t_cur);
     uint4* zrow = reinterpret_cast<uint4*>(a.dz + m * kC);
-    if (static_cast<int>(m % a.P) >= a.T) {  // pitch padding: no gradient flows through it
+    if (t_row >= a.T) {  // pitch padding: no gradient flows through it
       if (!a.dz_f32) {
         zrow[lane] = make_uint4(0, 0, 0, 0);
         zrow[32 + lane] = make_uint4(0, 0, 0, 0);
@@ -1767,7 +1792,7 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
       const unsigned w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) xh[j] = f2_bits(w[j] << 16, w[j] & 0xffff0000u);
-      const long long drow = (m / a.P) * a.dout_P + (m % a.P);
+      const long long drow = static_cast<long long>(b_row) * a.dout_P + t_row;
       const float4* gr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.dout) + drow * kC);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -1827,7 +1852,7 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
       z[j] = pack_bf16x2(zf[2 * j], zf[2 * j + 1]);
     }
     if (a.dz_f32) {  // small tensors only (the feature projection): fp32 rows in the caller's layout
-      float4* fr = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.dz) + ((m / a.P) * a.dz_P + (m % a.P)) * kC);
+      float4* fr = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.dz) + (static_cast<long long>(b_row) * a.dz_P + t_row) * kC);
       fr[2 * lane] = make_float4(zf[0], zf[1], zf[2], zf[3]);
       fr[2 * lane + 1] = make_float4(zf[4], zf[5], zf[6], zf[7]);
       fr[64 + 2 * lane] = make_float4(zf[8], zf[9], zf[10], zf[11]);
@@ -1842,6 +1867,7 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
   if constexpr (kNorm) {
     if (a.dgamma == nullptr) return;  // uniform over the grid
     // CTA-level reduction of the affine gradients, then one atomic per channel per CTA
+    __syncthreads();  // every warp is done with its ring slots: the memory becomes s_acc
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = l0_channel(lane, 2 * j);
@@ -2227,13 +2253,15 @@ __global__ void layer0_gn_bwd_finalize_kernel(const float* __restrict__ part, co
 // the reduction index m runs over shared-memory rows of 128 bytes, exactly what TMA writes for a {64 elements, 64 rows}
 // box of the row-major dZ / X tensors, so no transposed copy of either is ever made.
 constexpr int kWgThreads = 192;
-constexpr int kWgStages = 4;
 constexpr int kWgKm = 64;                         // frames per pipeline stage
 constexpr int kWgABytes = 2 * kWgKm * 128;        // 128 channels = 2 boxes of 64
 constexpr int kWgBBytes = 4 * kWgKm * 128;        // 256 K columns = 4 boxes of 64
 constexpr int kWgStageBytes = kWgABytes + kWgBBytes;
-constexpr int kWgBarOff = kWgStages * kWgStageBytes;
-constexpr int kWgSmemBytes = kWgBarOff + (2 * kWgStages + 1) * 8 + 16 + 1024;
+template <int kStages>
+struct WgCfg {
+  static constexpr int kBarOff = kStages * kWgStageBytes;
+  static constexpr int kSmemBytes = kBarOff + (2 * kStages + 1) * 8 + 16 + 1024;
+};
 
 struct WgradArgs {
   float* dw;        // fp32, accumulated with atomics: [512, K] in the packed K order tap*512 + c, or (ckpt) the
@@ -2251,6 +2279,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
          (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+template <int kStages>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradArgs g) {
@@ -2258,9 +2287,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  auto bar = [&](int i) { return smem_base + kWgBarOff + 8u * static_cast<uint32_t>(i); };
-  const int kFull = 0, kEmpty = kWgStages, kDone = 2 * kWgStages;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kWgBarOff + (2 * kWgStages + 1) * 8);
+  auto bar = [&](int i) { return smem_base + WgCfg<kStages>::kBarOff + 8u * static_cast<uint32_t>(i); };
+  const int kFull = 0, kEmpty = kStages, kDone = 2 * kStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + WgCfg<kStages>::kBarOff + (2 * kStages + 1) * 8);
 
   const int kk_tiles = g.K / 256;
   const int tile = static_cast<int>(blockIdx.x) / g.split, slice = static_cast<int>(blockIdx.x) % g.split;
@@ -2272,7 +2301,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_g);
     ptx::prefetch_tmap(&tmap_x);
-    for (int s = 0; s < kWgStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(bar(kFull + s), 1);
       ptx::mbar_init(bar(kEmpty + s), 1);
     }
@@ -2305,7 +2334,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         for (int j = 0; j < 4; ++j)
           ptx::tma_load_3d(b_dst + j * (kWgKm * 128), &tmap_x, bar(kFull + stage), c0 + 64 * j, tap % g.stride,
                            m0 + tap / g.stride);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
     __syncwarp();
@@ -2325,7 +2354,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
           ptx::umma_bf16(tmem_base, umma_desc_sw128_mn(a_src + k * (kUmmaK * 128)),
                          umma_desc_sw128_mn(b_src + k * (kUmmaK * 128)), idesc, (st > st_begin || k > 0) ? 1u : 0u);
         ptx::umma_commit(bar(kEmpty + stage));
-        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
       ptx::umma_commit(bar(kDone));
     }
@@ -3010,20 +3039,20 @@ int nrse_ln_gelu_bwd(const void* dout, int dout_dtype, int dout_pitch, const voi
   const long long want = ceil_div(static_cast<long long>(rows), static_cast<long long>(kLnBwdWarps));
   const unsigned grid = static_cast<unsigned>(want < 4 * g_sm_budget ? want : 4 * g_sm_budget);
   cudaStream_t s = as_stream(stream);
+  static bool attr_set = false;  // benign race: idempotent attributes
+  if (!attr_set) {
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnDynBytes));
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnDynBytes));
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnDynBytesF32));
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnDynBytesF32));
+    attr_set = true;
+  }
   if (a.dout_f32) {
-    if (norm) ln_gelu_bwd_kernel<true, true><<<grid, kLnBwdThreads, 0, s>>>(a);
-    else ln_gelu_bwd_kernel<true, false><<<grid, kLnBwdThreads, 0, s>>>(a);
+    if (norm) ln_gelu_bwd_kernel<true, true><<<grid, kLnBwdThreads, kLnDynBytesF32, s>>>(a);
+    else ln_gelu_bwd_kernel<true, false><<<grid, kLnBwdThreads, kLnDynBytesF32, s>>>(a);
   } else {
-    static bool attr_set = false;  // benign race: idempotent attribute
-    if (!attr_set) {
-      NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kLnRingBytes));
-      NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kLnRingBytes));
-      attr_set = true;
-    }
-    if (norm) ln_gelu_bwd_kernel<false, true><<<grid, kLnBwdThreads, kLnRingBytes, s>>>(a);
-    else ln_gelu_bwd_kernel<false, false><<<grid, kLnBwdThreads, kLnRingBytes, s>>>(a);
+    if (norm) ln_gelu_bwd_kernel<false, true><<<grid, kLnBwdThreads, kLnDynBytes, s>>>(a);
+    else ln_gelu_bwd_kernel<false, false><<<grid, kLnBwdThreads, kLnDynBytes, s>>>(a);
   }
   NRSE_CHECK_LAUNCH();
   return NRSE_OK;
@@ -3097,7 +3126,7 @@ static int launch_wgrad(const void* g_rows, int N, const void* x_rows, int64_t x
   if (rc != NRSE_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<4>::kSmemBytes));
     attr_set = true;
   }
   WgradArgs g;
@@ -3111,7 +3140,7 @@ static int launch_wgrad(const void* g_rows, int N, const void* x_rows, int64_t x
   if (split > g.n_stages) split = g.n_stages;
   if (split < 1) split = 1;
   g.split = split;
-  conv_wgrad_kernel<<<tiles * split, kWgThreads, kWgSmemBytes, as_stream(stream)>>>(tg, tx, g);
+  conv_wgrad_kernel<4><<<tiles * split, kWgThreads, WgCfg<4>::kSmemBytes, as_stream(stream)>>>(tg, tx, g);
   NRSE_CHECK_LAUNCH();
   return NRSE_OK;
 }
@@ -3229,7 +3258,6 @@ int nrse_conv_frontend_bwd(const float* x, const nrse_frontend_params* prm, cons
   }
   return NRSE_OK;
 }
-
 
 /* ---- feature projection ----------------------------------------------------------------------------- */
 int nrse_feature_projection_pack(const float* w, void* w_bf16, void* wt_bf16, nrse_stream_t stream) {
@@ -3377,10 +3405,10 @@ int nrse_feature_projection_bwd(const float* d_hidden, const void* tape, const f
   static bool attr_set = false;  // benign race: idempotent attribute
   if (!attr_set) {
     NRSE_CUDA_TRY(cudaFuncSetAttribute(ln_gelu_bwd_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kLnRingBytes));
+                                       kLnDynBytes));
     attr_set = true;
   }
-  ln_gelu_bwd_kernel<false, true, false><<<grid, kLnBwdThreads, kLnRingBytes, s>>>(a);
+  ln_gelu_bwd_kernel<false, true, false><<<grid, kLnBwdThreads, kLnDynBytes, s>>>(a);
   NRSE_CHECK_LAUNCH();
   return NRSE_OK;
 }

@@ -33,8 +33,11 @@ def timeit(fn, n=5, repeats=3):
     return best, out
 
 t_fwd, _ = timeit(lambda: ops.conv_frontend(x, w, g, b, "layer", out_dtype=torch.bfloat16, packed=packed))
-t_train, (y, tape) = timeit(lambda: ops.conv_frontend_train(x, w, g, b, packed=packed))
-t_bwd, _ = timeit(lambda: ops.conv_frontend_backward(x, w, g, b, tape, gy, dgrad_packs=dpacks))
+t_train, (y, tape) = timeit(lambda: ops.conv_frontend_train(x, w, g, b, "layer", packed=packed))
+t_bwd, _ = timeit(lambda: ops.conv_frontend_backward(x, w, g, b, tape, gy, "layer", dgrad_packs=dpacks))
+if "--quick" in sys.argv:
+    print(json.dumps({"shape": [B, L], "fwd_ms": t_fwd, "train_fwd_ms": t_train, "bwd_ms": t_bwd}))
+    sys.exit(0)
 fwd_flops = sum(2.0 * B * T[i] * 512 * 512 * k for i, k in enumerate((10, 3, 3, 3, 3, 2, 2)) if i > 0)
 # stock torch (cuDNN / ATen) forward+backward of the same stack for comparison, fp32 and bf16 autocast
 import torch.nn.functional as F
@@ -57,5 +60,6 @@ for name, ac in (("fp32", False), ("bf16_autocast", True)):
             return torch_stack(x, ws, gs, bs)
     res[name] = {"fwd_ms": timeit(fo, 3, 2)[0], "fwd_bwd_ms": timeit(fb, 3, 2)[0]}
 print(json.dumps({"shape": [B, L], "fwd_ms": t_fwd, "train_fwd_ms": t_train, "bwd_ms": t_bwd,
+
                   "bwd_tflops_2x_fwd_gemm": 2 * fwd_flops / (t_bwd * 1e-3) / 1e12,
                   "stock_torch_on_this_gpu": res}))
