@@ -411,6 +411,15 @@ def main_gpu(args):
     # ---- the north-star TRAINING step on the hot path, with its collective ---------------------------------------------------
     if not args.no_train_step:
         line["train_step"] = train_step_leg(args, dev, world, rank, layers, raw_d, snr_table, timed)
+        if world > 1 and args.train_allreduce == "full":
+            # the same step with only the hot path's OWN trainable parameters (conv frontend + heads, 14 M) in the gradient
+            # set: what the path costs under data parallelism when the transformer's 1.24 GB of gradients travel where
+            # they do in the real step -- behind the transformer's backward, which this leg excludes
+            import copy
+            args2 = copy.copy(args)
+            args2.train_allreduce = "hotpath"
+            torch.cuda.empty_cache()
+            line["train_step_hot_path_gradients_only"] = train_step_leg(args2, dev, world, rank, layers, raw_d, snr_table, timed)
 
     # ---- per-kernel rooflines (rank 0 only, outside the headline timing) -------------------------------------------
     if rank == 0:

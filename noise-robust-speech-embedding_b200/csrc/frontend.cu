@@ -1777,6 +1777,10 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
     slot = (slot + 1) % kLnStages;
     const int b_row = b_cur, t_row = t_cur;
     advance(b_cur, t_cur);
+    // 1/std of this frame: requested NOW, consumed ~300 instructions later (loaded at its point of use it was a full
+    // L2 round trip per row on the critical path: long_scoreboard was the top stall of this kernel)
+    [[maybe_unused]] float rs = 1.0f;
+    if constexpr (kNorm) rs = __ldg(a.rstd + m);
     uint4* zrow = reinterpret_cast<uint4*>(a.dz + m * kC);
     if (t_row >= a.T) {  // pitch padding: no gradient flows through it
       if (!a.dz_f32) {
@@ -1842,7 +1846,6 @@ __global__ void __launch_bounds__(kLnBwdThreads, 2) ln_gelu_bwd_kernel(const LnB
       m1 = warp_sum(a0 + a1) * (1.0f / kC);
       m2 = warp_sum(c0 + c1) * (1.0f / kC);
     }
-    const float rs = __ldg(a.rstd + m);
     const f2 rs2 = f2_make(rs, rs), nm1 = f2_make(-m1 * rs, -m1 * rs), nm2 = f2_make(-m2 * rs, -m2 * rs);
     uint32_t z[8];
     float zf[16];
