@@ -298,6 +298,11 @@ int nrse_conv_frontend_set_layer0_variant(int variant);
  * tiles in opposite directions (each layer starts on the rows its producer wrote last, which are still in L2);
  * 0 = every layer first-to-last.  Results do not depend on it. */
 int nrse_conv_frontend_set_tile_order(int alternate);
+/* 1 = nrse_conv_frontend_bwd (LayerNorm mode) runs the LayerNorm + GELU backward of layers 0-5 inside the epilogue of the
+ * data-gradient GEMM of the layer above (nrse_conv_layer_dgrad_lnbwd) instead of as kernels of their own: dOut_i never
+ * makes the round trip through HBM.  0 = separate kernels.  Same results up to bf16 rounding of dOut_i (the fused form
+ * keeps it in fp32). */
+int nrse_conv_frontend_set_bwd_fusion(int on);
 /* Number of SMs (8..148, default 148) the persistent kernels of the conv frontend / feature projection spread over.  The
  * data-parallel training step lowers it while the gradient all-reduce is in flight: NCCL's kernels need SMs of their own,
  * and a machine filled with one resident persistent CTA per SM would make them wait for the end of every kernel. */
@@ -365,6 +370,15 @@ int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out
                           nrse_stream_t stream);
 int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even, const void* wt_odd, int k, void* dx,
                           nrse_stream_t stream);
+/* nrse_conv_layer_dgrad followed by nrse_ln_gelu_bwd of the layer below, in one kernel: dz_prev [2*rows_out, 512] bf16
+ * receives dZ_{i-1}; dgamma_prev / dbeta_prev (both or neither, fp32 [512]) are accumulated into.  xhat_prev / rstd_prev:
+ * what nrse_conv_frontend_fwd_train saved for layer i-1 (frame pitch P_prev, T_prev valid frames per utterance; padding
+ * frames get zeros).  Replaces the autograd backward of Conv1d -> LayerNorm -> GELU across two layers,
+ * hf:models/wavlm/modeling_wavlm.py:250-275.  NRSE_ERR_UNSUPPORTED under set_variant(1). */
+int nrse_conv_layer_dgrad_lnbwd(const void* dz, int64_t rows_out, const void* wt_even, const void* wt_odd, int k,
+                                const void* xhat_prev, const float* rstd_prev, const float* gamma_prev,
+                                const float* beta_prev, void* dz_prev, float* dgamma_prev, float* dbeta_prev, int P_prev,
+                                int T_prev, nrse_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Feature projection: LayerNorm(512) + Linear(512 -> 1024) on the conv features, forward and backward.

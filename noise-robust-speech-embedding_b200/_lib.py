@@ -91,6 +91,7 @@ SIGNATURES = {
     "nrse_conv_frontend_set_variant": (_i, [_i]),
     "nrse_conv_frontend_set_layer0_variant": (_i, [_i]),
     "nrse_conv_frontend_set_tile_order": (_i, [_i]),
+    "nrse_conv_frontend_set_bwd_fusion": (_i, [_i]),
     "nrse_conv_frontend_set_sm_budget": (_i, [_i]),
     "nrse_conv_frontend_set_l2_prefetch": (_i, [_i]),
     "nrse_conv_frontend_tape_bytes": (_sz, [_i, _i]),
@@ -105,6 +106,7 @@ SIGNATURES = {
     "nrse_conv_layer0_gn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "nrse_conv_layer_wgrad": (_i, [_p, _p, _i64, _i, _p, _i, _p]),
     "nrse_conv_layer_dgrad": (_i, [_p, _i64, _p, _p, _i, _p, _p]),
+    "nrse_conv_layer_dgrad_lnbwd": (_i, [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "nrse_multimem_allreduce_mean_f32": (_i, [_p, _i64, _i64, _i, _i, _i, _p]),
     "nrse_pos_conv_pack_bytes": (_sz, []),
     "nrse_pos_conv_pack": (_i, [_p, _p, _p, _p, _p, _p]),

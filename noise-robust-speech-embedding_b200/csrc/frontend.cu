@@ -386,6 +386,14 @@ struct GemmArgs {
   // output row (mode 2); bias = [n_split * 512] fp32 (mode 2)
   int a_wide, n_split, out_pitch;
   const float* bias;
+  // mode 3 (data gradient with the LayerNorm + GELU backward of the layer BELOW fused into the epilogue): the accumulator
+  // row 2 m + parity is dOut of layer i-1; with that layer's saved xhat / 1/std (tape) and its gamma / beta (g.gamma, g.beta)
+  // the epilogue emits dZ of layer i-1 (bf16, through `out` / tmap_out) and accumulates its dgamma / dbeta (nullable)
+  const __nv_bfloat16* bw_xhat = nullptr;  // [rows_prev, 512]
+  const float* bw_rstd = nullptr;          // [rows_prev]
+  float* bw_dgamma = nullptr;
+  float* bw_dbeta = nullptr;
+  int bw_P = 1, bw_T = 1;                // frame pitch / valid frames per utterance of layer i-1
   // L2 prefetch of the NEXT tile's A rows (they come from HBM; the weights are L2-resident): base pointer and row count
   const char* a_ptr;
   long long a_rows;
@@ -693,7 +701,153 @@ __device__ __forceinline__ void epilogue_bias_f32_row(uint32_t taddr, uint32_t b
   }
 }
 
-template <int kClusterN, bool kSave>
+// Column sums over the 32 rows of a warp: lane l holds 32 column values of ITS row; afterwards lane l holds the sum of
+// column l over the warp's rows (butterfly: at every step a lane keeps the half of the columns that matches its lane bit
+// and hands the other half to its partner).  31 shuffles + 31 adds + 62 selects.
+__device__ __forceinline__ float warp_transpose_sum32(const float (&v)[32], int lane) {
+  float a[16];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float send = up ? v[j] : v[j + 16], keep = up ? v[j + 16] : v[j];
+      a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+#pragma unroll
+  for (int half = 8; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = up ? a[j] : a[j + half], keep = up ? a[j + half] : a[j];
+      a[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return a[0];
+}
+
+// Mode-3 epilogue: the accumulator row is dOut of the layer below; LayerNorm + GELU backward of that layer runs here, on the
+// fp32 accumulator, instead of in a separate elementwise kernel behind a bf16 round trip through HBM:
+//   dv = dOut gelu'(xhat gamma + beta),  dxh = dv gamma,  dZ = rstd (dxh - mean(dxh) - xhat mean(dxh xhat)),
+//   dgamma += sum_rows dv xhat,  dbeta += sum_rows dv.
+// One thread = one frame, this CTA's 256 channels.  Pass 1 reads the accumulator and the frame's xhat (row-owner 64-byte
+// loads), writes dxh back INTO the accumulator (tcgen05.st) and collects the two row sums; the CTA pair exchanges them like
+// the forward exchanges its LayerNorm partials (st.async + mbarrier complete_tx); pass 2 re-reads dxh and xhat and emits dZ
+// through the staging buffer + TMA store.  Column sums for dgamma / dbeta: a warp-level transpose reduction per 32-channel
+// chunk, accumulated per lane across the tiles of the launch (dg_acc / db_acc: column = chunk * 32 + lane).
+struct LnBwdEpi {
+  const __nv_bfloat16* xhat_row;  // this frame's xhat, first channel of this CTA
+  float rstd;
+  bool valid;                     // false: pitch padding / past the end -> dZ = 0, no contribution to any sum
+  bool want_affine;
+};
+
+template <int kClusterN>
+__device__ __forceinline__ void epilogue_lnbwd_row(const EpiCtx& e, const LnBwdEpi& b, float (&dg_acc)[8], float (&db_acc)[8]) {
+  static_assert(kClusterN == 2, "the fused backward epilogue exchanges its row sums inside a CTA pair");
+  constexpr int kChunks = 8;  // 256 channels per CTA
+  const float2* s_gamma2 = e.s_gb;               // [128] pairs of gamma, then [128] pairs of beta (NOT halved in this mode)
+  const float2* s_beta2 = e.s_gb + 128;
+  const uint4* xrow = reinterpret_cast<const uint4*>(b.xhat_row);
+  uint32_t ra[32];
+  uint4 xw[4], xn[4];
+  auto load_x = [&](int c, uint4 (&x)[4]) {
+    if (b.valid) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[q] = __ldg(xrow + c * 4 + q);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[q] = make_uint4(0, 0, 0, 0);
+    }
+  };
+  auto xpair = [](const uint4 (&x)[4], int j) -> f2 {  // pair j (0..15) of the chunk as fp32x2
+    const uint32_t w = j & 3;
+    const uint4& q = x[j >> 2];
+    const uint32_t bits = w == 0 ? q.x : (w == 1 ? q.y : (w == 2 ? q.z : q.w));
+    return f2_bits(bits << 16, bits & 0xffff0000u);
+  };
+  if (e.arm) ptx::mbar_arrive_expect_tx(e.bar_stats, kBlockM * 8);  // 128 peer rows x (s1, s2)
+  f2 s1 = f2_make(0.f, 0.f), s2 = s1;
+  load_x(0, xw);
+#pragma unroll 1
+  for (int c = 0; c < kChunks; ++c) {
+    ptx::tmem_ld32(e.taddr + c * 32, ra);
+    if (c + 1 < kChunks) load_x(c + 1, xn);
+    ptx::tmem_ld_wait();
+    float dv[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const f2 x = xpair(xw, j);
+      const float2 gm = s_gamma2[c * 16 + j], bt = s_beta2[c * 16 + j];
+      const f2 g2 = f2_make(gm.x, gm.y);
+      f2 acc = f2_bits(ra[2 * j], ra[2 * j + 1]);
+      if (!b.valid) acc = f2_make(0.f, 0.f);
+      const f2 d = f2_mul(acc, gelu_grad2(f2_fma(x, g2, f2_make(bt.x, bt.y))));
+      f2_split(d, dv[2 * j], dv[2 * j + 1]);
+      const f2 dxh = f2_mul(d, g2);
+      s1 = f2_add(s1, dxh);
+      s2 = f2_fma(dxh, x, s2);
+      float h0, h1;
+      f2_split(dxh, h0, h1);
+      ra[2 * j] = __float_as_uint(h0);
+      ra[2 * j + 1] = __float_as_uint(h1);
+    }
+    ptx::tmem_st32(e.taddr + c * 32, ra);  // dxh replaces dOut in the accumulator
+    if (b.want_affine) {
+      db_acc[c] += warp_transpose_sum32(dv, e.ost.lane);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x0, x1;
+        f2_split(xpair(xw, j), x0, x1);
+        dv[2 * j] *= x0;
+        dv[2 * j + 1] *= x1;
+      }
+      dg_acc[c] += warp_transpose_sum32(dv, e.ost.lane);
+    }
+    if (c + 1 < kChunks) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) xw[q] = xn[q];
+    }
+  }
+  ptx::tmem_st_wait();
+  float a0, a1, c0, c1;
+  f2_split(s1, a0, a1);
+  f2_split(s2, c0, c1);
+  const float sum1 = a0 + a1, sum2 = c0 + c1;
+  ptx::st_async_f2(ptx::mapa(e.stats_slot, e.peer), sum1, sum2, ptx::mapa(e.bar_stats, e.peer));
+  ptx::mbar_wait(e.bar_stats, e.stats_parity);
+  const float2 o = *e.stats_local;
+  const float m1 = (sum1 + o.x) * (1.0f / kC), m2 = (sum2 + o.y) * (1.0f / kC);
+  const f2 rs2 = f2_make(b.rstd, b.rstd), nm1 = f2_make(-m1 * b.rstd, -m1 * b.rstd), nm2 = f2_make(-m2 * b.rstd, -m2 * b.rstd);
+  // pass 2: dZ = rstd (dxh - m1 - xhat m2)
+  load_x(0, xw);
+#pragma unroll 1
+  for (int c = 0; c < kChunks; ++c) {
+    ptx::tmem_ld32(e.taddr + c * 32, ra);
+    if (c + 1 < kChunks) load_x(c + 1, xn);
+    ptx::tmem_ld_wait();
+    if (c + 1 == kChunks) {  // the accumulator is read for the last time: hand it back to the MMA warp
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(e.bar_tmem_empty);
+    }
+    uint32_t z16[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float z0, z1;
+      f2_split(f2_fma(xpair(xw, j), nm2, f2_fma(f2_bits(ra[2 * j], ra[2 * j + 1]), rs2, nm1)), z0, z1);
+      z16[j] = b.valid ? pack_bf16x2(z0, z1) : 0u;
+    }
+    out_stage_store(e.ost, z16, c * 32);
+    if (c + 1 < kChunks) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) xw[q] = xn[q];
+    }
+  }
+}
+
+// kBwdFuse: the instantiation that carries the mode-3 epilogue (data gradient + LayerNorm / GELU backward of the layer
+// below); a separate instantiation so that the forward / plain data-gradient kernels keep their register allocation.
+template <int kClusterN, bool kSave, bool kBwdFuse = false>
 __global__ void __launch_bounds__(GemmCfg<kClusterN>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
@@ -741,9 +895,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   ptx::pdl_wait();
   ptx::pdl_launch_dependents();
   const bool has_norm = g.gamma != nullptr;
+  const float gb_scale = (kBwdFuse && g.mode == 3) ? 1.0f : 0.5f;  // mode 3 (fused backward of the layer below): gamma / beta as they are
   for (int i = threadIdx.x; i < Cfg::kNPC; i += Cfg::kThreads) {  // gamma[kNPC] / 2 then beta[kNPC] / 2 (see gelu2h)
-    reinterpret_cast<float*>(s_gb)[i] = has_norm ? 0.5f * g.gamma[n0 + i] : 0.5f;
-    reinterpret_cast<float*>(s_gb)[Cfg::kNPC + i] = has_norm ? 0.5f * g.beta[n0 + i] : 0.f;
+    reinterpret_cast<float*>(s_gb)[i] = has_norm ? gb_scale * g.gamma[n0 + i] : 0.5f;
+    reinterpret_cast<float*>(s_gb)[Cfg::kNPC + i] = has_norm ? gb_scale * g.beta[n0 + i] : 0.f;
   }
   ptx::tc_fence_before();
   if constexpr (kClusterN == 2) ptx::cluster_sync_all();  // peer barriers must be initialised before remote arrives
@@ -841,6 +996,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;        // accumulator row == TMEM lane
     const uint32_t peer = cta_rank ^ 1u;
+    [[maybe_unused]] float dg_acc[8], db_acc[8];  // mode 3: this lane's column sums (column = chunk * 32 + lane) over its tiles
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dg_acc[c] = db_acc[c] = 0.f;
     for (int it = team, tile = first_tile + team * tile_step; tile < g.num_tiles;
          it += Cfg::kTeams, tile += Cfg::kTeams * tile_step) {
       const int buf = team;
@@ -864,6 +1022,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ost.policy = NRSE_EXP(g.exp_flags, 8) ? 0ull : ptx::kL2EvictFirst;
       ost.exp_flags = g.exp_flags;
 
+      if constexpr (kBwdFuse) {
+        if (g.mode == 3) {
+          const long long orow = m * g.out_row_mul + g.out_row_add;   // frame of the layer below
+          const int t_prev = static_cast<int>(static_cast<unsigned>(orow) % static_cast<unsigned>(g.bw_P));
+          LnBwdEpi lb;
+          lb.valid = m < g.M_total && t_prev < g.bw_T;
+          lb.xhat_row = g.bw_xhat + (lb.valid ? orow : 0) * kC + n0;
+          lb.rstd = lb.valid ? __ldg(g.bw_rstd + orow) : 0.f;
+          lb.want_affine = g.bw_dgamma != nullptr;
+          const int slot3 = team * 2 + static_cast<int>(acc_phase);
+          EpiCtx ec;
+          ec.taddr = taddr;
+          ec.bar_tmem_empty = bar(kTmemEmpty + buf);
+          ec.stats_slot = smem_base + Cfg::kStatsOff + static_cast<uint32_t>((slot3 * kBlockM + row) * 8);
+          ec.stats_local = s_stats + slot3 * kBlockM + row;
+          ec.bar_stats = bar(kStats + team);
+          ec.stats_parity = acc_phase;
+          ec.arm = row == 0;
+          ec.peer = peer;
+          ec.s_gb = s_gb;
+          ec.ost = ost;
+          epilogue_lnbwd_row<kClusterN>(ec, lb, dg_acc, db_acc);
+          continue;
+        }
+      }
       if (g.mode == 2) {
         epilogue_bias_f32_row<kClusterN>(taddr, bar(kTmemEmpty + buf), m < g.M_total,
                                          reinterpret_cast<float*>(g.out) + m * g.out_pitch + ng * kC + n0,
@@ -903,6 +1086,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ec.tmem_empty_cluster = 0;
       ec.ost = ost;
       epilogue_row<kClusterN, kSave>(ec);
+    }
+    if constexpr (kBwdFuse) {
+      if (g.mode == 3 && g.bw_dgamma != nullptr) {  // this warp's column sums -> the layer's affine gradients
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          atomicAdd(g.bw_dgamma + n0 + c * 32 + lane, dg_acc[c]);
+          atomicAdd(g.bw_dbeta + n0 + c * 32 + lane, db_acc[c]);
+        }
+      }
     }
     if (lane == 0) ptx::bulk_wait<0>();  // this warp's output stores are complete before the CTA may exit
   }
@@ -2612,6 +2804,8 @@ constexpr int experiment_flags() { return 0; }
 int g_sm_budget = kNumSMs;  // SMs the persistent kernels of this file spread over (nrse_conv_frontend_set_sm_budget): the
                            // training step leaves a few SMs to the NCCL all-reduce kernels that run concurrently with
                            // the backward (a resident persistent CTA per SM would otherwise starve them until a kernel ends)
+int g_bwd_fusion = 0;   // 1: nrse_conv_frontend_bwd (LayerNorm mode) runs each layer's LayerNorm / GELU backward in the
+                        // epilogue of the data-gradient GEMM above it (nrse_conv_layer_dgrad_lnbwd); 0: separate kernels
 int g_tile_order = 1;   // 1: consecutive layers walk their tiles in opposite directions, so that every layer starts on the
                         // rows its producer wrote last (still in L2) instead of the ones it wrote first (long evicted); 0: all forward
 int g_l2_prefetch = 0;  // 1: producer bulk-prefetches the next tile's A rows into L2 (measured 2-3 % slower: off)
@@ -2653,13 +2847,13 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap
   return NRSE_OK;
 }
 
-template <int kClusterN, bool kSave = false>
+template <int kClusterN, bool kSave = false, bool kBwdFuse = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const GemmArgs& g,
                 cudaStream_t stream) {
   using Cfg = GemmCfg<kClusterN>;
   static bool attr_set = false;  // benign race: the attribute is idempotent
   if (!attr_set) {
-    NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<kClusterN, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<kClusterN, kSave, kBwdFuse>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -2679,7 +2873,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = NRSE_EXP(experiment_flags(), 512) ? 1 : 2;  // 512: no programmatic dependent launch (A/B timing)
-  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<kClusterN, kSave>, ta, tw, to, g));
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<kClusterN, kSave, kBwdFuse>, ta, tw, to, g));
   return NRSE_OK;
 }
 
@@ -2798,6 +2992,11 @@ int nrse_conv_frontend_set_variant(int variant) {
 int nrse_conv_frontend_set_sm_budget(int sms) {
   if (sms < 8 || sms > nrse::kNumSMs) return NRSE_ERR_INVALID_ARG;
   nrse::g_sm_budget = sms & ~1;  // CTA pairs
+  return NRSE_OK;
+}
+
+int nrse_conv_frontend_set_bwd_fusion(int on) {
+  nrse::g_bwd_fusion = on ? 1 : 0;
   return NRSE_OK;
 }
 
@@ -3156,11 +3355,47 @@ int nrse_conv_layer_wgrad(const void* dz, const void* act_prev, int64_t rows_out
   return launch_wgrad(dz, nrse::kC, act_prev, 2 * rows_out, 2, rows_out, k * nrse::kC, dw, ckpt_layout ? 1 : 0, stream);
 }
 
+namespace nrse {
+/* The LayerNorm + GELU backward of the layer BELOW, run in the data-gradient epilogue (mode 3): what that layer saved. */
+struct DgradFuse {
+  const void* xhat;     // [2*rows_out, 512] bf16
+  const float* rstd;    // [2*rows_out]
+  const float* gamma;
+  const float* beta;
+  float* dgamma;        // nullable (both or neither)
+  float* dbeta;
+  int P, T;             // frame pitch / valid frames per utterance of the layer below
+};
+static int dgrad_impl(const void* dz, int64_t rows_out, const void* wt_even, const void* wt_odd, int k, void* dx,
+                      const DgradFuse* fuse, cudaStream_t stream);
+}  // namespace nrse
+
 /* dX [2*rows_out, 512] bf16 = dZ W (transposed convolution, stride 2) as two GEMMs over even / odd input frames. */
 int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even, const void* wt_odd, int k, void* dx,
                           nrse_stream_t stream) {
-  using namespace nrse;
   if (!dz || !wt_even || !wt_odd || !dx || rows_out < 1 || (k != 2 && k != 3)) return NRSE_ERR_INVALID_ARG;
+  return nrse::dgrad_impl(dz, rows_out, wt_even, wt_odd, k, dx, nullptr, nrse::as_stream(stream));
+}
+
+/* The same with the layer below's LayerNorm + GELU backward fused into the epilogue: dx receives dZ_{i-1} rather than
+ * dOut_{i-1}, and dgamma / dbeta of that layer are accumulated. */
+int nrse_conv_layer_dgrad_lnbwd(const void* dz, int64_t rows_out, const void* wt_even, const void* wt_odd, int k,
+                                const void* xhat_prev, const float* rstd_prev, const float* gamma_prev,
+                                const float* beta_prev, void* dz_prev, float* dgamma_prev, float* dbeta_prev, int P_prev,
+                                int T_prev, nrse_stream_t stream) {
+  if (!dz || !wt_even || !wt_odd || !dz_prev || rows_out < 1 || (k != 2 && k != 3)) return NRSE_ERR_INVALID_ARG;
+  if (!xhat_prev || !rstd_prev || !gamma_prev || !beta_prev || P_prev < 1 || T_prev < 1 || T_prev > P_prev)
+    return NRSE_ERR_INVALID_ARG;
+  if ((dgamma_prev == nullptr) != (dbeta_prev == nullptr)) return NRSE_ERR_INVALID_ARG;
+  if ((2 * rows_out) % P_prev != 0) return NRSE_ERR_INVALID_ARG;
+  if (nrse::g_variant < 2) return NRSE_ERR_UNSUPPORTED;  // the fused epilogue lives in the CTA-pair kernel
+  nrse::DgradFuse f = {xhat_prev, rstd_prev, gamma_prev, beta_prev, dgamma_prev, dbeta_prev, P_prev, T_prev};
+  return nrse::dgrad_impl(dz, rows_out, wt_even, wt_odd, k, dz_prev, &f, nrse::as_stream(stream));
+}
+
+namespace nrse {
+static int dgrad_impl(const void* dz, int64_t rows_out, const void* wt_even, const void* wt_odd, int k, void* dx,
+                      const DgradFuse* fuse, cudaStream_t stream) {
   CUtensorMap ta, tw;
   int rc = make_tmap_rows(&ta, dz, rows_out, kBlockM);
   if (rc != NRSE_OK) return rc;
@@ -3177,6 +3412,14 @@ int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even,
     g.stride = 2;
     g.xhat = nullptr; g.rstd = nullptr;
     g.mode = 1;
+    if (fuse) {
+      g.mode = 3;
+      g.gamma = fuse->gamma; g.beta = fuse->beta;
+      g.bw_xhat = reinterpret_cast<const __nv_bfloat16*>(fuse->xhat);
+      g.bw_rstd = fuse->rstd;
+      g.bw_dgamma = fuse->dgamma; g.bw_dbeta = fuse->dbeta;
+      g.bw_P = fuse->P; g.bw_T = fuse->T;
+    }
     g.a_wide = 0; g.n_split = 1; g.out_pitch = kC; g.bias = nullptr;
     g.a_2d = 1;
     g.a_row_off[0] = 0;    // even: tap 0 <- dZ[m];  odd: tap 1 <- dZ[m]
@@ -3190,11 +3433,13 @@ int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even,
     CUtensorMap to;  // rows 2 m + parity of dX
     rc = make_tmap_out(&to, reinterpret_cast<const char*>(dx) + static_cast<size_t>(parity) * kC * 2, rows_out, 2);
     if (rc != NRSE_OK) return rc;
-    rc = g_variant >= 2 ? launch_gemm<2>(ta, tw, to, g, as_stream(stream)) : launch_gemm<1>(ta, tw, to, g, as_stream(stream));
+    if (fuse) rc = launch_gemm<2, false, true>(ta, tw, to, g, stream);
+    else rc = g_variant >= 2 ? launch_gemm<2>(ta, tw, to, g, stream) : launch_gemm<1>(ta, tw, to, g, stream);
     if (rc != NRSE_OK) return rc;
   }
   return NRSE_OK;
 }
+}  // namespace nrse
 
 size_t nrse_conv_frontend_bwd_workspace_bytes(int B, int L) {
   int32_t T[nrse::kLayers], P[nrse::kLayers];
@@ -3217,6 +3462,7 @@ int nrse_conv_frontend_bwd(const float* x, const nrse_frontend_params* prm, cons
   if (dy_pitch < T[kLayers - 1]) return NRSE_ERR_INVALID_ARG;
   if (workspace_bytes < nrse_conv_frontend_bwd_workspace_bytes(B, L)) return NRSE_ERR_WORKSPACE;
   const bool norm = norm_mode == NRSE_NORM_LAYER;
+  const bool fused = norm && g_bwd_fusion != 0 && g_variant >= 2;  // LayerNorm / GELU backward in the dgrad epilogue
   // which layers want what; `stop` = the lowest layer that wants anything: nothing below it is computed
   bool need_w[kLayers], need_aff[kLayers];
   int stop = kLayers;
@@ -3240,12 +3486,15 @@ int nrse_conv_frontend_bwd(const float* x, const nrse_frontend_params* prm, cons
       return nrse_conv_layer0_gn_bwd(x, dz, t.xhat[0], tape_gn_rstd(t, B), prm->gamma[0], prm->beta[0], grads->dw0,
                                      grads->dgamma[0], grads->dbeta[0], gn_scratch, B, L, T[0], P[0], stream);
     }
-    // dOut_i (dy for the last layer, else the dgrad output already sitting in dz) -> dZ_i, in place
-    rc = nrse_ln_gelu_bwd(last ? static_cast<const void*>(dy) : static_cast<const void*>(dz),
-                          last ? NRSE_DTYPE_F32 : NRSE_DTYPE_BF16, last ? dy_pitch : P[i], t.xhat[i],
-                          norm ? t.rstd[i] : nullptr, norm ? prm->gamma[i] : nullptr, norm ? prm->beta[i] : nullptr, dz,
-                          grads->dgamma[i], grads->dbeta[i], rows, P[i], T[i], stream);
-    if (rc != NRSE_OK) return rc;
+    // dOut_i (dy for the last layer, else the dgrad output already sitting in dz) -> dZ_i, in place; with the fused
+    // data gradient the layer above has already left dZ_i (and this layer's affine gradients) behind
+    if (last || !fused) {
+      rc = nrse_ln_gelu_bwd(last ? static_cast<const void*>(dy) : static_cast<const void*>(dz),
+                            last ? NRSE_DTYPE_F32 : NRSE_DTYPE_BF16, last ? dy_pitch : P[i], t.xhat[i],
+                            norm ? t.rstd[i] : nullptr, norm ? prm->gamma[i] : nullptr, norm ? prm->beta[i] : nullptr, dz,
+                            grads->dgamma[i], grads->dbeta[i], rows, P[i], T[i], stream);
+      if (rc != NRSE_OK) return rc;
+    }
     if (i == 0) {
       if (need_w[0]) rc = nrse_conv_layer0_wgrad(x, dz, grads->dw0, B, L, T[0], P[0], stream);
       return rc;
@@ -3255,7 +3504,12 @@ int nrse_conv_frontend_bwd(const float* x, const nrse_frontend_params* prm, cons
       if (rc != NRSE_OK) return rc;
     }
     if (i > stop) {
-      rc = nrse_conv_layer_dgrad(dz, rows, wb->wt_even[i - 1], wb->wt_odd[i - 1], kKernel[i], buf[(i - 1) & 1], stream);
+      if (fused)
+        rc = nrse_conv_layer_dgrad_lnbwd(dz, rows, wb->wt_even[i - 1], wb->wt_odd[i - 1], kKernel[i], t.xhat[i - 1],
+                                         t.rstd[i - 1], prm->gamma[i - 1], prm->beta[i - 1], buf[(i - 1) & 1],
+                                         grads->dgamma[i - 1], grads->dbeta[i - 1], P[i - 1], T[i - 1], stream);
+      else
+        rc = nrse_conv_layer_dgrad(dz, rows, wb->wt_even[i - 1], wb->wt_odd[i - 1], kKernel[i], buf[(i - 1) & 1], stream);
       if (rc != NRSE_OK) return rc;
     }
   }

@@ -663,6 +663,7 @@ def conv_frontend(x: Tensor, conv_weights: Sequence[Tensor], gammas: Sequence[Op
 
 DEFAULT_FRONTEND_VARIANT = 4  # see nrse_conv_frontend_set_variant (include/nrse_b200.h)
 DEFAULT_LAYER0_VARIANT = 3    # see nrse_conv_frontend_set_layer0_variant
+DEFAULT_BWD_FUSION = False    # see nrse_conv_frontend_set_bwd_fusion
 
 
 def set_frontend_variant(variant: int) -> None:
@@ -695,6 +696,11 @@ def set_sm_budget(sms: int) -> None:
     """SMs the persistent conv-frontend kernels spread over (148 = all).  The data-parallel step lowers it while a
     gradient all-reduce is in flight so that NCCL's kernels find free SMs (see include/nrse_b200.h)."""
     check(_lib.load().nrse_conv_frontend_set_sm_budget(int(sms)), "nrse_conv_frontend_set_sm_budget")
+
+
+def set_bwd_fusion(on: bool) -> None:
+    """LayerNorm / GELU backward of layers 0-5 inside the data-gradient epilogue of the layer above (see the header)."""
+    check(_lib.load().nrse_conv_frontend_set_bwd_fusion(1 if on else 0), "nrse_conv_frontend_set_bwd_fusion")
 
 
 def set_tile_order(alternate: int) -> None:
@@ -898,6 +904,19 @@ def conv_layer_dgrad(dz: Tensor, wt_even: Tensor, wt_odd: Tensor, k: int) -> Ten
     check(lib.nrse_conv_layer_dgrad(_ptr(dz), dz.shape[0], _ptr(wt_even), _ptr(wt_odd), k, _ptr(dx), _stream()),
           "nrse_conv_layer_dgrad")
     return dx
+
+
+def conv_layer_dgrad_lnbwd(dz: Tensor, wt_even: Tensor, wt_odd: Tensor, k: int, xhat_prev: Tensor, rstd_prev: Tensor,
+                           gamma_prev: Tensor, beta_prev: Tensor, P_prev: int, T_prev: int, want_affine: bool = True):
+    """Data gradient of layer i fused with the LayerNorm + GELU backward of layer i-1 -> (dZ_{i-1}, dgamma, dbeta)."""
+    lib = _lib.load()
+    dzp = torch.empty(2 * dz.shape[0], 512, dtype=torch.bfloat16, device=dz.device)
+    dg = torch.zeros(512, dtype=torch.float32, device=dz.device) if want_affine else None
+    db = torch.zeros(512, dtype=torch.float32, device=dz.device) if want_affine else None
+    check(lib.nrse_conv_layer_dgrad_lnbwd(_ptr(dz), dz.shape[0], _ptr(wt_even), _ptr(wt_odd), k, _ptr(xhat_prev),
+                                          _ptr(rstd_prev), _ptr(gamma_prev), _ptr(beta_prev), _ptr(dzp), _ptr(dg),
+                                          _ptr(db), int(P_prev), int(T_prev), _stream()), "nrse_conv_layer_dgrad_lnbwd")
+    return dzp, dg, db
 
 
 def conv_layer0_wgrad(x: Tensor, dz0: Tensor, T0: int, P0: int) -> Tensor:

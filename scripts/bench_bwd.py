@@ -34,9 +34,18 @@ def timeit(fn, n=5, repeats=3):
 
 t_fwd, _ = timeit(lambda: ops.conv_frontend(x, w, g, b, "layer", out_dtype=torch.bfloat16, packed=packed))
 t_train, (y, tape) = timeit(lambda: ops.conv_frontend_train(x, w, g, b, "layer", packed=packed))
-t_bwd, _ = timeit(lambda: ops.conv_frontend_backward(x, w, g, b, tape, gy, "layer", dgrad_packs=dpacks))
+bwd = lambda: ops.conv_frontend_backward(x, w, g, b, tape, gy, "layer", dgrad_packs=dpacks)
+ops.set_bwd_fusion(False)
+t_bwd_sep, _ = timeit(bwd)
+ops.set_bwd_fusion(True)      # LayerNorm / GELU backward inside the data-gradient epilogue
+t_bwd_fused, _ = timeit(bwd)
+ops.set_bwd_fusion(False)
+t_bwd_sep = min(t_bwd_sep, timeit(bwd)[0])
+ops.set_bwd_fusion(ops.DEFAULT_BWD_FUSION)
+t_bwd = t_bwd_fused if ops.DEFAULT_BWD_FUSION else t_bwd_sep
 if "--quick" in sys.argv:
-    print(json.dumps({"shape": [B, L], "fwd_ms": t_fwd, "train_fwd_ms": t_train, "bwd_ms": t_bwd}))
+    print(json.dumps({"shape": [B, L], "fwd_ms": t_fwd, "train_fwd_ms": t_train, "bwd_ms": t_bwd,
+                      "bwd_separate_ms": t_bwd_sep, "bwd_fused_ms": t_bwd_fused}))
     sys.exit(0)
 fwd_flops = sum(2.0 * B * T[i] * 512 * 512 * k for i, k in enumerate((10, 3, 3, 3, 3, 2, 2)) if i > 0)
 # stock torch (cuDNN / ATen) forward+backward of the same stack for comparison, fp32 and bf16 autocast

@@ -83,6 +83,48 @@ def test_wgrad_and_dgrad_vs_autograd(dev, k, rows_out):
     assert rel_err(dx.float().cpu().numpy(), dx_ref.numpy()) < 6e-3   # bf16 output rounding
 
 
+@pytest.mark.parametrize("k,B,P_prev,T_prev", [(3, 3, 128, 121), (2, 2, 256, 250), (3, 5, 640, 639), (2, 64, 24, 21)])
+def test_dgrad_with_fused_ln_gelu_bwd_vs_autograd(dev, k, B, P_prev, T_prev):
+    """One kernel: dX = dZ W (transposed stride-2 conv) -> LayerNorm + GELU backward of the layer below
+    (hf:models/wavlm/modeling_wavlm.py:250-275 twice over, through autograd).  Checked against autograd on the same
+    operands and against the two-kernel native path it replaces."""
+    rs = np.random.RandomState(k * 11 + P_prev)
+    rows_prev, rows_out = B * P_prev, B * P_prev // 2
+    valid = torch.from_numpy((np.arange(rows_prev) % P_prev) < T_prev)
+    zp = torch.from_numpy((rs.standard_normal((rows_prev, 512)) * 1.5 + 0.3).astype(np.float32)).requires_grad_(True)
+    gamma = torch.from_numpy((1 + 0.1 * rs.standard_normal(512)).astype(np.float32)).requires_grad_(True)
+    beta = torch.from_numpy((0.1 * rs.standard_normal(512)).astype(np.float32)).requires_grad_(True)
+    w = torch.from_numpy((rs.standard_normal((512, 512, k)) * np.sqrt(2.0 / (512 * k))).astype(np.float32))
+    dz = torch.from_numpy(rs.standard_normal((rows_out, 512)).astype(np.float32)).bfloat16()
+    # the layer above sees zero gradient on its own padding frames (as the real backward guarantees)
+    T_out = (T_prev - k) // 2 + 1
+    dz = dz * torch.from_numpy((np.arange(rows_out) % (P_prev // 2)) < T_out)[:, None]
+    act = F.gelu(F.layer_norm(zp, (512,), gamma, beta, 1e-5)) * valid[:, None]
+    a = torch.cat([act, torch.zeros(2, 512)], 0)
+    h = F.conv1d(a.t()[None], w.bfloat16().float(), stride=2)[0].t()[:rows_out]
+    h.backward(dz.float())
+    mean = zp.detach().mean(1, keepdim=True)
+    rstd = 1.0 / torch.sqrt(zp.detach().var(1, unbiased=False, keepdim=True) + 1e-5)
+    xhat = ((zp.detach() - mean) * rstd).bfloat16().to(dev)
+    rstd_d, g_d, b_d = rstd.flatten().to(dev), gamma.detach().to(dev), beta.detach().to(dev)
+    even, odd = ops.pack_conv_weight_dgrad(w.to(dev))
+    got, dg, db = ops.conv_layer_dgrad_lnbwd(dz.to(dev), even, odd, k, xhat, rstd_d, g_d, b_d, P_prev, T_prev)
+    ref = zp.grad * valid[:, None]
+    assert rel_err(got.float().cpu().numpy(), ref.numpy()) < 1e-2
+    assert rel_err(dg.cpu().numpy(), gamma.grad.numpy()) < 1e-2
+    assert rel_err(db.cpu().numpy(), beta.grad.numpy()) < 1e-2
+    assert not got.float().cpu()[~valid].any()              # pitch padding carries zero gradient
+    # against the two kernels it replaces (those round dX to bf16 in between; the fused form keeps it in fp32)
+    dx = ops.conv_layer_dgrad(dz.to(dev), even, odd, k)
+    two, dg2, db2 = ops.ln_gelu_bwd(dx, xhat, rstd_d, g_d, b_d, P_prev, T_prev)
+    assert rel_err(got.float().cpu().numpy(), two.float().cpu().numpy()) < 8e-3
+    assert rel_err(dg.cpu().numpy(), dg2.cpu().numpy()) < 8e-3 and rel_err(db.cpu().numpy(), db2.cpu().numpy()) < 8e-3
+    # without the affine gradients (frozen LayerNorm): same dZ, nothing else written
+    only, none_g, none_b = ops.conv_layer_dgrad_lnbwd(dz.to(dev), even, odd, k, xhat, rstd_d, g_d, b_d, P_prev, T_prev,
+                                                      want_affine=False)
+    assert none_g is None and none_b is None and torch.equal(only, got)
+
+
 def test_layer0_wgrad_vs_autograd(dev):
     rs = np.random.RandomState(3)
     B, L = 3, 4000
@@ -120,8 +162,17 @@ def _dev_params(layers, dev, n_norm):
 FULL_BWD_TOL = {i: 2.0e-2 for i in range(7)}
 
 
+@pytest.fixture(params=[False, True], ids=["separate", "fused"])
+def bwd_fusion(request):
+    """Both forms of the LayerNorm-mode backward: LayerNorm / GELU backward as kernels of their own, or inside the
+    data-gradient epilogue of the layer above."""
+    ops.set_bwd_fusion(request.param)
+    yield request.param
+    ops.set_bwd_fusion(ops.DEFAULT_BWD_FUSION)
+
+
 @pytest.mark.parametrize("B,L", [(2, 4000), (3, 16000)])
-def test_full_backward_vs_autograd(dev, B, L):
+def test_full_backward_vs_autograd(dev, B, L, bwd_fusion):
     layers = synthetic.frontend_weights("layer", seed=9)
     x = synthetic.waveforms(B, L, seed=5)[0]
     x = ((x - x.mean(1, keepdims=True)) / x.std(1, keepdims=True)).astype(np.float32)
@@ -179,7 +230,7 @@ def test_full_backward_group_mode_vs_autograd(dev, B, L):
     assert max(e_g, e_b) < FULL_BWD_TOL[0], (e_g, e_b)
 
 
-def test_backward_honours_needs_grad_mask(dev):
+def test_backward_honours_needs_grad_mask(dev, bwd_fusion):
     """Partial unfreeze (ref:src/models/emotion.py:114-129): only what is asked for is computed; what IS computed equals
     the corresponding tensors of the full backward (same kernels, same order), the rest comes back as None."""
     B, L = 2, 6000
@@ -205,7 +256,7 @@ def test_backward_honours_needs_grad_mask(dev):
     assert all(t is None for part in nothing for t in part)
 
 
-def test_full_size_backward(dev):
+def test_full_size_backward(dev, bwd_fusion):
     """BASELINE shape 64 x 64 000 (split-K weight gradients over M = 409 536 frames, fp32 atomics, 3.3 GB tape).
     (1) Frame independence: the gradients of the whole batch equal the SUM of the gradients of its eight 8-utterance
     chunks run separately (differences = fp32 summation order only).  (2) Chunk 0 against torch autograd on the fp32
