@@ -660,6 +660,11 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
 
     hbm = peaks["hbm_gbs"]
     kernels = []
+    # the >= 2 s sustained replay above leaves the board power-capped (~1.45 GHz); the kernels below are timed ALONE against the
+    # burst copy bandwidth of MEASURED_PEAKS.json, and the latency-bound ones among them (mix at B = 64) follow the SM clock:
+    # let the clocks recover first (round 2 measured 24 us instead of 17 us for the same mix kernel without this pause)
+    torch.cuda.synchronize()
+    time.sleep(2.0)
     # 6 distinct input sets (6 x 65 MB in+out > 126 MB L2) cycled inside the graph: every launch reads from HBM
     sets = [(clean_d.clone(), noise_d.clone()) for _ in range(6)]
     t_mix = ev_time(lambda i=0: ops.mix_normalize(sets[i % 6][0], sets[i % 6][1], snr_d, snr_list, True), n=24)

@@ -374,7 +374,8 @@ int nrse_conv_layer_dgrad(const void* dz, int64_t rows_out, const void* wt_even,
  * receives dZ_{i-1}; dgamma_prev / dbeta_prev (both or neither, fp32 [512]) are accumulated into.  xhat_prev / rstd_prev:
  * what nrse_conv_frontend_fwd_train saved for layer i-1 (frame pitch P_prev, T_prev valid frames per utterance; padding
  * frames get zeros).  Replaces the autograd backward of Conv1d -> LayerNorm -> GELU across two layers,
- * hf:models/wavlm/modeling_wavlm.py:250-275.  NRSE_ERR_UNSUPPORTED under set_variant(1). */
+ * hf:models/wavlm/modeling_wavlm.py:250-275.  As for nrse_conv_layer_dgrad, the rows of dz that belong to pitch padding
+ * must be zero (every kernel of this library that writes a gradient buffer leaves them so). */
 int nrse_conv_layer_dgrad_lnbwd(const void* dz, int64_t rows_out, const void* wt_even, const void* wt_odd, int k,
                                 const void* xhat_prev, const float* rstd_prev, const float* gamma_prev,
                                 const float* beta_prev, void* dz_prev, float* dgamma_prev, float* dbeta_prev, int P_prev,

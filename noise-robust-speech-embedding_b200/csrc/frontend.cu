@@ -386,14 +386,6 @@ struct GemmArgs {
   // output row (mode 2); bias = [n_split * 512] fp32 (mode 2)
   int a_wide, n_split, out_pitch;
   const float* bias;
-  // mode 3 (data gradient with the LayerNorm + GELU backward of the layer BELOW fused into the epilogue): the accumulator
-  // row 2 m + parity is dOut of layer i-1; with that layer's saved xhat / 1/std (tape) and its gamma / beta (g.gamma, g.beta)
-  // the epilogue emits dZ of layer i-1 (bf16, through `out` / tmap_out) and accumulates its dgamma / dbeta (nullable)
-  const __nv_bfloat16* bw_xhat = nullptr;  // [rows_prev, 512]
-  const float* bw_rstd = nullptr;          // [rows_prev]
-  float* bw_dgamma = nullptr;
-  float* bw_dbeta = nullptr;
-  int bw_P = 1, bw_T = 1;                // frame pitch / valid frames per utterance of layer i-1
   // L2 prefetch of the NEXT tile's A rows (they come from HBM; the weights are L2-resident): base pointer and row count
   const char* a_ptr;
   long long a_rows;
@@ -726,128 +718,366 @@ __device__ __forceinline__ float warp_transpose_sum32(const float (&v)[32], int 
   return a[0];
 }
 
-// Mode-3 epilogue: the accumulator row is dOut of the layer below; LayerNorm + GELU backward of that layer runs here, on the
-// fp32 accumulator, instead of in a separate elementwise kernel behind a bf16 round trip through HBM:
-//   dv = dOut gelu'(xhat gamma + beta),  dxh = dv gamma,  dZ = rstd (dxh - mean(dxh) - xhat mean(dxh xhat)),
-//   dgamma += sum_rows dv xhat,  dbeta += sum_rows dv.
-// One thread = one frame, this CTA's 256 channels.  Pass 1 reads the accumulator and the frame's xhat (row-owner 64-byte
-// loads), writes dxh back INTO the accumulator (tcgen05.st) and collects the two row sums; the CTA pair exchanges them like
-// the forward exchanges its LayerNorm partials (st.async + mbarrier complete_tx); pass 2 re-reads dxh and xhat and emits dZ
-// through the staging buffer + TMA store.  Column sums for dgamma / dbeta: a warp-level transpose reduction per 32-channel
-// chunk, accumulated per lane across the tiles of the launch (dg_acc / db_acc: column = chunk * 32 + lane).
-struct LnBwdEpi {
-  const __nv_bfloat16* xhat_row;  // this frame's xhat, first channel of this CTA
-  float rstd;
-  bool valid;                     // false: pitch padding / past the end -> dZ = 0, no contribution to any sum
-  bool want_affine;
-};
 
-template <int kClusterN>
-__device__ __forceinline__ void epilogue_lnbwd_row(const EpiCtx& e, const LnBwdEpi& b, float (&dg_acc)[8], float (&db_acc)[8]) {
-  static_assert(kClusterN == 2, "the fused backward epilogue exchanges its row sums inside a CTA pair");
-  constexpr int kChunks = 8;  // 256 channels per CTA
-  const float2* s_gamma2 = e.s_gb;               // [128] pairs of gamma, then [128] pairs of beta (NOT halved in this mode)
-  const float2* s_beta2 = e.s_gb + 128;
-  const uint4* xrow = reinterpret_cast<const uint4*>(b.xhat_row);
-  uint32_t ra[32];
-  uint4 xw[4], xn[4];
-  auto load_x = [&](int c, uint4 (&x)[4]) {
-    if (b.valid) {
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// The same on 16 packed bf16 pairs per lane (word j = columns 2j, 2j+1 of the lane's row): the first two butterfly steps add
+// packed pairs (two bf16 roundings on partial sums of 2 and 4 rows -- unbiased, and the 25 000 partials of a launch are added
+// in fp32), the last three run in fp32.  19 shuffles instead of 31, half the selects.
+__device__ __forceinline__ float warp_transpose_sum32_bf16(const uint32_t (&v)[16], int lane) {
+  uint32_t a[8];
+  {
+    const bool up = (lane & 16) != 0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) x[q] = __ldg(xrow + c * 4 + q);
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) x[q] = make_uint4(0, 0, 0, 0);
-    }
-  };
-  auto xpair = [](const uint4 (&x)[4], int j) -> f2 {  // pair j (0..15) of the chunk as fp32x2
-    const uint32_t w = j & 3;
-    const uint4& q = x[j >> 2];
-    const uint32_t bits = w == 0 ? q.x : (w == 1 ? q.y : (w == 2 ? q.z : q.w));
-    return f2_bits(bits << 16, bits & 0xffff0000u);
-  };
-  if (e.arm) ptx::mbar_arrive_expect_tx(e.bar_stats, kBlockM * 8);  // 128 peer rows x (s1, s2)
-  f2 s1 = f2_make(0.f, 0.f), s2 = s1;
-  load_x(0, xw);
-#pragma unroll 1
-  for (int c = 0; c < kChunks; ++c) {
-    ptx::tmem_ld32(e.taddr + c * 32, ra);
-    if (c + 1 < kChunks) load_x(c + 1, xn);
-    ptx::tmem_ld_wait();
-    float dv[32];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const f2 x = xpair(xw, j);
-      const float2 gm = s_gamma2[c * 16 + j], bt = s_beta2[c * 16 + j];
-      const f2 g2 = f2_make(gm.x, gm.y);
-      f2 acc = f2_bits(ra[2 * j], ra[2 * j + 1]);
-      if (!b.valid) acc = f2_make(0.f, 0.f);
-      const f2 d = f2_mul(acc, gelu_grad2(f2_fma(x, g2, f2_make(bt.x, bt.y))));
-      f2_split(d, dv[2 * j], dv[2 * j + 1]);
-      const f2 dxh = f2_mul(d, g2);
-      s1 = f2_add(s1, dxh);
-      s2 = f2_fma(dxh, x, s2);
-      float h0, h1;
-      f2_split(dxh, h0, h1);
-      ra[2 * j] = __float_as_uint(h0);
-      ra[2 * j + 1] = __float_as_uint(h1);
-    }
-    ptx::tmem_st32(e.taddr + c * 32, ra);  // dxh replaces dOut in the accumulator
-    if (b.want_affine) {
-      db_acc[c] += warp_transpose_sum32(dv, e.ost.lane);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x0, x1;
-        f2_split(xpair(xw, j), x0, x1);
-        dv[2 * j] *= x0;
-        dv[2 * j + 1] *= x1;
-      }
-      dg_acc[c] += warp_transpose_sum32(dv, e.ost.lane);
-    }
-    if (c + 1 < kChunks) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) xw[q] = xn[q];
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t send = up ? v[j] : v[j + 8], keep = up ? v[j + 8] : v[j];
+      a[j] = add_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 16));
     }
   }
-  ptx::tmem_st_wait();
-  float a0, a1, c0, c1;
-  f2_split(s1, a0, a1);
-  f2_split(s2, c0, c1);
-  const float sum1 = a0 + a1, sum2 = c0 + c1;
-  ptx::st_async_f2(ptx::mapa(e.stats_slot, e.peer), sum1, sum2, ptx::mapa(e.bar_stats, e.peer));
-  ptx::mbar_wait(e.bar_stats, e.stats_parity);
-  const float2 o = *e.stats_local;
-  const float m1 = (sum1 + o.x) * (1.0f / kC), m2 = (sum2 + o.y) * (1.0f / kC);
-  const f2 rs2 = f2_make(b.rstd, b.rstd), nm1 = f2_make(-m1 * b.rstd, -m1 * b.rstd), nm2 = f2_make(-m2 * b.rstd, -m2 * b.rstd);
-  // pass 2: dZ = rstd (dxh - m1 - xhat m2)
-  load_x(0, xw);
-#pragma unroll 1
-  for (int c = 0; c < kChunks; ++c) {
-    ptx::tmem_ld32(e.taddr + c * 32, ra);
-    if (c + 1 < kChunks) load_x(c + 1, xn);
-    ptx::tmem_ld_wait();
-    if (c + 1 == kChunks) {  // the accumulator is read for the last time: hand it back to the MMA warp
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(e.bar_tmem_empty);
-    }
-    uint32_t z16[16];
+  {
+    const bool up = (lane & 8) != 0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float z0, z1;
-      f2_split(f2_fma(xpair(xw, j), nm2, f2_fma(f2_bits(ra[2 * j], ra[2 * j + 1]), rs2, nm1)), z0, z1);
-      z16[j] = b.valid ? pack_bf16x2(z0, z1) : 0u;
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t send = up ? a[j] : a[j + 4], keep = up ? a[j + 4] : a[j];
+      a[j] = add_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8));
     }
-    out_stage_store(e.ost, z16, c * 32);
-    if (c + 1 < kChunks) {
+  }
+  float f[8];  // words 0..3 = 8 columns
 #pragma unroll
-      for (int q = 0; q < 4; ++q) xw[q] = xn[q];
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(a[j] << 16);
+    f[2 * j + 1] = __uint_as_float(a[j] & 0xffff0000u);
+  }
+#pragma unroll
+  for (int half = 4; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = up ? f[j] : f[j + half], keep = up ? f[j + half] : f[j];
+      f[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
     }
+  }
+  return f[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Data gradient of layer i with the LayerNorm + GELU backward of layer i-1 in its epilogue (nrse_conv_layer_dgrad_lnbwd).
+//
+// The accumulator row 2 m + parity is dOut of layer i-1; with that layer's saved xhat / 1/std (tape) and its gamma / beta
+//   dv = dOut gelu'(xhat gamma + beta),  dxh = dv gamma,  dZ = rstd (dxh - mean(dxh) - xhat mean(dxh xhat)),
+//   dgamma += sum_rows dv xhat,  dbeta += sum_rows dv
+// run on the fp32 accumulator instead of in an elementwise kernel behind a bf16 round trip through HBM.  The elementwise
+// work is ~20 instructions per element against a K = 512 / 1024 GEMM: the kernel is bound by what its epilogue warps can
+// issue, so it is built around them -- a CTA pair splits the 512 channels (as conv_gemm_kernel<2>), each CTA runs SIXTEEN
+// epilogue warps (two per TMEM lane quadrant and accumulator buffer, 128 channels each) next to the TMA and MMA warps:
+//   pass 1: accumulator + the frame's xhat (row-owner loads, requested before the accumulator is waited for) -> dv, the two
+//           row sums; (bf16 dv | bf16 xhat) pairs go back INTO the accumulator columns (tcgen05.st), so pass 2 reads nothing
+//           from global memory;
+//   row sums: 4 partials per frame (2 column halves x 2 CTAs) -- the partner warp through shared memory and a 64-thread
+//           named barrier, the peer CTA through st.async + mbarrier complete_tx (as the forward's LayerNorm statistics);
+//   pass 2: dZ from the packed accumulator -> staging buffer -> TMA store (rows 2 m + parity); column sums of dv and
+//           dv xhat by a warp-level transpose reduction into a per-warp shared-memory array, added up per CTA at the end
+//           (one atomic per channel and CTA).
+// Frames of the pitch padding (t >= T) and rows past the end read xhat = 0, 1/std = 0 and produce dZ = 0; their
+// accumulator rows are zero because the gradient rows that feed them are (precondition shared with the plain dgrad).
+struct DgLnCfg {
+  static constexpr int kNPC = kC / 2;                    // channels per CTA
+  static constexpr int kNumMma = kNPC / kUmmaN;
+  static constexpr int kEpiWarps = 16;                   // [64-channel quarter 4][lane quadrant 4], all on the same tile
+  static constexpr int kThreads = 64 + kEpiWarps * 32;   // warp 0 TMA, warp 1 MMA
+  static constexpr int kStages = 3;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = kNPC * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutOff = kStages * kStageBytes;                  // one staging buffer per epilogue warp
+  static constexpr int kGbOff = kOutOff + kEpiWarps * kOutStageBytes;    // gamma[256] then beta[256]
+  static constexpr int kPeerOff = kGbOff + kNPC * 8;                     // peer CTA's row partials [tile parity][quarter][128] float2
+  static constexpr int kLocOff = kPeerOff + 8 * kBlockM * 8;             // this CTA's row partials, same shape
+  static constexpr int kColOff = kLocOff + 8 * kBlockM * 8;              // column sums [warp][dbeta | dgamma][64] float
+  static constexpr int kBarOff = kColOff + kEpiWarps * 2 * 64 * 4;
+  static constexpr int kNumBars = 2 * kStages + 4 + 2;
+  static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr int kSmemBytes = kTmemPtrOff + 16 + 1024;
+};
+static_assert(DgLnCfg::kSmemBytes <= 232448, "shared memory budget");
+
+struct DgLnArgs {
+  int M_total;          // rows of dZ_i = accumulator rows of one parity
+  int num_tiles;
+  int k_stages;         // 8 per 512-wide K block
+  int a_row_off[2];     // row shift of K block 0 / 1
+  int parity;           // output row = 2 m + parity
+  int reverse;
+  const float* gamma;   // layer i-1
+  const float* beta;
+  const __nv_bfloat16* xhat;  // [2 * M_total, 512]
+  const float* rstd;          // [2 * M_total]
+  float* dgamma;        // nullable (both)
+  float* dbeta;
+  int P, T;             // frame pitch / valid frames per utterance of layer i-1
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_line(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+__global__ void __launch_bounds__(DgLnCfg::kThreads, 1)
+dgrad_lnbwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                   const __grid_constant__ CUtensorMap tmap_out, const DgLnArgs g) {
+  using Cfg = DgLnCfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const int n0 = static_cast<int>(cta_rank) * Cfg::kNPC;
+
+  auto bar = [&](int i) { return smem_base + Cfg::kBarOff + 8u * static_cast<uint32_t>(i); };
+  const int kFull = 0, kEmpty = Cfg::kStages, kTmemFull = 2 * Cfg::kStages, kTmemEmpty = kTmemFull + 2, kStats = kTmemEmpty + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + Cfg::kTmemPtrOff);
+  float* s_gb = reinterpret_cast<float*>(smem + Cfg::kGbOff);
+  float* s_col = reinterpret_cast<float*>(smem + Cfg::kColOff);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_w);
+    ptx::prefetch_tmap(&tmap_out);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(bar(kFull + s), 1);
+      ptx::mbar_init(bar(kEmpty + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(bar(kTmemFull + b), 1);
+      ptx::mbar_init(bar(kTmemEmpty + b), Cfg::kEpiWarps * 32);
+      ptx::mbar_init(bar(kStats + b), 1);        // (one used) armed per tile with expect_tx; the peer's st.async complete the bytes
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_smem), 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
+  for (int i = threadIdx.x; i < Cfg::kNPC; i += Cfg::kThreads) {
+    s_gb[i] = g.gamma[n0 + i];
+    s_gb[Cfg::kNPC + i] = g.beta[n0 + i];
+  }
+  for (int i = threadIdx.x; i < Cfg::kEpiWarps * 2 * 64; i += Cfg::kThreads) s_col[i] = 0.f;
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int first_tile = static_cast<int>(blockIdx.x) >> 1, tile_step = static_cast<int>(gridDim.x) >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first_tile; tile < g.num_tiles; tile += tile_step) {
+        const int m0 = (g.reverse ? g.num_tiles - 1 - tile : tile) * kBlockM;
+        for (int kb = 0; kb < g.k_stages; ++kb) {
+          ptx::mbar_wait(bar(kEmpty + stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes, b_dst = a_dst + Cfg::kABytes;
+          ptx::mbar_arrive_expect_tx(bar(kFull + stage), Cfg::kStageBytes);
+          ptx::tma_load_2d(a_dst, &tmap_a, bar(kFull + stage), (kb & 7) * kBlockK, m0 + g.a_row_off[kb >> 3]);
+#pragma unroll
+          for (int h = 0; h < Cfg::kNumMma; ++h)
+            ptx::tma_load_2d(b_dst + h * (kUmmaN * kBlockK * 2), &tmap_w, bar(kFull + stage), kb * kBlockK, n0 + h * kUmmaN);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, kUmmaN);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = first_tile; tile < g.num_tiles; tile += tile_step, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = static_cast<uint32_t>(it >> 1) & 1u;
+        ptx::mbar_wait(bar(kTmemEmpty + buf), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(buf * Cfg::kNPC);
+        for (int kb = 0; kb < g.k_stages; ++kb) {
+          ptx::mbar_wait(bar(kFull + stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t a_src = smem_base + stage * Cfg::kStageBytes, b_src = a_src + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = ptx::umma_desc_sw128(a_src + k * (kUmmaK * 2));
+#pragma unroll
+            for (int h = 0; h < Cfg::kNumMma; ++h) {
+              const uint64_t db = ptx::umma_desc_sw128(b_src + h * (kUmmaN * kBlockK * 2) + k * (kUmmaK * 2));
+              ptx::umma_bf16(tmem_acc + h * kUmmaN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit(bar(kEmpty + stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(bar(kTmemFull + buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue ====================================================================================================
+    // All sixteen warps work on the SAME tile (accumulator buffer it & 1) while the MMA warp fills the other buffer with the
+    // next one: warp = (TMEM lane quadrant, 64-channel quarter of this CTA's 256).
+    const int e = warp - 2;
+    const int colq = e >> 2;                 // which 64 of this CTA's 256 channels
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const uint32_t peer = cta_rank ^ 1u;
+    const bool want_affine = g.dgamma != nullptr;
+    const float2* s_gamma2 = reinterpret_cast<const float2*>(s_gb) + colq * 32;
+    const float2* s_beta2 = reinterpret_cast<const float2*>(s_gb + Cfg::kNPC) + colq * 32;
+    float* my_col = s_col + e * 128;         // [dbeta 64 | dgamma 64] of this warp's channels
+    float2* s_loc = reinterpret_cast<float2*>(smem + Cfg::kLocOff);
+    const float2* s_peer = reinterpret_cast<const float2*>(smem + Cfg::kPeerOff);
+    OutStage ost;
+    ost.tmap = &tmap_out;
+    ost.tmap2 = nullptr;
+    ost.smem = smem_base + Cfg::kOutOff + static_cast<uint32_t>(e * kOutStageBytes);
+    ost.col0 = n0 + colq * 64;
+    ost.lane = lane;
+    ost.policy = ptx::kL2EvictFirst;
+    ost.exp_flags = 0;
+    int it = 0;
+    for (int tile = first_tile; tile < g.num_tiles; tile += tile_step, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(it >> 1) & 1u;
+      const long long m = static_cast<long long>(g.reverse ? g.num_tiles - 1 - tile : tile) * kBlockM + row;
+      const long long orow = 2 * m + g.parity;   // frame of the layer below (row of xhat / rstd / the output)
+      const int t_prev = static_cast<int>(static_cast<unsigned>(orow) % static_cast<unsigned>(g.P));
+      const bool valid = m < g.M_total && t_prev < g.T;
+      // everything that does not depend on the accumulator is requested before waiting for it: 1/std and this frame's 64 xhat
+      const float rstd = valid ? __ldg(g.rstd + orow) : 0.f;
+      const int slot = (it & 1) * 4;             // [tile parity][column quarter][row]
+      if (row == 0 && colq == 0) ptx::mbar_arrive_expect_tx(bar(kStats), 4 * kBlockM * 8);
+      uint4 xw[8];
+      if (valid) {
+        const uint4* xrow = reinterpret_cast<const uint4*>(g.xhat + orow * kC + n0 + colq * 64);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xw[q] = __ldg(xrow + q);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xw[q] = make_uint4(0, 0, 0, 0);
+      }
+      ptx::mbar_wait(bar(kTmemFull + buf), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * Cfg::kNPC + colq * 64);
+      uint32_t ra[32];
+      // ---- pass 1 -----------------------------------------------------------------------------------------------------
+      f2 s1 = f2_make(0.f, 0.f), s2 = s1;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        ptx::tmem_ld32(taddr + c * 32, ra);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint4& xq = xw[c * 4 + (j >> 2)];
+          const uint32_t xb = (j & 3) == 0 ? xq.x : ((j & 3) == 1 ? xq.y : ((j & 3) == 2 ? xq.z : xq.w));
+          const f2 x = f2_bits(xb << 16, xb & 0xffff0000u);
+          const float2 gm = s_gamma2[c * 16 + j], bt = s_beta2[c * 16 + j];
+          const f2 g2 = f2_make(gm.x, gm.y);
+          const f2 d = f2_mul(f2_bits(ra[2 * j], ra[2 * j + 1]), gelu_grad2(f2_fma(x, g2, f2_make(bt.x, bt.y))));
+          const f2 dxh = f2_mul(d, g2);
+          s1 = f2_add(s1, dxh);
+          s2 = f2_fma(dxh, x, s2);
+          float d0, d1;
+          f2_split(d, d0, d1);
+          ra[2 * j] = pack_bf16x2(d0, d1);   // bf16 dv pair
+          ra[2 * j + 1] = xb;                // bf16 xhat pair
+        }
+        ptx::tmem_st32(taddr + c * 32, ra);
+        if (c == 1) {  // row sums out before the last chunk's column sums: those run while the partials travel
+          float a0, a1, c0, c1;
+          f2_split(s1, a0, a1);
+          f2_split(s2, c0, c1);
+          s_loc[(slot + colq) * kBlockM + row] = make_float2(a0 + a1, c0 + c1);
+          ptx::st_async_f2(ptx::mapa(smem_base + Cfg::kPeerOff + static_cast<uint32_t>(((slot + colq) * kBlockM + row) * 8), peer),
+                           a0 + a1, c0 + c1, ptx::mapa(bar(kStats), peer));
+        }
+        if (want_affine) {
+          uint32_t v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = ra[2 * j];
+          my_col[c * 32 + lane] += warp_transpose_sum32_bf16(v, lane);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = mul_bf16x2(ra[2 * j], ra[2 * j + 1]);
+          my_col[64 + c * 32 + lane] += warp_transpose_sum32_bf16(v, lane);
+        }
+      }
+      ptx::tmem_st_wait();
+      // ---- row sums: the 3 other column quarters of this CTA + the peer CTA's 4 ---------------------------------------------
+      named_bar_sync(1 + quad, 128);
+      ptx::mbar_wait(bar(kStats), static_cast<uint32_t>(it & 1));
+      float sum1 = 0.f, sum2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 a = s_loc[(slot + q) * kBlockM + row], b = s_peer[(slot + q) * kBlockM + row];
+        sum1 += a.x + b.x;
+        sum2 += a.y + b.y;
+      }
+      const float m1 = sum1 * (1.0f / kC), m2 = sum2 * (1.0f / kC);
+      const f2 rs2 = f2_make(rstd, rstd), nm1 = f2_make(-m1 * rstd, -m1 * rstd), nm2 = f2_make(-m2 * rstd, -m2 * rstd);
+      // ---- pass 2 -----------------------------------------------------------------------------------------------------
+      ost.row0 = static_cast<int>(m) - lane;
+      ost.active = ost.row0 < g.M_total;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        ptx::tmem_ld32(taddr + c * 32, ra);
+        ptx::tmem_ld_wait();
+        if (c == 1) {  // the accumulator is read for the last time: hand it back to the MMA warp
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(bar(kTmemEmpty + buf));
+        }
+        uint32_t z16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 gm = s_gamma2[c * 16 + j];
+          const f2 d = f2_bits(ra[2 * j] << 16, ra[2 * j] & 0xffff0000u);
+          const f2 x = f2_bits(ra[2 * j + 1] << 16, ra[2 * j + 1] & 0xffff0000u);
+          float z0, z1;
+          f2_split(f2_fma(x, nm2, f2_fma(f2_mul(d, f2_make(gm.x, gm.y)), rs2, nm1)), z0, z1);
+          z16[j] = pack_bf16x2(z0, z1);
+        }
+        out_stage_store(ost, z16, c * 32);
+      }
+    }
+    if (want_affine) {  // the 4 warps (lane quadrants) that share a column quarter -> one atomic per channel and CTA
+      named_bar_sync(9, Cfg::kEpiWarps * 32);
+      const int idx = e * 32 + lane;           // 0..511: [dbeta | dgamma][256 channels of this CTA]
+      const int which = idx >> 8, ch = idx & 255, cq = ch >> 6, cc = ch & 63;
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc += s_col[(cq * 4 + q) * 128 + which * 64 + cc];
+      atomicAdd((which ? g.dgamma : g.dbeta) + n0 + ch, acc);
+    }
+    if (lane == 0) ptx::bulk_wait<0>();
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
-// kBwdFuse: the instantiation that carries the mode-3 epilogue (data gradient + LayerNorm / GELU backward of the layer
-// below); a separate instantiation so that the forward / plain data-gradient kernels keep their register allocation.
-template <int kClusterN, bool kSave, bool kBwdFuse = false>
+template <int kClusterN, bool kSave>
 __global__ void __launch_bounds__(GemmCfg<kClusterN>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
@@ -895,10 +1125,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   ptx::pdl_wait();
   ptx::pdl_launch_dependents();
   const bool has_norm = g.gamma != nullptr;
-  const float gb_scale = (kBwdFuse && g.mode == 3) ? 1.0f : 0.5f;  // mode 3 (fused backward of the layer below): gamma / beta as they are
   for (int i = threadIdx.x; i < Cfg::kNPC; i += Cfg::kThreads) {  // gamma[kNPC] / 2 then beta[kNPC] / 2 (see gelu2h)
-    reinterpret_cast<float*>(s_gb)[i] = has_norm ? gb_scale * g.gamma[n0 + i] : 0.5f;
-    reinterpret_cast<float*>(s_gb)[Cfg::kNPC + i] = has_norm ? gb_scale * g.beta[n0 + i] : 0.f;
+    reinterpret_cast<float*>(s_gb)[i] = has_norm ? 0.5f * g.gamma[n0 + i] : 0.5f;
+    reinterpret_cast<float*>(s_gb)[Cfg::kNPC + i] = has_norm ? 0.5f * g.beta[n0 + i] : 0.f;
   }
   ptx::tc_fence_before();
   if constexpr (kClusterN == 2) ptx::cluster_sync_all();  // peer barriers must be initialised before remote arrives
@@ -996,9 +1225,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;        // accumulator row == TMEM lane
     const uint32_t peer = cta_rank ^ 1u;
-    [[maybe_unused]] float dg_acc[8], db_acc[8];  // mode 3: this lane's column sums (column = chunk * 32 + lane) over its tiles
-#pragma unroll
-    for (int c = 0; c < 8; ++c) dg_acc[c] = db_acc[c] = 0.f;
     for (int it = team, tile = first_tile + team * tile_step; tile < g.num_tiles;
          it += Cfg::kTeams, tile += Cfg::kTeams * tile_step) {
       const int buf = team;
@@ -1022,31 +1248,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ost.policy = NRSE_EXP(g.exp_flags, 8) ? 0ull : ptx::kL2EvictFirst;
       ost.exp_flags = g.exp_flags;
 
-      if constexpr (kBwdFuse) {
-        if (g.mode == 3) {
-          const long long orow = m * g.out_row_mul + g.out_row_add;   // frame of the layer below
-          const int t_prev = static_cast<int>(static_cast<unsigned>(orow) % static_cast<unsigned>(g.bw_P));
-          LnBwdEpi lb;
-          lb.valid = m < g.M_total && t_prev < g.bw_T;
-          lb.xhat_row = g.bw_xhat + (lb.valid ? orow : 0) * kC + n0;
-          lb.rstd = lb.valid ? __ldg(g.bw_rstd + orow) : 0.f;
-          lb.want_affine = g.bw_dgamma != nullptr;
-          const int slot3 = team * 2 + static_cast<int>(acc_phase);
-          EpiCtx ec;
-          ec.taddr = taddr;
-          ec.bar_tmem_empty = bar(kTmemEmpty + buf);
-          ec.stats_slot = smem_base + Cfg::kStatsOff + static_cast<uint32_t>((slot3 * kBlockM + row) * 8);
-          ec.stats_local = s_stats + slot3 * kBlockM + row;
-          ec.bar_stats = bar(kStats + team);
-          ec.stats_parity = acc_phase;
-          ec.arm = row == 0;
-          ec.peer = peer;
-          ec.s_gb = s_gb;
-          ec.ost = ost;
-          epilogue_lnbwd_row<kClusterN>(ec, lb, dg_acc, db_acc);
-          continue;
-        }
-      }
       if (g.mode == 2) {
         epilogue_bias_f32_row<kClusterN>(taddr, bar(kTmemEmpty + buf), m < g.M_total,
                                          reinterpret_cast<float*>(g.out) + m * g.out_pitch + ng * kC + n0,
@@ -1086,15 +1287,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ec.tmem_empty_cluster = 0;
       ec.ost = ost;
       epilogue_row<kClusterN, kSave>(ec);
-    }
-    if constexpr (kBwdFuse) {
-      if (g.mode == 3 && g.bw_dgamma != nullptr) {  // this warp's column sums -> the layer's affine gradients
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          atomicAdd(g.bw_dgamma + n0 + c * 32 + lane, dg_acc[c]);
-          atomicAdd(g.bw_dbeta + n0 + c * 32 + lane, db_acc[c]);
-        }
-      }
     }
     if (lane == 0) ptx::bulk_wait<0>();  // this warp's output stores are complete before the CTA may exit
   }
@@ -2847,13 +3039,13 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap
   return NRSE_OK;
 }
 
-template <int kClusterN, bool kSave = false, bool kBwdFuse = false>
+template <int kClusterN, bool kSave = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const GemmArgs& g,
                 cudaStream_t stream) {
   using Cfg = GemmCfg<kClusterN>;
   static bool attr_set = false;  // benign race: the attribute is idempotent
   if (!attr_set) {
-    NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<kClusterN, kSave, kBwdFuse>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<kClusterN, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -2873,7 +3065,35 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = NRSE_EXP(experiment_flags(), 512) ? 1 : 2;  // 512: no programmatic dependent launch (A/B timing)
-  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<kClusterN, kSave, kBwdFuse>, ta, tw, to, g));
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<kClusterN, kSave>, ta, tw, to, g));
+  return NRSE_OK;
+}
+
+int launch_dgrad_lnbwd(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const DgLnArgs& g,
+                       cudaStream_t stream) {
+  using Cfg = DgLnCfg;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NRSE_CUDA_TRY(cudaFuncSetAttribute(dgrad_lnbwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int max_groups = g_sm_budget / 2;
+  const int groups = g.num_tiles < max_groups ? g.num_tiles : max_groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, dgrad_lnbwd_kernel, ta, tw, to, g));
   return NRSE_OK;
 }
 
@@ -3388,8 +3608,7 @@ int nrse_conv_layer_dgrad_lnbwd(const void* dz, int64_t rows_out, const void* wt
     return NRSE_ERR_INVALID_ARG;
   if ((dgamma_prev == nullptr) != (dbeta_prev == nullptr)) return NRSE_ERR_INVALID_ARG;
   if ((2 * rows_out) % P_prev != 0) return NRSE_ERR_INVALID_ARG;
-  if (nrse::g_variant < 2) return NRSE_ERR_UNSUPPORTED;  // the fused epilogue lives in the CTA-pair kernel
-  nrse::DgradFuse f = {xhat_prev, rstd_prev, gamma_prev, beta_prev, dgamma_prev, dbeta_prev, P_prev, T_prev};
+    nrse::DgradFuse f = {xhat_prev, rstd_prev, gamma_prev, beta_prev, dgamma_prev, dbeta_prev, P_prev, T_prev};
   return nrse::dgrad_impl(dz, rows_out, wt_even, wt_odd, k, dz_prev, &f, nrse::as_stream(stream));
 }
 
@@ -3412,14 +3631,6 @@ static int dgrad_impl(const void* dz, int64_t rows_out, const void* wt_even, con
     g.stride = 2;
     g.xhat = nullptr; g.rstd = nullptr;
     g.mode = 1;
-    if (fuse) {
-      g.mode = 3;
-      g.gamma = fuse->gamma; g.beta = fuse->beta;
-      g.bw_xhat = reinterpret_cast<const __nv_bfloat16*>(fuse->xhat);
-      g.bw_rstd = fuse->rstd;
-      g.bw_dgamma = fuse->dgamma; g.bw_dbeta = fuse->dbeta;
-      g.bw_P = fuse->P; g.bw_T = fuse->T;
-    }
     g.a_wide = 0; g.n_split = 1; g.out_pitch = kC; g.bias = nullptr;
     g.a_2d = 1;
     g.a_row_off[0] = 0;    // even: tap 0 <- dZ[m];  odd: tap 1 <- dZ[m]
@@ -3433,8 +3644,17 @@ static int dgrad_impl(const void* dz, int64_t rows_out, const void* wt_even, con
     CUtensorMap to;  // rows 2 m + parity of dX
     rc = make_tmap_out(&to, reinterpret_cast<const char*>(dx) + static_cast<size_t>(parity) * kC * 2, rows_out, 2);
     if (rc != NRSE_OK) return rc;
-    if (fuse) rc = launch_gemm<2, false, true>(ta, tw, to, g, stream);
-    else rc = g_variant >= 2 ? launch_gemm<2>(ta, tw, to, g, stream) : launch_gemm<1>(ta, tw, to, g, stream);
+    if (fuse) {
+      DgLnArgs d;
+      d.M_total = g.M_total; d.num_tiles = g.num_tiles; d.k_stages = g.k_stages;
+      d.a_row_off[0] = g.a_row_off[0]; d.a_row_off[1] = g.a_row_off[1];
+      d.parity = parity; d.reverse = 0;
+      d.gamma = fuse->gamma; d.beta = fuse->beta;
+      d.xhat = reinterpret_cast<const __nv_bfloat16*>(fuse->xhat); d.rstd = fuse->rstd;
+      d.dgamma = fuse->dgamma; d.dbeta = fuse->dbeta;
+      d.P = fuse->P; d.T = fuse->T;
+      rc = launch_dgrad_lnbwd(ta, tw, to, d, stream);
+    } else rc = g_variant >= 2 ? launch_gemm<2>(ta, tw, to, g, stream) : launch_gemm<1>(ta, tw, to, g, stream);
     if (rc != NRSE_OK) return rc;
   }
   return NRSE_OK;
@@ -3462,7 +3682,7 @@ int nrse_conv_frontend_bwd(const float* x, const nrse_frontend_params* prm, cons
   if (dy_pitch < T[kLayers - 1]) return NRSE_ERR_INVALID_ARG;
   if (workspace_bytes < nrse_conv_frontend_bwd_workspace_bytes(B, L)) return NRSE_ERR_WORKSPACE;
   const bool norm = norm_mode == NRSE_NORM_LAYER;
-  const bool fused = norm && g_bwd_fusion != 0 && g_variant >= 2;  // LayerNorm / GELU backward in the dgrad epilogue
+  const bool fused = norm && g_bwd_fusion != 0;  // LayerNorm / GELU backward in the dgrad epilogue
   // which layers want what; `stop` = the lowest layer that wants anything: nothing below it is computed
   bool need_w[kLayers], need_aff[kLayers];
   int stop = kLayers;

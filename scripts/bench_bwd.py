@@ -35,6 +35,27 @@ def timeit(fn, n=5, repeats=3):
 t_fwd, _ = timeit(lambda: ops.conv_frontend(x, w, g, b, "layer", out_dtype=torch.bfloat16, packed=packed))
 t_train, (y, tape) = timeit(lambda: ops.conv_frontend_train(x, w, g, b, "layer", packed=packed))
 bwd = lambda: ops.conv_frontend_backward(x, w, g, b, tape, gy, "layer", dgrad_packs=dpacks)
+if "--timeline" in sys.argv:   # CUPTI timeline of one warm backward of each form: start, duration, gap to the previous kernel
+    from torch.profiler import profile, ProfilerActivity
+    for on in (False, True):
+        ops.set_bwd_fusion(on)
+        for _ in range(3):
+            bwd()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            bwd(); torch.cuda.synchronize()
+        ev = sorted((e for e in prof.events() if e.device_type.name == "CUDA"), key=lambda e: e.time_range.start)
+        t0 = ev[0].time_range.start
+        print("fusion", on, "span_us", ev[-1].time_range.end - t0, "sum_us", sum(e.time_range.end - e.time_range.start for e in ev))
+        prev_end = t0
+        for e in ev:
+            print(f"  {e.time_range.start - t0:8.1f} dur {e.time_range.end - e.time_range.start:7.1f} gap {e.time_range.start - prev_end:6.1f}  {e.name[:60]}")
+            prev_end = max(prev_end, e.time_range.end)
+    sys.exit(0)
+if "--profile" in sys.argv:   # under ncu: two backward passes of each form (the second of each is the warm one)
+    for on in (False, False, True, True):
+        ops.set_bwd_fusion(on); bwd(); torch.cuda.synchronize()
+    sys.exit(0)
 ops.set_bwd_fusion(False)
 t_bwd_sep, _ = timeit(bwd)
 ops.set_bwd_fusion(True)      # LayerNorm / GELU backward inside the data-gradient epilogue
