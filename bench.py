@@ -221,7 +221,8 @@ def load_frontend(module, layers, dev):
 
 
 # launches of THIS repository's kernels per step (torch's own small kernels -- index / sum / mean -- are not counted)
-MIXER_LAUNCHES = 1 + 4 + 1       # GpuBatchMixer: mix, 4 device-side retries (no-ops on a healthy batch), substitute
+MIXER_LAUNCHES = 1 + 1 + 1       # GpuBatchMixer (nrse_mix_batch_f32): mix, one retry launch (all further attempts loop inside
+                                 # it; a no-op on a healthy batch), finish (substitute + snr labels + rejected-row count)
 FRONTEND_FWD_LAUNCHES = 7        # layer 0 + six tcgen05 GEMM layers
 FRONTEND_BWD_LAUNCHES = 7 + 6 + 12 + 1   # norm+GELU backward x7, wgrad x6, dgrad (even / odd) x6, layer-0 wgrad
 PACK_LAUNCHES = 6                # bf16 re-pack of conv weights 1..6 after a parameter update

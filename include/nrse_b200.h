@@ -124,6 +124,24 @@ int nrse_mix_normalize_retry_f32(const float* clean, const float* noise, const i
  * clean_out and snr_idx_used are nullable. */
 int nrse_mix_substitute_rows_f32(float* clean_out, float* noisy_out, const int32_t* status, int32_t* snr_idx_used, int B,
                                  int L, nrse_stream_t stream);
+/* The whole attempt loop of NoiseRobustSpeechDataset.__getitem__ (ref:src/data/noisy_speech_dataset.py:55-149) for a batch,
+ * in one host call and THREE launches whatever max_attempts is:
+ *   1. nrse_mix_normalize_f32 on every row, recording the SNR index used in snr_idx_used [B] (required);
+ *   2. (max_attempts > 1, B > 1) one retry launch: a row that was rejected is redone INSIDE the launch with the noise
+ *      and SNR draw of rows b + 1, b + 2, ... (mod B) until it passes or max_attempts - 1 further attempts are used up --
+ *      the same donors, in the same order, as max_attempts - 1 calls of nrse_mix_normalize_retry_f32 with
+ *      noise_row_shift = 1, 2, ...; the CTAs of good rows exit at once;
+ *   3. one finishing launch: substitute_bad_rows != 0 copies the nearest following good row over every row that is still
+ *      rejected (nrse_mix_substitute_rows_f32); snr_labels_out (nullable, [B] int64) receives
+ *      snr_label_table[snr_idx_used[b]] (snr_label_table: DEVICE [n_snr] int64, the "snr" entry of the reference's item
+ *      dict, :140-144); n_rejected (nullable, DEVICE int32 scalar) receives the number of rows with status != 0 -- what
+ *      the host logs, copied back asynchronously by the caller.
+ * The host never reads the status to decide anything; replaces 6 launches + 6 small torch kernels per batch of the
+ * earlier retry-per-launch form. */
+int nrse_mix_batch_f32(const float* clean, const float* noise, const int32_t* snr_idx, const double* snr_db_table_host,
+                       int n_snr, float* clean_out, float* noisy_out, int32_t* status, int32_t* snr_idx_used,
+                       const int64_t* snr_label_table, int64_t* snr_labels_out, int32_t* n_rejected, int B, int L,
+                       int L_noise, int peak_norm, int max_attempts, int substitute_bad_rows, nrse_stream_t stream);
 const char* nrse_mix_status_name(int status_code);
 /* 4 (default): on-chip resident -- the CTAs of a cluster (1..8 per row) keep their segment of the row in registers and
  * shared memory between the three passes, exchanges by st.async + mbarrier; needs 16-byte aligned rows, L % 4 == 0,

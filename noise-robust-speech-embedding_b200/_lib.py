@@ -66,6 +66,7 @@ SIGNATURES = {
     "nrse_mix_normalize_f32": (_i, [_p, _p, _p, C.POINTER(C.c_double), _i, _p, _p, _p, _i, _i, _i, _i, _p]),
     "nrse_mix_normalize_retry_f32": (_i, [_p, _p, _p, C.POINTER(C.c_double), _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "nrse_mix_substitute_rows_f32": (_i, [_p, _p, _p, _p, _i, _i, _p]),
+    "nrse_mix_batch_f32": (_i, [_p, _p, _p, C.POINTER(C.c_double), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "nrse_mix_status_name": (C.c_char_p, [_i]),
     "nrse_mix_set_variant": (_i, [_i]),
     "nrse_mix_set_cluster": (_i, [_i]),

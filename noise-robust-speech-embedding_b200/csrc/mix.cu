@@ -41,6 +41,8 @@ struct MixParams {
   int retry;        // 1: only rows whose status is != 0 are processed (the others keep their outputs), ...
   int noise_shift;  // ... with the noise AND the SNR draw of row (row + noise_shift) % B: the device-side "try another
                     // noise file, draw another SNR" of ref:src/data/noisy_speech_dataset.py:69-81
+  int n_attempts;   // retry launches only: attempts made inside ONE launch (shift noise_shift, noise_shift + 1, ...) while
+                    // the row keeps failing -- the reference's `for attempt in range(max_attempts)` loop (:58) on the device
   float snr_lin[kMaxSnr];  // float(10 ** (snr_db / 10)), ref:src/data/augment.py:39
 };
 
@@ -112,7 +114,9 @@ __device__ __forceinline__ float absmax4(float m, const float (&x)[4]) {
   return fmaxf(fmaxf(m, fmaxf(fabsf(x[0]), fabsf(x[1]))), fmaxf(fabsf(x[2]), fabsf(x[3])));
 }
 
-template <bool kVec>
+// kRetry: the launch redoes rejected rows only, up to p.n_attempts times with successive noise / SNR donors (every CTA
+// of a row's cluster derives the same verdict, so all of them leave the loop together).
+template <bool kVec, bool kRetry>
 __global__ void __launch_bounds__(kMixThreads) mix_normalize_kernel(const MixParams p) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = static_cast<int>(cluster.block_rank());
@@ -126,14 +130,19 @@ __global__ void __launch_bounds__(kMixThreads) mix_normalize_kernel(const MixPar
   __shared__ float xch2_f[kMixCluster];
   __shared__ unsigned xch2_u[kMixCluster];
 
-  if (p.retry && p.status[row] == 0) return;  // whole cluster (same row): nothing to redo
+  if (kRetry && p.status[row] == 0) return;  // whole cluster (same row): nothing to redo
   const int L = p.L, Ln = p.Ln;
   const float* c_row = p.clean + static_cast<size_t>(row) * L;
-  const float* n_row = p.noise + static_cast<size_t>(p.retry ? (row + p.noise_shift) % p.B : row) * Ln;
   const int nvec = (L + 3) / 4;
   const int seg = (nvec + kMixCluster - 1) / kMixCluster;
   const int v_begin = rank * seg;
   const int v_end = min(nvec, v_begin + seg);
+  const int n_att = kRetry ? p.n_attempts : 1;
+  for (int att = 0; att < n_att; ++att) {
+  const int donor = kRetry ? (row + p.noise_shift + att) % p.B : row;  // whose noise crop and SNR draw this attempt uses
+  const float* n_row = p.noise + static_cast<size_t>(donor) * Ln;
+  // exchange buffers / reduction scratch of the previous attempt have been read by every CTA of the cluster
+  if (kRetry && att > 0) cluster.sync();
 
   // ---- pass 1 (HBM): sum c^2, n^2, c, n, c*n; max|c|, max|n| -------------------------------------
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(kMixThreads) mix_normalize_kernel(const MixPar
   const double Ld = static_cast<double>(L);
   const float Ps = static_cast<float>(s_cc / Ld);  // torch.mean(speech ** 2)
   const float Pn = static_cast<float>(s_nn / Ld);
-  int idx = p.snr_idx[p.retry ? (row + p.noise_shift) % p.B : row];
+  int idx = p.snr_idx[donor];
   idx = idx < 0 ? 0 : (idx >= p.n_snr ? p.n_snr - 1 : idx);
   if (rank == 0 && tid == 0 && p.snr_used != nullptr) p.snr_used[row] = idx;
   const float scale = __fsqrt_rn(__fdiv_rn(Ps, __fmul_rn(Pn, p.snr_lin[idx])));  // augment.py:40, fp32
@@ -297,7 +306,7 @@ __global__ void __launch_bounds__(kMixThreads) mix_normalize_kernel(const MixPar
       store4<kVec>(co_row, L, v0, z);
       store4<kVec>(no_row, L, v0, z);
     }
-    return;
+    continue;  // next attempt, if this launch makes one
   }
   for (int v0 = v_begin + tid; v0 < v_end; v0 += 2 * kMixThreads) {
     float c[2][4], n[2][4];
@@ -323,6 +332,8 @@ __global__ void __launch_bounds__(kMixThreads) mix_normalize_kernel(const MixPar
       store4<kVec>(no_row, L, u ? v1 : v0, on);
     }
   }
+  if (st == 0) break;  // (emotion mode: a rejected mix wrote the clean waveform and may be retried)
+  }  // attempts
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -402,7 +413,10 @@ struct ResCfg {
   static constexpr int kCap = kRegCap + kSmemCap;
 };
 
-template <int kResThreads>
+// kRetry: the launch redoes rejected rows only and makes up to p.n_attempts attempts per row inside the launch (see MixParams);
+// every barrier then completes one phase per attempt, and a cluster barrier between attempts keeps a fast CTA's next
+// messages out of buffers a slower CTA of the row is still reading.  The first-attempt instantiation carries none of this.
+template <int kResThreads, bool kRetry>
 __global__ void __launch_bounds__(kResThreads, 1024 / kResThreads)
 mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
   constexpr int kResWarps = ResCfg<kResThreads>::kWarps;
@@ -432,23 +446,30 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
   const int chunk_vec = (n_sm + kResChunks - 1) / kResChunks;
   float4* s_c = reinterpret_cast<float4*>(mix_smem);
   float4* s_n = s_c + smem_pitch;
-  if (p.retry && p.status[row] == 0) return;  // whole cluster (same row): nothing to redo
+  if (kRetry && p.status[row] == 0) return;  // whole cluster (same row): nothing to redo
   const float4* g_c = reinterpret_cast<const float4*>(p.clean + static_cast<size_t>(row) * L) + v_begin;
-  const float4* g_n = reinterpret_cast<const float4*>(
-                          p.noise + static_cast<size_t>(p.retry ? (row + p.noise_shift) % p.B : row) * p.Ln) + v_begin;
 
   // The cluster exchanges are st.async messages that complete_tx on the RECEIVER's mbarrier: no cluster barrier and no
   // gpu-scope fence on the critical path (cg::cluster.sync() costs MEMBAR.GPU + ERRBAR twice per row).  Each CTA
   // sends its partials to every CTA of the cluster (itself included), in both exchanges, before it waits for the
   // second one -- so once a CTA has received everything nothing can still be addressed to it and it may exit.
   const unsigned xbar1 = ptx::smem_u32(&xbar[0]), xbar2 = ptx::smem_u32(&xbar[1]);
+  const int n_att = kRetry ? p.n_attempts : 1;
+  unsigned x2_phase = 0;  // phases xbar2 has completed: the second exchange only happens for rows that pass add_noise_to_speech,
+  bool x2_armed = false;  // so an attempt that skipped it leaves the barrier armed for the next one
+  for (int att = 0; att < n_att; ++att) {
+  const unsigned ph = static_cast<unsigned>(att) & 1u;  // phase parity of the per-attempt barriers
+  const int donor = kRetry ? (row + p.noise_shift + att) % p.B : row;  // whose noise crop and SNR draw this attempt uses
+  const float4* g_n = reinterpret_cast<const float4*>(p.noise + static_cast<size_t>(donor) * p.Ln) + v_begin;
   if (tid == 0) {
-    for (int c = 0; c < kResChunks; ++c) ptx::mbar_init(ptx::smem_u32(&bars[c]), 1);
-    ptx::mbar_init(xbar1, 1);
-    ptx::mbar_init(xbar2, 1);
-    ptx::fence_mbar_init();
+    if (att == 0) {
+      for (int c = 0; c < kResChunks; ++c) ptx::mbar_init(ptx::smem_u32(&bars[c]), 1);
+      ptx::mbar_init(xbar1, 1);
+      ptx::mbar_init(xbar2, 1);
+      ptx::fence_mbar_init();
+    }
     ptx::mbar_arrive_expect_tx(xbar1, static_cast<unsigned>(cs) * 48u);
-    ptx::mbar_arrive_expect_tx(xbar2, static_cast<unsigned>(cs) * 4u);
+    if (!x2_armed) ptx::mbar_arrive_expect_tx(xbar2, static_cast<unsigned>(cs) * 4u);
     for (int c = 0; c < kResChunks; ++c) {
       const int c0 = c * chunk_vec;
       const int len = min(chunk_vec, n_sm - c0);
@@ -479,8 +500,13 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
       rc[u] = rn[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  x2_armed = true;
   __syncthreads();  // mbarrier init visible to the waiting threads
-  if (cs > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");  // peers: my barriers exist
+  // peers: my barriers exist (and, from the second attempt on: I have read everything they sent me for the previous one)
+  if (cs > 1) {
+    if (kRetry) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    else asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  }
 
   // ---- pass 1: packed fp32 partial sums per thread (<= 40 samples per lane-half), fp64 across ---------------------
   const f2 zero2 = f2_make(0.f, 0.f);
@@ -507,8 +533,8 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
       const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&bars[c]));
       asm volatile(
           "{\n\t.reg .pred p;\n\tRES_WAIT_LOOP:\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
-          "@p bra RES_WAIT_DONE;\n\tbra RES_WAIT_LOOP;\n\tRES_WAIT_DONE:\n\t}\n" ::"r"(bar)
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+          "@p bra RES_WAIT_DONE;\n\tbra RES_WAIT_LOOP;\n\tRES_WAIT_DONE:\n\t}\n" ::"r"(bar), "r"(ph)
           : "memory");
       for (int v = c0 + tid; v < c_end; v += kResThreads) accum(s_c[v], s_n[v]);
     }
@@ -551,7 +577,7 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
       }
     }
   }
-  if (tid == 0) ptx::mbar_wait(xbar1, 0);
+  if (tid == 0) ptx::mbar_wait(xbar1, ph);
 
   double s_cc = 0.0, s_nn = 0.0, s_c1 = 0.0, s_n1 = 0.0, s_cn = 0.0;
   const double inv_L = 1.0 / static_cast<double>(L);
@@ -570,7 +596,7 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
     }
     const float Ps = static_cast<float>(s_cc * inv_L);
     const float Pn = static_cast<float>(s_nn * inv_L);
-    int idx = p.snr_idx[p.retry ? (row + p.noise_shift) % p.B : row];
+    int idx = p.snr_idx[donor];
     idx = idx < 0 ? 0 : (idx >= p.n_snr ? p.n_snr - 1 : idx);
     if (rank == 0 && p.snr_used != nullptr) p.snr_used[row] = idx;
     const float scale = __fsqrt_rn(__fdiv_rn(Ps, __fmul_rn(Pn, p.snr_lin[idx])));
@@ -627,7 +653,9 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
                      "r"(__float_as_uint(m)), "r"(ptx::mapa(xbar2, lane))
                      : "memory");
     }
-    if (tid == 0) ptx::mbar_wait(xbar2, 0);
+    if (tid == 0) ptx::mbar_wait(xbar2, x2_phase & 1u);
+    ++x2_phase;
+    x2_armed = false;
   }
 
   if (tid == 0) {
@@ -691,7 +719,8 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
       st_stream_cs_f4(co + v, z);
       st_stream_cs_f4(no + v, z);
     }
-    return;
+    if (kRetry) __syncthreads();
+    continue;  // next attempt, if this launch makes one
   }
   const f2 nac2 = f2_make(-sc.a_c, -sc.a_c), bc2 = f2_make(sc.b_c, sc.b_c), idc2 = f2_make(sc.inv_dc, sc.inv_dc);
   const f2 nan2 = f2_make(-sc.a_n, -sc.a_n), bn2 = f2_make(sc.b_n, sc.b_n), idn2 = f2_make(sc.inv_dn, sc.inv_dn);
@@ -725,28 +754,53 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
     if (v < n_reg) emit(v, rc[u], rn[u]);
   }
   for (int v = tid; v < n_sm; v += kResThreads) emit(n_reg + v, s_c[v], s_n[v]);
+  if (st == 0) break;  // (emotion mode: a rejected mix wrote the clean waveform and may be retried)
+  if (kRetry) __syncthreads();  // every thread is done with the on-chip row before the next attempt's copies overwrite it
+  }  // attempts
 }
 
-// Rows that failed every attempt (status != 0 after the retries) take over the outputs of the nearest following good row
-// of the batch -- the device-side form of the reference's "move on to the next item" (ref:src/data/
-// noisy_speech_dataset.py:60-66) -- so that no all-zero waveform reaches BatchNorm statistics or the loss mean.  One CTA
-// per row; the CTAs of good rows exit at once: on a healthy batch the launch moves no data.  `status` is not modified (it
-// keeps reporting why the row failed); a batch without any good row is left as it is.
-__global__ void __launch_bounds__(256) mix_substitute_kernel(float* __restrict__ clean_out, float* __restrict__ noisy_out,
-                                                             const int32_t* __restrict__ status,
-                                                             int32_t* __restrict__ snr_used, int B, int L) {
+// The tail of the batch: (1) rows that failed every attempt (status != 0 after the retries) take over the outputs of the
+// nearest following good row of the batch -- the device-side form of the reference's "move on to the next item"
+// (ref:src/data/noisy_speech_dataset.py:60-66) -- so that no all-zero waveform reaches BatchNorm statistics or the loss
+// mean; (2) the batch's "snr" labels (the value of the table entry every row was FINALLY mixed at, :140-144) are gathered;
+// (3) the number of rows that were rejected for good is written for the host's log.  One CTA per row; on a healthy batch
+// the launch moves no waveform data.  `status` is not modified (it keeps reporting why the row failed); a batch without
+// any good row is left as it is.
+__global__ void __launch_bounds__(256) mix_finish_kernel(float* __restrict__ clean_out, float* __restrict__ noisy_out,
+                                                         const int32_t* __restrict__ status,
+                                                         int32_t* __restrict__ snr_used,
+                                                         const int64_t* __restrict__ label_table,
+                                                         int64_t* __restrict__ labels_out,
+                                                         int32_t* __restrict__ n_rejected, int substitute, int B, int L) {
   const int row = blockIdx.x;
-  if (status[row] == 0) return;
   __shared__ int s_src;
+  __shared__ int s_cnt;
+  const bool bad = status[row] != 0;
+  if (row == 0 && n_rejected != nullptr) {  // status is read-only here: CTA 0 counts the whole batch
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    int c = 0;
+    for (int r = threadIdx.x; r < B; r += blockDim.x) c += status[r] != 0 ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) *n_rejected = s_cnt;
+  }
   if (threadIdx.x == 0) {
     int src = -1;
-    for (int d = 1; d < B; ++d) {
-      const int r = (row + d) % B;
-      if (status[r] == 0) { src = r; break; }
+    if (bad && substitute) {
+      for (int d = 1; d < B; ++d) {
+        const int r = (row + d) % B;
+        if (status[r] == 0) { src = r; break; }
+      }
     }
     s_src = src;
-    if (src >= 0 && snr_used != nullptr) snr_used[row] = snr_used[src];  // good rows' entries are never written here
+    // good rows' snr_used entries are never written here, so reading the donor's is race-free
+    const int used = snr_used != nullptr ? snr_used[src >= 0 ? src : row] : 0;
+    if (src >= 0 && snr_used != nullptr) snr_used[row] = used;
+    if (labels_out != nullptr) labels_out[row] = label_table[used];
   }
+  if (!bad || !substitute) return;
   __syncthreads();
   const int src = s_src;
   if (src < 0) return;
@@ -806,13 +860,13 @@ const char* nrse_mix_status_name(int code) {
 static int mix_normalize_impl(const float* clean, const float* noise, const int32_t* snr_idx,
                               const double* snr_db_table_host, int n_snr, float* clean_out, float* noisy_out,
                               int32_t* status, int32_t* snr_used, int B, int L, int L_noise, int peak_norm, int retry,
-                              int noise_shift, nrse_stream_t stream) {
+                              int noise_shift, int n_attempts, nrse_stream_t stream) {
   using namespace nrse;
   if (!clean || !noise || !snr_idx || !snr_db_table_host || !noisy_out || !status) return NRSE_ERR_INVALID_ARG;
   if (B < 0 || L <= 0 || L_noise <= 0 || n_snr <= 0 || n_snr > kMaxSnr) return NRSE_ERR_INVALID_ARG;
   if (peak_norm < 0 || peak_norm > 2) return NRSE_ERR_INVALID_ARG;
   if (peak_norm == 1 && !clean_out) return NRSE_ERR_INVALID_ARG;
-  if (retry && noise_shift < 0) return NRSE_ERR_INVALID_ARG;
+  if (retry && (noise_shift < 0 || n_attempts < 1)) return NRSE_ERR_INVALID_ARG;
   if (B == 0) return NRSE_OK;
 
   MixParams p;
@@ -823,6 +877,7 @@ static int mix_normalize_impl(const float* clean, const float* noise, const int3
   p.raw = peak_norm == 2 ? 1 : 0;
   p.retry = retry ? 1 : 0;
   p.noise_shift = retry ? noise_shift % B : 0;
+  p.n_attempts = retry ? n_attempts : 1;
   for (int i = 0; i < kMaxSnr; ++i)
     p.snr_lin[i] = i < n_snr ? static_cast<float>(std::pow(10.0, snr_db_table_host[i] / 10.0)) : 1.0f;
 
@@ -866,9 +921,13 @@ static int mix_normalize_impl(const float* clean, const float* noise, const int3
       const size_t dyn = static_cast<size_t>(smem_pitch) * 32;
       static bool res_attr_set = false;  // benign race: idempotent attributes
       if (!res_attr_set) {
-        NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<512>,
+        NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<512, false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, ResCfg<512>::kSmemCap * 32));
-        NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<1024>,
+        NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<1024, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, ResCfg<1024>::kSmemCap * 32));
+        NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<512, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, ResCfg<512>::kSmemCap * 32));
+        NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<1024, true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, ResCfg<1024>::kSmemCap * 32));
         res_attr_set = true;
       }
@@ -883,12 +942,17 @@ static int mix_normalize_impl(const float* clean, const float* noise, const int3
         static int last_pct[2] = {-1, -1};  // benign race: idempotent attribute
         int& last = last_pct[threads == 512 ? 0 : 1];
         if (pct != last) {
-          if (threads == 512)
-            NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<512>,
+          if (threads == 512) {
+            NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<512, false>,
                                                cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-          else
-            NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<1024>,
+            NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<512, true>,
                                                cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+          } else {
+            NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<1024, false>,
+                                               cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            NRSE_CUDA_TRY(cudaFuncSetAttribute(mix_normalize_resident_kernel<1024, true>,
+                                               cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+          }
           last = pct;
         }
       }
@@ -896,10 +960,13 @@ static int mix_normalize_impl(const float* clean, const float* noise, const int3
       cfg.blockDim = dim3(threads);
       cfg.dynamicSmemBytes = dyn;
       attr[0].val.clusterDim.x = cs;
-      if (threads == 512)
-        NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_resident_kernel<512>, p, seg_vec, smem_pitch));
-      else
-        NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_resident_kernel<1024>, p, seg_vec, smem_pitch));
+      if (threads == 512) {
+        if (retry) NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_resident_kernel<512, true>, p, seg_vec, smem_pitch));
+        else NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_resident_kernel<512, false>, p, seg_vec, smem_pitch));
+      } else {
+        if (retry) NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_resident_kernel<1024, true>, p, seg_vec, smem_pitch));
+        else NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_resident_kernel<1024, false>, p, seg_vec, smem_pitch));
+      }
       return NRSE_OK;
     }
   }
@@ -909,26 +976,41 @@ static int mix_normalize_impl(const float* clean, const float* noise, const int3
   cfg.blockDim = dim3(kMixThreads);
   cfg.dynamicSmemBytes = 0;
   attr[0].val.clusterDim.x = kMixCluster;
-  if (vec) NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_kernel<true>, p));
-  else NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_kernel<false>, p));
+  if (vec) {
+    if (retry) NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_kernel<true, true>, p));
+    else NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_kernel<true, false>, p));
+  } else {
+    if (retry) NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_kernel<false, true>, p));
+    else NRSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, mix_normalize_kernel<false, false>, p));
+  }
+  return NRSE_OK;
+}
+
+static int mix_finish_impl(float* clean_out, float* noisy_out, const int32_t* status, int32_t* snr_used,
+                           const int64_t* label_table, int64_t* labels_out, int32_t* n_rejected, int substitute, int B, int L,
+                           nrse_stream_t stream) {
+  using namespace nrse;
+  if (!noisy_out || !status || B < 0 || L <= 0) return NRSE_ERR_INVALID_ARG;
+  if ((labels_out != nullptr) && (label_table == nullptr || snr_used == nullptr)) return NRSE_ERR_INVALID_ARG;
+  if (B == 0) return NRSE_OK;
+  if (B < 2) substitute = 0;  // nothing to substitute from
+  if (!substitute && !labels_out && !n_rejected) return NRSE_OK;
+  mix_finish_kernel<<<B, 256, 0, as_stream(stream)>>>(clean_out, noisy_out, status, snr_used, label_table, labels_out,
+                                                     n_rejected, substitute, B, L);
+  NRSE_CHECK_LAUNCH();
   return NRSE_OK;
 }
 
 int nrse_mix_substitute_rows_f32(float* clean_out, float* noisy_out, const int32_t* status, int32_t* snr_idx_used, int B,
                                  int L, nrse_stream_t stream) {
-  using namespace nrse;
-  if (!noisy_out || !status || B < 0 || L <= 0) return NRSE_ERR_INVALID_ARG;
-  if (B < 2) return NRSE_OK;  // nothing to substitute from
-  mix_substitute_kernel<<<B, 256, 0, as_stream(stream)>>>(clean_out, noisy_out, status, snr_idx_used, B, L);
-  NRSE_CHECK_LAUNCH();
-  return NRSE_OK;
+  return mix_finish_impl(clean_out, noisy_out, status, snr_idx_used, nullptr, nullptr, nullptr, 1, B, L, stream);
 }
 
 int nrse_mix_normalize_f32(const float* clean, const float* noise, const int32_t* snr_idx,
                            const double* snr_db_table_host, int n_snr, float* clean_out, float* noisy_out,
                            int32_t* status, int B, int L, int L_noise, int peak_norm, nrse_stream_t stream) {
   return mix_normalize_impl(clean, noise, snr_idx, snr_db_table_host, n_snr, clean_out, noisy_out, status, nullptr, B, L,
-                            L_noise, peak_norm, 0, 0, stream);
+                            L_noise, peak_norm, 0, 0, 1, stream);
 }
 
 int nrse_mix_normalize_retry_f32(const float* clean, const float* noise, const int32_t* snr_idx,
@@ -936,7 +1018,24 @@ int nrse_mix_normalize_retry_f32(const float* clean, const float* noise, const i
                                  int32_t* status, int32_t* snr_idx_used, int B, int L, int L_noise, int peak_norm,
                                  int noise_row_shift, nrse_stream_t stream) {
   return mix_normalize_impl(clean, noise, snr_idx, snr_db_table_host, n_snr, clean_out, noisy_out, status, snr_idx_used,
-                            B, L, L_noise, peak_norm, 1, noise_row_shift, stream);
+                            B, L, L_noise, peak_norm, 1, noise_row_shift, 1, stream);
+}
+
+int nrse_mix_batch_f32(const float* clean, const float* noise, const int32_t* snr_idx, const double* snr_db_table_host,
+                       int n_snr, float* clean_out, float* noisy_out, int32_t* status, int32_t* snr_idx_used,
+                       const int64_t* snr_label_table, int64_t* snr_labels_out, int32_t* n_rejected, int B, int L,
+                       int L_noise, int peak_norm, int max_attempts, int substitute_bad_rows, nrse_stream_t stream) {
+  if (!snr_idx_used || max_attempts < 1) return NRSE_ERR_INVALID_ARG;
+  int rc = mix_normalize_impl(clean, noise, snr_idx, snr_db_table_host, n_snr, clean_out, noisy_out, status, snr_idx_used, B,
+                              L, L_noise, peak_norm, 0, 0, 1, stream);
+  if (rc != NRSE_OK) return rc;
+  if (max_attempts > 1 && B > 1) {  // attempts 2..max_attempts: ONE launch, rows still rejected loop inside it
+    rc = mix_normalize_impl(clean, noise, snr_idx, snr_db_table_host, n_snr, clean_out, noisy_out, status, snr_idx_used, B, L,
+                            L_noise, peak_norm, 1, 1, max_attempts - 1, stream);
+    if (rc != NRSE_OK) return rc;
+  }
+  return mix_finish_impl(peak_norm == 1 ? clean_out : nullptr, noisy_out, status, snr_idx_used, snr_label_table,
+                         snr_labels_out, n_rejected, substitute_bad_rows, B, L, stream);
 }
 
 }  // extern "C"

@@ -152,11 +152,12 @@ class GpuBatchMixer:
     reject it, drawing another noise file AND another SNR each time (ref:src/data/noisy_speech_dataset.py:55-149), and
     never emits an unusable item.  Here the decisions stay on the device:
 
-    * after the first launch, ``max_attempts - 1`` retry launches redo exactly the rows whose status is non-zero with
-      another row's noise crop and SNR draw (``ops.mix_normalize_retry_``); for a healthy batch their CTAs exit at once;
+    * after the first launch ONE retry launch redoes exactly the rows whose status is non-zero, looping INSIDE the kernel
+      over up to ``max_attempts - 1`` further attempts with the following rows' noise crops and SNR draws
+      (``ops.mix_batch`` = ``nrse_mix_batch_f32``); for a healthy batch its CTAs exit at once;
     * rows that are still bad after that (a silent or NaN CLEAN crop can never recover) are handled by ``bad_rows``:
-      ``"substitute"`` (default) -- one more no-op-when-healthy launch copies the nearest following good row over them
-      (``ops.mix_substitute_rows_``), the device-side form of the reference's "move on to the next item"
+      ``"substitute"`` (default) -- the finishing launch (which also gathers the ``snr`` labels and counts the rejected rows)
+      copies the nearest following good row over them, the device-side form of the reference's "move on to the next item"
       (:60-66): the batch keeps its size, no all-zero waveform reaches BatchNorm statistics or the loss mean, and the
       host still never waits; ``"drop"`` -- read the status and remove the rows (one host synchronisation per batch);
       ``"keep"`` -- leave them zero-filled (BYOL mode) / as the clean waveform (emotion mode).
@@ -181,7 +182,7 @@ class GpuBatchMixer:
         self.rejected_rows = 0          # rows that stayed bad after all attempts, as far as already observed
         self._pending = []              # [(pinned count tensor, event)] of batches not yet looked at
         self._free = []                 # pinned counters / events to reuse (cudaHostAlloc per batch would cost ~100 us)
-        self._snr_values = None
+        self._snr_labels = None
 
     @property
     def drop_bad_rows(self) -> bool:
@@ -214,20 +215,20 @@ class GpuBatchMixer:
         clean = raw["clean_wave"].to(dev, non_blocking=True).flatten(1).contiguous().float()
         noise = raw["noise_wave"].to(dev, non_blocking=True).flatten(1).contiguous().float()
         snr_idx = torch.as_tensor(raw["snr_idx"]).to(dev, non_blocking=True).to(torch.int32).contiguous()
-        c, n, status = ops.mix_normalize(clean, noise, snr_idx, self.snr_table, self.peak_norm)
         retried = self.peak_norm and clean.shape[0] > 1 and self.max_attempts > 1
-        snr_used = snr_idx.clone() if retried else snr_idx
         if retried:
-            for attempt in range(1, self.max_attempts):  # device-side retries: no-ops unless a row was rejected
-                ops.mix_normalize_retry_(clean, noise, snr_idx, self.snr_table, c, n, status, attempt, True, snr_used)
-            if self.bad_rows == "substitute":
-                ops.mix_substitute_rows_(c, n, status, snr_used)
-        if self._snr_values is None or self._snr_values.device != clean.device:
-            self._snr_values = torch.tensor([int(round(v)) if float(v).is_integer() else v for v in self.snr_table],
-                                            device=clean.device)
-        # the label every row was FINALLY mixed at (a retry re-draws the SNR, as the reference's next attempt does)
-        snr = self._snr_values[snr_used.long()].to(torch.int64) if retried else \
-            torch.as_tensor(raw["snr"]).to(dev, non_blocking=True).to(torch.int64)
+            # mix, device-side retries (one launch: rejected rows loop inside it over the following rows' noise crops and SNR
+            # draws; a no-op on a healthy batch), substitute + labels + rejected-row count: ops.mix_batch
+            if self._snr_labels is None or self._snr_labels.device != clean.device:
+                # the label every row was FINALLY mixed at (a retry re-draws the SNR, as the reference's next attempt does)
+                self._snr_labels = torch.tensor([int(round(v)) if float(v).is_integer() else v for v in self.snr_table],
+                                                device=clean.device).to(torch.int64)
+            c, n, status, _, snr, n_bad = ops.mix_batch(clean, noise, snr_idx, self.snr_table, self._snr_labels, True,
+                                                        self.max_attempts, self.bad_rows == "substitute")
+        else:
+            c, n, status = ops.mix_normalize(clean, noise, snr_idx, self.snr_table, self.peak_norm)
+            snr = torch.as_tensor(raw["snr"]).to(dev, non_blocking=True).to(torch.int64)
+            n_bad = None
         if self.bad_rows == "drop":
             bad = status != 0
             if bool(bad.any()):  # host synchronisation
@@ -236,8 +237,8 @@ class GpuBatchMixer:
                 self.rejected_rows += int(bad.sum())
                 c, n, snr, status = (c[keep] if c is not None else None), n[keep], snr[keep], status[keep]
         elif self.peak_norm:
-            cnt, ev = self._free.pop() if self._free else (torch.empty(1, dtype=torch.int64).pin_memory(), torch.cuda.Event())
-            cnt.copy_((status != 0).sum().reshape(1), non_blocking=True)
+            cnt, ev = self._free.pop() if self._free else (torch.empty(1, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+            cnt.copy_(n_bad if n_bad is not None else (status != 0).sum().reshape(1).to(torch.int32), non_blocking=True)
             ev.record()
             self._pending.append((cnt, ev))
         out = {"noisy_input_values": n.unsqueeze(1), "snr": snr, "mix_status": status}

@@ -159,6 +159,55 @@ def mix_substitute_rows_(clean_out: Optional[Tensor], noisy_out: Tensor, status:
                        snr_idx_used if snr_idx_used is not None else empty)
 
 
+@torch.library.custom_op("nrse::mix_batch", mutates_args=())
+def _mix_batch_op(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db: Sequence[float], label_table: Tensor, mode: int,
+                  max_attempts: int, substitute: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    _need_cuda(clean, noise, snr_idx, label_table)
+    B, L = clean.shape
+    noisy_out = torch.empty_like(clean)
+    clean_out = torch.empty_like(clean) if mode == 1 else clean.new_empty(0)
+    # status [B] | snr index finally used [B] | number of rows rejected for good [1], one int32 allocation
+    meta = torch.empty(2 * B + 1, dtype=torch.int32, device=clean.device)
+    labels = torch.empty(B, dtype=torch.int64, device=clean.device)
+    table = (C.c_double * len(snr_db))(*[float(v) for v in snr_db])
+    base = meta.data_ptr()
+    check(_lib.load().nrse_mix_batch_f32(
+        _ptr(clean), _ptr(noise), _ptr(snr_idx), table, len(snr_db), _ptr(clean_out) if mode == 1 else None,
+        _ptr(noisy_out), C.c_void_p(base), C.c_void_p(base + 4 * B), _ptr(label_table), _ptr(labels),
+        C.c_void_p(base + 8 * B), B, L, noise.shape[1], int(mode), int(max_attempts), 1 if substitute else 0, _stream()),
+        "nrse_mix_batch_f32")
+    return clean_out, noisy_out, meta, labels   # (outputs of a custom op may not alias each other: `meta` is sliced outside)
+
+
+@_mix_batch_op.register_fake
+def _(clean, noise, snr_idx, snr_db, label_table, mode, max_attempts, substitute):
+    B = clean.shape[0]
+    return (torch.empty_like(clean) if mode == 1 else clean.new_empty(0), torch.empty_like(clean),
+            clean.new_empty(2 * B + 1, dtype=torch.int32), clean.new_empty(B, dtype=torch.int64))
+
+
+def mix_batch(clean: Tensor, noise: Tensor, snr_idx: Tensor, snr_db_table: Sequence[float], snr_label_table: Tensor,
+              peak_norm: bool = True, max_attempts: int = 5, substitute: bool = True):
+    """The attempt loop of ``NoiseRobustSpeechDataset.__getitem__`` (ref:src/data/noisy_speech_dataset.py:55-149) for a
+    whole batch in ONE host call and three launches: mix + normalise every row; redo the rejected rows inside one retry
+    launch with the noise and SNR draw of the following rows (up to ``max_attempts - 1`` further attempts each); then
+    substitute what is still rejected by the nearest following good row (``substitute``), gather the int64 ``snr`` labels
+    (``snr_label_table[index finally used]``, a device int64 table) and count the rows rejected for good.  No host
+    synchronisation.  Returns (clean | None, noisy, status [B] i32, snr_idx_used [B] i32, snr_labels [B] i64,
+    n_rejected [1] i32)."""
+    if clean.dim() != 2 or noise.dim() != 2 or clean.shape[0] != noise.shape[0]:
+        raise NrseError("mix_batch expects clean [B,L] and noise [B,Ln]")
+    if snr_label_table.dtype != torch.int64 or snr_label_table.numel() != len(snr_db_table):
+        raise NrseError("mix_batch: snr_label_table must be an int64 tensor with one entry per SNR table value")
+    clean = clean.contiguous().float()
+    noise = noise.contiguous().float()
+    snr_idx = snr_idx.to(device=clean.device, dtype=torch.int32).contiguous()
+    c, n, meta, labels = _mix_batch_op(clean, noise, snr_idx, [float(v) for v in snr_db_table],
+                                       snr_label_table.contiguous(), 1 if peak_norm else 0, int(max_attempts), bool(substitute))
+    B = clean.shape[0]
+    return (c if peak_norm else None), n, meta[:B], meta[B:2 * B], labels, meta[2 * B:]
+
+
 def mix_status_name(code: int) -> str:
     return _lib.load().nrse_mix_status_name(int(code)).decode()
 

@@ -199,6 +199,59 @@ def test_substitute_rows_replaces_permanently_bad_rows(dev, mix_variant):
     assert torch.equal(c[4], c0[0]) and torch.equal(n[4], n0[0]) and int(used[4]) == int(snr_idx[0])
 
 
+@pytest.mark.parametrize("L", [4000, 64000, 6001])
+@pytest.mark.parametrize("substitute", [True, False])
+def test_mix_batch_equals_launch_per_attempt(dev, mix_variant, L, substitute):
+    """nrse_mix_batch_f32 (three launches: mix, ONE retry launch that loops over the attempts inside the kernel, finish)
+    against the launch-per-attempt sequence it replaces (mix, 4 x retry with shifts 1..4, substitute, torch gather of the
+    labels, torch count): outputs, status, SNR indices, labels and the rejected-row count bit for bit.  The batch has rows
+    that recover at the first retry, a row that needs THREE retries (its next two donors are bad as well), rows that never
+    recover (silent clean crop) and, at L = 6001, takes the unaligned generic kernel."""
+    B = 9
+    clean, noise, snr_idx, table = synthetic.waveforms(B, L, seed=41)
+    snr_idx = (np.arange(B, dtype=np.int32) * 2) % len(table)
+    noise[2] = 0.0          # row 2: donors 3 (bad), 4 (bad), 5 (good): third retry
+    noise[3] = np.nan       # row 3: donors 4 (bad), 5 (good)
+    noise[4] = 0.0          # row 4: donor 5 (good)
+    clean[6] = 0.0          # never recovers -> substituted by row 7
+    clean[8] = 0.0          # last row: wraps around to row 0
+    cd, nd = torch.from_numpy(clean).to(dev), torch.from_numpy(noise).to(dev)
+    sd = torch.from_numpy(snr_idx).to(dev)
+    tab = [float(v) for v in table]
+    labels_tab = torch.tensor([int(round(v)) for v in tab], device=dev, dtype=torch.int64)
+    # reference sequence
+    c, n, st = ops.mix_normalize(cd, nd, sd, tab, True)
+    assert st.tolist() == [0, 0, 4, 2, 4, 0, 3, 0, 3]
+    used = sd.clone()
+    for attempt in range(1, 5):
+        ops.mix_normalize_retry_(cd, nd, sd, tab, c, n, st, attempt, True, used)
+    assert st.tolist() == [0, 0, 0, 0, 0, 0, 3, 0, 2]   # row 8's last donor is row 3 (NaN noise): rejected as noise_nan
+    assert used.cpu().tolist()[2:5] == [int(snr_idx[5])] * 3
+    if substitute:
+        ops.mix_substitute_rows_(c, n, st, used)
+    want_labels = labels_tab[used.long()]
+    # one call
+    c2, n2, st2, used2, labels2, cnt2 = ops.mix_batch(cd, nd, sd, tab, labels_tab, True, 5, substitute)
+    assert st2.tolist() == st.tolist() and used2.tolist() == used.tolist()
+    assert torch.equal(c2, c) and torch.equal(n2, n)
+    assert torch.equal(labels2, want_labels) and labels2.dtype == torch.int64
+    assert cnt2.tolist() == [2]
+    if substitute:
+        assert torch.equal(c2[6], c2[7]) and torch.equal(n2[8], n2[0]) and c2[6].any()
+    else:
+        assert not c2[6].any() and not n2[8].any()
+    # fewer attempts: row 2 (needs three retries) stays rejected with max_attempts = 3
+    _, _, st3, _, _, cnt3 = ops.mix_batch(cd, nd, sd, tab, labels_tab, True, 3, substitute)
+    assert st3.tolist() == [0, 0, 4, 0, 0, 0, 3, 0, 3] and cnt3.tolist() == [3]
+    # a healthy batch: same as the plain mix, nothing rejected
+    clean_h, noise_h, idx_h, _ = synthetic.waveforms(4, L, seed=42)
+    ch, nh, ih = (torch.from_numpy(a).to(dev) for a in (clean_h, noise_h, idx_h))
+    c4, n4, st4, used4, labels4, cnt4 = ops.mix_batch(ch, nh, ih, tab, labels_tab, True, 5, substitute)
+    c5, n5, st5 = ops.mix_normalize(ch, nh, ih, tab, True)
+    assert torch.equal(c4, c5) and torch.equal(n4, n5) and st4.tolist() == [0] * 4 == st5.tolist()
+    assert used4.tolist() == idx_h.tolist() and cnt4.tolist() == [0] and torch.equal(labels4, labels_tab[ih.long()])
+
+
 def test_full_size_vs_oracle(dev):
     """BASELINE shape 64 x 64000 directly against the CPU oracle, 1e-6 per row (north star: mixing fp32 within 1e-6)."""
     B, L = 64, 64000
