@@ -68,6 +68,8 @@ class ClockSampler:
         self.t_begin = None
 
     def start(self, wait_first_sample_s: float = 3.0):
+        if os.environ.get("NRSE_BENCH_NO_SAMPLER"):  # diagnosis only: does the sampler process perturb the launches?
+            return
         try:
             self.out = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
@@ -313,15 +315,24 @@ def main_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    debug = bool(os.environ.get("NRSE_BENCH_DEBUG"))
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        host = []
         e0.record()
         for _ in range(steps):
+            h0 = time.perf_counter()
             out = fn()
+            host.append(time.perf_counter() - h0)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        if debug and rank == 0:  # host enqueue time per step: a stalled launch queue shows up as one long step
+            top = sorted(range(steps), key=lambda i: -host[i])[:3]
+            print(f"[bench debug] {steps} steps, device {ms:.2f} ms, host enqueue sum {sum(host) * 1e3:.2f} ms, longest steps "
+                  + ", ".join(f"#{i}: {host[i] * 1e3:.2f} ms" for i in top), file=sys.stderr)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -334,8 +345,14 @@ def main_gpu(args):
     if rank == 0:
         sampler.start()  # up and sampling before the warm-up: its start-up must not perturb the timed region
     warmup = max(args.warmup, 3)
+    out = None
     for _ in range(warmup):
-        step_dev()
+        out = step_dev()  # the result is kept exactly as in the timed loop (the previous step's outputs are still alive while
+        # a step allocates), and dropped before the timed region starts: the caching allocator then owns every block the
+        # loop will ask for.  Without this the SECOND timed step was the first to need a third generation of output blocks
+        # and called cudaMalloc next to running kernels -- 0.8 ms at best, 30-115 ms in one of six runs, inside a 50 ms
+        # window (`NRSE_BENCH_DEBUG=1` prints the host time of the slowest steps; gpurun_out/r2x_*, r2w_*).
+    out = None
     sampler.mark_begin()
     ms_total, out = timed(step_dev, args.steps)
     clocks = sampler.stop() if rank == 0 else None
@@ -351,6 +368,7 @@ def main_gpu(args):
         if rank == 0:
             sus_sampler.start()
         sus_sampler.mark_begin()
+        out = None
         ms_sus, _ = timed(step_dev, n_sus)
         sus_clocks = sus_sampler.stop() if rank == 0 else None
         sustained = {"value": world * UTT_SEC_PER_STEP / (ms_sus / n_sus * 1e-3), "unit": UNIT, "steps": n_sus,
@@ -384,8 +402,10 @@ def main_gpu(args):
         n_e2e[0] += 1
         return y_o, y_t, st
 
+    out = None
     for _ in range(3):
-        step_e2e()
+        out = step_e2e()  # same liveness pattern as the timed loop (see the warm-up of `value`)
+    out = None
     ms_e2e_total, _ = timed(step_e2e, args.steps)
     e2e_value = world * UTT_SEC_PER_STEP / (ms_e2e_total / args.steps * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in raw_h.values())

@@ -180,28 +180,58 @@ class GpuBatchMixer:
         self.max_attempts = max_attempts
         self.bad_rows = bad_rows
         self.rejected_rows = 0          # rows that stayed bad after all attempts, as far as already observed
-        self._pending = []              # [(pinned count tensor, event)] of batches not yet looked at
-        self._free = []                 # pinned counters / events to reuse (cudaHostAlloc per batch would cost ~100 us)
+        # rejected-row counts travel through a fixed ring of pinned int32 slots allocated ONCE (cudaHostAlloc inside a
+        # training loop stalls the launch queue for milliseconds): slot i of batches [tail, head) is in flight
+        self._ring = None               # pinned int32 [RING]
+        self._ring_events = None
+        self._ring_srcs = None          # the device counters, referenced until their copy has been seen
+        self._head = self._tail = 0
+        self._side = None               # stream of the count read-back: keeps the D2H copy off the step's critical path
+        self._produced = None
         self._snr_labels = None
+
+    RING = 64  # batches whose count may be in flight; a host that runs further ahead than this waits for the oldest one
 
     @property
     def drop_bad_rows(self) -> bool:
         return self.bad_rows == "drop"
 
     def _poll(self, block: bool = False) -> None:
-        keep = []
-        for cnt, ev in self._pending:
+        """Look at the counts that have arrived (in order; ``block``: wait for all outstanding ones)."""
+        while self._tail < self._head:
+            i = self._tail % self.RING
+            ev = self._ring_events[i]
             if block:
                 ev.synchronize()
-            if ev.query():
-                n = int(cnt.item())
-                if n:
-                    self.rejected_rows += n
-                    logger.error("%d row(s) failed all %d mix attempts (policy: %s)", n, self.max_attempts, self.bad_rows)
-                self._free.append((cnt, ev))
-            else:
-                keep.append((cnt, ev))
-        self._pending = keep
+            elif not ev.query():
+                break
+            n = int(self._ring[i])
+            if n:
+                self.rejected_rows += n
+                logger.error("%d row(s) failed all %d mix attempts (policy: %s)", n, self.max_attempts, self.bad_rows)
+            self._ring_srcs[i] = None  # releases the device counter to the allocator
+            self._tail += 1
+
+    def _read_back(self, src: torch.Tensor) -> None:
+        """Queue the asynchronous copy of a device int32 [1] count into the next ring slot, on the side stream."""
+        if self._ring is None:
+            self._ring = torch.zeros(self.RING, dtype=torch.int32).pin_memory()
+            self._ring_events = [torch.cuda.Event() for _ in range(self.RING)]
+            self._ring_srcs = [None] * self.RING
+            self._side, self._produced = torch.cuda.Stream(device=self.device), torch.cuda.Event()
+        if self._head - self._tail == self.RING:   # ring full: the oldest copy was queued 64 batches ago
+            self._ring_events[self._tail % self.RING].synchronize()
+            self._poll()
+        i = self._head % self.RING
+        # on the compute stream the 4-byte copy sat between the mix and the first frontend kernel (~12 us per step of
+        # copy-engine latency); `src` stays referenced until the copy has been seen
+        self._produced.record()
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._produced)
+            self._ring[i:i + 1].copy_(src, non_blocking=True)
+            self._ring_events[i].record()
+        self._ring_srcs[i] = src
+        self._head += 1
 
     def flush(self) -> int:
         """Wait for the outstanding status counts (end of an epoch); returns the total number of rejected rows."""
@@ -237,10 +267,7 @@ class GpuBatchMixer:
                 self.rejected_rows += int(bad.sum())
                 c, n, snr, status = (c[keep] if c is not None else None), n[keep], snr[keep], status[keep]
         elif self.peak_norm:
-            cnt, ev = self._free.pop() if self._free else (torch.empty(1, dtype=torch.int32).pin_memory(), torch.cuda.Event())
-            cnt.copy_(n_bad if n_bad is not None else (status != 0).sum().reshape(1).to(torch.int32), non_blocking=True)
-            ev.record()
-            self._pending.append((cnt, ev))
+            self._read_back(n_bad if n_bad is not None else (status != 0).sum().reshape(1).to(torch.int32))
         out = {"noisy_input_values": n.unsqueeze(1), "snr": snr, "mix_status": status}
         if self.peak_norm:
             out["clean_input_values"] = c.unsqueeze(1)
