@@ -662,7 +662,7 @@ def kernel_rooflines(ops, dev, peaks, clean_d, noise_d, snr_d, snr_list, conv_w,
     sus_achieved = gemm_flops / (sus_ms * 1e-3) / 1e12
     del seq_graph, seq_acts
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1c_ncu_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2z_ncu_traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of the six launches, from the ncu capture
         with open(tpath) as f:
             tj = json.load(f)
