@@ -127,7 +127,8 @@ int nrse_mix_substitute_rows_f32(float* clean_out, float* noisy_out, const int32
 /* The whole attempt loop of NoiseRobustSpeechDataset.__getitem__ (ref:src/data/noisy_speech_dataset.py:55-149) for a batch,
  * in one host call and THREE launches whatever max_attempts is:
  *   1. nrse_mix_normalize_f32 on every row, recording the SNR index used in snr_idx_used [B] (required);
- *   2. (max_attempts > 1, B > 1) one retry launch: a row that was rejected is redone INSIDE the launch with the noise
+ *   2. (max_attempts > 1, B > 1, peak_norm = 1 -- the emotion path never retries, ref:src/data/emotion_dataset.py:190-194)
+ *      one retry launch: a row that was rejected is redone INSIDE the launch with the noise
  *      and SNR draw of rows b + 1, b + 2, ... (mod B) until it passes or max_attempts - 1 further attempts are used up --
  *      the same donors, in the same order, as max_attempts - 1 calls of nrse_mix_normalize_retry_f32 with
  *      noise_row_shift = 1, 2, ...; the CTAs of good rows exit at once;

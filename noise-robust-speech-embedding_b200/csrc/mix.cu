@@ -1029,13 +1029,16 @@ int nrse_mix_batch_f32(const float* clean, const float* noise, const int32_t* sn
   int rc = mix_normalize_impl(clean, noise, snr_idx, snr_db_table_host, n_snr, clean_out, noisy_out, status, snr_idx_used, B,
                               L, L_noise, peak_norm, 0, 0, 1, stream);
   if (rc != NRSE_OK) return rc;
-  if (max_attempts > 1 && B > 1) {  // attempts 2..max_attempts: ONE launch, rows still rejected loop inside it
+  // attempts 2..max_attempts: ONE launch, rows still rejected loop inside it.  BYOL mode only: the emotion path never
+  // retries, a failed mix keeps the clean waveform (ref:src/data/emotion_dataset.py:190-194)
+  if (max_attempts > 1 && B > 1 && peak_norm == 1) {
     rc = mix_normalize_impl(clean, noise, snr_idx, snr_db_table_host, n_snr, clean_out, noisy_out, status, snr_idx_used, B, L,
                             L_noise, peak_norm, 1, 1, max_attempts - 1, stream);
     if (rc != NRSE_OK) return rc;
   }
+  // (emotion mode: a row whose mix was rejected carries the normalised CLEAN waveform -- a valid item, never substituted)
   return mix_finish_impl(peak_norm == 1 ? clean_out : nullptr, noisy_out, status, snr_idx_used, snr_label_table,
-                         snr_labels_out, n_rejected, substitute_bad_rows, B, L, stream);
+                         snr_labels_out, n_rejected, peak_norm == 1 ? substitute_bad_rows : 0, B, L, stream);
 }
 
 }  // extern "C"

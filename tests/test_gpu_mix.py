@@ -252,6 +252,22 @@ def test_mix_batch_equals_launch_per_attempt(dev, mix_variant, L, substitute):
     assert used4.tolist() == idx_h.tolist() and cnt4.tolist() == [0] and torch.equal(labels4, labels_tab[ih.long()])
 
 
+def test_mix_batch_emotion_mode_never_retries(dev, mix_variant):
+    """peak_norm = False (ref:src/data/emotion_dataset.py:177-203): a failed mix keeps the clean waveform and is NOT retried
+    with another noise crop; mix_batch equals the plain launch whatever max_attempts says, the count reports the rows."""
+    B, L = 5, 8000
+    clean, noise, snr_idx, table = synthetic.waveforms(B, L, seed=51)
+    noise[1] = 0.0
+    noise[3] = np.nan
+    cd, nd, sd = (torch.from_numpy(a).to(dev) for a in (clean, noise, snr_idx))
+    tab = [float(v) for v in table]
+    labels_tab = torch.tensor([int(round(v)) for v in tab], device=dev, dtype=torch.int64)
+    _, n_ref, st_ref = ops.mix_normalize(cd, nd, sd, tab, False)
+    c, n, st, used, labels, cnt = ops.mix_batch(cd, nd, sd, tab, labels_tab, False, 5, True)
+    assert c is None and torch.equal(n, n_ref) and st.tolist() == st_ref.tolist() == [0, 4, 0, 2, 0]
+    assert used.tolist() == snr_idx.tolist() and cnt.tolist() == [2] and torch.equal(labels, labels_tab[sd.long()])
+
+
 def test_full_size_vs_oracle(dev):
     """BASELINE shape 64 x 64000 directly against the CPU oracle, 1e-6 per row (north star: mixing fp32 within 1e-6)."""
     B, L = 64, 64000
