@@ -381,8 +381,10 @@ __device__ __forceinline__ float absmax_nan(float m, float x) {
 // Scalars every thread needs after a phase; computed once by thread 0 (fp64 divisions are ~40 instructions each)
 struct MixScalars {
   float scale, inv_dc, inv_dn, a_c, b_c, a_n, b_n;
-  int st1;  // verdict of add_noise_to_speech (after pass 1)
-  int st;   // final verdict
+  int st1;        // verdict of add_noise_to_speech (after pass 1)
+  int st;         // final verdict
+  int clean_ok;   // the clean view passes its own peak / z-norm checks (it may be written before the mixed peak is known)
+  int clean_nan;  // mean / variance of the peak-normalised clean view is not finite (status 13 if nothing earlier applies)
 };
 
 
@@ -577,10 +579,33 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
       }
     }
   }
-  if (tid == 0) ptx::mbar_wait(xbar1, ph);
+  // Two threads wait for the first exchange: thread 0 derives the mix scale (what pass 2 waits for), lane 0 of warp 1 the
+  // scalars of the CLEAN view -- they depend on nothing but the clean sums and peak, so the clean view can leave for HBM while
+  // pass 2, the second exchange and the noisy view's scalars (~2.5 us of latency chain per row) are still under way.
+  constexpr int kCleanTid = 32;
+  if (tid == 0 || (p.peak_norm && tid == kCleanTid)) ptx::mbar_wait(xbar1, ph);
 
   double s_cc = 0.0, s_nn = 0.0, s_c1 = 0.0, s_n1 = 0.0, s_cn = 0.0;
   const double inv_L = 1.0 / static_cast<double>(L);
+  if (p.peak_norm && tid == kCleanTid) {
+    double q_cc = 0.0, q_c1 = 0.0;
+    float pk_c = 0.f;
+    for (int r = 0; r < cs; ++r) {
+      q_cc += xch1_d[r][0];
+      q_c1 += xch1_d[r][2];
+      pk_c = fmaxf(pk_c, reinterpret_cast<const float2*>(&xch1_d[r][5])->x);
+    }
+    const double rdc = 1.0 / static_cast<double>(__fadd_rn(pk_c, 1e-8f));
+    const double mc = q_c1 * inv_L * rdc;
+    const double vc = q_cc * inv_L * rdc * rdc - mc * mc;
+    const float vcf = static_cast<float>(vc), mcf = static_cast<float>(mc);
+    const bool bad = !isfinite(mcf) || !isfinite(vcf);
+    sc.inv_dc = static_cast<float>(rdc);
+    sc.a_c = mcf;
+    sc.b_c = 1.0f / __fsqrt_rn(__fadd_rn(vcf, 1e-7f));  // np.sqrt(x.var() + 1e-7) in float32
+    sc.clean_nan = bad ? 1 : 0;
+    sc.clean_ok = (!bad && !(pk_c < 1e-8f) && !isinf(pk_c)) ? 1 : 0;
+  }
   if (tid == 0) {
     cmax = 0.f;
     nmax_in = 0.f;
@@ -616,6 +641,25 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
   const int st1 = sc.st1;
   const bool mixed = st1 == 0;
   const f2 s2 = f2_make(scale, scale);
+
+  // ---- clean view out (BYOL mode), ahead of pass 2.  If a later check rejects the row after all, pass 3 overwrites it with
+  // zeros: same thread, same addresses, program order.
+  float4* co = p.clean_out ? reinterpret_cast<float4*>(p.clean_out + static_cast<size_t>(row) * L) + v_begin : nullptr;
+  if (p.peak_norm && mixed && sc.clean_ok) {
+    const f2 nac2 = f2_make(-sc.a_c, -sc.a_c), bc2 = f2_make(sc.b_c, sc.b_c), idc2 = f2_make(sc.inv_dc, sc.inv_dc);
+    auto emit_clean = [&](int v, const float4& cv) {
+      float4 oc;
+      f2_split(f2_mul(f2_add(f2_mul(f2_make(cv.x, cv.y), idc2), nac2), bc2), oc.x, oc.y);  // (c/dc - mean) / std, 3 roundings
+      f2_split(f2_mul(f2_add(f2_mul(f2_make(cv.z, cv.w), idc2), nac2), bc2), oc.z, oc.w);
+      st_stream_cs_f4(co + v, oc);
+    };
+#pragma unroll
+    for (int u = 0; u < kResRegVec; ++u) {
+      const int v = u * kResThreads + tid;
+      if (v < n_reg) emit_clean(v, rc[u]);
+    }
+    for (int v = tid; v < n_sm; v += kResThreads) emit_clean(n_reg + v, s_c[v]);
+  }
 
   // ---- pass 2 (on chip): y = c + s*n replaces n; peak of the mixed signal (BYOL mode) ----------------------------
   float nmax = 0.f;
@@ -661,7 +705,7 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
   if (tid == 0) {
     int st = st1;
     const double s = static_cast<double>(scale);
-    float a_c = 0.f, b_c = 0.f, a_n = 0.f, b_n = 0.f, inv_dc = 1.f, inv_dn = 1.f;
+    float a_n = 0.f, b_n = 0.f, inv_dn = 1.f;
     if (p.peak_norm) {
       if (st == 0) {
         nmax = xch2_f[0];
@@ -672,21 +716,14 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
         else if (isinf(cmax)) st = 11;
         else if (isinf(nmax)) st = 12;
       }
-      if (st == 0) {
-        const double rdc = 1.0 / static_cast<double>(__fadd_rn(cmax, 1e-8f));
+      if (st == 0) {  // (the clean view's scalars are in `sc` already: kCleanTid, after the first exchange)
         const double rdn = 1.0 / static_cast<double>(__fadd_rn(nmax, 1e-8f));
-        const double mc = s_c1 * inv_L * rdc;
-        const double vc = s_cc * inv_L * rdc * rdc - mc * mc;
         const double mn = (s_c1 + s * s_n1) * inv_L * rdn;
         const double vn = (s_cc + 2.0 * s * s_cn + s * s * s_nn) * inv_L * rdn * rdn - mn * mn;
-        const float vcf = static_cast<float>(vc), vnf = static_cast<float>(vn);
-        const float mcf = static_cast<float>(mc), mnf = static_cast<float>(mn);
-        if (!isfinite(mcf) || !isfinite(vcf)) st = 13;
+        const float vnf = static_cast<float>(vn), mnf = static_cast<float>(mn);
+        if (sc.clean_nan) st = 13;
         else if (!isfinite(mnf) || !isfinite(vnf)) st = 14;
-        inv_dc = static_cast<float>(rdc);
         inv_dn = static_cast<float>(rdn);
-        a_c = mcf;
-        b_c = 1.0f / __fsqrt_rn(__fadd_rn(vcf, 1e-7f));
         a_n = mnf;
         b_n = 1.0f / __fsqrt_rn(__fadd_rn(vnf, 1e-7f));
       }
@@ -702,16 +739,15 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
         b_n = 1.f;
       }
     }
-    sc.inv_dc = inv_dc; sc.inv_dn = inv_dn;
-    sc.a_c = a_c; sc.b_c = b_c; sc.a_n = a_n; sc.b_n = b_n;
+    sc.inv_dn = inv_dn;
+    sc.a_n = a_n; sc.b_n = b_n;
     sc.st = st;
     if (rank == 0) p.status[row] = st;
   }
   __syncthreads();
   const int st = sc.st;
 
-  // ---- pass 3 (on chip -> HBM) ---------------------------------------------------------------------------------------
-  float4* co = p.clean_out ? reinterpret_cast<float4*>(p.clean_out + static_cast<size_t>(row) * L) + v_begin : nullptr;
+  // ---- pass 3 (on chip -> HBM): the noisy view (the clean one left before pass 2) -----------------------------------------
   float4* no = reinterpret_cast<float4*>(p.noisy_out + static_cast<size_t>(row) * L) + v_begin;
   if (p.peak_norm && st != 0) {
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -722,20 +758,15 @@ mix_normalize_resident_kernel(const MixParams p, int seg_vec, int smem_pitch) {
     if (kRetry) __syncthreads();
     continue;  // next attempt, if this launch makes one
   }
-  const f2 nac2 = f2_make(-sc.a_c, -sc.a_c), bc2 = f2_make(sc.b_c, sc.b_c), idc2 = f2_make(sc.inv_dc, sc.inv_dc);
   const f2 nan2 = f2_make(-sc.a_n, -sc.a_n), bn2 = f2_make(sc.b_n, sc.b_n), idn2 = f2_make(sc.inv_dn, sc.inv_dn);
   auto emit = [&](int v, const float4& cv, const float4& yv) {
-    const f2 c01 = f2_make(cv.x, cv.y), c23 = f2_make(cv.z, cv.w);
     f2 y01 = f2_make(yv.x, yv.y), y23 = f2_make(yv.z, yv.w);
     float4 on;
-    if (p.peak_norm) {  // the noise slot already holds the mixed signal
-      float4 oc;
-      f2_split(f2_mul(f2_add(f2_mul(c01, idc2), nac2), bc2), oc.x, oc.y);  // (c/dc - mean) / std, 3 roundings
-      f2_split(f2_mul(f2_add(f2_mul(c23, idc2), nac2), bc2), oc.z, oc.w);
+    if (p.peak_norm) {  // the noise slot already holds the mixed signal: (y/dn - mean) / std, 3 roundings
       f2_split(f2_mul(f2_add(f2_mul(y01, idn2), nan2), bn2), on.x, on.y);
       f2_split(f2_mul(f2_add(f2_mul(y23, idn2), nan2), bn2), on.z, on.w);
-      st_stream_cs_f4(co + v, oc);
     } else {
+      const f2 c01 = f2_make(cv.x, cv.y), c23 = f2_make(cv.z, cv.w);
       if (mixed) {
         y01 = f2_add(c01, f2_mul(y01, s2));
         y23 = f2_add(c23, f2_mul(y23, s2));
