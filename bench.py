@@ -317,7 +317,7 @@ def main_gpu(args):
 
     debug = bool(os.environ.get("NRSE_BENCH_DEBUG"))
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         host = []
@@ -326,6 +326,8 @@ def main_gpu(args):
             h0 = time.perf_counter()
             out = fn()
             host.append(time.perf_counter() - h0)
+        if finish is not None:
+            finish()  # work the loop left on other streams joins the timing stream before the closing event
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -381,6 +383,9 @@ def main_gpu(args):
     prefetch.put(raw_h)  # pipeline prologue: the first batch is in flight before step 0
 
     done = [torch.cuda.Event(), torch.cuda.Event()]
+    produced = [torch.cuda.Event(), torch.cuda.Event()]
+    d2h_stream = torch.cuda.Stream(device=dev)
+    keep = [None, None]  # device sources of the result copies in flight (allocated on the compute stream, read on d2h_stream)
     n_e2e = [0]
 
     def step_e2e():
@@ -391,10 +396,18 @@ def main_gpu(args):
         b = prefetch.get()
         y_o, y_t, st = hot_path(b)
         k = n_e2e[0] & 1
-        pooled_h[k, 0].copy_(y_o.mean(dim=2), non_blocking=True)  # the [B,H]-pooled result the BYOL heads consume
-        pooled_h[k, 1].copy_(y_t.mean(dim=2), non_blocking=True)
-        status_h[k].copy_(st, non_blocking=True)
-        done[k].record()
+        po, pt = y_o.mean(dim=2), y_t.mean(dim=2)  # the [B,H]-pooled result the BYOL heads consume
+        # the three small D2H copies run on their own stream behind an event: queued on the compute stream they sat between
+        # this step's last kernel and the next step's first one (~14 us of copy-engine latency each).  Slot k's sources were
+        # last read two steps ago, and that copy was waited for in the previous step, so `keep[k]` may be replaced.
+        produced[k].record()
+        keep[k] = (po, pt, st)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(produced[k])
+            pooled_h[k, 0].copy_(po, non_blocking=True)
+            pooled_h[k, 1].copy_(pt, non_blocking=True)
+            status_h[k].copy_(st, non_blocking=True)
+            done[k].record()
         prefetch.release()
         prefetch.put(raw_h)
         if n_e2e[0] > 0:
@@ -406,7 +419,9 @@ def main_gpu(args):
     for _ in range(3):
         out = step_e2e()  # same liveness pattern as the timed loop (see the warm-up of `value`)
     out = None
-    ms_e2e_total, _ = timed(step_e2e, args.steps)
+    # the last step's result copies are inside the timed region: the compute stream waits for them before the closing event
+    ms_e2e_total, _ = timed(step_e2e, args.steps,
+                            finish=lambda: torch.cuda.current_stream().wait_event(done[(n_e2e[0] - 1) & 1]))
     e2e_value = world * UTT_SEC_PER_STEP / (ms_e2e_total / args.steps * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in raw_h.values())
     d2h = (pooled_h.numel() * 4 + status_h.numel() * 4) // 2
@@ -423,8 +438,9 @@ def main_gpu(args):
                 "how": "pinned host batch of RAW waveforms -> DevicePrefetcher (copy stream, depth 2: the H2D copy of step "
                        "i+1 overlaps the kernels of step i) -> GpuBatchMixer (mix + device-side retries + substitute) -> "
                        "B200FeatureEncoder.forward on both views (the module calls of INTEGRATION.md level 1, eager, no CUDA "
-                       "graph) -> D2H of the pooled [2,B,512] features + status every step; the host waits for the PREVIOUS "
-                       "step's result after queueing the current one (one-step lag, as for loss.item() in a training loop)"},
+                       "graph) -> D2H of the pooled [2,B,512] features + status every step (copy stream behind an event; "
+                       "the last step's copies complete inside the timed region); the host waits for the PREVIOUS step's "
+                       "result after queueing the current one (one-step lag, as for loss.item() in a training loop)"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
     }
