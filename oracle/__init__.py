@@ -23,6 +23,7 @@ from .mix import (  # noqa: F401
     STATUS_OK,
     STATUS_NAMES,
     add_noise_to_speech,
+    mix_batch_attempts,
     mix_normalize_batch,
     mix_normalize_item,
     peak_normalize_pair,

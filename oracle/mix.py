@@ -156,3 +156,51 @@ def mix_normalize_batch(clean, noise, snr_idx, snr_table, peak_norm: bool = True
         if n is not None:
             noisy_out[b] = n[0]
     return clean_out, noisy_out, status
+
+
+def mix_batch_attempts(clean, noise, snr_idx, snr_table, max_attempts: int = 5, substitute: bool = True):
+    """The attempt loop of ``NoiseRobustSpeechDataset.__getitem__`` (ref:src/data/noisy_speech_dataset.py:55-149) for a
+    batch, with the reference's random re-draws replaced by EXPLICIT donors so that it can be compared bit for bit:
+
+    * ``for attempt in range(max_attempts)`` (:58): attempt a of row b mixes clean[b] with the noise crop AND the SNR
+      draw of row ``(b + a) % B`` -- attempt 0 is the row's own draw; every later attempt "loads another random noise"
+      (:69-70) and "selects a random SNR" (:78) again, here the following rows' draws;
+    * the first attempt that passes every check (:81-138) is the item (:140-144); ``snr`` is the table value it was
+      mixed at;
+    * a row that fails all attempts is not emitted by the reference (:146-149 raises after moving on, :60-66); with
+      ``substitute`` it takes the outputs and the SNR of the nearest following row that passed, otherwise it stays
+      zero-filled with its last status.
+
+    A single-row batch has no donors: one attempt.  Returns (clean_out [B,L], noisy_out [B,L], status [B] int32 -- 0 or
+    the last attempt's exit --, snr_idx_used [B] int32, n_rejected).
+    """
+    clean = torch.as_tensor(clean, dtype=torch.float32)
+    noise = torch.as_tensor(noise, dtype=torch.float32)
+    snr_idx = np.asarray(snr_idx, dtype=np.int32)
+    B, L = clean.shape
+    clean_out, noisy_out = torch.zeros(B, L), torch.zeros(B, L)
+    status = torch.zeros(B, dtype=torch.int32)
+    used = snr_idx.copy()
+    for b in range(B):
+        for attempt in range(max_attempts if B > 1 else 1):                       # :58
+            donor = (b + attempt) % B
+            snr_db = snr_table[int(snr_idx[donor])]
+            snr_db = snr_db.item() if hasattr(snr_db, "item") else snr_db
+            c, n, st = mix_normalize_item(clean[b:b + 1], noise[donor:donor + 1], snr_db, True)
+            status[b], used[b] = st, snr_idx[donor]
+            if st == STATUS_OK:                                                   # :140-144
+                clean_out[b], noisy_out[b] = c[0], n[0]
+                break
+    good = [int(status[b]) == STATUS_OK for b in range(B)]
+    n_rejected = B - sum(good)
+    if substitute and B > 1:
+        src_c, src_n, src_used = clean_out.clone(), noisy_out.clone(), used.copy()
+        for b in range(B):
+            if good[b]:
+                continue
+            for d in range(1, B):                                                 # "move on to the next item", :60-66
+                r = (b + d) % B
+                if good[r]:
+                    clean_out[b], noisy_out[b], used[b] = src_c[r], src_n[r], src_used[r]
+                    break
+    return clean_out, noisy_out, status, used, n_rejected

@@ -252,6 +252,34 @@ def test_mix_batch_equals_launch_per_attempt(dev, mix_variant, L, substitute):
     assert used4.tolist() == idx_h.tolist() and cnt4.tolist() == [0] and torch.equal(labels4, labels_tab[ih.long()])
 
 
+@pytest.mark.parametrize("max_attempts,substitute", [(5, True), (5, False), (3, True), (1, True)])
+def test_mix_batch_vs_oracle_attempt_loop(dev, mix_variant, max_attempts, substitute):
+    """nrse_mix_batch_f32 against the oracle's restatement of the reference's attempt loop
+    (ref:src/data/noisy_speech_dataset.py:55-149 with explicit donors, ``oracle.mix_batch_attempts``): waveforms within 1e-6
+    per row, statuses, SNR indices, labels and the rejected-row count exactly."""
+    B, L = 9, 16000
+    clean, noise, snr_idx, table = synthetic.waveforms(B, L, seed=43)
+    snr_idx = (np.arange(B, dtype=np.int32) * 3 + 1) % len(table)
+    noise[2] = 0.0
+    noise[3] = np.nan
+    noise[4] = 0.0
+    clean[6] = 0.0
+    clean[8, ::2] = np.inf      # speech power inf: scale invalid whatever the noise
+    c_ref, n_ref, st_ref, used_ref, rejected = oracle.mix_batch_attempts(clean, noise, snr_idx, table, max_attempts, substitute)
+    cd, nd, sd = (torch.from_numpy(a).to(dev) for a in (clean, noise, snr_idx))
+    tab = [float(v) for v in table]
+    labels_tab = torch.tensor([int(round(v)) for v in tab], device=dev, dtype=torch.int64)
+    c, n, st, used, labels, cnt = ops.mix_batch(cd, nd, sd, tab, labels_tab, True, max_attempts, substitute)
+    assert st.tolist() == st_ref.tolist()
+    assert used.tolist() == used_ref.tolist() and labels.tolist() == [int(round(tab[i])) for i in used_ref]
+    assert cnt.tolist() == [rejected]
+    for b in range(B):
+        if not n_ref[b].any():
+            assert not n[b].any() and not c[b].any(), b
+        else:
+            assert rel_err(n[b].cpu().numpy(), n_ref[b].numpy()) < TOL and rel_err(c[b].cpu().numpy(), c_ref[b].numpy()) < TOL, b
+
+
 def test_mix_batch_emotion_mode_never_retries(dev, mix_variant):
     """peak_norm = False (ref:src/data/emotion_dataset.py:177-203): a failed mix keeps the clean waveform and is NOT retried
     with another noise crop; mix_batch equals the plain launch whatever max_attempts says, the count reports the rows."""

@@ -238,3 +238,31 @@ def test_feature_projection_fixture_matches_installed_transformers(golden):
     out = model(torch.from_numpy(g["x"]))
     assert rel_err(out.last_hidden_state.detach().numpy(), g["last_hidden"]) < 1e-5
     assert rel_err(out.extract_features.detach().numpy(), g["norm"]) < 1e-5
+
+
+def test_mix_batch_attempts_restates_the_attempt_loop():
+    """``oracle.mix_batch_attempts`` (ref:src/data/noisy_speech_dataset.py:55-149 with explicit donors): a healthy batch is the
+    plain per-row chain; a row whose noise crop is unusable takes the next usable donor's noise AND SNR draw; a row whose
+    clean crop is silent never recovers and is substituted by the nearest following good row (or stays zero-filled)."""
+    import numpy as np
+    import torch
+
+    import oracle
+    from nrse_b200.utils import synthetic
+    B, L = 6, 2000
+    clean, noise, snr_idx, table = synthetic.waveforms(B, L, seed=7)
+    c0, n0, st0 = oracle.mix_normalize_batch(clean, noise, snr_idx, table)
+    c, n, st, used, rejected = oracle.mix_batch_attempts(clean, noise, snr_idx, table)
+    assert torch.equal(c, c0) and torch.equal(n, n0) and st.tolist() == st0.tolist() == [0] * B
+    assert used.tolist() == snr_idx.tolist() and rejected == 0
+    noise[1] = 0.0          # rows 1 and 2 have unusable noise: row 1 needs two retries (donors 2, 3), row 2 one (donor 3)
+    noise[2] = np.nan
+    clean[5] = 0.0          # silent clean crop: never recovers; last row wraps around to row 0
+    c, n, st, used, rejected = oracle.mix_batch_attempts(clean, noise, snr_idx, table)
+    assert st.tolist() == [0, 0, 0, 0, 0, 3] and rejected == 1
+    for b in (1, 2):
+        cr, nr, sr = oracle.mix_normalize_batch(clean[b:b + 1], noise[3:4], snr_idx[3:4], table)
+        assert sr.tolist() == [0] and torch.equal(n[b], nr[0]) and torch.equal(c[b], cr[0]) and used[b] == snr_idx[3]
+    assert torch.equal(c[5], c[0]) and torch.equal(n[5], n[0]) and used[5] == snr_idx[0]
+    c2, n2, st2, _, rejected2 = oracle.mix_batch_attempts(clean, noise, snr_idx, table, max_attempts=2, substitute=False)
+    assert st2.tolist() == [0, 2, 0, 0, 0, 3] and rejected2 == 2 and not c2[1].any() and not n2[5].any()
